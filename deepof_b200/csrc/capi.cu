@@ -1,0 +1,60 @@
+// C-ABI dispatch for the convolution family: picks the SIMT fp32 kernels (igemm_simt.cu) or the
+// tcgen05 TF32 kernels (conv_tc.cu) according to `math`.  See include/deepof_b200.h.
+#include "common.cuh"
+
+namespace dofb {
+int simt_conv_fwd(const dofb_conv_geom *g, const float *x, int x_ld, const float *w, const float *bias, float *y, int y_ld,
+                  int act, cudaStream_t st);
+int simt_conv_dgrad(const dofb_conv_geom *g, const float *dy, int dy_ld, const float *w, const float *bias, float *dx, int dx_ld,
+                    int act, int accumulate, cudaStream_t st);
+int simt_conv_wgrad(const dofb_conv_geom *g, const float *x, int x_ld, const float *dy, int dy_ld, float *dw, cudaStream_t st);
+int launch_colsum(const float *X, int ld, long long n_pix, int c, float *out, cudaStream_t st);
+// tcgen05 path (conv_tc.cu); returns -1 when the shape is not covered so that the caller can
+// decide (the C ABI reports an error: there is no silent fallback between math modes).
+int tc_conv_fwd(const dofb_conv_geom *g, const float *x, int x_ld, const float *w, const float *bias, float *y, int y_ld,
+                int act, cudaStream_t st);
+int tc_conv_dgrad(const dofb_conv_geom *g, const float *dy, int dy_ld, const float *w, const float *bias, float *dx, int dx_ld,
+                  int act, int accumulate, cudaStream_t st);
+int tc_conv_wgrad(const dofb_conv_geom *g, const float *x, int x_ld, const float *dy, int dy_ld, float *dw, cudaStream_t st);
+}  // namespace dofb
+
+using namespace dofb;
+
+extern "C" int dofb_conv_fwd(const dofb_conv_geom *g, const float *x, int x_ld, const float *w, const float *bias, float *y,
+                             int y_ld, int act, int math, void *stream) {
+    DOFB_CHECK_ARG(x && w && y, "dofb_conv_fwd: null tensor");
+    if (math == DOFB_MATH_TF32) return tc_conv_fwd(g, x, x_ld, w, bias, y, y_ld, act, as_stream(stream));
+    DOFB_CHECK_ARG(math == DOFB_MATH_FP32, "dofb_conv_fwd: unknown math mode %d", math);
+    return simt_conv_fwd(g, x, x_ld, w, bias, y, y_ld, act, as_stream(stream));
+}
+
+extern "C" int dofb_conv_dgrad(const dofb_conv_geom *g, const float *dy, int dy_ld, const float *w, const float *bias, float *dx,
+                               int dx_ld, int act, int accumulate, int math, void *stream) {
+    DOFB_CHECK_ARG(dy && w && dx, "dofb_conv_dgrad: null tensor");
+    if (math == DOFB_MATH_TF32) return tc_conv_dgrad(g, dy, dy_ld, w, bias, dx, dx_ld, act, accumulate, as_stream(stream));
+    DOFB_CHECK_ARG(math == DOFB_MATH_FP32, "dofb_conv_dgrad: unknown math mode %d", math);
+    return simt_conv_dgrad(g, dy, dy_ld, w, bias, dx, dx_ld, act, accumulate, as_stream(stream));
+}
+
+extern "C" int dofb_conv_wgrad(const dofb_conv_geom *g, const float *x, int x_ld, const float *dy, int dy_ld, float *dw, float *db,
+                               int math, void *stream) {
+    DOFB_CHECK_ARG(x && dy && dw && g, "dofb_conv_wgrad: null argument");
+    int rc;
+    if (math == DOFB_MATH_TF32) rc = tc_conv_wgrad(g, x, x_ld, dy, dy_ld, dw, as_stream(stream));
+    else {
+        DOFB_CHECK_ARG(math == DOFB_MATH_FP32, "dofb_conv_wgrad: unknown math mode %d", math);
+        rc = simt_conv_wgrad(g, x, x_ld, dy, dy_ld, dw, as_stream(stream));
+    }
+    if (rc) return rc;
+    if (db) return launch_colsum(dy, dy_ld, (long long)g->B * g->oh * g->ow, g->co, db, as_stream(stream));
+    return 0;
+}
+
+extern "C" int dofb_conv_wgrad_tbias(const dofb_conv_geom *g, const float *x, int x_ld, const float *dy, int dy_ld, float *dw,
+                                     float *db_large, int math, void *stream) {
+    DOFB_CHECK_ARG(x && dy && dw && g, "dofb_conv_wgrad_tbias: null argument");
+    int rc = dofb_conv_wgrad(g, x, x_ld, dy, dy_ld, dw, nullptr, math, stream);
+    if (rc) return rc;
+    if (db_large) return launch_colsum(x, x_ld, (long long)g->B * g->ih * g->iw, g->ci, db_large, as_stream(stream));
+    return 0;
+}

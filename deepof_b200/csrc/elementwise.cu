@@ -1,0 +1,217 @@
+// Bandwidth-bound element-wise kernels: pre-processing + pyramid, ELU backward, TF-form Adam,
+// end-point-error.  All fp32, float4 where the layout allows, grid sized from the SM count.
+#include "common.cuh"
+
+namespace dofb {
+
+// ---- library state -------------------------------------------------------------
+std::atomic<long long> g_launches{0};
+static thread_local char t_err[512] = "";
+char *err_buf() { return t_err; }
+int set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_err, sizeof(t_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+    }
+    return n;
+}
+
+// ---- pre-processing + pyramid ------------------------------------------------------
+// flyingChairsWrapFlow.py:16-31 and the resize_bilinear calls at :61-62 etc.
+// One thread per full-resolution pixel.  It writes the 6(+pad)-channel conv1 input and, when
+// the pixel sits on the 2^s grid, the LRN-normalised pixel of pyramid level s (legacy
+// resize_bilinear at an integer ratio is exact decimation, so no interpolation is needed).
+struct PreParams {
+    const float *src, *tgt;
+    float *x6;
+    int x6_ld;
+    int B, H, W;
+    float mean[3];
+    int n_scales;
+    float *pyr_src[8];
+    float *pyr_tgt[8];
+};
+
+__device__ __forceinline__ void lrn3(const float x[3], float o[3]) {
+    // tf.nn.local_response_normalization(depth_radius=4, beta=0.7), bias=1 alpha=1; 3 channels
+    const float s = 1.f + (x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+    const float den = powf(s, 0.7f);
+    o[0] = x[0] / den; o[1] = x[1] / den; o[2] = x[2] / den;
+}
+
+__global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__ PreParams P) {
+    const long long npix = (long long)P.B * P.H * P.W;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(p % P.W);
+        const int y = (int)((p / P.W) % P.H);
+        const int b = (int)(p / ((long long)P.W * P.H));
+        float a[3], t[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            a[c] = (__ldg(P.src + p * 3 + c) - P.mean[c]) / 255.0f;
+            t[c] = (__ldg(P.tgt + p * 3 + c) - P.mean[c]) / 255.0f;
+        }
+        float *o = P.x6 + p * P.x6_ld;
+        if (P.x6_ld == 8) {
+            reinterpret_cast<float4 *>(o)[0] = make_float4(a[0], a[1], a[2], t[0]);
+            reinterpret_cast<float4 *>(o)[1] = make_float4(t[1], t[2], 0.f, 0.f);
+        } else {
+            o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; o[3] = t[0]; o[4] = t[1]; o[5] = t[2];
+            for (int c = 6; c < P.x6_ld; ++c) o[c] = 0.f;
+        }
+        if (P.n_scales > 0 && ((x | y) & 1) == 0) {
+            float an[3], tn[3];
+            lrn3(a, an);
+            lrn3(t, tn);
+            for (int s = 0; s < P.n_scales; ++s) {
+                const int r = 2 << s;
+                if ((x & (r - 1)) | (y & (r - 1))) break;
+                const int hs = P.H >> (s + 1), ws = P.W >> (s + 1);
+                const long long q = (((long long)b * hs + (y >> (s + 1))) * ws + (x >> (s + 1))) * 3;
+                P.pyr_src[s][q] = an[0]; P.pyr_src[s][q + 1] = an[1]; P.pyr_src[s][q + 2] = an[2];
+                P.pyr_tgt[s][q] = tn[0]; P.pyr_tgt[s][q + 1] = tn[1]; P.pyr_tgt[s][q + 2] = tn[2];
+            }
+        }
+    }
+}
+
+// ---- ELU backward --------------------------------------------------------------------
+__global__ void __launch_bounds__(256) elu_bwd_kernel(float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c4) {
+    const long long n = n_pix * c4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / c4;
+        const int q = (int)(i - p * c4) * 4;
+        float4 gv = *reinterpret_cast<float4 *>(g + p * g_ld + q);
+        const float4 yv = __ldg(reinterpret_cast<const float4 *>(y + p * y_ld + q));
+        gv.x *= elu_grad_from_out(yv.x); gv.y *= elu_grad_from_out(yv.y);
+        gv.z *= elu_grad_from_out(yv.z); gv.w *= elu_grad_from_out(yv.w);
+        *reinterpret_cast<float4 *>(g + p * g_ld + q) = gv;
+    }
+}
+
+// ---- Adam (TF epsilon-hat form, flyingChairsTrain.py:124) ----------------------------
+__global__ void __launch_bounds__(256) adam_kernel(float *__restrict__ theta, const float *__restrict__ g, float *__restrict__ m,
+                                                   float *__restrict__ v, long long n4, long long n, float lr_t, float b1,
+                                                   float b2, float eps, float gscale) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 t = reinterpret_cast<float4 *>(theta)[i];
+        float4 gg = __ldg(reinterpret_cast<const float4 *>(g) + i);
+        float4 mm = reinterpret_cast<float4 *>(m)[i];
+        float4 vv = reinterpret_cast<float4 *>(v)[i];
+#define DOFB_ADAM1(T, G, M, V)                  \
+    {                                           \
+        const float gs = G * gscale;            \
+        M = b1 * M + (1.f - b1) * gs;           \
+        V = b2 * V + (1.f - b2) * gs * gs;      \
+        T -= lr_t * M / (sqrtf(V) + eps);       \
+    }
+        DOFB_ADAM1(t.x, gg.x, mm.x, vv.x) DOFB_ADAM1(t.y, gg.y, mm.y, vv.y)
+        DOFB_ADAM1(t.z, gg.z, mm.z, vv.z) DOFB_ADAM1(t.w, gg.w, mm.w, vv.w)
+        reinterpret_cast<float4 *>(theta)[i] = t;
+        reinterpret_cast<float4 *>(m)[i] = mm;
+        reinterpret_cast<float4 *>(v)[i] = vv;
+    }
+    // scalar tail (n not a multiple of 4)
+    for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float T = theta[i], M = m[i], V = v[i];
+        const float G = g[i];
+        DOFB_ADAM1(T, G, M, V)
+        theta[i] = T; m[i] = M; v[i] = V;
+    }
+#undef DOFB_ADAM1
+}
+
+// ---- EPE (utils.py:64-68) -----------------------------------------------------------------
+__global__ void __launch_bounds__(256) epe_kernel(const float *flow, const float *gt, long long n_pix, double *out) {
+    double acc = 0.0;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n_pix; p += (long long)gridDim.x * blockDim.x) {
+        const float2 a = __ldg(reinterpret_cast<const float2 *>(flow) + p);
+        const float2 b = __ldg(reinterpret_cast<const float2 *>(gt) + p);
+        const float du = a.x - b.x, dv = a.y - b.y;
+        acc += (double)sqrtf(du * du + dv * dv);
+    }
+    acc = warp_sum(acc);
+    __shared__ double red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0;
+        for (int i = 0; i < 8; ++i) s += red[i];
+        atomicAdd(out, s);
+    }
+}
+
+static inline int grid_for(long long n_items, int threads, int per_sm = 8) {
+    long long want = (n_items + threads - 1) / threads;
+    long long cap = (long long)num_sms() * per_sm;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+}  // namespace dofb
+
+using namespace dofb;
+
+extern "C" int dofb_version(void) { return DOFB_VERSION; }
+extern "C" const char *dofb_last_error(void) { return err_buf(); }
+extern "C" long long dofb_launch_count(void) { return g_launches.load(); }
+extern "C" void dofb_reset_launch_count(void) { g_launches.store(0); }
+
+extern "C" int dofb_preprocess(const float *src, const float *tgt, const float mean_bgr[3], int B, int H, int W, float *x6,
+                               int x6_ld, int n_scales, float *const *pyr_src, float *const *pyr_tgt, void *stream) {
+    DOFB_CHECK_ARG(src && tgt && x6 && mean_bgr, "dofb_preprocess: null argument");
+    DOFB_CHECK_ARG(B > 0 && H > 0 && W > 0 && x6_ld >= 6, "dofb_preprocess: bad shape B=%d H=%d W=%d ld=%d", B, H, W, x6_ld);
+    DOFB_CHECK_ARG(n_scales >= 0 && n_scales <= 8, "dofb_preprocess: n_scales=%d out of range", n_scales);
+    DOFB_CHECK_ARG(n_scales == 0 || (H % (1 << n_scales) == 0 && W % (1 << n_scales) == 0),
+                   "dofb_preprocess: H=%d W=%d must be multiples of 2^%d", H, W, n_scales);
+    DOFB_CHECK_ARG(x6_ld != 8 || aligned16(x6), "dofb_preprocess: x6 must be 16-byte aligned");
+    PreParams P;
+    P.src = src; P.tgt = tgt; P.x6 = x6; P.x6_ld = x6_ld; P.B = B; P.H = H; P.W = W;
+    for (int c = 0; c < 3; ++c) P.mean[c] = mean_bgr[c];
+    P.n_scales = n_scales;
+    for (int s = 0; s < 8; ++s) {
+        P.pyr_src[s] = s < n_scales ? pyr_src[s] : nullptr;
+        P.pyr_tgt[s] = s < n_scales ? pyr_tgt[s] : nullptr;
+        DOFB_CHECK_ARG(s >= n_scales || (P.pyr_src[s] && P.pyr_tgt[s]), "dofb_preprocess: null pyramid level %d", s);
+    }
+    preprocess_kernel<<<grid_for((long long)B * H * W, 256), 256, 0, as_stream(stream)>>>(P);
+    DOFB_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int dofb_elu_bwd(float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c, void *stream) {
+    DOFB_CHECK_ARG(g && y && n_pix > 0 && c > 0, "dofb_elu_bwd: bad argument");
+    DOFB_CHECK_ARG(c % 4 == 0 && g_ld % 4 == 0 && y_ld % 4 == 0 && aligned16(g) && aligned16(y),
+                   "dofb_elu_bwd: channels/pitches must be multiples of 4 and pointers 16-byte aligned (c=%d)", c);
+    elu_bwd_kernel<<<grid_for(n_pix * (c / 4), 256), 256, 0, as_stream(stream)>>>(g, g_ld, y, y_ld, n_pix, c / 4);
+    DOFB_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int dofb_adam(float *theta, const float *g, float *m, float *v, long long n, float lr_t, float beta1, float beta2,
+                         float epsilon, float grad_scale, void *stream) {
+    DOFB_CHECK_ARG(theta && g && m && v && n > 0, "dofb_adam: bad argument");
+    DOFB_CHECK_ARG(aligned16(theta) && aligned16(g) && aligned16(m) && aligned16(v), "dofb_adam: arenas must be 16-byte aligned");
+    adam_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, as_stream(stream)>>>(theta, g, m, v, n / 4, n, lr_t, beta1, beta2, epsilon,
+                                                                         grad_scale);
+    DOFB_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int dofb_epe_sum(const float *flow, const float *gt, long long n_pix, double *out, void *stream) {
+    DOFB_CHECK_ARG(flow && gt && out && n_pix > 0, "dofb_epe_sum: bad argument");
+    DOFB_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(double), as_stream(stream)));
+    epe_kernel<<<grid_for(n_pix, 256, 4), 256, 0, as_stream(stream)>>>(flow, gt, n_pix, out);
+    DOFB_LAUNCH_OK();
+    return 0;
+}

@@ -1,0 +1,300 @@
+"""FlowNetS guided-flow training engine: static memory plan + hand-scheduled forward/backward.
+
+Replaces the TF graph built by ``flyingChairsWrapFlow.flowNet`` (flyingChairsWrapFlow.py:5-129)
+plus ``AdamOptimizer.minimize`` (flyingChairsTrain.py:121-124).  There is no tracing compiler and
+no autograd on this path: the layer list is static, so the backward schedule is written out once
+(reverse topological order, accumulation flags fixed at plan time) and every launch is one of the
+CUDA kernels behind include/deepof_b200.h.
+
+Memory plan (NHWC fp32, sized for 180 GB HBM3e; B=32 @384x512 needs ~3 GB):
+  * one flat parameter arena + identically laid out gradient / Adam-m / Adam-v arenas
+    (TF layouts, every tensor 256-byte aligned) -> Adam and the gradient all-reduce are single
+    passes over flat memory;
+  * tf.concat is never materialised: conv / deconv / up_pr write into channel slices of the
+    concat buffers (pitch rounded up to 32 floats: 128, 224, 416, 800, 1056);
+  * gradient buffers mirror the activation buffers; a slice's gradient is accumulated in place by
+    its consumers in a fixed order, then multiplied by ELU' once.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+
+import torch
+
+from . import ops
+from .ops import Slab, full, conv_geom, ACT_ELU, ACT_NONE, MATH_FP32, MATH_TF32
+
+FLYINGCHAIRS_MEAN = (97.533268117955444, 99.238235788550085, 97.055973199626948)   # flyingChairsWrapFlow.py:16
+SINTEL_MEAN = (70.1433, 83.1915, 92.8827)                                          # sintelWrapFlow.py:773
+
+# (name, k, stride, cin, cout)  flyingChairsWrapFlow.py:31-40
+TOWER = [("conv1", 7, 2, 6, 64), ("conv2", 5, 2, 64, 128), ("conv3_1", 5, 2, 128, 256), ("conv3_2", 3, 1, 256, 256),
+         ("conv4_1", 3, 2, 256, 512), ("conv4_2", 3, 1, 512, 512), ("conv5_1", 3, 2, 512, 512), ("conv5_2", 3, 1, 512, 512),
+         ("conv6_1", 3, 2, 512, 1024), ("conv6_2", 3, 1, 1024, 1024)]
+# (s, feat channels at s, upconv name, upconv cout, up_pr name, skip channels at s-1)  :58-111
+REFINE = [(6, 1024, "upconv5", 512, "up_pr6to5", 512), (5, 1026, "upconv4", 256, "up_pr5to4", 512),
+          (4, 770, "upconv3", 128, "up_pr4to3", 256), (3, 386, "upconv2", 64, "up_pr3to2", 128),
+          (2, 194, "upconv1", 32, "up_pr2to1", 64)]
+FEAT_C = {6: 1024, 5: 1026, 4: 770, 3: 386, 2: 194, 1: 98}
+FLOW_SCALES = {1: 10.0, 2: 5.0, 3: 2.5, 4: 1.25, 5: 0.625, 6: 0.3125}            # :118,107,96,85,74,63
+HYPER = dict(epsilon=1e-4, alpha_c=0.25, alpha_s=0.37, lambda_smooth=1.0)         # :43-46
+LOSS_WEIGHTS = (16.0, 8.0, 4.0, 2.0, 1.0, 1.0)                                    # flyingChairsTrain.py:165
+
+
+def param_shapes() -> "OrderedDict[str, tuple]":
+    """The 52 trainable tensors in TF creation order and TF layouts."""
+    sh: "OrderedDict[str, tuple]" = OrderedDict()
+    for name, k, _s, cin, cout in TOWER:
+        sh[name + "/weights"] = (k, k, cin, cout)
+        sh[name + "/biases"] = (cout,)
+    for s, cfeat, up, upc, uppr, _skip in REFINE:
+        sh[f"pr{s}/weights"] = (3, 3, cfeat, 2)
+        sh[f"pr{s}/biases"] = (2,)
+        sh[up + "/weights"] = (4, 4, upc, cfeat)
+        sh[up + "/biases"] = (upc,)
+        sh[uppr + "/weights"] = (4, 4, 2, 2)
+        sh[uppr + "/biases"] = (2,)
+    sh["pr1/weights"] = (3, 3, 98, 2)
+    sh["pr1/biases"] = (2,)
+    return sh
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class ParamArena:
+    """Flat fp32 arena with named TF-layout views (256-byte aligned starts)."""
+
+    def __init__(self, shapes: "OrderedDict[str, tuple]", device):
+        self.shapes = shapes
+        self.offsets = OrderedDict()
+        off = 0
+        for name, shape in shapes.items():
+            self.offsets[name] = off
+            off += _round_up(math.prod(shape), 64)
+        self.numel = off
+        self.n_true = sum(math.prod(s) for s in shapes.values())
+        self.device = device
+
+    def new(self):
+        return torch.zeros(self.numel, dtype=torch.float32, device=self.device)
+
+    def views(self, flat: torch.Tensor) -> "OrderedDict[str, torch.Tensor]":
+        out = OrderedDict()
+        for name, shape in self.shapes.items():
+            o = self.offsets[name]
+            out[name] = flat[o:o + math.prod(shape)].view(shape)
+        return out
+
+
+def xavier_uniform(shape, gen):
+    rf = math.prod(shape[:-2])
+    lim = math.sqrt(6.0 / (rf * shape[-2] + rf * shape[-1]))
+    return ((torch.rand(shape, generator=gen, dtype=torch.float64) * 2 - 1) * lim).float()
+
+
+def bilinear_deconv(shape):
+    """flyingChairsTrain.py:78-92 (k=4 -> outer([.25,.75,.75,.25]) on the channel diagonal)."""
+    k = shape[0]
+    f = float(math.ceil(k / 2.0))
+    c = (2 * f - 1 - f % 2) / (2.0 * f)
+    ax = torch.tensor([1 - abs(i / f - c) for i in range(k)], dtype=torch.float64)
+    w = torch.zeros(shape, dtype=torch.float64)
+    for i in range(shape[2]):
+        w[:, :, i, i] = torch.outer(ax, ax)
+    return w.float()
+
+
+class FlowNetS:
+    """Static-shape FlowNetS engine.  ``math``: 'fp32' (SIMT FFMA, parity grade) or 'tf32' (tcgen05)."""
+
+    def __init__(self, batch: int, height: int = 384, width: int = 512, device="cuda", variant: str = "A",
+                 math_mode: str = "fp32", mean=FLYINGCHAIRS_MEAN, hyper=None, seed: int | None = 1):
+        if height % 64 or width % 64:
+            raise ValueError("FlowNetS needs H and W to be multiples of 64 (the reference resizes/pads as well, SURVEY.md 0.5)")
+        if not torch.cuda.is_available():
+            raise ops.DeepOFError("deepof_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.B, self.H, self.W = batch, height, width
+        self.device = torch.device(device)
+        self.variant = {"A": 0, "B": 1}[variant]
+        self.math = {"fp32": MATH_FP32, "tf32": MATH_TF32}[math_mode]
+        self.mean = tuple(float(m) for m in mean)
+        self.hyper = dict(HYPER)
+        if hyper:
+            self.hyper.update(hyper)
+        self.arena = ParamArena(param_shapes(), self.device)
+        self.theta, self.grad = self.arena.new(), self.arena.new()
+        self.m, self.v = self.arena.new(), self.arena.new()
+        self.params = self.arena.views(self.theta)
+        self.grads = self.arena.views(self.grad)
+        self.t = 0
+        self._alloc()
+        self._plan()
+        self.warp_loss = ops.WarpLoss(self.device)
+        if seed is not None:
+            self.init_params(seed)
+
+    # ------------------------------------------------------------------ parameters
+    def init_params(self, seed: int = 1):
+        """slim defaults (xavier-uniform, zero bias) + bilinear overwrite of every 'up*' weight."""
+        gen = torch.Generator().manual_seed(seed)
+        for name, shape in self.arena.shapes.items():
+            if name.endswith("biases"):
+                self.params[name].zero_()
+                continue
+            w = xavier_uniform(shape, gen)
+            if name.startswith("up"):
+                w = bilinear_deconv(shape)
+            self.params[name].copy_(w)
+
+    def load_params(self, params: dict):
+        for name, p in params.items():
+            self.params[name].copy_(torch.as_tensor(p, dtype=torch.float32).reshape(self.arena.shapes[name]))
+
+    def export_params(self) -> "OrderedDict[str, torch.Tensor]":
+        return OrderedDict((k, v.detach().cpu().clone()) for k, v in self.params.items())
+
+    # ------------------------------------------------------------------ buffers
+    def _alloc(self):
+        B, H, W, dev = self.B, self.H, self.W, self.device
+        z = lambda h, w, c: torch.zeros(B, h, w, c, dtype=torch.float32, device=dev)  # noqa: E731
+        self.x6 = z(H, W, 8)
+        shp = {"concat1": (H // 2, W // 2, 128), "concat2": (H // 4, W // 4, 224), "c31": (H // 8, W // 8, 256),
+               "concat3": (H // 8, W // 8, 416), "c41": (H // 16, W // 16, 512), "concat4": (H // 16, W // 16, 800),
+               "c51": (H // 32, W // 32, 512), "concat5": (H // 32, W // 32, 1056), "c61": (H // 64, W // 64, 1024),
+               "c62": (H // 64, W // 64, 1024)}
+        self.act = {k: z(*v) for k, v in shp.items()}
+        self.dact = {k: z(*v) for k, v in shp.items()}
+        self.hw = {s: (H >> s, W >> s) for s in range(1, 7)}
+        self.pr = {s: z(*self.hw[s], 2) for s in range(1, 7)}
+        self.dpr = {s: z(*self.hw[s], 2) for s in range(1, 7)}
+        self.pyr_src = {s: z(*self.hw[s], 3) for s in range(1, 7)}
+        self.pyr_tgt = {s: z(*self.hw[s], 3) for s in range(1, 7)}
+        self.recon1 = z(*self.hw[1], 3)
+        self.loss4 = torch.zeros(6, 4, dtype=torch.float32, device=dev)
+
+    def _plan(self):
+        B, H, W = self.B, self.H, self.W
+        a, d = self.act, self.dact
+        S = Slab
+        io = [(S(self.x6, 0, 6), None, S(a["concat1"], 0, 64), S(d["concat1"], 0, 64)),
+              (S(a["concat1"], 0, 64), S(d["concat1"], 0, 64), S(a["concat2"], 0, 128), S(d["concat2"], 0, 128)),
+              (S(a["concat2"], 0, 128), S(d["concat2"], 0, 128), full(a["c31"]), full(d["c31"])),
+              (full(a["c31"]), full(d["c31"]), S(a["concat3"], 0, 256), S(d["concat3"], 0, 256)),
+              (S(a["concat3"], 0, 256), S(d["concat3"], 0, 256), full(a["c41"]), full(d["c41"])),
+              (full(a["c41"]), full(d["c41"]), S(a["concat4"], 0, 512), S(d["concat4"], 0, 512)),
+              (S(a["concat4"], 0, 512), S(d["concat4"], 0, 512), full(a["c51"]), full(d["c51"])),
+              (full(a["c51"]), full(d["c51"]), S(a["concat5"], 0, 512), S(d["concat5"], 0, 512)),
+              (S(a["concat5"], 0, 512), S(d["concat5"], 0, 512), full(a["c61"]), full(d["c61"])),
+              (full(a["c61"]), full(d["c61"]), full(a["c62"]), full(d["c62"]))]
+        # d_in buffers that already hold gradient from the refinement part when the tower backward reaches them
+        acc_in = {"conv2": True, "conv3_1": True, "conv4_1": True, "conv5_1": True, "conv6_1": True}
+        self.tower = []
+        ih, iw = H, W
+        for (name, k, s, cin, cout), (x, dx, y, dy) in zip(TOWER, io):
+            g = conv_geom(B, ih, iw, cin, cout, k, s)
+            self.tower.append(dict(name=name, g=g, x=x, dx=dx, y=y, dy=dy, acc=acc_in.get(name, False)))
+            ih, iw = g.oh, g.ow
+        feat = {6: (full(a["c62"]), full(d["c62"])), 5: (S(a["concat5"], 0, 1026), S(d["concat5"], 0, 1026)),
+                4: (S(a["concat4"], 0, 770), S(d["concat4"], 0, 770)), 3: (S(a["concat3"], 0, 386), S(d["concat3"], 0, 386)),
+                2: (S(a["concat2"], 0, 194), S(d["concat2"], 0, 194)), 1: (S(a["concat1"], 0, 98), S(d["concat1"], 0, 98))}
+        self.feat = feat
+        cat = {5: "concat5", 4: "concat4", 3: "concat3", 2: "concat2", 1: "concat1"}
+        self.refine = []
+        for s, cfeat, up, upc, uppr, skipc in REFINE:
+            hs, ws = self.hw[s]
+            g = conv_geom(B, 2 * hs, 2 * ws, upc, cfeat, 4, 2)     # the conv whose input-gradient is this deconv
+            assert g.oh == hs and g.ow == ws and g.pad_t == 1
+            tgt = cat[s - 1]
+            self.refine.append(dict(s=s, g=g, up=up, uppr=uppr,
+                                    up_y=S(a[tgt], skipc, upc), up_dy=S(d[tgt], skipc, upc),
+                                    pr_y=S(a[tgt], skipc + upc, 2), pr_dy=S(d[tgt], skipc + upc, 2)))
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, source: torch.Tensor, target: torch.Tensor, loss_weight=LOSS_WEIGHTS, with_grad: bool = True):
+        """flowNet(inputs, outputs, loss_weight): runs the whole forward; when ``with_grad`` the fused
+        warp/loss kernel also leaves d(total)/d(pr_s) in self.dpr (the start of the backward)."""
+        if tuple(source.shape) != (self.B, self.H, self.W, 3) or tuple(target.shape) != (self.B, self.H, self.W, 3):
+            raise ops.DeepOFError(f"expected [B={self.B},{self.H},{self.W},3] NHWC inputs, got {tuple(source.shape)} / {tuple(target.shape)}")
+        P, mth = self.params, self.math
+        ops.preprocess(source, target, self.mean, self.x6, [self.pyr_src[s] for s in range(1, 7)],
+                       [self.pyr_tgt[s] for s in range(1, 7)])
+        for L in self.tower:
+            ops.conv_fwd(L["g"], L["x"], P[L["name"] + "/weights"], P[L["name"] + "/biases"], L["y"], ACT_ELU, mth)
+        for R in self.refine:
+            s = R["s"]
+            x, _ = self.feat[s]
+            ops.head_fwd(x, P[f"pr{s}/weights"], P[f"pr{s}/biases"], self.pr[s])
+            ops.conv_dgrad(R["g"], x, P[R["up"] + "/weights"], P[R["up"] + "/biases"], R["up_y"], ACT_ELU, False, mth)
+            ops.uppr_fwd(self.pr[s], P[R["uppr"] + "/weights"], P[R["uppr"] + "/biases"], R["pr_y"])
+        ops.head_fwd(self.feat[1][0], P["pr1/weights"], P["pr1/biases"], self.pr[1])
+        lw = [float(v) for v in loss_weight]
+        self.loss_weight = lw
+        hp = self.hyper
+        scales = []
+        for s in range(1, 7):
+            wgt = lw[s - 1]
+            scales.append(dict(flow=self.pr[s], src=self.pyr_src[s], tgt=self.pyr_tgt[s],
+                               recon=self.recon1 if s == 1 else None, dflow=self.dpr[s] if with_grad else None,
+                               loss4=self.loss4[s - 1], flow_scale=FLOW_SCALES[s], epsilon=hp["epsilon"],
+                               alpha_c=hp["alpha_c"], alpha_s=hp["alpha_s"], lambda_smooth=hp["lambda_smooth"],
+                               g_charb=wgt, g_u=wgt * hp["lambda_smooth"], g_v=wgt * hp["lambda_smooth"],
+                               variant=self.variant))
+        self.warp_loss(scales)
+
+    def outputs(self):
+        """(losses, flows_all, prev1) exactly as flowNet returns them (flyingChairsWrapFlow.py:126-129)."""
+        keys = ("total", "Charbonnier_reconstruct", "U_loss", "V_loss")
+        losses = [{k: self.loss4[s, i] for i, k in enumerate(keys)} for s in range(6)]
+        flows_all = [self.pr[s] * FLOW_SCALES[s] for s in range(1, 7)]
+        return losses, flows_all, self.recon1
+
+    def total_loss(self) -> torch.Tensor:
+        lw = torch.tensor(self.loss_weight, dtype=torch.float32, device=self.device)
+        return (self.loss4[:, 0] * lw).sum()
+
+    # ------------------------------------------------------------------ backward
+    def backward(self):
+        P, G, mth = self.params, self.grads, self.math
+        self.grad.zero_()
+        # refinement part, finest scale first (each pr_s gradient is complete when its scale is reached)
+        x1, dx1 = self.feat[1]
+        ops.head_wgrad(x1, self.dpr[1], G["pr1/weights"], G["pr1/biases"])
+        ops.head_dgrad(self.dpr[1], P["pr1/weights"], dx1, accumulate=False)
+        for R in reversed(self.refine):                      # s = 2,3,4,5,6
+            s = R["s"]
+            x, dx = self.feat[s]
+            # up_pr (linear): dpr_s += ..., dW, db
+            ops.uppr_bwd(self.pr[s], R["pr_dy"], P[R["uppr"] + "/weights"], self.dpr[s], G[R["uppr"] + "/weights"],
+                         G[R["uppr"] + "/biases"])
+            # upconv (ELU): gradient through the activation, then weight / bias / input gradients
+            ops.elu_bwd(R["up_dy"], R["up_y"])
+            ops.conv_wgrad(R["g"], R["up_dy"], x, G[R["up"] + "/weights"], G[R["up"] + "/biases"], mth, bias_on_large=True)
+            ops.conv_fwd(R["g"], R["up_dy"], P[R["up"] + "/weights"], None, dx, ACT_NONE, mth)     # first writer of d feat_s
+            # pr_s head
+            ops.head_wgrad(x, self.dpr[s], G[f"pr{s}/weights"], G[f"pr{s}/biases"])
+            ops.head_dgrad(self.dpr[s], P[f"pr{s}/weights"], dx, accumulate=True)
+        # contracting tower, top down
+        for L in reversed(self.tower):
+            ops.elu_bwd(L["dy"], L["y"])
+            ops.conv_wgrad(L["g"], L["x"], L["dy"], G[L["name"] + "/weights"], G[L["name"] + "/biases"], mth)
+            if L["dx"] is not None:
+                ops.conv_dgrad(L["g"], L["dy"], P[L["name"] + "/weights"], None, L["dx"], ACT_NONE, L["acc"], mth)
+
+    # ------------------------------------------------------------------ optimiser
+    def adam_step(self, lr: float, grad_scale: float = 1.0, beta1=0.9, beta2=0.999, eps=1e-8):
+        """TF-form Adam over the flat arena (flyingChairsTrain.py:124)."""
+        self.t += 1
+        lr_t = lr * math.sqrt(1.0 - beta2 ** self.t) / (1.0 - beta1 ** self.t)
+        ops.adam(self.theta, self.grad, self.m, self.v, lr_t, beta1, beta2, eps, grad_scale)
+
+    def train_step(self, source, target, loss_weight=LOSS_WEIGHTS, lr: float = 1.6e-5, allreduce=None):
+        """One ``train_op.run(feed_dict)`` (flyingChairsTrain.py:178): forward, backward, Adam."""
+        self.forward(source, target, loss_weight, with_grad=True)
+        self.backward()
+        scale = 1.0
+        if allreduce is not None:
+            scale = allreduce(self.grad)
+        self.adam_step(lr, grad_scale=scale)

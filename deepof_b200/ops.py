@@ -1,0 +1,212 @@
+"""Tensor-level wrappers over the C ABI: argument checking + pointer/pitch plumbing.
+
+Every function launches hand-written CUDA from libdeepof_b200.so on the current torch stream.
+Tensors are NHWC float32 CUDA tensors; ``Slab`` describes a channel slice of a pitched buffer.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from ._lib import ConvGeom, LossScale, DeepOFError, check
+
+ACT_NONE, ACT_ELU = 0, 1
+MATH_FP32, MATH_TF32 = 0, 1
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _req(t: torch.Tensor, name: str) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise DeepOFError(f"{name}: expected a CUDA tensor (the deepof_b200 product path has no CPU fallback)")
+    if t.dtype != torch.float32:
+        raise DeepOFError(f"{name}: expected float32, got {t.dtype}")
+    if not t.is_contiguous():
+        raise DeepOFError(f"{name}: expected a contiguous tensor")
+
+
+@dataclass
+class Slab:
+    """Channels [c0, c0+c) of a contiguous [B,H,W,ld] buffer."""
+    t: torch.Tensor
+    c0: int
+    c: int
+
+    def __post_init__(self):
+        _req(self.t, "Slab")
+        assert self.t.dim() == 4 and 0 <= self.c0 and self.c0 + self.c <= self.t.shape[3]
+
+    @property
+    def ptr(self) -> int:
+        return self.t.data_ptr() + 4 * self.c0
+
+    @property
+    def ld(self) -> int:
+        return self.t.shape[3]
+
+    @property
+    def B(self):
+        return self.t.shape[0]
+
+    @property
+    def h(self):
+        return self.t.shape[1]
+
+    @property
+    def w(self):
+        return self.t.shape[2]
+
+    @property
+    def n_pix(self) -> int:
+        return self.t.shape[0] * self.t.shape[1] * self.t.shape[2]
+
+    def dense(self) -> torch.Tensor:
+        return self.t[..., self.c0:self.c0 + self.c]
+
+
+def full(t: torch.Tensor, c: int | None = None) -> Slab:
+    return Slab(t, 0, t.shape[3] if c is None else c)
+
+
+def same_pad(in_size: int, k: int, stride: int):
+    out = -(-in_size // stride)
+    total = max((out - 1) * stride + k - in_size, 0)
+    return out, total // 2
+
+
+def conv_geom(B, ih, iw, ci, co, k, stride) -> ConvGeom:
+    """Geometry of a TF-SAME conv (also used, as 'the conv it is the gradient of', for conv2d_transpose)."""
+    oh, pt = same_pad(ih, k, stride)
+    ow, pl = same_pad(iw, k, stride)
+    return ConvGeom(B, ih, iw, ci, oh, ow, co, k, k, stride, pt, pl)
+
+
+def preprocess(src, tgt, mean, x6, pyr_src, pyr_tgt):
+    _req(src, "src"); _req(tgt, "tgt"); _req(x6, "x6")
+    B, H, W, _ = src.shape
+    n = len(pyr_src)
+    for t in list(pyr_src) + list(pyr_tgt):
+        _req(t, "pyramid")
+    m = (C.c_float * 3)(*[float(v) for v in mean])
+    ps = (C.c_void_p * max(n, 1))(*[t.data_ptr() for t in pyr_src])
+    pt = (C.c_void_p * max(n, 1))(*[t.data_ptr() for t in pyr_tgt])
+    lib = _lib.load()
+    check(lib.dofb_preprocess(src.data_ptr(), tgt.data_ptr(), m, B, H, W, x6.data_ptr(), x6.shape[3], n, ps, pt, _stream()))
+
+
+def conv_fwd(g: ConvGeom, x: Slab, w, b, y: Slab, act=ACT_ELU, math=MATH_FP32):
+    _req(w, "w")
+    lib = _lib.load()
+    check(lib.dofb_conv_fwd(C.byref(g), x.ptr, x.ld, w.data_ptr(), b.data_ptr() if b is not None else None,
+                            y.ptr, y.ld, act, math, _stream()))
+
+
+def conv_dgrad(g: ConvGeom, dy: Slab, w, bias, dx: Slab, act=ACT_NONE, accumulate=False, math=MATH_FP32):
+    _req(w, "w")
+    lib = _lib.load()
+    check(lib.dofb_conv_dgrad(C.byref(g), dy.ptr, dy.ld, w.data_ptr(), bias.data_ptr() if bias is not None else None,
+                              dx.ptr, dx.ld, act, int(accumulate), math, _stream()))
+
+
+def conv_wgrad(g: ConvGeom, x: Slab, dy: Slab, dw, db, math=MATH_FP32, bias_on_large=False):
+    _req(dw, "dw")
+    lib = _lib.load()
+    fn = lib.dofb_conv_wgrad_tbias if bias_on_large else lib.dofb_conv_wgrad
+    check(fn(C.byref(g), x.ptr, x.ld, dy.ptr, dy.ld, dw.data_ptr(), db.data_ptr() if db is not None else None, math, _stream()))
+
+
+def elu_bwd(g: Slab, y: Slab):
+    assert g.c == y.c and g.n_pix == y.n_pix
+    check(_lib.load().dofb_elu_bwd(g.ptr, g.ld, y.ptr, y.ld, g.n_pix, g.c, _stream()))
+
+
+def head_fwd(x: Slab, w, b, pr):
+    _req(pr, "pr")
+    check(_lib.load().dofb_head_fwd(x.ptr, x.ld, x.B, x.h, x.w, x.c, w.data_ptr(), b.data_ptr(), pr.data_ptr(), _stream()))
+
+
+def head_dgrad(dpr, w, dx: Slab, accumulate: bool):
+    _req(dpr, "dpr")
+    check(_lib.load().dofb_head_dgrad(dpr.data_ptr(), dx.B, dx.h, dx.w, dx.c, w.data_ptr(), dx.ptr, dx.ld, int(accumulate), _stream()))
+
+
+def head_wgrad(x: Slab, dpr, dw, db):
+    check(_lib.load().dofb_head_wgrad(x.ptr, x.ld, dpr.data_ptr(), x.B, x.h, x.w, x.c, dw.data_ptr(),
+                                      db.data_ptr() if db is not None else None, _stream()))
+
+
+def uppr_fwd(pr, w, b, y: Slab):
+    B, h, wd, _ = pr.shape
+    assert y.c == 2 and y.h == 2 * h and y.w == 2 * wd
+    check(_lib.load().dofb_uppr_fwd(pr.data_ptr(), B, h, wd, w.data_ptr(), b.data_ptr(), y.ptr, y.ld, _stream()))
+
+
+def uppr_bwd(pr, dy: Slab, w, dpr, dw, db):
+    B, h, wd, _ = pr.shape
+    check(_lib.load().dofb_uppr_bwd(pr.data_ptr(), dy.ptr, dy.ld, B, h, wd, w.data_ptr(), dpr.data_ptr(), dw.data_ptr(),
+                                    db.data_ptr() if db is not None else None, _stream()))
+
+
+def adam(theta, g, m, v, lr_t, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    for t in (theta, g, m, v):
+        _req(t, "adam arena")
+    check(_lib.load().dofb_adam(theta.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), theta.numel(),
+                                lr_t, beta1, beta2, eps, grad_scale, _stream()))
+
+
+def epe_sum(flow, gt, out):
+    _req(flow, "flow"); _req(gt, "gt")
+    assert out.dtype == torch.float64 and out.is_cuda
+    check(_lib.load().dofb_epe_sum(flow.data_ptr(), gt.data_ptr(), flow.numel() // 2, out.data_ptr(), _stream()))
+
+
+def corr_fwd(f1: Slab, f2: Slab, out: Slab, max_disp=20, stride2=2):
+    assert f1.ld == f2.ld and f1.c == f2.c
+    check(_lib.load().dofb_corr_fwd(f1.ptr, f2.ptr, f1.ld, f1.B, f1.h, f1.w, f1.c, max_disp, stride2, out.ptr, out.ld, _stream()))
+
+
+def corr_bwd(f1: Slab, f2: Slab, dout: Slab, df1: Slab, df2: Slab, max_disp=20, stride2=2):
+    assert df1.ld == df2.ld
+    check(_lib.load().dofb_corr_bwd(f1.ptr, f2.ptr, f1.ld, f1.B, f1.h, f1.w, f1.c, max_disp, stride2, dout.ptr, dout.ld,
+                                    df1.ptr, df2.ptr, df1.ld, _stream()))
+
+
+class WarpLoss:
+    """All pyramid scales of loss_interp (forward + d/dflow) in one launch."""
+
+    def __init__(self, device):
+        self.device = device
+        self.ws = None
+
+    def __call__(self, scales: list[dict]):
+        n = len(scales)
+        arr = (LossScale * n)()
+        keep = []
+        for i, s in enumerate(scales):
+            flow, src, tgt = s["flow"], s["src"], s["tgt"]
+            for t, nm in ((flow, "flow"), (src, "src"), (tgt, "tgt"), (s["loss4"], "loss4")):
+                _req(t, nm)
+            B, h, w, _ = flow.shape
+            if tuple(src.shape) != (B, h, w, 3) or tuple(tgt.shape) != (B, h, w, 3):
+                raise DeepOFError(f"loss_interp: inputs/outputs must be [B,h,w,3] matching the flow {tuple(flow.shape)}")
+            recon, dflow = s.get("recon"), s.get("dflow")
+            arr[i] = LossScale(flow.data_ptr(), src.data_ptr(), tgt.data_ptr(),
+                               recon.data_ptr() if recon is not None else None,
+                               dflow.data_ptr() if dflow is not None else None,
+                               s["loss4"].data_ptr(), B, h, w, float(s["flow_scale"]),
+                               float(s["epsilon"]), float(s["alpha_c"]), float(s["alpha_s"]), float(s["lambda_smooth"]),
+                               float(s.get("g_charb", 1.0)), float(s.get("g_u", 1.0)), float(s.get("g_v", 1.0)),
+                               int(s.get("variant", 0)))
+            keep.append((flow, src, tgt, recon, dflow))
+        lib = _lib.load()
+        need = lib.dofb_warp_loss_workspace_bytes(n, arr)
+        if self.ws is None or self.ws.numel() < need:
+            self.ws = torch.zeros(int(need) + 256, dtype=torch.uint8, device=self.device)
+        base = self.ws.data_ptr()
+        off = (-base) % 256
+        check(lib.dofb_warp_loss(n, arr, base + off, self.ws.numel() - off, _stream()))

@@ -1,0 +1,154 @@
+/*
+ * deepof_b200 -- C ABI of the B200-native deepOF hot path.
+ *
+ * Every entry point takes plain device pointers, sizes and a CUDA stream handle
+ * (cudaStream_t passed as void*; NULL = legacy default stream).  No torch types.
+ * All tensors are NHWC float32 with an explicit row pitch ("ld", in elements)
+ * for the channel dimension, so that a producer can write straight into a
+ * channel slice of a concat buffer (tf.concat, flyingChairsWrapFlow.py:67,78,89,
+ * 100,111, is never materialised).
+ *
+ * The reference (bryanyzhu/deepOF, Python-2/TensorFlow-0.1x) has no FFI of its
+ * own: its "operator interface" is the set of Python call sites listed below.
+ * Each entry point names the reference op group it replaces (paths relative to
+ * the reference checkout).  The Python host side in deepof_b200/ binds these
+ * with ctypes and re-creates the reference's function signatures on top.
+ *
+ * Return value: 0 on success, non-zero on error; dofb_last_error() gives the
+ * message (thread-local).  Kernels are launched asynchronously on `stream`.
+ */
+#ifndef DEEPOF_B200_H
+#define DEEPOF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DOFB_VERSION 100
+
+/* ---- misc -------------------------------------------------------------- */
+int dofb_version(void);
+const char *dofb_last_error(void);
+/* number of kernels this library has launched since the last reset (host counter) */
+long long dofb_launch_count(void);
+void dofb_reset_launch_count(void);
+
+/* ---- pre-processing + image pyramid ------------------------------------ */
+/* Replaces: tf.sub/tf.truediv/tf.nn.local_response_normalization/tf.concat and
+ * the 12 tf.image.resize_bilinear calls of flyingChairsWrapFlow.py:16-31,61-62,
+ * 72-73,83-84,94-95,105-106,116-117.
+ *   src,tgt : [B,H,W,3] BGR 0..255
+ *   x6      : [B,H,W,x6_ld] out, channels 0..2 = (src-mean)/255, 3..5 = (tgt-mean)/255,
+ *             channels 6..x6_ld-1 are zero-filled
+ *   pyr_src/pyr_tgt[s] (s=0..n_scales-1): [B,H>>(s+1),W>>(s+1),3] LRN-normalised,
+ *             decimated (legacy resize_bilinear at an integer ratio == x[::r, ::r]).
+ */
+int dofb_preprocess(const float *src, const float *tgt, const float mean_bgr[3],
+                    int B, int H, int W, float *x6, int x6_ld,
+                    int n_scales, float *const *pyr_src, float *const *pyr_tgt, void *stream);
+
+/* ---- warp + Charbonnier photometric + smoothness loss -------------------- */
+/* Replaces: flyingChairsWrapFlow.loss_interp (flyingChairsWrapFlow.py:752-876,
+ * variant 0 = "A") and flyingChairsWrapFlow_vgg.loss_interp / version1/model/
+ * warpflow.loss_interp (warpflow.py:4-173, variant 1 = "B"), forward AND the
+ * TF-autodiff backward w.r.t. the flow, in one pass. */
+typedef struct dofb_loss_scale {
+    const float *flow;   /* [B,h,w,2] un-scaled network output pr_s              */
+    const float *src;    /* [B,h,w,3] `inputs`  (compared against)               */
+    const float *tgt;    /* [B,h,w,3] `outputs` (gathered from)                  */
+    float *recon;        /* [B,h,w,3] reconstruction, may be NULL                */
+    float *dflow;        /* [B,h,w,2] d(sum)/d(flow), may be NULL (forward only) */
+    float *loss4;        /* [4] {total, Charbonnier_reconstruct, U_loss, V_loss} */
+    int B, h, w;
+    float flow_scale;
+    float epsilon, alpha_c, alpha_s, lambda_smooth;
+    /* upstream gradient coefficients: d(objective)/d{Charbonnier, U_loss, V_loss}.
+     * For objective = weight * total they are {weight, weight*lambda, weight*lambda}. */
+    float g_charb, g_u, g_v;
+    int variant;         /* 0 = A (legacy), 1 = B (clean) */
+} dofb_loss_scale;
+
+/* bytes of scratch needed by dofb_warp_loss for these scales */
+size_t dofb_warp_loss_workspace_bytes(int n_scales, const dofb_loss_scale *scales);
+/* All scales in ONE launch (plus one tiny finalisation handled in-kernel by the
+ * last block); deterministic fixed-order reduction. */
+int dofb_warp_loss(int n_scales, const dofb_loss_scale *scales, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- convolution family (implicit GEMM) ---------------------------------- */
+/* Replaces: slim.conv2d / slim.conv2d_transpose (+BiasAdd +Elu) and their TF
+ * autodiff gradients, flyingChairsWrapFlow.py:31-40,58-113.
+ *
+ * Geometry is that of the *convolution* even for the transposed op:
+ *   conv        : x[B,ih,iw,ci] * w[kh,kw,ci,co] -> y[B,oh,ow,co], TF SAME padding
+ *                 (pad_t, pad_l given explicitly; the rest is implied)
+ *   transposed  : TF conv2d_transpose with w[kh,kw,co_t,ci_t] is the input-gradient
+ *                 of a conv whose ci = co_t and co = ci_t; describe THAT conv here
+ *                 (ih,iw = the large map) and call dofb_conv_dgrad as its forward.
+ */
+typedef struct dofb_conv_geom {
+    int B;
+    int ih, iw, ci;      /* conv input (large side)  */
+    int oh, ow, co;      /* conv output (small side) */
+    int kh, kw, stride, pad_t, pad_l;
+} dofb_conv_geom;
+
+enum { DOFB_ACT_NONE = 0, DOFB_ACT_ELU = 1 };
+enum { DOFB_MATH_FP32 = 0, DOFB_MATH_TF32 = 1 };   /* SIMT FFMA vs tcgen05 kind::tf32 */
+
+/* y = act(conv(x, w) + bias).  x pitch x_ld, y pitch y_ld (elements). */
+int dofb_conv_fwd(const dofb_conv_geom *g, const float *x, int x_ld, const float *w, const float *bias,
+                  float *y, int y_ld, int act, int math, void *stream);
+/* dx (+)= conv_input_gradient(dy, w) [+ bias, act : used when this IS a conv2d_transpose forward]. */
+int dofb_conv_dgrad(const dofb_conv_geom *g, const float *dy, int dy_ld, const float *w, const float *bias,
+                    float *dx, int dx_ld, int act, int accumulate, int math, void *stream);
+/* dw += sum_pixels x (x) dy ; db += sum_pixels dy (db may be NULL).  dw/db must be zeroed by the caller. */
+int dofb_conv_wgrad(const dofb_conv_geom *g, const float *x, int x_ld, const float *dy, int dy_ld,
+                    float *dw, float *db, int math, void *stream);
+/* same contraction but the bias gradient is taken over `x` (the large map): used for
+ * conv2d_transpose, whose bias lives on the large side. */
+int dofb_conv_wgrad_tbias(const dofb_conv_geom *g, const float *x, int x_ld, const float *dy, int dy_ld,
+                          float *dw, float *db_large, int math, void *stream);
+
+/* g[B*h*w, 0..c) *= elu'(y) where y is the ELU OUTPUT (elu' = y>0 ? 1 : y+1). */
+int dofb_elu_bwd(float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c, void *stream);
+
+/* ---- thin heads (N = 2: bandwidth-bound, not tensor-core shapes) ---------- */
+/* pr_s = conv3x3(feat -> 2) linear, flyingChairsWrapFlow.py:58,69,80,91,102,113 */
+int dofb_head_fwd(const float *x, int x_ld, int B, int h, int w, int c, const float *wt /*[3,3,c,2]*/,
+                  const float *bias /*[2]*/, float *pr /*[B,h,w,2]*/, void *stream);
+int dofb_head_dgrad(const float *dpr, int B, int h, int w, int c, const float *wt, float *dx, int dx_ld,
+                    int accumulate, void *stream);
+int dofb_head_wgrad(const float *x, int x_ld, const float *dpr, int B, int h, int w, int c,
+                    float *dwt, float *dbias, void *stream);
+/* up_pr = conv2d_transpose 4x4/2 (2 -> 2) linear, :66,77,88,99,110.  wt [4,4,2,2] = [kh,kw,co,ci] */
+int dofb_uppr_fwd(const float *pr, int B, int h, int w, const float *wt, const float *bias,
+                  float *y /* [B,2h,2w,y_ld] slice */, int y_ld, void *stream);
+int dofb_uppr_bwd(const float *pr, const float *dy, int dy_ld, int B, int h, int w, const float *wt,
+                  float *dpr /* += */, float *dwt /* += */, float *dbias /* += */, void *stream);
+
+/* ---- optimiser ------------------------------------------------------------ */
+/* Replaces: tf.train.AdamOptimizer(lr).minimize (flyingChairsTrain.py:124), 52 ApplyAdam
+ * ops -> one launch over the flat parameter arena.  lr_t = lr*sqrt(1-b2^t)/(1-b1^t) is
+ * computed by the caller;  grad_scale multiplies g first (1/world_size after a sum-allreduce). */
+int dofb_adam(float *theta, const float *g, float *m, float *v, long long n,
+              float lr_t, float beta1, float beta2, float epsilon, float grad_scale, void *stream);
+
+/* ---- metric ---------------------------------------------------------------- */
+/* utils.flow_ee (utils.py:64-68): out[0] = sum sqrt(du^2+dv^2), caller divides by n_pix. */
+int dofb_epe_sum(const float *flow, const float *gt, long long n_pix, double *out, void *stream);
+
+/* ---- FlowNetC correlation (no reference symbol; FlowNet paper definition) --- */
+/* out[b,y,x,(dy_i*D+dx_i)] = (1/C) sum_c f1[b,y,x,c] * f2[b,y+dy,x+dx,c],
+ * dy,dx in {-max_disp, -max_disp+stride2, ..., max_disp}, zero outside the map. */
+int dofb_corr_fwd(const float *f1, const float *f2, int ld, int B, int h, int w, int c, int max_disp, int stride2,
+                  float *out, int out_ld, void *stream);
+int dofb_corr_bwd(const float *f1, const float *f2, int ld, int B, int h, int w, int c, int max_disp, int stride2,
+                  const float *dout, int dout_ld, float *df1, float *df2, int dld, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPOF_B200_H */
