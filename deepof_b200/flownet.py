@@ -133,8 +133,19 @@ class FlowNetS:
         self._alloc()
         self._plan()
         self.warp_loss = ops.WarpLoss(self.device)
+        self.profile = None            # list of (tag, start_event, end_event) when per-launch timing is on
         if seed is not None:
             self.init_params(seed)
+
+    def _k(self, tag, fn, *args, **kw):
+        """Launch one kernel; with self.profile set, bracket it with CUDA events on the launch stream."""
+        if self.profile is None:
+            return fn(*args, **kw)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn(*args, **kw)
+        e1.record()
+        self.profile.append((tag, e0, e1))
 
     # ------------------------------------------------------------------ parameters
     def init_params(self, seed: int = 1):
@@ -219,17 +230,19 @@ class FlowNetS:
         if tuple(source.shape) != (self.B, self.H, self.W, 3) or tuple(target.shape) != (self.B, self.H, self.W, 3):
             raise ops.DeepOFError(f"expected [B={self.B},{self.H},{self.W},3] NHWC inputs, got {tuple(source.shape)} / {tuple(target.shape)}")
         P, mth = self.params, self.math
-        ops.preprocess(source, target, self.mean, self.x6, [self.pyr_src[s] for s in range(1, 7)],
-                       [self.pyr_tgt[s] for s in range(1, 7)])
+        self._k("preprocess", ops.preprocess, source, target, self.mean, self.x6, [self.pyr_src[s] for s in range(1, 7)],
+                [self.pyr_tgt[s] for s in range(1, 7)])
         for L in self.tower:
-            ops.conv_fwd(L["g"], L["x"], P[L["name"] + "/weights"], P[L["name"] + "/biases"], L["y"], ACT_ELU, mth)
+            self._k("conv_fwd:" + L["name"], ops.conv_fwd, L["g"], L["x"], P[L["name"] + "/weights"], P[L["name"] + "/biases"],
+                    L["y"], ACT_ELU, mth)
         for R in self.refine:
             s = R["s"]
             x, _ = self.feat[s]
-            ops.head_fwd(x, P[f"pr{s}/weights"], P[f"pr{s}/biases"], self.pr[s])
-            ops.conv_dgrad(R["g"], x, P[R["up"] + "/weights"], P[R["up"] + "/biases"], R["up_y"], ACT_ELU, False, mth)
-            ops.uppr_fwd(self.pr[s], P[R["uppr"] + "/weights"], P[R["uppr"] + "/biases"], R["pr_y"])
-        ops.head_fwd(self.feat[1][0], P["pr1/weights"], P["pr1/biases"], self.pr[1])
+            self._k(f"head_fwd:pr{s}", ops.head_fwd, x, P[f"pr{s}/weights"], P[f"pr{s}/biases"], self.pr[s])
+            self._k("deconv_fwd:" + R["up"], ops.conv_dgrad, R["g"], x, P[R["up"] + "/weights"], P[R["up"] + "/biases"],
+                    R["up_y"], ACT_ELU, False, mth)
+            self._k("uppr_fwd:" + R["uppr"], ops.uppr_fwd, self.pr[s], P[R["uppr"] + "/weights"], P[R["uppr"] + "/biases"], R["pr_y"])
+        self._k("head_fwd:pr1", ops.head_fwd, self.feat[1][0], P["pr1/weights"], P["pr1/biases"], self.pr[1])
         lw = [float(v) for v in loss_weight]
         self.loss_weight = lw
         hp = self.hyper
@@ -242,7 +255,7 @@ class FlowNetS:
                                alpha_c=hp["alpha_c"], alpha_s=hp["alpha_s"], lambda_smooth=hp["lambda_smooth"],
                                g_charb=wgt, g_u=wgt * hp["lambda_smooth"], g_v=wgt * hp["lambda_smooth"],
                                variant=self.variant))
-        self.warp_loss(scales)
+        self._k("warp_loss", self.warp_loss, scales)
 
     def outputs(self):
         """(losses, flows_all, prev1) exactly as flowNet returns them (flyingChairsWrapFlow.py:126-129)."""
@@ -258,37 +271,41 @@ class FlowNetS:
     # ------------------------------------------------------------------ backward
     def backward(self):
         P, G, mth = self.params, self.grads, self.math
-        self.grad.zero_()
+        self._k("zero_grad", self.grad.zero_)
         # refinement part, finest scale first (each pr_s gradient is complete when its scale is reached)
         x1, dx1 = self.feat[1]
-        ops.head_wgrad(x1, self.dpr[1], G["pr1/weights"], G["pr1/biases"])
-        ops.head_dgrad(self.dpr[1], P["pr1/weights"], dx1, accumulate=False)
+        self._k("head_wgrad:pr1", ops.head_wgrad, x1, self.dpr[1], G["pr1/weights"], G["pr1/biases"])
+        self._k("head_dgrad:pr1", ops.head_dgrad, self.dpr[1], P["pr1/weights"], dx1, accumulate=False)
         for R in reversed(self.refine):                      # s = 2,3,4,5,6
             s = R["s"]
             x, dx = self.feat[s]
             # up_pr (linear): dpr_s += ..., dW, db
-            ops.uppr_bwd(self.pr[s], R["pr_dy"], P[R["uppr"] + "/weights"], self.dpr[s], G[R["uppr"] + "/weights"],
-                         G[R["uppr"] + "/biases"])
+            self._k("uppr_bwd:" + R["uppr"], ops.uppr_bwd, self.pr[s], R["pr_dy"], P[R["uppr"] + "/weights"], self.dpr[s],
+                    G[R["uppr"] + "/weights"], G[R["uppr"] + "/biases"])
             # upconv (ELU): gradient through the activation, then weight / bias / input gradients
-            ops.elu_bwd(R["up_dy"], R["up_y"])
-            ops.conv_wgrad(R["g"], R["up_dy"], x, G[R["up"] + "/weights"], G[R["up"] + "/biases"], mth, bias_on_large=True)
-            ops.conv_fwd(R["g"], R["up_dy"], P[R["up"] + "/weights"], None, dx, ACT_NONE, mth)     # first writer of d feat_s
+            self._k("elu_bwd:" + R["up"], ops.elu_bwd, R["up_dy"], R["up_y"])
+            self._k("deconv_wgrad:" + R["up"], ops.conv_wgrad, R["g"], R["up_dy"], x, G[R["up"] + "/weights"],
+                    G[R["up"] + "/biases"], mth, bias_on_large=True)
+            self._k("deconv_dgrad:" + R["up"], ops.conv_fwd, R["g"], R["up_dy"], P[R["up"] + "/weights"], None, dx, ACT_NONE,
+                    mth)                                                   # first writer of d feat_s
             # pr_s head
-            ops.head_wgrad(x, self.dpr[s], G[f"pr{s}/weights"], G[f"pr{s}/biases"])
-            ops.head_dgrad(self.dpr[s], P[f"pr{s}/weights"], dx, accumulate=True)
+            self._k(f"head_wgrad:pr{s}", ops.head_wgrad, x, self.dpr[s], G[f"pr{s}/weights"], G[f"pr{s}/biases"])
+            self._k(f"head_dgrad:pr{s}", ops.head_dgrad, self.dpr[s], P[f"pr{s}/weights"], dx, accumulate=True)
         # contracting tower, top down
         for L in reversed(self.tower):
-            ops.elu_bwd(L["dy"], L["y"])
-            ops.conv_wgrad(L["g"], L["x"], L["dy"], G[L["name"] + "/weights"], G[L["name"] + "/biases"], mth)
+            self._k("elu_bwd:" + L["name"], ops.elu_bwd, L["dy"], L["y"])
+            self._k("conv_wgrad:" + L["name"], ops.conv_wgrad, L["g"], L["x"], L["dy"], G[L["name"] + "/weights"],
+                    G[L["name"] + "/biases"], mth)
             if L["dx"] is not None:
-                ops.conv_dgrad(L["g"], L["dy"], P[L["name"] + "/weights"], None, L["dx"], ACT_NONE, L["acc"], mth)
+                self._k("conv_dgrad:" + L["name"], ops.conv_dgrad, L["g"], L["dy"], P[L["name"] + "/weights"], None, L["dx"],
+                        ACT_NONE, L["acc"], mth)
 
     # ------------------------------------------------------------------ optimiser
     def adam_step(self, lr: float, grad_scale: float = 1.0, beta1=0.9, beta2=0.999, eps=1e-8):
         """TF-form Adam over the flat arena (flyingChairsTrain.py:124)."""
         self.t += 1
         lr_t = lr * math.sqrt(1.0 - beta2 ** self.t) / (1.0 - beta1 ** self.t)
-        ops.adam(self.theta, self.grad, self.m, self.v, lr_t, beta1, beta2, eps, grad_scale)
+        self._k("adam", ops.adam, self.theta, self.grad, self.m, self.v, lr_t, beta1, beta2, eps, grad_scale)
 
     def train_step(self, source, target, loss_weight=LOSS_WEIGHTS, lr: float = 1.6e-5, allreduce=None):
         """One ``train_op.run(feed_dict)`` (flyingChairsTrain.py:178): forward, backward, Adam."""

@@ -1,0 +1,164 @@
+"""GPU parity of the whole FlowNetS step against the CPU oracle + golden fixtures + size-independent properties."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import flownet_s as fs, adam as oadam, synth, metrics  # noqa: E402
+
+KEYS = ("total", "Charbonnier_reconstruct", "U_loss", "V_loss")
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+@pytest.fixture(scope="module")
+def small_case():
+    from deepof_b200.flownet import FlowNetS
+    B, H, W = 2, 192, 256
+    src, tgt, gt = synth.make_pairs(B, H, W, seed=5)
+    params = fs.init_params(seed=1)
+    total, grads, losses, flows_all, prev1 = fs.loss_and_grads(params, src, tgt)
+    eng = FlowNetS(B, H, W, seed=None)
+    eng.load_params(params)
+    eng.forward(src.cuda(), tgt.cuda(), fs.LOSS_WEIGHTS, with_grad=True)
+    eng.backward()
+    torch.cuda.synchronize()
+    return dict(eng=eng, params=params, total=total, grads=grads, losses=losses, flows_all=flows_all, prev1=prev1, src=src, tgt=tgt)
+
+
+def test_forward_losses_flows_recon(small_case):
+    c = small_case
+    eng = c["eng"]
+    want = torch.tensor([[l[k].item() for k in KEYS] for l in c["losses"]])
+    assert torch.allclose(eng.loss4.cpu(), want, rtol=5e-5, atol=1e-6), (eng.loss4.cpu(), want)
+    losses, flows_all, prev1 = eng.outputs()
+    for s in range(6):
+        # per-pixel flow L1 (pixels at that scale); fp32 both sides
+        assert (flows_all[s].cpu() - c["flows_all"][s].detach()).abs().max() < 2e-4, s
+    assert (prev1.cpu() - c["prev1"].detach()).abs().max() < 1e-4
+    assert abs(eng.total_loss().item() - c["total"].item()) < 5e-5 * abs(c["total"].item())
+    assert set(losses[0]) == set(KEYS)
+
+
+def test_all_52_gradients(small_case):
+    c = small_case
+    eng = c["eng"]
+    worst = 0.0
+    for name, gref in c["grads"].items():
+        r = rel(eng.grads[name], gref)
+        worst = max(worst, r)
+        assert r < 2e-3, (name, r)          # long fp32 reductions in different orders (atomics on the device)
+    print("worst relative gradient error", worst)
+
+
+def test_two_adam_steps_track_the_oracle(small_case):
+    from deepof_b200.flownet import FlowNetS
+    c = small_case
+    B, H, W = 2, 192, 256
+    params = {k: v.clone() for k, v in c["params"].items()}
+    opt = oadam.TFAdam(params)
+    eng = FlowNetS(B, H, W, seed=None)
+    eng.load_params(params)
+    for it in range(2):
+        _t, grads, *_ = fs.loss_and_grads(params, c["src"], c["tgt"])
+        opt.step(grads, 1.6e-5)
+        eng.train_step(c["src"].cuda(), c["tgt"].cuda(), fs.LOSS_WEIGHTS, 1.6e-5)
+    lr = 1.6e-5
+    for name in params:
+        # Adam's first steps move every weight by ~lr whatever the gradient's size, so a weight whose gradient is
+        # ~0 takes the sign of rounding noise and may differ by 2*lr per step.  Compare in units of lr: (almost)
+        # all weights must agree closely, none may differ by more than the 2*lr*steps bound.
+        d = (eng.params[name].cpu() - params[name]).abs()
+        assert d.max().item() <= 2 * lr * 2 + 1e-7, (name, d.max().item())
+        assert (d > 0.1 * lr).float().mean().item() < 2e-3, (name, (d > 0.1 * lr).float().mean().item())
+        assert d.mean().item() < 0.02 * lr, (name, d.mean().item())
+
+
+def test_golden_fixture(golden_dir):
+    from deepof_b200.flownet import FlowNetS
+    z = np.load(golden_dir / "flownet_s_192x256.npz")
+    src = torch.from_numpy(z["src_u8"].astype(np.float32)).cuda()
+    tgt = torch.from_numpy(z["tgt_u8"].astype(np.float32)).cuda()
+    eng = FlowNetS(1, 192, 256, seed=1)                  # product initialiser == oracle initialiser (CPU test pins it)
+    eng.forward(src, tgt, fs.LOSS_WEIGHTS, with_grad=True)
+    eng.backward()
+    assert np.allclose(eng.loss4.cpu().numpy(), z["loss4"], rtol=5e-5, atol=1e-6)
+    assert np.abs(eng.pr[1].cpu().numpy() * 10.0 - z["flow1"]).max() < 2e-4
+    assert np.abs(eng.pr[3].cpu().numpy() * 2.5 - z["flow3"]).max() < 2e-4
+    assert np.abs(eng.pr[6].cpu().numpy() * 0.3125 - z["flow6"]).max() < 2e-4
+    norms = np.array([eng.grads[str(n)].double().norm().item() for n in z["grad_names"]])
+    assert np.allclose(norms, z["grad_norm"], rtol=2e-3)
+    before = {k: v.clone() for k, v in eng.params.items()}
+    eng.adam_step(1.6e-5)
+    delta = np.array([(eng.params[str(n)] - before[str(n)]).double().norm().item() for n in z["grad_names"]])
+    assert np.allclose(delta, z["delta_norm"], rtol=2e-2, atol=1e-9)
+
+
+def test_batch_replication_invariance_full_size():
+    """Size-independent property at the BASELINE size: the loss normaliser contains B, so replicating one pair
+    B times leaves every loss and every gradient unchanged (checked 384x512, B=4 vs B=1)."""
+    from deepof_b200.flownet import FlowNetS
+    src, tgt, _ = synth.make_pairs(1, 384, 512, seed=21)
+    e1 = FlowNetS(1, 384, 512, seed=1)
+    e4 = FlowNetS(4, 384, 512, seed=1)
+    e1.forward(src.cuda(), tgt.cuda()); e1.backward()
+    e4.forward(src.repeat(4, 1, 1, 1).cuda(), tgt.repeat(4, 1, 1, 1).cuda()); e4.backward()
+    assert torch.allclose(e1.loss4, e4.loss4, rtol=1e-5, atol=1e-7)
+    assert torch.equal(e1.pr[1][0], e4.pr[1][3])         # same pair, same kernel arithmetic: bit exact per sample
+    for name in e1.grads:
+        assert rel(e4.grads[name], e1.grads[name]) < 2e-3, name
+    # determinism of the loss (fixed-order reduction)
+    l_a = e4.loss4.clone()
+    e4.forward(src.repeat(4, 1, 1, 1).cuda(), tgt.repeat(4, 1, 1, 1).cuda())
+    assert torch.equal(l_a, e4.loss4)
+
+
+def test_epe_within_tolerance_of_cpu_forward():
+    """north_star: EPE on a held-out synthetic batch within 1e-3 of the reference-semantics fp32 CPU forward."""
+    from deepof_b200.flownet import FlowNetS
+    from deepof_b200 import ops
+    B, H, W = 2, 384, 512
+    src, tgt, gt = synth.make_pairs(B, H, W, seed=1234)
+    params = fs.init_params(seed=1)
+    with torch.no_grad():
+        _l, flows_all, _p, _t = fs.forward(params, src, tgt)
+    ref_flow = metrics.eval_flow(flows_all[0], H, W)
+    epe_ref = metrics.flow_ee(ref_flow, gt).item()
+    eng = FlowNetS(B, H, W, seed=1)
+    eng.forward(src.cuda(), tgt.cuda(), with_grad=False)
+    _losses, fa, _prev = eng.outputs()
+    dev_flow = metrics.eval_flow(fa[0].cpu(), H, W)
+    epe_dev = metrics.flow_ee(dev_flow, gt).item()
+    l1 = (fa[0].cpu() - flows_all[0]).abs().mean().item()
+    print(f"EPE cpu={epe_ref:.6f} cuda={epe_dev:.6f} mean|flow L1|={l1:.2e}")
+    assert abs(epe_dev - epe_ref) < 1e-3
+    assert l1 < 1e-4
+    # the on-device metric kernel agrees with utils.flow_ee
+    out = torch.zeros(1, dtype=torch.float64, device="cuda")
+    ops.epe_sum(dev_flow.cuda().contiguous(), gt.cuda().contiguous(), out)
+    assert abs(out.item() / (B * H * W) - epe_dev) < 1e-5
+
+
+def test_train_step_reference_feed_dict_contract():
+    from deepof_b200.flyingChairsTrain import TrainStep, WEIGHT_L
+    src, tgt, _ = synth.make_pairs(1, 192, 256, seed=2)
+    step = TrainStep(1, (192, 256))
+    feed = {"source_img": src.numpy(), "target_img": tgt.numpy(), "loss_weight": WEIGHT_L, "learning_rate": 1.6e-5}
+    losses0, flows0, sum0 = step.fetch(feed)
+    for _ in range(3):
+        step.run(feed)
+    losses1, flows1, sum1 = step.fetch(feed)
+    assert len(losses0) == 6 and flows0[0].shape == (1, 96, 128, 2) and np.isfinite(sum1)
+    assert sum1 < sum0                                   # three Adam steps on one batch reduce its loss
+
+
+def test_flownet_functional_signature():
+    from deepof_b200 import flyingChairsWrapFlow as Wf
+    src, tgt, _ = synth.make_pairs(1, 192, 256, seed=2)
+    losses, flows_all, prev1 = Wf.flowNet(src.cuda(), tgt.cuda(), torch.tensor([16., 8, 4, 2, 1, 1]))
+    assert len(losses) == 6 and len(flows_all) == 6 and prev1.shape == (1, 96, 128, 3)
+    assert [tuple(f.shape) for f in flows_all][-1] == (1, 3, 4, 2)
