@@ -54,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             sys.stderr.write("\n".join(log))
             raise RuntimeError(f"nvcc failed on {src}")
     (obj_dir / "ptxas.log").write_text("\n".join(log))
-    cmd = [nvcc, "-shared", "-o", str(LIB), *objs, "-lcudart", "-lcuda"]
+    cmd = [nvcc, "-shared", "-o", str(LIB), *objs, "-lcudart"]
     subprocess.run(cmd, check=True)
     stamp_file.write_text(stamp)
     if verbose:

@@ -1,13 +1,537 @@
-// tcgen05 (kind::tf32) implicit-GEMM convolution family -- placeholder until the kernels land.
+// tcgen05 (kind::tf32) implicit-GEMM convolution family for sm_100a (math = DOFB_MATH_TF32).
+//
+//   out[row][n] (+)= sum_{tap, c} A[gather(row, tap)][c] * W(tap, c, n)
+//
+// rows  = output pixels, enumerated as tiles of TW x TH x TN = 128 pixels (one UMMA M=128 tile)
+// A     = NHWC activation, fetched per (tap, 32-channel block) by ONE TMA tiled load straight from
+//         the feature map: the box {32 ch, TW, TH, TN} lands in shared memory as 128 rows x 128 B,
+//         which is exactly the K-major SWIZZLE_128B operand layout of tcgen05.mma; TF-SAME padding
+//         is the TMA out-of-bounds zero fill (asymmetric pads are just a coordinate offset), so
+//         there is no im2col buffer and no padding kernel.  Stride-2 convs view the map as
+//         [N, H/2, 2, W/2, 2*C] (rank-5 map) so that the strided gather is again a dense box.
+// W     = weights re-packed per call to K-major [N][taps*Cpad] (zero padded), one TMA 2-D load.
+// acc   = fp32 in TMEM (BN columns); epilogue warps read it with tcgen05.ld, fuse bias + ELU
+//         (+ accumulate) and store NHWC with the caller's pitch (concat slices written in place).
+//
+// Warp roles (192 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 TMA producer,
+// warp 5 TMEM allocator + single-thread MMA issuer.  mbarrier ring of STAGES smem slots.
 #include "common.cuh"
+#include <cuda.h>
+#include <unordered_map>
+#include <mutex>
+#include <vector>
+
 namespace dofb {
-int tc_conv_fwd(const dofb_conv_geom *, const float *, int, const float *, const float *, float *, int, int, cudaStream_t) {
-    return set_error("dofb_conv_fwd: math=TF32 not available in this build");
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-int tc_conv_dgrad(const dofb_conv_geom *, const float *, int, const float *, const float *, float *, int, int, int, cudaStream_t) {
-    return set_error("dofb_conv_dgrad: math=TF32 not available in this build");
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem desc] * B[smem desc], tf32 inputs, fp32 accumulate, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i <-> TMEM lane base+i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major / SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major)
+//   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B between 8-row groups) | [46,48) version = 1
+//   [61,64) layout type: 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_desc_k128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b_format TF32 [7,10)/[10,13)=2,
+// a/b major K (bits 15/16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// gather-GEMM kernel
+// ------------------------------------------------------------------------------------------------
+constexpr int TC_BM = 128, TC_BK = 32, TC_THREADS = 192, TC_MAX_TAPS = 49;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
+
+struct TapInfo {
+    short oy, ox;      // unit mode: source = (iy + oy, ix + ox); parity mode: quotient offsets (qy, qx)
+    short py, px;      // parity mode: row / column parity
+    int wk;            // first K column of this tap in the packed weight matrix
+};
+
+struct TcParams {
+    float *out; int out_ld;
+    const float *bias;
+    int n_valid;                 // output channels
+    int rh, rw;                  // output map
+    int y0, x0, rstep;           // output pixel = (y0 + rstep*iy, x0 + rstep*ix)
+    int B, cnt_y, cnt_x;         // row sub-grid
+    int TW, TH, TN, tiles_x, tiles_y;
+    int a_coff;                  // channel offset of the A slab inside its buffer
+    int a_ld;                    // pitch of A (parity mode: px*a_ld + c)
+    int ncb;                     // 32-channel blocks per tap
+    int ntaps;
+    int parity;                  // 0: rank-4 unit-stride map, 1: rank-5 stride-2 map
+    int act, accumulate;
+    TapInfo taps[TC_MAX_TAPS];
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      const __grid_constant__ TcParams P) {
+    constexpr int B_BYTES = BN * TC_BK * 4;
+    constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+    constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *accum_bar = empty_bar + STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // ---- tile coordinates ----
+    const int tile = blockIdx.x;
+    const int tx = tile % P.tiles_x, ty = (tile / P.tiles_x) % P.tiles_y, tn = tile / (P.tiles_x * P.tiles_y);
+    const int ix0 = tx * P.TW, iy0 = ty * P.TH, in0 = tn * P.TN;
+    const int n0 = blockIdx.y * BN;
+    const int kiters = P.ntaps * P.ncb;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4 && lane == 0) { prefetch_tmap(&map_a); prefetch_tmap(&map_b); }
+    if (warp == 5) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int it = 0; it < kiters; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                const int t = it / P.ncb, cb = it - t * P.ncb;
+                const TapInfo ti = P.taps[t];
+                uint8_t *sa = smem + s * STAGE_BYTES;
+                uint8_t *sb = sa + TC_A_BYTES;
+                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                if (P.parity)
+                    tma_load_5d(sa, &map_a, &full_bar[s], ti.px * P.a_ld + P.a_coff + cb * TC_BK, ix0 + ti.ox, ti.py, iy0 + ti.oy, in0);
+                else
+                    tma_load_4d(sa, &map_a, &full_bar[s], P.a_coff + cb * TC_BK, ix0 + ti.ox, iy0 + ti.oy, in0);
+                tma_load_2d(sb, &map_b, &full_bar[s], ti.wk + cb * TC_BK, n0);
+            }
+        }
+    } else if (warp == 5) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN);
+            for (int it = 0; it < kiters; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                const uint64_t da = make_desc_k128(sa), db = make_desc_k128(sa + TC_A_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 8; ++k)     // UMMA_K = 8 for tf32: advance 32 B inside the 128 B swizzle row
+                    umma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) != 0);
+                umma_commit(&empty_bar[s]);             // frees the smem slot when these MMAs retire
+            }
+            umma_commit(accum_bar);                     // accumulator complete
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> bias/ELU -> NHWC global =====
+        const int r = warp * 32 + lane;                 // row of the tile == TMEM lane
+        const int ix = ix0 + r % P.TW, iy = iy0 + (r / P.TW) % P.TH, nn = in0 + r / (P.TW * P.TH);
+        const bool row_ok = ix < P.cnt_x && iy < P.cnt_y && nn < P.B;
+        float *orow = P.out + (((long long)nn * P.rh + P.y0 + iy * P.rstep) * P.rw + P.x0 + ix * P.rstep) * P.out_ld;
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const bool vec_ok = ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0) && (P.out_ld % 4 == 0);
+#pragma unroll 1
+        for (int j = 0; j < BN / 32 + (BN < 32 ? 1 : 0); ++j) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * 32), v);
+            if (!row_ok) continue;
+            const int cbase = n0 + j * 32;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int col = cbase + q * 4;
+                if (col >= P.n_valid) break;
+                float o[4] = {v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (col + e < P.n_valid) {
+                        if (P.bias) o[e] += __ldg(P.bias + col + e);
+                        if (P.act == DOFB_ACT_ELU) o[e] = elu_f(o[e]);
+                    }
+                }
+                if (vec_ok && col + 3 < P.n_valid) {
+                    float4 *dst = reinterpret_cast<float4 *>(orow + col);
+                    if (P.accumulate) {
+                        const float4 old = *dst;
+                        o[0] += old.x; o[1] += old.y; o[2] += old.z; o[3] += old.w;
+                    }
+                    *dst = make_float4(o[0], o[1], o[2], o[3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (col + e < P.n_valid) orow[col + e] = P.accumulate ? orow[col + e] + o[e] : o[e];
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight re-packing: canonical TF layout [tap][ci][co] -> K-major [N][taps*Cpad]
+//   fwd  (contract over ci): Wp[co][tap*Cpad + ci] = W[tap][ci][co]
+//   bwd  (contract over co): Wp[ci][tap*Cpad + co] = W[tap][ci][co]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restrict__ W, float *__restrict__ Wp, int taps, int ci, int co,
+                                                           int cpad, int contract_ci) {
+    const int n_rows = contract_ci ? co : ci;
+    const int kc = contract_ci ? ci : co;
+    const long long total = (long long)n_rows * taps * cpad;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cpad);
+        const int t = (int)((i / cpad) % taps);
+        const int n = (int)(i / ((long long)cpad * taps));
+        float v = 0.f;
+        if (c < kc) v = contract_ci ? __ldg(W + ((long long)t * ci + c) * co + n) : __ldg(W + ((long long)t * ci + n) * co + c);
+        Wp[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor maps, caches, launch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+static int make_map(CUtensorMap *m, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes, const uint32_t *box) {
+    PFN_encodeTiled enc = get_encode();
+    DOFB_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gd[5], gs[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), gd, gs, bx, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DOFB_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d (rank %d, dims %llu %llu %llu ..., box %u %u %u ...)", (int)r,
+                   rank, (unsigned long long)dims[0], (unsigned long long)dims[1], rank > 2 ? (unsigned long long)dims[2] : 0ull,
+                   box[0], box[1], rank > 2 ? box[2] : 0u);
+    return 0;
+}
+
+// packed-weight scratch, keyed by (canonical weight pointer, orientation); grown on demand, never freed
+struct PackKey {
+    const void *w; int orient;
+    bool operator==(const PackKey &o) const { return w == o.w && orient == o.orient; }
+};
+struct PackKeyHash {
+    size_t operator()(const PackKey &k) const { return std::hash<const void *>()(k.w) ^ (size_t)(k.orient * 0x9e3779b9u); }
+};
+static std::unordered_map<PackKey, std::pair<float *, size_t>, PackKeyHash> g_pack;
+static std::mutex g_pack_mu;
+
+static int get_pack_buffer(const void *w, int orient, size_t floats, float **out) {
+    std::lock_guard<std::mutex> lk(g_pack_mu);
+    auto it = g_pack.find({w, orient});
+    if (it != g_pack.end() && it->second.second >= floats) { *out = it->second.first; return 0; }
+    float *p = nullptr;
+    DOFB_CUDA_OK(cudaMalloc(&p, floats * sizeof(float)));
+    if (it != g_pack.end()) { cudaFree(it->second.first); it->second = {p, floats}; }
+    else g_pack[{w, orient}] = {p, floats};
+    *out = p;
+    return 0;
+}
+
+static inline int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+static void choose_tile(int cnt_y, int cnt_x, int &TW, int &TH, int &TN) {
+    TW = pow2_ceil(cnt_x) < 16 ? pow2_ceil(cnt_x) : 16;
+    int th_max = TC_BM / TW;
+    TH = pow2_ceil(cnt_y) < th_max ? pow2_ceil(cnt_y) : th_max;
+    // prefer a tile height that divides the row count (no wasted MMA rows)
+    for (int t = TH; t >= 1; t >>= 1)
+        if (cnt_y % t == 0) { TH = t; break; }
+    TN = TC_BM / (TW * TH);
+}
+
+template <int BN, int STAGES>
+static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &P, int tiles, int n_tiles, cudaStream_t st) {
+    constexpr int smem = STAGES * (TC_A_BYTES + BN * TC_BK * 4) + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        DOFB_CUDA_OK(cudaFuncSetAttribute(tc_gather_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    tc_gather_gemm_kernel<BN, STAGES><<<dim3(tiles, n_tiles, 1), TC_THREADS, smem, st>>>(ma, mb, P);
+    DOFB_LAUNCH_OK();
+    return 0;
+}
+
+// One (phase of a) gather-GEMM.  src: the gathered activation buffer description.
+struct GatherSpec {
+    const float *a_base; int a_ld, a_coff, a_c;     // buffer base (16 B aligned), pitch, slab offset, slab channels
+    int ah, aw;                                     // source map
+    const float *w; int w_ci, w_co, taps_h, taps_w; // canonical weights
+    int contract_ci;                                // 1: fwd-type (contract over ci), 0: bwd-type (contract over co)
+    float *out; int out_ld, rh, rw, n_valid;
+    const float *bias; int act, accumulate;
+    int B;
+};
+
+static int run_gather(const GatherSpec &G, const TcParams &Pin, cudaStream_t st) {
+    TcParams P = Pin;
+    const int kc = G.contract_ci ? G.w_ci : G.w_co;
+    const int cpad = (kc + TC_BK - 1) / TC_BK * TC_BK;
+    const int taps_all = G.taps_h * G.taps_w;
+    const int n_rows = G.contract_ci ? G.w_co : G.w_ci;
+    DOFB_CHECK_ARG(G.a_coff % 4 == 0 && G.a_ld % 4 == 0 && aligned16(G.a_base), "tc conv: activation slab must be 16-byte aligned");
+    DOFB_CHECK_ARG(cpad <= G.a_ld, "tc conv: %d channels rounded up to 32 exceed the pitch %d", kc, G.a_ld);
+    // ---- pack weights ----
+    float *wp = nullptr;
+    const size_t wfloats = (size_t)n_rows * taps_all * cpad;
+    if (get_pack_buffer(G.w, G.contract_ci, wfloats, &wp)) return 1;
+    {
+        long long blocks = ((long long)wfloats + 255) / 256;
+        const long long cap = (long long)num_sms() * 8;
+        if (blocks > cap) blocks = cap;
+        pack_weights_kernel<<<(unsigned)blocks, 256, 0, st>>>(G.w, wp, taps_all, G.w_ci, G.w_co, cpad, G.contract_ci);
+        DOFB_LAUNCH_OK();
+    }
+    for (int t = 0; t < P.ntaps; ++t) P.taps[t].wk *= cpad;     // caller stored the canonical tap index
+    P.ncb = cpad / TC_BK;
+    P.a_coff = G.a_coff; P.a_ld = G.a_ld;
+    P.out = G.out; P.out_ld = G.out_ld; P.bias = G.bias; P.n_valid = G.n_valid; P.rh = G.rh; P.rw = G.rw;
+    P.act = G.act; P.accumulate = G.accumulate; P.B = G.B;
+    choose_tile(P.cnt_y, P.cnt_x, P.TW, P.TH, P.TN);
+    P.tiles_x = (P.cnt_x + P.TW - 1) / P.TW;
+    P.tiles_y = (P.cnt_y + P.TH - 1) / P.TH;
+    const int tiles_n = (G.B + P.TN - 1) / P.TN;
+    const int tiles = P.tiles_x * P.tiles_y * tiles_n;
+    // ---- tensor maps ----
+    CUtensorMap ma, mb;
+    if (!P.parity) {
+        const uint64_t dims[4] = {(uint64_t)cpad, (uint64_t)G.aw, (uint64_t)G.ah, (uint64_t)G.B};
+        const uint64_t str[3] = {(uint64_t)G.a_ld * 4, (uint64_t)G.aw * G.a_ld * 4, (uint64_t)G.ah * G.aw * G.a_ld * 4};
+        const uint32_t box[4] = {(uint32_t)TC_BK, (uint32_t)P.TW, (uint32_t)P.TH, (uint32_t)P.TN};
+        if (make_map(&ma, G.a_base, 4, dims, str, box)) return 1;
+    } else {
+        DOFB_CHECK_ARG(G.ah % 2 == 0 && G.aw % 2 == 0, "tc conv: stride-2 gather needs even map sizes (%d x %d)", G.ah, G.aw);
+        const uint64_t dims[5] = {(uint64_t)2 * G.a_ld, (uint64_t)G.aw / 2, 2, (uint64_t)G.ah / 2, (uint64_t)G.B};
+        const uint64_t str[4] = {(uint64_t)2 * G.a_ld * 4, (uint64_t)G.aw * G.a_ld * 4, (uint64_t)2 * G.aw * G.a_ld * 4,
+                                 (uint64_t)G.ah * G.aw * G.a_ld * 4};
+        const uint32_t box[5] = {(uint32_t)TC_BK, (uint32_t)P.TW, 1, (uint32_t)P.TH, (uint32_t)P.TN};
+        if (make_map(&ma, G.a_base, 5, dims, str, box)) return 1;
+    }
+    const int bn = n_rows > 128 ? 256 : (n_rows > 64 ? 128 : (n_rows > 32 ? 64 : 32));
+    {
+        const uint64_t dims[2] = {(uint64_t)taps_all * cpad, (uint64_t)n_rows};
+        const uint64_t str[1] = {(uint64_t)taps_all * cpad * 4};
+        const uint32_t box[2] = {(uint32_t)TC_BK, (uint32_t)bn};
+        if (make_map(&mb, wp, 2, dims, str, box)) return 1;
+    }
+    const int n_tiles = (n_rows + bn - 1) / bn;
+    switch (bn) {
+        case 256: return launch_tc<256, 4>(ma, mb, P, tiles, n_tiles, st);
+        case 128: return launch_tc<128, 6>(ma, mb, P, tiles, n_tiles, st);
+        case 64: return launch_tc<64, 8>(ma, mb, P, tiles, n_tiles, st);
+        default: return launch_tc<32, 8>(ma, mb, P, tiles, n_tiles, st);
+    }
+}
+
+// ---- conv forward (and transposed-conv input gradient): fwd-type gather ----
+int tc_conv_fwd(const dofb_conv_geom *g, const float *x, int x_ld, const float *w, const float *bias, float *y, int y_ld, int act,
+                cudaStream_t st) {
+    DOFB_CHECK_ARG(g && g->kh * g->kw <= TC_MAX_TAPS, "dofb_conv_fwd(tf32): at most %d taps", TC_MAX_TAPS);
+    DOFB_CHECK_ARG(g->stride == 1 || g->stride == 2, "dofb_conv_fwd(tf32): stride must be 1 or 2");
+    // TMA base = the slab pointer itself (16-byte aligned); the 32-channel blocks read round_up(ci,32) channels from it, so
+    // the caller guarantees that those stay inside the pitch row and hold finite values (the engine's pad channels are zero).
+    DOFB_CHECK_ARG(x_ld % 32 == 0 && aligned16(x), "dofb_conv_fwd(tf32): pitch %d must be a multiple of 32 floats and x 16-byte aligned", x_ld);
+    GatherSpec G;
+    G.a_base = x; G.a_ld = x_ld; G.a_coff = 0; G.a_c = g->ci;
+    G.ah = g->ih; G.aw = g->iw;
+    G.w = w; G.w_ci = g->ci; G.w_co = g->co; G.taps_h = g->kh; G.taps_w = g->kw; G.contract_ci = 1;
+    G.out = y; G.out_ld = y_ld; G.rh = g->oh; G.rw = g->ow; G.n_valid = g->co; G.bias = bias; G.act = act; G.accumulate = 0; G.B = g->B;
+    TcParams P;
+    memset(&P, 0, sizeof(P));
+    P.y0 = P.x0 = 0; P.rstep = 1; P.cnt_y = g->oh; P.cnt_x = g->ow;
+    P.parity = g->stride == 2;
+    P.ntaps = g->kh * g->kw;
+    for (int kh = 0; kh < g->kh; ++kh)
+        for (int kw = 0; kw < g->kw; ++kw) {
+            TapInfo &t = P.taps[kh * g->kw + kw];
+            const int dy = kh - g->pad_t, dx = kw - g->pad_l;
+            if (g->stride == 1) { t.oy = (short)dy; t.ox = (short)dx; t.py = t.px = 0; }
+            else {
+                const int py = ((dy % 2) + 2) % 2, px = ((dx % 2) + 2) % 2;
+                t.py = (short)py; t.px = (short)px; t.oy = (short)((dy - py) / 2); t.ox = (short)((dx - px) / 2);
+            }
+            t.wk = kh * g->kw + kw;
+        }
+    return run_gather(G, P, st);
+}
+
+// ---- conv input gradient (and transposed-conv forward): bwd-type gather, one launch per stride phase ----
+int tc_conv_dgrad(const dofb_conv_geom *g, const float *dy, int dy_ld, const float *w, const float *bias, float *dx, int dx_ld, int act,
+                  int accumulate, cudaStream_t st) {
+    DOFB_CHECK_ARG(g && g->kh * g->kw <= TC_MAX_TAPS, "dofb_conv_dgrad(tf32): at most %d taps", TC_MAX_TAPS);
+    DOFB_CHECK_ARG(g->stride == 1 || g->stride == 2, "dofb_conv_dgrad(tf32): stride must be 1 or 2");
+    DOFB_CHECK_ARG(dy_ld % 32 == 0 && aligned16(dy), "dofb_conv_dgrad(tf32): pitch %d must be a multiple of 32 floats and dy 16-byte aligned", dy_ld);
+    GatherSpec G;
+    G.a_base = dy; G.a_ld = dy_ld; G.a_coff = 0; G.a_c = g->co;
+    G.ah = g->oh; G.aw = g->ow;
+    G.w = w; G.w_ci = g->ci; G.w_co = g->co; G.taps_h = g->kh; G.taps_w = g->kw; G.contract_ci = 0;
+    G.out = dx; G.out_ld = dx_ld; G.rh = g->ih; G.rw = g->iw; G.n_valid = g->ci; G.bias = bias; G.act = act; G.accumulate = accumulate;
+    G.B = g->B;
+    const int s = g->stride;
+    for (int py = 0; py < s; ++py)
+        for (int px = 0; px < s; ++px) {
+            TcParams P;
+            memset(&P, 0, sizeof(P));
+            P.rstep = s;
+            P.y0 = ((py - g->pad_t) % s + s) % s;
+            P.x0 = ((px - g->pad_l) % s + s) % s;
+            P.cnt_y = P.y0 < g->ih ? (g->ih - P.y0 + s - 1) / s : 0;
+            P.cnt_x = P.x0 < g->iw ? (g->iw - P.x0 + s - 1) / s : 0;
+            if (P.cnt_y == 0 || P.cnt_x == 0) continue;
+            P.parity = 0;
+            int nt = 0;
+            for (int kh = py; kh < g->kh; kh += s)
+                for (int kw = px; kw < g->kw; kw += s) {
+                    TapInfo &t = P.taps[nt++];
+                    t.oy = (short)((P.y0 + g->pad_t - kh) / s);   // exact: (y0 + pad_t - kh) is a multiple of s in this phase
+                    t.ox = (short)((P.x0 + g->pad_l - kw) / s);
+                    t.py = t.px = 0;
+                    t.wk = kh * g->kw + kw;
+                }
+            P.ntaps = nt;
+            DOFB_CHECK_ARG(nt > 0, "dofb_conv_dgrad(tf32): phase without taps (kernel smaller than the stride)");
+            if (run_gather(G, P, st)) return 1;
+        }
+    return 0;
+}
+
 int tc_conv_wgrad(const dofb_conv_geom *, const float *, int, const float *, int, float *, cudaStream_t) {
-    return set_error("dofb_conv_wgrad: math=TF32 not available in this build");
+    return set_error("dofb_conv_wgrad: math=TF32 weight-gradient kernel not built yet");
 }
+
 }  // namespace dofb

@@ -111,7 +111,7 @@ class FlowNetS:
     """Static-shape FlowNetS engine.  ``math``: 'fp32' (SIMT FFMA, parity grade) or 'tf32' (tcgen05)."""
 
     def __init__(self, batch: int, height: int = 384, width: int = 512, device="cuda", variant: str = "A",
-                 math_mode: str = "fp32", mean=FLYINGCHAIRS_MEAN, hyper=None, seed: int | None = 1):
+                 math_mode: str = "fp32", mean=FLYINGCHAIRS_MEAN, hyper=None, seed: int | None = 1, tc_wgrad: bool = False):
         if height % 64 or width % 64:
             raise ValueError("FlowNetS needs H and W to be multiples of 64 (the reference resizes/pads as well, SURVEY.md 0.5)")
         if not torch.cuda.is_available():
@@ -120,6 +120,9 @@ class FlowNetS:
         self.device = torch.device(device)
         self.variant = {"A": 0, "B": 1}[variant]
         self.math = {"fp32": MATH_FP32, "tf32": MATH_TF32}[math_mode]
+        # per-op math: the tcgen05 path needs 32-float pitches (conv1 reads the 8-float pitched input) and has its own
+        # weight-gradient kernel; anything it does not cover runs on the fp32 SIMT kernels (explicit, per layer).
+        self.math_wgrad = self.math if tc_wgrad else MATH_FP32
         self.mean = tuple(float(m) for m in mean)
         self.hyper = dict(HYPER)
         if hyper:
@@ -234,7 +237,7 @@ class FlowNetS:
                 [self.pyr_tgt[s] for s in range(1, 7)])
         for L in self.tower:
             self._k("conv_fwd:" + L["name"], ops.conv_fwd, L["g"], L["x"], P[L["name"] + "/weights"], P[L["name"] + "/biases"],
-                    L["y"], ACT_ELU, mth)
+                    L["y"], ACT_ELU, mth if L["x"].ld % 32 == 0 else MATH_FP32)
         for R in self.refine:
             s = R["s"]
             x, _ = self.feat[s]
@@ -270,7 +273,7 @@ class FlowNetS:
 
     # ------------------------------------------------------------------ backward
     def backward(self):
-        P, G, mth = self.params, self.grads, self.math
+        P, G, mth, mthw = self.params, self.grads, self.math, self.math_wgrad
         self._k("zero_grad", self.grad.zero_)
         # refinement part, finest scale first (each pr_s gradient is complete when its scale is reached)
         x1, dx1 = self.feat[1]
@@ -285,7 +288,7 @@ class FlowNetS:
             # upconv (ELU): gradient through the activation, then weight / bias / input gradients
             self._k("elu_bwd:" + R["up"], ops.elu_bwd, R["up_dy"], R["up_y"])
             self._k("deconv_wgrad:" + R["up"], ops.conv_wgrad, R["g"], R["up_dy"], x, G[R["up"] + "/weights"],
-                    G[R["up"] + "/biases"], mth, bias_on_large=True)
+                    G[R["up"] + "/biases"], mthw, bias_on_large=True)
             self._k("deconv_dgrad:" + R["up"], ops.conv_fwd, R["g"], R["up_dy"], P[R["up"] + "/weights"], None, dx, ACT_NONE,
                     mth)                                                   # first writer of d feat_s
             # pr_s head
@@ -295,7 +298,7 @@ class FlowNetS:
         for L in reversed(self.tower):
             self._k("elu_bwd:" + L["name"], ops.elu_bwd, L["dy"], L["y"])
             self._k("conv_wgrad:" + L["name"], ops.conv_wgrad, L["g"], L["x"], L["dy"], G[L["name"] + "/weights"],
-                    G[L["name"] + "/biases"], mth)
+                    G[L["name"] + "/biases"], mthw if L["x"].ld % 32 == 0 else MATH_FP32)
             if L["dx"] is not None:
                 self._k("conv_dgrad:" + L["name"], ops.conv_dgrad, L["g"], L["dy"], P[L["name"] + "/weights"], None, L["dx"],
                         ACT_NONE, L["acc"], mth)

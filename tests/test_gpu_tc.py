@@ -1,0 +1,124 @@
+"""tcgen05 (TF32) conv family vs the fp32 SIMT kernels on the same inputs (both on the device), then vs the oracle.
+
+TF32 keeps 10 mantissa bits of each operand and accumulates in fp32: tolerance 3e-3 of the output max-norm."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL = 3e-3
+
+
+def rel(a, b):
+    a, b = a.detach().double(), b.detach().double()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def _buf(B, h, w, ld, c, gen):
+    t = torch.zeros(B, h, w, ld, device="cuda")
+    t[..., :c] = torch.randn(B, h, w, c, generator=gen).cuda()
+    return t
+
+
+FWD_CASES = [
+    # B, H, W, ci, x_ld, co, k, s
+    (2, 24, 32, 64, 128, 128, 5, 2),      # conv2-like, parity gather, asymmetric pad (1,2)
+    (2, 12, 16, 256, 256, 256, 3, 1),     # conv3_2-like
+    (4, 12, 16, 256, 416, 512, 3, 2),     # conv4_1-like: slab of a concat buffer, pad (0,1)
+    (8, 6, 8, 512, 512, 1024, 3, 2),      # conv6_1-like: 3x4 output map
+    (8, 3, 4, 1024, 1024, 1024, 3, 1),    # conv6_2-like
+    (1, 48, 64, 128, 224, 256, 5, 2),     # conv3_1-like
+    (2, 10, 14, 32, 32, 32, 3, 1),        # ragged map, small N
+    (2, 16, 16, 96, 96, 64, 3, 1),
+]
+
+
+@pytest.mark.parametrize("case", FWD_CASES)
+def test_tc_conv_fwd_and_dgrad_match_simt(case):
+    from deepof_b200 import ops
+    B, H, W, ci, x_ld, co, k, s = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = _buf(B, H, W, x_ld, ci, g)
+    w = (torch.randn(k, k, ci, co, generator=g) / math.sqrt(k * k * ci)).cuda()
+    b = (torch.randn(co, generator=g) * 0.1).cuda()
+    geom = ops.conv_geom(B, H, W, ci, co, k, s)
+    y_ld = (co + 31) // 32 * 32 + 32
+    y0 = torch.zeros(B, geom.oh, geom.ow, y_ld, device="cuda")
+    y1 = torch.zeros_like(y0)
+    ops.conv_fwd(geom, ops.Slab(x, 0, ci), w, b, ops.Slab(y0, 32, co), ops.ACT_ELU, ops.MATH_FP32)
+    ops.conv_fwd(geom, ops.Slab(x, 0, ci), w, b, ops.Slab(y1, 32, co), ops.ACT_ELU, ops.MATH_TF32)
+    torch.cuda.synchronize()
+    assert rel(y1, y0) < TOL
+    assert float(y1[..., :32].abs().max()) == 0.0
+    # input gradient
+    dy = _buf(B, geom.oh, geom.ow, (co + 31) // 32 * 32, co, g)
+    d0 = torch.full((B, H, W, x_ld), 0.25, device="cuda")
+    d1 = torch.full((B, H, W, x_ld), 0.25, device="cuda")
+    for acc in (True, False):
+        ops.conv_dgrad(geom, ops.Slab(dy, 0, co), w, None, ops.Slab(d0, 0, ci), ops.ACT_NONE, acc, ops.MATH_FP32)
+        ops.conv_dgrad(geom, ops.Slab(dy, 0, co), w, None, ops.Slab(d1, 0, ci), ops.ACT_NONE, acc, ops.MATH_TF32)
+        torch.cuda.synchronize()
+        assert rel(d1[..., :ci], d0[..., :ci]) < TOL, acc
+
+
+DECONV_CASES = [
+    # B, h, w, cfeat, feat_ld, upc
+    (2, 6, 8, 1024, 1024, 512),
+    (2, 12, 16, 1026, 1056, 256),
+    (1, 24, 32, 770, 800, 128),
+    (1, 48, 64, 386, 416, 64),
+    (2, 24, 32, 194, 224, 32),
+]
+
+
+@pytest.mark.parametrize("case", DECONV_CASES)
+def test_tc_deconv_fwd_and_dgrad_match_simt(case):
+    from deepof_b200 import ops
+    B, h, w, cfeat, fld, upc = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = _buf(B, h, w, fld, cfeat, g)
+    wt = (torch.randn(4, 4, upc, cfeat, generator=g) / math.sqrt(4 * cfeat)).cuda()
+    b = (torch.randn(upc, generator=g) * 0.1).cuda()
+    geom = ops.conv_geom(B, 2 * h, 2 * w, upc, cfeat, 4, 2)
+    y0 = torch.zeros(B, 2 * h, 2 * w, upc + 64, device="cuda")
+    y1 = torch.zeros_like(y0)
+    ops.conv_dgrad(geom, ops.Slab(x, 0, cfeat), wt, b, ops.Slab(y0, 32, upc), ops.ACT_ELU, False, ops.MATH_FP32)
+    ops.conv_dgrad(geom, ops.Slab(x, 0, cfeat), wt, b, ops.Slab(y1, 32, upc), ops.ACT_ELU, False, ops.MATH_TF32)
+    torch.cuda.synchronize()
+    assert rel(y1, y0) < TOL
+    dy = _buf(B, 2 * h, 2 * w, (upc + 31) // 32 * 32, upc, g)
+    d0 = torch.zeros(B, h, w, fld, device="cuda")
+    d1 = torch.zeros(B, h, w, fld, device="cuda")
+    ops.conv_fwd(geom, ops.Slab(dy, 0, upc), wt, None, ops.Slab(d0, 0, cfeat), ops.ACT_NONE, ops.MATH_FP32)
+    ops.conv_fwd(geom, ops.Slab(dy, 0, upc), wt, None, ops.Slab(d1, 0, cfeat), ops.ACT_NONE, ops.MATH_TF32)
+    torch.cuda.synchronize()
+    assert rel(d1[..., :cfeat], d0[..., :cfeat]) < TOL
+
+
+def test_tf32_engine_tracks_fp32_engine_and_oracle_epe():
+    """Whole step in TF32 mode: flows within the stated tolerance of the fp32 device path and EPE within 1e-3 of the CPU oracle."""
+    from deepof_b200.flownet import FlowNetS
+    from oracle import flownet_s as fs, synth, metrics
+    B, H, W = 2, 384, 512
+    src, tgt, gt = synth.make_pairs(B, H, W, seed=1234)
+    e32 = FlowNetS(B, H, W, seed=1, math_mode="fp32")
+    etf = FlowNetS(B, H, W, seed=1, math_mode="tf32")
+    for e in (e32, etf):
+        e.forward(src.cuda(), tgt.cuda())
+        e.backward()
+    torch.cuda.synchronize()
+    l1 = (etf.pr[1] - e32.pr[1]).abs().mean().item() * 10.0
+    mx = (etf.pr[1] - e32.pr[1]).abs().max().item() * 10.0
+    epe32 = metrics.flow_ee(metrics.eval_flow(e32.pr[1].cpu() * 10.0, H, W), gt).item()
+    epetf = metrics.flow_ee(metrics.eval_flow(etf.pr[1].cpu() * 10.0, H, W), gt).item()
+    print(f"tf32 vs fp32: mean|dflow1|={l1:.3e} max={mx:.3e} EPE fp32={epe32:.6f} tf32={epetf:.6f}")
+    assert abs(epetf - epe32) < 1e-3
+    assert torch.allclose(etf.loss4, e32.loss4, rtol=5e-3, atol=1e-4)
+    worst = 0.0
+    for name in e32.grads:
+        r = rel(etf.grads[name], e32.grads[name])
+        worst = max(worst, r)
+        assert r < 5e-2, (name, r)
+    print("worst tf32 gradient deviation (max-norm relative)", worst)
