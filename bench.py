@@ -190,7 +190,7 @@ def run_ours(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     lib = _lib.load()
-    step = TrainStep(B, (H, W), device=dev, math_mode=args.math, distributed=world > 1)
+    step = TrainStep(B, (H, W), device=dev, math_mode=args.math, distributed=world > 1, tc_wgrad=(args.math == "tf32"))
     eng = step.engine
     # two different synthetic batches per rank, alternated (working set per step ~3 GB >> 126 MB L2)
     batches = []

@@ -530,8 +530,237 @@ int tc_conv_dgrad(const dofb_conv_geom *g, const float *dy, int dy_ld, const flo
     return 0;
 }
 
-int tc_conv_wgrad(const dofb_conv_geom *, const float *, int, const float *, int, float *, cudaStream_t) {
-    return set_error("dofb_conv_wgrad: math=TF32 weight-gradient kernel not built yet");
+// ------------------------------------------------------------------------------------------------
+// weight gradient:  dW[tap][ci][co] += sum_{pixels} X[gather(pixel, tap)][ci] * DY[pixel][co]
+// GEMM with K = pixels.  Both operands are "MN-major" (channels contiguous, K strided), which tcgen05
+// takes directly through MN-major SWIZZLE_128B descriptors: every 32-channel column block of a
+// 32-pixel tile is one TMA box {32 ch, TW, TH, TN} = 32 rows x 128 B; the blocks of one operand sit
+// LBO = 4 KB apart, 8-pixel groups SBO = 1 KB apart.  Split-K over CTAs, fp32 atomics into dW.
+// `swap` puts DY on the M side (used when ci < 128 <= co so that no MMA rows are wasted).
+// ------------------------------------------------------------------------------------------------
+constexpr int WG_BKP = 32;                    // pixels per pipeline stage
+constexpr int WG_REGION = WG_BKP * 128;       // bytes of one 32-channel column block
+
+struct WgParams {
+    float *dW; int CI, CO;
+    int swap;
+    int m_valid, n_valid;
+    int TW, TH, TN, tiles_x, tiles_y, tiles_total, tiles_per_split;
+    int n_mblk, n_nblk;
+    int parity, x_ld;
+    int ntaps;
+    TapInfo taps[TC_MAX_TAPS];               // wk = canonical tap index (kh*KW + kw)
+};
+
+__device__ __forceinline__ uint64_t make_desc_mn128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(WG_REGION >> 4) << 16;    // leading byte offset: next 32-channel block
+    d |= (uint64_t)(1024 >> 4) << 32;         // stride byte offset: next 8-pixel group
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) {
+    return make_idesc_tf32(M, N) | (1u << 15) | (1u << 16);     // A and B MN-major
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy,
+                const __grid_constant__ WgParams P) {
+    constexpr int A_BYTES = 4 * WG_REGION, B_BYTES = (BN / 32) * WG_REGION;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *accum_bar = empty_bar + STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int item = blockIdx.y;
+    const int nblk = item % P.n_nblk, mblk = (item / P.n_nblk) % P.n_mblk, tapi = item / (P.n_nblk * P.n_mblk);
+    const int m0 = mblk * TC_BM, n0 = nblk * BN;
+    const int t_begin = blockIdx.x * P.tiles_per_split;
+    const int t_end = min(P.tiles_total, t_begin + P.tiles_per_split);
+    const int kiters = t_end - t_begin;
+    if (kiters <= 0) return;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4 && lane == 0) { prefetch_tmap(&map_x); prefetch_tmap(&map_dy); }
+    if (warp == 5) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const TapInfo ti = P.taps[tapi];
+
+    if (warp == 4) {
+        if (lane == 0) {
+            // channel origin of the X / DY operand and how many 32-channel blocks each needs
+            const int x_c0 = P.swap ? n0 : m0, dy_c0 = P.swap ? m0 : n0;
+            const int x_blocks = P.swap ? BN / 32 : 4, dy_blocks = P.swap ? 4 : BN / 32;
+            for (int it = 0; it < kiters; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                const int tile = t_begin + it;
+                const int tx = tile % P.tiles_x, ty = (tile / P.tiles_x) % P.tiles_y, tn = tile / (P.tiles_x * P.tiles_y);
+                const int ix0 = tx * P.TW, iy0 = ty * P.TH, in0 = tn * P.TN;
+                uint8_t *sa = smem + s * STAGE_BYTES;
+                uint8_t *sb = sa + A_BYTES;
+                uint8_t *sx = P.swap ? sb : sa, *sd = P.swap ? sa : sb;
+                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                for (int j = 0; j < x_blocks; ++j) {
+                    if (P.parity)
+                        tma_load_5d(sx + j * WG_REGION, &map_x, &full_bar[s], ti.px * P.x_ld + x_c0 + j * 32, ix0 + ti.ox, ti.py,
+                                    iy0 + ti.oy, in0);
+                    else
+                        tma_load_4d(sx + j * WG_REGION, &map_x, &full_bar[s], x_c0 + j * 32, ix0 + ti.ox, iy0 + ti.oy, in0);
+                }
+                for (int j = 0; j < dy_blocks; ++j)
+                    tma_load_4d(sd + j * WG_REGION, &map_dy, &full_bar[s], dy_c0 + j * 32, ix0, iy0, in0);
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32_mn(TC_BM, BN);
+            for (int it = 0; it < kiters; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                const uint64_t da = make_desc_mn128(sa), db = make_desc_mn128(sa + A_BYTES);
+#pragma unroll
+                for (int k = 0; k < WG_BKP / 8; ++k)    // 8 pixels per MMA = one 1 KB swizzle group
+                    umma_tf32(tmem_base, da + (uint64_t)(k * 64), db + (uint64_t)(k * 64), idesc, (it | k) != 0);
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(accum_bar);
+        }
+    } else {
+        const int r = warp * 32 + lane;
+        const int mrow = m0 + r;
+        mbar_wait(accum_bar, 0);
+        tc_fence_after();
+        const int tap = ti.wk;
+#pragma unroll 1
+        for (int j = 0; j < BN / 32; ++j) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * 32), v);
+            if (mrow >= P.m_valid) continue;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+                const int ncol = n0 + j * 32 + q;
+                if (ncol >= P.n_valid) break;
+                const int ci = P.swap ? ncol : mrow, co = P.swap ? mrow : ncol;
+                atomicAdd(P.dW + ((long long)tap * P.CI + ci) * P.CO + co, v[q]);
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int BN, int STAGES>
+static int launch_wg(const CUtensorMap &mx, const CUtensorMap &md, const WgParams &P, int splits, int items, cudaStream_t st) {
+    constexpr int smem = STAGES * (4 + BN / 32) * WG_REGION + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        DOFB_CUDA_OK(cudaFuncSetAttribute(tc_wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    tc_wgrad_kernel<BN, STAGES><<<dim3(splits, items, 1), TC_THREADS, smem, st>>>(mx, md, P);
+    DOFB_LAUNCH_OK();
+    return 0;
+}
+
+int tc_conv_wgrad(const dofb_conv_geom *g, const float *x, int x_ld, const float *dy, int dy_ld, float *dw, cudaStream_t st) {
+    DOFB_CHECK_ARG(g && g->kh * g->kw <= TC_MAX_TAPS, "dofb_conv_wgrad(tf32): at most %d taps", TC_MAX_TAPS);
+    DOFB_CHECK_ARG(g->stride == 1 || g->stride == 2, "dofb_conv_wgrad(tf32): stride must be 1 or 2");
+    DOFB_CHECK_ARG(x_ld % 32 == 0 && dy_ld % 32 == 0 && aligned16(x) && aligned16(dy),
+                   "dofb_conv_wgrad(tf32): pitches (%d, %d) must be multiples of 32 floats, pointers 16-byte aligned", x_ld, dy_ld);
+    const int ci_pad = (g->ci + 31) / 32 * 32, co_pad = (g->co + 31) / 32 * 32;
+    DOFB_CHECK_ARG(ci_pad <= x_ld && co_pad <= dy_ld, "dofb_conv_wgrad(tf32): channels rounded up to 32 exceed the pitch");
+    WgParams P;
+    memset(&P, 0, sizeof(P));
+    P.dW = dw; P.CI = g->ci; P.CO = g->co;
+    P.swap = (g->ci < 128 && g->co >= 128) ? 1 : 0;
+    P.m_valid = P.swap ? g->co : g->ci;
+    P.n_valid = P.swap ? g->ci : g->co;
+    P.parity = g->stride == 2; P.x_ld = x_ld;
+    P.ntaps = g->kh * g->kw;
+    for (int kh = 0; kh < g->kh; ++kh)
+        for (int kw = 0; kw < g->kw; ++kw) {
+            TapInfo &t = P.taps[kh * g->kw + kw];
+            const int ddy = kh - g->pad_t, ddx = kw - g->pad_l;
+            if (g->stride == 1) { t.oy = (short)ddy; t.ox = (short)ddx; t.py = t.px = 0; }
+            else {
+                const int py = ((ddy % 2) + 2) % 2, px = ((ddx % 2) + 2) % 2;
+                t.py = (short)py; t.px = (short)px; t.oy = (short)((ddy - py) / 2); t.ox = (short)((ddx - px) / 2);
+            }
+            t.wk = kh * g->kw + kw;
+        }
+    // pixel tile of 32 output pixels
+    {
+        int TW = pow2_ceil(g->ow) < 16 ? pow2_ceil(g->ow) : 16;
+        int th_max = WG_BKP / TW;
+        int TH = pow2_ceil(g->oh) < th_max ? pow2_ceil(g->oh) : th_max;
+        for (int t = TH; t >= 1; t >>= 1)
+            if (g->oh % t == 0) { TH = t; break; }
+        P.TW = TW; P.TH = TH; P.TN = WG_BKP / (TW * TH);
+    }
+    P.tiles_x = (g->ow + P.TW - 1) / P.TW;
+    P.tiles_y = (g->oh + P.TH - 1) / P.TH;
+    const int tiles_n = (g->B + P.TN - 1) / P.TN;
+    P.tiles_total = P.tiles_x * P.tiles_y * tiles_n;
+    const int n_ch = P.n_valid;
+    const int bn = n_ch > 128 ? 256 : (n_ch > 64 ? 128 : (n_ch > 32 ? 64 : 32));
+    P.n_mblk = (P.m_valid + TC_BM - 1) / TC_BM;
+    P.n_nblk = (n_ch + bn - 1) / bn;
+    const int items = P.ntaps * P.n_mblk * P.n_nblk;
+    long long splits = ((long long)num_sms() * 2 + items - 1) / items;
+    if (splits < 1) splits = 1;
+    if (splits > P.tiles_total) splits = P.tiles_total;
+    P.tiles_per_split = (int)((P.tiles_total + splits - 1) / splits);
+    splits = (P.tiles_total + P.tiles_per_split - 1) / P.tiles_per_split;
+    CUtensorMap mx, md;
+    if (!P.parity) {
+        const uint64_t dims[4] = {(uint64_t)ci_pad, (uint64_t)g->iw, (uint64_t)g->ih, (uint64_t)g->B};
+        const uint64_t str[3] = {(uint64_t)x_ld * 4, (uint64_t)g->iw * x_ld * 4, (uint64_t)g->ih * g->iw * x_ld * 4};
+        const uint32_t box[4] = {32, (uint32_t)P.TW, (uint32_t)P.TH, (uint32_t)P.TN};
+        if (make_map(&mx, x, 4, dims, str, box)) return 1;
+    } else {
+        DOFB_CHECK_ARG(g->ih % 2 == 0 && g->iw % 2 == 0, "dofb_conv_wgrad(tf32): stride-2 gather needs even map sizes");
+        const uint64_t dims[5] = {(uint64_t)2 * x_ld, (uint64_t)g->iw / 2, 2, (uint64_t)g->ih / 2, (uint64_t)g->B};
+        const uint64_t str[4] = {(uint64_t)2 * x_ld * 4, (uint64_t)g->iw * x_ld * 4, (uint64_t)2 * g->iw * x_ld * 4,
+                                 (uint64_t)g->ih * g->iw * x_ld * 4};
+        const uint32_t box[5] = {32, (uint32_t)P.TW, 1, (uint32_t)P.TH, (uint32_t)P.TN};
+        if (make_map(&mx, x, 5, dims, str, box)) return 1;
+    }
+    {
+        const uint64_t dims[4] = {(uint64_t)co_pad, (uint64_t)g->ow, (uint64_t)g->oh, (uint64_t)g->B};
+        const uint64_t str[3] = {(uint64_t)dy_ld * 4, (uint64_t)g->ow * dy_ld * 4, (uint64_t)g->oh * g->ow * dy_ld * 4};
+        const uint32_t box[4] = {32, (uint32_t)P.TW, (uint32_t)P.TH, (uint32_t)P.TN};
+        if (make_map(&md, dy, 4, dims, str, box)) return 1;
+    }
+    switch (bn) {
+        case 256: return launch_wg<256, 4>(mx, md, P, (int)splits, items, st);
+        case 128: return launch_wg<128, 6>(mx, md, P, (int)splits, items, st);
+        case 64: return launch_wg<64, 8>(mx, md, P, (int)splits, items, st);
+        default: return launch_wg<32, 8>(mx, md, P, (int)splits, items, st);
+    }
 }
 
 }  // namespace dofb

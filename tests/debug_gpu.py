@@ -1,4 +1,6 @@
 """Scratch diagnostics run on the GPU box (not a test)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
 from oracle import loss_interp as li, flownet_s as fs, adam as oadam, synth
 from deepof_b200 import flyingChairsWrapFlow as W
