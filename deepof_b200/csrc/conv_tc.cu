@@ -323,7 +323,8 @@ static PFN_encodeTiled get_encode() {
     return fn;
 }
 
-static int make_map(CUtensorMap *m, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes, const uint32_t *box) {
+static int make_map(CUtensorMap *m, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes, const uint32_t *box,
+                    CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     PFN_encodeTiled enc = get_encode();
     DOFB_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t gd[5], gs[4];
@@ -331,7 +332,7 @@ static int make_map(CUtensorMap *m, const void *base, int rank, const uint64_t *
     for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), gd, gs, bx, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DOFB_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d (rank %d, dims %llu %llu %llu ..., box %u %u %u ...)", (int)r,
                    rank, (unsigned long long)dims[0], (unsigned long long)dims[1], rank > 2 ? (unsigned long long)dims[2] : 0ull,
@@ -533,9 +534,11 @@ int tc_conv_dgrad(const dofb_conv_geom *g, const float *dy, int dy_ld, const flo
 // ------------------------------------------------------------------------------------------------
 // weight gradient:  dW[tap][ci][co] += sum_{pixels} X[gather(pixel, tap)][ci] * DY[pixel][co]
 // GEMM with K = pixels.  Both operands are "MN-major" (channels contiguous, K strided), which tcgen05
-// takes directly through MN-major SWIZZLE_128B descriptors: every 32-channel column block of a
-// 32-pixel tile is one TMA box {32 ch, TW, TH, TN} = 32 rows x 128 B; the blocks of one operand sit
-// LBO = 4 KB apart, 8-pixel groups SBO = 1 KB apart.  Split-K over CTAs, fp32 atomics into dW.
+// takes directly through MN-major descriptors.  For 32-bit operands the only MN-major layout is
+// "128-byte swizzle with 32-byte atoms" (UMMA LayoutType 1 / CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B):
+// every 32-channel column block of a 32-pixel tile is one TMA box {32 ch, TW, TH, TN} = 32 rows x
+// 128 B; the blocks of one operand sit LBO = 4 KB apart, 4-pixel groups SBO = 512 B apart.
+// Split-K over CTAs, fp32 atomics into dW.
 // `swap` puts DY on the M side (used when ci < 128 <= co so that no MMA rows are wasted).
 // ------------------------------------------------------------------------------------------------
 constexpr int WG_BKP = 32;                    // pixels per pipeline stage
@@ -556,9 +559,9 @@ __device__ __forceinline__ uint64_t make_desc_mn128(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
     d |= (uint64_t)(WG_REGION >> 4) << 16;    // leading byte offset: next 32-channel block
-    d |= (uint64_t)(1024 >> 4) << 32;         // stride byte offset: next 8-pixel group
+    d |= (uint64_t)(512 >> 4) << 32;          // stride byte offset: next 4-pixel group (32-byte-atom swizzle repeats every 4 rows)
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)1 << 61;                   // SWIZZLE_128B_BASE32B: the only MN-major layout tcgen05 accepts for 32-bit operands
     return d;
 }
 __host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) {
@@ -740,20 +743,20 @@ int tc_conv_wgrad(const dofb_conv_geom *g, const float *x, int x_ld, const float
         const uint64_t dims[4] = {(uint64_t)ci_pad, (uint64_t)g->iw, (uint64_t)g->ih, (uint64_t)g->B};
         const uint64_t str[3] = {(uint64_t)x_ld * 4, (uint64_t)g->iw * x_ld * 4, (uint64_t)g->ih * g->iw * x_ld * 4};
         const uint32_t box[4] = {32, (uint32_t)P.TW, (uint32_t)P.TH, (uint32_t)P.TN};
-        if (make_map(&mx, x, 4, dims, str, box)) return 1;
+        if (make_map(&mx, x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
     } else {
         DOFB_CHECK_ARG(g->ih % 2 == 0 && g->iw % 2 == 0, "dofb_conv_wgrad(tf32): stride-2 gather needs even map sizes");
         const uint64_t dims[5] = {(uint64_t)2 * x_ld, (uint64_t)g->iw / 2, 2, (uint64_t)g->ih / 2, (uint64_t)g->B};
         const uint64_t str[4] = {(uint64_t)2 * x_ld * 4, (uint64_t)g->iw * x_ld * 4, (uint64_t)2 * g->iw * x_ld * 4,
                                  (uint64_t)g->ih * g->iw * x_ld * 4};
         const uint32_t box[5] = {32, (uint32_t)P.TW, 1, (uint32_t)P.TH, (uint32_t)P.TN};
-        if (make_map(&mx, x, 5, dims, str, box)) return 1;
+        if (make_map(&mx, x, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
     }
     {
         const uint64_t dims[4] = {(uint64_t)co_pad, (uint64_t)g->ow, (uint64_t)g->oh, (uint64_t)g->B};
         const uint64_t str[3] = {(uint64_t)dy_ld * 4, (uint64_t)g->ow * dy_ld * 4, (uint64_t)g->oh * g->ow * dy_ld * 4};
         const uint32_t box[4] = {32, (uint32_t)P.TW, (uint32_t)P.TH, (uint32_t)P.TN};
-        if (make_map(&md, dy, 4, dims, str, box)) return 1;
+        if (make_map(&md, dy, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
     }
     switch (bn) {
         case 256: return launch_wg<256, 4>(mx, md, P, (int)splits, items, st);

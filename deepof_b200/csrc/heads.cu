@@ -7,17 +7,24 @@
 
 namespace dofb {
 
-constexpr int HD_PX = 4;   // pixels per warp in the forward head
+constexpr int HD_PX = 8;   // pixels per warp in the forward head
 
-// ---- pr forward: one warp per 4 consecutive pixels of a row, lanes stride the channels -----
+// ---- pr forward: one warp per 8 consecutive pixels of a row; lanes stride the channels (float4);
+// the [3,3,c,2] filter is staged once per block in shared memory (<= 74 KB for c = 1026) ----
 __global__ void __launch_bounds__(256) head_fwd_kernel(const float *__restrict__ X, int x_ld, int B, int h, int w, int c,
                                                        const float *__restrict__ Wt, const float *__restrict__ bias,
                                                        float *__restrict__ pr) {
+    extern __shared__ __align__(16) float wsm[];           // [9][c4*4][2], zero padded beyond c
+    const int c4 = (c + 3) >> 2;
+    for (int i = threadIdx.x; i < 9 * c4 * 8; i += blockDim.x) {
+        const int tap = i / (c4 * 8), r = i - tap * (c4 * 8);
+        wsm[i] = (r >> 1) < c ? __ldg(Wt + (long long)tap * c * 2 + r) : 0.f;
+    }
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const int groups_per_row = (w + HD_PX - 1) / HD_PX;
     const long long n_groups = (long long)B * h * groups_per_row;
-    const int c4 = (c + 3) >> 2;
     for (long long gidx = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); gidx < n_groups;
          gidx += (long long)gridDim.x * warps_per_block) {
         const int gx = (int)(gidx % groups_per_row);
@@ -43,16 +50,13 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const float *__restrict__
                 }
 #pragma unroll
                 for (int kw = 0; kw < 3; ++kw) {
-                    // W[tap][ch..ch+3][0..1] = 8 contiguous floats (zero beyond c)
-                    const float *wp = Wt + ((long long)(kh * 3 + kw) * c + ch) * 2;
-                    float wv[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) wv[e] = (ch + (e >> 1) < c) ? __ldg(wp + e) : 0.f;
+                    const float4 *wp = reinterpret_cast<const float4 *>(wsm + ((kh * 3 + kw) * c4 + q) * 8);
+                    const float4 wa = wp[0], wb = wp[1];   // (c0o0,c0o1,c1o0,c1o1) (c2o0,c2o1,c3o0,c3o1)
 #pragma unroll
                     for (int p = 0; p < HD_PX; ++p) {
                         const float4 xx = xv[p + kw];
-                        acc[p][0] += xx.x * wv[0] + xx.y * wv[2] + xx.z * wv[4] + xx.w * wv[6];
-                        acc[p][1] += xx.x * wv[1] + xx.y * wv[3] + xx.z * wv[5] + xx.w * wv[7];
+                        acc[p][0] += xx.x * wa.x + xx.y * wa.z + xx.z * wb.x + xx.w * wb.z;
+                        acc[p][1] += xx.x * wa.y + xx.y * wa.w + xx.z * wb.y + xx.w * wb.w;
                     }
                 }
             }
@@ -67,6 +71,21 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const float *__restrict__
         }
     }
 }
+
+// the 9 neighbouring dpr values of pixel p (zero outside the map) as seen by the transposed stencil
+__device__ __forceinline__ void load_dpr9(const float2 *__restrict__ dpr, long long p, int h, int w, float2 g[9]) {
+    const int x = (int)(p % w), y = (int)((p / w) % h);
+    const long long img = p - ((long long)y * w + x);
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+            const int sy = y - kh + 1, sx = x - kw + 1;
+            g[kh * 3 + kw] = (sy >= 0 && sy < h && sx >= 0 && sx < w) ? __ldg(dpr + img + (long long)sy * w + sx) : make_float2(0.f, 0.f);
+        }
+}
+
+constexpr int HD_UNROLL = 4;   // pixels in flight per warp (independent loads -> latency hiding)
 
 // ---- pr input gradient: lane owns 4 channels (72 weights in registers), warp streams pixels ----
 // dX[b,y,x,ch] (+)= sum_{kh,kw,o} dpr[b,y-kh+1,x-kw+1,o] * W[kh,kw,ch,o]
@@ -87,32 +106,32 @@ __global__ void __launch_bounds__(256) head_dgrad_kernel(const float *__restrict
     const long long wglobal = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long p0 = wglobal * pix_per_warp;
     const long long p1 = p0 + pix_per_warp < n_pix ? p0 + pix_per_warp : n_pix;
-    for (long long p = p0; p < p1; ++p) {
-        const int x = (int)(p % w), y = (int)((p / w) % h);
-        const long long img = p - ((long long)y * w + x);           // pixel index of (b,0,0)
-        float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+    const float2 *dpr2 = reinterpret_cast<const float2 *>(dpr);
+    for (long long pb = p0; pb < p1; pb += HD_UNROLL) {
+        float2 g[HD_UNROLL][9];
+        float4 old[HD_UNROLL];
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-            const int sy = y - kh + 1;
-            if (sy < 0 || sy >= h) continue;
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                const int sx = x - kw + 1;
-                if (sx < 0 || sx >= w) continue;
-                const float2 g = __ldg(reinterpret_cast<const float2 *>(dpr) + img + (long long)sy * w + sx);
-                const int tap = kh * 3 + kw;
-                o0 += g.x * wr[tap][0][0] + g.y * wr[tap][0][1];
-                o1 += g.x * wr[tap][1][0] + g.y * wr[tap][1][1];
-                o2 += g.x * wr[tap][2][0] + g.y * wr[tap][2][1];
-                o3 += g.x * wr[tap][3][0] + g.y * wr[tap][3][1];
+        for (int u = 0; u < HD_UNROLL; ++u) {
+            if (pb + u < p1) {
+                load_dpr9(dpr2, pb + u, h, w, g[u]);
+                if (accumulate) old[u] = *reinterpret_cast<const float4 *>(dX + (pb + u) * dx_ld + ch);
             }
         }
-        float4 *dst = reinterpret_cast<float4 *>(dX + p * dx_ld + ch);
-        if (accumulate) {
-            const float4 old = *dst;
-            o0 += old.x; o1 += old.y; o2 += old.z; o3 += old.w;
+#pragma unroll
+        for (int u = 0; u < HD_UNROLL; ++u) {
+            if (pb + u >= p1) break;
+            float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const float2 gg = g[u][tap];
+                o0 += gg.x * wr[tap][0][0] + gg.y * wr[tap][0][1];
+                o1 += gg.x * wr[tap][1][0] + gg.y * wr[tap][1][1];
+                o2 += gg.x * wr[tap][2][0] + gg.y * wr[tap][2][1];
+                o3 += gg.x * wr[tap][3][0] + gg.y * wr[tap][3][1];
+            }
+            if (accumulate) { o0 += old[u].x; o1 += old[u].y; o2 += old[u].z; o3 += old[u].w; }
+            *reinterpret_cast<float4 *>(dX + (pb + u) * dx_ld + ch) = make_float4(o0, o1, o2, o3);
         }
-        *dst = make_float4(o0, o1, o2, o3);
     }
 }
 
@@ -139,30 +158,33 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(const float *__restrict
     const long long p0 = wglobal * pix_per_warp;
     const long long p1 = p0 + pix_per_warp < n_pix ? p0 + pix_per_warp : n_pix;
     const bool active = ch < c;
-    for (long long p = p0; p < p1; ++p) {
-        const int x = (int)(p % w), y = (int)((p / w) % h);
-        const long long img = p - ((long long)y * w + x);
-        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active) xv = __ldg(reinterpret_cast<const float4 *>(X + p * x_ld + ch));
+    const float2 *dpr2 = reinterpret_cast<const float2 *>(dpr);
+    for (long long pb = p0; pb < p1; pb += HD_UNROLL) {
+        float2 g[HD_UNROLL][9];
+        float4 xv[HD_UNROLL];
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-            const int oy = y - kh + 1;               // output pixel that reads q through tap (kh,kw)
-            if (oy < 0 || oy >= h) continue;
+        for (int u = 0; u < HD_UNROLL; ++u) {
+            xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pb + u < p1) {
+                // the output pixel reading q through tap (kh,kw) sits at q - (kh-1, kw-1): same 9-neighbourhood
+                load_dpr9(dpr2, pb + u, h, w, g[u]);
+                if (active) xv[u] = __ldg(reinterpret_cast<const float4 *>(X + (pb + u) * x_ld + ch));
+            } else {
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                const int ox = x - kw + 1;
-                if (ox < 0 || ox >= w) continue;
-                const float2 g = __ldg(reinterpret_cast<const float2 *>(dpr) + img + (long long)oy * w + ox);
-                const int tap = kh * 3 + kw;
-                acc[tap][0][0] += xv.x * g.x; acc[tap][0][1] += xv.x * g.y;
-                acc[tap][1][0] += xv.y * g.x; acc[tap][1][1] += xv.y * g.y;
-                acc[tap][2][0] += xv.z * g.x; acc[tap][2][1] += xv.z * g.y;
-                acc[tap][3][0] += xv.w * g.x; acc[tap][3][1] += xv.w * g.y;
+                for (int tap = 0; tap < 9; ++tap) g[u][tap] = make_float2(0.f, 0.f);
             }
         }
-        if (blockIdx.y == 0 && lane == 0) {
-            const float2 g = __ldg(reinterpret_cast<const float2 *>(dpr) + p);
-            b0 += g.x; b1 += g.y;
+#pragma unroll
+        for (int u = 0; u < HD_UNROLL; ++u) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const float2 gg = g[u][tap];
+                acc[tap][0][0] += xv[u].x * gg.x; acc[tap][0][1] += xv[u].x * gg.y;
+                acc[tap][1][0] += xv[u].y * gg.x; acc[tap][1][1] += xv[u].y * gg.y;
+                acc[tap][2][0] += xv[u].z * gg.x; acc[tap][2][1] += xv[u].z * gg.y;
+                acc[tap][3][0] += xv[u].w * gg.x; acc[tap][3][1] += xv[u].w * gg.y;
+            }
+            if (blockIdx.y == 0 && lane == 0) { b0 += g[u][4].x; b1 += g[u][4].y; }   // centre tap = dpr[q]
         }
     }
     // block-level combine in shared memory, then one global atomic per (tap,ch,o) per block
@@ -278,9 +300,16 @@ extern "C" int dofb_head_fwd(const float *x, int x_ld, int B, int h, int w, int 
     DOFB_CHECK_ARG(x_ld % 4 == 0 && aligned16(x) && x_ld >= ((c + 3) & ~3), "dofb_head_fwd: x pitch %d must be a multiple of 4 covering c=%d", x_ld, c);
     const long long groups = (long long)B * h * ((w + HD_PX - 1) / HD_PX);
     long long blocks = (groups + 7) / 8;
-    const long long cap = (long long)num_sms() * 16;
+    const long long cap = (long long)num_sms() * 4;
     if (blocks > cap) blocks = cap;
-    head_fwd_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(x, x_ld, B, h, w, c, wt, bias, pr);
+    const int smem = 9 * ((c + 3) / 4) * 8 * (int)sizeof(float);
+    DOFB_CHECK_ARG(smem <= 200 * 1024, "dofb_head_fwd: %d channels do not fit the shared-memory filter stage", c);
+    static int configured = 0;
+    if (smem > 48 * 1024 && configured < smem) {
+        DOFB_CUDA_OK(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = 200 * 1024;
+    }
+    head_fwd_kernel<<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(x, x_ld, B, h, w, c, wt, bias, pr);
     DOFB_LAUNCH_OK();
     return 0;
 }
