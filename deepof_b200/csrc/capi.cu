@@ -16,6 +16,10 @@ int tc_conv_fwd(const dofb_conv_geom *g, const float *x, int x_ld, const float *
 int tc_conv_dgrad(const dofb_conv_geom *g, const float *dy, int dy_ld, const float *w, const float *bias, float *dx, int dx_ld,
                   int act, int accumulate, cudaStream_t st);
 int tc_conv_wgrad(const dofb_conv_geom *g, const float *x, int x_ld, const float *dy, int dy_ld, float *dw, cudaStream_t st);
+int tc_conv1_fwd(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *w, const float *bias,
+                 float *y, int y_ld, int act, cudaStream_t st);
+int tc_conv1_wgrad(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *dy, int dy_ld,
+                   float *dw, cudaStream_t st);
 }  // namespace dofb
 
 using namespace dofb;
@@ -56,5 +60,18 @@ extern "C" int dofb_conv_wgrad_tbias(const dofb_conv_geom *g, const float *x, in
     int rc = dofb_conv_wgrad(g, x, x_ld, dy, dy_ld, dw, nullptr, math, stream);
     if (rc) return rc;
     if (db_large) return launch_colsum(x, x_ld, (long long)g->B * g->ih * g->iw, g->ci, db_large, as_stream(stream));
+    return 0;
+}
+
+extern "C" int dofb_conv1_fwd(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *w,
+                              const float *bias, float *y, int y_ld, int act, void *stream) {
+    return tc_conv1_fwd(g, x, xp_h, xp_w, xp_y0, xp_x0, w, bias, y, y_ld, act, as_stream(stream));
+}
+
+extern "C" int dofb_conv1_wgrad(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *dy,
+                                int dy_ld, float *dw, float *db, void *stream) {
+    int rc = tc_conv1_wgrad(g, x, xp_h, xp_w, xp_y0, xp_x0, dy, dy_ld, dw, as_stream(stream));
+    if (rc) return rc;
+    if (db) return launch_colsum(dy, dy_ld, (long long)g->B * g->oh * g->ow, g->co, db, as_stream(stream));
     return 0;
 }

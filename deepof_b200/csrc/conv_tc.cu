@@ -552,7 +552,8 @@ struct WgParams {
     int n_mblk, n_nblk;
     int parity, x_ld;
     int ntaps;
-    TapInfo taps[TC_MAX_TAPS];               // wk = canonical tap index (kh*KW + kw)
+    int conv1, c1_kh, c1_kw;                 // first-layer mode: M = 2 filter rows x (8 pixels x 8 channels)
+    TapInfo taps[TC_MAX_TAPS];               // wk = canonical tap index (kh*KW + kw); conv1 mode: one entry per filter row
 };
 
 __device__ __forceinline__ uint64_t make_desc_mn128(uint32_t saddr) {
@@ -621,7 +622,12 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 uint8_t *sx = P.swap ? sb : sa, *sd = P.swap ? sa : sb;
                 mbar_expect_tx(&full_bar[s], STAGE_BYTES);
                 for (int j = 0; j < x_blocks; ++j) {
-                    if (P.parity)
+                    if (P.conv1) {
+                        // region j = filter row 2*tapi + (j>>1), floats [(j&1)*32, +32) of its 8-pixel chunk
+                        const int kh = min(2 * tapi + (j >> 1), P.c1_kh - 1);      // (an odd kh count re-loads the last row; masked later)
+                        const TapInfo tr = P.taps[kh];
+                        tma_load_5d(sx + j * WG_REGION, &map_x, &full_bar[s], (j & 1) * 32, ix0, tr.py, iy0 + tr.oy, in0);
+                    } else if (P.parity)
                         tma_load_5d(sx + j * WG_REGION, &map_x, &full_bar[s], ti.px * P.x_ld + x_c0 + j * 32, ix0 + ti.ox, ti.py,
                                     iy0 + ti.oy, in0);
                     else
@@ -658,6 +664,18 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         for (int j = 0; j < BN / 32; ++j) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * 32), v);
+            if (P.conv1) {
+                const int kh = 2 * tapi + (r >> 6), kw = (r & 63) >> 3, ci = r & 7;
+                if (kh >= P.c1_kh || kw >= P.c1_kw || ci >= P.CI) continue;
+                float *dst = P.dW + (((long long)kh * P.c1_kw + kw) * P.CI + ci) * P.CO;
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const int ncol = n0 + j * 32 + q;
+                    if (ncol >= P.n_valid) break;
+                    atomicAdd(dst + ncol, v[q]);
+                }
+                continue;
+            }
             if (mrow >= P.m_valid) continue;
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
@@ -752,6 +770,123 @@ int tc_conv_wgrad(const dofb_conv_geom *g, const float *x, int x_ld, const float
         const uint32_t box[5] = {32, (uint32_t)P.TW, 1, (uint32_t)P.TH, (uint32_t)P.TN};
         if (make_map(&mx, x, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
     }
+    {
+        const uint64_t dims[4] = {(uint64_t)co_pad, (uint64_t)g->ow, (uint64_t)g->oh, (uint64_t)g->B};
+        const uint64_t str[3] = {(uint64_t)dy_ld * 4, (uint64_t)g->ow * dy_ld * 4, (uint64_t)g->oh * g->ow * dy_ld * 4};
+        const uint32_t box[4] = {32, (uint32_t)P.TW, (uint32_t)P.TH, (uint32_t)P.TN};
+        if (make_map(&md, dy, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+    }
+    switch (bn) {
+        case 256: return launch_wg<256, 4>(mx, md, P, (int)splits, items, st);
+        case 128: return launch_wg<128, 6>(mx, md, P, (int)splits, items, st);
+        case 64: return launch_wg<64, 8>(mx, md, P, (int)splits, items, st);
+        default: return launch_wg<32, 8>(mx, md, P, (int)splits, items, st);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// first layer (ci <= 8, stride 2, kw <= 8): one filter ROW = kw pixels x 8 channels = 64 contiguous floats of the
+// zero-bordered NHWC input -> K chunk of 64 (two 32-float TMA boxes); rank-5 map with OVERLAPPING rows:
+//   d0 = 64 floats of the chunk, d1 = ox (stride 2 pixels = 64 B), d2 = row parity, d3 = row pair, d4 = image
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_conv1_kernel(const float *__restrict__ W, float *__restrict__ Wp, int kh, int kw, int ci, int co) {
+    const int total = co * kh * 64;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int c = i & 7, x = (i >> 3) & 7, r = (i >> 6) % kh, n = i / (64 * kh);
+        Wp[i] = (c < ci && x < kw) ? __ldg(W + (((long long)r * kw + x) * ci + c) * co + n) : 0.f;
+    }
+}
+
+struct Conv1Map {
+    const float *base; int ok;
+    TapInfo rows[8];
+};
+
+static int conv1_prepare(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, int TW, int TH, int TN,
+                         CUtensorMapSwizzle swz, CUtensorMap *map, TapInfo *rows) {
+    DOFB_CHECK_ARG(g->stride == 2 && g->ci <= 8 && g->kw <= 8 && g->kh <= 8, "dofb_conv1: needs stride 2, ci <= 8, kernel <= 8x8");
+    DOFB_CHECK_ARG(xp_h % 2 == 0 && xp_w % 2 == 0 && aligned16(x), "dofb_conv1: buffer sizes must be even and the buffer 16-byte aligned");
+    const int rowoff = xp_y0 - g->pad_t, coloff = xp_x0 - g->pad_l;
+    DOFB_CHECK_ARG(rowoff >= 0 && coloff >= 0, "dofb_conv1: the zero border must cover the SAME padding (%d,%d)", g->pad_t, g->pad_l);
+    DOFB_CHECK_ARG(2 * (g->ow - 1) + coloff + 8 <= xp_w && 2 * (g->oh - 1) + rowoff + g->kh <= xp_h,
+                   "dofb_conv1: the zero border after the image is too small for %dx%d taps", g->kh, g->kw);
+    for (int kh = 0; kh < g->kh; ++kh) {
+        rows[kh].oy = (short)((kh + rowoff) >> 1); rows[kh].py = (short)((kh + rowoff) & 1);
+        rows[kh].ox = 0; rows[kh].px = 0; rows[kh].wk = kh * 64;
+    }
+    const uint64_t rowb = (uint64_t)xp_w * 8 * 4;
+    const uint64_t dims[5] = {64, (uint64_t)g->ow, 2, (uint64_t)xp_h / 2, (uint64_t)g->B};
+    const uint64_t str[4] = {64, rowb, 2 * rowb, (uint64_t)xp_h * rowb};
+    const uint32_t box[5] = {32, (uint32_t)TW, 1, (uint32_t)TH, (uint32_t)TN};
+    return make_map(map, x + (size_t)coloff * 8, 5, dims, str, box, swz);
+}
+
+int tc_conv1_fwd(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *w, const float *bias,
+                 float *y, int y_ld, int act, cudaStream_t st) {
+    DOFB_CHECK_ARG(g && x && w && y, "dofb_conv1_fwd: null argument");
+    TcParams P;
+    memset(&P, 0, sizeof(P));
+    P.cnt_y = g->oh; P.cnt_x = g->ow; P.rstep = 1;
+    choose_tile(P.cnt_y, P.cnt_x, P.TW, P.TH, P.TN);
+    CUtensorMap ma, mb;
+    if (conv1_prepare(g, x, xp_h, xp_w, xp_y0, xp_x0, P.TW, P.TH, P.TN, CU_TENSOR_MAP_SWIZZLE_128B, &ma, P.taps)) return 1;
+    P.parity = 1; P.ntaps = g->kh; P.ncb = 2; P.a_coff = 0; P.a_ld = 0;
+    P.out = y; P.out_ld = y_ld; P.bias = bias; P.n_valid = g->co; P.rh = g->oh; P.rw = g->ow; P.act = act; P.accumulate = 0; P.B = g->B;
+    P.tiles_x = (P.cnt_x + P.TW - 1) / P.TW;
+    P.tiles_y = (P.cnt_y + P.TH - 1) / P.TH;
+    const int tiles = P.tiles_x * P.tiles_y * ((g->B + P.TN - 1) / P.TN);
+    float *wp = nullptr;
+    const size_t wfloats = (size_t)g->co * g->kh * 64;
+    if (get_pack_buffer(w, 2, wfloats, &wp)) return 1;
+    pack_conv1_kernel<<<(unsigned)((wfloats + 255) / 256), 256, 0, st>>>(w, wp, g->kh, g->kw, g->ci, g->co);
+    DOFB_LAUNCH_OK();
+    const int bn = g->co > 128 ? 256 : (g->co > 64 ? 128 : (g->co > 32 ? 64 : 32));
+    const uint64_t dims[2] = {(uint64_t)g->kh * 64, (uint64_t)g->co};
+    const uint64_t str[1] = {(uint64_t)g->kh * 64 * 4};
+    const uint32_t box[2] = {32, (uint32_t)bn};
+    if (make_map(&mb, wp, 2, dims, str, box)) return 1;
+    const int n_tiles = (g->co + bn - 1) / bn;
+    switch (bn) {
+        case 256: return launch_tc<256, 4>(ma, mb, P, tiles, n_tiles, st);
+        case 128: return launch_tc<128, 6>(ma, mb, P, tiles, n_tiles, st);
+        case 64: return launch_tc<64, 8>(ma, mb, P, tiles, n_tiles, st);
+        default: return launch_tc<32, 8>(ma, mb, P, tiles, n_tiles, st);
+    }
+}
+
+int tc_conv1_wgrad(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *dy, int dy_ld,
+                   float *dw, cudaStream_t st) {
+    DOFB_CHECK_ARG(g && x && dy && dw, "dofb_conv1_wgrad: null argument");
+    DOFB_CHECK_ARG(dy_ld % 32 == 0 && aligned16(dy), "dofb_conv1_wgrad: dy pitch %d must be a multiple of 32 floats", dy_ld);
+    const int co_pad = (g->co + 31) / 32 * 32;
+    DOFB_CHECK_ARG(co_pad <= dy_ld, "dofb_conv1_wgrad: channels rounded up to 32 exceed the pitch");
+    WgParams P;
+    memset(&P, 0, sizeof(P));
+    P.dW = dw; P.CI = g->ci; P.CO = g->co; P.swap = 0; P.m_valid = TC_BM; P.n_valid = g->co;
+    P.conv1 = 1; P.c1_kh = g->kh; P.c1_kw = g->kw; P.parity = 1;
+    {
+        int TW = pow2_ceil(g->ow) < 16 ? pow2_ceil(g->ow) : 16;
+        int th_max = WG_BKP / TW;
+        int TH = pow2_ceil(g->oh) < th_max ? pow2_ceil(g->oh) : th_max;
+        for (int t = TH; t >= 1; t >>= 1)
+            if (g->oh % t == 0) { TH = t; break; }
+        P.TW = TW; P.TH = TH; P.TN = WG_BKP / (TW * TH);
+    }
+    CUtensorMap mx, md;
+    if (conv1_prepare(g, x, xp_h, xp_w, xp_y0, xp_x0, P.TW, P.TH, P.TN, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, &mx, P.taps)) return 1;
+    P.tiles_x = (g->ow + P.TW - 1) / P.TW;
+    P.tiles_y = (g->oh + P.TH - 1) / P.TH;
+    P.tiles_total = P.tiles_x * P.tiles_y * ((g->B + P.TN - 1) / P.TN);
+    const int bn = g->co > 128 ? 256 : (g->co > 64 ? 128 : (g->co > 32 ? 64 : 32));
+    P.ntaps = (g->kh + 1) / 2;                 // work items along the filter rows: pairs of rows
+    P.n_mblk = 1;
+    P.n_nblk = (g->co + bn - 1) / bn;
+    const int items = P.ntaps * P.n_nblk;
+    long long splits = ((long long)num_sms() * 2 + items - 1) / items;
+    if (splits > P.tiles_total) splits = P.tiles_total;
+    if (splits < 1) splits = 1;
+    P.tiles_per_split = (int)((P.tiles_total + splits - 1) / splits);
+    splits = (P.tiles_total + P.tiles_per_split - 1) / P.tiles_per_split;
     {
         const uint64_t dims[4] = {(uint64_t)co_pad, (uint64_t)g->ow, (uint64_t)g->oh, (uint64_t)g->B};
         const uint64_t str[3] = {(uint64_t)dy_ld * 4, (uint64_t)g->ow * dy_ld * 4, (uint64_t)g->oh * g->ow * dy_ld * 4};

@@ -33,7 +33,7 @@ int num_sms() {
 struct PreParams {
     const float *src, *tgt;
     float *x6;
-    int x6_ld;
+    int x6_ld, x6_h, x6_w, x6_y0, x6_x0;
     int B, H, W;
     float mean[3];
     int n_scales;
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
             a[c] = (__ldg(P.src + p * 3 + c) - P.mean[c]) / 255.0f;
             t[c] = (__ldg(P.tgt + p * 3 + c) - P.mean[c]) / 255.0f;
         }
-        float *o = P.x6 + p * P.x6_ld;
+        float *o = P.x6 + (((long long)b * P.x6_h + y + P.x6_y0) * P.x6_w + x + P.x6_x0) * P.x6_ld;
         if (P.x6_ld == 8) {
             reinterpret_cast<float4 *>(o)[0] = make_float4(a[0], a[1], a[2], t[0]);
             reinterpret_cast<float4 *>(o)[1] = make_float4(t[1], t[2], 0.f, 0.f);
@@ -168,15 +168,18 @@ extern "C" long long dofb_launch_count(void) { return g_launches.load(); }
 extern "C" void dofb_reset_launch_count(void) { g_launches.store(0); }
 
 extern "C" int dofb_preprocess(const float *src, const float *tgt, const float mean_bgr[3], int B, int H, int W, float *x6,
-                               int x6_ld, int n_scales, float *const *pyr_src, float *const *pyr_tgt, void *stream) {
+                               int x6_ld, int x6_h, int x6_w, int x6_y0, int x6_x0, int n_scales, float *const *pyr_src,
+                               float *const *pyr_tgt, void *stream) {
     DOFB_CHECK_ARG(src && tgt && x6 && mean_bgr, "dofb_preprocess: null argument");
     DOFB_CHECK_ARG(B > 0 && H > 0 && W > 0 && x6_ld >= 6, "dofb_preprocess: bad shape B=%d H=%d W=%d ld=%d", B, H, W, x6_ld);
     DOFB_CHECK_ARG(n_scales >= 0 && n_scales <= 8, "dofb_preprocess: n_scales=%d out of range", n_scales);
     DOFB_CHECK_ARG(n_scales == 0 || (H % (1 << n_scales) == 0 && W % (1 << n_scales) == 0),
                    "dofb_preprocess: H=%d W=%d must be multiples of 2^%d", H, W, n_scales);
     DOFB_CHECK_ARG(x6_ld != 8 || aligned16(x6), "dofb_preprocess: x6 must be 16-byte aligned");
+    DOFB_CHECK_ARG(x6_y0 >= 0 && x6_x0 >= 0 && x6_y0 + H <= x6_h && x6_x0 + W <= x6_w, "dofb_preprocess: the image does not fit the x6 buffer");
     PreParams P;
     P.src = src; P.tgt = tgt; P.x6 = x6; P.x6_ld = x6_ld; P.B = B; P.H = H; P.W = W;
+    P.x6_h = x6_h; P.x6_w = x6_w; P.x6_y0 = x6_y0; P.x6_x0 = x6_x0;
     for (int c = 0; c < 3; ++c) P.mean[c] = mean_bgr[c];
     P.n_scales = n_scales;
     for (int s = 0; s < 8; ++s) {

@@ -123,6 +123,7 @@ class FlowNetS:
         # per-op math: the tcgen05 path needs 32-float pitches (conv1 reads the 8-float pitched input) and has its own
         # weight-gradient kernel; anything it does not cover runs on the fp32 SIMT kernels (explicit, per layer).
         self.math_wgrad = self.math if tc_wgrad else MATH_FP32
+        tc_wgrad = tc_wgrad and self.math == MATH_TF32
         self.mean = tuple(float(m) for m in mean)
         self.hyper = dict(HYPER)
         if hyper:
@@ -174,7 +175,10 @@ class FlowNetS:
     def _alloc(self):
         B, H, W, dev = self.B, self.H, self.W, self.device
         z = lambda h, w, c: torch.zeros(B, h, w, c, dtype=torch.float32, device=dev)  # noqa: E731
-        self.x6 = z(H, W, 8)
+        # conv1 input: dense for the SIMT path; zero-bordered (2 rows/cols before, 4/6 after) for the tcgen05 first-layer
+        # kernel, which reads the SAME padding (2,3) of the 7x7/2 conv straight from the border
+        self.x6_origin = (2, 2) if self.math == MATH_TF32 else (0, 0)
+        self.x6 = z(H + 6, W + 8, 8) if self.math == MATH_TF32 else z(H, W, 8)
         shp = {"concat1": (H // 2, W // 2, 128), "concat2": (H // 4, W // 4, 224), "c31": (H // 8, W // 8, 256),
                "concat3": (H // 8, W // 8, 416), "c41": (H // 16, W // 16, 512), "concat4": (H // 16, W // 16, 800),
                "c51": (H // 32, W // 32, 512), "concat5": (H // 32, W // 32, 1056), "c61": (H // 64, W // 64, 1024),
@@ -193,7 +197,7 @@ class FlowNetS:
         B, H, W = self.B, self.H, self.W
         a, d = self.act, self.dact
         S = Slab
-        io = [(S(self.x6, 0, 6), None, S(a["concat1"], 0, 64), S(d["concat1"], 0, 64)),
+        io = [(S(self.x6, 0, 6) if self.math == MATH_FP32 else None, None, S(a["concat1"], 0, 64), S(d["concat1"], 0, 64)),
               (S(a["concat1"], 0, 64), S(d["concat1"], 0, 64), S(a["concat2"], 0, 128), S(d["concat2"], 0, 128)),
               (S(a["concat2"], 0, 128), S(d["concat2"], 0, 128), full(a["c31"]), full(d["c31"])),
               (full(a["c31"]), full(d["c31"]), S(a["concat3"], 0, 256), S(d["concat3"], 0, 256)),
@@ -234,10 +238,14 @@ class FlowNetS:
             raise ops.DeepOFError(f"expected [B={self.B},{self.H},{self.W},3] NHWC inputs, got {tuple(source.shape)} / {tuple(target.shape)}")
         P, mth = self.params, self.math
         self._k("preprocess", ops.preprocess, source, target, self.mean, self.x6, [self.pyr_src[s] for s in range(1, 7)],
-                [self.pyr_tgt[s] for s in range(1, 7)])
+                [self.pyr_tgt[s] for s in range(1, 7)], self.x6_origin)
         for L in self.tower:
+            if L["x"] is None:      # conv1 on tensor cores from the zero-bordered buffer
+                self._k("conv_fwd:" + L["name"], ops.conv1_fwd, L["g"], self.x6, self.x6_origin, P[L["name"] + "/weights"],
+                        P[L["name"] + "/biases"], L["y"], ACT_ELU)
+                continue
             self._k("conv_fwd:" + L["name"], ops.conv_fwd, L["g"], L["x"], P[L["name"] + "/weights"], P[L["name"] + "/biases"],
-                    L["y"], ACT_ELU, mth if L["x"].ld % 32 == 0 else MATH_FP32)
+                    L["y"], ACT_ELU, mth)
         for R in self.refine:
             s = R["s"]
             x, _ = self.feat[s]
@@ -297,8 +305,12 @@ class FlowNetS:
         # contracting tower, top down
         for L in reversed(self.tower):
             self._k("elu_bwd:" + L["name"], ops.elu_bwd, L["dy"], L["y"])
-            self._k("conv_wgrad:" + L["name"], ops.conv_wgrad, L["g"], L["x"], L["dy"], G[L["name"] + "/weights"],
-                    G[L["name"] + "/biases"], mthw if L["x"].ld % 32 == 0 else MATH_FP32)
+            if L["x"] is None:
+                self._k("conv_wgrad:" + L["name"], ops.conv1_wgrad, L["g"], self.x6, self.x6_origin, L["dy"],
+                        G[L["name"] + "/weights"], G[L["name"] + "/biases"])
+            else:
+                self._k("conv_wgrad:" + L["name"], ops.conv_wgrad, L["g"], L["x"], L["dy"], G[L["name"] + "/weights"],
+                        G[L["name"] + "/biases"], mthw)
             if L["dx"] is not None:
                 self._k("conv_dgrad:" + L["name"], ops.conv_dgrad, L["g"], L["dy"], P[L["name"] + "/weights"], None, L["dx"],
                         ACT_NONE, L["acc"], mth)

@@ -86,7 +86,8 @@ def conv_geom(B, ih, iw, ci, co, k, stride) -> ConvGeom:
     return ConvGeom(B, ih, iw, ci, oh, ow, co, k, k, stride, pt, pl)
 
 
-def preprocess(src, tgt, mean, x6, pyr_src, pyr_tgt):
+def preprocess(src, tgt, mean, x6, pyr_src, pyr_tgt, origin=(0, 0)):
+    """x6 may be larger than the image (zero border for dofb_conv1_*); ``origin`` = (row, col) of the image in it."""
     _req(src, "src"); _req(tgt, "tgt"); _req(x6, "x6")
     B, H, W, _ = src.shape
     n = len(pyr_src)
@@ -96,7 +97,21 @@ def preprocess(src, tgt, mean, x6, pyr_src, pyr_tgt):
     ps = (C.c_void_p * max(n, 1))(*[t.data_ptr() for t in pyr_src])
     pt = (C.c_void_p * max(n, 1))(*[t.data_ptr() for t in pyr_tgt])
     lib = _lib.load()
-    check(lib.dofb_preprocess(src.data_ptr(), tgt.data_ptr(), m, B, H, W, x6.data_ptr(), x6.shape[3], n, ps, pt, _stream()))
+    check(lib.dofb_preprocess(src.data_ptr(), tgt.data_ptr(), m, B, H, W, x6.data_ptr(), x6.shape[3], x6.shape[1], x6.shape[2],
+                              origin[0], origin[1], n, ps, pt, _stream()))
+
+
+def conv1_fwd(g: ConvGeom, xpad, origin, w, b, y: Slab, act=ACT_ELU):
+    """conv1 on tensor cores from the zero-bordered input buffer (see dofb_conv1_fwd)."""
+    _req(xpad, "xpad"); _req(w, "w")
+    check(_lib.load().dofb_conv1_fwd(C.byref(g), xpad.data_ptr(), xpad.shape[1], xpad.shape[2], origin[0], origin[1], w.data_ptr(),
+                                     b.data_ptr() if b is not None else None, y.ptr, y.ld, act, _stream()))
+
+
+def conv1_wgrad(g: ConvGeom, xpad, origin, dy: Slab, dw, db):
+    _req(xpad, "xpad"); _req(dw, "dw")
+    check(_lib.load().dofb_conv1_wgrad(C.byref(g), xpad.data_ptr(), xpad.shape[1], xpad.shape[2], origin[0], origin[1], dy.ptr, dy.ld,
+                                       dw.data_ptr(), db.data_ptr() if db is not None else None, _stream()))
 
 
 def conv_fwd(g: ConvGeom, x: Slab, w, b, y: Slab, act=ACT_ELU, math=MATH_FP32):

@@ -41,13 +41,14 @@ void dofb_reset_launch_count(void);
  * the 12 tf.image.resize_bilinear calls of flyingChairsWrapFlow.py:16-31,61-62,
  * 72-73,83-84,94-95,105-106,116-117.
  *   src,tgt : [B,H,W,3] BGR 0..255
- *   x6      : [B,H,W,x6_ld] out, channels 0..2 = (src-mean)/255, 3..5 = (tgt-mean)/255,
- *             channels 6..x6_ld-1 are zero-filled
+ *   x6      : [B,x6_h,x6_w,x6_ld] out; the image occupies rows [x6_y0, x6_y0+H) and columns [x6_x0, x6_x0+W)
+ *             (a zero border around it is the caller's: dofb_conv1_* reads it as the conv padding); channels
+ *             0..2 = (src-mean)/255, 3..5 = (tgt-mean)/255, channels 6..x6_ld-1 are zero-filled
  *   pyr_src/pyr_tgt[s] (s=0..n_scales-1): [B,H>>(s+1),W>>(s+1),3] LRN-normalised,
  *             decimated (legacy resize_bilinear at an integer ratio == x[::r, ::r]).
  */
 int dofb_preprocess(const float *src, const float *tgt, const float mean_bgr[3],
-                    int B, int H, int W, float *x6, int x6_ld,
+                    int B, int H, int W, float *x6, int x6_ld, int x6_h, int x6_w, int x6_y0, int x6_x0,
                     int n_scales, float *const *pyr_src, float *const *pyr_tgt, void *stream);
 
 /* ---- warp + Charbonnier photometric + smoothness loss -------------------- */
@@ -111,6 +112,16 @@ int dofb_conv_wgrad(const dofb_conv_geom *g, const float *x, int x_ld, const flo
  * conv2d_transpose, whose bias lives on the large side. */
 int dofb_conv_wgrad_tbias(const dofb_conv_geom *g, const float *x, int x_ld, const float *dy, int dy_ld,
                           float *dw, float *db_large, int math, void *stream);
+
+/* First-layer convolution on tensor cores (tcgen05 kind::tf32): few input channels (ci <= 8, stored with pitch 8),
+ * stride 2, kw <= 8 (conv1 7x7/2, flyingChairsWrapFlow.py:31).  One filter ROW (kw x 8 channels, 64 floats, contiguous
+ * in NHWC) is one K chunk, so K = kh*64 instead of kh*kw*32.  x is the zero-bordered buffer written by
+ * dofb_preprocess: [B,xp_h,xp_w,8] with the image at (xp_y0, xp_x0); the border must cover the SAME padding
+ * (xp_y0 >= pad_t, xp_x0 >= pad_l, enough rows/columns after the image) and xp_h, xp_w must be even. */
+int dofb_conv1_fwd(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *w,
+                   const float *bias, float *y, int y_ld, int act, void *stream);
+int dofb_conv1_wgrad(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *dy,
+                     int dy_ld, float *dw, float *db, void *stream);
 
 /* g[B*h*w, 0..c) *= elu'(y) where y is the ELU OUTPUT (elu' = y>0 ? 1 : y+1). */
 int dofb_elu_bwd(float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c, void *stream);

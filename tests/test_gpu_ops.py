@@ -54,6 +54,11 @@ def test_preprocess_and_pyramid():
     ps = [torch.zeros(B, H >> (s + 1), W >> (s + 1), 3, device="cuda") for s in range(ns)]
     pt = [torch.zeros_like(t) for t in ps]
     ops.preprocess(src.cuda(), tgt.cuda(), fs.FLYINGCHAIRS_MEAN, x6, ps, pt)
+    # zero-bordered variant used by the tensor-core first layer
+    xb = torch.zeros(B, H + 6, W + 8, 8, device="cuda")
+    ops.preprocess(src.cuda(), tgt.cuda(), fs.FLYINGCHAIRS_MEAN, xb, ps, pt, origin=(2, 2))
+    assert torch.equal(xb[:, 2:2 + H, 2:2 + W], x6)
+    assert float(xb[:, :2].abs().max()) == 0.0 and float(xb[:, :, 2 + W:].abs().max()) == 0.0
     xi, ni = fs.preprocess(src)
     xo, no = fs.preprocess(tgt)
     ref6 = torch.cat([xi, xo, torch.zeros(B, H, W, 2)], dim=3)

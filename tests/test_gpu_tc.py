@@ -128,6 +128,36 @@ def test_tc_wgrad_matches_simt(case):
     assert rel(db1, db0) < 1e-4
 
 
+@pytest.mark.parametrize("B,H,W", [(2, 64, 128), (1, 384, 512), (3, 48, 80)])
+def test_tc_conv1_fwd_and_wgrad_match_simt(B, H, W):
+    """First-layer 7x7/2 conv (ci=6) on tensor cores from the zero-bordered buffer vs the SIMT kernel on the dense one."""
+    from deepof_b200 import ops
+    g = torch.Generator().manual_seed(B * H + W)
+    ci, co, k = 6, 64, 7
+    img = torch.randn(B, H, W, ci, generator=g).cuda()
+    dense = torch.zeros(B, H, W, 8, device="cuda")
+    dense[..., :ci] = img
+    padded = torch.zeros(B, H + 6, W + 8, 8, device="cuda")
+    padded[:, 2:2 + H, 2:2 + W, :ci] = img
+    w = (torch.randn(k, k, ci, co, generator=g) / math.sqrt(k * k * ci)).cuda()
+    b = (torch.randn(co, generator=g) * 0.1).cuda()
+    geom = ops.conv_geom(B, H, W, ci, co, k, 2)
+    y0 = torch.zeros(B, geom.oh, geom.ow, 128, device="cuda")
+    y1 = torch.zeros_like(y0)
+    ops.conv_fwd(geom, ops.Slab(dense, 0, ci), w, b, ops.Slab(y0, 0, co), ops.ACT_ELU, ops.MATH_FP32)
+    ops.conv1_fwd(geom, padded, (2, 2), w, b, ops.Slab(y1, 0, co), ops.ACT_ELU)
+    torch.cuda.synchronize()
+    assert rel(y1, y0) < TOL
+    dy = _buf(B, geom.oh, geom.ow, 128, co, g)
+    dw0 = torch.zeros(k, k, ci, co, device="cuda"); dw1 = torch.zeros_like(dw0)
+    db0 = torch.zeros(co, device="cuda"); db1 = torch.zeros_like(db0)
+    ops.conv_wgrad(geom, ops.Slab(dense, 0, ci), ops.Slab(dy, 0, co), dw0, db0, ops.MATH_FP32)
+    ops.conv1_wgrad(geom, padded, (2, 2), ops.Slab(dy, 0, co), dw1, db1)
+    torch.cuda.synchronize()
+    assert rel(dw1, dw0) < TOL
+    assert rel(db1, db0) < 1e-4
+
+
 def test_tf32_engine_tracks_fp32_engine_and_oracle_epe():
     """Whole step in TF32 mode: flows within the stated tolerance of the fp32 device path and EPE within 1e-3 of the CPU oracle."""
     from deepof_b200.flownet import FlowNetS
