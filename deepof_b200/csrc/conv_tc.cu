@@ -553,6 +553,7 @@ struct WgParams {
     int parity, x_ld;
     int ntaps;
     int conv1, c1_kh, c1_kw;                 // first-layer mode: M = 2 filter rows x (8 pixels x 8 channels)
+    int pack_g, pack_cb, ntaps_real;         // packed-M mode (ci = 32/64): M = pack_g taps x pack_cb channels
     TapInfo taps[TC_MAX_TAPS];               // wk = canonical tap index (kh*KW + kw); conv1 mode: one entry per filter row
 };
 
@@ -627,11 +628,19 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                         const int kh = min(2 * tapi + (j >> 1), P.c1_kh - 1);      // (an odd kh count re-loads the last row; masked later)
                         const TapInfo tr = P.taps[kh];
                         tma_load_5d(sx + j * WG_REGION, &map_x, &full_bar[s], (j & 1) * 32, ix0, tr.py, iy0 + tr.oy, in0);
-                    } else if (P.parity)
-                        tma_load_5d(sx + j * WG_REGION, &map_x, &full_bar[s], ti.px * P.x_ld + x_c0 + j * 32, ix0 + ti.ox, ti.py,
-                                    iy0 + ti.oy, in0);
-                    else
-                        tma_load_4d(sx + j * WG_REGION, &map_x, &full_bar[s], x_c0 + j * 32, ix0 + ti.ox, iy0 + ti.oy, in0);
+                    } else {
+                        TapInfo tr = ti;
+                        int c0 = x_c0 + j * 32;
+                        if (P.pack_g > 1) {     // region j = tap (tapi*G + j/per), channel block j%per
+                            const int per = P.pack_cb >> 5;
+                            tr = P.taps[min(tapi * P.pack_g + j / per, P.ntaps_real - 1)];
+                            c0 = (j % per) * 32;
+                        }
+                        if (P.parity)
+                            tma_load_5d(sx + j * WG_REGION, &map_x, &full_bar[s], tr.px * P.x_ld + c0, ix0 + tr.ox, tr.py, iy0 + tr.oy, in0);
+                        else
+                            tma_load_4d(sx + j * WG_REGION, &map_x, &full_bar[s], c0, ix0 + tr.ox, iy0 + tr.oy, in0);
+                    }
                 }
                 for (int j = 0; j < dy_blocks; ++j)
                     tma_load_4d(sd + j * WG_REGION, &map_dy, &full_bar[s], dy_c0 + j * 32, ix0, iy0, in0);
@@ -668,6 +677,18 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 const int kh = 2 * tapi + (r >> 6), kw = (r & 63) >> 3, ci = r & 7;
                 if (kh >= P.c1_kh || kw >= P.c1_kw || ci >= P.CI) continue;
                 float *dst = P.dW + (((long long)kh * P.c1_kw + kw) * P.CI + ci) * P.CO;
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const int ncol = n0 + j * 32 + q;
+                    if (ncol >= P.n_valid) break;
+                    atomicAdd(dst + ncol, v[q]);
+                }
+                continue;
+            }
+            if (P.pack_g > 1) {
+                const int tsel = tapi * P.pack_g + r / P.pack_cb, ci = r % P.pack_cb;
+                if (tsel >= P.ntaps_real || ci >= P.CI) continue;
+                float *dst = P.dW + ((long long)P.taps[tsel].wk * P.CI + ci) * P.CO;
 #pragma unroll
                 for (int q = 0; q < 32; ++q) {
                     const int ncol = n0 + j * 32 + q;
@@ -717,15 +738,19 @@ int tc_conv_wgrad(const dofb_conv_geom *g, const float *x, int x_ld, const float
     WgParams P;
     memset(&P, 0, sizeof(P));
     P.dW = dw; P.CI = g->ci; P.CO = g->co;
-    P.swap = (g->ci < 128 && g->co >= 128) ? 1 : 0;
-    P.m_valid = P.swap ? g->co : g->ci;
+    // ci <= 64: several taps share one 128-row M tile (no wasted MMA rows); otherwise ci < 128 <= co swaps the operands
+    P.pack_cb = g->ci <= 32 ? 32 : 64;
+    P.pack_g = g->ci <= 64 ? TC_BM / P.pack_cb : 1;
+    P.swap = (P.pack_g == 1 && g->ci < 128 && g->co >= 128) ? 1 : 0;
+    P.m_valid = P.pack_g > 1 ? TC_BM : (P.swap ? g->co : g->ci);
     P.n_valid = P.swap ? g->ci : g->co;
     P.parity = g->stride == 2; P.x_ld = x_ld;
-    P.ntaps = g->kh * g->kw;
+    P.ntaps_real = g->kh * g->kw;
+    P.ntaps = (P.ntaps_real + P.pack_g - 1) / P.pack_g;
     for (int kh = 0; kh < g->kh; ++kh)
         for (int kw = 0; kw < g->kw; ++kw) {
             TapInfo &t = P.taps[kh * g->kw + kw];
-            const int ddy = kh - g->pad_t, ddx = kw - g->pad_l;
+            const int ddy = kh - g->pad_t, ddx = kw - g->pad_l;   // (table holds every real tap; P.ntaps counts work items)
             if (g->stride == 1) { t.oy = (short)ddy; t.ox = (short)ddx; t.py = t.px = 0; }
             else {
                 const int py = ((ddy % 2) + 2) % 2, px = ((ddx % 2) + 2) % 2;

@@ -72,26 +72,50 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const float *__restrict__
     }
 }
 
-// the 9 neighbouring dpr values of pixel p (zero outside the map) as seen by the transposed stencil
-__device__ __forceinline__ void load_dpr9(const float2 *__restrict__ dpr, long long p, int h, int w, float2 g[9]) {
-    const int x = (int)(p % w), y = (int)((p / w) % h);
-    const long long img = p - ((long long)y * w + x);
-#pragma unroll
-    for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-            const int sy = y - kh + 1, sx = x - kw + 1;
-            g[kh * 3 + kw] = (sy >= 0 && sy < h && sx >= 0 && sx < w) ? __ldg(dpr + img + (long long)sy * w + sx) : make_float2(0.f, 0.f);
-        }
-}
+// ---- sliding 3x3 window over dpr for a warp that walks pixels in row-major order -------------------
+// col[j][r] = dpr[y-1+r][x-1+j] (zero outside the map).  Moving one pixel right shifts the columns and
+// loads ONE new column (3 float2) instead of 9 values; the next column is requested before the FMAs of the
+// current pixel so that its latency hides behind them.
+struct DprWindow {
+    float2 col[3][3];
+    float2 nxt[3];
+    int x, y, h, w;
+    const float2 *img;      // dpr of the current image
 
-constexpr int HD_UNROLL = 4;   // pixels in flight per warp (independent loads -> latency hiding)
+    __device__ __forceinline__ void load_col(int sx, float2 out[3]) const {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int sy = y - 1 + r;
+            out[r] = (sx >= 0 && sx < w && sy >= 0 && sy < h) ? __ldg(img + (long long)sy * w + sx) : make_float2(0.f, 0.f);
+        }
+    }
+    __device__ __forceinline__ void start(const float2 *dpr, long long p, int h_, int w_) {
+        h = h_; w = w_;
+        x = (int)(p % w); y = (int)((p / w) % h);
+        img = dpr + (p - ((long long)y * w + x));
+        load_col(x - 1, col[0]); load_col(x, col[1]); load_col(x + 1, col[2]);
+    }
+    __device__ __forceinline__ void prefetch_next() { load_col(x + 2, nxt); }   // harmless at a row end (reloaded there)
+    __device__ __forceinline__ void advance() {
+        ++x;
+        if (x < w) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { col[0][r] = col[1][r]; col[1][r] = col[2][r]; col[2][r] = nxt[r]; }
+        } else {
+            x = 0; ++y;
+            if (y == h) { y = 0; img += (long long)h * w; }
+            load_col(-1, col[0]); load_col(0, col[1]); load_col(1, col[2]);
+        }
+    }
+    // dpr seen through tap (kh,kw) of the TRANSPOSED stencil: (y - kh + 1, x - kw + 1)
+    __device__ __forceinline__ float2 tap(int kh, int kw) const { return col[2 - kw][2 - kh]; }
+};
 
 // ---- pr input gradient: lane owns 4 channels (72 weights in registers), warp streams pixels ----
 // dX[b,y,x,ch] (+)= sum_{kh,kw,o} dpr[b,y-kh+1,x-kw+1,o] * W[kh,kw,ch,o]
-__global__ void __launch_bounds__(256) head_dgrad_kernel(const float *__restrict__ dpr, int B, int h, int w, int c,
-                                                         const float *__restrict__ Wt, float *__restrict__ dX, int dx_ld,
-                                                         int accumulate, long long pix_per_warp) {
+__global__ void __launch_bounds__(256, 2) head_dgrad_kernel(const float *__restrict__ dpr, int B, int h, int w, int c,
+                                                            const float *__restrict__ Wt, float *__restrict__ dX, int dx_ld,
+                                                            int accumulate, long long pix_per_warp) {
     const int lane = threadIdx.x & 31;
     const int ch = (blockIdx.y * 32 + lane) * 4;
     if (ch >= c) return;
@@ -106,40 +130,36 @@ __global__ void __launch_bounds__(256) head_dgrad_kernel(const float *__restrict
     const long long wglobal = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const long long p0 = wglobal * pix_per_warp;
     const long long p1 = p0 + pix_per_warp < n_pix ? p0 + pix_per_warp : n_pix;
-    const float2 *dpr2 = reinterpret_cast<const float2 *>(dpr);
-    for (long long pb = p0; pb < p1; pb += HD_UNROLL) {
-        float2 g[HD_UNROLL][9];
-        float4 old[HD_UNROLL];
+    if (p0 >= p1) return;
+    DprWindow win;
+    win.start(reinterpret_cast<const float2 *>(dpr), p0, h, w);
+    for (long long p = p0; p < p1; ++p) {
+        float4 *dst = reinterpret_cast<float4 *>(dX + p * dx_ld + ch);
+        float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (accumulate) old = *dst;
+        win.prefetch_next();
+        float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
 #pragma unroll
-        for (int u = 0; u < HD_UNROLL; ++u) {
-            if (pb + u < p1) {
-                load_dpr9(dpr2, pb + u, h, w, g[u]);
-                if (accumulate) old[u] = *reinterpret_cast<const float4 *>(dX + (pb + u) * dx_ld + ch);
-            }
-        }
+        for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-        for (int u = 0; u < HD_UNROLL; ++u) {
-            if (pb + u >= p1) break;
-            float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-#pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-                const float2 gg = g[u][tap];
+            for (int kw = 0; kw < 3; ++kw) {
+                const float2 gg = win.tap(kh, kw);
+                const int tap = kh * 3 + kw;
                 o0 += gg.x * wr[tap][0][0] + gg.y * wr[tap][0][1];
                 o1 += gg.x * wr[tap][1][0] + gg.y * wr[tap][1][1];
                 o2 += gg.x * wr[tap][2][0] + gg.y * wr[tap][2][1];
                 o3 += gg.x * wr[tap][3][0] + gg.y * wr[tap][3][1];
             }
-            if (accumulate) { o0 += old[u].x; o1 += old[u].y; o2 += old[u].z; o3 += old[u].w; }
-            *reinterpret_cast<float4 *>(dX + (pb + u) * dx_ld + ch) = make_float4(o0, o1, o2, o3);
-        }
+        *dst = make_float4(o0 + old.x, o1 + old.y, o2 + old.z, o3 + old.w);
+        win.advance();
     }
 }
 
 // ---- pr weight gradient: lane owns 4 channels, 72 accumulators; X is read exactly once ----
-// dW[kh,kw,ch,o] += sum_q X[q,ch] * dpr[q - off(kh,kw), o]   (q = input pixel)
-__global__ void __launch_bounds__(256) head_wgrad_kernel(const float *__restrict__ X, int x_ld, const float *__restrict__ dpr,
-                                                         int B, int h, int w, int c, float *__restrict__ dWt,
-                                                         float *__restrict__ dbias, long long pix_per_warp) {
+// dW[kh,kw,ch,o] += sum_q X[q,ch] * dpr[q - off(kh,kw), o]   (q = input pixel; same 3x3 window as the input gradient)
+__global__ void __launch_bounds__(256, 2) head_wgrad_kernel(const float *__restrict__ X, int x_ld, const float *__restrict__ dpr,
+                                                            int B, int h, int w, int c, float *__restrict__ dWt,
+                                                            float *__restrict__ dbias, long long pix_per_warp) {
     __shared__ float red[72][33];
     __shared__ float redb[2];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -158,33 +178,28 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(const float *__restrict
     const long long p0 = wglobal * pix_per_warp;
     const long long p1 = p0 + pix_per_warp < n_pix ? p0 + pix_per_warp : n_pix;
     const bool active = ch < c;
-    const float2 *dpr2 = reinterpret_cast<const float2 *>(dpr);
-    for (long long pb = p0; pb < p1; pb += HD_UNROLL) {
-        float2 g[HD_UNROLL][9];
-        float4 xv[HD_UNROLL];
+    if (p0 < p1) {
+        DprWindow win;
+        win.start(reinterpret_cast<const float2 *>(dpr), p0, h, w);
+        float4 xv = active ? __ldg(reinterpret_cast<const float4 *>(X + p0 * x_ld + ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (long long p = p0; p < p1; ++p) {
+            float4 xn = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (active && p + 1 < p1) xn = __ldg(reinterpret_cast<const float4 *>(X + (p + 1) * x_ld + ch));
+            win.prefetch_next();
 #pragma unroll
-        for (int u = 0; u < HD_UNROLL; ++u) {
-            xv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (pb + u < p1) {
-                // the output pixel reading q through tap (kh,kw) sits at q - (kh-1, kw-1): same 9-neighbourhood
-                load_dpr9(dpr2, pb + u, h, w, g[u]);
-                if (active) xv[u] = __ldg(reinterpret_cast<const float4 *>(X + (pb + u) * x_ld + ch));
-            } else {
+            for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) g[u][tap] = make_float2(0.f, 0.f);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < HD_UNROLL; ++u) {
-#pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-                const float2 gg = g[u][tap];
-                acc[tap][0][0] += xv[u].x * gg.x; acc[tap][0][1] += xv[u].x * gg.y;
-                acc[tap][1][0] += xv[u].y * gg.x; acc[tap][1][1] += xv[u].y * gg.y;
-                acc[tap][2][0] += xv[u].z * gg.x; acc[tap][2][1] += xv[u].z * gg.y;
-                acc[tap][3][0] += xv[u].w * gg.x; acc[tap][3][1] += xv[u].w * gg.y;
-            }
-            if (blockIdx.y == 0 && lane == 0) { b0 += g[u][4].x; b1 += g[u][4].y; }   // centre tap = dpr[q]
+                for (int kw = 0; kw < 3; ++kw) {
+                    const float2 gg = win.tap(kh, kw);
+                    const int tap = kh * 3 + kw;
+                    acc[tap][0][0] += xv.x * gg.x; acc[tap][0][1] += xv.x * gg.y;
+                    acc[tap][1][0] += xv.y * gg.x; acc[tap][1][1] += xv.y * gg.y;
+                    acc[tap][2][0] += xv.z * gg.x; acc[tap][2][1] += xv.z * gg.y;
+                    acc[tap][3][0] += xv.w * gg.x; acc[tap][3][1] += xv.w * gg.y;
+                }
+            if (blockIdx.y == 0 && lane == 0) { const float2 cc = win.tap(1, 1); b0 += cc.x; b1 += cc.y; }
+            xv = xn;
+            win.advance();
         }
     }
     // block-level combine in shared memory, then one global atomic per (tap,ch,o) per block
