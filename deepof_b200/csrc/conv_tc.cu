@@ -155,6 +155,7 @@ struct TcParams {
     int y0, x0, rstep;           // output pixel = (y0 + rstep*iy, x0 + rstep*ix)
     int B, cnt_y, cnt_x;         // row sub-grid
     int TW, TH, TN, tiles_x, tiles_y;
+    int m_tiles, n_tiles;        // tiles along pixels / output channels (persistent scheduler)
     int a_coff;                  // channel offset of the A slab inside its buffer
     int a_ld;                    // pitch of A (parity mode: px*a_ld + c)
     int ncb;                     // 32-channel blocks per tap
@@ -164,31 +165,35 @@ struct TcParams {
     TapInfo taps[TC_MAX_TAPS];
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, += gridDim.x (M fastest, so CTAs running
+// at the same time share the weight tile in L2).  Two TMEM accumulators: the epilogue of tile i overlaps the MMAs of tile i+1.
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ TcParams P) {
     constexpr int B_BYTES = BN * TC_BK * 4;
     constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
-    constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    constexpr int ACC_COLS = BN < 32 ? 32 : BN;
+    constexpr int TMEM_COLS = 2 * ACC_COLS;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
     uint64_t *empty_bar = full_bar + STAGES;
-    uint64_t *accum_bar = empty_bar + STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
+    uint64_t *acc_full = empty_bar + STAGES;       // [2] MMA -> epilogue
+    uint64_t *acc_empty = acc_full + 2;            // [2] epilogue -> MMA (4 warps arrive)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // ---- tile coordinates ----
-    const int tile = blockIdx.x;
-    const int tx = tile % P.tiles_x, ty = (tile / P.tiles_x) % P.tiles_y, tn = tile / (P.tiles_x * P.tiles_y);
-    const int ix0 = tx * P.TW, iy0 = ty * P.TH, in0 = tn * P.TN;
-    const int n0 = blockIdx.y * BN;
     const int kiters = P.ntaps * P.ncb;
+    const int m_tiles = P.m_tiles, total_tiles = P.m_tiles * P.n_tiles;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(accum_bar, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
         fence_barrier_init();
     }
     if (warp == 4 && lane == 0) { prefetch_tmap(&map_a); prefetch_tmap(&map_b); }
@@ -201,83 +206,106 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     if (warp == 4) {
         // ===== TMA producer =====
         if (lane == 0) {
-            for (int it = 0; it < kiters; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(&empty_bar[s], ph ^ 1);
-                const int t = it / P.ncb, cb = it - t * P.ncb;
-                const TapInfo ti = P.taps[t];
-                uint8_t *sa = smem + s * STAGE_BYTES;
-                uint8_t *sb = sa + TC_A_BYTES;
-                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-                if (P.parity)
-                    tma_load_5d(sa, &map_a, &full_bar[s], ti.px * P.a_ld + P.a_coff + cb * TC_BK, ix0 + ti.ox, ti.py, iy0 + ti.oy, in0);
-                else
-                    tma_load_4d(sa, &map_a, &full_bar[s], P.a_coff + cb * TC_BK, ix0 + ti.ox, iy0 + ti.oy, in0);
-                tma_load_2d(sb, &map_b, &full_bar[s], ti.wk + cb * TC_BK, n0);
+            int it = 0;                                   // running k-iteration count across tiles
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int mt = t % m_tiles, nt = t / m_tiles;
+                const int tx = mt % P.tiles_x, ty = (mt / P.tiles_x) % P.tiles_y, tn = mt / (P.tiles_x * P.tiles_y);
+                const int ix0 = tx * P.TW, iy0 = ty * P.TH, in0 = tn * P.TN, n0 = nt * BN;
+                for (int k = 0; k < kiters; ++k, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    const int tp = k / P.ncb, cb = k - tp * P.ncb;
+                    const TapInfo ti = P.taps[tp];
+                    uint8_t *sa = smem + s * STAGE_BYTES;
+                    uint8_t *sb = sa + TC_A_BYTES;
+                    mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                    if (P.parity)
+                        tma_load_5d(sa, &map_a, &full_bar[s], ti.px * P.a_ld + P.a_coff + cb * TC_BK, ix0 + ti.ox, ti.py, iy0 + ti.oy, in0);
+                    else
+                        tma_load_4d(sa, &map_a, &full_bar[s], P.a_coff + cb * TC_BK, ix0 + ti.ox, iy0 + ti.oy, in0);
+                    tma_load_2d(sb, &map_b, &full_bar[s], ti.wk + cb * TC_BK, n0);
+                }
             }
         }
     } else if (warp == 5) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN);
-            for (int it = 0; it < kiters; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
+            int it = 0, lt = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+                const int acc = lt & 1;
+                mbar_wait(&acc_empty[acc], ((lt >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-                const uint64_t da = make_desc_k128(sa), db = make_desc_k128(sa + TC_A_BYTES);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
+                for (int k = 0; k < kiters; ++k, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+                    const uint64_t da = make_desc_k128(sa), db = make_desc_k128(sa + TC_A_BYTES);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 8; ++k)     // UMMA_K = 8 for tf32: advance 32 B inside the 128 B swizzle row
-                    umma_tf32(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (it | k) != 0);
-                umma_commit(&empty_bar[s]);             // frees the smem slot when these MMAs retire
+                    for (int kk = 0; kk < TC_BK / 8; ++kk)  // UMMA_K = 8 for tf32: advance 32 B inside the 128 B swizzle row
+                        umma_tf32(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (k | kk) != 0);
+                    umma_commit(&empty_bar[s]);             // frees the smem slot when these MMAs retire
+                }
+                umma_commit(&acc_full[acc]);                // accumulator complete
             }
-            umma_commit(accum_bar);                     // accumulator complete
         }
     } else {
         // ===== epilogue: TMEM -> registers -> bias/ELU -> NHWC global =====
-        const int r = warp * 32 + lane;                 // row of the tile == TMEM lane
-        const int ix = ix0 + r % P.TW, iy = iy0 + (r / P.TW) % P.TH, nn = in0 + r / (P.TW * P.TH);
-        const bool row_ok = ix < P.cnt_x && iy < P.cnt_y && nn < P.B;
-        float *orow = P.out + (((long long)nn * P.rh + P.y0 + iy * P.rstep) * P.rw + P.x0 + ix * P.rstep) * P.out_ld;
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
+        const int r = warp * 32 + lane;                     // row of the tile == TMEM lane
         const bool vec_ok = ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0) && (P.out_ld % 4 == 0);
+        int lt = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+            const int mt = t % m_tiles, nt = t / m_tiles;
+            const int tx = mt % P.tiles_x, ty = (mt / P.tiles_x) % P.tiles_y, tn = mt / (P.tiles_x * P.tiles_y);
+            const int ix = tx * P.TW + r % P.TW, iy = ty * P.TH + (r / P.TW) % P.TH, nn = tn * P.TN + r / (P.TW * P.TH);
+            const int n0 = nt * BN;
+            const bool row_ok = ix < P.cnt_x && iy < P.cnt_y && nn < P.B;
+            float *orow = P.out + (((long long)nn * P.rh + P.y0 + iy * P.rstep) * P.rw + P.x0 + ix * P.rstep) * P.out_ld;
+            const int acc = lt & 1;
+            mbar_wait(&acc_full[acc], (lt >> 1) & 1);
+            tc_fence_after();
 #pragma unroll 1
-        for (int j = 0; j < BN / 32 + (BN < 32 ? 1 : 0); ++j) {
-            float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * 32), v);
-            if (!row_ok) continue;
-            const int cbase = n0 + j * 32;
+            for (int j = 0; j < BN / 32; ++j) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * ACC_COLS + j * 32), v);
+                if (!row_ok) continue;
+                const int cbase = n0 + j * 32;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int col = cbase + q * 4;
-                if (col >= P.n_valid) break;
-                float o[4] = {v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]};
+                for (int q = 0; q < 8; ++q) {
+                    const int col = cbase + q * 4;
+                    if (col >= P.n_valid) break;
+                    float o[4] = {v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    if (col + e < P.n_valid) {
-                        if (P.bias) o[e] += __ldg(P.bias + col + e);
-                        if (P.act == DOFB_ACT_ELU) o[e] = elu_f(o[e]);
+                    for (int e = 0; e < 4; ++e) {
+                        if (col + e < P.n_valid) {
+                            if (P.bias) o[e] += __ldg(P.bias + col + e);
+                            if (P.act == DOFB_ACT_ELU) o[e] = elu_f(o[e]);
+                        }
                     }
-                }
-                if (vec_ok && col + 3 < P.n_valid) {
-                    float4 *dst = reinterpret_cast<float4 *>(orow + col);
-                    if (P.accumulate) {
-                        const float4 old = *dst;
-                        o[0] += old.x; o[1] += old.y; o[2] += old.z; o[3] += old.w;
-                    }
-                    *dst = make_float4(o[0], o[1], o[2], o[3]);
-                } else {
+                    if (vec_ok && col + 3 < P.n_valid) {
+                        float4 *dst = reinterpret_cast<float4 *>(orow + col);
+                        if (P.accumulate) {
+                            const float4 old = *dst;
+                            o[0] += old.x; o[1] += old.y; o[2] += old.z; o[3] += old.w;
+                        }
+                        *dst = make_float4(o[0], o[1], o[2], o[3]);
+                    } else {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (col + e < P.n_valid) orow[col + e] = P.accumulate ? orow[col + e] + o[e] : o[e];
+                        for (int e = 0; e < 4; ++e)
+                            if (col + e < P.n_valid) orow[col + e] = P.accumulate ? orow[col + e] + o[e] : o[e];
+                    }
                 }
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);    // this warp's quarter of the accumulator is free again
         }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 5) {
         tc_fence_after();
@@ -376,14 +404,18 @@ static void choose_tile(int cnt_y, int cnt_x, int &TW, int &TH, int &TN) {
 }
 
 template <int BN, int STAGES>
-static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &P, int tiles, int n_tiles, cudaStream_t st) {
+static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &Pin, int tiles, int n_tiles, cudaStream_t st) {
     constexpr int smem = STAGES * (TC_A_BYTES + BN * TC_BK * 4) + 1024 + 256;
     static bool configured = false;
     if (!configured) {
         DOFB_CUDA_OK(cudaFuncSetAttribute(tc_gather_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    tc_gather_gemm_kernel<BN, STAGES><<<dim3(tiles, n_tiles, 1), TC_THREADS, smem, st>>>(ma, mb, P);
+    TcParams P = Pin;
+    P.m_tiles = tiles; P.n_tiles = n_tiles;
+    const long long total = (long long)tiles * n_tiles;
+    const int grid = (int)(total < num_sms() ? total : num_sms());
+    tc_gather_gemm_kernel<BN, STAGES><<<grid, TC_THREADS, smem, st>>>(ma, mb, P);
     DOFB_LAUNCH_OK();
     return 0;
 }
@@ -443,7 +475,8 @@ static int run_gather(const GatherSpec &G, const TcParams &Pin, cudaStream_t st)
         const uint32_t box[5] = {(uint32_t)TC_BK, (uint32_t)P.TW, 1, (uint32_t)P.TH, (uint32_t)P.TN};
         if (make_map(&ma, G.a_base, 5, dims, str, box)) return 1;
     }
-    const int bn = n_rows > 128 ? 256 : (n_rows > 64 ? 128 : (n_rows > 32 ? 64 : 32));
+    int bn = n_rows > 128 ? 256 : (n_rows > 64 ? 128 : (n_rows > 32 ? 64 : 32));
+    while (bn > 64 && (long long)tiles * ((n_rows + bn - 1) / bn) < num_sms()) bn >>= 1;   // small maps: more, narrower tiles
     {
         const uint64_t dims[2] = {(uint64_t)taps_all * cpad, (uint64_t)n_rows};
         const uint64_t str[1] = {(uint64_t)taps_all * cpad * 4};

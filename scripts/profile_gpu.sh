@@ -1,0 +1,16 @@
+#!/bin/bash
+# Run on the GPU box (under gpurun): launch list + full ncu captures of the top kernels.  Outputs -> gpurun_out/
+set -u
+mkdir -p gpurun_out
+MATH=${1:-tf32}
+# 1) every launch of ~2 steps with its device time (cold-cache, serialised: compare shares, not absolutes)
+ncu --metrics gpu__time_duration.sum --clock-control none -s 800 -c 420 --csv --log-file gpurun_out/launches_${MATH}.csv \
+    python bench.py --math $MATH --steps 3 --warmup 3 --no-cpu > gpurun_out/ncu_bench_${MATH}.log 2>&1
+# 2) full-set captures of the dominant kernels (3 launches each, after the warm-up)
+ncu --set full --clock-control none --import-source on -k regex:tc_gather_gemm -s 60 -c 4 -f -o gpurun_out/prof_tc_gemm \
+    python bench.py --math $MATH --steps 1 --warmup 3 --no-cpu > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:tc_wgrad -s 30 -c 3 -f -o gpurun_out/prof_tc_wgrad \
+    python bench.py --math $MATH --steps 1 --warmup 3 --no-cpu > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"warp_loss|head_dgrad|head_wgrad|head_fwd|adam" -s 40 -c 6 -f -o gpurun_out/prof_hbm \
+    python bench.py --math $MATH --steps 1 --warmup 3 --no-cpu > /dev/null 2>&1
+ls -la gpurun_out/*.ncu-rep gpurun_out/launches_${MATH}.csv
