@@ -590,6 +590,22 @@ struct WgParams {
     TapInfo taps[TC_MAX_TAPS];               // wk = canonical tap index (kh*KW + kw); conv1 mode: one entry per filter row
 };
 
+// accumulate 32 consecutive fp32 values into dst with the widest atomic the alignment allows (sm_90+: red.global.add.v4/v2.f32)
+__device__ __forceinline__ void atomic_add_row32(float *dst, const float *v, int n_ok) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(dst);
+    if ((a & 15) == 0 && n_ok == 32) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) atomicAdd(reinterpret_cast<float4 *>(dst) + q, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+    } else if ((a & 7) == 0 && n_ok == 32) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) atomicAdd(reinterpret_cast<float2 *>(dst) + q, make_float2(v[2 * q], v[2 * q + 1]));
+    } else {
+#pragma unroll
+        for (int q = 0; q < 32; ++q)
+            if (q < n_ok) atomicAdd(dst + q, v[q]);
+    }
+}
+
 __device__ __forceinline__ uint64_t make_desc_mn128(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
@@ -640,44 +656,49 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     const TapInfo ti = P.taps[tapi];
 
     if (warp == 4) {
-        if (lane == 0) {
-            // channel origin of the X / DY operand and how many 32-channel blocks each needs
-            const int x_c0 = P.swap ? n0 : m0, dy_c0 = P.swap ? m0 : n0;
-            const int x_blocks = P.swap ? BN / 32 : 4, dy_blocks = P.swap ? 4 : BN / 32;
-            for (int it = 0; it < kiters; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
+        // ===== TMA producer: lane 0 owns the barrier hand-shake, lanes 0..(4+BN/32) issue one 4 KB box each =====
+        // channel origin of the X / DY operand and how many 32-channel blocks each needs
+        const int x_c0 = P.swap ? n0 : m0, dy_c0 = P.swap ? m0 : n0;
+        const int x_blocks = P.swap ? BN / 32 : 4, dy_blocks = P.swap ? 4 : BN / 32;
+        for (int it = 0; it < kiters; ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
+            if (lane == 0) {
                 mbar_wait(&empty_bar[s], ph ^ 1);
-                const int tile = t_begin + it;
-                const int tx = tile % P.tiles_x, ty = (tile / P.tiles_x) % P.tiles_y, tn = tile / (P.tiles_x * P.tiles_y);
-                const int ix0 = tx * P.TW, iy0 = ty * P.TH, in0 = tn * P.TN;
-                uint8_t *sa = smem + s * STAGE_BYTES;
-                uint8_t *sb = sa + A_BYTES;
-                uint8_t *sx = P.swap ? sb : sa, *sd = P.swap ? sa : sb;
                 mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-                for (int j = 0; j < x_blocks; ++j) {
-                    if (P.conv1) {
-                        // region j = filter row 2*tapi + (j>>1), floats [(j&1)*32, +32) of its 8-pixel chunk
-                        const int kh = min(2 * tapi + (j >> 1), P.c1_kh - 1);      // (an odd kh count re-loads the last row; masked later)
-                        const TapInfo tr = P.taps[kh];
-                        tma_load_5d(sx + j * WG_REGION, &map_x, &full_bar[s], (j & 1) * 32, ix0, tr.py, iy0 + tr.oy, in0);
-                    } else {
-                        TapInfo tr = ti;
-                        int c0 = x_c0 + j * 32;
-                        if (P.pack_g > 1) {     // region j = tap (tapi*G + j/per), channel block j%per
-                            const int per = P.pack_cb >> 5;
-                            tr = P.taps[min(tapi * P.pack_g + j / per, P.ntaps_real - 1)];
-                            c0 = (j % per) * 32;
-                        }
-                        if (P.parity)
-                            tma_load_5d(sx + j * WG_REGION, &map_x, &full_bar[s], tr.px * P.x_ld + c0, ix0 + tr.ox, tr.py, iy0 + tr.oy, in0);
-                        else
-                            tma_load_4d(sx + j * WG_REGION, &map_x, &full_bar[s], c0, ix0 + tr.ox, iy0 + tr.oy, in0);
-                    }
-                }
-                for (int j = 0; j < dy_blocks; ++j)
-                    tma_load_4d(sd + j * WG_REGION, &map_dy, &full_bar[s], dy_c0 + j * 32, ix0, iy0, in0);
             }
+            __syncwarp();
+            const int tile = t_begin + it;
+            const int tx = tile % P.tiles_x, ty = (tile / P.tiles_x) % P.tiles_y, tn = tile / (P.tiles_x * P.tiles_y);
+            const int ix0 = tx * P.TW, iy0 = ty * P.TH, in0 = tn * P.TN;
+            uint8_t *sa = smem + s * STAGE_BYTES;
+            uint8_t *sb = sa + A_BYTES;
+            uint8_t *sx = P.swap ? sb : sa, *sd = P.swap ? sa : sb;
+            if (lane < x_blocks) {
+                const int j = lane;
+                if (P.conv1) {
+                    // region j = filter row 2*tapi + (j>>1), floats [(j&1)*32, +32) of its 8-pixel chunk
+                    const int kh = min(2 * tapi + (j >> 1), P.c1_kh - 1);      // (an odd kh count re-loads the last row; masked later)
+                    const TapInfo tr = P.taps[kh];
+                    tma_load_5d(sx + j * WG_REGION, &map_x, &full_bar[s], (j & 1) * 32, ix0, tr.py, iy0 + tr.oy, in0);
+                } else {
+                    TapInfo tr = ti;
+                    int c0 = x_c0 + j * 32;
+                    if (P.pack_g > 1) {     // region j = tap (tapi*G + j/per), channel block j%per
+                        const int per = P.pack_cb >> 5;
+                        tr = P.taps[min(tapi * P.pack_g + j / per, P.ntaps_real - 1)];
+                        c0 = (j % per) * 32;
+                    }
+                    if (P.parity)
+                        tma_load_5d(sx + j * WG_REGION, &map_x, &full_bar[s], tr.px * P.x_ld + c0, ix0 + tr.ox, tr.py, iy0 + tr.oy, in0);
+                    else
+                        tma_load_4d(sx + j * WG_REGION, &map_x, &full_bar[s], c0, ix0 + tr.ox, iy0 + tr.oy, in0);
+                }
+            } else if (lane < x_blocks + dy_blocks) {
+                const int j = lane - x_blocks;
+                tma_load_4d(sd + j * WG_REGION, &map_dy, &full_bar[s], dy_c0 + j * 32, ix0, iy0, in0);
+            }
+            __syncwarp();
         }
     } else if (warp == 5) {
         if (lane == 0) {
@@ -709,34 +730,28 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             if (P.conv1) {
                 const int kh = 2 * tapi + (r >> 6), kw = (r & 63) >> 3, ci = r & 7;
                 if (kh >= P.c1_kh || kw >= P.c1_kw || ci >= P.CI) continue;
-                float *dst = P.dW + (((long long)kh * P.c1_kw + kw) * P.CI + ci) * P.CO;
-#pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    const int ncol = n0 + j * 32 + q;
-                    if (ncol >= P.n_valid) break;
-                    atomicAdd(dst + ncol, v[q]);
-                }
+                float *dst = P.dW + (((long long)kh * P.c1_kw + kw) * P.CI + ci) * P.CO + n0 + j * 32;
+                atomic_add_row32(dst, v, min(32, P.n_valid - (n0 + j * 32)));
                 continue;
             }
             if (P.pack_g > 1) {
                 const int tsel = tapi * P.pack_g + r / P.pack_cb, ci = r % P.pack_cb;
                 if (tsel >= P.ntaps_real || ci >= P.CI) continue;
-                float *dst = P.dW + ((long long)P.taps[tsel].wk * P.CI + ci) * P.CO;
-#pragma unroll
-                for (int q = 0; q < 32; ++q) {
-                    const int ncol = n0 + j * 32 + q;
-                    if (ncol >= P.n_valid) break;
-                    atomicAdd(dst + ncol, v[q]);
-                }
+                float *dst = P.dW + ((long long)P.taps[tsel].wk * P.CI + ci) * P.CO + n0 + j * 32;
+                atomic_add_row32(dst, v, min(32, P.n_valid - (n0 + j * 32)));
                 continue;
             }
             if (mrow >= P.m_valid) continue;
+            if (!P.swap) {
+                if (n0 + j * 32 < P.n_valid)
+                    atomic_add_row32(P.dW + ((long long)tap * P.CI + mrow) * P.CO + n0 + j * 32, v, min(32, P.n_valid - (n0 + j * 32)));
+                continue;
+            }
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
                 const int ncol = n0 + j * 32 + q;
                 if (ncol >= P.n_valid) break;
-                const int ci = P.swap ? ncol : mrow, co = P.swap ? mrow : ncol;
-                atomicAdd(P.dW + ((long long)tap * P.CI + ci) * P.CO + co, v[q]);
+                atomicAdd(P.dW + ((long long)tap * P.CI + ncol) * P.CO + mrow, v[q]);     // swapped: rows = co (coalesced across lanes)
             }
         }
         tc_fence_before();

@@ -19,7 +19,10 @@ WEIGHT_L = [16, 8, 4, 2, 1, 1]      # :165
 
 
 class TrainStep:
-    """train_op + the fetches of flyingChairsTrain.trainNet."""
+    """train_op + the fetches of flyingChairsTrain.trainNet.
+
+    Host<->device traffic is pipelined like a training loop would do it by hand: two device input buffers, a copy stream,
+    and a lagged loss read-back -- the H2D copy of step i+1 and the D2H of step i's loss overlap the kernels of step i."""
 
     def __init__(self, batch_size: int, image_size=(384, 512), device="cuda", variant="A", math_mode="fp32",
                  seed: int | None = 1, distributed: bool = False, **kw):
@@ -27,36 +30,65 @@ class TrainStep:
                                seed=seed, **kw)
         self.device = self.engine.device
         B, H, W = batch_size, image_size[0], image_size[1]
-        # pinned staging: the feed_dict H2D copy of flyingChairsTrain.py:178
-        self._pin_src = torch.empty(B, H, W, 3, dtype=torch.float32).pin_memory()
-        self._pin_tgt = torch.empty(B, H, W, 3, dtype=torch.float32).pin_memory()
-        self._dev_src = torch.empty(B, H, W, 3, dtype=torch.float32, device=self.device)
-        self._dev_tgt = torch.empty(B, H, W, 3, dtype=torch.float32, device=self.device)
+        shape = (B, H, W, 3)
+        # pinned staging for pageable (numpy) feeds: the feed_dict H2D copy of flyingChairsTrain.py:178
+        self._pin = [[torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(2)] for _ in range(2)]
+        self._dev = [[torch.empty(shape, dtype=torch.float32, device=self.device) for _ in range(2)] for _ in range(2)]
+        self._copy_stream = torch.cuda.Stream(device=self.device)
+        self._copied = [torch.cuda.Event() for _ in range(2)]       # H2D of slot i finished
+        self._consumed = [torch.cuda.Event() for _ in range(2)]     # the step reading slot i has consumed its inputs
+        self._loss_pin = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self._loss_ready = [torch.cuda.Event() for _ in range(2)]
+        self._n = 0
         self.reducer = _ddp.GradReducer(self.engine) if distributed else None
         if self.reducer is not None:
             self.reducer.broadcast_params()
 
     def _feed(self, source, target):
+        """Stage one batch; returns device tensors valid for the current stream."""
         if isinstance(source, torch.Tensor) and source.is_cuda:
             return source, target
-        self._pin_src.copy_(torch.as_tensor(source, dtype=torch.float32))
-        self._pin_tgt.copy_(torch.as_tensor(target, dtype=torch.float32))
-        self._dev_src.copy_(self._pin_src, non_blocking=True)
-        self._dev_tgt.copy_(self._pin_tgt, non_blocking=True)
-        return self._dev_src, self._dev_tgt
+        slot = self._n & 1
+        host = []
+        for j, arr in enumerate((source, target)):
+            t = torch.as_tensor(arr, dtype=torch.float32)
+            if not t.is_pinned():                     # pageable feed (numpy): one host memcpy into pinned staging
+                self._copied[slot].synchronize()      # the previous H2D out of this staging buffer is done
+                self._pin[slot][j].copy_(t)
+                t = self._pin[slot][j]
+            host.append(t)
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(self._consumed[slot])      # step n-2 no longer reads this device buffer
+            self._dev[slot][0].copy_(host[0], non_blocking=True)
+            self._dev[slot][1].copy_(host[1], non_blocking=True)
+            self._copied[slot].record(self._copy_stream)
+        cur.wait_event(self._copied[slot])
+        return self._dev[slot][0], self._dev[slot][1]
 
     def run(self, feed_dict: dict):
-        """train_op.run(feed_dict={'source_img','target_img','loss_weight','learning_rate'})."""
+        """train_op.run(feed_dict={'source_img','target_img','loss_weight','learning_rate'}) -- asynchronous."""
+        slot = self._n & 1
         src, tgt = self._feed(feed_dict["source_img"], feed_dict["target_img"])
         lw = feed_dict.get("loss_weight", WEIGHT_L)
         lr = float(feed_dict.get("learning_rate", LEARNING_RATE))
-        self.engine.train_step(src, tgt, lw, lr, allreduce=self.reducer)
+        self.engine.forward(src, tgt, lw, with_grad=True)
+        self._consumed[slot].record()                 # inputs are only read by the pre-processing kernel
+        self.engine.backward()
+        scale = self.reducer(self.engine.grad) if self.reducer is not None else 1.0
+        self.engine.adam_step(lr, grad_scale=scale)
+        # lagged loss read-back: D2H into pinned memory, consumed one step later (or by last_loss(sync=True))
+        self._loss_pin[slot:slot + 1].copy_(self.engine.total_loss().reshape(1), non_blocking=True)
+        self._loss_ready[slot].record()
+        self._n += 1
 
     def fetch(self, feed_dict: dict):
         """sess.run([loss, midFlows, total_loss], feed_dict) -> numpy (flyingChairsTrain.py:181)."""
         src, tgt = self._feed(feed_dict["source_img"], feed_dict["target_img"])
         lw = feed_dict.get("loss_weight", WEIGHT_L)
         self.engine.forward(src, tgt, lw, with_grad=False)
+        self._consumed[self._n & 1].record()
+        self._n += 1
         losses, flows_all, _prev = self.engine.outputs()
         l4 = self.engine.loss4.cpu().numpy()
         keys = ("total", "Charbonnier_reconstruct", "U_loss", "V_loss")
@@ -64,9 +96,14 @@ class TrainStep:
         loss_sum = float((l4[:, 0] * np.asarray(lw, dtype=np.float32)).sum())
         return losses_np, [f.cpu().numpy() for f in flows_all], loss_sum
 
-    def last_loss(self) -> float:
-        """D2H read of the weighted total of the step that just ran."""
-        return float(self.engine.total_loss().item())
+    def last_loss(self, lag: int = 0) -> float:
+        """Weighted total loss of the most recent run() (lag=0, waits for it) or of the one before (lag=1: its D2H has
+        already landed, so the host never stalls the device -- what a pipelined training loop logs)."""
+        k = self._n - 1 - lag
+        if k < 0:
+            return float("nan")
+        self._loss_ready[k & 1].synchronize()
+        return float(self._loss_pin[k & 1])
 
 
 class train:
