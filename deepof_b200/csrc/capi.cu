@@ -16,6 +16,8 @@ int tc_conv_fwd(const dofb_conv_geom *g, const float *x, int x_ld, const float *
 int tc_conv_dgrad(const dofb_conv_geom *g, const float *dy, int dy_ld, const float *w, const float *bias, float *dx, int dx_ld,
                   int act, int accumulate, cudaStream_t st);
 int tc_conv_wgrad(const dofb_conv_geom *g, const float *x, int x_ld, const float *dy, int dy_ld, float *dw, cudaStream_t st);
+void invalidate_weight_cache();
+void enable_weight_cache(int on);
 int tc_conv1_fwd(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *w, const float *bias,
                  float *y, int y_ld, int act, cudaStream_t st);
 int tc_conv1_wgrad(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *dy, int dy_ld,
@@ -75,3 +77,6 @@ extern "C" int dofb_conv1_wgrad(const dofb_conv_geom *g, const float *x, int xp_
     if (db) return launch_colsum(dy, dy_ld, (long long)g->B * g->oh * g->ow, g->co, db, as_stream(stream));
     return 0;
 }
+
+extern "C" void dofb_invalidate_weight_cache(void) { invalidate_weight_cache(); }
+extern "C" void dofb_enable_weight_cache(int on) { enable_weight_cache(on); }

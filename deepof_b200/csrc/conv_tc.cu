@@ -320,16 +320,35 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restrict__ W, float *__restrict__ Wp, int taps, int ci, int co,
                                                            int cpad, int contract_ci) {
-    const int n_rows = contract_ci ? co : ci;
-    const int kc = contract_ci ? ci : co;
+    // bwd orientation (contract over co): rows are already co-contiguous -> straight padded copy
+    const int n_rows = ci;
     const long long total = (long long)n_rows * taps * cpad;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % cpad);
         const int t = (int)((i / cpad) % taps);
         const int n = (int)(i / ((long long)cpad * taps));
-        float v = 0.f;
-        if (c < kc) v = contract_ci ? __ldg(W + ((long long)t * ci + c) * co + n) : __ldg(W + ((long long)t * ci + n) * co + c);
-        Wp[i] = v;
+        Wp[i] = c < co ? __ldg(W + ((long long)t * ci + n) * co + c) : 0.f;
+    }
+}
+
+// fwd orientation (contract over ci): per tap a [ci][co] -> [co][cpad] transpose through a 32x33 shared tile so that both the
+// global reads (co contiguous) and the global writes (ci contiguous) are coalesced
+__global__ void __launch_bounds__(256) pack_weights_t_kernel(const float *__restrict__ W, float *__restrict__ Wp, int taps, int ci, int co,
+                                                             int cpad) {
+    __shared__ float tile[32][33];
+    const int t = blockIdx.z;
+    const int c0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;         // 32 x 8
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r, n = n0 + tx;
+        tile[r][tx] = (c < ci && n < co) ? __ldg(W + ((long long)t * ci + c) * co + n) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int n = n0 + r, c = c0 + tx;
+        if (n < co && c < cpad) Wp[((long long)n * taps + t) * cpad + c] = tile[tx][r];
     }
 }
 
@@ -376,18 +395,38 @@ struct PackKey {
 struct PackKeyHash {
     size_t operator()(const PackKey &k) const { return std::hash<const void *>()(k.w) ^ (size_t)(k.orient * 0x9e3779b9u); }
 };
-static std::unordered_map<PackKey, std::pair<float *, size_t>, PackKeyHash> g_pack;
+struct PackEntry { float *p; size_t floats; unsigned long long epoch; };
+static std::unordered_map<PackKey, PackEntry, PackKeyHash> g_pack;
 static std::mutex g_pack_mu;
+static unsigned long long g_weight_epoch = 1;      // bumped by dofb_invalidate_weight_cache() (the optimiser step)
+static bool g_cache_enabled = false;               // off: every call re-packs (always correct); on: caller promises to invalidate
 
-static int get_pack_buffer(const void *w, int orient, size_t floats, float **out) {
+void invalidate_weight_cache() {
+    std::lock_guard<std::mutex> lk(g_pack_mu);
+    ++g_weight_epoch;
+}
+void enable_weight_cache(int on) {
+    std::lock_guard<std::mutex> lk(g_pack_mu);
+    g_cache_enabled = on != 0;
+    ++g_weight_epoch;
+}
+
+// *fresh = true when the buffer already holds the packed weights of the current epoch (no re-pack needed)
+static int get_pack_buffer(const void *w, int orient, size_t floats, float **out, bool *fresh) {
     std::lock_guard<std::mutex> lk(g_pack_mu);
     auto it = g_pack.find({w, orient});
-    if (it != g_pack.end() && it->second.second >= floats) { *out = it->second.first; return 0; }
+    if (it != g_pack.end() && it->second.floats >= floats) {
+        *out = it->second.p;
+        *fresh = g_cache_enabled && it->second.epoch == g_weight_epoch;
+        it->second.epoch = g_weight_epoch;
+        return 0;
+    }
     float *p = nullptr;
     DOFB_CUDA_OK(cudaMalloc(&p, floats * sizeof(float)));
-    if (it != g_pack.end()) { cudaFree(it->second.first); it->second = {p, floats}; }
-    else g_pack[{w, orient}] = {p, floats};
+    if (it != g_pack.end()) { cudaFree(it->second.p); it->second = {p, floats, g_weight_epoch}; }
+    else g_pack[{w, orient}] = {p, floats, g_weight_epoch};
     *out = p;
+    *fresh = false;
     return 0;
 }
 
@@ -442,12 +481,18 @@ static int run_gather(const GatherSpec &G, const TcParams &Pin, cudaStream_t st)
     // ---- pack weights ----
     float *wp = nullptr;
     const size_t wfloats = (size_t)n_rows * taps_all * cpad;
-    if (get_pack_buffer(G.w, G.contract_ci, wfloats, &wp)) return 1;
-    {
-        long long blocks = ((long long)wfloats + 255) / 256;
-        const long long cap = (long long)num_sms() * 8;
-        if (blocks > cap) blocks = cap;
-        pack_weights_kernel<<<(unsigned)blocks, 256, 0, st>>>(G.w, wp, taps_all, G.w_ci, G.w_co, cpad, G.contract_ci);
+    bool fresh = false;
+    if (get_pack_buffer(G.w, G.contract_ci, wfloats, &wp, &fresh)) return 1;
+    if (!fresh) {       // once per weight epoch and orientation (all stride phases of a dgrad share one packing)
+        if (G.contract_ci) {
+            dim3 grid((G.w_co + 31) / 32, cpad / 32, taps_all);
+            pack_weights_t_kernel<<<grid, 256, 0, st>>>(G.w, wp, taps_all, G.w_ci, G.w_co, cpad);
+        } else {
+            long long blocks = ((long long)wfloats + 255) / 256;
+            const long long cap = (long long)num_sms() * 8;
+            if (blocks > cap) blocks = cap;
+            pack_weights_kernel<<<(unsigned)blocks, 256, 0, st>>>(G.w, wp, taps_all, G.w_ci, G.w_co, cpad, 0);
+        }
         DOFB_LAUNCH_OK();
     }
     for (int t = 0; t < P.ntaps; ++t) P.taps[t].wk *= cpad;     // caller stored the canonical tap index
@@ -910,9 +955,12 @@ int tc_conv1_fwd(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, in
     const int tiles = P.tiles_x * P.tiles_y * ((g->B + P.TN - 1) / P.TN);
     float *wp = nullptr;
     const size_t wfloats = (size_t)g->co * g->kh * 64;
-    if (get_pack_buffer(w, 2, wfloats, &wp)) return 1;
-    pack_conv1_kernel<<<(unsigned)((wfloats + 255) / 256), 256, 0, st>>>(w, wp, g->kh, g->kw, g->ci, g->co);
-    DOFB_LAUNCH_OK();
+    bool fresh = false;
+    if (get_pack_buffer(w, 2, wfloats, &wp, &fresh)) return 1;
+    if (!fresh) {
+        pack_conv1_kernel<<<(unsigned)((wfloats + 255) / 256), 256, 0, st>>>(w, wp, g->kh, g->kw, g->ci, g->co);
+        DOFB_LAUNCH_OK();
+    }
     const int bn = g->co > 128 ? 256 : (g->co > 64 ? 128 : (g->co > 32 ? 64 : 32));
     const uint64_t dims[2] = {(uint64_t)g->kh * 64, (uint64_t)g->co};
     const uint64_t str[1] = {(uint64_t)g->kh * 64 * 4};

@@ -84,17 +84,35 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
     }
 }
 
-// ---- ELU backward --------------------------------------------------------------------
-__global__ void __launch_bounds__(256) elu_bwd_kernel(float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c4) {
-    const long long n = n_pix * c4;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const long long p = i / c4;
-        const int q = (int)(i - p * c4) * 4;
-        float4 gv = *reinterpret_cast<float4 *>(g + p * g_ld + q);
-        const float4 yv = __ldg(reinterpret_cast<const float4 *>(y + p * y_ld + q));
-        gv.x *= elu_grad_from_out(yv.x); gv.y *= elu_grad_from_out(yv.y);
-        gv.z *= elu_grad_from_out(yv.z); gv.w *= elu_grad_from_out(yv.w);
-        *reinterpret_cast<float4 *>(g + p * g_ld + q) = gv;
+// ---- ELU backward (+ fused bias gradient) -----------------------------------------------
+// block = 256 threads = 8 pixel rows x 32 channel quads; a block owns a channel-quad stripe [q0, q0+32) and a pixel range, so
+// the column sums of the result (BiasAddGrad) reduce in registers -> shared -> one atomicAdd per channel per block.
+__global__ void __launch_bounds__(256) elu_bwd_kernel(float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c4,
+                                                      long long pix_per_block, float *db) {
+    const int q = blockIdx.y * 32 + (threadIdx.x & 31);
+    const int prow = threadIdx.x >> 5;
+    const long long p0 = (long long)blockIdx.x * pix_per_block;
+    const long long p1 = p0 + pix_per_block < n_pix ? p0 + pix_per_block : n_pix;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < c4) {
+        for (long long p = p0 + prow; p < p1; p += 8) {
+            float4 gv = *reinterpret_cast<float4 *>(g + p * g_ld + q * 4);
+            const float4 yv = __ldg(reinterpret_cast<const float4 *>(y + p * y_ld + q * 4));
+            gv.x *= elu_grad_from_out(yv.x); gv.y *= elu_grad_from_out(yv.y);
+            gv.z *= elu_grad_from_out(yv.z); gv.w *= elu_grad_from_out(yv.w);
+            *reinterpret_cast<float4 *>(g + p * g_ld + q * 4) = gv;
+            acc.x += gv.x; acc.y += gv.y; acc.z += gv.z; acc.w += gv.w;
+        }
+    }
+    if (db == nullptr) return;
+    __shared__ float4 red[8][32];
+    red[prow][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (prow == 0 && q < c4) {
+        float4 s = red[0][threadIdx.x];
+#pragma unroll
+        for (int r = 1; r < 8; ++r) { const float4 t = red[r][threadIdx.x]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+        atomicAdd(db + q * 4, s.x); atomicAdd(db + q * 4 + 1, s.y); atomicAdd(db + q * 4 + 2, s.z); atomicAdd(db + q * 4 + 3, s.w);
     }
 }
 
@@ -192,11 +210,18 @@ extern "C" int dofb_preprocess(const float *src, const float *tgt, const float m
     return 0;
 }
 
-extern "C" int dofb_elu_bwd(float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c, void *stream) {
+extern "C" int dofb_elu_bwd(float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c, float *db, void *stream) {
     DOFB_CHECK_ARG(g && y && n_pix > 0 && c > 0, "dofb_elu_bwd: bad argument");
     DOFB_CHECK_ARG(c % 4 == 0 && g_ld % 4 == 0 && y_ld % 4 == 0 && aligned16(g) && aligned16(y),
                    "dofb_elu_bwd: channels/pitches must be multiples of 4 and pointers 16-byte aligned (c=%d)", c);
-    elu_bwd_kernel<<<grid_for(n_pix * (c / 4), 256), 256, 0, as_stream(stream)>>>(g, g_ld, y, y_ld, n_pix, c / 4);
+    const int c4 = c / 4, stripes = (c4 + 31) / 32;
+    long long blocks = (long long)num_sms() * 8 / stripes;
+    if (blocks < 1) blocks = 1;
+    long long ppb = (n_pix + blocks - 1) / blocks;
+    if (ppb < 32) ppb = 32;
+    ppb = (ppb + 7) / 8 * 8;
+    blocks = (n_pix + ppb - 1) / ppb;
+    elu_bwd_kernel<<<dim3((unsigned)blocks, stripes), 256, 0, as_stream(stream)>>>(g, g_ld, y, y_ld, n_pix, c4, ppb, db);
     DOFB_LAUNCH_OK();
     return 0;
 }

@@ -137,6 +137,7 @@ class FlowNetS:
         self._alloc()
         self._plan()
         self.warp_loss = ops.WarpLoss(self.device)
+        ops._lib.load().dofb_enable_weight_cache(1)     # this engine invalidates after every parameter change
         self.profile = None            # list of (tag, start_event, end_event) when per-launch timing is on
         if seed is not None:
             self.init_params(seed)
@@ -163,10 +164,12 @@ class FlowNetS:
             if name.startswith("up"):
                 w = bilinear_deconv(shape)
             self.params[name].copy_(w)
+        ops.invalidate_weight_cache()
 
     def load_params(self, params: dict):
         for name, p in params.items():
             self.params[name].copy_(torch.as_tensor(p, dtype=torch.float32).reshape(self.arena.shapes[name]))
+        ops.invalidate_weight_cache()
 
     def export_params(self) -> "OrderedDict[str, torch.Tensor]":
         return OrderedDict((k, v.detach().cpu().clone()) for k, v in self.params.items())
@@ -276,8 +279,12 @@ class FlowNetS:
         return losses, flows_all, self.recon1
 
     def total_loss(self) -> torch.Tensor:
-        lw = torch.tensor(self.loss_weight, dtype=torch.float32, device=self.device)
-        return (self.loss4[:, 0] * lw).sum()
+        """sum_s loss_weight[s] * total_s (flyingChairsWrapFlow.py:122-123) as a device scalar (no host sync)."""
+        key = tuple(self.loss_weight)
+        if getattr(self, "_lw_key", None) != key:      # the weights live on the device; re-uploaded only when they change
+            self._lw_dev = torch.tensor(self.loss_weight, dtype=torch.float32, device=self.device)
+            self._lw_key = key
+        return torch.dot(self.loss4[:, 0], self._lw_dev)
 
     # ------------------------------------------------------------------ backward
     def backward(self):
@@ -294,9 +301,8 @@ class FlowNetS:
             self._k("uppr_bwd:" + R["uppr"], ops.uppr_bwd, self.pr[s], R["pr_dy"], P[R["uppr"] + "/weights"], self.dpr[s],
                     G[R["uppr"] + "/weights"], G[R["uppr"] + "/biases"])
             # upconv (ELU): gradient through the activation, then weight / bias / input gradients
-            self._k("elu_bwd:" + R["up"], ops.elu_bwd, R["up_dy"], R["up_y"])
-            self._k("deconv_wgrad:" + R["up"], ops.conv_wgrad, R["g"], R["up_dy"], x, G[R["up"] + "/weights"],
-                    G[R["up"] + "/biases"], mthw, bias_on_large=True)
+            self._k("elu_bwd:" + R["up"], ops.elu_bwd, R["up_dy"], R["up_y"], G[R["up"] + "/biases"])      # + bias gradient
+            self._k("deconv_wgrad:" + R["up"], ops.conv_wgrad, R["g"], R["up_dy"], x, G[R["up"] + "/weights"], None, mthw)
             self._k("deconv_dgrad:" + R["up"], ops.conv_fwd, R["g"], R["up_dy"], P[R["up"] + "/weights"], None, dx, ACT_NONE,
                     mth)                                                   # first writer of d feat_s
             # pr_s head
@@ -304,13 +310,12 @@ class FlowNetS:
             self._k(f"head_dgrad:pr{s}", ops.head_dgrad, self.dpr[s], P[f"pr{s}/weights"], dx, accumulate=True)
         # contracting tower, top down
         for L in reversed(self.tower):
-            self._k("elu_bwd:" + L["name"], ops.elu_bwd, L["dy"], L["y"])
+            self._k("elu_bwd:" + L["name"], ops.elu_bwd, L["dy"], L["y"], G[L["name"] + "/biases"])         # + bias gradient
             if L["x"] is None:
                 self._k("conv_wgrad:" + L["name"], ops.conv1_wgrad, L["g"], self.x6, self.x6_origin, L["dy"],
-                        G[L["name"] + "/weights"], G[L["name"] + "/biases"])
+                        G[L["name"] + "/weights"], None)
             else:
-                self._k("conv_wgrad:" + L["name"], ops.conv_wgrad, L["g"], L["x"], L["dy"], G[L["name"] + "/weights"],
-                        G[L["name"] + "/biases"], mthw)
+                self._k("conv_wgrad:" + L["name"], ops.conv_wgrad, L["g"], L["x"], L["dy"], G[L["name"] + "/weights"], None, mthw)
             if L["dx"] is not None:
                 self._k("conv_dgrad:" + L["name"], ops.conv_dgrad, L["g"], L["dy"], P[L["name"] + "/weights"], None, L["dx"],
                         ACT_NONE, L["acc"], mth)
@@ -321,6 +326,7 @@ class FlowNetS:
         self.t += 1
         lr_t = lr * math.sqrt(1.0 - beta2 ** self.t) / (1.0 - beta1 ** self.t)
         self._k("adam", ops.adam, self.theta, self.grad, self.m, self.v, lr_t, beta1, beta2, eps, grad_scale)
+        ops.invalidate_weight_cache()           # the tcgen05 path re-packs its K-major weight copies lazily
 
     def train_step(self, source, target, loss_weight=LOSS_WEIGHTS, lr: float = 1.6e-5, allreduce=None):
         """One ``train_op.run(feed_dict)`` (flyingChairsTrain.py:178): forward, backward, Adam."""

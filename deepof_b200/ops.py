@@ -135,9 +135,14 @@ def conv_wgrad(g: ConvGeom, x: Slab, dy: Slab, dw, db, math=MATH_FP32, bias_on_l
     check(fn(C.byref(g), x.ptr, x.ld, dy.ptr, dy.ld, dw.data_ptr(), db.data_ptr() if db is not None else None, math, _stream()))
 
 
-def elu_bwd(g: Slab, y: Slab):
+def elu_bwd(g: Slab, y: Slab, db=None):
+    """g *= elu'(y); with db, also db += column sums of the result (the layer's bias gradient) in the same pass."""
     assert g.c == y.c and g.n_pix == y.n_pix
-    check(_lib.load().dofb_elu_bwd(g.ptr, g.ld, y.ptr, y.ld, g.n_pix, g.c, _stream()))
+    check(_lib.load().dofb_elu_bwd(g.ptr, g.ld, y.ptr, y.ld, g.n_pix, g.c, db.data_ptr() if db is not None else None, _stream()))
+
+
+def invalidate_weight_cache():
+    _lib.load().dofb_invalidate_weight_cache()
 
 
 def head_fwd(x: Slab, w, b, pr):

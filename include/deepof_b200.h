@@ -123,8 +123,16 @@ int dofb_conv1_fwd(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, 
 int dofb_conv1_wgrad(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *dy,
                      int dy_ld, float *dw, float *db, void *stream);
 
-/* g[B*h*w, 0..c) *= elu'(y) where y is the ELU OUTPUT (elu' = y>0 ? 1 : y+1). */
-int dofb_elu_bwd(float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c, void *stream);
+/* The tcgen05 path keeps re-packed (K-major, zero-padded) copies of the weights it has seen, keyed by pointer.  Call this
+ * whenever weight VALUES change (i.e. after every optimiser step / parameter load); packs are rebuilt lazily. */
+void dofb_invalidate_weight_cache(void);
+/* Off by default (every call re-packs its weights: always correct).  A caller that enables the cache promises to call
+ * dofb_invalidate_weight_cache() after changing weight values; the training engine does (once per Adam step). */
+void dofb_enable_weight_cache(int on);
+
+/* g[B*h*w, 0..c) *= elu'(y) where y is the ELU OUTPUT (elu' = y>0 ? 1 : y+1).  If db != NULL, db[c] += column sums of the
+ * result (the BiasAddGrad of the layer) in the same pass. */
+int dofb_elu_bwd(float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c, float *db, void *stream);
 
 /* ---- thin heads (N = 2: bandwidth-bound, not tensor-core shapes) ---------- */
 /* pr_s = conv3x3(feat -> 2) linear, flyingChairsWrapFlow.py:58,69,80,91,102,113 */

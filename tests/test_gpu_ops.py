@@ -9,6 +9,15 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True)
+def _no_weight_cache():
+    """Direct op calls re-use weight POINTERS with new values (allocator recycling): keep the pack cache off here.
+    (A FlowNetS engine switches it on for itself and invalidates after every parameter update.)"""
+    from deepof_b200 import _lib
+    _lib.load().dofb_enable_weight_cache(0)
+    yield
+
 from oracle import tf_ops, loss_interp as li, flownet_s as fs, adam as oadam, metrics  # noqa: E402
 
 KEYS = ("total", "Charbonnier_reconstruct", "U_loss", "V_loss")
@@ -324,8 +333,10 @@ def test_elu_bwd():
     gb[..., 16:48] = gr.cuda()
     yb = torch.zeros(2, 5, 6, 48, device="cuda")
     yb[..., 8:40] = y.cuda()
-    ops.elu_bwd(ops.Slab(gb, 16, 32), ops.Slab(yb, 8, 32))
+    db = torch.full((32,), 0.5, device="cuda")
+    ops.elu_bwd(ops.Slab(gb, 16, 32), ops.Slab(yb, 8, 32), db)
     assert rel(gb[..., 16:48], xr.grad) < 1e-6
+    assert rel(db - 0.5, xr.grad.sum(dim=(0, 1, 2))) < 1e-5          # fused BiasAddGrad
 
 
 def test_adam_matches_tf_form():

@@ -8,6 +8,15 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True)
+def _no_weight_cache():
+    """Direct op calls re-use weight POINTERS with new values (allocator recycling): keep the pack cache off here.
+    (A FlowNetS engine switches it on for itself and invalidates after every parameter update.)"""
+    from deepof_b200 import _lib
+    _lib.load().dofb_enable_weight_cache(0)
+    yield
+
 TOL = 3e-3
 
 
