@@ -8,7 +8,7 @@ namespace dofb {
 // horizontal displacements re-using the f1 fragment held in registers.
 __global__ void __launch_bounds__(256) corr_fwd_kernel(const float *__restrict__ f1, const float *__restrict__ f2, int ld, int B,
                                                        int h, int w, int c, int md, int s2, int D, float *__restrict__ out,
-                                                       int out_ld) {
+                                                       int out_ld, int act) {
     const int lane = threadIdx.x & 31;
     const long long n_items = (long long)B * h * w * D;
     const int c4 = c >> 2;
@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256) corr_fwd_kernel(const float *__restrict__
         const int sy = y - md + dyi * s2;
         float *op = out + p * out_ld + dyi * D;
         if (sy < 0 || sy >= h) {
-            for (int d = lane; d < D; d += 32) op[d] = 0.f;
+            for (int d = lane; d < D; d += 32) op[d] = 0.f;      // ELU(0) = 0
             continue;
         }
         const float *a = f1 + p * ld;
@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) corr_fwd_kernel(const float *__restrict__
                 }
             }
             acc = warp_sum(acc);
-            if (lane == 0) op[dxi] = acc * inv_c;
+            if (lane == 0) op[dxi] = act == DOFB_ACT_ELU ? elu_f(acc * inv_c) : acc * inv_c;
         }
     }
 }
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) corr_bwd_kernel(const float *__restrict__
 using namespace dofb;
 
 extern "C" int dofb_corr_fwd(const float *f1, const float *f2, int ld, int B, int h, int w, int c, int max_disp, int stride2,
-                             float *out, int out_ld, void *stream) {
+                             float *out, int out_ld, int act, void *stream) {
     DOFB_CHECK_ARG(f1 && f2 && out && B > 0 && h > 0 && w > 0 && c > 0 && stride2 > 0 && max_disp >= 0, "dofb_corr_fwd: bad argument");
     DOFB_CHECK_ARG(c % 4 == 0 && ld % 4 == 0 && aligned16(f1) && aligned16(f2), "dofb_corr_fwd: c and pitch must be multiples of 4, pointers 16-byte aligned");
     DOFB_CHECK_ARG(max_disp % stride2 == 0, "dofb_corr_fwd: max_disp must be a multiple of stride2");
@@ -97,7 +97,7 @@ extern "C" int dofb_corr_fwd(const float *f1, const float *f2, int ld, int B, in
     long long blocks = ((long long)B * h * w * D + 7) / 8;
     const long long cap = (long long)num_sms() * 16;
     if (blocks > cap) blocks = cap;
-    corr_fwd_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(f1, f2, ld, B, h, w, c, max_disp, stride2, D, out, out_ld);
+    corr_fwd_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(f1, f2, ld, B, h, w, c, max_disp, stride2, D, out, out_ld, act);
     DOFB_LAUNCH_OK();
     return 0;
 }

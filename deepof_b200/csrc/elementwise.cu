@@ -32,7 +32,7 @@ int num_sms() {
 // resize_bilinear at an integer ratio is exact decimation, so no interpolation is needed).
 struct PreParams {
     const float *src, *tgt;
-    float *x6;
+    float *x6, *x6b;
     int x6_ld, x6_h, x6_w, x6_y0, x6_x0;
     int B, H, W;
     float mean[3];
@@ -60,8 +60,14 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
             a[c] = (__ldg(P.src + p * 3 + c) - P.mean[c]) / 255.0f;
             t[c] = (__ldg(P.tgt + p * 3 + c) - P.mean[c]) / 255.0f;
         }
-        float *o = P.x6 + (((long long)b * P.x6_h + y + P.x6_y0) * P.x6_w + x + P.x6_x0) * P.x6_ld;
-        if (P.x6_ld == 8) {
+        const long long xo = (((long long)b * P.x6_h + y + P.x6_y0) * P.x6_w + x + P.x6_x0) * P.x6_ld;
+        float *o = P.x6 + xo;
+        if (P.x6b != nullptr) {             // siamese: source and target in separate 3(+pad)-channel buffers
+            float *ob = P.x6b + xo;
+            o[0] = a[0]; o[1] = a[1]; o[2] = a[2];
+            ob[0] = t[0]; ob[1] = t[1]; ob[2] = t[2];
+            for (int c = 3; c < P.x6_ld; ++c) { o[c] = 0.f; ob[c] = 0.f; }
+        } else if (P.x6_ld == 8) {
             reinterpret_cast<float4 *>(o)[0] = make_float4(a[0], a[1], a[2], t[0]);
             reinterpret_cast<float4 *>(o)[1] = make_float4(t[1], t[2], 0.f, 0.f);
         } else {
@@ -85,17 +91,20 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
 }
 
 // ---- ELU backward (+ fused bias gradient) -----------------------------------------------
-// block = 256 threads = 8 pixel rows x 32 channel quads; a block owns a channel-quad stripe [q0, q0+32) and a pixel range, so
-// the column sums of the result (BiasAddGrad) reduce in registers -> shared -> one atomicAdd per channel per block.
-__global__ void __launch_bounds__(256) elu_bwd_kernel(float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c4,
+// block = 256 threads = (256/QW) pixel rows x QW channel quads (QW = power of two <= 32 chosen from the channel count, so narrow
+// layers still use every lane); a block owns a quad stripe and a pixel range, so the column sums of the result (BiasAddGrad)
+// reduce in registers -> shared -> one atomicAdd per channel per block.
+__global__ void __launch_bounds__(256) elu_bwd_kernel(float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c4, int qw,
                                                       long long pix_per_block, float *db) {
-    const int q = blockIdx.y * 32 + (threadIdx.x & 31);
-    const int prow = threadIdx.x >> 5;
+    const int ql = threadIdx.x & (qw - 1);
+    const int q = blockIdx.y * qw + ql;
+    const int rows = 256 / qw;
+    const int prow = threadIdx.x / qw;
     const long long p0 = (long long)blockIdx.x * pix_per_block;
     const long long p1 = p0 + pix_per_block < n_pix ? p0 + pix_per_block : n_pix;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (q < c4) {
-        for (long long p = p0 + prow; p < p1; p += 8) {
+        for (long long p = p0 + prow; p < p1; p += rows) {
             float4 gv = *reinterpret_cast<float4 *>(g + p * g_ld + q * 4);
             const float4 yv = __ldg(reinterpret_cast<const float4 *>(y + p * y_ld + q * 4));
             gv.x *= elu_grad_from_out(yv.x); gv.y *= elu_grad_from_out(yv.y);
@@ -105,13 +114,12 @@ __global__ void __launch_bounds__(256) elu_bwd_kernel(float *g, int g_ld, const 
         }
     }
     if (db == nullptr) return;
-    __shared__ float4 red[8][32];
-    red[prow][threadIdx.x & 31] = acc;
+    __shared__ float4 red[256];
+    red[threadIdx.x] = acc;
     __syncthreads();
     if (prow == 0 && q < c4) {
-        float4 s = red[0][threadIdx.x];
-#pragma unroll
-        for (int r = 1; r < 8; ++r) { const float4 t = red[r][threadIdx.x]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+        float4 s = red[ql];
+        for (int r = 1; r < rows; ++r) { const float4 t = red[r * qw + ql]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
         atomicAdd(db + q * 4, s.x); atomicAdd(db + q * 4 + 1, s.y); atomicAdd(db + q * 4 + 2, s.z); atomicAdd(db + q * 4 + 3, s.w);
     }
 }
@@ -186,8 +194,8 @@ extern "C" long long dofb_launch_count(void) { return g_launches.load(); }
 extern "C" void dofb_reset_launch_count(void) { g_launches.store(0); }
 
 extern "C" int dofb_preprocess(const float *src, const float *tgt, const float mean_bgr[3], int B, int H, int W, float *x6,
-                               int x6_ld, int x6_h, int x6_w, int x6_y0, int x6_x0, int n_scales, float *const *pyr_src,
-                               float *const *pyr_tgt, void *stream) {
+                               float *x6b, int x6_ld, int x6_h, int x6_w, int x6_y0, int x6_x0, int n_scales,
+                               float *const *pyr_src, float *const *pyr_tgt, void *stream) {
     DOFB_CHECK_ARG(src && tgt && x6 && mean_bgr, "dofb_preprocess: null argument");
     DOFB_CHECK_ARG(B > 0 && H > 0 && W > 0 && x6_ld >= 6, "dofb_preprocess: bad shape B=%d H=%d W=%d ld=%d", B, H, W, x6_ld);
     DOFB_CHECK_ARG(n_scales >= 0 && n_scales <= 8, "dofb_preprocess: n_scales=%d out of range", n_scales);
@@ -197,7 +205,7 @@ extern "C" int dofb_preprocess(const float *src, const float *tgt, const float m
     DOFB_CHECK_ARG(x6_y0 >= 0 && x6_x0 >= 0 && x6_y0 + H <= x6_h && x6_x0 + W <= x6_w, "dofb_preprocess: the image does not fit the x6 buffer");
     PreParams P;
     P.src = src; P.tgt = tgt; P.x6 = x6; P.x6_ld = x6_ld; P.B = B; P.H = H; P.W = W;
-    P.x6_h = x6_h; P.x6_w = x6_w; P.x6_y0 = x6_y0; P.x6_x0 = x6_x0;
+    P.x6_h = x6_h; P.x6_w = x6_w; P.x6_y0 = x6_y0; P.x6_x0 = x6_x0; P.x6b = x6b;
     for (int c = 0; c < 3; ++c) P.mean[c] = mean_bgr[c];
     P.n_scales = n_scales;
     for (int s = 0; s < 8; ++s) {
@@ -214,14 +222,17 @@ extern "C" int dofb_elu_bwd(float *g, int g_ld, const float *y, int y_ld, long l
     DOFB_CHECK_ARG(g && y && n_pix > 0 && c > 0, "dofb_elu_bwd: bad argument");
     DOFB_CHECK_ARG(c % 4 == 0 && g_ld % 4 == 0 && y_ld % 4 == 0 && aligned16(g) && aligned16(y),
                    "dofb_elu_bwd: channels/pitches must be multiples of 4 and pointers 16-byte aligned (c=%d)", c);
-    const int c4 = c / 4, stripes = (c4 + 31) / 32;
+    const int c4 = c / 4;
+    int qw = 1;
+    while (qw < c4 && qw < 32) qw <<= 1;
+    const int stripes = (c4 + qw - 1) / qw, rows = 256 / qw;
     long long blocks = (long long)num_sms() * 8 / stripes;
     if (blocks < 1) blocks = 1;
     long long ppb = (n_pix + blocks - 1) / blocks;
-    if (ppb < 32) ppb = 32;
-    ppb = (ppb + 7) / 8 * 8;
+    if (ppb < 4 * rows) ppb = 4 * rows;
+    ppb = (ppb + rows - 1) / rows * rows;
     blocks = (n_pix + ppb - 1) / ppb;
-    elu_bwd_kernel<<<dim3((unsigned)blocks, stripes), 256, 0, as_stream(stream)>>>(g, g_ld, y, y_ld, n_pix, c4, ppb, db);
+    elu_bwd_kernel<<<dim3((unsigned)blocks, stripes), 256, 0, as_stream(stream)>>>(g, g_ld, y, y_ld, n_pix, c4, qw, ppb, db);
     DOFB_LAUNCH_OK();
     return 0;
 }

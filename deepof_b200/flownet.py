@@ -128,7 +128,7 @@ class FlowNetS:
         self.hyper = dict(HYPER)
         if hyper:
             self.hyper.update(hyper)
-        self.arena = ParamArena(param_shapes(), self.device)
+        self.arena = ParamArena(self.param_shapes(), self.device)
         self.theta, self.grad = self.arena.new(), self.arena.new()
         self.m, self.v = self.arena.new(), self.arena.new()
         self.params = self.arena.views(self.theta)
@@ -141,6 +141,10 @@ class FlowNetS:
         self.profile = None            # list of (tag, start_event, end_event) when per-launch timing is on
         if seed is not None:
             self.init_params(seed)
+
+    @staticmethod
+    def param_shapes():
+        return param_shapes()
 
     def _k(self, tag, fn, *args, **kw):
         """Launch one kernel; with self.profile set, bracket it with CUDA events on the launch stream."""
@@ -175,17 +179,26 @@ class FlowNetS:
         return OrderedDict((k, v.detach().cpu().clone()) for k, v in self.params.items())
 
     # ------------------------------------------------------------------ buffers
+    ARCH = "S"
+
     def _alloc(self):
         B, H, W, dev = self.B, self.H, self.W, self.device
-        z = lambda h, w, c: torch.zeros(B, h, w, c, dtype=torch.float32, device=dev)  # noqa: E731
-        # conv1 input: dense for the SIMT path; zero-bordered (2 rows/cols before, 4/6 after) for the tcgen05 first-layer
+        z = lambda h, w, c, b=B: torch.zeros(b, h, w, c, dtype=torch.float32, device=dev)  # noqa: E731
+        self._z = z
+        # first-layer input: dense for the SIMT path; zero-bordered (2 rows/cols before, 4/6 after) for the tcgen05 first-layer
         # kernel, which reads the SAME padding (2,3) of the 7x7/2 conv straight from the border
         self.x6_origin = (2, 2) if self.math == MATH_TF32 else (0, 0)
-        self.x6 = z(H + 6, W + 8, 8) if self.math == MATH_TF32 else z(H, W, 8)
+        xshape = (H + 6, W + 8, 8) if self.math == MATH_TF32 else (H, W, 8)
+        self.x6 = z(*xshape)
+        self.x6b = z(*xshape) if self.ARCH == "C" else None          # siamese: target image in its own buffer
         shp = {"concat1": (H // 2, W // 2, 128), "concat2": (H // 4, W // 4, 224), "c31": (H // 8, W // 8, 256),
                "concat3": (H // 8, W // 8, 416), "c41": (H // 16, W // 16, 512), "concat4": (H // 16, W // 16, 800),
                "c51": (H // 32, W // 32, 512), "concat5": (H // 32, W // 32, 1056), "c61": (H // 64, W // 64, 1024),
                "c62": (H // 64, W // 64, 1024)}
+        if self.ARCH == "C":
+            del shp["c31"]
+            shp.update({"c1b": (H // 2, W // 2, 64), "c2b": (H // 4, W // 4, 128), "c3a": (H // 8, W // 8, 256),
+                        "c3b": (H // 8, W // 8, 256), "cat3": (H // 8, W // 8, 480)})
         self.act = {k: z(*v) for k, v in shp.items()}
         self.dact = {k: z(*v) for k, v in shp.items()}
         self.hw = {s: (H >> s, W >> s) for s in range(1, 7)}
@@ -196,28 +209,41 @@ class FlowNetS:
         self.recon1 = z(*self.hw[1], 3)
         self.loss4 = torch.zeros(6, 4, dtype=torch.float32, device=dev)
 
+    def _conv_rec(self, name, k, stride, cin, cout, x, dx, y, dy, acc=False, wname=None, xpad=None, ih=None, iw=None):
+        """One conv layer record: y = ELU(conv(x)); backward writes (or accumulates, acc=True) into dx."""
+        ih = ih if ih is not None else (x.h if x is not None else self.H)
+        iw = iw if iw is not None else (x.w if x is not None else self.W)
+        return dict(op="conv", name=name, wname=wname or name, g=conv_geom(self.B, ih, iw, cin, cout, k, stride),
+                    x=x, dx=dx, y=y, dy=dy, acc=acc, xpad=xpad)
+
+    def _plan_tower(self):
+        a, d, S = self.act, self.dact, Slab
+        first_x = S(self.x6, 0, 6) if self.math == MATH_FP32 else None
+        first_pad = self.x6 if self.math == MATH_TF32 else None
+        R = self._conv_rec
+        return [
+            R("conv1", 7, 2, 6, 64, first_x, None, S(a["concat1"], 0, 64), S(d["concat1"], 0, 64), xpad=first_pad),
+            R("conv2", 5, 2, 64, 128, S(a["concat1"], 0, 64), S(d["concat1"], 0, 64), S(a["concat2"], 0, 128), S(d["concat2"], 0, 128), acc=True),
+            R("conv3_1", 5, 2, 128, 256, S(a["concat2"], 0, 128), S(d["concat2"], 0, 128), full(a["c31"]), full(d["c31"]), acc=True),
+            R("conv3_2", 3, 1, 256, 256, full(a["c31"]), full(d["c31"]), S(a["concat3"], 0, 256), S(d["concat3"], 0, 256)),
+        ] + self._plan_tower_top()
+
+    def _plan_tower_top(self):
+        a, d, S, R = self.act, self.dact, Slab, self._conv_rec
+        return [
+            R("conv4_1", 3, 2, 256, 512, S(a["concat3"], 0, 256), S(d["concat3"], 0, 256), full(a["c41"]), full(d["c41"]), acc=True),
+            R("conv4_2", 3, 1, 512, 512, full(a["c41"]), full(d["c41"]), S(a["concat4"], 0, 512), S(d["concat4"], 0, 512)),
+            R("conv5_1", 3, 2, 512, 512, S(a["concat4"], 0, 512), S(d["concat4"], 0, 512), full(a["c51"]), full(d["c51"]), acc=True),
+            R("conv5_2", 3, 1, 512, 512, full(a["c51"]), full(d["c51"]), S(a["concat5"], 0, 512), S(d["concat5"], 0, 512)),
+            R("conv6_1", 3, 2, 512, 1024, S(a["concat5"], 0, 512), S(d["concat5"], 0, 512), full(a["c61"]), full(d["c61"]), acc=True),
+            R("conv6_2", 3, 1, 1024, 1024, full(a["c61"]), full(d["c61"]), full(a["c62"]), full(d["c62"])),
+        ]
+
     def _plan(self):
-        B, H, W = self.B, self.H, self.W
+        B = self.B
         a, d = self.act, self.dact
         S = Slab
-        io = [(S(self.x6, 0, 6) if self.math == MATH_FP32 else None, None, S(a["concat1"], 0, 64), S(d["concat1"], 0, 64)),
-              (S(a["concat1"], 0, 64), S(d["concat1"], 0, 64), S(a["concat2"], 0, 128), S(d["concat2"], 0, 128)),
-              (S(a["concat2"], 0, 128), S(d["concat2"], 0, 128), full(a["c31"]), full(d["c31"])),
-              (full(a["c31"]), full(d["c31"]), S(a["concat3"], 0, 256), S(d["concat3"], 0, 256)),
-              (S(a["concat3"], 0, 256), S(d["concat3"], 0, 256), full(a["c41"]), full(d["c41"])),
-              (full(a["c41"]), full(d["c41"]), S(a["concat4"], 0, 512), S(d["concat4"], 0, 512)),
-              (S(a["concat4"], 0, 512), S(d["concat4"], 0, 512), full(a["c51"]), full(d["c51"])),
-              (full(a["c51"]), full(d["c51"]), S(a["concat5"], 0, 512), S(d["concat5"], 0, 512)),
-              (S(a["concat5"], 0, 512), S(d["concat5"], 0, 512), full(a["c61"]), full(d["c61"])),
-              (full(a["c61"]), full(d["c61"]), full(a["c62"]), full(d["c62"]))]
-        # d_in buffers that already hold gradient from the refinement part when the tower backward reaches them
-        acc_in = {"conv2": True, "conv3_1": True, "conv4_1": True, "conv5_1": True, "conv6_1": True}
-        self.tower = []
-        ih, iw = H, W
-        for (name, k, s, cin, cout), (x, dx, y, dy) in zip(TOWER, io):
-            g = conv_geom(B, ih, iw, cin, cout, k, s)
-            self.tower.append(dict(name=name, g=g, x=x, dx=dx, y=y, dy=dy, acc=acc_in.get(name, False)))
-            ih, iw = g.oh, g.ow
+        self.tower = self._plan_tower()
         feat = {6: (full(a["c62"]), full(d["c62"])), 5: (S(a["concat5"], 0, 1026), S(d["concat5"], 0, 1026)),
                 4: (S(a["concat4"], 0, 770), S(d["concat4"], 0, 770)), 3: (S(a["concat3"], 0, 386), S(d["concat3"], 0, 386)),
                 2: (S(a["concat2"], 0, 194), S(d["concat2"], 0, 194)), 1: (S(a["concat1"], 0, 98), S(d["concat1"], 0, 98))}
@@ -234,21 +260,45 @@ class FlowNetS:
                                     pr_y=S(a[tgt], skipc + upc, 2), pr_dy=S(d[tgt], skipc + upc, 2)))
 
     # ------------------------------------------------------------------ forward
+    def _preprocess(self, source, target):
+        self._k("preprocess", ops.preprocess, source, target, self.mean, self.x6, [self.pyr_src[s] for s in range(1, 7)],
+                [self.pyr_tgt[s] for s in range(1, 7)], self.x6_origin, self.x6b)
+
+    def _fwd_layer(self, L):
+        P, mth = self.params, self.math
+        if L["op"] == "conv":
+            w, b = P[L["wname"] + "/weights"], P[L["wname"] + "/biases"]
+            if L["xpad"] is not None:       # first layer on tensor cores from the zero-bordered buffer
+                self._k("conv_fwd:" + L["name"], ops.conv1_fwd, L["g"], L["xpad"], self.x6_origin, w, b, L["y"], ACT_ELU)
+            else:
+                self._k("conv_fwd:" + L["name"], ops.conv_fwd, L["g"], L["x"], w, b, L["y"], ACT_ELU, mth)
+        elif L["op"] == "corr":
+            self._k("corr_fwd", ops.corr_fwd, L["f1"], L["f2"], L["y"], L["max_disp"], L["stride2"], ACT_ELU)
+
+    def _bwd_layer(self, L):
+        P, G, mth, mthw = self.params, self.grads, self.math, self.math_wgrad
+        if L["op"] == "conv":
+            w, dw, db = P[L["wname"] + "/weights"], G[L["wname"] + "/weights"], G[L["wname"] + "/biases"]
+            self._k("elu_bwd:" + L["name"], ops.elu_bwd, L["dy"], L["y"], db)                      # + bias gradient
+            if L["xpad"] is not None:
+                self._k("conv_wgrad:" + L["name"], ops.conv1_wgrad, L["g"], L["xpad"], self.x6_origin, L["dy"], dw, None)
+            else:
+                self._k("conv_wgrad:" + L["name"], ops.conv_wgrad, L["g"], L["x"], L["dy"], dw, None, mthw)
+            if L["dx"] is not None:
+                self._k("conv_dgrad:" + L["name"], ops.conv_dgrad, L["g"], L["dy"], w, None, L["dx"], ACT_NONE, L["acc"], mth)
+        elif L["op"] == "corr":
+            self._k("elu_bwd:corr", ops.elu_bwd, L["dy4"], L["y4"], None)
+            self._k("corr_bwd", ops.corr_bwd, L["f1"], L["f2"], L["dy"], L["df1"], L["df2"], L["max_disp"], L["stride2"])
+
     def forward(self, source: torch.Tensor, target: torch.Tensor, loss_weight=LOSS_WEIGHTS, with_grad: bool = True):
         """flowNet(inputs, outputs, loss_weight): runs the whole forward; when ``with_grad`` the fused
         warp/loss kernel also leaves d(total)/d(pr_s) in self.dpr (the start of the backward)."""
         if tuple(source.shape) != (self.B, self.H, self.W, 3) or tuple(target.shape) != (self.B, self.H, self.W, 3):
             raise ops.DeepOFError(f"expected [B={self.B},{self.H},{self.W},3] NHWC inputs, got {tuple(source.shape)} / {tuple(target.shape)}")
         P, mth = self.params, self.math
-        self._k("preprocess", ops.preprocess, source, target, self.mean, self.x6, [self.pyr_src[s] for s in range(1, 7)],
-                [self.pyr_tgt[s] for s in range(1, 7)], self.x6_origin)
+        self._preprocess(source, target)
         for L in self.tower:
-            if L["x"] is None:      # conv1 on tensor cores from the zero-bordered buffer
-                self._k("conv_fwd:" + L["name"], ops.conv1_fwd, L["g"], self.x6, self.x6_origin, P[L["name"] + "/weights"],
-                        P[L["name"] + "/biases"], L["y"], ACT_ELU)
-                continue
-            self._k("conv_fwd:" + L["name"], ops.conv_fwd, L["g"], L["x"], P[L["name"] + "/weights"], P[L["name"] + "/biases"],
-                    L["y"], ACT_ELU, mth)
+            self._fwd_layer(L)
         for R in self.refine:
             s = R["s"]
             x, _ = self.feat[s]
@@ -310,15 +360,7 @@ class FlowNetS:
             self._k(f"head_dgrad:pr{s}", ops.head_dgrad, self.dpr[s], P[f"pr{s}/weights"], dx, accumulate=True)
         # contracting tower, top down
         for L in reversed(self.tower):
-            self._k("elu_bwd:" + L["name"], ops.elu_bwd, L["dy"], L["y"], G[L["name"] + "/biases"])         # + bias gradient
-            if L["x"] is None:
-                self._k("conv_wgrad:" + L["name"], ops.conv1_wgrad, L["g"], self.x6, self.x6_origin, L["dy"],
-                        G[L["name"] + "/weights"], None)
-            else:
-                self._k("conv_wgrad:" + L["name"], ops.conv_wgrad, L["g"], L["x"], L["dy"], G[L["name"] + "/weights"], None, mthw)
-            if L["dx"] is not None:
-                self._k("conv_dgrad:" + L["name"], ops.conv_dgrad, L["g"], L["dy"], P[L["name"] + "/weights"], None, L["dx"],
-                        ACT_NONE, L["acc"], mth)
+            self._bwd_layer(L)
 
     # ------------------------------------------------------------------ optimiser
     def adam_step(self, lr: float, grad_scale: float = 1.0, beta1=0.9, beta2=0.999, eps=1e-8):
@@ -336,3 +378,60 @@ class FlowNetS:
         if allreduce is not None:
             scale = allreduce(self.grad)
         self.adam_step(lr, grad_scale=scale)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# FlowNetC: siamese conv1-3 + correlation cost volume (FlowNet paper; the reference has NO such model -- SURVEY.md 0.2 --
+# so this architecture is specified here and its parity is pinned only against our own oracle, oracle/flownet_c.py).
+#   conv1 7x7/2 3->64, conv2 5x5/2 64->128, conv3 5x5/2 128->256 on each image (shared weights)
+#   corr(conv3a, conv3b): max displacement 20, stride2 2 -> 21x21 = 441 channels, /C, ELU
+#   conv_redir 1x1 256->32 (ELU) on conv3a ; concat [conv_redir, corr] = 473 -> conv3_1 3x3 -> 256
+#   conv4_1 ... conv6_2 and the refinement exactly as FlowNetS (skips: conv5_2, conv4_2, conv3_1, conv2a, conv1a)
+# ---------------------------------------------------------------------------------------------------------------------
+CORR_MAX_DISP, CORR_STRIDE2 = 20, 2
+
+
+def param_shapes_c() -> "OrderedDict[str, tuple]":
+    sh: "OrderedDict[str, tuple]" = OrderedDict()
+    for name, k, cin, cout in [("conv1", 7, 3, 64), ("conv2", 5, 64, 128), ("conv3", 5, 128, 256), ("conv_redir", 1, 256, 32),
+                               ("conv3_1", 3, 473, 256), ("conv4_1", 3, 256, 512), ("conv4_2", 3, 512, 512), ("conv5_1", 3, 512, 512),
+                               ("conv5_2", 3, 512, 512), ("conv6_1", 3, 512, 1024), ("conv6_2", 3, 1024, 1024)]:
+        sh[name + "/weights"] = (k, k, cin, cout)
+        sh[name + "/biases"] = (cout,)
+    for key, shape in param_shapes().items():
+        if key.startswith(("pr", "up")):
+            sh[key] = shape
+    return sh
+
+
+class FlowNetC(FlowNetS):
+    ARCH = "C"
+
+    @staticmethod
+    def param_shapes():
+        return param_shapes_c()
+
+    def _plan_tower(self):
+        a, d, S, R = self.act, self.dact, Slab, self._conv_rec
+        fp32 = self.math == MATH_FP32
+        xa = S(self.x6, 0, 3) if fp32 else None
+        xb = S(self.x6b, 0, 3) if fp32 else None
+        pa = None if fp32 else self.x6
+        pb = None if fp32 else self.x6b
+        D = 2 * (CORR_MAX_DISP // CORR_STRIDE2) + 1
+        corr = dict(op="corr", name="corr", f1=full(a["c3a"]), f2=full(a["c3b"]), y=S(a["cat3"], 32, D * D), dy=S(d["cat3"], 32, D * D),
+                    y4=S(a["cat3"], 32, 444), dy4=S(d["cat3"], 32, 444),       # ELU' runs on a multiple of 4 channels (pad = 0)
+                    df1=full(d["c3a"]), df2=full(d["c3b"]), max_disp=CORR_MAX_DISP, stride2=CORR_STRIDE2)
+        return [
+            R("conv1a", 7, 2, 3, 64, xa, None, S(a["concat1"], 0, 64), S(d["concat1"], 0, 64), wname="conv1", xpad=pa),
+            R("conv1b", 7, 2, 3, 64, xb, None, full(a["c1b"]), full(d["c1b"]), wname="conv1", xpad=pb),
+            R("conv2a", 5, 2, 64, 128, S(a["concat1"], 0, 64), S(d["concat1"], 0, 64), S(a["concat2"], 0, 128), S(d["concat2"], 0, 128),
+              acc=True, wname="conv2"),
+            R("conv2b", 5, 2, 64, 128, full(a["c1b"]), full(d["c1b"]), full(a["c2b"]), full(d["c2b"]), wname="conv2"),
+            R("conv3a", 5, 2, 128, 256, S(a["concat2"], 0, 128), S(d["concat2"], 0, 128), full(a["c3a"]), full(d["c3a"]), acc=True, wname="conv3"),
+            R("conv3b", 5, 2, 128, 256, full(a["c2b"]), full(d["c2b"]), full(a["c3b"]), full(d["c3b"]), wname="conv3"),
+            # backward runs in reverse: conv3_1 (writes d cat3) -> corr (overwrites d c3a, d c3b) -> conv_redir (accumulates d c3a)
+            R("conv_redir", 1, 1, 256, 32, full(a["c3a"]), full(d["c3a"]), S(a["cat3"], 0, 32), S(d["cat3"], 0, 32), acc=True),
+            corr,
+            R("conv3_1", 3, 1, 473, 256, S(a["cat3"], 0, 473), S(d["cat3"], 0, 473), S(a["concat3"], 0, 256), S(d["concat3"], 0, 256)),
+        ] + self._plan_tower_top()

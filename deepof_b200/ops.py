@@ -86,8 +86,9 @@ def conv_geom(B, ih, iw, ci, co, k, stride) -> ConvGeom:
     return ConvGeom(B, ih, iw, ci, oh, ow, co, k, k, stride, pt, pl)
 
 
-def preprocess(src, tgt, mean, x6, pyr_src, pyr_tgt, origin=(0, 0)):
-    """x6 may be larger than the image (zero border for dofb_conv1_*); ``origin`` = (row, col) of the image in it."""
+def preprocess(src, tgt, mean, x6, pyr_src, pyr_tgt, origin=(0, 0), x6b=None):
+    """x6 may be larger than the image (zero border for dofb_conv1_*); ``origin`` = (row, col) of the image in it.
+    With ``x6b`` (siamese models) the source goes to x6[..., 0:3] and the target to x6b[..., 0:3] instead of 6 stacked channels."""
     _req(src, "src"); _req(tgt, "tgt"); _req(x6, "x6")
     B, H, W, _ = src.shape
     n = len(pyr_src)
@@ -97,8 +98,8 @@ def preprocess(src, tgt, mean, x6, pyr_src, pyr_tgt, origin=(0, 0)):
     ps = (C.c_void_p * max(n, 1))(*[t.data_ptr() for t in pyr_src])
     pt = (C.c_void_p * max(n, 1))(*[t.data_ptr() for t in pyr_tgt])
     lib = _lib.load()
-    check(lib.dofb_preprocess(src.data_ptr(), tgt.data_ptr(), m, B, H, W, x6.data_ptr(), x6.shape[3], x6.shape[1], x6.shape[2],
-                              origin[0], origin[1], n, ps, pt, _stream()))
+    check(lib.dofb_preprocess(src.data_ptr(), tgt.data_ptr(), m, B, H, W, x6.data_ptr(), x6b.data_ptr() if x6b is not None else None,
+                              x6.shape[3], x6.shape[1], x6.shape[2], origin[0], origin[1], n, ps, pt, _stream()))
 
 
 def conv1_fwd(g: ConvGeom, xpad, origin, w, b, y: Slab, act=ACT_ELU):
@@ -185,9 +186,9 @@ def epe_sum(flow, gt, out):
     check(_lib.load().dofb_epe_sum(flow.data_ptr(), gt.data_ptr(), flow.numel() // 2, out.data_ptr(), _stream()))
 
 
-def corr_fwd(f1: Slab, f2: Slab, out: Slab, max_disp=20, stride2=2):
+def corr_fwd(f1: Slab, f2: Slab, out: Slab, max_disp=20, stride2=2, act=ACT_NONE):
     assert f1.ld == f2.ld and f1.c == f2.c
-    check(_lib.load().dofb_corr_fwd(f1.ptr, f2.ptr, f1.ld, f1.B, f1.h, f1.w, f1.c, max_disp, stride2, out.ptr, out.ld, _stream()))
+    check(_lib.load().dofb_corr_fwd(f1.ptr, f2.ptr, f1.ld, f1.B, f1.h, f1.w, f1.c, max_disp, stride2, out.ptr, out.ld, act, _stream()))
 
 
 def corr_bwd(f1: Slab, f2: Slab, dout: Slab, df1: Slab, df2: Slab, max_disp=20, stride2=2):

@@ -43,12 +43,14 @@ void dofb_reset_launch_count(void);
  *   src,tgt : [B,H,W,3] BGR 0..255
  *   x6      : [B,x6_h,x6_w,x6_ld] out; the image occupies rows [x6_y0, x6_y0+H) and columns [x6_x0, x6_x0+W)
  *             (a zero border around it is the caller's: dofb_conv1_* reads it as the conv padding); channels
- *             0..2 = (src-mean)/255, 3..5 = (tgt-mean)/255, channels 6..x6_ld-1 are zero-filled
+ *             0..2 = (src-mean)/255, 3..5 = (tgt-mean)/255, channels 6..x6_ld-1 are zero-filled.
+ *   x6b     : NULL, or a second buffer of the same geometry (siamese models, FlowNetC): then x6 receives the source in
+ *             channels 0..2 and x6b the target in channels 0..2 (the rest zero)
  *   pyr_src/pyr_tgt[s] (s=0..n_scales-1): [B,H>>(s+1),W>>(s+1),3] LRN-normalised,
  *             decimated (legacy resize_bilinear at an integer ratio == x[::r, ::r]).
  */
 int dofb_preprocess(const float *src, const float *tgt, const float mean_bgr[3],
-                    int B, int H, int W, float *x6, int x6_ld, int x6_h, int x6_w, int x6_y0, int x6_x0,
+                    int B, int H, int W, float *x6, float *x6b, int x6_ld, int x6_h, int x6_w, int x6_y0, int x6_x0,
                     int n_scales, float *const *pyr_src, float *const *pyr_tgt, void *stream);
 
 /* ---- warp + Charbonnier photometric + smoothness loss -------------------- */
@@ -163,7 +165,7 @@ int dofb_epe_sum(const float *flow, const float *gt, long long n_pix, double *ou
 /* out[b,y,x,(dy_i*D+dx_i)] = (1/C) sum_c f1[b,y,x,c] * f2[b,y+dy,x+dx,c],
  * dy,dx in {-max_disp, -max_disp+stride2, ..., max_disp}, zero outside the map. */
 int dofb_corr_fwd(const float *f1, const float *f2, int ld, int B, int h, int w, int c, int max_disp, int stride2,
-                  float *out, int out_ld, void *stream);
+                  float *out, int out_ld, int act, void *stream);
 int dofb_corr_bwd(const float *f1, const float *f2, int ld, int B, int h, int w, int c, int max_disp, int stride2,
                   const float *dout, int dout_ld, float *df1, float *df2, int dld, void *stream);
 

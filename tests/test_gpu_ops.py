@@ -68,6 +68,11 @@ def test_preprocess_and_pyramid():
     ops.preprocess(src.cuda(), tgt.cuda(), fs.FLYINGCHAIRS_MEAN, xb, ps, pt, origin=(2, 2))
     assert torch.equal(xb[:, 2:2 + H, 2:2 + W], x6)
     assert float(xb[:, :2].abs().max()) == 0.0 and float(xb[:, :, 2 + W:].abs().max()) == 0.0
+    # siamese variant (FlowNetC): source and target in separate 3-channel buffers
+    xa, xt = torch.full((B, H, W, 8), 3.0, device="cuda"), torch.full((B, H, W, 8), 3.0, device="cuda")
+    ops.preprocess(src.cuda(), tgt.cuda(), fs.FLYINGCHAIRS_MEAN, xa, ps, pt, x6b=xt)
+    assert torch.equal(xa[..., :3], x6[..., :3]) and torch.equal(xt[..., :3], x6[..., 3:6])
+    assert float(xa[..., 3:].abs().max()) == 0.0 and float(xt[..., 3:].abs().max()) == 0.0
     xi, ni = fs.preprocess(src)
     xo, no = fs.preprocess(tgt)
     ref6 = torch.cat([xi, xo, torch.zeros(B, H, W, 2)], dim=3)
@@ -400,6 +405,9 @@ def test_correlation_fwd_bwd():
     f1b, f2b = pitched(f1, 32), pitched(f2, 32)
     ops.corr_fwd(ops.Slab(f1b, 0, c), ops.Slab(f2b, 0, c), ops.Slab(out, 0, D2), md, s2)
     assert rel(out[..., :D2], ref) < 1e-5
+    out_e = torch.zeros_like(out)
+    ops.corr_fwd(ops.Slab(f1b, 0, c), ops.Slab(f2b, 0, c), ops.Slab(out_e, 0, D2), md, s2, ops.ACT_ELU)
+    assert rel(out_e[..., :D2], tf_ops.elu(ref)) < 1e-5               # fused activation
     df1 = torch.zeros(B, h, w, 32, device="cuda")
     df2 = torch.zeros(B, h, w, 32, device="cuda")
     doutb = pitched(dout, D2 + 3)
