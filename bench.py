@@ -31,12 +31,30 @@ TRAIN_GFLOP_PER_PAIR = None  # computed from the layer list below
 
 
 # ----------------------------------------------------------------------------- workload arithmetic
-def layer_flops(B: int):
+def layer_flops(B: int, model: str = "flownets"):
     """Algorithmic FLOPs per launch tag (2*M*N*K of the implicit GEMM), DESIGN.md 'kernels'."""
     from deepof_b200.flownet import TOWER, REFINE
     fl = {}
     ih, iw = H, W
-    for name, k, s, cin, cout in TOWER:
+    tower = TOWER
+    if model == "flownetc":
+        h8, w8 = H // 8, W // 8
+        tower = [("conv4_1", 3, 2, 256, 512), ("conv4_2", 3, 1, 512, 512), ("conv5_1", 3, 2, 512, 512), ("conv5_2", 3, 1, 512, 512),
+                 ("conv6_1", 3, 2, 512, 1024), ("conv6_2", 3, 1, 1024, 1024)]
+        for nm, k, s, cin, cout, hh, ww in [("conv1", 7, 2, 3, 64, H, W), ("conv2", 5, 2, 64, 128, H // 2, W // 2), ("conv3", 5, 2, 128, 256, H // 4, W // 4)]:
+            f = 2.0 * B * (hh // s) * (ww // s) * cout * k * k * cin
+            for br in "ab":
+                fl[f"conv_fwd:{nm}{br}"] = f
+                fl[f"conv_wgrad:{nm}{br}"] = f
+                if nm != "conv1":
+                    fl[f"conv_dgrad:{nm}{br}"] = f
+        for nm, k, cin, cout in [("conv_redir", 1, 256, 32), ("conv3_1", 3, 473, 256)]:
+            f = 2.0 * B * h8 * w8 * cout * k * k * cin
+            fl["conv_fwd:" + nm] = fl["conv_wgrad:" + nm] = fl["conv_dgrad:" + nm] = f
+        fl["corr_fwd"] = 2.0 * B * h8 * w8 * 441 * 256
+        fl["corr_bwd"] = 2.0 * fl["corr_fwd"]
+        ih, iw = h8, w8
+    for name, k, s, cin, cout in tower:
         oh, ow = -(-ih // s), -(-iw // s)
         f = 2.0 * B * oh * ow * cout * k * k * cin
         fl["conv_fwd:" + name] = f
@@ -190,7 +208,8 @@ def run_ours(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     lib = _lib.load()
-    step = TrainStep(B, (H, W), device=dev, math_mode=args.math, distributed=world > 1, tc_wgrad=(args.math == "tf32"))
+    step = TrainStep(B, (H, W), device=dev, math_mode=args.math, distributed=world > 1, tc_wgrad=(args.math == "tf32"),
+                     model=args.model, variant=args.variant)
     eng = step.engine
     # two different synthetic batches per rank, alternated (working set per step ~3 GB >> 126 MB L2)
     batches = []
@@ -267,7 +286,7 @@ def run_ours(args, rank, local_rank, world):
             per.setdefault(tag, []).append(a.elapsed_time(b))
         eng.profile = None
         avg = {k: sum(v) / len(v) * (len(v) / psteps) for k, v in per.items()}     # ms per step per tag
-        fl = layer_flops(B)
+        fl = layer_flops(B, args.model)
         by = layer_bytes(B, eng.arena.n_true)
         peaks = load_peaks()
         classes = {}
@@ -279,7 +298,7 @@ def run_ours(args, rank, local_rank, world):
             c["bytes"] += by.get(tag, 0.0)
             c["launches"] += len(per[tag]) // psteps
         total_ms = sum(c["ms"] for c in classes.values())
-        gemm = [k for k in classes if k.startswith("conv_") or k.startswith("deconv_")]
+        gemm = [k for k in classes if k.startswith("conv_") or k.startswith("deconv_")]   # (corr_* reported separately)
         gemm_ms = sum(classes[k]["ms"] for k in gemm)
         gemm_fl = sum(classes[k]["flops"] for k in gemm)
         gemm_n = sum(classes[k]["launches"] for k in gemm)
@@ -303,7 +322,7 @@ def run_ours(args, rank, local_rank, world):
             breakdown.append(e)
         out_dir = ROOT / "gpurun_out"
         out_dir.mkdir(exist_ok=True)
-        (out_dir / f"bench_layers_{args.math}_n{world}.json").write_text(json.dumps(
+        (out_dir / f"bench_layers_{args.model}_{args.math}_n{world}.json").write_text(json.dumps(
             {"per_tag_ms": {k: round(v, 5) for k, v in sorted(avg.items(), key=lambda kv: -kv[1])}, "classes": breakdown}, indent=1))
 
     if rank != 0:
@@ -320,8 +339,10 @@ def run_ours(args, rank, local_rank, world):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "tf32" if args.math == "tf32" else "f32", "data": "synthetic",
-            "config": {"workload": f"FlowNetS training (fwd+bwd+Adam), synthetic FlyingChairs {H}x{W}, batch={B} per GPU",
-                       "global_batch": gb, "parallelism": f"dp{world}", "loss_variant": "A (flyingChairsWrapFlow.loss_interp)",
+            "config": {"workload": f"{'FlowNetS' if args.model == 'flownets' else 'FlowNetC (correlation cost-volume)'} training "
+                                   f"(fwd+bwd+Adam), synthetic FlyingChairs {H}x{W}, batch={B} per GPU",
+                       "global_batch": gb, "parallelism": f"dp{world}",
+                       "loss_variant": "A (flyingChairsWrapFlow.loss_interp)" if args.variant == "A" else "B (flyingChairsWrapFlow_vgg / version1 warpflow)",
                        "math": args.math, "l2": "inputs+activations per step (~3 GB) exceed the 126 MB L2; two alternating batches"},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
@@ -344,6 +365,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--math", default=os.environ.get("DEEPOF_MATH", "fp32"), choices=["fp32", "tf32"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (BASELINE config: 32)")
+    ap.add_argument("--model", default="flownets", choices=["flownets", "flownetc"], help="flownets = BASELINE configs[1]; flownetc = configs[2]")
+    ap.add_argument("--variant", default="A", choices=["A", "B"], help="loss_interp variant (A: flyingChairsWrapFlow, B: _vgg/version1)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

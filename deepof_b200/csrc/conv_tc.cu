@@ -116,6 +116,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // K-major / SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (unused for swizzled K-major)
 //   [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 B between 8-row groups) | [46,48) version = 1
@@ -1020,6 +1031,182 @@ int tc_conv1_wgrad(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, 
         case 64: return launch_wg<64, 8>(mx, md, P, (int)splits, items, st);
         default: return launch_wg<32, 8>(mx, md, P, (int)splits, items, st);
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FlowNetC correlation forward on tensor cores (no reference symbol; FlowNet paper definition).
+// Work unit = (image b, row pair yp, 64-pixel column tile xt, vertical displacement dy):
+//   A = conv3a rows (2yp, 2yp+1), pixels [x0, x0+64)            -> M = 128 rows
+//   B = conv3b rows (2yp+dy, 2yp+dy+1), pixels [x0-32, x0+96)   -> N = 256 columns (TMA zero-fills outside the map)
+//   G = A . B^T over the 256 channels (8 k-blocks of 32): the 128x256 fp32 tile in TMEM holds, in its two diagonal
+//   128-column blocks, the channel dot products of every pixel with its 128-pixel horizontal neighbourhood on the row dy below;
+//   the epilogue keeps the D = 2*md/s2+1 displacements dx = -md..md step s2 per pixel (a band of the tile), scales by 1/C,
+//   applies ELU and writes out[b,y,x,(dy_i, 0..D)].  Same persistent pipeline as the conv kernel (3 stages, 2 accumulators).
+// ------------------------------------------------------------------------------------------------
+struct CorrParams {
+    float *out; int out_ld;
+    int B, h, w, c, md, s2, D;
+    int ncb;                 // 32-channel blocks
+    int ypairs, xtiles, units;
+    int act;
+    float inv_c;
+};
+
+constexpr int CORR_STAGES = 3;
+constexpr int CORR_BN = 256;
+constexpr int CORR_STAGE_BYTES = TC_A_BYTES + CORR_BN * TC_BK * 4;     // 48 KB
+constexpr int CORR_STG_LD = 97;                                         // staging row pitch (floats)
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_corr_fwd_kernel(const __grid_constant__ CUtensorMap map_f1, const __grid_constant__ CUtensorMap map_f2,
+                   const __grid_constant__ CorrParams P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float *stage_f = reinterpret_cast<float *>(smem + CORR_STAGES * CORR_STAGE_BYTES);          // [4 warps][32][97]
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(stage_f + 4 * 32 * CORR_STG_LD);
+    uint64_t *empty_bar = full_bar + CORR_STAGES;
+    uint64_t *acc_full = empty_bar + CORR_STAGES;
+    uint64_t *acc_empty = acc_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = P.units * P.D;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < CORR_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 4 && lane == 0) { prefetch_tmap(&map_f1); prefetch_tmap(&map_f2); }
+    if (warp == 5) tmem_alloc(tmem_slot, 2 * CORR_BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            int it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int dyi = t % P.D, u = t / P.D;
+                const int xt = u % P.xtiles, yp = (u / P.xtiles) % P.ypairs, b = u / (P.xtiles * P.ypairs);
+                const int x0 = xt * 64, y0 = yp * 2, dy = -P.md + dyi * P.s2;
+                for (int k = 0; k < P.ncb; ++k, ++it) {
+                    const int s = it % CORR_STAGES;
+                    const uint32_t ph = (it / CORR_STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t *sa = smem + s * CORR_STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[s], CORR_STAGE_BYTES);
+                    tma_load_4d(sa, &map_f1, &full_bar[s], k * TC_BK, x0, y0, b);
+                    tma_load_4d(sa + TC_A_BYTES, &map_f2, &full_bar[s], k * TC_BK, x0 - 32, y0 + dy, b);
+                }
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(TC_BM, CORR_BN);
+            int it = 0, lt = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+                const int acc = lt & 1;
+                mbar_wait(&acc_empty[acc], ((lt >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * CORR_BN);
+                for (int k = 0; k < P.ncb; ++k, ++it) {
+                    const int s = it % CORR_STAGES;
+                    const uint32_t ph = (it / CORR_STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * CORR_STAGE_BYTES);
+                    const uint64_t da = make_desc_k128(sa), db = make_desc_k128(sa + TC_A_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < TC_BK / 8; ++kk)
+                        umma_tf32(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (k | kk) != 0);
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&acc_full[acc]);
+            }
+        }
+    } else {
+        // ===== epilogue: band extraction =====
+        const int r = warp * 32 + lane;
+        const int ry = r >> 6, xl = r & 63;
+        float *my_stage = stage_f + (warp * 32 + lane) * CORR_STG_LD;
+        // columns this warp needs: pixel xl (= xw0 + lane) sees x' = xl + 32 + dx, dx >= -md  ->  window [ry*128 + xw0 + 32 - md, +32 + 2*md)
+        const int xw0 = (warp & 1) * 32;
+        const int col0 = ry * 128 + xw0 + 32 - P.md;
+        const int span = 32 + 2 * P.md;                      // <= 96
+        int lt = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+            const int dyi = t % P.D, u = t / P.D;
+            const int xt = u % P.xtiles, yp = (u / P.xtiles) % P.ypairs, b = u / (P.xtiles * P.ypairs);
+            const int x = xt * 64 + xl, y = yp * 2 + ry;
+            const int acc = lt & 1;
+            mbar_wait(&acc_full[acc], (lt >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tbase = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * CORR_BN + col0);
+            int cdone = 0;
+#pragma unroll 1
+            for (; cdone + 32 <= span; cdone += 32) {
+                float v[32];
+                tmem_ld32(tbase + (uint32_t)cdone, v);
+#pragma unroll
+                for (int q = 0; q < 32; ++q) my_stage[cdone + q] = v[q];
+            }
+#pragma unroll 1
+            for (; cdone < span; cdone += 8) {               // span is a multiple of 8: never reads past the band
+                float v[8];
+                tmem_ld8(tbase + (uint32_t)cdone, v);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) my_stage[cdone + q] = v[q];
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);     // accumulator drained into shared memory: MMA may overwrite it
+            if (x < P.w && y < P.h) {
+                float *dst = P.out + (((long long)b * P.h + y) * P.w + x) * P.out_ld + dyi * P.D;
+                for (int jj = 0; jj < P.D; ++jj) {
+                    float val = my_stage[lane + jj * P.s2] * P.inv_c;       // column (xl + 32 + dx) - (xw0 + 32 - md) = lane + jj*s2
+                    if (P.act == DOFB_ACT_ELU) val = elu_f(val);
+                    dst[jj] = val;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * CORR_BN);
+    }
+}
+
+int tc_corr_fwd(const float *f1, const float *f2, int ld, int B, int h, int w, int c, int md, int s2, float *out, int out_ld, int act,
+                cudaStream_t st) {
+    DOFB_CHECK_ARG(c % 32 == 0 && ld % 32 == 0 && aligned16(f1) && aligned16(f2), "dofb_corr_fwd(tf32): c and pitch must be multiples of 32");
+    DOFB_CHECK_ARG(md >= 0 && md <= 32 && s2 >= 1 && md % s2 == 0 && md % 4 == 0,
+                   "dofb_corr_fwd(tf32): max displacement must be <= 32, a multiple of 4 and of stride2");
+    CorrParams P;
+    P.out = out; P.out_ld = out_ld; P.B = B; P.h = h; P.w = w; P.c = c; P.md = md; P.s2 = s2; P.D = 2 * (md / s2) + 1;
+    P.ncb = c / 32; P.ypairs = (h + 1) / 2; P.xtiles = (w + 63) / 64; P.units = B * P.ypairs * P.xtiles;
+    P.act = act; P.inv_c = 1.0f / (float)c;
+    CUtensorMap m1, m2;
+    const uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)ld * 4, (uint64_t)w * ld * 4, (uint64_t)h * w * ld * 4};
+    const uint32_t box1[4] = {32, 64, 2, 1}, box2[4] = {32, 128, 2, 1};
+    if (make_map(&m1, f1, 4, dims, str, box1)) return 1;
+    if (make_map(&m2, f2, 4, dims, str, box2)) return 1;
+    constexpr int smem = CORR_STAGES * CORR_STAGE_BYTES + 4 * 32 * CORR_STG_LD * 4 + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        DOFB_CUDA_OK(cudaFuncSetAttribute(tc_corr_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    const long long total = (long long)P.units * P.D;
+    const int grid = (int)(total < num_sms() ? total : num_sms());
+    tc_corr_fwd_kernel<<<grid, TC_THREADS, smem, st>>>(m1, m2, P);
+    DOFB_LAUNCH_OK();
+    return 0;
 }
 
 }  // namespace dofb

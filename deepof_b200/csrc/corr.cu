@@ -85,11 +85,19 @@ __global__ void __launch_bounds__(256) corr_bwd_kernel(const float *__restrict__
 
 }  // namespace dofb
 
+namespace dofb {
+int tc_corr_fwd(const float *f1, const float *f2, int ld, int B, int h, int w, int c, int md, int s2, float *out, int out_ld, int act,
+                cudaStream_t st);
+}
 using namespace dofb;
 
 extern "C" int dofb_corr_fwd(const float *f1, const float *f2, int ld, int B, int h, int w, int c, int max_disp, int stride2,
-                             float *out, int out_ld, int act, void *stream) {
+                             float *out, int out_ld, int act, int math, void *stream) {
     DOFB_CHECK_ARG(f1 && f2 && out && B > 0 && h > 0 && w > 0 && c > 0 && stride2 > 0 && max_disp >= 0, "dofb_corr_fwd: bad argument");
+    if (math == DOFB_MATH_TF32) {
+        DOFB_CHECK_ARG(out_ld >= (2 * (max_disp / stride2) + 1) * (2 * (max_disp / stride2) + 1), "dofb_corr_fwd: out pitch too small");
+        return tc_corr_fwd(f1, f2, ld, B, h, w, c, max_disp, stride2, out, out_ld, act, as_stream(stream));
+    }
     DOFB_CHECK_ARG(c % 4 == 0 && ld % 4 == 0 && aligned16(f1) && aligned16(f2), "dofb_corr_fwd: c and pitch must be multiples of 4, pointers 16-byte aligned");
     DOFB_CHECK_ARG(max_disp % stride2 == 0, "dofb_corr_fwd: max_disp must be a multiple of stride2");
     const int D = 2 * (max_disp / stride2) + 1;

@@ -273,7 +273,7 @@ class FlowNetS:
             else:
                 self._k("conv_fwd:" + L["name"], ops.conv_fwd, L["g"], L["x"], w, b, L["y"], ACT_ELU, mth)
         elif L["op"] == "corr":
-            self._k("corr_fwd", ops.corr_fwd, L["f1"], L["f2"], L["y"], L["max_disp"], L["stride2"], ACT_ELU)
+            self._k("corr_fwd", ops.corr_fwd, L["f1"], L["f2"], L["y"], L["max_disp"], L["stride2"], ACT_ELU, mth)
 
     def _bwd_layer(self, L):
         P, G, mth, mthw = self.params, self.grads, self.math, self.math_wgrad

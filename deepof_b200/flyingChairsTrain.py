@@ -10,7 +10,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .flownet import FlowNetS, LOSS_WEIGHTS
+from .flownet import FlowNetS, FlowNetC, LOSS_WEIGHTS
 from . import ddp as _ddp
 
 LEARNING_RATE = 0.000016            # flyingChairsTrain.py:27
@@ -25,9 +25,10 @@ class TrainStep:
     and a lagged loss read-back -- the H2D copy of step i+1 and the D2H of step i's loss overlap the kernels of step i."""
 
     def __init__(self, batch_size: int, image_size=(384, 512), device="cuda", variant="A", math_mode="fp32",
-                 seed: int | None = 1, distributed: bool = False, **kw):
-        self.engine = FlowNetS(batch_size, image_size[0], image_size[1], device=device, variant=variant, math_mode=math_mode,
-                               seed=seed, **kw)
+                 seed: int | None = 1, distributed: bool = False, model: str = "flownets", **kw):
+        cls = {"flownets": FlowNetS, "flownetc": FlowNetC}[model.lower()]
+        self.engine = cls(batch_size, image_size[0], image_size[1], device=device, variant=variant, math_mode=math_mode,
+                          seed=seed, **kw)
         self.device = self.engine.device
         B, H, W = batch_size, image_size[0], image_size[1]
         shape = (B, H, W, 3)

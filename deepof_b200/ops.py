@@ -186,9 +186,10 @@ def epe_sum(flow, gt, out):
     check(_lib.load().dofb_epe_sum(flow.data_ptr(), gt.data_ptr(), flow.numel() // 2, out.data_ptr(), _stream()))
 
 
-def corr_fwd(f1: Slab, f2: Slab, out: Slab, max_disp=20, stride2=2, act=ACT_NONE):
+def corr_fwd(f1: Slab, f2: Slab, out: Slab, max_disp=20, stride2=2, act=ACT_NONE, math=MATH_FP32):
     assert f1.ld == f2.ld and f1.c == f2.c
-    check(_lib.load().dofb_corr_fwd(f1.ptr, f2.ptr, f1.ld, f1.B, f1.h, f1.w, f1.c, max_disp, stride2, out.ptr, out.ld, act, _stream()))
+    check(_lib.load().dofb_corr_fwd(f1.ptr, f2.ptr, f1.ld, f1.B, f1.h, f1.w, f1.c, max_disp, stride2, out.ptr, out.ld, act, math,
+                                    _stream()))
 
 
 def corr_bwd(f1: Slab, f2: Slab, dout: Slab, df1: Slab, df2: Slab, max_disp=20, stride2=2):

@@ -162,10 +162,11 @@ int dofb_adam(float *theta, const float *g, float *m, float *v, long long n,
 int dofb_epe_sum(const float *flow, const float *gt, long long n_pix, double *out, void *stream);
 
 /* ---- FlowNetC correlation (no reference symbol; FlowNet paper definition) --- */
-/* out[b,y,x,(dy_i*D+dx_i)] = (1/C) sum_c f1[b,y,x,c] * f2[b,y+dy,x+dx,c],
- * dy,dx in {-max_disp, -max_disp+stride2, ..., max_disp}, zero outside the map. */
+/* out[b,y,x,(dy_i*D+dx_i)] = act((1/C) sum_c f1[b,y,x,c] * f2[b,y+dy,x+dx,c]),
+ * dy,dx in {-max_disp, -max_disp+stride2, ..., max_disp}, zero outside the map.
+ * math = DOFB_MATH_TF32: the per-displacement channel dot products run as tcgen05 band-GEMMs (c, pitch % 32 == 0, max_disp <= 32). */
 int dofb_corr_fwd(const float *f1, const float *f2, int ld, int B, int h, int w, int c, int max_disp, int stride2,
-                  float *out, int out_ld, int act, void *stream);
+                  float *out, int out_ld, int act, int math, void *stream);
 int dofb_corr_bwd(const float *f1, const float *f2, int ld, int B, int h, int w, int c, int max_disp, int stride2,
                   const float *dout, int dout_ld, float *df1, float *df2, int dld, void *stream);
 

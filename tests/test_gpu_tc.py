@@ -167,6 +167,23 @@ def test_tc_conv1_fwd_and_wgrad_match_simt(B, H, W):
     assert rel(db1, db0) < 1e-4
 
 
+@pytest.mark.parametrize("B,h,w,md,s2", [(2, 12, 64, 20, 2), (1, 7, 40, 20, 2), (2, 6, 128, 20, 2), (1, 5, 64, 16, 4), (1, 48, 64, 20, 2)])
+def test_tc_correlation_matches_simt(B, h, w, md, s2):
+    from deepof_b200 import ops
+    g = torch.Generator().manual_seed(B * h + w)
+    c = 256
+    f1 = _buf(B, h, w, c, c, g)
+    f2 = _buf(B, h, w, c, c, g)
+    D = 2 * (md // s2) + 1
+    o0 = torch.zeros(B, h, w, D * D + 7, device="cuda")
+    o1 = torch.full((B, h, w, D * D + 7), 5.0, device="cuda")
+    ops.corr_fwd(ops.Slab(f1, 0, c), ops.Slab(f2, 0, c), ops.Slab(o0, 0, D * D), md, s2, ops.ACT_ELU, ops.MATH_FP32)
+    ops.corr_fwd(ops.Slab(f1, 0, c), ops.Slab(f2, 0, c), ops.Slab(o1, 0, D * D), md, s2, ops.ACT_ELU, ops.MATH_TF32)
+    torch.cuda.synchronize()
+    assert rel(o1[..., :D * D], o0[..., :D * D]) < TOL
+    assert float((o1[..., D * D:] - 5.0).abs().max()) == 0.0          # nothing written past the D*D channels
+
+
 def test_tf32_engine_tracks_fp32_engine_and_oracle_epe():
     """Whole step in TF32 mode: flows within the stated tolerance of the fp32 device path and EPE within 1e-3 of the CPU oracle."""
     from deepof_b200.flownet import FlowNetS
