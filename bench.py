@@ -329,6 +329,35 @@ def run_ours(args, rank, local_rank, world):
         if world > 1:
             dist.destroy_process_group()
         return
+    # ---- accuracy of the benched math mode on a held-out synthetic batch (north_star: EPE within 1e-3 of the fp32 forward) ----
+    accuracy = None
+    if not args.no_accuracy:
+        from deepof_b200.flownet import FlowNetS, FlowNetC
+        from deepof_b200 import ops as _ops
+        cls = FlowNetS if args.model == "flownets" else FlowNetC
+        hb = 4
+        hs, ht, hgt = make_pairs(hb, H, W, seed=1234)
+        hs, ht, hgt = hs.to(dev), ht.to(dev), hgt.to(dev)
+        flows = {}
+        for mode in ("fp32", args.math):
+            if mode in flows:
+                continue
+            e = cls(hb, H, W, device=dev, math_mode=mode, seed=1, variant=args.variant, tc_wgrad=(mode == "tf32"))
+            e.forward(hs, ht, with_grad=False)
+            flows[mode] = (e.pr[1] * 10.0).clone()
+            del e
+        def epe(flow_s1):      # evaluation recipe of flyingChairsTrain.py:264-266,294-296: x2, clip, bilinear resize to HxW, AEE
+            f = torch.clamp(flow_s1 * 2.0, -300.0, 250.0).permute(0, 3, 1, 2)
+            f = torch.nn.functional.interpolate(f, size=(H, W), mode="bilinear", align_corners=False).permute(0, 2, 3, 1).contiguous()
+            out = torch.zeros(1, dtype=torch.float64, device=dev)
+            _ops.epe_sum(f, hgt.contiguous(), out)
+            return out.item() / (hb * H * W)
+        e32, em = epe(flows["fp32"]), epe(flows[args.math])
+        accuracy = {"held_out_pairs": hb, "epe_fp32_path": e32, "epe_benched_path": em, "abs_epe_delta": abs(em - e32),
+                    "flow_l1_mean_px": float((flows[args.math] - flows["fp32"]).abs().mean()),
+                    "flow_l1_max_px": float((flows[args.math] - flows["fp32"]).abs().max()), "tolerance": 1e-3,
+                    "note": "fp32 path == CPU oracle to 5e-7 px (tests/test_gpu_flownet.py)"}
+        torch.cuda.empty_cache()
     # ---- CPU baseline on the host cores (N=1 only, bounded sample) ----
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -350,7 +379,7 @@ def run_ours(args, rank, local_rank, world):
                     "api": "deepof_b200.flyingChairsTrain.TrainStep.run(feed_dict) + last_loss(lag=1): pinned-host inputs, "
                            "H2D on a copy stream double-buffered against the previous step, loss D2H read one step late"},
             "gpu_launches": launches,
-            "roofline": roof, "cpu_baseline": cpu, "kernel_classes": breakdown,
+            "roofline": roof, "cpu_baseline": cpu, "accuracy": accuracy, "kernel_classes": breakdown,
             "loss_after": loss_dev, "loss_after_e2e": last}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -363,11 +392,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--math", default=os.environ.get("DEEPOF_MATH", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--math", default=os.environ.get("DEEPOF_MATH", "tf32"), choices=["fp32", "tf32"],
+                    help="tf32: tcgen05 tensor-core convolutions (TF32 operands, fp32 accumulate; EPE within 1e-3 of the fp32 path, "
+                         "checked in this run); fp32: SIMT FFMA parity path")
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (BASELINE config: 32)")
     ap.add_argument("--model", default="flownets", choices=["flownets", "flownetc"], help="flownets = BASELINE configs[1]; flownetc = configs[2]")
     ap.add_argument("--variant", default="A", choices=["A", "B"], help="loss_interp variant (A: flyingChairsWrapFlow, B: _vgg/version1)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-accuracy", action="store_true", help="skip the held-out EPE check")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
