@@ -43,7 +43,9 @@ SIGNATURES = {
     "dofb_last_error": (C.c_char_p, []),
     "dofb_launch_count": (_LL, []),
     "dofb_reset_launch_count": (None, []),
-    "dofb_preprocess": (_I, [_P, _P, C.POINTER(C.c_float), _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_void_p),
+    "dofb_maxpool2_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P]),
+    "dofb_maxpool2_bwd": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _P]),
+    "dofb_preprocess": (_I, [_P, _P, C.POINTER(C.c_float), _F, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_void_p),
                              C.POINTER(C.c_void_p), _P]),
     "dofb_conv1_fwd": (_I, [_G, _P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P]),
     "dofb_conv1_wgrad": (_I, [_G, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P]),

@@ -36,6 +36,7 @@ struct PreParams {
     int x6_ld, x6_h, x6_w, x6_y0, x6_x0;
     int B, H, W;
     float mean[3];
+    float divisor;
     int n_scales;
     float *pyr_src[8];
     float *pyr_tgt[8];
@@ -57,12 +58,14 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
         float a[3], t[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            a[c] = (__ldg(P.src + p * 3 + c) - P.mean[c]) / 255.0f;
-            t[c] = (__ldg(P.tgt + p * 3 + c) - P.mean[c]) / 255.0f;
+            a[c] = (__ldg(P.src + p * 3 + c) - P.mean[c]) / P.divisor;
+            t[c] = (__ldg(P.tgt + p * 3 + c) - P.mean[c]) / P.divisor;
         }
         const long long xo = (((long long)b * P.x6_h + y + P.x6_y0) * P.x6_w + x + P.x6_x0) * P.x6_ld;
         float *o = P.x6 + xo;
-        if (P.x6b != nullptr) {             // siamese: source and target in separate 3(+pad)-channel buffers
+        if (P.x6 == nullptr) {
+            // pyramid-only call (models whose network input and loss images differ: VGG16 photo/geo pairs)
+        } else if (P.x6b != nullptr) {             // siamese: source and target in separate 3(+pad)-channel buffers
             float *ob = P.x6b + xo;
             o[0] = a[0]; o[1] = a[1]; o[2] = a[2];
             ob[0] = t[0]; ob[1] = t[1]; ob[2] = t[2];
@@ -87,6 +90,62 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
                 P.pyr_tgt[s][q] = tn[0]; P.pyr_tgt[s][q + 1] = tn[1]; P.pyr_tgt[s][q + 2] = tn[2];
             }
         }
+    }
+}
+
+// ---- 2x2 / stride-2 max pooling (slim.max_pool2d, VALID), NHWC float4 ---------------------------------
+// forward:  y[b,oy,ox,c] = max over the 2x2 window.   backward: the gradient goes to the FIRST maximum in window scan
+// order (row-major), which is what TF's MaxPoolGrad and torch's max_pool2d backward do.
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float *__restrict__ x, int x_ld, int B, int oh, int ow, int c4,
+                                                          float *__restrict__ y, int y_ld) {
+    const long long n = (long long)B * oh * ow * c4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int q = (int)(i % c4);
+        const long long p = i / c4;
+        const int ox = (int)(p % ow), oy = (int)((p / ow) % oh), b = (int)(p / ((long long)ow * oh));
+        const float *src = x + (((long long)b * 2 * oh + 2 * oy) * (2 * ow) + 2 * ox) * x_ld + q * 4;
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(src));
+        const float4 bb = __ldg(reinterpret_cast<const float4 *>(src + x_ld));
+        const float4 cc = __ldg(reinterpret_cast<const float4 *>(src + (long long)2 * ow * x_ld));
+        const float4 d = __ldg(reinterpret_cast<const float4 *>(src + (long long)2 * ow * x_ld + x_ld));
+        float4 m;
+        m.x = fmaxf(fmaxf(a.x, bb.x), fmaxf(cc.x, d.x)); m.y = fmaxf(fmaxf(a.y, bb.y), fmaxf(cc.y, d.y));
+        m.z = fmaxf(fmaxf(a.z, bb.z), fmaxf(cc.z, d.z)); m.w = fmaxf(fmaxf(a.w, bb.w), fmaxf(cc.w, d.w));
+        *reinterpret_cast<float4 *>(y + p * y_ld + q * 4) = m;
+    }
+}
+
+__device__ __forceinline__ void route4(float a, float b, float c, float d, float g, float &oa, float &ob, float &oc, float &od) {
+    const float m = fmaxf(fmaxf(a, b), fmaxf(c, d));
+    oa = ob = oc = od = 0.f;
+    if (a == m) oa = g; else if (b == m) ob = g; else if (c == m) oc = g; else od = g;
+}
+
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float *__restrict__ x, int x_ld, const float *__restrict__ dy, int dy_ld,
+                                                          int B, int oh, int ow, int c4, float *__restrict__ dx, int dx_ld) {
+    const long long n = (long long)B * oh * ow * c4;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int q = (int)(i % c4);
+        const long long p = i / c4;
+        const int ox = (int)(p % ow), oy = (int)((p / ow) % oh), b = (int)(p / ((long long)ow * oh));
+        const long long pix = ((long long)b * 2 * oh + 2 * oy) * (2 * ow) + 2 * ox;
+        const float *src = x + pix * x_ld + q * 4;
+        const long long row = (long long)2 * ow;
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(src));
+        const float4 bb = __ldg(reinterpret_cast<const float4 *>(src + x_ld));
+        const float4 cc = __ldg(reinterpret_cast<const float4 *>(src + row * x_ld));
+        const float4 d = __ldg(reinterpret_cast<const float4 *>(src + row * x_ld + x_ld));
+        const float4 g = __ldg(reinterpret_cast<const float4 *>(dy + p * dy_ld + q * 4));
+        float4 oa, ob, oc, od;
+        route4(a.x, bb.x, cc.x, d.x, g.x, oa.x, ob.x, oc.x, od.x);
+        route4(a.y, bb.y, cc.y, d.y, g.y, oa.y, ob.y, oc.y, od.y);
+        route4(a.z, bb.z, cc.z, d.z, g.z, oa.z, ob.z, oc.z, od.z);
+        route4(a.w, bb.w, cc.w, d.w, g.w, oa.w, ob.w, oc.w, od.w);
+        float *dst = dx + pix * dx_ld + q * 4;
+        *reinterpret_cast<float4 *>(dst) = oa;
+        *reinterpret_cast<float4 *>(dst + dx_ld) = ob;
+        *reinterpret_cast<float4 *>(dst + row * dx_ld) = oc;
+        *reinterpret_cast<float4 *>(dst + row * dx_ld + dx_ld) = od;
     }
 }
 
@@ -193,20 +252,21 @@ extern "C" const char *dofb_last_error(void) { return err_buf(); }
 extern "C" long long dofb_launch_count(void) { return g_launches.load(); }
 extern "C" void dofb_reset_launch_count(void) { g_launches.store(0); }
 
-extern "C" int dofb_preprocess(const float *src, const float *tgt, const float mean_bgr[3], int B, int H, int W, float *x6,
+extern "C" int dofb_preprocess(const float *src, const float *tgt, const float mean_bgr[3], float divisor, int B, int H, int W, float *x6,
                                float *x6b, int x6_ld, int x6_h, int x6_w, int x6_y0, int x6_x0, int n_scales,
                                float *const *pyr_src, float *const *pyr_tgt, void *stream) {
-    DOFB_CHECK_ARG(src && tgt && x6 && mean_bgr, "dofb_preprocess: null argument");
-    DOFB_CHECK_ARG(B > 0 && H > 0 && W > 0 && x6_ld >= 6, "dofb_preprocess: bad shape B=%d H=%d W=%d ld=%d", B, H, W, x6_ld);
+    DOFB_CHECK_ARG(src && tgt && mean_bgr && (x6 || n_scales > 0), "dofb_preprocess: null argument");
+    DOFB_CHECK_ARG(B > 0 && H > 0 && W > 0 && (x6 == nullptr || x6_ld >= 6) && divisor != 0.f, "dofb_preprocess: bad shape B=%d H=%d W=%d ld=%d", B, H, W, x6_ld);
     DOFB_CHECK_ARG(n_scales >= 0 && n_scales <= 8, "dofb_preprocess: n_scales=%d out of range", n_scales);
     DOFB_CHECK_ARG(n_scales == 0 || (H % (1 << n_scales) == 0 && W % (1 << n_scales) == 0),
                    "dofb_preprocess: H=%d W=%d must be multiples of 2^%d", H, W, n_scales);
     DOFB_CHECK_ARG(x6_ld != 8 || aligned16(x6), "dofb_preprocess: x6 must be 16-byte aligned");
-    DOFB_CHECK_ARG(x6_y0 >= 0 && x6_x0 >= 0 && x6_y0 + H <= x6_h && x6_x0 + W <= x6_w, "dofb_preprocess: the image does not fit the x6 buffer");
+    DOFB_CHECK_ARG(x6 == nullptr || (x6_y0 >= 0 && x6_x0 >= 0 && x6_y0 + H <= x6_h && x6_x0 + W <= x6_w), "dofb_preprocess: the image does not fit the x6 buffer");
     PreParams P;
     P.src = src; P.tgt = tgt; P.x6 = x6; P.x6_ld = x6_ld; P.B = B; P.H = H; P.W = W;
     P.x6_h = x6_h; P.x6_w = x6_w; P.x6_y0 = x6_y0; P.x6_x0 = x6_x0; P.x6b = x6b;
     for (int c = 0; c < 3; ++c) P.mean[c] = mean_bgr[c];
+    P.divisor = divisor;
     P.n_scales = n_scales;
     for (int s = 0; s < 8; ++s) {
         P.pyr_src[s] = s < n_scales ? pyr_src[s] : nullptr;
@@ -214,6 +274,24 @@ extern "C" int dofb_preprocess(const float *src, const float *tgt, const float m
         DOFB_CHECK_ARG(s >= n_scales || (P.pyr_src[s] && P.pyr_tgt[s]), "dofb_preprocess: null pyramid level %d", s);
     }
     preprocess_kernel<<<grid_for((long long)B * H * W, 256), 256, 0, as_stream(stream)>>>(P);
+    DOFB_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int dofb_maxpool2_fwd(const float *x, int x_ld, int B, int oh, int ow, int c, float *y, int y_ld, void *stream) {
+    DOFB_CHECK_ARG(x && y && B > 0 && oh > 0 && ow > 0 && c > 0, "dofb_maxpool2_fwd: bad argument");
+    DOFB_CHECK_ARG(c % 4 == 0 && x_ld % 4 == 0 && y_ld % 4 == 0 && aligned16(x) && aligned16(y), "dofb_maxpool2_fwd: channels/pitches must be multiples of 4");
+    maxpool_fwd_kernel<<<grid_for((long long)B * oh * ow * (c / 4), 256), 256, 0, as_stream(stream)>>>(x, x_ld, B, oh, ow, c / 4, y, y_ld);
+    DOFB_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int dofb_maxpool2_bwd(const float *x, int x_ld, const float *dy, int dy_ld, int B, int oh, int ow, int c, float *dx, int dx_ld,
+                                 void *stream) {
+    DOFB_CHECK_ARG(x && dy && dx && B > 0 && oh > 0 && ow > 0 && c > 0, "dofb_maxpool2_bwd: bad argument");
+    DOFB_CHECK_ARG(c % 4 == 0 && x_ld % 4 == 0 && dy_ld % 4 == 0 && dx_ld % 4 == 0 && aligned16(x) && aligned16(dy) && aligned16(dx),
+                   "dofb_maxpool2_bwd: channels/pitches must be multiples of 4");
+    maxpool_bwd_kernel<<<grid_for((long long)B * oh * ow * (c / 4), 256), 256, 0, as_stream(stream)>>>(x, x_ld, dy, dy_ld, B, oh, ow, c / 4, dx, dx_ld);
     DOFB_LAUNCH_OK();
     return 0;
 }

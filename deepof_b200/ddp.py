@@ -16,7 +16,15 @@ import torch.distributed as dist
 
 
 class GradReducer:
-    def __init__(self, engine, bucket_mb: float = 64.0, group=None):
+    """Bucketed sum-all-reduce of the flat gradient arena, overlapped with the backward pass.
+
+    The backward completes gradients in exactly the reverse of the arena order (decoder from the finest scale up, then the tower
+    top-down), so the arena is cut into buckets from its END; the engine reports the lowest finished offset after every layer
+    (``ready(offset)``) and each bucket's all-reduce is issued the moment it is complete.  NCCL runs on its own stream: issuing it
+    makes that stream wait for the gradients already enqueued, and the remaining backward kernels overlap the transfer over
+    NVLink 5 / NVSwitch.  ``finish()`` joins before Adam and returns the 1/world scale the optimiser folds in."""
+
+    def __init__(self, engine, bucket_mb: float = 32.0, group=None):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised before building a GradReducer")
         self.engine = engine
@@ -24,20 +32,38 @@ class GradReducer:
         self.world = dist.get_world_size(group)
         n = engine.grad.numel()
         per = max(int(bucket_mb * (1 << 20) // 4), 1)
-        self.bounds = [(i, min(i + per, n)) for i in range(0, n, per)]
+        self.bounds = [(i, min(i + per, n)) for i in range(0, n, per)]      # ascending; consumed from the end
+        self._next = len(self.bounds) - 1
+        self._works = []
 
     def broadcast_params(self, src: int = 0):
         dist.broadcast(self.engine.theta, src=src, group=self.group)
 
-    def __call__(self, flat_grad: torch.Tensor) -> float:
-        """Sum-all-reduce the arena; returns the scale (1/world) the optimiser must apply."""
+    def begin(self):
+        self._next = len(self.bounds) - 1
+        self._works = []
+
+    def ready(self, floor_offset: int):
+        """All gradients at arena offsets >= floor_offset are final: launch every bucket that lies entirely above it."""
         if self.world == 1:
-            return 1.0
-        works = [dist.all_reduce(flat_grad[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-                 for a, b in reversed(self.bounds)]
-        for w in works:
+            return
+        g = self.engine.grad
+        while self._next >= 0 and self.bounds[self._next][0] >= floor_offset:
+            a, b = self.bounds[self._next]
+            self._works.append(dist.all_reduce(g[a:b], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            self._next -= 1
+
+    def finish(self) -> float:
+        self.ready(0)
+        for w in self._works:
             w.wait()
+        self._works = []
         return 1.0 / self.world
+
+    def __call__(self, flat_grad: torch.Tensor) -> float:
+        """Non-overlapped form (whole arena at once); returns the scale (1/world) the optimiser must apply."""
+        self.begin()
+        return self.finish()
 
 
 def shard_batch(global_batch: int, rank: int, world: int) -> tuple[int, int]:

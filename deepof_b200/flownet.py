@@ -112,8 +112,9 @@ class FlowNetS:
 
     def __init__(self, batch: int, height: int = 384, width: int = 512, device="cuda", variant: str = "A",
                  math_mode: str = "fp32", mean=FLYINGCHAIRS_MEAN, hyper=None, seed: int | None = 1, tc_wgrad: bool = False):
-        if height % 64 or width % 64:
-            raise ValueError("FlowNetS needs H and W to be multiples of 64 (the reference resizes/pads as well, SURVEY.md 0.5)")
+        mult = 32 if self.ARCH == "V" else 64
+        if height % mult or width % mult:
+            raise ValueError(f"H and W must be multiples of {mult} (the reference resizes/pads as well, SURVEY.md 0.5)")
         if not torch.cuda.is_available():
             raise ops.DeepOFError("deepof_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.B, self.H, self.W = batch, height, width
@@ -180,6 +181,8 @@ class FlowNetS:
 
     # ------------------------------------------------------------------ buffers
     ARCH = "S"
+    N_SCALES = 6
+    REFINE_SPEC = REFINE
 
     def _alloc(self):
         B, H, W, dev = self.B, self.H, self.W, self.device
@@ -189,8 +192,23 @@ class FlowNetS:
         # kernel, which reads the SAME padding (2,3) of the 7x7/2 conv straight from the border
         self.x6_origin = (2, 2) if self.math == MATH_TF32 else (0, 0)
         xshape = (H + 6, W + 8, 8) if self.math == MATH_TF32 else (H, W, 8)
+        if self.ARCH == "V":            # VGG16: 3x3/1 first layer, generic kernels, 6 channels padded to one 32-float K block
+            xshape, self.x6_origin = (H, W, 32), (0, 0)
         self.x6 = z(*xshape)
         self.x6b = z(*xshape) if self.ARCH == "C" else None          # siamese: target image in its own buffer
+        shp = self._buffer_shapes()
+        self.act = {k: z(*v) for k, v in shp.items()}
+        self.dact = {k: z(*v) for k, v in shp.items()}
+        self.hw = {s: (H >> s, W >> s) for s in range(1, self.N_SCALES + 1)}
+        self.pr = {s: z(*self.hw[s], 2) for s in range(1, self.N_SCALES + 1)}
+        self.dpr = {s: z(*self.hw[s], 2) for s in range(1, self.N_SCALES + 1)}
+        self.pyr_src = {s: z(*self.hw[s], 3) for s in range(1, self.N_SCALES + 1)}
+        self.pyr_tgt = {s: z(*self.hw[s], 3) for s in range(1, self.N_SCALES + 1)}
+        self.recon1 = z(*self.hw[1], 3)
+        self.loss4 = torch.zeros(self.N_SCALES, 4, dtype=torch.float32, device=dev)
+
+    def _buffer_shapes(self):
+        H, W = self.H, self.W
         shp = {"concat1": (H // 2, W // 2, 128), "concat2": (H // 4, W // 4, 224), "c31": (H // 8, W // 8, 256),
                "concat3": (H // 8, W // 8, 416), "c41": (H // 16, W // 16, 512), "concat4": (H // 16, W // 16, 800),
                "c51": (H // 32, W // 32, 512), "concat5": (H // 32, W // 32, 1056), "c61": (H // 64, W // 64, 1024),
@@ -199,15 +217,7 @@ class FlowNetS:
             del shp["c31"]
             shp.update({"c1b": (H // 2, W // 2, 64), "c2b": (H // 4, W // 4, 128), "c3a": (H // 8, W // 8, 256),
                         "c3b": (H // 8, W // 8, 256), "cat3": (H // 8, W // 8, 480)})
-        self.act = {k: z(*v) for k, v in shp.items()}
-        self.dact = {k: z(*v) for k, v in shp.items()}
-        self.hw = {s: (H >> s, W >> s) for s in range(1, 7)}
-        self.pr = {s: z(*self.hw[s], 2) for s in range(1, 7)}
-        self.dpr = {s: z(*self.hw[s], 2) for s in range(1, 7)}
-        self.pyr_src = {s: z(*self.hw[s], 3) for s in range(1, 7)}
-        self.pyr_tgt = {s: z(*self.hw[s], 3) for s in range(1, 7)}
-        self.recon1 = z(*self.hw[1], 3)
-        self.loss4 = torch.zeros(6, 4, dtype=torch.float32, device=dev)
+        return shp
 
     def _conv_rec(self, name, k, stride, cin, cout, x, dx, y, dy, acc=False, wname=None, xpad=None, ih=None, iw=None):
         """One conv layer record: y = ELU(conv(x)); backward writes (or accumulates, acc=True) into dx."""
@@ -239,18 +249,21 @@ class FlowNetS:
             R("conv6_2", 3, 1, 1024, 1024, full(a["c61"]), full(d["c61"]), full(a["c62"]), full(d["c62"])),
         ]
 
+    def _plan_feat(self):
+        a, d, S = self.act, self.dact, Slab
+        return {6: (full(a["c62"]), full(d["c62"])), 5: (S(a["concat5"], 0, 1026), S(d["concat5"], 0, 1026)),
+                4: (S(a["concat4"], 0, 770), S(d["concat4"], 0, 770)), 3: (S(a["concat3"], 0, 386), S(d["concat3"], 0, 386)),
+                2: (S(a["concat2"], 0, 194), S(d["concat2"], 0, 194)), 1: (S(a["concat1"], 0, 98), S(d["concat1"], 0, 98))}
+
     def _plan(self):
         B = self.B
         a, d = self.act, self.dact
         S = Slab
         self.tower = self._plan_tower()
-        feat = {6: (full(a["c62"]), full(d["c62"])), 5: (S(a["concat5"], 0, 1026), S(d["concat5"], 0, 1026)),
-                4: (S(a["concat4"], 0, 770), S(d["concat4"], 0, 770)), 3: (S(a["concat3"], 0, 386), S(d["concat3"], 0, 386)),
-                2: (S(a["concat2"], 0, 194), S(d["concat2"], 0, 194)), 1: (S(a["concat1"], 0, 98), S(d["concat1"], 0, 98))}
-        self.feat = feat
+        self.feat = self._plan_feat()
         cat = {5: "concat5", 4: "concat4", 3: "concat3", 2: "concat2", 1: "concat1"}
         self.refine = []
-        for s, cfeat, up, upc, uppr, skipc in REFINE:
+        for s, cfeat, up, upc, uppr, skipc in self.REFINE_SPEC:
             hs, ws = self.hw[s]
             g = conv_geom(B, 2 * hs, 2 * ws, upc, cfeat, 4, 2)     # the conv whose input-gradient is this deconv
             assert g.oh == hs and g.ow == ws and g.pad_t == 1
@@ -261,8 +274,8 @@ class FlowNetS:
 
     # ------------------------------------------------------------------ forward
     def _preprocess(self, source, target):
-        self._k("preprocess", ops.preprocess, source, target, self.mean, self.x6, [self.pyr_src[s] for s in range(1, 7)],
-                [self.pyr_tgt[s] for s in range(1, 7)], self.x6_origin, self.x6b)
+        self._k("preprocess", ops.preprocess, source, target, self.mean, self.x6, [self.pyr_src[s] for s in range(1, self.N_SCALES + 1)],
+                [self.pyr_tgt[s] for s in range(1, self.N_SCALES + 1)], self.x6_origin, self.x6b)
 
     def _fwd_layer(self, L):
         P, mth = self.params, self.math
@@ -272,6 +285,8 @@ class FlowNetS:
                 self._k("conv_fwd:" + L["name"], ops.conv1_fwd, L["g"], L["xpad"], self.x6_origin, w, b, L["y"], ACT_ELU)
             else:
                 self._k("conv_fwd:" + L["name"], ops.conv_fwd, L["g"], L["x"], w, b, L["y"], ACT_ELU, mth)
+        elif L["op"] == "pool":
+            self._k("pool_fwd:" + L["name"], ops.maxpool2_fwd, L["x"], L["y"])
         elif L["op"] == "corr":
             self._k("corr_fwd", ops.corr_fwd, L["f1"], L["f2"], L["y"], L["max_disp"], L["stride2"], ACT_ELU, mth)
 
@@ -286,6 +301,8 @@ class FlowNetS:
                 self._k("conv_wgrad:" + L["name"], ops.conv_wgrad, L["g"], L["x"], L["dy"], dw, None, mthw)
             if L["dx"] is not None:
                 self._k("conv_dgrad:" + L["name"], ops.conv_dgrad, L["g"], L["dy"], w, None, L["dx"], ACT_NONE, L["acc"], mth)
+        elif L["op"] == "pool":
+            self._k("pool_bwd:" + L["name"], ops.maxpool2_bwd, L["x"], L["dy"], L["dx"])
         elif L["op"] == "corr":
             self._k("elu_bwd:corr", ops.elu_bwd, L["dy4"], L["y4"], None)
             self._k("corr_bwd", ops.corr_bwd, L["f1"], L["f2"], L["dy"], L["df1"], L["df2"], L["max_disp"], L["stride2"])
@@ -311,7 +328,7 @@ class FlowNetS:
         self.loss_weight = lw
         hp = self.hyper
         scales = []
-        for s in range(1, 7):
+        for s in range(1, self.N_SCALES + 1):
             wgt = lw[s - 1]
             scales.append(dict(flow=self.pr[s], src=self.pyr_src[s], tgt=self.pyr_tgt[s],
                                recon=self.recon1 if s == 1 else None, dflow=self.dpr[s] if with_grad else None,
@@ -324,8 +341,8 @@ class FlowNetS:
     def outputs(self):
         """(losses, flows_all, prev1) exactly as flowNet returns them (flyingChairsWrapFlow.py:126-129)."""
         keys = ("total", "Charbonnier_reconstruct", "U_loss", "V_loss")
-        losses = [{k: self.loss4[s, i] for i, k in enumerate(keys)} for s in range(6)]
-        flows_all = [self.pr[s] * FLOW_SCALES[s] for s in range(1, 7)]
+        losses = [{k: self.loss4[s, i] for i, k in enumerate(keys)} for s in range(self.N_SCALES)]
+        flows_all = [self.pr[s] * FLOW_SCALES[s] for s in range(1, self.N_SCALES + 1)]
         return losses, flows_all, self.recon1
 
     def total_loss(self) -> torch.Tensor:
@@ -337,13 +354,21 @@ class FlowNetS:
         return torch.dot(self.loss4[:, 0], self._lw_dev)
 
     # ------------------------------------------------------------------ backward
-    def backward(self):
+    def _grad_ready(self, reducer, *names):
+        """Tell the gradient reducer that every parameter at or above the lowest offset of ``names`` has its final gradient."""
+        if reducer is not None:
+            reducer.ready(min(self.arena.offsets[n + "/weights"] for n in names))
+
+    def backward(self, reducer=None):
         P, G, mth, mthw = self.params, self.grads, self.math, self.math_wgrad
         self._k("zero_grad", self.grad.zero_)
+        if reducer is not None:
+            reducer.begin()
         # refinement part, finest scale first (each pr_s gradient is complete when its scale is reached)
         x1, dx1 = self.feat[1]
         self._k("head_wgrad:pr1", ops.head_wgrad, x1, self.dpr[1], G["pr1/weights"], G["pr1/biases"])
         self._k("head_dgrad:pr1", ops.head_dgrad, self.dpr[1], P["pr1/weights"], dx1, accumulate=False)
+        self._grad_ready(reducer, "pr1")
         for R in reversed(self.refine):                      # s = 2,3,4,5,6
             s = R["s"]
             x, dx = self.feat[s]
@@ -358,9 +383,13 @@ class FlowNetS:
             # pr_s head
             self._k(f"head_wgrad:pr{s}", ops.head_wgrad, x, self.dpr[s], G[f"pr{s}/weights"], G[f"pr{s}/biases"])
             self._k(f"head_dgrad:pr{s}", ops.head_dgrad, self.dpr[s], P[f"pr{s}/weights"], dx, accumulate=True)
-        # contracting tower, top down
-        for L in reversed(self.tower):
+            self._grad_ready(reducer, f"pr{s}", R["up"], R["uppr"])
+        # contracting tower, top down (shared siamese weights are final after their LAST use, which the reverse order reaches last)
+        rev = list(reversed(self.tower))
+        for i, L in enumerate(rev):
             self._bwd_layer(L)
+            if L["op"] == "conv" and all(M.get("wname") != L["wname"] for M in rev[i + 1:]):
+                self._grad_ready(reducer, L["wname"])
 
     # ------------------------------------------------------------------ optimiser
     def adam_step(self, lr: float, grad_scale: float = 1.0, beta1=0.9, beta2=0.999, eps=1e-8):
@@ -373,10 +402,8 @@ class FlowNetS:
     def train_step(self, source, target, loss_weight=LOSS_WEIGHTS, lr: float = 1.6e-5, allreduce=None):
         """One ``train_op.run(feed_dict)`` (flyingChairsTrain.py:178): forward, backward, Adam."""
         self.forward(source, target, loss_weight, with_grad=True)
-        self.backward()
-        scale = 1.0
-        if allreduce is not None:
-            scale = allreduce(self.grad)
+        self.backward(reducer=allreduce)
+        scale = allreduce.finish() if allreduce is not None else 1.0
         self.adam_step(lr, grad_scale=scale)
 
 
@@ -435,3 +462,96 @@ class FlowNetC(FlowNetS):
             corr,
             R("conv3_1", 3, 1, 473, 256, S(a["cat3"], 0, 473), S(d["cat3"], 0, 473), S(a["concat3"], 0, 256), S(d["concat3"], 0, 256)),
         ] + self._plan_tower_top()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# VGG16 guided model: flyingChairsWrapFlow_vgg.VGG16 (flyingChairsWrapFlow_vgg.py:7-132) -- what deepOF_fc.py
+# really launches.  13 3x3 ELU convs + 5 2x2 max-pools, the same decoder at 5 scales (pool outputs are the skips), loss variant B,
+# separate photo (network input) and geo (loss images) pairs, all pre-scaled by the trainer (flyingChairsTrain_vgg.py:181-188).
+# ---------------------------------------------------------------------------------------------------------------------
+VGG_CONVS = [("conv1_1", 6, 64), ("conv1_2", 64, 64), ("conv2_1", 64, 128), ("conv2_2", 128, 128), ("conv3_1", 128, 256),
+             ("conv3_2", 256, 256), ("conv3_3", 256, 256), ("conv4_1", 256, 512), ("conv4_2", 512, 512), ("conv4_3", 512, 512),
+             ("conv5_1", 512, 512), ("conv5_2", 512, 512), ("conv5_3", 512, 512)]
+VGG_REFINE = [(5, 512, "upconv4", 256, "up_pr5to4", 512), (4, 770, "upconv3", 128, "up_pr4to3", 256),
+              (3, 386, "upconv2", 64, "up_pr3to2", 128), (2, 194, "upconv1", 32, "up_pr2to1", 64)]
+VGG_LOSS_WEIGHTS = (16.0, 8.0, 4.0, 2.0, 1.0)         # flyingChairsTrain_vgg.py:171
+
+
+def param_shapes_vgg() -> "OrderedDict[str, tuple]":
+    sh: "OrderedDict[str, tuple]" = OrderedDict()
+    for name, cin, cout in VGG_CONVS:
+        sh[name + "/weights"] = (3, 3, cin, cout)
+        sh[name + "/biases"] = (cout,)
+    for s, cfeat, up, upc, uppr, _skip in VGG_REFINE:
+        sh[f"pr{s}/weights"] = (3, 3, cfeat, 2)
+        sh[f"pr{s}/biases"] = (2,)
+        sh[up + "/weights"] = (4, 4, upc, cfeat)
+        sh[up + "/biases"] = (upc,)
+        sh[uppr + "/weights"] = (4, 4, 2, 2)
+        sh[uppr + "/biases"] = (2,)
+    sh["pr1/weights"] = (3, 3, 98, 2)
+    sh["pr1/biases"] = (2,)
+    return sh
+
+
+class VGG16Flow(FlowNetS):
+    ARCH = "V"
+    N_SCALES = 5
+    REFINE_SPEC = VGG_REFINE
+
+    def __init__(self, batch, height=320, width=448, device="cuda", variant="B", **kw):
+        super().__init__(batch, height, width, device=device, variant=variant, **kw)
+
+    @staticmethod
+    def param_shapes():
+        return param_shapes_vgg()
+
+    def _buffer_shapes(self):
+        H, W = self.H, self.W
+        shp = {"concat1": (H // 2, W // 2, 128), "concat2": (H // 4, W // 4, 224), "concat3": (H // 8, W // 8, 416),
+               "concat4": (H // 16, W // 16, 800), "pool5": (H // 32, W // 32, 512)}
+        for lvl, (div, c, n) in enumerate([(1, 64, 2), (2, 128, 2), (4, 256, 3), (8, 512, 3), (16, 512, 3)], start=1):
+            for i in range(1, n + 1):
+                shp[f"c{lvl}{i}"] = (H // div, W // div, c)
+        return shp
+
+    def _plan_tower(self):
+        a, d, S, R = self.act, self.dact, Slab, self._conv_rec
+        recs = []
+        skip_c = {1: 64, 2: 128, 3: 256, 4: 512}
+        prev, dprev, prev_acc = S(self.x6, 0, 6), None, False
+        for lvl, n in enumerate([2, 2, 3, 3, 3], start=1):
+            for i in range(1, n + 1):
+                name = f"conv{lvl}_{i}"
+                cin, cout = next((ci, co) for nm, ci, co in VGG_CONVS if nm == name)
+                y, dy = full(a[f"c{lvl}{i}"]), full(d[f"c{lvl}{i}"])
+                recs.append(R(name, 3, 1, cin, cout, prev, dprev, y, dy, acc=prev_acc))
+                prev, dprev, prev_acc = y, dy, False
+            if lvl < 5:
+                py, pdy = S(a[f"concat{lvl}"], 0, skip_c[lvl]), S(d[f"concat{lvl}"], 0, skip_c[lvl])
+            else:
+                py, pdy = full(a["pool5"]), full(d["pool5"])
+            recs.append(dict(op="pool", name=f"pool{lvl}", x=prev, dx=dprev, y=py, dy=pdy))
+            prev, dprev, prev_acc = py, pdy, True        # the next conv's input gradient ADDS to the decoder's contributions
+        return recs
+
+    def _plan_feat(self):
+        a, d, S = self.act, self.dact, Slab
+        return {5: (full(a["pool5"]), full(d["pool5"])), 4: (S(a["concat4"], 0, 770), S(d["concat4"], 0, 770)),
+                3: (S(a["concat3"], 0, 386), S(d["concat3"], 0, 386)), 2: (S(a["concat2"], 0, 194), S(d["concat2"], 0, 194)),
+                1: (S(a["concat1"], 0, 98), S(d["concat1"], 0, 98))}
+
+    def forward(self, photo_source, photo_target, loss_weight=VGG_LOSS_WEIGHTS, with_grad=True, geo_source=None, geo_target=None,
+                prescaled=True):
+        """VGG16(photo_source, photo_target, geo_source, geo_target, loss_weight) (flyingChairsWrapFlow_vgg.py:7).
+        ``prescaled`` (the reference's contract): the four images are already (x - mean)/255."""
+        self._geo = (geo_source if geo_source is not None else photo_source, geo_target if geo_target is not None else photo_target)
+        self._prescaled = prescaled
+        return super().forward(photo_source, photo_target, loss_weight, with_grad)
+
+    def _preprocess(self, source, target):
+        mean, div = ((0.0, 0.0, 0.0), 1.0) if self._prescaled else (self.mean, 255.0)
+        n = self.N_SCALES
+        self._k("preprocess", ops.preprocess, source, target, mean, self.x6, [], [], (0, 0), None, div)
+        self._k("preprocess", ops.preprocess, self._geo[0], self._geo[1], mean, None, [self.pyr_src[s] for s in range(1, n + 1)],
+                [self.pyr_tgt[s] for s in range(1, n + 1)], (0, 0), None, div)

@@ -75,8 +75,8 @@ class TrainStep:
         lr = float(feed_dict.get("learning_rate", LEARNING_RATE))
         self.engine.forward(src, tgt, lw, with_grad=True)
         self._consumed[slot].record()                 # inputs are only read by the pre-processing kernel
-        self.engine.backward()
-        scale = self.reducer(self.engine.grad) if self.reducer is not None else 1.0
+        self.engine.backward(reducer=self.reducer)                       # bucketed all-reduce overlapped with the backward
+        scale = self.reducer.finish() if self.reducer is not None else 1.0
         self.engine.adam_step(lr, grad_scale=scale)
         # lagged loss read-back: D2H into pinned memory, consumed one step later (or by last_loss(sync=True))
         self._loss_pin[slot:slot + 1].copy_(self.engine.total_loss().reshape(1), non_blocking=True)

@@ -86,10 +86,12 @@ def conv_geom(B, ih, iw, ci, co, k, stride) -> ConvGeom:
     return ConvGeom(B, ih, iw, ci, oh, ow, co, k, k, stride, pt, pl)
 
 
-def preprocess(src, tgt, mean, x6, pyr_src, pyr_tgt, origin=(0, 0), x6b=None):
+def preprocess(src, tgt, mean, x6, pyr_src, pyr_tgt, origin=(0, 0), x6b=None, divisor=255.0):
     """x6 may be larger than the image (zero border for dofb_conv1_*); ``origin`` = (row, col) of the image in it.
     With ``x6b`` (siamese models) the source goes to x6[..., 0:3] and the target to x6b[..., 0:3] instead of 6 stacked channels."""
-    _req(src, "src"); _req(tgt, "tgt"); _req(x6, "x6")
+    _req(src, "src"); _req(tgt, "tgt")
+    if x6 is not None:
+        _req(x6, "x6")
     B, H, W, _ = src.shape
     n = len(pyr_src)
     for t in list(pyr_src) + list(pyr_tgt):
@@ -98,8 +100,18 @@ def preprocess(src, tgt, mean, x6, pyr_src, pyr_tgt, origin=(0, 0), x6b=None):
     ps = (C.c_void_p * max(n, 1))(*[t.data_ptr() for t in pyr_src])
     pt = (C.c_void_p * max(n, 1))(*[t.data_ptr() for t in pyr_tgt])
     lib = _lib.load()
-    check(lib.dofb_preprocess(src.data_ptr(), tgt.data_ptr(), m, B, H, W, x6.data_ptr(), x6b.data_ptr() if x6b is not None else None,
-                              x6.shape[3], x6.shape[1], x6.shape[2], origin[0], origin[1], n, ps, pt, _stream()))
+    xs = x6.shape if x6 is not None else (0, 0, 0, 0)
+    check(lib.dofb_preprocess(src.data_ptr(), tgt.data_ptr(), m, float(divisor), B, H, W, x6.data_ptr() if x6 is not None else None,
+                              x6b.data_ptr() if x6b is not None else None, xs[3], xs[1], xs[2], origin[0], origin[1], n, ps, pt, _stream()))
+
+
+def maxpool2_fwd(x: Slab, y: Slab):
+    assert x.c == y.c and x.h == 2 * y.h and x.w == 2 * y.w
+    check(_lib.load().dofb_maxpool2_fwd(x.ptr, x.ld, y.B, y.h, y.w, y.c, y.ptr, y.ld, _stream()))
+
+
+def maxpool2_bwd(x: Slab, dy: Slab, dx: Slab):
+    check(_lib.load().dofb_maxpool2_bwd(x.ptr, x.ld, dy.ptr, dy.ld, dy.B, dy.h, dy.w, dy.c, dx.ptr, dx.ld, _stream()))
 
 
 def conv1_fwd(g: ConvGeom, xpad, origin, w, b, y: Slab, act=ACT_ELU):

@@ -40,7 +40,10 @@ void dofb_reset_launch_count(void);
 /* Replaces: tf.sub/tf.truediv/tf.nn.local_response_normalization/tf.concat and
  * the 12 tf.image.resize_bilinear calls of flyingChairsWrapFlow.py:16-31,61-62,
  * 72-73,83-84,94-95,105-106,116-117.
- *   src,tgt : [B,H,W,3] BGR 0..255
+ *   src,tgt : [B,H,W,3] BGR; every pixel becomes (x - mean) / divisor (255 for raw 0..255 images; mean 0 / divisor 1 for the
+ *             pre-scaled feeds of flyingChairsTrain_vgg.py:181-188)
+ *   x6 may be NULL (pyramid-only call: the VGG16 model builds its network input from the photo pair and the loss images from the
+ *             geo pair, flyingChairsWrapFlow_vgg.py:7-20)
  *   x6      : [B,x6_h,x6_w,x6_ld] out; the image occupies rows [x6_y0, x6_y0+H) and columns [x6_x0, x6_x0+W)
  *             (a zero border around it is the caller's: dofb_conv1_* reads it as the conv padding); channels
  *             0..2 = (src-mean)/255, 3..5 = (tgt-mean)/255, channels 6..x6_ld-1 are zero-filled.
@@ -49,7 +52,7 @@ void dofb_reset_launch_count(void);
  *   pyr_src/pyr_tgt[s] (s=0..n_scales-1): [B,H>>(s+1),W>>(s+1),3] LRN-normalised,
  *             decimated (legacy resize_bilinear at an integer ratio == x[::r, ::r]).
  */
-int dofb_preprocess(const float *src, const float *tgt, const float mean_bgr[3],
+int dofb_preprocess(const float *src, const float *tgt, const float mean_bgr[3], float divisor,
                     int B, int H, int W, float *x6, float *x6b, int x6_ld, int x6_h, int x6_w, int x6_y0, int x6_x0,
                     int n_scales, float *const *pyr_src, float *const *pyr_tgt, void *stream);
 
@@ -124,6 +127,11 @@ int dofb_conv1_fwd(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, 
                    const float *bias, float *y, int y_ld, int act, void *stream);
 int dofb_conv1_wgrad(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *dy,
                      int dy_ld, float *dw, float *db, void *stream);
+
+/* slim.max_pool2d(x, [2,2]) (stride 2, VALID) and its gradient (flyingChairsWrapFlow_vgg.py:22-41).  x [B,2oh,2ow,c], y [B,oh,ow,c].
+ * The backward OVERWRITES dx (gradient to the first maximum of each window, zero elsewhere). */
+int dofb_maxpool2_fwd(const float *x, int x_ld, int B, int oh, int ow, int c, float *y, int y_ld, void *stream);
+int dofb_maxpool2_bwd(const float *x, int x_ld, const float *dy, int dy_ld, int B, int oh, int ow, int c, float *dx, int dx_ld, void *stream);
 
 /* The tcgen05 path keeps re-packed (K-major, zero-padded) copies of the weights it has seen, keyed by pointer.  Call this
  * whenever weight VALUES change (i.e. after every optimiser step / parameter load); packs are rebuilt lazily. */

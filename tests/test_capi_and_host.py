@@ -102,6 +102,15 @@ assert abs(scale - 1.0 / world) < 1e-12
 want = sum(range(1, world + 1))
 assert torch.all(e.grad == want), (rank, e.grad[:3])
 assert len(r.bounds) == 4 and r.bounds[-1][1] == n
+# overlapped form: the backward reports falling arena offsets; every bucket is reduced exactly once, top bucket first
+e.grad.fill_(float(rank + 1))
+r.begin()
+r.ready(900000); assert len(r._works) == 0          # the last bucket starts at 786432: not yet entirely final
+r.ready(786432); assert len(r._works) == 1
+r.ready(300000); assert len(r._works) == 2
+r.ready(300000); assert len(r._works) == 2          # idempotent
+assert abs(r.finish() - 1.0 / world) < 1e-12
+assert torch.all(e.grad == want)
 dist.barrier()
 dist.destroy_process_group()
 print("rank", rank, "ok")

@@ -172,3 +172,41 @@ def test_flownet_functional_signature():
     losses, flows_all, prev1 = Wf.flowNet(src.cuda(), tgt.cuda(), torch.tensor([16., 8, 4, 2, 1, 1]))
     assert len(losses) == 6 and len(flows_all) == 6 and prev1.shape == (1, 96, 128, 3)
     assert [tuple(f.shape) for f in flows_all][-1] == (1, 3, 4, 2)
+
+
+def test_variant_B_engine_matches_oracle():
+    """BASELINE configs[3] semantics: the 'guided' loss of flyingChairsWrapFlow_vgg / version1 warpflow (variant B)."""
+    from deepof_b200.flownet import FlowNetS
+    B, H, W = 1, 192, 256
+    src, tgt, _ = synth.make_pairs(B, H, W, seed=8)
+    params = fs.init_params(seed=1)
+    total, grads, losses, flows_all, _p = fs.loss_and_grads(params, src, tgt, variant="B")
+    _t, g64, *_ = fs.loss_and_grads({k: v.double() for k, v in params.items()}, src.double(), tgt.double(), variant="B")
+    eng = FlowNetS(B, H, W, seed=None, variant="B")
+    eng.load_params(params)
+    eng.forward(src.cuda(), tgt.cuda())
+    eng.backward()
+    want = torch.tensor([[l[k].item() for k in KEYS] for l in losses])
+    assert torch.allclose(eng.loss4.cpu(), want, rtol=5e-5, atol=1e-6)
+    for name in grads:
+        e_dev, e_cpu = rel(eng.grads[name], g64[name]), rel(grads[name], g64[name])
+        assert e_dev < 3.0 * e_cpu + 1e-3, (name, e_dev, e_cpu)
+
+
+def test_sintel_shaped_config():
+    """BASELINE configs[4]: Sintel 436x1024 padded to 448x1024, Sintel mean, alpha_c = alpha_s = 0.3, lambda = 0,
+    loss weights [16,8,4,4,2,1] (sintelTrain.py:50-53,180; sintelWrapFlow.py:773)."""
+    from deepof_b200.flownet import FlowNetS, SINTEL_MEAN
+    B, H, W = 1, 448, 1024
+    hyper = dict(epsilon=1e-4, alpha_c=0.3, alpha_s=0.3, lambda_smooth=0.0)
+    lw = (16.0, 8.0, 4.0, 4.0, 2.0, 1.0)
+    src, tgt, _ = synth.make_pairs(B, H, W, seed=12)
+    params = fs.init_params(seed=1)
+    with torch.no_grad():
+        losses, flows_all, _p, total = fs.forward(params, src, tgt, lw, mean=SINTEL_MEAN, hyper=hyper)
+    for mode, tol in (("fp32", 2e-4), ("tf32", 5e-3)):
+        eng = FlowNetS(B, H, W, seed=None, mean=SINTEL_MEAN, hyper=hyper, math_mode=mode, tc_wgrad=(mode == "tf32"))
+        eng.load_params(params)
+        eng.train_step(src.cuda(), tgt.cuda(), lw, 1.6e-5)
+        assert (eng.pr[1].cpu() * 10.0 - flows_all[0]).abs().max() < tol, mode
+        assert abs(eng.total_loss().item() - total.item()) < (5e-5 if mode == "fp32" else 5e-3) * abs(total.item())

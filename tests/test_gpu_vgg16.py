@@ -1,0 +1,90 @@
+"""VGG16 guided model (flyingChairsWrapFlow_vgg.py:7-132) on the device vs oracle/vgg16.py."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import vgg16 as ov, synth, tf_ops  # noqa: E402
+
+KEYS = ("total", "Charbonnier_reconstruct", "U_loss", "V_loss")
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def _inputs(B, H, W, seed):
+    src, tgt, _ = synth.make_pairs(B, H, W, seed=seed)
+    mean = torch.tensor([97.53, 99.24, 97.06]).view(1, 1, 1, 3)
+    geo_s, geo_t = (src - mean) / 255.0, (tgt - mean) / 255.0              # flyingChairsTrain_vgg.py:181-182
+    g = torch.Generator().manual_seed(seed)
+    photo_s = geo_s * 1.1 + 0.02 * torch.randn(geo_s.shape, generator=g)   # stand-in for photoAugmentation (:186)
+    photo_t = geo_t * 0.9 + 0.02 * torch.randn(geo_t.shape, generator=g)
+    return photo_s, photo_t, geo_s, geo_t
+
+
+def test_maxpool_fwd_bwd():
+    from deepof_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 8, 12, 64, generator=g)
+    xr = x.clone().requires_grad_(True)
+    y = ov.max_pool2(xr)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    xb = torch.zeros(2, 8, 12, 96, device="cuda"); xb[..., 16:80] = x.cuda()
+    yb = torch.zeros(2, 4, 6, 128, device="cuda")
+    ops.maxpool2_fwd(ops.Slab(xb, 16, 64), ops.Slab(yb, 32, 64))
+    assert torch.equal(yb[..., 32:96].cpu(), y.detach())
+    dyb = torch.zeros(2, 4, 6, 128, device="cuda"); dyb[..., 32:96] = dy.cuda()
+    dxb = torch.full((2, 8, 12, 64), 7.0, device="cuda")
+    ops.maxpool2_bwd(ops.Slab(xb, 16, 64), ops.Slab(dyb, 32, 64), ops.Slab(dxb, 0, 64))
+    assert torch.equal(dxb.cpu(), xr.grad)
+
+
+@pytest.fixture(scope="module")
+def case():
+    from deepof_b200.flownet import VGG16Flow
+    B, H, W = 2, 96, 128
+    imgs = _inputs(B, H, W, 3)
+    params = ov.init_params(1)
+    total, grads, losses, flows_all, prev1 = ov.loss_and_grads(params, *imgs)
+    _t, g64, *_ = ov.loss_and_grads({k: v.double() for k, v in params.items()}, *[i.double() for i in imgs])
+    eng = VGG16Flow(B, H, W, seed=None)
+    eng.load_params(params)
+    eng.forward(imgs[0].cuda(), imgs[1].cuda(), ov.LOSS_WEIGHTS, True, imgs[2].cuda(), imgs[3].cuda())
+    eng.backward()
+    torch.cuda.synchronize()
+    return dict(eng=eng, imgs=imgs, params=params, total=total, grads=grads, g64=g64, losses=losses, flows_all=flows_all, prev1=prev1)
+
+
+def test_vgg16_forward(case):
+    eng = case["eng"]
+    want = torch.tensor([[l[k].item() for k in KEYS] for l in case["losses"]])
+    assert torch.allclose(eng.loss4.cpu(), want, rtol=5e-5, atol=1e-6), (eng.loss4.cpu(), want)
+    losses, flows_all, prev1 = eng.outputs()
+    assert len(losses) == 5 and len(flows_all) == 5
+    for s in range(5):
+        assert (flows_all[s].cpu() - case["flows_all"][s].detach()).abs().max() < 2e-4, s
+    assert (prev1.cpu() - case["prev1"].detach()).abs().max() < 1e-4
+
+
+def test_vgg16_gradients(case):
+    eng = case["eng"]
+    for name, g32 in case["grads"].items():
+        e_dev, e_cpu = rel(eng.grads[name], case["g64"][name]), rel(g32, case["g64"][name])
+        assert e_dev < 3.0 * e_cpu + 1e-3, (name, e_dev, e_cpu)
+
+
+def test_vgg16_tf32_and_reference_signature(case):
+    from deepof_b200 import flyingChairsWrapFlow_vgg as Wv
+    from deepof_b200.flownet import VGG16Flow
+    B, H, W = 2, 96, 128
+    imgs = [i.cuda() for i in case["imgs"]]
+    etf = VGG16Flow(B, H, W, seed=None, math_mode="tf32", tc_wgrad=True)
+    etf.load_params(case["params"])
+    losses, flows_all, prev1 = Wv.VGG16(*imgs, torch.tensor(ov.LOSS_WEIGHTS), engine=etf)
+    assert prev1.shape == (B, H // 2, W // 2, 3)
+    assert (flows_all[0].cpu() - case["flows_all"][0].detach()).abs().max() < 2e-2          # TF32 operands
+    etf.train_step(imgs[0], imgs[1], ov.LOSS_WEIGHTS, 1.6e-5)                               # geo defaults to photo here
+    assert torch.isfinite(etf.theta).all()
