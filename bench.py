@@ -111,7 +111,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                        "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -268,8 +268,15 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- max over ranks ----
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    ddp_sync = None
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # replicas must hold bit-identical parameters after every step (same broadcast start, same reduced gradients)
+        chk = eng.theta.double().sum().reshape(1)
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        ddp_sync = bool((lo == hi).item())
     ms, ms_e2e = float(t[0]), float(t[1])
 
     # ---- per-launch timing for the roofline (rank 0, a few instrumented steps, CUDA events per launch) ----
@@ -378,7 +385,7 @@ def run_ours(args, rank, local_rank, world):
                     "h2d_bytes_per_step": 2 * B * H * W * 3 * 4, "d2h_bytes_per_step": 4,
                     "api": "deepof_b200.flyingChairsTrain.TrainStep.run(feed_dict) + last_loss(lag=1): pinned-host inputs, "
                            "H2D on a copy stream double-buffered against the previous step, loss D2H read one step late"},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "ddp_replicas_in_sync": ddp_sync,
             "roofline": roof, "cpu_baseline": cpu, "accuracy": accuracy, "kernel_classes": breakdown,
             "loss_after": loss_dev, "loss_after_e2e": last}
     print(json.dumps(line), flush=True)
