@@ -66,7 +66,7 @@ SIGNATURES = {
     "dofb_adam": (_I, [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _P]),
     "dofb_epe_sum": (_I, [_P, _P, _LL, _P, _P]),
     "dofb_corr_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P]),
-    "dofb_corr_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P]),
+    "dofb_corr_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _I, _I, _P]),
 }
 
 _lib = None

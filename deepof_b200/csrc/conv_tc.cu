@@ -1209,4 +1209,203 @@ int tc_corr_fwd(const float *f1, const float *f2, int ld, int B, int h, int w, i
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// FlowNetC correlation BACKWARD on tensor cores: two band-GEMMs per unit (image, row pair, 64-px column tile)
+//   df1[y,x,:] = 1/C * sum_{dy,dx} g[y,x,(dy,dx)]       * f2[y+dy, x+dx, :]      (transpose = 0, F = f2)
+//   df2[y,x,:] = 1/C * sum_{dy,dx} g[y-dy,x-dx,(dy,dx)] * f1[y-dy, x-dx, :]      (transpose = 1, F = f1)
+// For a fixed dy the sum over dx is a GEMM  D[128 px, 256 ch] += A[128 px, K] . B[K, 256 ch]  whose K runs over the 2 x 128 pixels of
+// the F rows the tile can see, B = those F pixels (MN-major, TMA, 8 boxes of 4 KB) and A = the BAND matrix of the g values
+// (<= 21 non-zeros per row).  A does not exist in memory: the four epilogue warps generate every 128x32 K-block straight into
+// shared memory in the K-major SWIZZLE_128B layout (16-byte chunk c of row r at chunk c ^ (r & 7)), publish it to the async proxy
+// (fence.proxy.async) and arrive on the same mbarrier the TMA bytes land on.  All D dy's x 8 K-blocks accumulate in ONE TMEM tile;
+// the epilogue runs once per unit.
+// ------------------------------------------------------------------------------------------------
+struct CorrBwdParams {
+    const float *g; int g_ld;         // dout [B,h,w,g_ld], D*D channels used
+    float *out; int out_ld;           // df1 or df2 [B,h,w,out_ld]
+    int B, h, w, c, md, s2, D, transpose;
+    int ypairs, xtiles, units;
+    float inv_c;
+};
+
+constexpr int CB_STAGES = 4;
+constexpr int CB_STAGE_BYTES = TC_A_BYTES + 8 * WG_REGION;      // 16 KB generated A + 32 KB TMA B
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_corr_bwd_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_constant__ CorrBwdParams P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + CB_STAGES * CB_STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + CB_STAGES;
+    uint64_t *acc_full = empty_bar + CB_STAGES;
+    uint64_t *acc_empty = acc_full + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kiters_per_unit = P.D * 8;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < CB_STAGES; ++s) { mbar_init(&full_bar[s], 5); mbar_init(&empty_bar[s], 1); }   // TMA thread + 4 generator warps
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 4);
+        fence_barrier_init();
+    }
+    if (warp == 4 && lane == 0) prefetch_tmap(&map_f);
+    if (warp == 5) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ===== TMA producer: the F pixels of this K block, one 4 KB box per 32-channel block (lanes 0..7) =====
+        int it = 0;
+        for (int u = blockIdx.x; u < P.units; u += gridDim.x) {
+            const int xt = u % P.xtiles, yp = (u / P.xtiles) % P.ypairs, b = u / (P.xtiles * P.ypairs);
+            const int x0 = xt * 64, y0 = yp * 2;
+            for (int dyi = 0; dyi < P.D; ++dyi) {
+                const int dy = -P.md + dyi * P.s2;
+                for (int kb = 0; kb < 8; ++kb, ++it) {
+                    const int s = it % CB_STAGES;
+                    const uint32_t ph = (it / CB_STAGES) & 1;
+                    if (lane == 0) {
+                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        mbar_expect_tx(&full_bar[s], 8 * WG_REGION);
+                    }
+                    __syncwarp();
+                    if (lane < 8) {
+                        const int ysrc = y0 + (kb >> 2) + (P.transpose ? -dy : dy);
+                        tma_load_4d(smem + s * CB_STAGE_BYTES + TC_A_BYTES + lane * WG_REGION, &map_f, &full_bar[s], lane * 32,
+                                    x0 - 32 + (kb & 3) * 32, ysrc, b);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_tf32(TC_BM, 256) | (1u << 16);     // A K-major, B MN-major
+            int it = 0, lu = 0;
+            for (int u = blockIdx.x; u < P.units; u += gridDim.x, ++lu) {
+                mbar_wait(acc_empty, (lu & 1) ^ 1);
+                tc_fence_after();
+                for (int k = 0; k < kiters_per_unit; ++k, ++it) {
+                    const int s = it % CB_STAGES;
+                    const uint32_t ph = (it / CB_STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * CB_STAGE_BYTES);
+                    const uint64_t da = make_desc_k128(sa), db = make_desc_mn128(sa + TC_A_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)          // K = 8 per MMA: A +32 B inside the swizzle row, B +8 pixel rows (1 KB)
+                        umma_tf32(tmem_base, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 64), idesc, (k | kk) != 0);
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(acc_full);
+            }
+        }
+    } else {
+        // ===== band-matrix generator + epilogue (warps 0..3: thread r owns row r of the tile = pixel (ry, xl)) =====
+        const int r = warp * 32 + lane;
+        const int ry = r >> 6, xl = r & 63;
+        int it = 0, lu = 0;
+        for (int u = blockIdx.x; u < P.units; u += gridDim.x, ++lu) {
+            const int xt = u % P.xtiles, yp = (u / P.xtiles) % P.ypairs, b = u / (P.xtiles * P.ypairs);
+            const int x0 = xt * 64, y0 = yp * 2;
+            const int py = y0 + ry, px = x0 + xl;                       // this row's pixel
+            const bool pix_ok = py < P.h && px < P.w;
+            for (int dyi = 0; dyi < P.D; ++dyi) {
+                const int dy = -P.md + dyi * P.s2;
+                // where this row's g values live: its own pixel (df1) or the source row py - dy (df2, column varies with k)
+                const int gy = P.transpose ? py - dy : py;
+                const bool grow_ok = pix_ok && gy >= 0 && gy < P.h;
+                const float *grow = P.g + ((long long)b * P.h + (grow_ok ? gy : 0)) * P.w * P.g_ld + dyi * P.D;
+                for (int kb = 0; kb < 8; ++kb, ++it) {
+                    const int s = it % CB_STAGES;
+                    const uint32_t ph = (it / CB_STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t *arow = smem + s * CB_STAGE_BYTES + r * 128;
+                    const bool active = grow_ok && (kb >> 2) == ry;
+                    const int xk0 = (kb & 3) * 32;
+#pragma unroll
+                    for (int cidx = 0; cidx < 8; ++cidx) {
+                        float v[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (active) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int xk = xk0 + cidx * 4 + e;
+                                const int t = P.transpose ? (xl + 32 - xk + P.md) : (xk - xl - 32 + P.md);
+                                if (t >= 0 && t <= 2 * P.md && (t % P.s2) == 0) {
+                                    if (!P.transpose) v[e] = __ldg(grow + (long long)px * P.g_ld + t / P.s2);
+                                    else {
+                                        const int gx = x0 - 32 + xk;
+                                        if (gx >= 0 && gx < P.w) v[e] = __ldg(grow + (long long)gx * P.g_ld + t / P.s2);
+                                    }
+                                }
+                            }
+                        }
+                        *reinterpret_cast<float4 *>(arow + ((cidx ^ (r & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+                    }
+                    fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_bar[s]);
+                }
+            }
+            // ---- epilogue of this unit ----
+            mbar_wait(acc_full, lu & 1);
+            tc_fence_after();
+            float *orow = P.out + (((long long)b * P.h + py) * P.w + px) * P.out_ld;
+#pragma unroll 1
+            for (int j = 0; j < 8; ++j) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * 32), v);
+                if (pix_ok && j * 32 < P.c) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        *reinterpret_cast<float4 *>(orow + j * 32 + q * 4) =
+                            make_float4(v[4 * q] * P.inv_c, v[4 * q + 1] * P.inv_c, v[4 * q + 2] * P.inv_c, v[4 * q + 3] * P.inv_c);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+int tc_corr_bwd(const float *f1, const float *f2, int ld, int B, int h, int w, int c, int md, int s2, const float *dout, int dout_ld,
+                float *df1, float *df2, int dld, cudaStream_t st) {
+    DOFB_CHECK_ARG(c == 256 && ld % 32 == 0 && dld % 4 == 0 && aligned16(f1) && aligned16(f2) && aligned16(df1) && aligned16(df2),
+                   "dofb_corr_bwd(tf32): needs c = 256 channels, pitches multiples of 32, 16-byte aligned pointers");
+    DOFB_CHECK_ARG(md >= 0 && md <= 32 && s2 >= 1 && md % s2 == 0, "dofb_corr_bwd(tf32): max displacement must be <= 32 and a multiple of stride2");
+    constexpr int smem = CB_STAGES * CB_STAGE_BYTES + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        DOFB_CUDA_OK(cudaFuncSetAttribute(tc_corr_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+        CorrBwdParams P;
+        P.g = dout; P.g_ld = dout_ld; P.out = pass == 0 ? df1 : df2; P.out_ld = dld;
+        P.B = B; P.h = h; P.w = w; P.c = c; P.md = md; P.s2 = s2; P.D = 2 * (md / s2) + 1; P.transpose = pass;
+        P.ypairs = (h + 1) / 2; P.xtiles = (w + 63) / 64; P.units = B * P.ypairs * P.xtiles; P.inv_c = 1.0f / (float)c;
+        const float *F = pass == 0 ? f2 : f1;
+        CUtensorMap mf;
+        const uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)B};
+        const uint64_t str[3] = {(uint64_t)ld * 4, (uint64_t)w * ld * 4, (uint64_t)h * w * ld * 4};
+        const uint32_t box[4] = {32, 32, 1, 1};
+        if (make_map(&mf, F, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+        const int grid = P.units < num_sms() ? P.units : num_sms();
+        tc_corr_bwd_kernel<<<grid, TC_THREADS, smem, st>>>(mf, P);
+        DOFB_LAUNCH_OK();
+    }
+    return 0;
+}
+
 }  // namespace dofb

@@ -88,6 +88,8 @@ __global__ void __launch_bounds__(256) corr_bwd_kernel(const float *__restrict__
 namespace dofb {
 int tc_corr_fwd(const float *f1, const float *f2, int ld, int B, int h, int w, int c, int md, int s2, float *out, int out_ld, int act,
                 cudaStream_t st);
+int tc_corr_bwd(const float *f1, const float *f2, int ld, int B, int h, int w, int c, int md, int s2, const float *dout, int dout_ld,
+                float *df1, float *df2, int dld, cudaStream_t st);
 }
 using namespace dofb;
 
@@ -111,8 +113,9 @@ extern "C" int dofb_corr_fwd(const float *f1, const float *f2, int ld, int B, in
 }
 
 extern "C" int dofb_corr_bwd(const float *f1, const float *f2, int ld, int B, int h, int w, int c, int max_disp, int stride2,
-                             const float *dout, int dout_ld, float *df1, float *df2, int dld, void *stream) {
+                             const float *dout, int dout_ld, float *df1, float *df2, int dld, int math, void *stream) {
     DOFB_CHECK_ARG(f1 && f2 && dout && df1 && df2 && B > 0 && h > 0 && w > 0 && c > 0 && stride2 > 0, "dofb_corr_bwd: bad argument");
+    if (math == DOFB_MATH_TF32) return tc_corr_bwd(f1, f2, ld, B, h, w, c, max_disp, stride2, dout, dout_ld, df1, df2, dld, as_stream(stream));
     DOFB_CHECK_ARG(c % 4 == 0 && ld % 4 == 0 && dld % 4 == 0 && aligned16(f1) && aligned16(f2) && aligned16(df1) && aligned16(df2),
                    "dofb_corr_bwd: c and pitches must be multiples of 4, pointers 16-byte aligned");
     DOFB_CHECK_ARG(max_disp % stride2 == 0, "dofb_corr_bwd: max_disp must be a multiple of stride2");

@@ -305,7 +305,7 @@ class FlowNetS:
             self._k("pool_bwd:" + L["name"], ops.maxpool2_bwd, L["x"], L["dy"], L["dx"])
         elif L["op"] == "corr":
             self._k("elu_bwd:corr", ops.elu_bwd, L["dy4"], L["y4"], None)
-            self._k("corr_bwd", ops.corr_bwd, L["f1"], L["f2"], L["dy"], L["df1"], L["df2"], L["max_disp"], L["stride2"])
+            self._k("corr_bwd", ops.corr_bwd, L["f1"], L["f2"], L["dy"], L["df1"], L["df2"], L["max_disp"], L["stride2"], mth)
 
     def forward(self, source: torch.Tensor, target: torch.Tensor, loss_weight=LOSS_WEIGHTS, with_grad: bool = True):
         """flowNet(inputs, outputs, loss_weight): runs the whole forward; when ``with_grad`` the fused

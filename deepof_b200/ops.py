@@ -204,10 +204,10 @@ def corr_fwd(f1: Slab, f2: Slab, out: Slab, max_disp=20, stride2=2, act=ACT_NONE
                                     _stream()))
 
 
-def corr_bwd(f1: Slab, f2: Slab, dout: Slab, df1: Slab, df2: Slab, max_disp=20, stride2=2):
+def corr_bwd(f1: Slab, f2: Slab, dout: Slab, df1: Slab, df2: Slab, max_disp=20, stride2=2, math=MATH_FP32):
     assert df1.ld == df2.ld
     check(_lib.load().dofb_corr_bwd(f1.ptr, f2.ptr, f1.ld, f1.B, f1.h, f1.w, f1.c, max_disp, stride2, dout.ptr, dout.ld,
-                                    df1.ptr, df2.ptr, df1.ld, _stream()))
+                                    df1.ptr, df2.ptr, df1.ld, math, _stream()))
 
 
 class WarpLoss:

@@ -176,7 +176,7 @@ int dofb_epe_sum(const float *flow, const float *gt, long long n_pix, double *ou
 int dofb_corr_fwd(const float *f1, const float *f2, int ld, int B, int h, int w, int c, int max_disp, int stride2,
                   float *out, int out_ld, int act, int math, void *stream);
 int dofb_corr_bwd(const float *f1, const float *f2, int ld, int B, int h, int w, int c, int max_disp, int stride2,
-                  const float *dout, int dout_ld, float *df1, float *df2, int dld, void *stream);
+                  const float *dout, int dout_ld, float *df1, float *df2, int dld, int math, void *stream);
 
 #ifdef __cplusplus
 }

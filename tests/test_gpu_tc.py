@@ -184,6 +184,26 @@ def test_tc_correlation_matches_simt(B, h, w, md, s2):
     assert float((o1[..., D * D:] - 5.0).abs().max()) == 0.0          # nothing written past the D*D channels
 
 
+@pytest.mark.parametrize("B,h,w,md,s2", [(2, 12, 64, 20, 2), (1, 7, 40, 20, 2), (2, 6, 128, 20, 2), (1, 5, 64, 16, 4), (1, 48, 64, 20, 2)])
+def test_tc_correlation_backward_matches_simt(B, h, w, md, s2):
+    from deepof_b200 import ops
+    g = torch.Generator().manual_seed(B * h + w + 1)
+    c = 256
+    f1 = _buf(B, h, w, c, c, g)
+    f2 = _buf(B, h, w, c, c, g)
+    D = 2 * (md // s2) + 1
+    dout = _buf(B, h, w, D * D + 7, D * D, g)
+    outs = []
+    for math_mode in (ops.MATH_FP32, ops.MATH_TF32):
+        d1 = torch.full((B, h, w, c), 3.0, device="cuda")
+        d2 = torch.full((B, h, w, c), 3.0, device="cuda")
+        ops.corr_bwd(ops.Slab(f1, 0, c), ops.Slab(f2, 0, c), ops.Slab(dout, 0, D * D), ops.Slab(d1, 0, c), ops.Slab(d2, 0, c), md, s2, math_mode)
+        outs.append((d1, d2))
+    torch.cuda.synchronize()
+    assert rel(outs[1][0], outs[0][0]) < TOL
+    assert rel(outs[1][1], outs[0][1]) < TOL
+
+
 def test_tf32_engine_tracks_fp32_engine_and_oracle_epe():
     """Whole step in TF32 mode: flows within the stated tolerance of the fp32 device path and EPE within 1e-3 of the CPU oracle."""
     from deepof_b200.flownet import FlowNetS
