@@ -1235,7 +1235,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_corr_bwd_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_constant__ CorrBwdParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + CB_STAGES * CB_STAGE_BYTES);
+    float *g_stage = reinterpret_cast<float *>(smem + CB_STAGES * CB_STAGE_BYTES);          // [128 rows][33]
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(g_stage + 128 * 33 + 1);
+    full_bar = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(full_bar) + 7) & ~uintptr_t(7));
     uint64_t *empty_bar = full_bar + CB_STAGES;
     uint64_t *acc_full = empty_bar + CB_STAGES;
     uint64_t *acc_empty = acc_full + 1;
@@ -1308,6 +1310,8 @@ tc_corr_bwd_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_const
         // ===== band-matrix generator + epilogue (warps 0..3: thread r owns row r of the tile = pixel (ry, xl)) =====
         const int r = warp * 32 + lane;
         const int ry = r >> 6, xl = r & 63;
+        float *my_g = g_stage + r * 33;                                   // thread-private row (pitch 33: conflict-free)
+        const int s2_mask = P.s2 - 1, s2_shift = P.s2 == 1 ? 0 : (P.s2 == 2 ? 1 : 2);
         int it = 0, lu = 0;
         for (int u = blockIdx.x; u < P.units; u += gridDim.x, ++lu) {
             const int xt = u % P.xtiles, yp = (u / P.xtiles) % P.ypairs, b = u / (P.xtiles * P.ypairs);
@@ -1316,32 +1320,38 @@ tc_corr_bwd_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_const
             const bool pix_ok = py < P.h && px < P.w;
             for (int dyi = 0; dyi < P.D; ++dyi) {
                 const int dy = -P.md + dyi * P.s2;
-                // where this row's g values live: its own pixel (df1) or the source row py - dy (df2, column varies with k)
+                // the <= D non-zeros of this row of the band matrix, fetched ONCE per dy into a thread-private shared-memory row:
+                //   df1: g[py, px, (dy, dx_j)]                       (21 contiguous floats of this pixel)
+                //   df2: g[py - dy, px - dx_j, (dy, dx_j)]           (one value from each of 21 source pixels)
                 const int gy = P.transpose ? py - dy : py;
                 const bool grow_ok = pix_ok && gy >= 0 && gy < P.h;
                 const float *grow = P.g + ((long long)b * P.h + (grow_ok ? gy : 0)) * P.w * P.g_ld + dyi * P.D;
+                for (int j = 0; j < P.D; ++j) {
+                    float v = 0.f;
+                    if (grow_ok) {
+                        const int gx = P.transpose ? px - (-P.md + j * P.s2) : px;
+                        if (gx >= 0 && gx < P.w) v = __ldg(grow + (long long)gx * P.g_ld + j);
+                    }
+                    my_g[j] = v;
+                }
                 for (int kb = 0; kb < 8; ++kb, ++it) {
                     const int s = it % CB_STAGES;
                     const uint32_t ph = (it / CB_STAGES) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t *arow = smem + s * CB_STAGE_BYTES + r * 128;
                     const bool active = grow_ok && (kb >> 2) == ry;
+                    // t = displacement index * s2 of column xk for this row; it advances by +-1 per column
                     const int xk0 = (kb & 3) * 32;
+                    const int t0 = P.transpose ? (xl + 32 - xk0 + P.md) : (xk0 - xl - 32 + P.md);
+                    const int tstep = P.transpose ? -1 : 1;
 #pragma unroll
                     for (int cidx = 0; cidx < 8; ++cidx) {
                         float v[4] = {0.f, 0.f, 0.f, 0.f};
                         if (active) {
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                const int xk = xk0 + cidx * 4 + e;
-                                const int t = P.transpose ? (xl + 32 - xk + P.md) : (xk - xl - 32 + P.md);
-                                if (t >= 0 && t <= 2 * P.md && (t % P.s2) == 0) {
-                                    if (!P.transpose) v[e] = __ldg(grow + (long long)px * P.g_ld + t / P.s2);
-                                    else {
-                                        const int gx = x0 - 32 + xk;
-                                        if (gx >= 0 && gx < P.w) v[e] = __ldg(grow + (long long)gx * P.g_ld + t / P.s2);
-                                    }
-                                }
+                                const int t = t0 + tstep * (cidx * 4 + e);
+                                if (t >= 0 && t <= 2 * P.md && (t & s2_mask) == 0) v[e] = my_g[t >> s2_shift];
                             }
                         }
                         *reinterpret_cast<float4 *>(arow + ((cidx ^ (r & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
@@ -1384,7 +1394,8 @@ int tc_corr_bwd(const float *f1, const float *f2, int ld, int B, int h, int w, i
     DOFB_CHECK_ARG(c == 256 && ld % 32 == 0 && dld % 4 == 0 && aligned16(f1) && aligned16(f2) && aligned16(df1) && aligned16(df2),
                    "dofb_corr_bwd(tf32): needs c = 256 channels, pitches multiples of 32, 16-byte aligned pointers");
     DOFB_CHECK_ARG(md >= 0 && md <= 32 && s2 >= 1 && md % s2 == 0, "dofb_corr_bwd(tf32): max displacement must be <= 32 and a multiple of stride2");
-    constexpr int smem = CB_STAGES * CB_STAGE_BYTES + 1024 + 256;
+    DOFB_CHECK_ARG(s2 == 1 || s2 == 2 || s2 == 4, "dofb_corr_bwd(tf32): stride2 must be 1, 2 or 4");
+    constexpr int smem = CB_STAGES * CB_STAGE_BYTES + 128 * 33 * 4 + 1024 + 256;
     static bool configured = false;
     if (!configured) {
         DOFB_CUDA_OK(cudaFuncSetAttribute(tc_corr_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
