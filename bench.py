@@ -365,6 +365,24 @@ def run_ours(args, rank, local_rank, world):
                     "flow_l1_max_px": float((flows[args.math] - flows["fp32"]).abs().max()), "tolerance": 1e-3,
                     "note": "fp32 path == CPU oracle to 5e-7 px (tests/test_gpu_flownet.py)"}
         torch.cuda.empty_cache()
+    # ---- the same step on the fp32 SIMT kernels (bit-auditable path), a few steps, for the record ----
+    fp32_ref = None
+    if world == 1 and args.math != "fp32" and not args.no_accuracy:
+        del step, eng
+        torch.cuda.empty_cache()
+        s32 = TrainStep(B, (H, W), device=dev, math_mode="fp32", model=args.model, variant=args.variant)
+        for i in range(2):
+            s32.engine.train_step(batches[i % 2][2], batches[i % 2][3], WEIGHT_L, lr)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        g0.record()
+        for i in range(3):
+            s32.engine.train_step(batches[i % 2][2], batches[i % 2][3], WEIGHT_L, lr)
+        g1.record()
+        torch.cuda.synchronize()
+        fp32_ref = {"math": "fp32 (SIMT FFMA kernels)", "ms_per_step": g0.elapsed_time(g1) / 3, "value": B * 3 / (g0.elapsed_time(g1) * 1e-3), "unit": UNIT}
+        del s32
+        torch.cuda.empty_cache()
     # ---- CPU baseline on the host cores (N=1 only, bounded sample) ----
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -386,7 +404,7 @@ def run_ours(args, rank, local_rank, world):
                     "api": "deepof_b200.flyingChairsTrain.TrainStep.run(feed_dict) + last_loss(lag=1): pinned-host inputs, "
                            "H2D on a copy stream double-buffered against the previous step, loss D2H read one step late"},
             "gpu_launches": launches, "ddp_replicas_in_sync": ddp_sync,
-            "roofline": roof, "cpu_baseline": cpu, "accuracy": accuracy, "kernel_classes": breakdown,
+            "roofline": roof, "cpu_baseline": cpu, "accuracy": accuracy, "fp32_math_path": fp32_ref, "kernel_classes": breakdown,
             "loss_after": loss_dev, "loss_after_e2e": last}
     print(json.dumps(line), flush=True)
     if world > 1:
