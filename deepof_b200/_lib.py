@@ -47,7 +47,11 @@ SIGNATURES = {
     "dofb_maxpool2_bwd": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _I, _P]),
     "dofb_preprocess": (_I, [_P, _P, C.POINTER(C.c_float), _F, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_void_p),
                              C.POINTER(C.c_void_p), _P]),
-    "dofb_conv1_fwd": (_I, [_G, _P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P]),
+    "dofb_conv1_fwd": (_I, [_G, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P]),
+    "dofb_conv_fwd_bf16": (_I, [_G, _P, _I, _P, _P, _P, _P, _I, _I, _P]),
+    "dofb_conv_dgrad_bf16": (_I, [_G, _P, _I, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "dofb_conv_wgrad_bf16": (_I, [_G, _P, _I, _P, _I, _P, _P]),
+    "dofb_cast_bf16": (_I, [_P, _I, _P, _I, _LL, _I, _P]),
     "dofb_conv1_wgrad": (_I, [_G, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P]),
     "dofb_warp_loss_workspace_bytes": (C.c_size_t, [_I, C.POINTER(LossScale)]),
     "dofb_warp_loss": (_I, [_I, C.POINTER(LossScale), _P, C.c_size_t, _P]),
@@ -55,7 +59,7 @@ SIGNATURES = {
     "dofb_conv_dgrad": (_I, [_G, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P]),
     "dofb_conv_wgrad": (_I, [_G, _P, _I, _P, _I, _P, _P, _I, _P]),
     "dofb_conv_wgrad_tbias": (_I, [_G, _P, _I, _P, _I, _P, _P, _I, _P]),
-    "dofb_elu_bwd": (_I, [_P, _I, _P, _I, _LL, _I, _P, _P]),
+    "dofb_elu_bwd": (_I, [_P, _I, _P, _I, _LL, _I, _P, _P, _P]),
     "dofb_invalidate_weight_cache": (None, []),
     "dofb_enable_weight_cache": (None, [_I]),
     "dofb_head_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),

@@ -12,14 +12,15 @@ int launch_colsum(const float *X, int ld, long long n_pix, int c, float *out, cu
 // tcgen05 path (conv_tc.cu); returns -1 when the shape is not covered so that the caller can
 // decide (the C ABI reports an error: there is no silent fallback between math modes).
 int tc_conv_fwd(const dofb_conv_geom *g, const float *x, int x_ld, const float *w, const float *bias, float *y, int y_ld,
-                int act, cudaStream_t st);
+                int act, cudaStream_t st, const void *x16 = nullptr, void *y16 = nullptr);
 int tc_conv_dgrad(const dofb_conv_geom *g, const float *dy, int dy_ld, const float *w, const float *bias, float *dx, int dx_ld,
-                  int act, int accumulate, cudaStream_t st);
-int tc_conv_wgrad(const dofb_conv_geom *g, const float *x, int x_ld, const float *dy, int dy_ld, float *dw, cudaStream_t st);
+                  int act, int accumulate, cudaStream_t st, const void *dy16 = nullptr, void *dx16 = nullptr);
+int tc_conv_wgrad(const dofb_conv_geom *g, const float *x, int x_ld, const float *dy, int dy_ld, float *dw, cudaStream_t st,
+                  const void *x16 = nullptr, const void *dy16 = nullptr);
 void invalidate_weight_cache();
 void enable_weight_cache(int on);
 int tc_conv1_fwd(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *w, const float *bias,
-                 float *y, int y_ld, int act, cudaStream_t st);
+                 float *y, int y_ld, int act, cudaStream_t st, void *y16 = nullptr);
 int tc_conv1_wgrad(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *dy, int dy_ld,
                    float *dw, cudaStream_t st);
 }  // namespace dofb
@@ -66,8 +67,27 @@ extern "C" int dofb_conv_wgrad_tbias(const dofb_conv_geom *g, const float *x, in
 }
 
 extern "C" int dofb_conv1_fwd(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *w,
-                              const float *bias, float *y, int y_ld, int act, void *stream) {
-    return tc_conv1_fwd(g, x, xp_h, xp_w, xp_y0, xp_x0, w, bias, y, y_ld, act, as_stream(stream));
+                              const float *bias, float *y, void *y_bf16, int y_ld, int act, void *stream) {
+    return tc_conv1_fwd(g, x, xp_h, xp_w, xp_y0, xp_x0, w, bias, y, y_ld, act, as_stream(stream), y_bf16);
+}
+
+// ---- BF16 tensor-core math: operands are bf16 shadows of the NHWC activations (same pitch in elements, multiple of 64) ----
+extern "C" int dofb_conv_fwd_bf16(const dofb_conv_geom *g, const void *x_bf16, int x_ld, const float *w, const float *bias, float *y,
+                                  void *y_bf16, int y_ld, int act, void *stream) {
+    DOFB_CHECK_ARG(x_bf16 && w && y, "dofb_conv_fwd_bf16: null tensor");
+    return tc_conv_fwd(g, nullptr, x_ld, w, bias, y, y_ld, act, as_stream(stream), x_bf16, y_bf16);
+}
+
+extern "C" int dofb_conv_dgrad_bf16(const dofb_conv_geom *g, const void *dy_bf16, int dy_ld, const float *w, const float *bias, float *dx,
+                                    void *dx_bf16, int dx_ld, int act, int accumulate, void *stream) {
+    DOFB_CHECK_ARG(dy_bf16 && w && dx, "dofb_conv_dgrad_bf16: null tensor");
+    return tc_conv_dgrad(g, nullptr, dy_ld, w, bias, dx, dx_ld, act, accumulate, as_stream(stream), dy_bf16, dx_bf16);
+}
+
+extern "C" int dofb_conv_wgrad_bf16(const dofb_conv_geom *g, const void *x_bf16, int x_ld, const void *dy_bf16, int dy_ld, float *dw,
+                                    void *stream) {
+    DOFB_CHECK_ARG(x_bf16 && dy_bf16 && dw && g, "dofb_conv_wgrad_bf16: null argument");
+    return tc_conv_wgrad(g, nullptr, x_ld, nullptr, dy_ld, dw, as_stream(stream), x_bf16, dy_bf16);
 }
 
 extern "C" int dofb_conv1_wgrad(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *dy,

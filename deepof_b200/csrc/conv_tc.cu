@@ -17,6 +17,7 @@
 // warp 5 TMEM allocator + single-thread MMA issuer.  mbarrier ring of STAGES smem slots.
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <unordered_map>
 #include <mutex>
 #include <vector>
@@ -94,6 +95,22 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same with bf16 operands (kind::f16), fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+template <bool BF>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if (BF) umma_bf16(d_tmem, a_desc, b_desc, idesc, accumulate);
+    else umma_tf32(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
 // mbarrier arrives when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -145,6 +162,10 @@ __device__ __forceinline__ uint64_t make_desc_k128(uint32_t saddr) {
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// bf16 operands (F16F32Format::BF16 = 1), fp32 accumulate
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
 
 // ------------------------------------------------------------------------------------------------
 // gather-GEMM kernel
@@ -160,6 +181,7 @@ struct TapInfo {
 
 struct TcParams {
     float *out; int out_ld;
+    __nv_bfloat16 *out16;        // optional bf16 shadow of the output (same pitch in elements), written when not accumulating
     const float *bias;
     int n_valid;                 // output channels
     int rh, rw;                  // output map
@@ -182,10 +204,14 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 
 // Persistent: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, += gridDim.x (M fastest, so CTAs running
 // at the same time share the weight tile in L2).  Two TMEM accumulators: the epilogue of tile i overlaps the MMAs of tile i+1.
-template <int BN, int STAGES>
+// BF = false: fp32 activations/weights fed as TF32 (32 channels per 128-byte K block, UMMA_K = 8);
+// BF = true : bf16 shadows of the activations + bf16 packed weights (64 channels per K block, UMMA_K = 16): same bytes per stage,
+//             twice the MMA rate and twice the K per byte fetched from L2.  Accumulation and the epilogue stay fp32.
+template <int BN, int STAGES, bool BF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ TcParams P) {
+    constexpr int KELEMS = BF ? 64 : 32;             // channels per K block (128 bytes)
     constexpr int B_BYTES = BN * TC_BK * 4;
     constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
     constexpr int ACC_COLS = BN < 32 ? 32 : BN;
@@ -232,17 +258,17 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     uint8_t *sb = sa + TC_A_BYTES;
                     mbar_expect_tx(&full_bar[s], STAGE_BYTES);
                     if (P.parity)
-                        tma_load_5d(sa, &map_a, &full_bar[s], ti.px * P.a_ld + P.a_coff + cb * TC_BK, ix0 + ti.ox, ti.py, iy0 + ti.oy, in0);
+                        tma_load_5d(sa, &map_a, &full_bar[s], ti.px * P.a_ld + P.a_coff + cb * KELEMS, ix0 + ti.ox, ti.py, iy0 + ti.oy, in0);
                     else
-                        tma_load_4d(sa, &map_a, &full_bar[s], P.a_coff + cb * TC_BK, ix0 + ti.ox, iy0 + ti.oy, in0);
-                    tma_load_2d(sb, &map_b, &full_bar[s], ti.wk + cb * TC_BK, n0);
+                        tma_load_4d(sa, &map_a, &full_bar[s], P.a_coff + cb * KELEMS, ix0 + ti.ox, iy0 + ti.oy, in0);
+                    tma_load_2d(sb, &map_b, &full_bar[s], ti.wk + cb * KELEMS, n0);
                 }
             }
         }
     } else if (warp == 5) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(TC_BM, BN);
+            constexpr uint32_t idesc = BF ? make_idesc_bf16(TC_BM, BN) : make_idesc_tf32(TC_BM, BN);
             int it = 0, lt = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
                 const int acc = lt & 1;
@@ -257,8 +283,8 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
                     const uint64_t da = make_desc_k128(sa), db = make_desc_k128(sa + TC_A_BYTES);
 #pragma unroll
-                    for (int kk = 0; kk < TC_BK / 8; ++kk)  // UMMA_K = 8 for tf32: advance 32 B inside the 128 B swizzle row
-                        umma_tf32(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (k | kk) != 0);
+                    for (int kk = 0; kk < TC_BK / 8; ++kk)  // UMMA_K = 8 (tf32) / 16 (bf16) = 32 bytes: advance inside the 128 B swizzle row
+                        umma<BF>(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (k | kk) != 0);
                     umma_commit(&empty_bar[s]);             // frees the smem slot when these MMAs retire
                 }
                 umma_commit(&acc_full[acc]);                // accumulator complete
@@ -304,10 +330,21 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                             o[0] += old.x; o[1] += old.y; o[2] += old.z; o[3] += old.w;
                         }
                         *dst = make_float4(o[0], o[1], o[2], o[3]);
+                        if (P.out16 != nullptr) {            // bf16 shadow for the next tensor-core consumer (same pitch, 8-byte store)
+                            __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
+                            uint2 pk;
+                            pk.x = *reinterpret_cast<uint32_t *>(&lo);
+                            pk.y = *reinterpret_cast<uint32_t *>(&hi);
+                            *reinterpret_cast<uint2 *>(P.out16 + (orow - P.out) + col) = pk;
+                        }
                     } else {
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
-                            if (col + e < P.n_valid) orow[col + e] = P.accumulate ? orow[col + e] + o[e] : o[e];
+                            if (col + e < P.n_valid) {
+                                const float val = P.accumulate ? orow[col + e] + o[e] : o[e];
+                                orow[col + e] = val;
+                                if (P.out16 != nullptr) P.out16[(orow - P.out) + col + e] = __float2bfloat16_rn(val);
+                            }
                     }
                 }
             }
@@ -329,7 +366,12 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 //   fwd  (contract over ci): Wp[co][tap*Cpad + ci] = W[tap][ci][co]
 //   bwd  (contract over co): Wp[ci][tap*Cpad + co] = W[tap][ci][co]
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restrict__ W, float *__restrict__ Wp, int taps, int ci, int co,
+template <typename T> __device__ __forceinline__ T cvt_out(float v);
+template <> __device__ __forceinline__ float cvt_out<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restrict__ W, T *__restrict__ Wp, int taps, int ci, int co,
                                                            int cpad, int contract_ci) {
     // bwd orientation (contract over co): rows are already co-contiguous -> straight padded copy
     const int n_rows = ci;
@@ -338,13 +380,14 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restri
         const int c = (int)(i % cpad);
         const int t = (int)((i / cpad) % taps);
         const int n = (int)(i / ((long long)cpad * taps));
-        Wp[i] = c < co ? __ldg(W + ((long long)t * ci + n) * co + c) : 0.f;
+        Wp[i] = cvt_out<T>(c < co ? __ldg(W + ((long long)t * ci + n) * co + c) : 0.f);
     }
 }
 
 // fwd orientation (contract over ci): per tap a [ci][co] -> [co][cpad] transpose through a 32x33 shared tile so that both the
 // global reads (co contiguous) and the global writes (ci contiguous) are coalesced
-__global__ void __launch_bounds__(256) pack_weights_t_kernel(const float *__restrict__ W, float *__restrict__ Wp, int taps, int ci, int co,
+template <typename T>
+__global__ void __launch_bounds__(256) pack_weights_t_kernel(const float *__restrict__ W, T *__restrict__ Wp, int taps, int ci, int co,
                                                              int cpad) {
     __shared__ float tile[32][33];
     const int t = blockIdx.z;
@@ -359,7 +402,7 @@ __global__ void __launch_bounds__(256) pack_weights_t_kernel(const float *__rest
 #pragma unroll
     for (int r = ty; r < 32; r += 8) {
         const int n = n0 + r, c = c0 + tx;
-        if (n < co && c < cpad) Wp[((long long)n * taps + t) * cpad + c] = tile[tx][r];
+        if (n < co && c < cpad) Wp[((long long)n * taps + t) * cpad + c] = cvt_out<T>(tile[tx][r]);
     }
 }
 
@@ -382,14 +425,14 @@ static PFN_encodeTiled get_encode() {
 }
 
 static int make_map(CUtensorMap *m, const void *base, int rank, const uint64_t *dims, const uint64_t *strides_bytes, const uint32_t *box,
-                    CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+                    CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32) {
     PFN_encodeTiled enc = get_encode();
     DOFB_CHECK_ARG(enc != nullptr, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t gd[5], gs[4];
     cuuint32_t bx[5], es[5];
     for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(base), gd, gs, bx, es,
+    CUresult r = enc(m, dt, (cuuint32_t)rank, const_cast<void *>(base), gd, gs, bx, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     DOFB_CHECK_ARG(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d (rank %d, dims %llu %llu %llu ..., box %u %u %u ...)", (int)r,
@@ -453,19 +496,19 @@ static void choose_tile(int cnt_y, int cnt_x, int &TW, int &TH, int &TN) {
     TN = TC_BM / (TW * TH);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool BF = false>
 static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &Pin, int tiles, int n_tiles, cudaStream_t st) {
     constexpr int smem = STAGES * (TC_A_BYTES + BN * TC_BK * 4) + 1024 + 256;
     static bool configured = false;
     if (!configured) {
-        DOFB_CUDA_OK(cudaFuncSetAttribute(tc_gather_gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        DOFB_CUDA_OK(cudaFuncSetAttribute(tc_gather_gemm_kernel<BN, STAGES, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
     TcParams P = Pin;
     P.m_tiles = tiles; P.n_tiles = n_tiles;
     const long long total = (long long)tiles * n_tiles;
     const int grid = (int)(total < num_sms() ? total : num_sms());
-    tc_gather_gemm_kernel<BN, STAGES><<<grid, TC_THREADS, smem, st>>>(ma, mb, P);
+    tc_gather_gemm_kernel<BN, STAGES, BF><<<grid, TC_THREADS, smem, st>>>(ma, mb, P);
     DOFB_LAUNCH_OK();
     return 0;
 }
@@ -473,43 +516,52 @@ static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcParam
 // One (phase of a) gather-GEMM.  src: the gathered activation buffer description.
 struct GatherSpec {
     const float *a_base; int a_ld, a_coff, a_c;     // buffer base (16 B aligned), pitch, slab offset, slab channels
+    const void *a16;                                // bf16 shadow of the same slab (same pitch in elements) -> bf16 math when non-null
     int ah, aw;                                     // source map
     const float *w; int w_ci, w_co, taps_h, taps_w; // canonical weights
     int contract_ci;                                // 1: fwd-type (contract over ci), 0: bwd-type (contract over co)
     float *out; int out_ld, rh, rw, n_valid;
+    void *out16;                                    // optional bf16 shadow of the output
     const float *bias; int act, accumulate;
     int B;
 };
 
 static int run_gather(const GatherSpec &G, const TcParams &Pin, cudaStream_t st) {
     TcParams P = Pin;
+    const bool bf = G.a16 != nullptr;
+    const int kel = bf ? 64 : 32;                   // channels per 128-byte K block
+    const int esz = bf ? 2 : 4;
     const int kc = G.contract_ci ? G.w_ci : G.w_co;
-    const int cpad = (kc + TC_BK - 1) / TC_BK * TC_BK;
+    const int cpad = (kc + kel - 1) / kel * kel;
     const int taps_all = G.taps_h * G.taps_w;
     const int n_rows = G.contract_ci ? G.w_co : G.w_ci;
-    DOFB_CHECK_ARG(G.a_coff % 4 == 0 && G.a_ld % 4 == 0 && aligned16(G.a_base), "tc conv: activation slab must be 16-byte aligned");
-    DOFB_CHECK_ARG(cpad <= G.a_ld, "tc conv: %d channels rounded up to 32 exceed the pitch %d", kc, G.a_ld);
-    // ---- pack weights ----
+    const void *abase = bf ? G.a16 : (const void *)G.a_base;
+    DOFB_CHECK_ARG(G.a_coff % 8 == 0 && G.a_ld % 8 == 0 && aligned16(abase), "tc conv: activation slab must be 16-byte aligned");
+    DOFB_CHECK_ARG(cpad <= G.a_ld, "tc conv: %d channels rounded up to %d exceed the pitch %d", kc, kel, G.a_ld);
+    // ---- pack weights (fp32 for TF32 math, bf16 for BF16 math) ----
     float *wp = nullptr;
-    const size_t wfloats = (size_t)n_rows * taps_all * cpad;
+    const size_t welems = (size_t)n_rows * taps_all * cpad;
     bool fresh = false;
-    if (get_pack_buffer(G.w, G.contract_ci, wfloats, &wp, &fresh)) return 1;
+    if (get_pack_buffer(G.w, G.contract_ci + (bf ? 8 : 0), bf ? (welems + 1) / 2 : welems, &wp, &fresh)) return 1;
     if (!fresh) {       // once per weight epoch and orientation (all stride phases of a dgrad share one packing)
         if (G.contract_ci) {
             dim3 grid((G.w_co + 31) / 32, cpad / 32, taps_all);
-            pack_weights_t_kernel<<<grid, 256, 0, st>>>(G.w, wp, taps_all, G.w_ci, G.w_co, cpad);
+            if (bf) pack_weights_t_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(G.w, reinterpret_cast<__nv_bfloat16 *>(wp), taps_all, G.w_ci, G.w_co, cpad);
+            else pack_weights_t_kernel<float><<<grid, 256, 0, st>>>(G.w, wp, taps_all, G.w_ci, G.w_co, cpad);
         } else {
-            long long blocks = ((long long)wfloats + 255) / 256;
+            long long blocks = ((long long)welems + 255) / 256;
             const long long cap = (long long)num_sms() * 8;
             if (blocks > cap) blocks = cap;
-            pack_weights_kernel<<<(unsigned)blocks, 256, 0, st>>>(G.w, wp, taps_all, G.w_ci, G.w_co, cpad, 0);
+            if (bf) pack_weights_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>(G.w, reinterpret_cast<__nv_bfloat16 *>(wp), taps_all, G.w_ci, G.w_co, cpad, 0);
+            else pack_weights_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(G.w, wp, taps_all, G.w_ci, G.w_co, cpad, 0);
         }
         DOFB_LAUNCH_OK();
     }
     for (int t = 0; t < P.ntaps; ++t) P.taps[t].wk *= cpad;     // caller stored the canonical tap index
-    P.ncb = cpad / TC_BK;
+    P.ncb = cpad / kel;
     P.a_coff = G.a_coff; P.a_ld = G.a_ld;
-    P.out = G.out; P.out_ld = G.out_ld; P.bias = G.bias; P.n_valid = G.n_valid; P.rh = G.rh; P.rw = G.rw;
+    P.out = G.out; P.out_ld = G.out_ld; P.out16 = G.accumulate ? nullptr : reinterpret_cast<__nv_bfloat16 *>(G.out16);
+    P.bias = G.bias; P.n_valid = G.n_valid; P.rh = G.rh; P.rw = G.rw;
     P.act = G.act; P.accumulate = G.accumulate; P.B = G.B;
     choose_tile(P.cnt_y, P.cnt_x, P.TW, P.TH, P.TN);
     P.tiles_x = (P.cnt_x + P.TW - 1) / P.TW;
@@ -517,29 +569,38 @@ static int run_gather(const GatherSpec &G, const TcParams &Pin, cudaStream_t st)
     const int tiles_n = (G.B + P.TN - 1) / P.TN;
     const int tiles = P.tiles_x * P.tiles_y * tiles_n;
     // ---- tensor maps ----
+    const CUtensorMapDataType dt = bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     CUtensorMap ma, mb;
     if (!P.parity) {
         const uint64_t dims[4] = {(uint64_t)cpad, (uint64_t)G.aw, (uint64_t)G.ah, (uint64_t)G.B};
-        const uint64_t str[3] = {(uint64_t)G.a_ld * 4, (uint64_t)G.aw * G.a_ld * 4, (uint64_t)G.ah * G.aw * G.a_ld * 4};
-        const uint32_t box[4] = {(uint32_t)TC_BK, (uint32_t)P.TW, (uint32_t)P.TH, (uint32_t)P.TN};
-        if (make_map(&ma, G.a_base, 4, dims, str, box)) return 1;
+        const uint64_t str[3] = {(uint64_t)G.a_ld * esz, (uint64_t)G.aw * G.a_ld * esz, (uint64_t)G.ah * G.aw * G.a_ld * esz};
+        const uint32_t box[4] = {(uint32_t)kel, (uint32_t)P.TW, (uint32_t)P.TH, (uint32_t)P.TN};
+        if (make_map(&ma, abase, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, dt)) return 1;
     } else {
         DOFB_CHECK_ARG(G.ah % 2 == 0 && G.aw % 2 == 0, "tc conv: stride-2 gather needs even map sizes (%d x %d)", G.ah, G.aw);
         const uint64_t dims[5] = {(uint64_t)2 * G.a_ld, (uint64_t)G.aw / 2, 2, (uint64_t)G.ah / 2, (uint64_t)G.B};
-        const uint64_t str[4] = {(uint64_t)2 * G.a_ld * 4, (uint64_t)G.aw * G.a_ld * 4, (uint64_t)2 * G.aw * G.a_ld * 4,
-                                 (uint64_t)G.ah * G.aw * G.a_ld * 4};
-        const uint32_t box[5] = {(uint32_t)TC_BK, (uint32_t)P.TW, 1, (uint32_t)P.TH, (uint32_t)P.TN};
-        if (make_map(&ma, G.a_base, 5, dims, str, box)) return 1;
+        const uint64_t str[4] = {(uint64_t)2 * G.a_ld * esz, (uint64_t)G.aw * G.a_ld * esz, (uint64_t)2 * G.aw * G.a_ld * esz,
+                                 (uint64_t)G.ah * G.aw * G.a_ld * esz};
+        const uint32_t box[5] = {(uint32_t)kel, (uint32_t)P.TW, 1, (uint32_t)P.TH, (uint32_t)P.TN};
+        if (make_map(&ma, abase, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, dt)) return 1;
     }
     int bn = n_rows > 128 ? 256 : (n_rows > 64 ? 128 : (n_rows > 32 ? 64 : 32));
     while (bn > 64 && (long long)tiles * ((n_rows + bn - 1) / bn) < num_sms()) bn >>= 1;   // small maps: more, narrower tiles
     {
         const uint64_t dims[2] = {(uint64_t)taps_all * cpad, (uint64_t)n_rows};
-        const uint64_t str[1] = {(uint64_t)taps_all * cpad * 4};
-        const uint32_t box[2] = {(uint32_t)TC_BK, (uint32_t)bn};
-        if (make_map(&mb, wp, 2, dims, str, box)) return 1;
+        const uint64_t str[1] = {(uint64_t)taps_all * cpad * esz};
+        const uint32_t box[2] = {(uint32_t)kel, (uint32_t)bn};
+        if (make_map(&mb, wp, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, dt)) return 1;
     }
     const int n_tiles = (n_rows + bn - 1) / bn;
+    if (bf) {
+        switch (bn) {
+            case 256: return launch_tc<256, 4, true>(ma, mb, P, tiles, n_tiles, st);
+            case 128: return launch_tc<128, 6, true>(ma, mb, P, tiles, n_tiles, st);
+            case 64: return launch_tc<64, 8, true>(ma, mb, P, tiles, n_tiles, st);
+            default: return launch_tc<32, 8, true>(ma, mb, P, tiles, n_tiles, st);
+        }
+    }
     switch (bn) {
         case 256: return launch_tc<256, 4>(ma, mb, P, tiles, n_tiles, st);
         case 128: return launch_tc<128, 6>(ma, mb, P, tiles, n_tiles, st);
@@ -550,14 +611,14 @@ static int run_gather(const GatherSpec &G, const TcParams &Pin, cudaStream_t st)
 
 // ---- conv forward (and transposed-conv input gradient): fwd-type gather ----
 int tc_conv_fwd(const dofb_conv_geom *g, const float *x, int x_ld, const float *w, const float *bias, float *y, int y_ld, int act,
-                cudaStream_t st) {
+                cudaStream_t st, const void *x16, void *y16) {
     DOFB_CHECK_ARG(g && g->kh * g->kw <= TC_MAX_TAPS, "dofb_conv_fwd(tf32): at most %d taps", TC_MAX_TAPS);
     DOFB_CHECK_ARG(g->stride == 1 || g->stride == 2, "dofb_conv_fwd(tf32): stride must be 1 or 2");
     // TMA base = the slab pointer itself (16-byte aligned); the 32-channel blocks read round_up(ci,32) channels from it, so
     // the caller guarantees that those stay inside the pitch row and hold finite values (the engine's pad channels are zero).
-    DOFB_CHECK_ARG(x_ld % 32 == 0 && aligned16(x), "dofb_conv_fwd(tf32): pitch %d must be a multiple of 32 floats and x 16-byte aligned", x_ld);
+    DOFB_CHECK_ARG(x_ld % (x16 ? 64 : 32) == 0 && aligned16(x), "dofb_conv_fwd(tensor): pitch %d must be a multiple of %d and x 16-byte aligned", x_ld, x16 ? 64 : 32);
     GatherSpec G;
-    G.a_base = x; G.a_ld = x_ld; G.a_coff = 0; G.a_c = g->ci;
+    G.a_base = x; G.a_ld = x_ld; G.a_coff = 0; G.a_c = g->ci; G.a16 = x16; G.out16 = y16;
     G.ah = g->ih; G.aw = g->iw;
     G.w = w; G.w_ci = g->ci; G.w_co = g->co; G.taps_h = g->kh; G.taps_w = g->kw; G.contract_ci = 1;
     G.out = y; G.out_ld = y_ld; G.rh = g->oh; G.rw = g->ow; G.n_valid = g->co; G.bias = bias; G.act = act; G.accumulate = 0; G.B = g->B;
@@ -582,12 +643,12 @@ int tc_conv_fwd(const dofb_conv_geom *g, const float *x, int x_ld, const float *
 
 // ---- conv input gradient (and transposed-conv forward): bwd-type gather, one launch per stride phase ----
 int tc_conv_dgrad(const dofb_conv_geom *g, const float *dy, int dy_ld, const float *w, const float *bias, float *dx, int dx_ld, int act,
-                  int accumulate, cudaStream_t st) {
+                  int accumulate, cudaStream_t st, const void *dy16, void *dx16) {
     DOFB_CHECK_ARG(g && g->kh * g->kw <= TC_MAX_TAPS, "dofb_conv_dgrad(tf32): at most %d taps", TC_MAX_TAPS);
     DOFB_CHECK_ARG(g->stride == 1 || g->stride == 2, "dofb_conv_dgrad(tf32): stride must be 1 or 2");
-    DOFB_CHECK_ARG(dy_ld % 32 == 0 && aligned16(dy), "dofb_conv_dgrad(tf32): pitch %d must be a multiple of 32 floats and dy 16-byte aligned", dy_ld);
+    DOFB_CHECK_ARG(dy_ld % (dy16 ? 64 : 32) == 0 && aligned16(dy), "dofb_conv_dgrad(tensor): pitch %d must be a multiple of %d and dy 16-byte aligned", dy_ld, dy16 ? 64 : 32);
     GatherSpec G;
-    G.a_base = dy; G.a_ld = dy_ld; G.a_coff = 0; G.a_c = g->co;
+    G.a_base = dy; G.a_ld = dy_ld; G.a_coff = 0; G.a_c = g->co; G.a16 = dy16; G.out16 = dx16;
     G.ah = g->oh; G.aw = g->ow;
     G.w = w; G.w_ci = g->ci; G.w_co = g->co; G.taps_h = g->kh; G.taps_w = g->kw; G.contract_ci = 0;
     G.out = dx; G.out_ld = dx_ld; G.rh = g->ih; G.rw = g->iw; G.n_valid = g->ci; G.bias = bias; G.act = act; G.accumulate = accumulate;
@@ -671,15 +732,33 @@ __device__ __forceinline__ uint64_t make_desc_mn128(uint32_t saddr) {
     d |= (uint64_t)1 << 61;                   // SWIZZLE_128B_BASE32B: the only MN-major layout tcgen05 accepts for 32-bit operands
     return d;
 }
+// MN-major descriptor: fp32 operands need the 32-byte-atom swizzle (layout 1, 4-row groups of 512 B); 16-bit operands use the
+// plain 128-byte swizzle (layout 2, 8-row groups of 1 KB).  region_bytes = distance between channel blocks (LBO).
+template <bool BF>
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t region_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(region_bytes >> 4) << 16;
+    d |= (uint64_t)((BF ? 1024 : 512) >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(BF ? 2 : 1) << 61;
+    return d;
+}
 __host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) {
     return make_idesc_tf32(M, N) | (1u << 15) | (1u << 16);     // A and B MN-major
 }
 
-template <int BN, int STAGES>
+// BF = false: fp32 operands as TF32 (32-channel x 32-pixel regions, 32-byte-atom swizzle); BF = true: bf16 shadows (64-channel x
+// 64-pixel regions, plain 128-byte swizzle, UMMA_K = 16).  Same bytes per stage, twice the pixels (K) per stage.
+template <int BN, int STAGES, bool BF>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy,
                 const __grid_constant__ WgParams P) {
-    constexpr int A_BYTES = 4 * WG_REGION, B_BYTES = (BN / 32) * WG_REGION;
+    constexpr int CH = BF ? 64 : 32;                    // channels per region (128 bytes)
+    constexpr int REGION = (BF ? 64 : 32) * 128;        // bytes: pixels per stage x 128
+    constexpr int A_REGS = TC_BM / CH, B_REGS = BN / CH;
+    constexpr int A_BYTES = A_REGS * REGION, B_BYTES = B_REGS * REGION;
+    constexpr int KADV = BF ? 128 : 64;                 // descriptor units (16 B) per MMA along K: 16 or 8 pixel rows of 128 B
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -715,7 +794,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         // ===== TMA producer: lane 0 owns the barrier hand-shake, lanes 0..(4+BN/32) issue one 4 KB box each =====
         // channel origin of the X / DY operand and how many 32-channel blocks each needs
         const int x_c0 = P.swap ? n0 : m0, dy_c0 = P.swap ? m0 : n0;
-        const int x_blocks = P.swap ? BN / 32 : 4, dy_blocks = P.swap ? 4 : BN / 32;
+        const int x_blocks = P.swap ? B_REGS : A_REGS, dy_blocks = P.swap ? A_REGS : B_REGS;
         for (int it = 0; it < kiters; ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
@@ -732,43 +811,43 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             uint8_t *sx = P.swap ? sb : sa, *sd = P.swap ? sa : sb;
             if (lane < x_blocks) {
                 const int j = lane;
-                if (P.conv1) {
+                if (!BF && P.conv1) {
                     // region j = filter row 2*tapi + (j>>1), floats [(j&1)*32, +32) of its 8-pixel chunk
                     const int kh = min(2 * tapi + (j >> 1), P.c1_kh - 1);      // (an odd kh count re-loads the last row; masked later)
                     const TapInfo tr = P.taps[kh];
-                    tma_load_5d(sx + j * WG_REGION, &map_x, &full_bar[s], (j & 1) * 32, ix0, tr.py, iy0 + tr.oy, in0);
+                    tma_load_5d(sx + j * REGION, &map_x, &full_bar[s], (j & 1) * 32, ix0, tr.py, iy0 + tr.oy, in0);
                 } else {
                     TapInfo tr = ti;
-                    int c0 = x_c0 + j * 32;
+                    int c0 = x_c0 + j * CH;
                     if (P.pack_g > 1) {     // region j = tap (tapi*G + j/per), channel block j%per
-                        const int per = P.pack_cb >> 5;
+                        const int per = P.pack_cb / CH;
                         tr = P.taps[min(tapi * P.pack_g + j / per, P.ntaps_real - 1)];
-                        c0 = (j % per) * 32;
+                        c0 = (j % per) * CH;
                     }
                     if (P.parity)
-                        tma_load_5d(sx + j * WG_REGION, &map_x, &full_bar[s], tr.px * P.x_ld + c0, ix0 + tr.ox, tr.py, iy0 + tr.oy, in0);
+                        tma_load_5d(sx + j * REGION, &map_x, &full_bar[s], tr.px * P.x_ld + c0, ix0 + tr.ox, tr.py, iy0 + tr.oy, in0);
                     else
-                        tma_load_4d(sx + j * WG_REGION, &map_x, &full_bar[s], c0, ix0 + tr.ox, iy0 + tr.oy, in0);
+                        tma_load_4d(sx + j * REGION, &map_x, &full_bar[s], c0, ix0 + tr.ox, iy0 + tr.oy, in0);
                 }
             } else if (lane < x_blocks + dy_blocks) {
                 const int j = lane - x_blocks;
-                tma_load_4d(sd + j * WG_REGION, &map_dy, &full_bar[s], dy_c0 + j * 32, ix0, iy0, in0);
+                tma_load_4d(sd + j * REGION, &map_dy, &full_bar[s], dy_c0 + j * CH, ix0, iy0, in0);
             }
             __syncwarp();
         }
     } else if (warp == 5) {
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32_mn(TC_BM, BN);
+            constexpr uint32_t idesc = (BF ? make_idesc_bf16(TC_BM, BN) : make_idesc_tf32(TC_BM, BN)) | (1u << 15) | (1u << 16);   // A, B MN-major
             for (int it = 0; it < kiters; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
                 const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-                const uint64_t da = make_desc_mn128(sa), db = make_desc_mn128(sa + A_BYTES);
+                const uint64_t da = make_desc_mn<BF>(sa, REGION), db = make_desc_mn<BF>(sa + A_BYTES, REGION);
 #pragma unroll
-                for (int k = 0; k < WG_BKP / 8; ++k)    // 8 pixels per MMA = one 1 KB swizzle group
-                    umma_tf32(tmem_base, da + (uint64_t)(k * 64), db + (uint64_t)(k * 64), idesc, (it | k) != 0);
+                for (int k = 0; k < 4; ++k)             // 8 (tf32) / 16 (bf16) pixels per MMA
+                    umma<BF>(tmem_base, da + (uint64_t)(k * KADV), db + (uint64_t)(k * KADV), idesc, (it | k) != 0);
                 umma_commit(&empty_bar[s]);
             }
             umma_commit(accum_bar);
@@ -783,7 +862,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         for (int j = 0; j < BN / 32; ++j) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * 32), v);
-            if (P.conv1) {
+            if (!BF && P.conv1) {
                 const int kh = 2 * tapi + (r >> 6), kw = (r & 63) >> 3, ci = r & 7;
                 if (kh >= P.c1_kh || kw >= P.c1_kw || ci >= P.CI) continue;
                 float *dst = P.dW + (((long long)kh * P.c1_kw + kw) * P.CI + ci) * P.CO + n0 + j * 32;
@@ -819,31 +898,34 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool BF = false>
 static int launch_wg(const CUtensorMap &mx, const CUtensorMap &md, const WgParams &P, int splits, int items, cudaStream_t st) {
-    constexpr int smem = STAGES * (4 + BN / 32) * WG_REGION + 1024 + 256;
+    constexpr int smem = STAGES * (4 + BN / 32) * WG_REGION + 1024 + 256;      // identical for both operand types
     static bool configured = false;
     if (!configured) {
-        DOFB_CUDA_OK(cudaFuncSetAttribute(tc_wgrad_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        DOFB_CUDA_OK(cudaFuncSetAttribute(tc_wgrad_kernel<BN, STAGES, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    tc_wgrad_kernel<BN, STAGES><<<dim3(splits, items, 1), TC_THREADS, smem, st>>>(mx, md, P);
+    tc_wgrad_kernel<BN, STAGES, BF><<<dim3(splits, items, 1), TC_THREADS, smem, st>>>(mx, md, P);
     DOFB_LAUNCH_OK();
     return 0;
 }
 
-int tc_conv_wgrad(const dofb_conv_geom *g, const float *x, int x_ld, const float *dy, int dy_ld, float *dw, cudaStream_t st) {
-    DOFB_CHECK_ARG(g && g->kh * g->kw <= TC_MAX_TAPS, "dofb_conv_wgrad(tf32): at most %d taps", TC_MAX_TAPS);
-    DOFB_CHECK_ARG(g->stride == 1 || g->stride == 2, "dofb_conv_wgrad(tf32): stride must be 1 or 2");
-    DOFB_CHECK_ARG(x_ld % 32 == 0 && dy_ld % 32 == 0 && aligned16(x) && aligned16(dy),
-                   "dofb_conv_wgrad(tf32): pitches (%d, %d) must be multiples of 32 floats, pointers 16-byte aligned", x_ld, dy_ld);
-    const int ci_pad = (g->ci + 31) / 32 * 32, co_pad = (g->co + 31) / 32 * 32;
-    DOFB_CHECK_ARG(ci_pad <= x_ld && co_pad <= dy_ld, "dofb_conv_wgrad(tf32): channels rounded up to 32 exceed the pitch");
+int tc_conv_wgrad(const dofb_conv_geom *g, const float *x, int x_ld, const float *dy, int dy_ld, float *dw, cudaStream_t st,
+                  const void *x16, const void *dy16) {
+    DOFB_CHECK_ARG(g && g->kh * g->kw <= TC_MAX_TAPS, "dofb_conv_wgrad(tensor): at most %d taps", TC_MAX_TAPS);
+    DOFB_CHECK_ARG(g->stride == 1 || g->stride == 2, "dofb_conv_wgrad(tensor): stride must be 1 or 2");
+    const bool bf = x16 != nullptr && dy16 != nullptr;
+    const int CH = bf ? 64 : 32, BKP = bf ? 64 : 32, esz = bf ? 2 : 4;
+    DOFB_CHECK_ARG(x_ld % CH == 0 && dy_ld % CH == 0 && aligned16(x) && aligned16(dy),
+                   "dofb_conv_wgrad(tensor): pitches (%d, %d) must be multiples of %d, pointers 16-byte aligned", x_ld, dy_ld, CH);
+    const int ci_pad = (g->ci + CH - 1) / CH * CH, co_pad = (g->co + CH - 1) / CH * CH;
+    DOFB_CHECK_ARG(ci_pad <= x_ld && co_pad <= dy_ld, "dofb_conv_wgrad(tensor): channels rounded up to %d exceed the pitch", CH);
     WgParams P;
     memset(&P, 0, sizeof(P));
     P.dW = dw; P.CI = g->ci; P.CO = g->co;
     // ci <= 64: several taps share one 128-row M tile (no wasted MMA rows); otherwise ci < 128 <= co swaps the operands
-    P.pack_cb = g->ci <= 32 ? 32 : 64;
+    P.pack_cb = (!bf && g->ci <= 32) ? 32 : 64;
     P.pack_g = g->ci <= 64 ? TC_BM / P.pack_cb : 1;
     P.swap = (P.pack_g == 1 && g->ci < 128 && g->co >= 128) ? 1 : 0;
     P.m_valid = P.pack_g > 1 ? TC_BM : (P.swap ? g->co : g->ci);
@@ -862,21 +944,22 @@ int tc_conv_wgrad(const dofb_conv_geom *g, const float *x, int x_ld, const float
             }
             t.wk = kh * g->kw + kw;
         }
-    // pixel tile of 32 output pixels
+    // pixel tile of BKP output pixels
     {
         int TW = pow2_ceil(g->ow) < 16 ? pow2_ceil(g->ow) : 16;
-        int th_max = WG_BKP / TW;
+        int th_max = BKP / TW;
         int TH = pow2_ceil(g->oh) < th_max ? pow2_ceil(g->oh) : th_max;
         for (int t = TH; t >= 1; t >>= 1)
             if (g->oh % t == 0) { TH = t; break; }
-        P.TW = TW; P.TH = TH; P.TN = WG_BKP / (TW * TH);
+        P.TW = TW; P.TH = TH; P.TN = BKP / (TW * TH);
     }
     P.tiles_x = (g->ow + P.TW - 1) / P.TW;
     P.tiles_y = (g->oh + P.TH - 1) / P.TH;
     const int tiles_n = (g->B + P.TN - 1) / P.TN;
     P.tiles_total = P.tiles_x * P.tiles_y * tiles_n;
     const int n_ch = P.n_valid;
-    const int bn = n_ch > 128 ? 256 : (n_ch > 64 ? 128 : (n_ch > 32 ? 64 : 32));
+    int bn = n_ch > 128 ? 256 : (n_ch > 64 ? 128 : (n_ch > 32 ? 64 : 32));
+    if (bf && bn < 64) bn = 64;
     P.n_mblk = (P.m_valid + TC_BM - 1) / TC_BM;
     P.n_nblk = (n_ch + bn - 1) / bn;
     const int items = P.ntaps * P.n_mblk * P.n_nblk;
@@ -885,25 +968,35 @@ int tc_conv_wgrad(const dofb_conv_geom *g, const float *x, int x_ld, const float
     if (splits > P.tiles_total) splits = P.tiles_total;
     P.tiles_per_split = (int)((P.tiles_total + splits - 1) / splits);
     splits = (P.tiles_total + P.tiles_per_split - 1) / P.tiles_per_split;
+    const CUtensorMapDataType dt = bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const CUtensorMapSwizzle swz = bf ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    const void *xb = bf ? x16 : (const void *)x, *db = bf ? dy16 : (const void *)dy;
     CUtensorMap mx, md;
     if (!P.parity) {
         const uint64_t dims[4] = {(uint64_t)ci_pad, (uint64_t)g->iw, (uint64_t)g->ih, (uint64_t)g->B};
-        const uint64_t str[3] = {(uint64_t)x_ld * 4, (uint64_t)g->iw * x_ld * 4, (uint64_t)g->ih * g->iw * x_ld * 4};
-        const uint32_t box[4] = {32, (uint32_t)P.TW, (uint32_t)P.TH, (uint32_t)P.TN};
-        if (make_map(&mx, x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+        const uint64_t str[3] = {(uint64_t)x_ld * esz, (uint64_t)g->iw * x_ld * esz, (uint64_t)g->ih * g->iw * x_ld * esz};
+        const uint32_t box[4] = {(uint32_t)CH, (uint32_t)P.TW, (uint32_t)P.TH, (uint32_t)P.TN};
+        if (make_map(&mx, xb, 4, dims, str, box, swz, dt)) return 1;
     } else {
-        DOFB_CHECK_ARG(g->ih % 2 == 0 && g->iw % 2 == 0, "dofb_conv_wgrad(tf32): stride-2 gather needs even map sizes");
+        DOFB_CHECK_ARG(g->ih % 2 == 0 && g->iw % 2 == 0, "dofb_conv_wgrad(tensor): stride-2 gather needs even map sizes");
         const uint64_t dims[5] = {(uint64_t)2 * x_ld, (uint64_t)g->iw / 2, 2, (uint64_t)g->ih / 2, (uint64_t)g->B};
-        const uint64_t str[4] = {(uint64_t)2 * x_ld * 4, (uint64_t)g->iw * x_ld * 4, (uint64_t)2 * g->iw * x_ld * 4,
-                                 (uint64_t)g->ih * g->iw * x_ld * 4};
-        const uint32_t box[5] = {32, (uint32_t)P.TW, 1, (uint32_t)P.TH, (uint32_t)P.TN};
-        if (make_map(&mx, x, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+        const uint64_t str[4] = {(uint64_t)2 * x_ld * esz, (uint64_t)g->iw * x_ld * esz, (uint64_t)2 * g->iw * x_ld * esz,
+                                 (uint64_t)g->ih * g->iw * x_ld * esz};
+        const uint32_t box[5] = {(uint32_t)CH, (uint32_t)P.TW, 1, (uint32_t)P.TH, (uint32_t)P.TN};
+        if (make_map(&mx, xb, 5, dims, str, box, swz, dt)) return 1;
     }
     {
         const uint64_t dims[4] = {(uint64_t)co_pad, (uint64_t)g->ow, (uint64_t)g->oh, (uint64_t)g->B};
-        const uint64_t str[3] = {(uint64_t)dy_ld * 4, (uint64_t)g->ow * dy_ld * 4, (uint64_t)g->oh * g->ow * dy_ld * 4};
-        const uint32_t box[4] = {32, (uint32_t)P.TW, (uint32_t)P.TH, (uint32_t)P.TN};
-        if (make_map(&md, dy, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+        const uint64_t str[3] = {(uint64_t)dy_ld * esz, (uint64_t)g->ow * dy_ld * esz, (uint64_t)g->oh * g->ow * dy_ld * esz};
+        const uint32_t box[4] = {(uint32_t)CH, (uint32_t)P.TW, (uint32_t)P.TH, (uint32_t)P.TN};
+        if (make_map(&md, db, 4, dims, str, box, swz, dt)) return 1;
+    }
+    if (bf) {
+        switch (bn) {
+            case 256: return launch_wg<256, 4, true>(mx, md, P, (int)splits, items, st);
+            case 128: return launch_wg<128, 6, true>(mx, md, P, (int)splits, items, st);
+            default: return launch_wg<64, 8, true>(mx, md, P, (int)splits, items, st);
+        }
     }
     switch (bn) {
         case 256: return launch_wg<256, 4>(mx, md, P, (int)splits, items, st);
@@ -951,7 +1044,7 @@ static int conv1_prepare(const dofb_conv_geom *g, const float *x, int xp_h, int 
 }
 
 int tc_conv1_fwd(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *w, const float *bias,
-                 float *y, int y_ld, int act, cudaStream_t st) {
+                 float *y, int y_ld, int act, cudaStream_t st, void *y16) {
     DOFB_CHECK_ARG(g && x && w && y, "dofb_conv1_fwd: null argument");
     TcParams P;
     memset(&P, 0, sizeof(P));
@@ -960,7 +1053,8 @@ int tc_conv1_fwd(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, in
     CUtensorMap ma, mb;
     if (conv1_prepare(g, x, xp_h, xp_w, xp_y0, xp_x0, P.TW, P.TH, P.TN, CU_TENSOR_MAP_SWIZZLE_128B, &ma, P.taps)) return 1;
     P.parity = 1; P.ntaps = g->kh; P.ncb = 2; P.a_coff = 0; P.a_ld = 0;
-    P.out = y; P.out_ld = y_ld; P.bias = bias; P.n_valid = g->co; P.rh = g->oh; P.rw = g->ow; P.act = act; P.accumulate = 0; P.B = g->B;
+    P.out = y; P.out_ld = y_ld; P.out16 = reinterpret_cast<__nv_bfloat16 *>(y16);
+    P.bias = bias; P.n_valid = g->co; P.rh = g->oh; P.rw = g->ow; P.act = act; P.accumulate = 0; P.B = g->B;
     P.tiles_x = (P.cnt_x + P.TW - 1) / P.TW;
     P.tiles_y = (P.cnt_y + P.TH - 1) / P.TH;
     const int tiles = P.tiles_x * P.tiles_y * ((g->B + P.TN - 1) / P.TN);

@@ -1,6 +1,7 @@
 // Bandwidth-bound element-wise kernels: pre-processing + pyramid, ELU backward, TF-form Adam,
 // end-point-error.  All fp32, float4 where the layout allows, grid sized from the SM count.
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace dofb {
 
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float *__restric
 // layers still use every lane); a block owns a quad stripe and a pixel range, so the column sums of the result (BiasAddGrad)
 // reduce in registers -> shared -> one atomicAdd per channel per block.
 __global__ void __launch_bounds__(256) elu_bwd_kernel(float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c4, int qw,
-                                                      long long pix_per_block, float *db) {
+                                                      long long pix_per_block, float *db, __nv_bfloat16 *g16) {
     const int ql = threadIdx.x & (qw - 1);
     const int q = blockIdx.y * qw + ql;
     const int rows = 256 / qw;
@@ -169,6 +170,13 @@ __global__ void __launch_bounds__(256) elu_bwd_kernel(float *g, int g_ld, const 
             gv.x *= elu_grad_from_out(yv.x); gv.y *= elu_grad_from_out(yv.y);
             gv.z *= elu_grad_from_out(yv.z); gv.w *= elu_grad_from_out(yv.w);
             *reinterpret_cast<float4 *>(g + p * g_ld + q * 4) = gv;
+            if (g16 != nullptr) {               // bf16 shadow of the finished gradient for the tensor-core consumers
+                __nv_bfloat162 lo = __floats2bfloat162_rn(gv.x, gv.y), hi = __floats2bfloat162_rn(gv.z, gv.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<uint32_t *>(&lo);
+                pk.y = *reinterpret_cast<uint32_t *>(&hi);
+                *reinterpret_cast<uint2 *>(g16 + p * g_ld + q * 4) = pk;
+            }
             acc.x += gv.x; acc.y += gv.y; acc.z += gv.z; acc.w += gv.w;
         }
     }
@@ -296,7 +304,24 @@ extern "C" int dofb_maxpool2_bwd(const float *x, int x_ld, const float *dy, int 
     return 0;
 }
 
-extern "C" int dofb_elu_bwd(float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c, float *db, void *stream) {
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float *__restrict__ src, int src_ld, __nv_bfloat16 *__restrict__ dst, int dst_ld,
+                                                        long long n_pix, int c) {
+    const long long n = n_pix * c;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / c;
+        const int ch = (int)(i - p * c);
+        dst[p * dst_ld + ch] = __float2bfloat16_rn(__ldg(src + p * src_ld + ch));
+    }
+}
+
+extern "C" int dofb_cast_bf16(const float *src, int src_ld, void *dst_bf16, int dst_ld, long long n_pix, int c, void *stream) {
+    DOFB_CHECK_ARG(src && dst_bf16 && n_pix > 0 && c > 0 && src_ld >= c && dst_ld >= c, "dofb_cast_bf16: bad argument");
+    cast_bf16_kernel<<<grid_for(n_pix * c, 256), 256, 0, as_stream(stream)>>>(src, src_ld, reinterpret_cast<__nv_bfloat16 *>(dst_bf16), dst_ld, n_pix, c);
+    DOFB_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int dofb_elu_bwd(float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c, float *db, void *g_bf16, void *stream) {
     DOFB_CHECK_ARG(g && y && n_pix > 0 && c > 0, "dofb_elu_bwd: bad argument");
     DOFB_CHECK_ARG(c % 4 == 0 && g_ld % 4 == 0 && y_ld % 4 == 0 && aligned16(g) && aligned16(y),
                    "dofb_elu_bwd: channels/pitches must be multiples of 4 and pointers 16-byte aligned (c=%d)", c);
@@ -310,7 +335,8 @@ extern "C" int dofb_elu_bwd(float *g, int g_ld, const float *y, int y_ld, long l
     if (ppb < 4 * rows) ppb = 4 * rows;
     ppb = (ppb + rows - 1) / rows * rows;
     blocks = (n_pix + ppb - 1) / ppb;
-    elu_bwd_kernel<<<dim3((unsigned)blocks, stripes), 256, 0, as_stream(stream)>>>(g, g_ld, y, y_ld, n_pix, c4, qw, ppb, db);
+    elu_bwd_kernel<<<dim3((unsigned)blocks, stripes), 256, 0, as_stream(stream)>>>(g, g_ld, y, y_ld, n_pix, c4, qw, ppb, db,
+                                                                                   reinterpret_cast<__nv_bfloat16 *>(g_bf16));
     DOFB_LAUNCH_OK();
     return 0;
 }

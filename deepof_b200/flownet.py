@@ -23,7 +23,7 @@ from collections import OrderedDict
 import torch
 
 from . import ops
-from .ops import Slab, full, conv_geom, ACT_ELU, ACT_NONE, MATH_FP32, MATH_TF32
+from .ops import Slab, full, conv_geom, ACT_ELU, ACT_NONE, MATH_FP32, MATH_TF32, MATH_BF16
 
 FLYINGCHAIRS_MEAN = (97.533268117955444, 99.238235788550085, 97.055973199626948)   # flyingChairsWrapFlow.py:16
 SINTEL_MEAN = (70.1433, 83.1915, 92.8827)                                          # sintelWrapFlow.py:773
@@ -120,11 +120,10 @@ class FlowNetS:
         self.B, self.H, self.W = batch, height, width
         self.device = torch.device(device)
         self.variant = {"A": 0, "B": 1}[variant]
-        self.math = {"fp32": MATH_FP32, "tf32": MATH_TF32}[math_mode]
+        self.math = {"fp32": MATH_FP32, "tf32": MATH_TF32, "bf16": MATH_BF16}[math_mode]
         # per-op math: the tcgen05 path needs 32-float pitches (conv1 reads the 8-float pitched input) and has its own
         # weight-gradient kernel; anything it does not cover runs on the fp32 SIMT kernels (explicit, per layer).
-        self.math_wgrad = self.math if tc_wgrad else MATH_FP32
-        tc_wgrad = tc_wgrad and self.math == MATH_TF32
+        self.math_wgrad = self.math if (tc_wgrad or self.math == MATH_BF16) else MATH_FP32
         self.mean = tuple(float(m) for m in mean)
         self.hyper = dict(HYPER)
         if hyper:
@@ -190,15 +189,26 @@ class FlowNetS:
         self._z = z
         # first-layer input: dense for the SIMT path; zero-bordered (2 rows/cols before, 4/6 after) for the tcgen05 first-layer
         # kernel, which reads the SAME padding (2,3) of the 7x7/2 conv straight from the border
-        self.x6_origin = (2, 2) if self.math == MATH_TF32 else (0, 0)
-        xshape = (H + 6, W + 8, 8) if self.math == MATH_TF32 else (H, W, 8)
-        if self.ARCH == "V":            # VGG16: 3x3/1 first layer, generic kernels, 6 channels padded to one 32-float K block
-            xshape, self.x6_origin = (H, W, 32), (0, 0)
+        tensor = self.math != MATH_FP32
+        self.x6_origin = (2, 2) if tensor else (0, 0)
+        xshape = (H + 6, W + 8, 8) if tensor else (H, W, 8)
+        if self.ARCH == "V":            # VGG16: 3x3/1 first layer, generic kernels, 6 channels padded to one K block (32 floats / 64 bf16)
+            xshape, self.x6_origin = (H, W, 64 if self.math == MATH_BF16 else 32), (0, 0)
         self.x6 = z(*xshape)
         self.x6b = z(*xshape) if self.ARCH == "C" else None          # siamese: target image in its own buffer
         shp = self._buffer_shapes()
+        if self.math == MATH_BF16:      # bf16 K blocks are 64 channels: pitches become multiples of 64
+            shp = {k: (h, w, _round_up(c, 64)) for k, (h, w, c) in shp.items()}
         self.act = {k: z(*v) for k, v in shp.items()}
         self.dact = {k: z(*v) for k, v in shp.items()}
+        # bf16 shadows (same shapes): written by the tensor-core epilogues / elu_bwd / cast, read by the tensor-core consumers
+        self._sh = {}
+        if self.math == MATH_BF16:
+            for dct in (self.act, self.dact):
+                for t in dct.values():
+                    self._sh[id(t)] = torch.zeros(t.shape, dtype=torch.bfloat16, device=dev)
+            if self.ARCH == "V":
+                self._sh[id(self.x6)] = torch.zeros(self.x6.shape, dtype=torch.bfloat16, device=dev)
         self.hw = {s: (H >> s, W >> s) for s in range(1, self.N_SCALES + 1)}
         self.pr = {s: z(*self.hw[s], 2) for s in range(1, self.N_SCALES + 1)}
         self.dpr = {s: z(*self.hw[s], 2) for s in range(1, self.N_SCALES + 1)}
@@ -206,6 +216,12 @@ class FlowNetS:
         self.pyr_tgt = {s: z(*self.hw[s], 3) for s in range(1, self.N_SCALES + 1)}
         self.recon1 = z(*self.hw[1], 3)
         self.loss4 = torch.zeros(self.N_SCALES, 4, dtype=torch.float32, device=dev)
+
+    def _S(self, t, c0, c):
+        return Slab(t, c0, c, self._sh.get(id(t)))
+
+    def _F(self, t):
+        return Slab(t, 0, t.shape[3], self._sh.get(id(t)))
 
     def _buffer_shapes(self):
         H, W = self.H, self.W
@@ -227,9 +243,9 @@ class FlowNetS:
                     x=x, dx=dx, y=y, dy=dy, acc=acc, xpad=xpad)
 
     def _plan_tower(self):
-        a, d, S = self.act, self.dact, Slab
+        a, d, S, full = self.act, self.dact, self._S, self._F
         first_x = S(self.x6, 0, 6) if self.math == MATH_FP32 else None
-        first_pad = self.x6 if self.math == MATH_TF32 else None
+        first_pad = self.x6 if self.math != MATH_FP32 else None
         R = self._conv_rec
         return [
             R("conv1", 7, 2, 6, 64, first_x, None, S(a["concat1"], 0, 64), S(d["concat1"], 0, 64), xpad=first_pad),
@@ -239,7 +255,7 @@ class FlowNetS:
         ] + self._plan_tower_top()
 
     def _plan_tower_top(self):
-        a, d, S, R = self.act, self.dact, Slab, self._conv_rec
+        a, d, S, R, full = self.act, self.dact, self._S, self._conv_rec, self._F
         return [
             R("conv4_1", 3, 2, 256, 512, S(a["concat3"], 0, 256), S(d["concat3"], 0, 256), full(a["c41"]), full(d["c41"]), acc=True),
             R("conv4_2", 3, 1, 512, 512, full(a["c41"]), full(d["c41"]), S(a["concat4"], 0, 512), S(d["concat4"], 0, 512)),
@@ -250,7 +266,7 @@ class FlowNetS:
         ]
 
     def _plan_feat(self):
-        a, d, S = self.act, self.dact, Slab
+        a, d, S, full = self.act, self.dact, self._S, self._F
         return {6: (full(a["c62"]), full(d["c62"])), 5: (S(a["concat5"], 0, 1026), S(d["concat5"], 0, 1026)),
                 4: (S(a["concat4"], 0, 770), S(d["concat4"], 0, 770)), 3: (S(a["concat3"], 0, 386), S(d["concat3"], 0, 386)),
                 2: (S(a["concat2"], 0, 194), S(d["concat2"], 0, 194)), 1: (S(a["concat1"], 0, 98), S(d["concat1"], 0, 98))}
@@ -258,7 +274,7 @@ class FlowNetS:
     def _plan(self):
         B = self.B
         a, d = self.act, self.dact
-        S = Slab
+        S = self._S
         self.tower = self._plan_tower()
         self.feat = self._plan_feat()
         cat = {5: "concat5", 4: "concat4", 3: "concat3", 2: "concat2", 1: "concat1"}
@@ -287,8 +303,13 @@ class FlowNetS:
                 self._k("conv_fwd:" + L["name"], ops.conv_fwd, L["g"], L["x"], w, b, L["y"], ACT_ELU, mth)
         elif L["op"] == "pool":
             self._k("pool_fwd:" + L["name"], ops.maxpool2_fwd, L["x"], L["y"])
+            if mth == MATH_BF16:
+                self._k("cast:" + L["name"], ops.cast_bf16, L["y"])
         elif L["op"] == "corr":
-            self._k("corr_fwd", ops.corr_fwd, L["f1"], L["f2"], L["y"], L["max_disp"], L["stride2"], ACT_ELU, mth)
+            self._k("corr_fwd", ops.corr_fwd, L["f1"], L["f2"], L["y"], L["max_disp"], L["stride2"], ACT_ELU,
+                    MATH_TF32 if mth == MATH_BF16 else mth)          # the correlation band-GEMMs read the fp32 maps (TF32)
+            if mth == MATH_BF16:
+                self._k("cast:corr", ops.cast_bf16, L["y"])
 
     def _bwd_layer(self, L):
         P, G, mth, mthw = self.params, self.grads, self.math, self.math_wgrad
@@ -305,7 +326,8 @@ class FlowNetS:
             self._k("pool_bwd:" + L["name"], ops.maxpool2_bwd, L["x"], L["dy"], L["dx"])
         elif L["op"] == "corr":
             self._k("elu_bwd:corr", ops.elu_bwd, L["dy4"], L["y4"], None)
-            self._k("corr_bwd", ops.corr_bwd, L["f1"], L["f2"], L["dy"], L["df1"], L["df2"], L["max_disp"], L["stride2"], mth)
+            self._k("corr_bwd", ops.corr_bwd, L["f1"], L["f2"], L["dy"], L["df1"], L["df2"], L["max_disp"], L["stride2"],
+                    MATH_TF32 if mth == MATH_BF16 else mth)
 
     def forward(self, source: torch.Tensor, target: torch.Tensor, loss_weight=LOSS_WEIGHTS, with_grad: bool = True):
         """flowNet(inputs, outputs, loss_weight): runs the whole forward; when ``with_grad`` the fused
@@ -323,6 +345,8 @@ class FlowNetS:
             self._k("deconv_fwd:" + R["up"], ops.conv_dgrad, R["g"], x, P[R["up"] + "/weights"], P[R["up"] + "/biases"],
                     R["up_y"], ACT_ELU, False, mth)
             self._k("uppr_fwd:" + R["uppr"], ops.uppr_fwd, self.pr[s], P[R["uppr"] + "/weights"], P[R["uppr"] + "/biases"], R["pr_y"])
+            if mth == MATH_BF16:
+                self._k("cast:" + R["uppr"], ops.cast_bf16, R["pr_y"])
         self._k("head_fwd:pr1", ops.head_fwd, self.feat[1][0], P["pr1/weights"], P["pr1/biases"], self.pr[1])
         lw = [float(v) for v in loss_weight]
         self.loss_weight = lw
@@ -439,7 +463,7 @@ class FlowNetC(FlowNetS):
         return param_shapes_c()
 
     def _plan_tower(self):
-        a, d, S, R = self.act, self.dact, Slab, self._conv_rec
+        a, d, S, R, full = self.act, self.dact, self._S, self._conv_rec, self._F
         fp32 = self.math == MATH_FP32
         xa = S(self.x6, 0, 3) if fp32 else None
         xb = S(self.x6b, 0, 3) if fp32 else None
@@ -516,7 +540,7 @@ class VGG16Flow(FlowNetS):
         return shp
 
     def _plan_tower(self):
-        a, d, S, R = self.act, self.dact, Slab, self._conv_rec
+        a, d, S, R, full = self.act, self.dact, self._S, self._conv_rec, self._F
         recs = []
         skip_c = {1: 64, 2: 128, 3: 256, 4: 512}
         prev, dprev, prev_acc = S(self.x6, 0, 6), None, False
@@ -536,7 +560,7 @@ class VGG16Flow(FlowNetS):
         return recs
 
     def _plan_feat(self):
-        a, d, S = self.act, self.dact, Slab
+        a, d, S, full = self.act, self.dact, self._S, self._F
         return {5: (full(a["pool5"]), full(d["pool5"])), 4: (S(a["concat4"], 0, 770), S(d["concat4"], 0, 770)),
                 3: (S(a["concat3"], 0, 386), S(d["concat3"], 0, 386)), 2: (S(a["concat2"], 0, 194), S(d["concat2"], 0, 194)),
                 1: (S(a["concat1"], 0, 98), S(d["concat1"], 0, 98))}
@@ -553,5 +577,7 @@ class VGG16Flow(FlowNetS):
         mean, div = ((0.0, 0.0, 0.0), 1.0) if self._prescaled else (self.mean, 255.0)
         n = self.N_SCALES
         self._k("preprocess", ops.preprocess, source, target, mean, self.x6, [], [], (0, 0), None, div)
+        if self.math == MATH_BF16:
+            self._k("cast:x6", ops.cast_bf16, self._F(self.x6))
         self._k("preprocess", ops.preprocess, self._geo[0], self._geo[1], mean, None, [self.pyr_src[s] for s in range(1, n + 1)],
                 [self.pyr_tgt[s] for s in range(1, n + 1)], (0, 0), None, div)

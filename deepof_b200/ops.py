@@ -14,7 +14,7 @@ from . import _lib
 from ._lib import ConvGeom, LossScale, DeepOFError, check
 
 ACT_NONE, ACT_ELU = 0, 1
-MATH_FP32, MATH_TF32 = 0, 1
+MATH_FP32, MATH_TF32, MATH_BF16 = 0, 1, 2
 
 
 def _stream() -> C.c_void_p:
@@ -32,18 +32,25 @@ def _req(t: torch.Tensor, name: str) -> None:
 
 @dataclass
 class Slab:
-    """Channels [c0, c0+c) of a contiguous [B,H,W,ld] buffer."""
+    """Channels [c0, c0+c) of a contiguous [B,H,W,ld] buffer (optionally with its bf16 shadow of the same shape)."""
     t: torch.Tensor
     c0: int
     c: int
+    t16: torch.Tensor | None = None
 
     def __post_init__(self):
         _req(self.t, "Slab")
         assert self.t.dim() == 4 and 0 <= self.c0 and self.c0 + self.c <= self.t.shape[3]
+        if self.t16 is not None:
+            assert self.t16.dtype == torch.bfloat16 and self.t16.shape == self.t.shape and self.t16.is_cuda and self.t16.is_contiguous()
 
     @property
     def ptr(self) -> int:
         return self.t.data_ptr() + 4 * self.c0
+
+    @property
+    def ptr16(self):
+        return None if self.t16 is None else self.t16.data_ptr() + 2 * self.c0
 
     @property
     def ld(self) -> int:
@@ -118,7 +125,7 @@ def conv1_fwd(g: ConvGeom, xpad, origin, w, b, y: Slab, act=ACT_ELU):
     """conv1 on tensor cores from the zero-bordered input buffer (see dofb_conv1_fwd)."""
     _req(xpad, "xpad"); _req(w, "w")
     check(_lib.load().dofb_conv1_fwd(C.byref(g), xpad.data_ptr(), xpad.shape[1], xpad.shape[2], origin[0], origin[1], w.data_ptr(),
-                                     b.data_ptr() if b is not None else None, y.ptr, y.ld, act, _stream()))
+                                     b.data_ptr() if b is not None else None, y.ptr, y.ptr16, y.ld, act, _stream()))
 
 
 def conv1_wgrad(g: ConvGeom, xpad, origin, dy: Slab, dw, db):
@@ -127,9 +134,19 @@ def conv1_wgrad(g: ConvGeom, xpad, origin, dy: Slab, dw, db):
                                        dw.data_ptr(), db.data_ptr() if db is not None else None, _stream()))
 
 
+def _need16(s: Slab, who: str):
+    if s.ptr16 is None:
+        raise DeepOFError(f"{who}: bf16 math needs a bf16 shadow of this operand (Slab.t16)")
+    return s.ptr16
+
+
 def conv_fwd(g: ConvGeom, x: Slab, w, b, y: Slab, act=ACT_ELU, math=MATH_FP32):
     _req(w, "w")
     lib = _lib.load()
+    if math == MATH_BF16:
+        check(lib.dofb_conv_fwd_bf16(C.byref(g), _need16(x, "conv_fwd"), x.ld, w.data_ptr(), b.data_ptr() if b is not None else None,
+                                     y.ptr, y.ptr16, y.ld, act, _stream()))
+        return
     check(lib.dofb_conv_fwd(C.byref(g), x.ptr, x.ld, w.data_ptr(), b.data_ptr() if b is not None else None,
                             y.ptr, y.ld, act, math, _stream()))
 
@@ -137,6 +154,10 @@ def conv_fwd(g: ConvGeom, x: Slab, w, b, y: Slab, act=ACT_ELU, math=MATH_FP32):
 def conv_dgrad(g: ConvGeom, dy: Slab, w, bias, dx: Slab, act=ACT_NONE, accumulate=False, math=MATH_FP32):
     _req(w, "w")
     lib = _lib.load()
+    if math == MATH_BF16:
+        check(lib.dofb_conv_dgrad_bf16(C.byref(g), _need16(dy, "conv_dgrad"), dy.ld, w.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                       dx.ptr, dx.ptr16, dx.ld, act, int(accumulate), _stream()))
+        return
     check(lib.dofb_conv_dgrad(C.byref(g), dy.ptr, dy.ld, w.data_ptr(), bias.data_ptr() if bias is not None else None,
                               dx.ptr, dx.ld, act, int(accumulate), math, _stream()))
 
@@ -144,6 +165,11 @@ def conv_dgrad(g: ConvGeom, dy: Slab, w, bias, dx: Slab, act=ACT_NONE, accumulat
 def conv_wgrad(g: ConvGeom, x: Slab, dy: Slab, dw, db, math=MATH_FP32, bias_on_large=False):
     _req(dw, "dw")
     lib = _lib.load()
+    if math == MATH_BF16:
+        if db is not None:
+            raise DeepOFError("conv_wgrad(bf16): the bias gradient comes from elu_bwd(db=...) on this path")
+        check(lib.dofb_conv_wgrad_bf16(C.byref(g), _need16(x, "conv_wgrad"), x.ld, _need16(dy, "conv_wgrad"), dy.ld, dw.data_ptr(), _stream()))
+        return
     fn = lib.dofb_conv_wgrad_tbias if bias_on_large else lib.dofb_conv_wgrad
     check(fn(C.byref(g), x.ptr, x.ld, dy.ptr, dy.ld, dw.data_ptr(), db.data_ptr() if db is not None else None, math, _stream()))
 
@@ -151,7 +177,12 @@ def conv_wgrad(g: ConvGeom, x: Slab, dy: Slab, dw, db, math=MATH_FP32, bias_on_l
 def elu_bwd(g: Slab, y: Slab, db=None):
     """g *= elu'(y); with db, also db += column sums of the result (the layer's bias gradient) in the same pass."""
     assert g.c == y.c and g.n_pix == y.n_pix
-    check(_lib.load().dofb_elu_bwd(g.ptr, g.ld, y.ptr, y.ld, g.n_pix, g.c, db.data_ptr() if db is not None else None, _stream()))
+    check(_lib.load().dofb_elu_bwd(g.ptr, g.ld, y.ptr, y.ld, g.n_pix, g.c, db.data_ptr() if db is not None else None, g.ptr16, _stream()))
+
+
+def cast_bf16(s: Slab):
+    """Refresh the bf16 shadow of a slab whose producer has no fused shadow output."""
+    check(_lib.load().dofb_cast_bf16(s.ptr, s.ld, _need16(s, "cast_bf16"), s.ld, s.n_pix, s.c, _stream()))
 
 
 def invalidate_weight_cache():

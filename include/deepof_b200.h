@@ -102,7 +102,7 @@ typedef struct dofb_conv_geom {
 } dofb_conv_geom;
 
 enum { DOFB_ACT_NONE = 0, DOFB_ACT_ELU = 1 };
-enum { DOFB_MATH_FP32 = 0, DOFB_MATH_TF32 = 1 };   /* SIMT FFMA vs tcgen05 kind::tf32 */
+enum { DOFB_MATH_FP32 = 0, DOFB_MATH_TF32 = 1 };   /* SIMT FFMA vs tcgen05 kind::tf32 (bf16: the *_bf16 entry points below) */
 
 /* y = act(conv(x, w) + bias).  x pitch x_ld, y pitch y_ld (elements). */
 int dofb_conv_fwd(const dofb_conv_geom *g, const float *x, int x_ld, const float *w, const float *bias,
@@ -124,7 +124,7 @@ int dofb_conv_wgrad_tbias(const dofb_conv_geom *g, const float *x, int x_ld, con
  * dofb_preprocess: [B,xp_h,xp_w,8] with the image at (xp_y0, xp_x0); the border must cover the SAME padding
  * (xp_y0 >= pad_t, xp_x0 >= pad_l, enough rows/columns after the image) and xp_h, xp_w must be even. */
 int dofb_conv1_fwd(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *w,
-                   const float *bias, float *y, int y_ld, int act, void *stream);
+                   const float *bias, float *y, void *y_bf16 /* optional shadow, may be NULL */, int y_ld, int act, void *stream);
 int dofb_conv1_wgrad(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *dy,
                      int dy_ld, float *dw, float *db, void *stream);
 
@@ -140,9 +140,22 @@ void dofb_invalidate_weight_cache(void);
  * dofb_invalidate_weight_cache() after changing weight values; the training engine does (once per Adam step). */
 void dofb_enable_weight_cache(int on);
 
+/* ---- BF16 tensor-core math (tcgen05 kind::f16, bf16 operands, fp32 accumulate + fp32 epilogue) ----
+ * Activations keep their fp32 NHWC buffers; every producer additionally writes a bf16 "shadow" with the same pitch in elements
+ * (a multiple of 64), and the tensor-core consumers read the shadows: half the bytes per K element and twice the MMA rate of the
+ * TF32 path.  Weights stay fp32 (canonical TF layout) and are re-packed to bf16 K-major copies inside the call. */
+int dofb_conv_fwd_bf16(const dofb_conv_geom *g, const void *x_bf16, int x_ld, const float *w, const float *bias, float *y,
+                       void *y_bf16 /* may be NULL */, int y_ld, int act, void *stream);
+int dofb_conv_dgrad_bf16(const dofb_conv_geom *g, const void *dy_bf16, int dy_ld, const float *w, const float *bias, float *dx,
+                         void *dx_bf16 /* written only when !accumulate; may be NULL */, int dx_ld, int act, int accumulate, void *stream);
+int dofb_conv_wgrad_bf16(const dofb_conv_geom *g, const void *x_bf16, int x_ld, const void *dy_bf16, int dy_ld, float *dw, void *stream);
+/* dst_bf16[p, 0..c) = bf16(src[p, 0..c)) for producers that have no fused shadow output (flow heads' up_pr, correlation, pooling) */
+int dofb_cast_bf16(const float *src, int src_ld, void *dst_bf16, int dst_ld, long long n_pix, int c, void *stream);
+
 /* g[B*h*w, 0..c) *= elu'(y) where y is the ELU OUTPUT (elu' = y>0 ? 1 : y+1).  If db != NULL, db[c] += column sums of the
  * result (the BiasAddGrad of the layer) in the same pass. */
-int dofb_elu_bwd(float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c, float *db, void *stream);
+int dofb_elu_bwd(float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c, float *db, void *g_bf16 /* optional shadow */,
+                 void *stream);
 
 /* ---- thin heads (N = 2: bandwidth-bound, not tensor-core shapes) ---------- */
 /* pr_s = conv3x3(feat -> 2) linear, flyingChairsWrapFlow.py:58,69,80,91,102,113 */

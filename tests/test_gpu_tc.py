@@ -204,6 +204,108 @@ def test_tc_correlation_backward_matches_simt(B, h, w, md, s2):
     assert rel(outs[1][1], outs[0][1]) < TOL
 
 
+def _shadow(t):
+    return t.to(torch.bfloat16).contiguous()
+
+
+BF_TOL = 2e-2     # bf16 operands (8-bit mantissa), fp32 accumulate: max-norm relative
+
+
+@pytest.mark.parametrize("case", [
+    (2, 24, 32, 64, 128, 128, 5, 2), (2, 12, 16, 256, 256, 256, 3, 1), (4, 12, 16, 256, 448, 512, 3, 2), (8, 3, 4, 1024, 1024, 1024, 3, 1),
+    (1, 48, 64, 128, 256, 256, 5, 2), (2, 10, 14, 32, 64, 32, 3, 1), (2, 16, 16, 96, 128, 64, 3, 1)])
+def test_bf16_conv_fwd_dgrad_wgrad_match_simt(case):
+    from deepof_b200 import ops
+    B, H, W, ci, x_ld, co, k, s = case
+    g = torch.Generator().manual_seed(sum(case) + 1)
+    x = _buf(B, H, W, x_ld, ci, g)
+    w = (torch.randn(k, k, ci, co, generator=g) / math.sqrt(k * k * ci)).cuda()
+    b = (torch.randn(co, generator=g) * 0.1).cuda()
+    geom = ops.conv_geom(B, H, W, ci, co, k, s)
+    y_ld = (co + 63) // 64 * 64 + 64
+    y0 = torch.zeros(B, geom.oh, geom.ow, y_ld, device="cuda")
+    y1 = torch.zeros_like(y0)
+    y1s = torch.zeros(y1.shape, dtype=torch.bfloat16, device="cuda")
+    ops.conv_fwd(geom, ops.Slab(x, 0, ci), w, b, ops.Slab(y0, 64, co), ops.ACT_ELU, ops.MATH_FP32)
+    ops.conv_fwd(geom, ops.Slab(x, 0, ci, _shadow(x)), w, b, ops.Slab(y1, 64, co, y1s), ops.ACT_ELU, ops.MATH_BF16)
+    torch.cuda.synchronize()
+    assert rel(y1, y0) < BF_TOL
+    assert torch.equal(y1s[..., 64:64 + co], y1[..., 64:64 + co].to(torch.bfloat16))          # fused shadow == rounded fp32 output
+    assert float(y1s[..., :64].abs().max()) == 0.0
+    dyl = (co + 63) // 64 * 64
+    dy = _buf(B, geom.oh, geom.ow, dyl, co, g)
+    d0 = torch.full((B, H, W, x_ld), 0.25, device="cuda")
+    d1 = torch.full((B, H, W, x_ld), 0.25, device="cuda")
+    for acc in (True, False):
+        ops.conv_dgrad(geom, ops.Slab(dy, 0, co), w, None, ops.Slab(d0, 0, ci), ops.ACT_NONE, acc, ops.MATH_FP32)
+        ops.conv_dgrad(geom, ops.Slab(dy, 0, co, _shadow(dy)), w, None, ops.Slab(d1, 0, ci), ops.ACT_NONE, acc, ops.MATH_BF16)
+        torch.cuda.synchronize()
+        assert rel(d1[..., :ci], d0[..., :ci]) < BF_TOL, acc
+    dw0 = torch.zeros(k, k, ci, co, device="cuda"); dw1 = torch.zeros_like(dw0)
+    ops.conv_wgrad(geom, ops.Slab(x, 0, ci), ops.Slab(dy, 0, co), dw0, None, ops.MATH_FP32)
+    ops.conv_wgrad(geom, ops.Slab(x, 0, ci, _shadow(x)), ops.Slab(dy, 0, co, _shadow(dy)), dw1, None, ops.MATH_BF16)
+    torch.cuda.synchronize()
+    assert rel(dw1, dw0) < BF_TOL
+
+
+@pytest.mark.parametrize("case", [(2, 6, 8, 1024, 1024, 512), (2, 12, 16, 1026, 1088, 256), (1, 48, 64, 386, 448, 64), (2, 24, 32, 194, 256, 32)])
+def test_bf16_deconv_match_simt(case):
+    from deepof_b200 import ops
+    B, h, w, cfeat, fld, upc = case
+    g = torch.Generator().manual_seed(sum(case) + 2)
+    x = _buf(B, h, w, fld, cfeat, g)
+    wt = (torch.randn(4, 4, upc, cfeat, generator=g) / math.sqrt(4 * cfeat)).cuda()
+    b = (torch.randn(upc, generator=g) * 0.1).cuda()
+    geom = ops.conv_geom(B, 2 * h, 2 * w, upc, cfeat, 4, 2)
+    y0 = torch.zeros(B, 2 * h, 2 * w, 128, device="cuda")
+    y1 = torch.zeros_like(y0)
+    y1s = torch.zeros(y1.shape, dtype=torch.bfloat16, device="cuda")
+    ld_out = 64 + (upc + 63) // 64 * 64
+    y0 = torch.zeros(B, 2 * h, 2 * w, ld_out, device="cuda"); y1 = torch.zeros_like(y0)
+    y1s = torch.zeros(y1.shape, dtype=torch.bfloat16, device="cuda")
+    ops.conv_dgrad(geom, ops.Slab(x, 0, cfeat), wt, b, ops.Slab(y0, 64, upc), ops.ACT_ELU, False, ops.MATH_FP32)
+    ops.conv_dgrad(geom, ops.Slab(x, 0, cfeat, _shadow(x)), wt, b, ops.Slab(y1, 64, upc, y1s), ops.ACT_ELU, False, ops.MATH_BF16)
+    torch.cuda.synchronize()
+    assert rel(y1, y0) < BF_TOL
+    assert torch.equal(y1s[..., 64:64 + upc], y1[..., 64:64 + upc].to(torch.bfloat16))
+    dy = _buf(B, 2 * h, 2 * w, (upc + 63) // 64 * 64, upc, g)
+    d0 = torch.zeros(B, h, w, fld, device="cuda"); d1 = torch.zeros_like(d0)
+    ops.conv_fwd(geom, ops.Slab(dy, 0, upc), wt, None, ops.Slab(d0, 0, cfeat), ops.ACT_NONE, ops.MATH_FP32)
+    ops.conv_fwd(geom, ops.Slab(dy, 0, upc, _shadow(dy)), wt, None, ops.Slab(d1, 0, cfeat), ops.ACT_NONE, ops.MATH_BF16)
+    dw0 = torch.zeros(4, 4, upc, cfeat, device="cuda"); dw1 = torch.zeros_like(dw0)
+    ops.conv_wgrad(geom, ops.Slab(dy, 0, upc), ops.Slab(x, 0, cfeat), dw0, None, ops.MATH_FP32)
+    ops.conv_wgrad(geom, ops.Slab(dy, 0, upc, _shadow(dy)), ops.Slab(x, 0, cfeat, _shadow(x)), dw1, None, ops.MATH_BF16)
+    torch.cuda.synchronize()
+    assert rel(d1[..., :cfeat], d0[..., :cfeat]) < BF_TOL
+    assert rel(dw1, dw0) < BF_TOL
+
+
+def test_bf16_engine_epe_within_tolerance():
+    """BF16 tensor-core math (bf16 operands, fp32 accumulate/epilogue): EPE on the held-out batch within 1e-3 of the fp32 path."""
+    from deepof_b200.flownet import FlowNetS
+    from oracle import synth, metrics
+    B, H, W = 2, 384, 512
+    src, tgt, gt = synth.make_pairs(B, H, W, seed=1234)
+    e32 = FlowNetS(B, H, W, seed=1, math_mode="fp32")
+    ebf = FlowNetS(B, H, W, seed=1, math_mode="bf16")
+    for e in (e32, ebf):
+        e.forward(src.cuda(), tgt.cuda())
+        e.backward()
+    torch.cuda.synchronize()
+    d = (ebf.pr[1] - e32.pr[1]).abs() * 10.0
+    epe32 = metrics.flow_ee(metrics.eval_flow(e32.pr[1].cpu() * 10.0, H, W), gt).item()
+    epebf = metrics.flow_ee(metrics.eval_flow(ebf.pr[1].cpu() * 10.0, H, W), gt).item()
+    cos = torch.nn.functional.cosine_similarity(ebf.grad.double(), e32.grad.double(), dim=0).item()
+    print(f"bf16 vs fp32: mean|dflow1|={d.mean().item():.3e} max={d.max().item():.3e} EPE fp32={epe32:.6f} bf16={epebf:.6f} grad cosine={cos:.4f}")
+    assert abs(epebf - epe32) < 1e-3
+    assert d.mean().item() < 1e-2
+    assert torch.allclose(ebf.loss4, e32.loss4, rtol=2e-2, atol=1e-3)
+    assert cos > 0.9
+    for _ in range(2):
+        ebf.train_step(src.cuda(), tgt.cuda(), lr=1.6e-5)
+    assert torch.isfinite(ebf.theta).all()
+
+
 def test_tf32_engine_tracks_fp32_engine_and_oracle_epe():
     """Whole step in TF32 mode: flows within the stated tolerance of the fp32 device path and EPE within 1e-3 of the CPU oracle."""
     from deepof_b200.flownet import FlowNetS
