@@ -208,7 +208,7 @@ def run_ours(args, rank, local_rank, world):
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     lib = _lib.load()
-    step = TrainStep(B, (H, W), device=dev, math_mode=args.math, distributed=world > 1, tc_wgrad=(args.math == "tf32"),
+    step = TrainStep(B, (H, W), device=dev, math_mode=args.math, distributed=world > 1, tc_wgrad=(args.math != "fp32"),
                      model=args.model, variant=args.variant)
     eng = step.engine
     # two different synthetic batches per rank, alternated (working set per step ~3 GB >> 126 MB L2)
@@ -310,10 +310,11 @@ def run_ours(args, rank, local_rank, world):
         gemm_fl = sum(classes[k]["flops"] for k in gemm)
         gemm_n = sum(classes[k]["launches"] for k in gemm)
         tf32 = args.math == "tf32"
-        peak = peaks["bf16_sustained"] * (0.5 if tf32 else 1.0)
+        peak = peaks["bf16_sustained"] * (0.5 if tf32 else 1.0)        # bf16 math (and the fp32 SIMT path) are divided by the bf16 peak
         ach = gemm_fl / (gemm_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "kernel": "implicit-GEMM conv family (fwd/dgrad/wgrad, conv + transposed conv), "
-                                             + ("tcgen05 kind::tf32" if tf32 else "SIMT fp32 FFMA (parity-grade path)"),
+                                             + {"tf32": "tcgen05 kind::tf32", "bf16": "tcgen05 kind::f16 (bf16 operands, fp32 accumulate)",
+                                                "fp32": "SIMT fp32 FFMA (parity-grade path)"}[args.math],
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})" + (" x0.5 for tf32" if tf32 else ""),
                 "traffic": None, "share_of_step": gemm_ms / total_ms, "launches_per_step": gemm_n,
@@ -349,7 +350,7 @@ def run_ours(args, rank, local_rank, world):
         for mode in ("fp32", args.math):
             if mode in flows:
                 continue
-            e = cls(hb, H, W, device=dev, math_mode=mode, seed=1, variant=args.variant, tc_wgrad=(mode == "tf32"))
+            e = cls(hb, H, W, device=dev, math_mode=mode, seed=1, variant=args.variant, tc_wgrad=(mode != "fp32"))
             e.forward(hs, ht, with_grad=False)
             flows[mode] = (e.pr[1] * 10.0).clone()
             del e
@@ -392,7 +393,7 @@ def run_ours(args, rank, local_rank, world):
     e2e = gb * args.steps / (ms_e2e * 1e-3)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32" if args.math == "tf32" else "f32", "data": "synthetic",
+            "dtype": {"tf32": "tf32", "bf16": "bf16", "fp32": "f32"}[args.math], "data": "synthetic",
             "config": {"workload": f"{'FlowNetS' if args.model == 'flownets' else 'FlowNetC (correlation cost-volume)'} training "
                                    f"(fwd+bwd+Adam), synthetic FlyingChairs {H}x{W}, batch={B} per GPU",
                        "global_batch": gb, "parallelism": f"dp{world}",
@@ -417,8 +418,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--math", default=os.environ.get("DEEPOF_MATH", "tf32"), choices=["fp32", "tf32"],
-                    help="tf32: tcgen05 tensor-core convolutions (TF32 operands, fp32 accumulate; EPE within 1e-3 of the fp32 path, "
+    ap.add_argument("--math", default=os.environ.get("DEEPOF_MATH", "tf32"), choices=["fp32", "tf32", "bf16"],
+                    help="bf16: tcgen05 kind::f16 on bf16 activation shadows + bf16 packed weights, fp32 accumulate/epilogue/master weights; tf32: tcgen05 tensor-core convolutions (TF32 operands, fp32 accumulate; EPE within 1e-3 of the fp32 path, "
                          "checked in this run); fp32: SIMT FFMA parity path")
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (BASELINE config: 32)")
     ap.add_argument("--model", default="flownets", choices=["flownets", "flownetc"], help="flownets = BASELINE configs[1]; flownetc = configs[2]")
