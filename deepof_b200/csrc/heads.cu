@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256, 2) head_dgrad_kernel(const float *__restr
                 o3 += gg.x * wr[tap][3][0] + gg.y * wr[tap][3][1];
             }
         *dst = make_float4(o0 + old.x, o1 + old.y, o2 + old.z, o3 + old.w);
-        win.advance();
+        if (p + 1 < p1) win.advance();          // (never step past the last pixel: the next image may not exist)
     }
 }
 
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(256, 2) head_wgrad_kernel(const float *__restr
                 }
             if (blockIdx.y == 0 && lane == 0) { const float2 cc = win.tap(1, 1); b0 += cc.x; b1 += cc.y; }
             xv = xn;
-            win.advance();
+            if (p + 1 < p1) win.advance();          // (never step past the last pixel: the next image may not exist)
         }
     }
     // block-level combine in shared memory, then one global atomic per (tap,ch,o) per block
