@@ -218,7 +218,8 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     constexpr int TMEM_COLS = 2 * ACC_COLS;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    float *stage_f = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);                 // [4 warps][32][36] epilogue transpose tiles
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(stage_f + 4 * 32 * 36);
     uint64_t *empty_bar = full_bar + STAGES;
     uint64_t *acc_full = empty_bar + STAGES;       // [2] MMA -> epilogue
     uint64_t *acc_empty = acc_full + 2;            // [2] epilogue -> MMA (4 warps arrive)
@@ -291,9 +292,15 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             }
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> bias/ELU -> NHWC global =====
+        // ===== epilogue: TMEM -> registers -> shared-memory transpose -> bias/ELU -> coalesced NHWC stores =====
+        // tcgen05.ld hands every thread one ROW of the tile (32 columns at a time); storing that directly would make each warp
+        // store instruction touch 32 different pixels (32 half-used sectors).  Each warp therefore stages its 32x32 block in a
+        // private shared-memory tile (pitch 36 floats: conflict-free float4 writes and reads) and re-reads it so that 8 lanes cover
+        // the 128 contiguous bytes of one output pixel: 4 pixels x 128 B per store instruction, bias and ELU applied per column quad.
         const int r = warp * 32 + lane;                     // row of the tile == TMEM lane
-        const bool vec_ok = ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0) && (P.out_ld % 4 == 0);
+        float *stg = stage_f + warp * (32 * 36);
+        const int q = lane & 7, rsub = lane >> 3;           // this lane's column quad and row-within-group in the store phase
+        const bool out_al = ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0) && (P.out_ld % 4 == 0);
         int lt = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
             const int mt = t % m_tiles, nt = t / m_tiles;
@@ -301,7 +308,8 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             const int ix = tx * P.TW + r % P.TW, iy = ty * P.TH + (r / P.TW) % P.TH, nn = tn * P.TN + r / (P.TW * P.TH);
             const int n0 = nt * BN;
             const bool row_ok = ix < P.cnt_x && iy < P.cnt_y && nn < P.B;
-            float *orow = P.out + (((long long)nn * P.rh + P.y0 + iy * P.rstep) * P.rw + P.x0 + ix * P.rstep) * P.out_ld;
+            // element offset of this thread's output pixel (-1: no pixel); fetched by the storing lanes through shuffles
+            const long long my_off = row_ok ? (((long long)nn * P.rh + P.y0 + iy * P.rstep) * P.rw + P.x0 + ix * P.rstep) * P.out_ld : -1;
             const int acc = lt & 1;
             mbar_wait(&acc_full[acc], (lt >> 1) & 1);
             tc_fence_after();
@@ -309,44 +317,55 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             for (int j = 0; j < BN / 32; ++j) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * ACC_COLS + j * 32), v);
-                if (!row_ok) continue;
                 const int cbase = n0 + j * 32;
+                if (cbase >= P.n_valid) continue;           // (warp-uniform)
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int col = cbase + q * 4;
-                    if (col >= P.n_valid) break;
-                    float o[4] = {v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]};
+                for (int c = 0; c < 8; ++c)
+                    *reinterpret_cast<float4 *>(stg + lane * 36 + c * 4) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                __syncwarp();
+                const int col = cbase + q * 4;
+                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (P.bias != nullptr && col < P.n_valid) {
+                    if (col + 3 < P.n_valid) bv = __ldg(reinterpret_cast<const float4 *>(P.bias + col));
+                    else { bv.x = __ldg(P.bias + col); if (col + 1 < P.n_valid) bv.y = __ldg(P.bias + col + 1); if (col + 2 < P.n_valid) bv.z = __ldg(P.bias + col + 2); }
+                }
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        if (col + e < P.n_valid) {
-                            if (P.bias) o[e] += __ldg(P.bias + col + e);
-                            if (P.act == DOFB_ACT_ELU) o[e] = elu_f(o[e]);
-                        }
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = i * 4 + rsub;
+                    const long long off = __shfl_sync(0xffffffffu, my_off, rr);
+                    if (off < 0 || col >= P.n_valid) continue;
+                    float4 o = *reinterpret_cast<const float4 *>(stg + rr * 36 + q * 4);
+                    o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                    if (P.act == DOFB_ACT_ELU) {            // fast ELU: exp via MUFU (absolute error ~1e-7, irrelevant next to TF32/BF16 operands)
+                        o.x = o.x > 0.f ? o.x : __expf(o.x) - 1.f; o.y = o.y > 0.f ? o.y : __expf(o.y) - 1.f;
+                        o.z = o.z > 0.f ? o.z : __expf(o.z) - 1.f; o.w = o.w > 0.f ? o.w : __expf(o.w) - 1.f;
                     }
-                    if (vec_ok && col + 3 < P.n_valid) {
-                        float4 *dst = reinterpret_cast<float4 *>(orow + col);
+                    float *dst = P.out + off + col;
+                    if (out_al && col + 3 < P.n_valid) {
                         if (P.accumulate) {
-                            const float4 old = *dst;
-                            o[0] += old.x; o[1] += old.y; o[2] += old.z; o[3] += old.w;
+                            const float4 old = *reinterpret_cast<const float4 *>(dst);
+                            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
                         }
-                        *dst = make_float4(o[0], o[1], o[2], o[3]);
-                        if (P.out16 != nullptr) {            // bf16 shadow for the next tensor-core consumer (same pitch, 8-byte store)
-                            __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
+                        *reinterpret_cast<float4 *>(dst) = o;
+                        if (P.out16 != nullptr) {           // bf16 shadow for the next tensor-core consumer (same pitch, 8-byte store)
+                            __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
                             uint2 pk;
                             pk.x = *reinterpret_cast<uint32_t *>(&lo);
                             pk.y = *reinterpret_cast<uint32_t *>(&hi);
-                            *reinterpret_cast<uint2 *>(P.out16 + (orow - P.out) + col) = pk;
+                            *reinterpret_cast<uint2 *>(P.out16 + off + col) = pk;
                         }
                     } else {
+                        const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
                             if (col + e < P.n_valid) {
-                                const float val = P.accumulate ? orow[col + e] + o[e] : o[e];
-                                orow[col + e] = val;
-                                if (P.out16 != nullptr) P.out16[(orow - P.out) + col + e] = __float2bfloat16_rn(val);
+                                const float val = P.accumulate ? dst[e] + ov[e] : ov[e];
+                                dst[e] = val;
+                                if (P.out16 != nullptr) P.out16[off + col + e] = __float2bfloat16_rn(val);
                             }
                     }
                 }
+                __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
@@ -498,7 +517,8 @@ static void choose_tile(int cnt_y, int cnt_x, int &TW, int &TH, int &TN) {
 
 template <int BN, int STAGES, bool BF = false>
 static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &Pin, int tiles, int n_tiles, cudaStream_t st) {
-    constexpr int smem = STAGES * (TC_A_BYTES + BN * TC_BK * 4) + 1024 + 256;
+    constexpr int smem = STAGES * (TC_A_BYTES + BN * TC_BK * 4) + 4 * 32 * 36 * 4 + 1024 + 256;
+    static_assert(smem <= 227 * 1024, "shared-memory budget");
     static bool configured = false;
     if (!configured) {
         DOFB_CUDA_OK(cudaFuncSetAttribute(tc_gather_gemm_kernel<BN, STAGES, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
