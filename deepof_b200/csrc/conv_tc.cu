@@ -329,10 +329,19 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     if (col + 3 < P.n_valid) bv = __ldg(reinterpret_cast<const float4 *>(P.bias + col));
                     else { bv.x = __ldg(P.bias + col); if (col + 1 < P.n_valid) bv.y = __ldg(P.bias + col + 1); if (col + 2 < P.n_valid) bv.z = __ldg(P.bias + col + 2); }
                 }
+                long long offs[8];
+                float4 olds[8];
+                const bool vec = out_al && col + 3 < P.n_valid;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {               // all 8 read-modify-write loads in flight before any is consumed
+                    offs[i] = __shfl_sync(0xffffffffu, my_off, i * 4 + rsub);
+                    olds[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (P.accumulate && vec && offs[i] >= 0) olds[i] = *reinterpret_cast<const float4 *>(P.out + offs[i] + col);
+                }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int rr = i * 4 + rsub;
-                    const long long off = __shfl_sync(0xffffffffu, my_off, rr);
+                    const long long off = offs[i];
                     if (off < 0 || col >= P.n_valid) continue;
                     float4 o = *reinterpret_cast<const float4 *>(stg + rr * 36 + q * 4);
                     o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
@@ -341,11 +350,8 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                         o.z = o.z > 0.f ? o.z : __expf(o.z) - 1.f; o.w = o.w > 0.f ? o.w : __expf(o.w) - 1.f;
                     }
                     float *dst = P.out + off + col;
-                    if (out_al && col + 3 < P.n_valid) {
-                        if (P.accumulate) {
-                            const float4 old = *reinterpret_cast<const float4 *>(dst);
-                            o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                        }
+                    if (vec) {
+                        o.x += olds[i].x; o.y += olds[i].y; o.z += olds[i].z; o.w += olds[i].w;
                         *reinterpret_cast<float4 *>(dst) = o;
                         if (P.out16 != nullptr) {           // bf16 shadow for the next tensor-core consumer (same pitch, 8-byte store)
                             __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
