@@ -311,6 +311,18 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             // element offset of this thread's output pixel (-1: no pixel); fetched by the storing lanes through shuffles
             const long long my_off = row_ok ? (((long long)nn * P.rh + P.y0 + iy * P.rstep) * P.rw + P.x0 + ix * P.rstep) * P.out_ld : -1;
             const int acc = lt & 1;
+            // pixel offsets of the 8 rows this lane stores in every chunk, and (accumulate) the old values of chunk 0, requested
+            // BEFORE waiting for the accumulator so that their DRAM latency hides behind the MMAs still running
+            long long offs[8];
+            float4 olds[8], nxt[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                offs[i] = __shfl_sync(0xffffffffu, my_off, i * 4 + rsub);
+                olds[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                nxt[i] = olds[i];
+                const int col0 = n0 + q * 4;
+                if (P.accumulate && out_al && offs[i] >= 0 && col0 + 3 < P.n_valid) olds[i] = *reinterpret_cast<const float4 *>(P.out + offs[i] + col0);
+            }
             mbar_wait(&acc_full[acc], (lt >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
@@ -319,6 +331,14 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * ACC_COLS + j * 32), v);
                 const int cbase = n0 + j * 32;
                 if (cbase >= P.n_valid) continue;           // (warp-uniform)
+                if (P.accumulate && j + 1 < BN / 32) {      // next chunk's old values in flight while this chunk is processed
+                    const int coln = cbase + 32 + q * 4;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (out_al && offs[i] >= 0 && coln + 3 < P.n_valid) nxt[i] = *reinterpret_cast<const float4 *>(P.out + offs[i] + coln);
+                    }
+                }
 #pragma unroll
                 for (int c = 0; c < 8; ++c)
                     *reinterpret_cast<float4 *>(stg + lane * 36 + c * 4) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
@@ -329,15 +349,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     if (col + 3 < P.n_valid) bv = __ldg(reinterpret_cast<const float4 *>(P.bias + col));
                     else { bv.x = __ldg(P.bias + col); if (col + 1 < P.n_valid) bv.y = __ldg(P.bias + col + 1); if (col + 2 < P.n_valid) bv.z = __ldg(P.bias + col + 2); }
                 }
-                long long offs[8];
-                float4 olds[8];
                 const bool vec = out_al && col + 3 < P.n_valid;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {               // all 8 read-modify-write loads in flight before any is consumed
-                    offs[i] = __shfl_sync(0xffffffffu, my_off, i * 4 + rsub);
-                    olds[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (P.accumulate && vec && offs[i] >= 0) olds[i] = *reinterpret_cast<const float4 *>(P.out + offs[i] + col);
-                }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int rr = i * 4 + rsub;
@@ -371,6 +383,8 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                             }
                     }
                 }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) olds[i] = nxt[i];
                 __syncwarp();
             }
             tc_fence_before();
