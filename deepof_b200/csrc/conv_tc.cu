@@ -661,7 +661,8 @@ int tc_conv_fwd(const dofb_conv_geom *g, const float *x, int x_ld, const float *
     G.a_base = x; G.a_ld = x_ld; G.a_coff = 0; G.a_c = g->ci; G.a16 = x16; G.out16 = y16;
     G.ah = g->ih; G.aw = g->iw;
     G.w = w; G.w_ci = g->ci; G.w_co = g->co; G.taps_h = g->kh; G.taps_w = g->kw; G.contract_ci = 1;
-    G.out = y; G.out_ld = y_ld; G.rh = g->oh; G.rw = g->ow; G.n_valid = g->co; G.bias = bias; G.act = act; G.accumulate = 0; G.B = g->B;
+    G.out = y; G.out_ld = y_ld; G.rh = g->oh; G.rw = g->ow; G.n_valid = g->co; G.bias = bias; G.B = g->B;
+    G.act = act & ~DOFB_ACT_ACCUMULATE; G.accumulate = (act & DOFB_ACT_ACCUMULATE) != 0;
     TcParams P;
     memset(&P, 0, sizeof(P));
     P.y0 = P.x0 = 0; P.rstep = 1; P.cnt_y = g->oh; P.cnt_x = g->ow;

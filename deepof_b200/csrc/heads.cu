@@ -7,13 +7,96 @@
 
 namespace dofb {
 
-constexpr int HD_PX = 8;   // pixels per warp in the forward head
+constexpr int HD_PX = 8;   // pixels per warp strip in the forward head
 
-// ---- pr forward: one warp per 8 consecutive pixels of a row; lanes stride the channels (float4);
-// the [3,3,c,2] filter is staged once per block in shared memory (<= 74 KB for c = 1026) ----
-__global__ void __launch_bounds__(256) head_fwd_kernel(const float *__restrict__ X, int x_ld, int B, int h, int w, int c,
-                                                       const float *__restrict__ Wt, const float *__restrict__ bias,
-                                                       float *__restrict__ pr) {
+// acc += (a, a) * b with ONE packed FFMA2 (sm_100): the heads are FP32-issue bound, and written as "x*w0 + y*w1" the compiler
+// emits FMUL+FFMA+FADD per pair of multiply-adds; explicit packed FMAs halve the FMA instruction count instead.
+__device__ __forceinline__ void fma2(float2 &acc, float a, float2 b) { acc = __ffma2_rn(make_float2(a, a), b, acc); }
+
+// Sum 16 per-lane values across the warp with 16 shuffles (instead of 16 x 5): every step halves the number of values a lane
+// keeps.  On return lane L holds the warp total of value index L >> 1 (lanes 2i and 2i+1 hold the same number).
+__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float keep = b4 ? v[i + 8] : v[i], send = b4 ? v[i] : v[i + 8];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float keep = b3 ? v[i + 4] : v[i], send = b3 ? v[i] : v[i + 4];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float keep = b2 ? v[i + 2] : v[i], send = b2 ? v[i] : v[i + 2];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    {
+        const float keep = b1 ? v[1] : v[0], send = b1 ? v[0] : v[1];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// ---- pr forward: one warp per STRIP of 8 pixels x R rows; lanes stride the channels (float4) ----
+// The strip is walked top to bottom and every input row is read ONCE (plus the one-pixel halo): its 8+2 pixels are scattered
+// into three rotating accumulator rows (the output rows y-1, y, y+1 it touches), so the 3x vertical re-read of a gather
+// formulation -- which made this kernel L2-bandwidth bound -- disappears.  S = (row index within the strip) mod 3 is a
+// template parameter so that the accumulator rotation is pure register renaming.
+// The [3,3,c,2] filter is staged once per block in shared memory (<= 74 KB for c = 1026).
+template <int S>
+__device__ __forceinline__ void head_fwd_row(float2 (&acc)[3][HD_PX], const float *__restrict__ X, int x_ld, int h, int w, int c4,
+                                             const float *wsm, int b, int iy, int x0, bool k0, bool k1, bool k2, int lane) {
+    if (iy < 0 || iy >= h) return;
+    const float *rowp = X + ((long long)b * h + iy) * w * x_ld;
+    for (int q = lane; q < c4; q += 32) {
+        float4 xv[HD_PX + 2];
+#pragma unroll
+        for (int i = 0; i < HD_PX + 2; ++i) {
+            const int sx = x0 - 1 + i;
+            xv[i] = (sx >= 0 && sx < w) ? __ldg(reinterpret_cast<const float4 *>(rowp + (long long)sx * x_ld + q * 4))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            // input row iy feeds output row iy - kh + 1, which lives in accumulator slot (S + 1 - kh) mod 3
+            const bool on = kh == 0 ? k0 : (kh == 1 ? k1 : k2);
+            if (!on) continue;                              // (warp-uniform: that output row is outside the strip)
+            float2 (&a)[HD_PX] = acc[(S + 4 - kh) % 3];
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const float4 *wp = reinterpret_cast<const float4 *>(wsm + ((kh * 3 + kw) * c4 + q) * 8);
+                const float4 wa = wp[0], wb = wp[1];       // (c0o0,c0o1,c1o0,c1o1) (c2o0,c2o1,c3o0,c3o1)
+#pragma unroll
+                for (int p = 0; p < HD_PX; ++p) {
+                    const float4 xx = xv[p + kw];
+                    fma2(a[p], xx.x, make_float2(wa.x, wa.y));
+                    fma2(a[p], xx.y, make_float2(wa.z, wa.w));
+                    fma2(a[p], xx.z, make_float2(wb.x, wb.y));
+                    fma2(a[p], xx.w, make_float2(wb.z, wb.w));
+                }
+            }
+        }
+    }
+}
+
+template <int S>
+__device__ __forceinline__ void head_fwd_emit(float2 (&acc)[3][HD_PX], float *__restrict__ pr, const float *__restrict__ bias, int h,
+                                              int w, int b, int oy, int x0, int lane) {
+    // output row oy sits in slot (oy - y0 + 1) mod 3 == (S + 2) mod 3 when called after input row oy + 1
+    float2 (&a)[HD_PX] = acc[(S + 2) % 3];
+    float v[16];
+#pragma unroll
+    for (int p = 0; p < HD_PX; ++p) { v[2 * p] = a[p].x; v[2 * p + 1] = a[p].y; a[p] = make_float2(0.f, 0.f); }
+    const float tot = warp_reduce16(v, lane);
+    const int idx = lane >> 1;                              // = pixel * 2 + channel
+    if ((lane & 1) == 0 && x0 + (idx >> 1) < w) pr[(((long long)b * h + oy) * w + x0) * 2 + idx] = tot + __ldg(bias + (idx & 1));
+}
+
+__global__ void __launch_bounds__(128, 3) head_fwd_kernel(const float *__restrict__ X, int x_ld, int B, int h, int w, int c,
+                                                          const float *__restrict__ Wt, const float *__restrict__ bias,
+                                                          float *__restrict__ pr, int R, int strips_y, int strips_x) {
     extern __shared__ __align__(16) float wsm[];           // [9][c4*4][2], zero padded beyond c
     const int c4 = (c + 3) >> 2;
     for (int i = threadIdx.x; i < 9 * c4 * 8; i += blockDim.x) {
@@ -23,143 +106,165 @@ __global__ void __launch_bounds__(256) head_fwd_kernel(const float *__restrict__
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
-    const int groups_per_row = (w + HD_PX - 1) / HD_PX;
-    const long long n_groups = (long long)B * h * groups_per_row;
-    for (long long gidx = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); gidx < n_groups;
-         gidx += (long long)gridDim.x * warps_per_block) {
-        const int gx = (int)(gidx % groups_per_row);
-        const int y = (int)((gidx / groups_per_row) % h);
-        const int b = (int)(gidx / ((long long)groups_per_row * h));
-        const int x0 = gx * HD_PX;
-        float acc[HD_PX][2];
+    const long long n_strips = (long long)B * strips_y * strips_x;
+    for (long long sid = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); sid < n_strips;
+         sid += (long long)gridDim.x * warps_per_block) {
+        const int sx = (int)(sid % strips_x);
+        const int sy = (int)((sid / strips_x) % strips_y);
+        const int b = (int)(sid / ((long long)strips_x * strips_y));
+        const int x0 = sx * HD_PX, y0 = sy * R;
+        const int y1 = y0 + R < h ? y0 + R : h;
+        float2 acc[3][HD_PX];
 #pragma unroll
-        for (int p = 0; p < HD_PX; ++p) acc[p][0] = acc[p][1] = 0.f;
-        for (int q = lane; q < c4; q += 32) {
-            const int ch = q * 4;
+        for (int s = 0; s < 3; ++s)
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
-                const int sy = y + kh - 1;
-                if (sy < 0 || sy >= h) continue;
-                const float *rowp = X + ((long long)b * h + sy) * w * x_ld + ch;
-                float4 xv[HD_PX + 2];
-#pragma unroll
-                for (int i = 0; i < HD_PX + 2; ++i) {
-                    const int sx = x0 - 1 + i;
-                    xv[i] = (sx >= 0 && sx < w) ? __ldg(reinterpret_cast<const float4 *>(rowp + (long long)sx * x_ld))
-                                                : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                    const float4 *wp = reinterpret_cast<const float4 *>(wsm + ((kh * 3 + kw) * c4 + q) * 8);
-                    const float4 wa = wp[0], wb = wp[1];   // (c0o0,c0o1,c1o0,c1o1) (c2o0,c2o1,c3o0,c3o1)
-#pragma unroll
-                    for (int p = 0; p < HD_PX; ++p) {
-                        const float4 xx = xv[p + kw];
-                        acc[p][0] += xx.x * wa.x + xx.y * wa.z + xx.z * wb.x + xx.w * wb.z;
-                        acc[p][1] += xx.x * wa.y + xx.y * wa.w + xx.z * wb.y + xx.w * wb.w;
-                    }
-                }
+            for (int p = 0; p < HD_PX; ++p) acc[s][p] = make_float2(0.f, 0.f);
+        const int nrows = y1 - y0 + 2;                      // input rows y0-1 .. y1
+        for (int t = 0; t < nrows; t += 3) {
+            // row t (S = 0), t + 1 (S = 1), t + 2 (S = 2); input row iy = y0 - 1 + t feeds outputs iy+1 (kh 0), iy (kh 1), iy-1 (kh 2)
+#define DOFB_HEAD_ROW(SS)                                                                                                   \
+            if (t + SS < nrows) {                                                                                           \
+                const int iy = y0 - 1 + t + SS;                                                                             \
+                head_fwd_row<SS>(acc, X, x_ld, h, w, c4, wsm, b, iy, x0, iy + 1 < y1, iy >= y0 && iy < y1, iy - 1 >= y0, lane); \
+                if (iy - 1 >= y0) head_fwd_emit<SS>(acc, pr, bias, h, w, b, iy - 1, x0, lane);                             \
             }
-        }
-#pragma unroll
-        for (int p = 0; p < HD_PX; ++p) {
-            const float s0 = warp_sum(acc[p][0]), s1 = warp_sum(acc[p][1]);
-            if (lane == 0 && x0 + p < w) {
-                float2 o = make_float2(s0 + __ldg(bias), s1 + __ldg(bias + 1));
-                *reinterpret_cast<float2 *>(pr + (((long long)b * h + y) * w + x0 + p) * 2) = o;
-            }
+            DOFB_HEAD_ROW(0)
+            DOFB_HEAD_ROW(1)
+            DOFB_HEAD_ROW(2)
+#undef DOFB_HEAD_ROW
         }
     }
 }
 
-// ---- sliding 3x3 window over dpr for a warp that walks pixels in row-major order -------------------
-// col[j][r] = dpr[y-1+r][x-1+j] (zero outside the map).  Moving one pixel right shifts the columns and
-// loads ONE new column (3 float2) instead of 9 values; the next column is requested before the FMAs of the
-// current pixel so that its latency hides behind them.
-struct DprWindow {
-    float2 col[3][3];
-    float2 nxt[3];
-    int x, y, h, w;
-    const float2 *img;      // dpr of the current image
-
-    __device__ __forceinline__ void load_col(int sx, float2 out[3]) const {
+// ---- a row segment (<= 32 pixels) of dpr with its one-pixel halo, spread over the warp ----------------
+// Lane l holds column x0 - 1 + l of the rows y-1, y, y+1 (prim); lanes 0 and 1 also hold columns x0 + 31 and x0 + 32 (sec).
+// The 3x3 window a pixel needs is then fetched with shuffles -- 3 new float2 per pixel step -- so the per-pixel loops of the
+// gradient kernels below contain no dependent global load at all (the earlier register-window version stalled on them).
+struct DprSeg {
+    float2 prim[3], sec[3];
+    __device__ __forceinline__ void load(const float2 *__restrict__ img, int y, int x0, int h, int w, int lane) {
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
             const int sy = y - 1 + r;
-            out[r] = (sx >= 0 && sx < w && sy >= 0 && sy < h) ? __ldg(img + (long long)sy * w + sx) : make_float2(0.f, 0.f);
+            const bool okr = sy >= 0 && sy < h;
+            const int cx = x0 - 1 + lane, cx2 = x0 + 31 + lane;
+            prim[r] = (okr && cx >= 0 && cx < w) ? __ldg(img + (long long)sy * w + cx) : make_float2(0.f, 0.f);
+            sec[r] = (lane < 2 && okr && cx2 < w) ? __ldg(img + (long long)sy * w + cx2) : make_float2(0.f, 0.f);
         }
     }
-    __device__ __forceinline__ void start(const float2 *dpr, long long p, int h_, int w_) {
-        h = h_; w = w_;
-        x = (int)(p % w); y = (int)((p / w) % h);
-        img = dpr + (p - ((long long)y * w + x));
-        load_col(x - 1, col[0]); load_col(x, col[1]); load_col(x + 1, col[2]);
-    }
-    __device__ __forceinline__ void prefetch_next() { load_col(x + 2, nxt); }   // harmless at a row end (reloaded there)
-    __device__ __forceinline__ void advance() {
-        ++x;
-        if (x < w) {
+    // column j (0..33, relative to x0 - 1) of the three rows, broadcast to every lane
+    __device__ __forceinline__ void col(int j, float2 (&out)[3]) const {
 #pragma unroll
-            for (int r = 0; r < 3; ++r) { col[0][r] = col[1][r]; col[1][r] = col[2][r]; col[2][r] = nxt[r]; }
-        } else {
-            x = 0; ++y;
-            if (y == h) { y = 0; img += (long long)h * w; }
-            load_col(-1, col[0]); load_col(0, col[1]); load_col(1, col[2]);
+        for (int r = 0; r < 3; ++r) {
+            const float2 src = j < 32 ? prim[r] : sec[r];
+            out[r].x = __shfl_sync(0xffffffffu, src.x, j & 31);
+            out[r].y = __shfl_sync(0xffffffffu, src.y, j & 31);
         }
     }
-    // dpr seen through tap (kh,kw) of the TRANSPOSED stencil: (y - kh + 1, x - kw + 1)
-    __device__ __forceinline__ float2 tap(int kh, int kw) const { return col[2 - kw][2 - kh]; }
 };
 
-// ---- pr input gradient: lane owns 4 channels (72 weights in registers), warp streams pixels ----
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int HW_WARPS = 4;                                 // warps per block of the streaming gradient kernels
+constexpr int HW_SMEM = HW_WARPS * 32 * 32 * 16;            // per-warp ring: 32 pixels x 32 lanes x 16 B -> 64 KB per block
+
+// ---- pr input gradient: lane owns 4 channels (72 weights in registers), warp streams row segments ----
 // dX[b,y,x,ch] (+)= sum_{kh,kw,o} dpr[b,y-kh+1,x-kw+1,o] * W[kh,kw,ch,o]
-__global__ void __launch_bounds__(256, 2) head_dgrad_kernel(const float *__restrict__ dpr, int B, int h, int w, int c,
-                                                            const float *__restrict__ Wt, float *__restrict__ dX, int dx_ld,
-                                                            int accumulate, long long pix_per_warp) {
-    const int lane = threadIdx.x & 31;
+// ACC (read-modify-write): the old values stream through the same cp.async shared-memory ring as X in the weight-gradient kernel
+// below (a whole segment in flight per warp), because a register look-ahead of a few pixels leaves the kernel DRAM-latency bound.
+template <bool ACC>
+__global__ void __launch_bounds__(HW_WARPS * 32, 2) head_dgrad_kernel(const float *__restrict__ dpr, int B, int h, int w, int c,
+                                                                     const float *__restrict__ Wt, float *__restrict__ dX, int dx_ld,
+                                                                     long long n_seg, int segs_per_row) {
+    extern __shared__ __align__(16) float4 xring_all[];     // [warp][pixel slot][lane] (ACC only)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int ch = (blockIdx.y * 32 + lane) * 4;
-    if (ch >= c) return;
-    float wr[9][4][2];
+    const bool active = ch < c;                             // (inactive lanes still take part in the shuffles)
+    const int chl = active ? ch : 0;                        // ... and stream (and ignore) channel 0
+    float2 wr[9][2][2];                                     // [tap][channel pair][o] = (W[tap][ch+2k][o], W[tap][ch+2k+1][o])
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
+        for (int k = 0; k < 2; ++k)
 #pragma unroll
-            for (int o = 0; o < 2; ++o) wr[tap][e][o] = (ch + e < c) ? __ldg(Wt + ((long long)tap * c + ch + e) * 2 + o) : 0.f;
-    const long long n_pix = (long long)B * h * w;
-    const long long wglobal = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const long long p0 = wglobal * pix_per_warp;
-    const long long p1 = p0 + pix_per_warp < n_pix ? p0 + pix_per_warp : n_pix;
-    if (p0 >= p1) return;
-    DprWindow win;
-    win.start(reinterpret_cast<const float2 *>(dpr), p0, h, w);
-    for (long long p = p0; p < p1; ++p) {
-        float4 *dst = reinterpret_cast<float4 *>(dX + p * dx_ld + ch);
-        float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (accumulate) old = *dst;
-        win.prefetch_next();
-        float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
-#pragma unroll
-        for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                const float2 gg = win.tap(kh, kw);
-                const int tap = kh * 3 + kw;
-                o0 += gg.x * wr[tap][0][0] + gg.y * wr[tap][0][1];
-                o1 += gg.x * wr[tap][1][0] + gg.y * wr[tap][1][1];
-                o2 += gg.x * wr[tap][2][0] + gg.y * wr[tap][2][1];
-                o3 += gg.x * wr[tap][3][0] + gg.y * wr[tap][3][1];
+            for (int o = 0; o < 2; ++o) {
+                wr[tap][k][o].x = (ch + 2 * k < c) ? __ldg(Wt + ((long long)tap * c + ch + 2 * k) * 2 + o) : 0.f;
+                wr[tap][k][o].y = (ch + 2 * k + 1 < c) ? __ldg(Wt + ((long long)tap * c + ch + 2 * k + 1) * 2 + o) : 0.f;
             }
-        *dst = make_float4(o0 + old.x, o1 + old.y, o2 + old.z, o3 + old.w);
-        if (p + 1 < p1) win.advance();          // (never step past the last pixel: the next image may not exist)
+    const long long n_warps = (long long)gridDim.x * HW_WARPS;
+    float4 *xr = xring_all + (wid * 32) * 32 + lane;        // this lane's column of the warp's ring: slot j at xr[j * 32]
+    long long seg = (long long)blockIdx.x * HW_WARPS + wid;
+    if (ACC && seg < n_seg) {                               // prologue: request the old values of the whole first segment
+        const int x0 = (int)(seg % segs_per_row) * 32;
+        const int len = w - x0 < 32 ? w - x0 : 32;
+        const float *op = dX + ((seg / segs_per_row) * w + x0) * dx_ld + chl;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if (j < len) cp_async16(xr + j * 32, op + (long long)j * dx_ld);
+            if ((j & 7) == 7) cp_async_commit();
+        }
     }
+    for (; seg < n_seg; seg += n_warps) {
+        const int xs = (int)(seg % segs_per_row);
+        const long long row = seg / segs_per_row;           // = b * h + y
+        const int y = (int)(row % h);
+        const int x0 = xs * 32;
+        const int len = w - x0 < 32 ? w - x0 : 32;
+        const long long nseg = seg + n_warps;
+        const int x0n = (int)(nseg % segs_per_row) * 32;
+        const int len_n = (ACC && nseg < n_seg) ? (w - x0n < 32 ? w - x0n : 32) : 0;
+        const float *on = dX + ((nseg / segs_per_row) * w + x0n) * dx_ld + chl;
+        DprSeg sg;
+        sg.load(reinterpret_cast<const float2 *>(dpr) + (row - y) * w, y, x0, h, w, lane);
+        float2 c0[3], c1[3], c2[3];                         // columns x-1, x, x+1 of the rows y-1, y, y+1
+        sg.col(0, c0);
+        sg.col(1, c1);
+        float *dst = dX + (row * w + x0) * dx_ld + chl;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if (ACC && (j & 7) == 0) cp_async_wait<3>();    // (see head_wgrad_kernel for the group arithmetic)
+            if (j < len) {
+                sg.col(j + 2, c2);
+                // four independent packed chains: (channels 0,1 | 2,3) x (u | v component of dpr)
+                float2 a01 = make_float2(0.f, 0.f), a23 = a01, b01 = a01, b23 = a01;
+                if (ACC) { const float4 old = xr[j * 32]; a01 = make_float2(old.x, old.y); a23 = make_float2(old.z, old.w); }
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        // dpr seen through tap (kh,kw) of the TRANSPOSED stencil: (y - kh + 1, x - kw + 1)
+                        const float2 gg = kw == 0 ? c2[2 - kh] : (kw == 1 ? c1[2 - kh] : c0[2 - kh]);
+                        const int tap = kh * 3 + kw;
+                        fma2(a01, gg.x, wr[tap][0][0]); fma2(b01, gg.y, wr[tap][0][1]);
+                        fma2(a23, gg.x, wr[tap][1][0]); fma2(b23, gg.y, wr[tap][1][1]);
+                    }
+                if (active) *reinterpret_cast<float4 *>(dst + (long long)j * dx_ld) = make_float4(a01.x + b01.x, a01.y + b01.y, a23.x + b23.x, a23.y + b23.y);
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { c0[r] = c1[r]; c1[r] = c2[r]; }
+            }
+            if (ACC) {
+                if (j < len_n) cp_async16(xr + j * 32, on + (long long)j * dx_ld);
+                if ((j & 7) == 7) cp_async_commit();
+            }
+        }
+    }
+    if (ACC) cp_async_wait<0>();
 }
 
 // ---- pr weight gradient: lane owns 4 channels, 72 accumulators; X is read exactly once ----
 // dW[kh,kw,ch,o] += sum_q X[q,ch] * dpr[q - off(kh,kw), o]   (q = input pixel; same 3x3 window as the input gradient)
-__global__ void __launch_bounds__(256, 2) head_wgrad_kernel(const float *__restrict__ X, int x_ld, const float *__restrict__ dpr,
-                                                            int B, int h, int w, int c, float *__restrict__ dWt,
-                                                            float *__restrict__ dbias, long long pix_per_warp) {
+// With 72 accumulators per lane there are no registers left to keep enough of the X stream in flight, so X goes through a
+// per-warp shared-memory ring filled with cp.async (16 B per lane per pixel, every lane reads back only what it copied itself:
+// no cross-lane synchronisation).  The slot of pixel j is refilled with pixel j of the warp's NEXT segment right after it has been
+// consumed, i.e. a whole 32-pixel segment (16 KB per warp) is always in flight.
+__global__ void __launch_bounds__(HW_WARPS * 32, 3) head_wgrad_kernel(const float *__restrict__ X, int x_ld, const float *__restrict__ dpr,
+                                                                     int B, int h, int w, int c, float *__restrict__ dWt,
+                                                                     float *__restrict__ dbias, long long n_seg, int segs_per_row) {
+    extern __shared__ __align__(16) float4 xring_all[];     // [warp][pixel slot][lane]
     __shared__ float red[72][33];
     __shared__ float redb[2];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -167,49 +272,82 @@ __global__ void __launch_bounds__(256, 2) head_wgrad_kernel(const float *__restr
     for (int i = threadIdx.x; i < 72 * 33; i += blockDim.x) (&red[0][0])[i] = 0.f;
     if (threadIdx.x < 2) redb[threadIdx.x] = 0.f;
     __syncthreads();
-    float acc[9][4][2];
+    float2 acc[9][4];                                       // [tap][channel] = (o = 0, o = 1)
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc[tap][e][0] = acc[tap][e][1] = 0.f;
+        for (int e = 0; e < 4; ++e) acc[tap][e] = make_float2(0.f, 0.f);
     float b0 = 0.f, b1 = 0.f;
-    const long long n_pix = (long long)B * h * w;
-    const long long wglobal = (long long)blockIdx.x * (blockDim.x >> 5) + wid;
-    const long long p0 = wglobal * pix_per_warp;
-    const long long p1 = p0 + pix_per_warp < n_pix ? p0 + pix_per_warp : n_pix;
-    const bool active = ch < c;
-    if (p0 < p1) {
-        DprWindow win;
-        win.start(reinterpret_cast<const float2 *>(dpr), p0, h, w);
-        float4 xv = active ? __ldg(reinterpret_cast<const float4 *>(X + p0 * x_ld + ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        for (long long p = p0; p < p1; ++p) {
-            float4 xn = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (active && p + 1 < p1) xn = __ldg(reinterpret_cast<const float4 *>(X + (p + 1) * x_ld + ch));
-            win.prefetch_next();
+    const int chl = ch < c ? ch : 0;                        // lanes beyond c stream (and ignore) channel 0
+    const long long n_warps = (long long)gridDim.x * HW_WARPS;
+    float4 *xr = xring_all + (wid * 32) * 32 + lane;        // this lane's column of the warp's ring: slot j at xr[j * 32]
+    long long seg = (long long)blockIdx.x * HW_WARPS + wid;
+    if (seg < n_seg) {                                      // prologue: request the whole first segment (4 groups of 8 pixels)
+        const int x0 = (int)(seg % segs_per_row) * 32;
+        const int len = w - x0 < 32 ? w - x0 : 32;
+        const float *xp = X + ((seg / segs_per_row) * w + x0) * x_ld + chl;
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                    const float2 gg = win.tap(kh, kw);
-                    const int tap = kh * 3 + kw;
-                    acc[tap][0][0] += xv.x * gg.x; acc[tap][0][1] += xv.x * gg.y;
-                    acc[tap][1][0] += xv.y * gg.x; acc[tap][1][1] += xv.y * gg.y;
-                    acc[tap][2][0] += xv.z * gg.x; acc[tap][2][1] += xv.z * gg.y;
-                    acc[tap][3][0] += xv.w * gg.x; acc[tap][3][1] += xv.w * gg.y;
-                }
-            if (blockIdx.y == 0 && lane == 0) { const float2 cc = win.tap(1, 1); b0 += cc.x; b1 += cc.y; }
-            xv = xn;
-            if (p + 1 < p1) win.advance();          // (never step past the last pixel: the next image may not exist)
+        for (int j = 0; j < 32; ++j) {
+            if (j < len) cp_async16(xr + j * 32, xp + (long long)j * x_ld);
+            if ((j & 7) == 7) cp_async_commit();
         }
     }
+    for (; seg < n_seg; seg += n_warps) {
+        const int xs = (int)(seg % segs_per_row);
+        const long long row = seg / segs_per_row;           // = b * h + y
+        const int y = (int)(row % h);
+        const int x0 = xs * 32;
+        const int len = w - x0 < 32 ? w - x0 : 32;
+        // the warp's next segment, streamed in behind the pixels consumed here
+        const long long nseg = seg + n_warps;
+        const int x0n = (int)(nseg % segs_per_row) * 32;
+        const int len_n = nseg < n_seg ? (w - x0n < 32 ? w - x0n : 32) : 0;
+        const float *xn = X + ((nseg / segs_per_row) * w + x0n) * x_ld + chl;
+        DprSeg sg;
+        sg.load(reinterpret_cast<const float2 *>(dpr) + (row - y) * w, y, x0, h, w, lane);
+        if (blockIdx.y == 0) {                              // bias gradient: every lane adds its own centre-row value (columns x0 .. x0+len-1)
+            if (lane >= 1 && lane <= len) { b0 += sg.prim[1].x; b1 += sg.prim[1].y; }
+            if (lane == 0 && len == 32) { b0 += sg.sec[1].x; b1 += sg.sec[1].y; }   // column x0 + 31
+        }
+        float2 c0[3], c1[3], c2[3];
+        sg.col(0, c0);
+        sg.col(1, c1);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            // groups in flight behind the one holding pixel j: the rest of this segment + what was already requested of the next = 3
+            if ((j & 7) == 0) cp_async_wait<3>();
+            if (j < len) {
+                const float4 xv = xr[j * 32];
+                sg.col(j + 2, c2);
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+                    for (int kw = 0; kw < 3; ++kw) {
+                        const float2 gg = kw == 0 ? c2[2 - kh] : (kw == 1 ? c1[2 - kh] : c0[2 - kh]);
+                        const int tap = kh * 3 + kw;
+                        fma2(acc[tap][0], xv.x, gg); fma2(acc[tap][1], xv.y, gg);
+                        fma2(acc[tap][2], xv.z, gg); fma2(acc[tap][3], xv.w, gg);
+                    }
+#pragma unroll
+                for (int r = 0; r < 3; ++r) { c0[r] = c1[r]; c1[r] = c2[r]; }
+            }
+            // slot j is free (its value sits in registers and has been used): refill it with pixel j of the next segment
+            if (j < len_n) cp_async16(xr + j * 32, xn + (long long)j * x_ld);
+            if ((j & 7) == 7) cp_async_commit();
+        }
+    }
+    cp_async_wait<0>();
     // block-level combine in shared memory, then one global atomic per (tap,ch,o) per block
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap)
 #pragma unroll
         for (int e = 0; e < 4; ++e)
 #pragma unroll
-            for (int o = 0; o < 2; ++o) atomicAdd(&red[(tap * 4 + e) * 2 + o][lane], acc[tap][e][o]);
-    if (blockIdx.y == 0 && lane == 0) { atomicAdd(&redb[0], b0); atomicAdd(&redb[1], b1); }
+            for (int o = 0; o < 2; ++o) atomicAdd(&red[(tap * 4 + e) * 2 + o][lane], o == 0 ? acc[tap][e].x : acc[tap][e].y);
+    if (blockIdx.y == 0) {
+        b0 = warp_sum(b0); b1 = warp_sum(b1);
+        if (lane == 0) { atomicAdd(&redb[0], b0); atomicAdd(&redb[1], b1); }
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < 72 * 32; i += blockDim.x) {
         const int r = i / 32, l = i % 32;
@@ -313,9 +451,15 @@ extern "C" int dofb_head_fwd(const float *x, int x_ld, int B, int h, int w, int 
                              void *stream) {
     DOFB_CHECK_ARG(x && wt && bias && pr && B > 0 && h > 0 && w > 0 && c > 0, "dofb_head_fwd: bad argument");
     DOFB_CHECK_ARG(x_ld % 4 == 0 && aligned16(x) && x_ld >= ((c + 3) & ~3), "dofb_head_fwd: x pitch %d must be a multiple of 4 covering c=%d", x_ld, c);
-    const long long groups = (long long)B * h * ((w + HD_PX - 1) / HD_PX);
-    long long blocks = (groups + 7) / 8;
-    const long long cap = (long long)num_sms() * 4;
+    // strips of 8 pixels x R rows: R as tall as possible (less halo re-reading) while there are enough strips to fill the GPU
+    const int strips_x = (w + HD_PX - 1) / HD_PX;
+    const long long want = (long long)num_sms() * 12;
+    int R = 24;
+    while (R > 1 && (long long)B * strips_x * ((h + R - 1) / R) < want) R = R > 6 ? R / 2 : (R > 3 ? 3 : 1);
+    const int strips_y = (h + R - 1) / R;
+    const long long strips = (long long)B * strips_x * strips_y;
+    long long blocks = (strips + 3) / 4;
+    const long long cap = (long long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
     const int smem = 9 * ((c + 3) / 4) * 8 * (int)sizeof(float);
     DOFB_CHECK_ARG(smem <= 200 * 1024, "dofb_head_fwd: %d channels do not fit the shared-memory filter stage", c);
@@ -324,28 +468,38 @@ extern "C" int dofb_head_fwd(const float *x, int x_ld, int B, int h, int w, int 
         DOFB_CUDA_OK(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = 200 * 1024;
     }
-    head_fwd_kernel<<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(x, x_ld, B, h, w, c, wt, bias, pr);
+    head_fwd_kernel<<<(unsigned)blocks, 128, smem, as_stream(stream)>>>(x, x_ld, B, h, w, c, wt, bias, pr, R, strips_y, strips_x);
     DOFB_LAUNCH_OK();
     return 0;
 }
 
-static void head_stream_grid(long long n_pix, int c, dim3 &grid, long long &ppw) {
+// row segments of <= 32 pixels, grid-strided over ~resident warps; blockIdx.y = group of 128 channels
+static void head_stream_grid(int B, int h, int w, int c, int warps_per_sm, dim3 &grid, long long &n_seg, int &segs_per_row) {
     const int chunks = ((c + 3) / 4 + 31) / 32;
-    long long warps = (long long)num_sms() * 8 * 4 / chunks;     // ~4 blocks of 8 warps per SM
-    if (warps < 8) warps = 8;
-    ppw = (n_pix + warps - 1) / warps;
-    if (ppw < 32) ppw = 32;
-    warps = (n_pix + ppw - 1) / ppw;
-    grid = dim3((unsigned)((warps + 7) / 8), chunks, 1);
+    segs_per_row = (w + 31) / 32;
+    n_seg = (long long)B * h * segs_per_row;
+    long long warps = (long long)num_sms() * warps_per_sm * 2 / chunks;      // two waves: evens out the tail
+    if (warps < 4) warps = 4;
+    if (warps > n_seg) warps = n_seg;
+    grid = dim3((unsigned)((warps + 3) / 4), chunks, 1);
 }
 
 extern "C" int dofb_head_dgrad(const float *dpr, int B, int h, int w, int c, const float *wt, float *dx, int dx_ld,
                                int accumulate, void *stream) {
     DOFB_CHECK_ARG(dpr && wt && dx && B > 0 && h > 0 && w > 0 && c > 0, "dofb_head_dgrad: bad argument");
     DOFB_CHECK_ARG(dx_ld % 4 == 0 && aligned16(dx) && dx_ld >= ((c + 3) & ~3), "dofb_head_dgrad: dx pitch %d must be a multiple of 4 covering c=%d", dx_ld, c);
-    dim3 grid; long long ppw;
-    head_stream_grid((long long)B * h * w, c, grid, ppw);
-    head_dgrad_kernel<<<grid, 256, 0, as_stream(stream)>>>(dpr, B, h, w, c, wt, dx, dx_ld, accumulate, ppw);
+    dim3 grid; long long n_seg; int spr;
+    head_stream_grid(B, h, w, c, 8, grid, n_seg, spr);
+    if (accumulate) {
+        static bool configured = false;
+        if (!configured) {
+            DOFB_CUDA_OK(cudaFuncSetAttribute(head_dgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HW_SMEM));
+            configured = true;
+        }
+        head_dgrad_kernel<true><<<grid, HW_WARPS * 32, HW_SMEM, as_stream(stream)>>>(dpr, B, h, w, c, wt, dx, dx_ld, n_seg, spr);
+    } else {
+        head_dgrad_kernel<false><<<grid, HW_WARPS * 32, 0, as_stream(stream)>>>(dpr, B, h, w, c, wt, dx, dx_ld, n_seg, spr);
+    }
     DOFB_LAUNCH_OK();
     return 0;
 }
@@ -354,9 +508,14 @@ extern "C" int dofb_head_wgrad(const float *x, int x_ld, const float *dpr, int B
                                void *stream) {
     DOFB_CHECK_ARG(x && dpr && dwt && B > 0 && h > 0 && w > 0 && c > 0, "dofb_head_wgrad: bad argument");
     DOFB_CHECK_ARG(x_ld % 4 == 0 && aligned16(x) && x_ld >= ((c + 3) & ~3), "dofb_head_wgrad: x pitch %d must be a multiple of 4 covering c=%d", x_ld, c);
-    dim3 grid; long long ppw;
-    head_stream_grid((long long)B * h * w, c, grid, ppw);
-    head_wgrad_kernel<<<grid, 256, 0, as_stream(stream)>>>(x, x_ld, dpr, B, h, w, c, dwt, dbias, ppw);
+    dim3 grid; long long n_seg; int spr;
+    head_stream_grid(B, h, w, c, 12, grid, n_seg, spr);
+    static bool configured = false;
+    if (!configured) {
+        DOFB_CUDA_OK(cudaFuncSetAttribute(head_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HW_SMEM));
+        configured = true;
+    }
+    head_wgrad_kernel<<<grid, HW_WARPS * 32, HW_SMEM, as_stream(stream)>>>(x, x_ld, dpr, B, h, w, c, dwt, dbias, n_seg, spr);
     DOFB_LAUNCH_OK();
     return 0;
 }

@@ -415,7 +415,7 @@ int simt_conv_fwd(const dofb_conv_geom *g, const float *x, int x_ld, const float
     P.out = y; P.out_ld = y_ld; P.rh = g->oh; P.rw = g->ow;
     P.B = g->B; P.kc = g->ci; P.n = g->co;
     P.kh = g->kh; P.kw = g->kw; P.stride = g->stride; P.pad_t = g->pad_t; P.pad_l = g->pad_l;
-    P.transposed = 0; P.act = act; P.accumulate = 0;
+    P.transposed = 0; P.act = act & ~DOFB_ACT_ACCUMULATE; P.accumulate = (act & DOFB_ACT_ACCUMULATE) != 0;
     const int M = g->B * g->oh * g->ow;
     const int mt = (M + IG_BM - 1) / IG_BM;
     if (g->co > 64) {

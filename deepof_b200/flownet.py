@@ -404,7 +404,8 @@ class FlowNetS:
             self._k("deconv_wgrad:" + R["up"], ops.conv_wgrad, R["g"], R["up_dy"], x, G[R["up"] + "/weights"], None, mthw)
             self._k("deconv_dgrad:" + R["up"], ops.conv_fwd, R["g"], R["up_dy"], P[R["up"] + "/weights"], None, dx, ACT_NONE,
                     mth)                                                   # first writer of d feat_s
-            # pr_s head
+            # pr_s head (its read-modify-write of d feat_s streams through a cp.async ring; measured faster than letting the GEMM
+            # epilogue of the deconv accumulate behind a pure-store head: 11.56 vs 11.76 ms per step)
             self._k(f"head_wgrad:pr{s}", ops.head_wgrad, x, self.dpr[s], G[f"pr{s}/weights"], G[f"pr{s}/biases"])
             self._k(f"head_dgrad:pr{s}", ops.head_dgrad, self.dpr[s], P[f"pr{s}/weights"], dx, accumulate=True)
             self._grad_ready(reducer, f"pr{s}", R["up"], R["uppr"])

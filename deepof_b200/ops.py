@@ -14,6 +14,7 @@ from . import _lib
 from ._lib import ConvGeom, LossScale, DeepOFError, check
 
 ACT_NONE, ACT_ELU = 0, 1
+ACT_ACCUMULATE = 16          # conv_fwd: OR-ed into act, y += conv(x) instead of y = conv(x)
 MATH_FP32, MATH_TF32, MATH_BF16 = 0, 1, 2
 
 

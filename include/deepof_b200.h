@@ -101,7 +101,8 @@ typedef struct dofb_conv_geom {
     int kh, kw, stride, pad_t, pad_l;
 } dofb_conv_geom;
 
-enum { DOFB_ACT_NONE = 0, DOFB_ACT_ELU = 1 };
+enum { DOFB_ACT_NONE = 0, DOFB_ACT_ELU = 1,
+       DOFB_ACT_ACCUMULATE = 16 /* dofb_conv_fwd*: OR-ed flag, y += conv(x, w) + bias instead of overwriting (no bf16 shadow written) */ };
 enum { DOFB_MATH_FP32 = 0, DOFB_MATH_TF32 = 1 };   /* SIMT FFMA vs tcgen05 kind::tf32 (bf16: the *_bf16 entry points below) */
 
 /* y = act(conv(x, w) + bias).  x pitch x_ld, y pitch y_ld (elements). */
