@@ -53,6 +53,8 @@ SIGNATURES = {
     "dofb_conv_wgrad_bf16": (_I, [_G, _P, _I, _P, _I, _P, _P]),
     "dofb_cast_bf16": (_I, [_P, _I, _P, _I, _LL, _I, _P]),
     "dofb_conv1_wgrad": (_I, [_G, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P]),
+    "dofb_conv1_fwd_bf16": (_I, [_G, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P]),
+    "dofb_conv1_wgrad_bf16": (_I, [_G, _P, _I, _I, _I, _I, _P, _I, _P, _P]),
     "dofb_warp_loss_workspace_bytes": (C.c_size_t, [_I, C.POINTER(LossScale)]),
     "dofb_warp_loss": (_I, [_I, C.POINTER(LossScale), _P, C.c_size_t, _P]),
     "dofb_conv_fwd": (_I, [_G, _P, _I, _P, _P, _P, _I, _I, _I, _P]),

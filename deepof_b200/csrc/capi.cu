@@ -20,9 +20,9 @@ int tc_conv_wgrad(const dofb_conv_geom *g, const float *x, int x_ld, const float
 void invalidate_weight_cache();
 void enable_weight_cache(int on);
 int tc_conv1_fwd(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *w, const float *bias,
-                 float *y, int y_ld, int act, cudaStream_t st, void *y16 = nullptr);
+                 float *y, int y_ld, int act, cudaStream_t st, void *y16 = nullptr, const void *x16 = nullptr);
 int tc_conv1_wgrad(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *dy, int dy_ld,
-                   float *dw, cudaStream_t st);
+                   float *dw, cudaStream_t st, const void *x16 = nullptr, const void *dy16 = nullptr);
 }  // namespace dofb
 
 using namespace dofb;
@@ -88,6 +88,18 @@ extern "C" int dofb_conv_wgrad_bf16(const dofb_conv_geom *g, const void *x_bf16,
                                     void *stream) {
     DOFB_CHECK_ARG(x_bf16 && dy_bf16 && dw && g, "dofb_conv_wgrad_bf16: null argument");
     return tc_conv_wgrad(g, nullptr, x_ld, nullptr, dy_ld, dw, as_stream(stream), x_bf16, dy_bf16);
+}
+
+extern "C" int dofb_conv1_fwd_bf16(const dofb_conv_geom *g, const void *x_bf16, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *w,
+                                   const float *bias, float *y, void *y_bf16, int y_ld, int act, void *stream) {
+    DOFB_CHECK_ARG(x_bf16, "dofb_conv1_fwd_bf16: null input");
+    return tc_conv1_fwd(g, nullptr, xp_h, xp_w, xp_y0, xp_x0, w, bias, y, y_ld, act, as_stream(stream), y_bf16, x_bf16);
+}
+
+extern "C" int dofb_conv1_wgrad_bf16(const dofb_conv_geom *g, const void *x_bf16, int xp_h, int xp_w, int xp_y0, int xp_x0,
+                                     const void *dy_bf16, int dy_ld, float *dw, void *stream) {
+    DOFB_CHECK_ARG(x_bf16 && dy_bf16, "dofb_conv1_wgrad_bf16: null operand");
+    return tc_conv1_wgrad(g, nullptr, xp_h, xp_w, xp_y0, xp_x0, nullptr, dy_ld, dw, as_stream(stream), x_bf16, dy_bf16);
 }
 
 extern "C" int dofb_conv1_wgrad(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *dy,

@@ -133,6 +133,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
     uint32_t r[8];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -171,6 +185,9 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 // gather-GEMM kernel
 // ------------------------------------------------------------------------------------------------
 constexpr int TC_BM = 128, TC_BK = 32, TC_THREADS = 192, TC_MAX_TAPS = 49;
+// gather-GEMM kernel: 8 epilogue warps (two per TMEM lane quadrant, alternating 16-column sub-chunks) + TMA producer + MMA issuer.
+// With 4 epilogue warps (one per scheduler, no latency hiding) every layer of the net was bound by the epilogue, not by the MMAs.
+constexpr int TCG_EPI_WARPS = 8, TCG_THREADS = (TCG_EPI_WARPS + 2) * 32, TCG_STG_BYTES = TCG_EPI_WARPS * 32 * 16 * 4;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 
 struct TapInfo {
@@ -208,7 +225,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // BF = true : bf16 shadows of the activations + bf16 packed weights (64 channels per K block, UMMA_K = 16): same bytes per stage,
 //             twice the MMA rate and twice the K per byte fetched from L2.  Accumulation and the epilogue stay fp32.
 template <int BN, int STAGES, bool BF>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TCG_THREADS, 1)
 tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ TcParams P) {
     constexpr int KELEMS = BF ? 64 : 32;             // channels per K block (128 bytes)
@@ -218,8 +235,8 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     constexpr int TMEM_COLS = 2 * ACC_COLS;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float *stage_f = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);                 // [4 warps][32][36] epilogue transpose tiles
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(stage_f + 4 * 32 * 36);
+    float *stage_f = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);                 // [8 warps][32 rows][16 floats] epilogue transpose tiles
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(stage_f + TCG_EPI_WARPS * 32 * 16);
     uint64_t *empty_bar = full_bar + STAGES;
     uint64_t *acc_full = empty_bar + STAGES;       // [2] MMA -> epilogue
     uint64_t *acc_empty = acc_full + 2;            // [2] epilogue -> MMA (4 warps arrive)
@@ -231,17 +248,17 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], TCG_EPI_WARPS); }
         fence_barrier_init();
     }
-    if (warp == 4 && lane == 0) { prefetch_tmap(&map_a); prefetch_tmap(&map_b); }
-    if (warp == 5) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == TCG_EPI_WARPS && lane == 0) { prefetch_tmap(&map_a); prefetch_tmap(&map_b); }
+    if (warp == TCG_EPI_WARPS + 1) tmem_alloc(tmem_slot, TMEM_COLS);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == TCG_EPI_WARPS) {
         // ===== TMA producer =====
         if (lane == 0) {
             int it = 0;                                   // running k-iteration count across tiles
@@ -266,7 +283,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == TCG_EPI_WARPS + 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
             constexpr uint32_t idesc = BF ? make_idesc_bf16(TC_BM, BN) : make_idesc_tf32(TC_BM, BN);
@@ -293,14 +310,19 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         }
     } else {
         // ===== epilogue: TMEM -> registers -> shared-memory transpose -> bias/ELU -> coalesced NHWC stores =====
-        // tcgen05.ld hands every thread one ROW of the tile (32 columns at a time); storing that directly would make each warp
-        // store instruction touch 32 different pixels (32 half-used sectors).  Each warp therefore stages its 32x32 block in a
-        // private shared-memory tile (pitch 36 floats: conflict-free float4 writes and reads) and re-reads it so that 8 lanes cover
-        // the 128 contiguous bytes of one output pixel: 4 pixels x 128 B per store instruction, bias and ELU applied per column quad.
-        const int r = warp * 32 + lane;                     // row of the tile == TMEM lane
-        float *stg = stage_f + warp * (32 * 36);
-        const int q = lane & 7, rsub = lane >> 3;           // this lane's column quad and row-within-group in the store phase
+        // tcgen05.ld hands every thread one ROW of the tile; storing that directly would make each warp store touch 32 different
+        // pixels.  Each warp therefore stages a 32-row x 16-column block in a private 2 KB shared-memory tile (XOR-swizzled 16-byte
+        // slots: conflict-free both ways) and re-reads it so that 4 lanes cover the 64 contiguous bytes of one output pixel.
+        // Warp w works on TMEM lanes (w & 3) * 32 .. +32 (the hardware's lane-quadrant rule) and on the sub-chunks of parity w >> 2.
+        // A tile whose 128 rows are all real pixels and whose BN columns are all valid (the common case) takes a fast path without
+        // any per-element predicate; the instruction count of this loop is what bounds the small-K layers.
+        constexpr int NSUB = BN / 16;
+        const int quad = warp & 3, half = warp >> 2;
+        const int r = quad * 32 + lane;                     // row of the tile == TMEM lane
+        float4 *stg = reinterpret_cast<float4 *>(stage_f) + warp * (32 * 4);
+        const int q = lane & 3, rsub = lane >> 2;           // store phase: this lane's column quad and row within a group of 8
         const bool out_al = ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0) && (P.out_ld % 4 == 0);
+        const bool elu = P.act == DOFB_ACT_ELU, has16 = P.out16 != nullptr, accum = P.accumulate != 0;
         int lt = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
             const int mt = t % m_tiles, nt = t / m_tiles;
@@ -310,91 +332,120 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             const bool row_ok = ix < P.cnt_x && iy < P.cnt_y && nn < P.B;
             // element offset of this thread's output pixel (-1: no pixel); fetched by the storing lanes through shuffles
             const long long my_off = row_ok ? (((long long)nn * P.rh + P.y0 + iy * P.rstep) * P.rw + P.x0 + ix * P.rstep) * P.out_ld : -1;
+            const bool fast = __all_sync(0xffffffffu, row_ok) && out_al && n0 + BN <= P.n_valid;
             const int acc = lt & 1;
-            // pixel offsets of the 8 rows this lane stores in every chunk, and (accumulate) the old values of chunk 0, requested
-            // BEFORE waiting for the accumulator so that their DRAM latency hides behind the MMAs still running
-            long long offs[8];
-            float4 olds[8], nxt[8];
+            // pixel offsets of the 4 rows this lane stores in every sub-chunk, and (accumulate) the old values of the first one,
+            // requested BEFORE waiting for the accumulator so that their DRAM latency hides behind the MMAs still running
+            long long offs[4];
+            float4 olds[4], nxt[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                offs[i] = __shfl_sync(0xffffffffu, my_off, i * 4 + rsub);
+            for (int i = 0; i < 4; ++i) {
+                offs[i] = __shfl_sync(0xffffffffu, my_off, i * 8 + rsub);
                 olds[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 nxt[i] = olds[i];
-                const int col0 = n0 + q * 4;
-                if (P.accumulate && out_al && offs[i] >= 0 && col0 + 3 < P.n_valid) olds[i] = *reinterpret_cast<const float4 *>(P.out + offs[i] + col0);
+                const int col0 = n0 + half * 16 + q * 4;
+                if (accum && out_al && offs[i] >= 0 && col0 + 3 < P.n_valid) olds[i] = *reinterpret_cast<const float4 *>(P.out + offs[i] + col0);
             }
             mbar_wait(&acc_full[acc], (lt >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int j = 0; j < BN / 32; ++j) {
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * ACC_COLS + j * 32), v);
-                const int cbase = n0 + j * 32;
+            for (int j = half; j < NSUB; j += 2) {
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * ACC_COLS + j * 16), v);
+                const int cbase = n0 + j * 16;
                 if (cbase >= P.n_valid) continue;           // (warp-uniform)
-                if (P.accumulate && j + 1 < BN / 32) {      // next chunk's old values in flight while this chunk is processed
+                if (accum && j + 2 < NSUB) {                // next sub-chunk's old values in flight while this one is processed
                     const int coln = cbase + 32 + q * 4;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < 4; ++i) {
                         nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (out_al && offs[i] >= 0 && coln + 3 < P.n_valid) nxt[i] = *reinterpret_cast<const float4 *>(P.out + offs[i] + coln);
                     }
                 }
+                // row `lane`, 16-byte slot c -> physical slot c ^ ((lane >> 1) & 3)
 #pragma unroll
-                for (int c = 0; c < 8; ++c)
-                    *reinterpret_cast<float4 *>(stg + lane * 36 + c * 4) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                for (int c = 0; c < 4; ++c)
+                    stg[lane * 4 + (c ^ ((lane >> 1) & 3))] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
                 __syncwarp();
                 const int col = cbase + q * 4;
-                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (P.bias != nullptr && col < P.n_valid) {
-                    if (col + 3 < P.n_valid) bv = __ldg(reinterpret_cast<const float4 *>(P.bias + col));
-                    else { bv.x = __ldg(P.bias + col); if (col + 1 < P.n_valid) bv.y = __ldg(P.bias + col + 1); if (col + 2 < P.n_valid) bv.z = __ldg(P.bias + col + 2); }
-                }
-                const bool vec = out_al && col + 3 < P.n_valid;
+                if (fast) {
+                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (P.bias != nullptr) bv = __ldg(reinterpret_cast<const float4 *>(P.bias + col));
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int rr = i * 4 + rsub;
-                    const long long off = offs[i];
-                    if (off < 0 || col >= P.n_valid) continue;
-                    float4 o = *reinterpret_cast<const float4 *>(stg + rr * 36 + q * 4);
-                    o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-                    if (P.act == DOFB_ACT_ELU) {            // fast ELU: exp via MUFU (absolute error ~1e-7, irrelevant next to TF32/BF16 operands)
-                        o.x = o.x > 0.f ? o.x : __expf(o.x) - 1.f; o.y = o.y > 0.f ? o.y : __expf(o.y) - 1.f;
-                        o.z = o.z > 0.f ? o.z : __expf(o.z) - 1.f; o.w = o.w > 0.f ? o.w : __expf(o.w) - 1.f;
-                    }
-                    float *dst = P.out + off + col;
-                    if (vec) {
-                        o.x += olds[i].x; o.y += olds[i].y; o.z += olds[i].z; o.w += olds[i].w;
-                        *reinterpret_cast<float4 *>(dst) = o;
-                        if (P.out16 != nullptr) {           // bf16 shadow for the next tensor-core consumer (same pitch, 8-byte store)
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = i * 8 + rsub;
+                        float4 o = stg[rr * 4 + (q ^ ((rr >> 1) & 3))];
+                        o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                        if (elu) {                          // fast ELU: exp via MUFU (absolute error ~1e-7, irrelevant next to TF32/BF16 operands)
+                            o.x = o.x > 0.f ? o.x : __expf(o.x) - 1.f; o.y = o.y > 0.f ? o.y : __expf(o.y) - 1.f;
+                            o.z = o.z > 0.f ? o.z : __expf(o.z) - 1.f; o.w = o.w > 0.f ? o.w : __expf(o.w) - 1.f;
+                        }
+                        if (accum) { o.x += olds[i].x; o.y += olds[i].y; o.z += olds[i].z; o.w += olds[i].w; }
+                        *reinterpret_cast<float4 *>(P.out + offs[i] + col) = o;
+                        if (has16) {                        // bf16 shadow for the next tensor-core consumer (same pitch, 8-byte store)
                             __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
                             uint2 pk;
                             pk.x = *reinterpret_cast<uint32_t *>(&lo);
                             pk.y = *reinterpret_cast<uint32_t *>(&hi);
-                            *reinterpret_cast<uint2 *>(P.out16 + off + col) = pk;
+                            *reinterpret_cast<uint2 *>(P.out16 + offs[i] + col) = pk;
                         }
-                    } else {
-                        const float ov[4] = {o.x, o.y, o.z, o.w};
+                    }
+                } else {
+                    // general path: edge tiles (missing pixels), partial column blocks, unaligned slabs
+                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (P.bias != nullptr && col < P.n_valid) {
+                        bv.x = __ldg(P.bias + col);
+                        if (col + 1 < P.n_valid) bv.y = __ldg(P.bias + col + 1);
+                        if (col + 2 < P.n_valid) bv.z = __ldg(P.bias + col + 2);
+                        if (col + 3 < P.n_valid) bv.w = __ldg(P.bias + col + 3);
+                    }
+                    const bool vec = out_al && col + 3 < P.n_valid;
 #pragma unroll
-                        for (int e = 0; e < 4; ++e)
-                            if (col + e < P.n_valid) {
-                                const float val = P.accumulate ? dst[e] + ov[e] : ov[e];
-                                dst[e] = val;
-                                if (P.out16 != nullptr) P.out16[off + col + e] = __float2bfloat16_rn(val);
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = i * 8 + rsub;
+                        const long long off = offs[i];
+                        if (off < 0 || col >= P.n_valid) continue;
+                        float4 o = stg[rr * 4 + (q ^ ((rr >> 1) & 3))];
+                        o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                        if (elu) {
+                            o.x = o.x > 0.f ? o.x : __expf(o.x) - 1.f; o.y = o.y > 0.f ? o.y : __expf(o.y) - 1.f;
+                            o.z = o.z > 0.f ? o.z : __expf(o.z) - 1.f; o.w = o.w > 0.f ? o.w : __expf(o.w) - 1.f;
+                        }
+                        float *dst = P.out + off + col;
+                        if (vec) {
+                            o.x += olds[i].x; o.y += olds[i].y; o.z += olds[i].z; o.w += olds[i].w;
+                            *reinterpret_cast<float4 *>(dst) = o;
+                            if (has16) {
+                                __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+                                uint2 pk;
+                                pk.x = *reinterpret_cast<uint32_t *>(&lo);
+                                pk.y = *reinterpret_cast<uint32_t *>(&hi);
+                                *reinterpret_cast<uint2 *>(P.out16 + off + col) = pk;
                             }
+                        } else {
+                            const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (col + e < P.n_valid) {
+                                    const float val = accum ? dst[e] + ov[e] : ov[e];
+                                    dst[e] = val;
+                                    if (has16) P.out16[off + col + e] = __float2bfloat16_rn(val);
+                                }
+                        }
                     }
                 }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) olds[i] = nxt[i];
+                for (int i = 0; i < 4; ++i) olds[i] = nxt[i];
                 __syncwarp();
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[acc]);    // this warp's quarter of the accumulator is free again
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);    // this warp's share of the accumulator is free again
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == TCG_EPI_WARPS + 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
@@ -537,7 +588,7 @@ static void choose_tile(int cnt_y, int cnt_x, int &TW, int &TH, int &TN) {
 
 template <int BN, int STAGES, bool BF = false>
 static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &Pin, int tiles, int n_tiles, cudaStream_t st) {
-    constexpr int smem = STAGES * (TC_A_BYTES + BN * TC_BK * 4) + 4 * 32 * 36 * 4 + 1024 + 256;
+    constexpr int smem = STAGES * (TC_A_BYTES + BN * TC_BK * 4) + TCG_STG_BYTES + 1024 + 256;
     static_assert(smem <= 227 * 1024, "shared-memory budget");
     static bool configured = false;
     if (!configured) {
@@ -548,7 +599,7 @@ static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcParam
     P.m_tiles = tiles; P.n_tiles = n_tiles;
     const long long total = (long long)tiles * n_tiles;
     const int grid = (int)(total < num_sms() ? total : num_sms());
-    tc_gather_gemm_kernel<BN, STAGES, BF><<<grid, TC_THREADS, smem, st>>>(ma, mb, P);
+    tc_gather_gemm_kernel<BN, STAGES, BF><<<grid, TCG_THREADS, smem, st>>>(ma, mb, P);
     DOFB_LAUNCH_OK();
     return 0;
 }
@@ -852,11 +903,12 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             uint8_t *sx = P.swap ? sb : sa, *sd = P.swap ? sa : sb;
             if (lane < x_blocks) {
                 const int j = lane;
-                if (!BF && P.conv1) {
-                    // region j = filter row 2*tapi + (j>>1), floats [(j&1)*32, +32) of its 8-pixel chunk
-                    const int kh = min(2 * tapi + (j >> 1), P.c1_kh - 1);      // (an odd kh count re-loads the last row; masked later)
+                if (P.conv1) {
+                    // tf32: region j = filter row 2*tapi + (j>>1), floats [(j&1)*32, +32) of its 8-pixel chunk;
+                    // bf16: region j = filter row 2*tapi + j, all 64 elements of the chunk
+                    const int kh = min(2 * tapi + (BF ? j : (j >> 1)), P.c1_kh - 1);   // (an odd kh count re-loads the last row; masked later)
                     const TapInfo tr = P.taps[kh];
-                    tma_load_5d(sx + j * REGION, &map_x, &full_bar[s], (j & 1) * 32, ix0, tr.py, iy0 + tr.oy, in0);
+                    tma_load_5d(sx + j * REGION, &map_x, &full_bar[s], BF ? 0 : (j & 1) * 32, ix0, tr.py, iy0 + tr.oy, in0);
                 } else {
                     TapInfo tr = ti;
                     int c0 = x_c0 + j * CH;
@@ -903,7 +955,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         for (int j = 0; j < BN / 32; ++j) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * 32), v);
-            if (!BF && P.conv1) {
+            if (P.conv1) {
                 const int kh = 2 * tapi + (r >> 6), kw = (r & 63) >> 3, ci = r & 7;
                 if (kh >= P.c1_kh || kw >= P.c1_kw || ci >= P.CI) continue;
                 float *dst = P.dW + (((long long)kh * P.c1_kw + kw) * P.CI + ci) * P.CO + n0 + j * 32;
@@ -1049,14 +1101,15 @@ int tc_conv_wgrad(const dofb_conv_geom *g, const float *x, int x_ld, const float
 
 // ------------------------------------------------------------------------------------------------
 // first layer (ci <= 8, stride 2, kw <= 8): one filter ROW = kw pixels x 8 channels = 64 contiguous floats of the
-// zero-bordered NHWC input -> K chunk of 64 (two 32-float TMA boxes); rank-5 map with OVERLAPPING rows:
+// zero-bordered NHWC input -> K chunk of 64 (two 32-float TMA boxes, or ONE 64-element box of the bf16 copy); rank-5 map with OVERLAPPING rows:
 //   d0 = 64 floats of the chunk, d1 = ox (stride 2 pixels = 64 B), d2 = row parity, d3 = row pair, d4 = image
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) pack_conv1_kernel(const float *__restrict__ W, float *__restrict__ Wp, int kh, int kw, int ci, int co) {
+template <typename T>
+__global__ void __launch_bounds__(256) pack_conv1_kernel(const float *__restrict__ W, T *__restrict__ Wp, int kh, int kw, int ci, int co) {
     const int total = co * kh * 64;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int c = i & 7, x = (i >> 3) & 7, r = (i >> 6) % kh, n = i / (64 * kh);
-        Wp[i] = (c < ci && x < kw) ? __ldg(W + (((long long)r * kw + x) * ci + c) * co + n) : 0.f;
+        Wp[i] = cvt_out<T>((c < ci && x < kw) ? __ldg(W + (((long long)r * kw + x) * ci + c) * co + n) : 0.f);
     }
 }
 
@@ -1065,7 +1118,7 @@ struct Conv1Map {
     TapInfo rows[8];
 };
 
-static int conv1_prepare(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, int TW, int TH, int TN,
+static int conv1_prepare(const dofb_conv_geom *g, const void *x, bool bf, int xp_h, int xp_w, int xp_y0, int xp_x0, int TW, int TH, int TN,
                          CUtensorMapSwizzle swz, CUtensorMap *map, TapInfo *rows) {
     DOFB_CHECK_ARG(g->stride == 2 && g->ci <= 8 && g->kw <= 8 && g->kh <= 8, "dofb_conv1: needs stride 2, ci <= 8, kernel <= 8x8");
     DOFB_CHECK_ARG(xp_h % 2 == 0 && xp_w % 2 == 0 && aligned16(x), "dofb_conv1: buffer sizes must be even and the buffer 16-byte aligned");
@@ -1077,23 +1130,26 @@ static int conv1_prepare(const dofb_conv_geom *g, const float *x, int xp_h, int 
         rows[kh].oy = (short)((kh + rowoff) >> 1); rows[kh].py = (short)((kh + rowoff) & 1);
         rows[kh].ox = 0; rows[kh].px = 0; rows[kh].wk = kh * 64;
     }
-    const uint64_t rowb = (uint64_t)xp_w * 8 * 4;
+    const uint64_t esz = bf ? 2 : 4;
+    const uint64_t rowb = (uint64_t)xp_w * 8 * esz;
     const uint64_t dims[5] = {64, (uint64_t)g->ow, 2, (uint64_t)xp_h / 2, (uint64_t)g->B};
-    const uint64_t str[4] = {64, rowb, 2 * rowb, (uint64_t)xp_h * rowb};
-    const uint32_t box[5] = {32, (uint32_t)TW, 1, (uint32_t)TH, (uint32_t)TN};
-    return make_map(map, x + (size_t)coloff * 8, 5, dims, str, box, swz);
+    const uint64_t str[4] = {16 * esz, rowb, 2 * rowb, (uint64_t)xp_h * rowb};          // d1: two pixels of 8 channels
+    const uint32_t box[5] = {bf ? 64u : 32u, (uint32_t)TW, 1, (uint32_t)TH, (uint32_t)TN};
+    return make_map(map, static_cast<const uint8_t *>(x) + (size_t)coloff * 8 * esz, 5, dims, str, box, swz,
+                    bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
 }
 
 int tc_conv1_fwd(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *w, const float *bias,
-                 float *y, int y_ld, int act, cudaStream_t st, void *y16) {
-    DOFB_CHECK_ARG(g && x && w && y, "dofb_conv1_fwd: null argument");
+                 float *y, int y_ld, int act, cudaStream_t st, void *y16, const void *x16) {
+    const bool bf = x16 != nullptr;                 // bf16 copy of the zero-bordered input -> kind::f16, one K block per filter row
+    DOFB_CHECK_ARG(g && (x || x16) && w && y, "dofb_conv1_fwd: null argument");
     TcParams P;
     memset(&P, 0, sizeof(P));
     P.cnt_y = g->oh; P.cnt_x = g->ow; P.rstep = 1;
     choose_tile(P.cnt_y, P.cnt_x, P.TW, P.TH, P.TN);
     CUtensorMap ma, mb;
-    if (conv1_prepare(g, x, xp_h, xp_w, xp_y0, xp_x0, P.TW, P.TH, P.TN, CU_TENSOR_MAP_SWIZZLE_128B, &ma, P.taps)) return 1;
-    P.parity = 1; P.ntaps = g->kh; P.ncb = 2; P.a_coff = 0; P.a_ld = 0;
+    if (conv1_prepare(g, bf ? x16 : (const void *)x, bf, xp_h, xp_w, xp_y0, xp_x0, P.TW, P.TH, P.TN, CU_TENSOR_MAP_SWIZZLE_128B, &ma, P.taps)) return 1;
+    P.parity = 1; P.ntaps = g->kh; P.ncb = bf ? 1 : 2; P.a_coff = 0; P.a_ld = 0;
     P.out = y; P.out_ld = y_ld; P.out16 = reinterpret_cast<__nv_bfloat16 *>(y16);
     P.bias = bias; P.n_valid = g->co; P.rh = g->oh; P.rw = g->ow; P.act = act; P.accumulate = 0; P.B = g->B;
     P.tiles_x = (P.cnt_x + P.TW - 1) / P.TW;
@@ -1102,17 +1158,26 @@ int tc_conv1_fwd(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, in
     float *wp = nullptr;
     const size_t wfloats = (size_t)g->co * g->kh * 64;
     bool fresh = false;
-    if (get_pack_buffer(w, 2, wfloats, &wp, &fresh)) return 1;
+    if (get_pack_buffer(w, bf ? 10 : 2, bf ? (wfloats + 1) / 2 : wfloats, &wp, &fresh)) return 1;
     if (!fresh) {
-        pack_conv1_kernel<<<(unsigned)((wfloats + 255) / 256), 256, 0, st>>>(w, wp, g->kh, g->kw, g->ci, g->co);
+        if (bf) pack_conv1_kernel<<<(unsigned)((wfloats + 255) / 256), 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16 *>(wp), g->kh, g->kw, g->ci, g->co);
+        else pack_conv1_kernel<<<(unsigned)((wfloats + 255) / 256), 256, 0, st>>>(w, wp, g->kh, g->kw, g->ci, g->co);
         DOFB_LAUNCH_OK();
     }
     const int bn = g->co > 128 ? 256 : (g->co > 64 ? 128 : (g->co > 32 ? 64 : 32));
     const uint64_t dims[2] = {(uint64_t)g->kh * 64, (uint64_t)g->co};
-    const uint64_t str[1] = {(uint64_t)g->kh * 64 * 4};
-    const uint32_t box[2] = {32, (uint32_t)bn};
-    if (make_map(&mb, wp, 2, dims, str, box)) return 1;
+    const uint64_t str[1] = {(uint64_t)g->kh * 64 * (bf ? 2 : 4)};
+    const uint32_t box[2] = {bf ? 64u : 32u, (uint32_t)bn};
+    if (make_map(&mb, wp, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32)) return 1;
     const int n_tiles = (g->co + bn - 1) / bn;
+    if (bf) {
+        switch (bn) {
+            case 256: return launch_tc<256, 4, true>(ma, mb, P, tiles, n_tiles, st);
+            case 128: return launch_tc<128, 6, true>(ma, mb, P, tiles, n_tiles, st);
+            case 64: return launch_tc<64, 8, true>(ma, mb, P, tiles, n_tiles, st);
+            default: return launch_tc<32, 8, true>(ma, mb, P, tiles, n_tiles, st);
+        }
+    }
     switch (bn) {
         case 256: return launch_tc<256, 4>(ma, mb, P, tiles, n_tiles, st);
         case 128: return launch_tc<128, 6>(ma, mb, P, tiles, n_tiles, st);
@@ -1122,25 +1187,29 @@ int tc_conv1_fwd(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, in
 }
 
 int tc_conv1_wgrad(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *dy, int dy_ld,
-                   float *dw, cudaStream_t st) {
-    DOFB_CHECK_ARG(g && x && dy && dw, "dofb_conv1_wgrad: null argument");
-    DOFB_CHECK_ARG(dy_ld % 32 == 0 && aligned16(dy), "dofb_conv1_wgrad: dy pitch %d must be a multiple of 32 floats", dy_ld);
-    const int co_pad = (g->co + 31) / 32 * 32;
-    DOFB_CHECK_ARG(co_pad <= dy_ld, "dofb_conv1_wgrad: channels rounded up to 32 exceed the pitch");
+                   float *dw, cudaStream_t st, const void *x16, const void *dy16) {
+    const bool bf = x16 != nullptr && dy16 != nullptr;
+    const int CH = bf ? 64 : 32, BKP = bf ? 64 : 32;
+    DOFB_CHECK_ARG(g && (bf || (x && dy)) && dw, "dofb_conv1_wgrad: null argument");
+    DOFB_CHECK_ARG(dy_ld % CH == 0 && aligned16(bf ? dy16 : (const void *)dy), "dofb_conv1_wgrad: dy pitch %d must be a multiple of %d elements", dy_ld, CH);
+    const int co_pad = (g->co + CH - 1) / CH * CH;
+    DOFB_CHECK_ARG(co_pad <= dy_ld, "dofb_conv1_wgrad: channels rounded up to %d exceed the pitch", CH);
     WgParams P;
     memset(&P, 0, sizeof(P));
     P.dW = dw; P.CI = g->ci; P.CO = g->co; P.swap = 0; P.m_valid = TC_BM; P.n_valid = g->co;
     P.conv1 = 1; P.c1_kh = g->kh; P.c1_kw = g->kw; P.parity = 1;
     {
         int TW = pow2_ceil(g->ow) < 16 ? pow2_ceil(g->ow) : 16;
-        int th_max = WG_BKP / TW;
+        int th_max = BKP / TW;
         int TH = pow2_ceil(g->oh) < th_max ? pow2_ceil(g->oh) : th_max;
         for (int t = TH; t >= 1; t >>= 1)
             if (g->oh % t == 0) { TH = t; break; }
-        P.TW = TW; P.TH = TH; P.TN = WG_BKP / (TW * TH);
+        P.TW = TW; P.TH = TH; P.TN = BKP / (TW * TH);
     }
     CUtensorMap mx, md;
-    if (conv1_prepare(g, x, xp_h, xp_w, xp_y0, xp_x0, P.TW, P.TH, P.TN, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, &mx, P.taps)) return 1;
+    // MN-major operands: fp32 needs the 32-byte-atom swizzle, bf16 the plain 128-byte one (as in tc_conv_wgrad)
+    const CUtensorMapSwizzle swz = bf ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    if (conv1_prepare(g, bf ? x16 : (const void *)x, bf, xp_h, xp_w, xp_y0, xp_x0, P.TW, P.TH, P.TN, swz, &mx, P.taps)) return 1;
     P.tiles_x = (g->ow + P.TW - 1) / P.TW;
     P.tiles_y = (g->oh + P.TH - 1) / P.TH;
     P.tiles_total = P.tiles_x * P.tiles_y * ((g->B + P.TN - 1) / P.TN);
@@ -1155,10 +1224,20 @@ int tc_conv1_wgrad(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, 
     P.tiles_per_split = (int)((P.tiles_total + splits - 1) / splits);
     splits = (P.tiles_total + P.tiles_per_split - 1) / P.tiles_per_split;
     {
+        const uint64_t esz = bf ? 2 : 4;
         const uint64_t dims[4] = {(uint64_t)co_pad, (uint64_t)g->ow, (uint64_t)g->oh, (uint64_t)g->B};
-        const uint64_t str[3] = {(uint64_t)dy_ld * 4, (uint64_t)g->ow * dy_ld * 4, (uint64_t)g->oh * g->ow * dy_ld * 4};
-        const uint32_t box[4] = {32, (uint32_t)P.TW, (uint32_t)P.TH, (uint32_t)P.TN};
-        if (make_map(&md, dy, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+        const uint64_t str[3] = {(uint64_t)dy_ld * esz, (uint64_t)g->ow * dy_ld * esz, (uint64_t)g->oh * g->ow * dy_ld * esz};
+        const uint32_t box[4] = {(uint32_t)CH, (uint32_t)P.TW, (uint32_t)P.TH, (uint32_t)P.TN};
+        if (make_map(&md, bf ? dy16 : (const void *)dy, 4, dims, str, box, swz,
+                     bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32)) return 1;
+    }
+    if (bf) {
+        switch (bn) {
+            case 256: return launch_wg<256, 4, true>(mx, md, P, (int)splits, items, st);
+            case 128: return launch_wg<128, 6, true>(mx, md, P, (int)splits, items, st);
+            case 64: return launch_wg<64, 8, true>(mx, md, P, (int)splits, items, st);
+            default: return launch_wg<32, 8, true>(mx, md, P, (int)splits, items, st);
+        }
     }
     switch (bn) {
         case 256: return launch_wg<256, 4>(mx, md, P, (int)splits, items, st);

@@ -207,8 +207,10 @@ class FlowNetS:
             for dct in (self.act, self.dact):
                 for t in dct.values():
                     self._sh[id(t)] = torch.zeros(t.shape, dtype=torch.bfloat16, device=dev)
-            if self.ARCH == "V":
-                self._sh[id(self.x6)] = torch.zeros(self.x6.shape, dtype=torch.bfloat16, device=dev)
+            # bf16 copies of the first-layer inputs (VGG: read by the generic kernels; S/C: by the bf16 first-layer kernels)
+            self._sh[id(self.x6)] = torch.zeros(self.x6.shape, dtype=torch.bfloat16, device=dev)
+            if self.x6b is not None:
+                self._sh[id(self.x6b)] = torch.zeros(self.x6b.shape, dtype=torch.bfloat16, device=dev)
         self.hw = {s: (H >> s, W >> s) for s in range(1, self.N_SCALES + 1)}
         self.pr = {s: z(*self.hw[s], 2) for s in range(1, self.N_SCALES + 1)}
         self.dpr = {s: z(*self.hw[s], 2) for s in range(1, self.N_SCALES + 1)}
@@ -292,13 +294,18 @@ class FlowNetS:
     def _preprocess(self, source, target):
         self._k("preprocess", ops.preprocess, source, target, self.mean, self.x6, [self.pyr_src[s] for s in range(1, self.N_SCALES + 1)],
                 [self.pyr_tgt[s] for s in range(1, self.N_SCALES + 1)], self.x6_origin, self.x6b)
+        if self.math == MATH_BF16:          # bf16 copies of the zero-bordered first-layer inputs
+            for t in (self.x6, self.x6b):
+                if t is not None:
+                    self._k("cast:x6", ops.cast_bf16_raw, t, self._sh[id(t)], t.shape[3])
 
     def _fwd_layer(self, L):
         P, mth = self.params, self.math
         if L["op"] == "conv":
             w, b = P[L["wname"] + "/weights"], P[L["wname"] + "/biases"]
             if L["xpad"] is not None:       # first layer on tensor cores from the zero-bordered buffer
-                self._k("conv_fwd:" + L["name"], ops.conv1_fwd, L["g"], L["xpad"], self.x6_origin, w, b, L["y"], ACT_ELU)
+                self._k("conv_fwd:" + L["name"], ops.conv1_fwd, L["g"], L["xpad"], self.x6_origin, w, b, L["y"], ACT_ELU,
+                        self._sh.get(id(L["xpad"])))
             else:
                 self._k("conv_fwd:" + L["name"], ops.conv_fwd, L["g"], L["x"], w, b, L["y"], ACT_ELU, mth)
         elif L["op"] == "pool":
@@ -317,7 +324,8 @@ class FlowNetS:
             w, dw, db = P[L["wname"] + "/weights"], G[L["wname"] + "/weights"], G[L["wname"] + "/biases"]
             self._k("elu_bwd:" + L["name"], ops.elu_bwd, L["dy"], L["y"], db)                      # + bias gradient
             if L["xpad"] is not None:
-                self._k("conv_wgrad:" + L["name"], ops.conv1_wgrad, L["g"], L["xpad"], self.x6_origin, L["dy"], dw, None)
+                self._k("conv_wgrad:" + L["name"], ops.conv1_wgrad, L["g"], L["xpad"], self.x6_origin, L["dy"], dw, None,
+                        self._sh.get(id(L["xpad"])) if mthw == MATH_BF16 else None)
             else:
                 self._k("conv_wgrad:" + L["name"], ops.conv_wgrad, L["g"], L["x"], L["dy"], dw, None, mthw)
             if L["dx"] is not None:

@@ -122,17 +122,36 @@ def maxpool2_bwd(x: Slab, dy: Slab, dx: Slab):
     check(_lib.load().dofb_maxpool2_bwd(x.ptr, x.ld, dy.ptr, dy.ld, dy.B, dy.h, dy.w, dy.c, dx.ptr, dx.ld, _stream()))
 
 
-def conv1_fwd(g: ConvGeom, xpad, origin, w, b, y: Slab, act=ACT_ELU):
-    """conv1 on tensor cores from the zero-bordered input buffer (see dofb_conv1_fwd)."""
+def conv1_fwd(g: ConvGeom, xpad, origin, w, b, y: Slab, act=ACT_ELU, xpad16=None):
+    """conv1 on tensor cores from the zero-bordered input buffer (see dofb_conv1_fwd); xpad16 = its bf16 copy -> bf16 math."""
     _req(xpad, "xpad"); _req(w, "w")
-    check(_lib.load().dofb_conv1_fwd(C.byref(g), xpad.data_ptr(), xpad.shape[1], xpad.shape[2], origin[0], origin[1], w.data_ptr(),
-                                     b.data_ptr() if b is not None else None, y.ptr, y.ptr16, y.ld, act, _stream()))
+    lib = _lib.load()
+    bp = b.data_ptr() if b is not None else None
+    if xpad16 is not None:
+        check(lib.dofb_conv1_fwd_bf16(C.byref(g), xpad16.data_ptr(), xpad.shape[1], xpad.shape[2], origin[0], origin[1], w.data_ptr(),
+                                      bp, y.ptr, y.ptr16, y.ld, act, _stream()))
+        return
+    check(lib.dofb_conv1_fwd(C.byref(g), xpad.data_ptr(), xpad.shape[1], xpad.shape[2], origin[0], origin[1], w.data_ptr(),
+                             bp, y.ptr, y.ptr16, y.ld, act, _stream()))
 
 
-def conv1_wgrad(g: ConvGeom, xpad, origin, dy: Slab, dw, db):
+def conv1_wgrad(g: ConvGeom, xpad, origin, dy: Slab, dw, db, xpad16=None):
     _req(xpad, "xpad"); _req(dw, "dw")
-    check(_lib.load().dofb_conv1_wgrad(C.byref(g), xpad.data_ptr(), xpad.shape[1], xpad.shape[2], origin[0], origin[1], dy.ptr, dy.ld,
-                                       dw.data_ptr(), db.data_ptr() if db is not None else None, _stream()))
+    lib = _lib.load()
+    if xpad16 is not None:
+        if db is not None:
+            raise DeepOFError("conv1_wgrad(bf16): the bias gradient comes from elu_bwd, pass db=None")
+        check(lib.dofb_conv1_wgrad_bf16(C.byref(g), xpad16.data_ptr(), xpad.shape[1], xpad.shape[2], origin[0], origin[1],
+                                        _need16(dy, "conv1_wgrad"), dy.ld, dw.data_ptr(), _stream()))
+        return
+    check(lib.dofb_conv1_wgrad(C.byref(g), xpad.data_ptr(), xpad.shape[1], xpad.shape[2], origin[0], origin[1], dy.ptr, dy.ld,
+                               dw.data_ptr(), db.data_ptr() if db is not None else None, _stream()))
+
+
+def cast_bf16_raw(src, dst16, c: int):
+    """bf16 copy of a dense [..., c] fp32 tensor (pitch c)."""
+    _req(src, "src")
+    check(_lib.load().dofb_cast_bf16(src.data_ptr(), c, dst16.data_ptr(), c, src.numel() // c, c, _stream()))
 
 
 def _need16(s: Slab, who: str):

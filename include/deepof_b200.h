@@ -151,6 +151,12 @@ int dofb_conv_dgrad_bf16(const dofb_conv_geom *g, const void *dy_bf16, int dy_ld
                          void *dx_bf16 /* written only when !accumulate; may be NULL */, int dx_ld, int act, int accumulate, void *stream);
 int dofb_conv_wgrad_bf16(const dofb_conv_geom *g, const void *x_bf16, int x_ld, const void *dy_bf16, int dy_ld, float *dw, void *stream);
 /* dst_bf16[p, 0..c) = bf16(src[p, 0..c)) for producers that have no fused shadow output (flow heads' up_pr, correlation, pooling) */
+/* First layer in bf16: x_bf16 = bf16 copy (dofb_cast_bf16, pitch 8) of the zero-bordered input of dofb_conv1_fwd; one 128-byte K block
+ * per filter row (half the L2->shared traffic of the TF32 form).  Same geometry arguments and semantics as dofb_conv1_fwd / _wgrad. */
+int dofb_conv1_fwd_bf16(const dofb_conv_geom *g, const void *x_bf16, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *w,
+                        const float *bias, float *y, void *y_bf16 /* optional shadow, may be NULL */, int y_ld, int act, void *stream);
+int dofb_conv1_wgrad_bf16(const dofb_conv_geom *g, const void *x_bf16, int xp_h, int xp_w, int xp_y0, int xp_x0, const void *dy_bf16,
+                          int dy_ld, float *dw, void *stream);
 int dofb_cast_bf16(const float *src, int src_ld, void *dst_bf16, int dst_ld, long long n_pix, int c, void *stream);
 
 /* g[B*h*w, 0..c) *= elu'(y) where y is the ELU OUTPUT (elu' = y>0 ? 1 : y+1).  If db != NULL, db[c] += column sums of the

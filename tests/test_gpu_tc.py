@@ -211,6 +211,58 @@ def _shadow(t):
 BF_TOL = 2e-2     # bf16 operands (8-bit mantissa), fp32 accumulate: max-norm relative
 
 
+@pytest.mark.parametrize("B,H,W,ci", [(2, 64, 128, 6), (1, 384, 512, 6), (3, 48, 80, 3)])
+def test_bf16_conv1_fwd_and_wgrad_match_simt(B, H, W, ci):
+    """First layer with bf16 operands (bf16 copy of the zero-bordered input, one K block per filter row) vs the fp32 SIMT kernel;
+    ci = 3 is FlowNetC's siamese first layer."""
+    from deepof_b200 import ops
+    g = torch.Generator().manual_seed(B * H + W + ci)
+    co, k = 64, 7
+    img = torch.randn(B, H, W, ci, generator=g).cuda()
+    dense = torch.zeros(B, H, W, 8, device="cuda")
+    dense[..., :ci] = img
+    padded = torch.zeros(B, H + 6, W + 8, 8, device="cuda")
+    padded[:, 2:2 + H, 2:2 + W, :ci] = img
+    padded16 = torch.zeros(padded.shape, dtype=torch.bfloat16, device="cuda")
+    ops.cast_bf16_raw(padded, padded16, 8)
+    torch.cuda.synchronize()
+    assert torch.equal(padded16, padded.to(torch.bfloat16))
+    w = (torch.randn(k, k, ci, co, generator=g) / math.sqrt(k * k * ci)).cuda()
+    b = (torch.randn(co, generator=g) * 0.1).cuda()
+    geom = ops.conv_geom(B, H, W, ci, co, k, 2)
+    y0 = torch.zeros(B, geom.oh, geom.ow, 128, device="cuda")
+    y1 = torch.zeros_like(y0)
+    y1s = torch.zeros(y1.shape, dtype=torch.bfloat16, device="cuda")
+    ops.conv_fwd(geom, ops.Slab(dense, 0, ci), w, b, ops.Slab(y0, 0, co), ops.ACT_ELU, ops.MATH_FP32)
+    ops.conv1_fwd(geom, padded, (2, 2), w, b, ops.Slab(y1, 0, co, y1s), ops.ACT_ELU, padded16)
+    torch.cuda.synchronize()
+    assert rel(y1, y0) < BF_TOL
+    assert torch.equal(y1s[..., :co], y1[..., :co].to(torch.bfloat16))
+    dy = _buf(B, geom.oh, geom.ow, 128, co, g)
+    dw0 = torch.zeros(k, k, ci, co, device="cuda"); dw1 = torch.zeros_like(dw0)
+    ops.conv_wgrad(geom, ops.Slab(dense, 0, ci), ops.Slab(dy, 0, co), dw0, None, ops.MATH_FP32)
+    ops.conv1_wgrad(geom, padded, (2, 2), ops.Slab(dy, 0, co, _shadow(dy)), dw1, None, padded16)
+    torch.cuda.synchronize()
+    assert rel(dw1, dw0) < BF_TOL
+
+
+def test_conv_fwd_accumulate_flag():
+    """ACT_ACCUMULATE: y += conv(x) + bias in all three math modes (used where a transposed conv's input gradient lands second)."""
+    from deepof_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    B, H, W, ci, co, k, s = 2, 12, 16, 64, 128, 3, 1
+    x = _buf(B, H, W, 64, ci, g)
+    w = (torch.randn(k, k, ci, co, generator=g) / math.sqrt(k * k * ci)).cuda()
+    geom = ops.conv_geom(B, H, W, ci, co, k, s)
+    ref = torch.zeros(B, geom.oh, geom.ow, 128, device="cuda")
+    ops.conv_fwd(geom, ops.Slab(x, 0, ci), w, None, ops.Slab(ref, 0, co), ops.ACT_NONE, ops.MATH_FP32)
+    for mth, tol in ((ops.MATH_FP32, 1e-5), (ops.MATH_TF32, TOL), (ops.MATH_BF16, BF_TOL)):
+        y = torch.full_like(ref, 0.5)
+        ops.conv_fwd(geom, ops.Slab(x, 0, ci, _shadow(x)), w, None, ops.Slab(y, 0, co), ops.ACT_NONE | ops.ACT_ACCUMULATE, mth)
+        torch.cuda.synchronize()
+        assert rel(y[..., :co] - 0.5, ref[..., :co]) < tol, mth
+
+
 @pytest.mark.parametrize("case", [
     (2, 24, 32, 64, 128, 128, 5, 2), (2, 12, 16, 256, 256, 256, 3, 1), (4, 12, 16, 256, 448, 512, 3, 2), (8, 3, 4, 1024, 1024, 1024, 3, 1),
     (1, 48, 64, 128, 256, 256, 5, 2), (2, 10, 14, 32, 64, 32, 3, 1), (2, 16, 16, 96, 128, 64, 3, 1)])
