@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- FlowNetS training-step throughput on synthetic FlyingChairs-shaped 384x512 pairs.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--math fp32|tf32]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--math bf16|tf32|fp32]
 
 One "step" = one pass of the hot path over one batch: H2D-resident inputs -> pre-processing -> conv
 tower -> refinement -> fused warp+loss -> backward -> (gradient all-reduce) -> Adam.
@@ -418,7 +418,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--math", default=os.environ.get("DEEPOF_MATH", "tf32"), choices=["fp32", "tf32", "bf16"],
+    ap.add_argument("--math", default=os.environ.get("DEEPOF_MATH", "bf16"), choices=["fp32", "tf32", "bf16"],
                     help="bf16: tcgen05 kind::f16 on bf16 activation shadows + bf16 packed weights, fp32 accumulate/epilogue/master weights; tf32: tcgen05 tensor-core convolutions (TF32 operands, fp32 accumulate; EPE within 1e-3 of the fp32 path, "
                          "checked in this run); fp32: SIMT FFMA parity path")
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (BASELINE config: 32)")

@@ -395,16 +395,18 @@ __global__ void __launch_bounds__(256) uppr_bwd_kernel(const float *__restrict__
                                                        int h, int w, const float *__restrict__ Wt, float *__restrict__ dpr,
                                                        float *__restrict__ dWt, float *__restrict__ dbias) {
     __shared__ float ws[64];
-    __shared__ float red[66];
+    __shared__ float red[64];
+    __shared__ double redd[2];
     if (threadIdx.x < 64) ws[threadIdx.x] = Wt[threadIdx.x];
-    if (threadIdx.x < 66) red[threadIdx.x] = 0.f;
+    if (threadIdx.x < 64) red[threadIdx.x] = 0.f;
+    if (threadIdx.x < 2) redd[threadIdx.x] = 0.0;
     __syncthreads();
     const int H2 = 2 * h, W2 = 2 * w;
     const long long n = (long long)B * h * w;
     float aw[64];
 #pragma unroll
     for (int i = 0; i < 64; ++i) aw[i] = 0.f;
-    float ab0 = 0.f, ab1 = 0.f;
+    double ab0 = 0.0, ab1 = 0.0;            // the bias gradient is a long signed sum with heavy cancellation: accumulate it in fp64
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
         const int x = (int)(p % w), y = (int)((p / w) % h), b = (int)(p / ((long long)w * h));
         const float2 v = __ldg(reinterpret_cast<const float2 *>(pr) + p);
@@ -436,11 +438,11 @@ __global__ void __launch_bounds__(256) uppr_bwd_kernel(const float *__restrict__
         const float s = warp_sum(aw[i]);
         if ((threadIdx.x & 31) == 0) atomicAdd(&red[i], s);
     }
-    const float s0 = warp_sum(ab0), s1 = warp_sum(ab1);
-    if ((threadIdx.x & 31) == 0) { atomicAdd(&red[64], s0); atomicAdd(&red[65], s1); }
+    const double s0 = warp_sum(ab0), s1 = warp_sum(ab1);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&redd[0], s0); atomicAdd(&redd[1], s1); }
     __syncthreads();
     if (threadIdx.x < 64) atomicAdd(dWt + threadIdx.x, red[threadIdx.x]);
-    else if (threadIdx.x < 66 && dbias) atomicAdd(dbias + (threadIdx.x - 64), red[threadIdx.x]);
+    else if (threadIdx.x < 66 && dbias) atomicAdd(dbias + (threadIdx.x - 64), (float)redd[threadIdx.x - 64]);
 }
 
 }  // namespace dofb

@@ -2,7 +2,7 @@
 # Run on the GPU box (under gpurun): launch list + full ncu captures of the top kernels.  Outputs -> gpurun_out/
 set -u
 mkdir -p gpurun_out
-MATH=${1:-tf32}
+MATH=${1:-bf16}
 # 1) every launch of ~2 steps with its device time (cold-cache, serialised: compare shares, not absolutes)
 ncu --metrics gpu__time_duration.sum --clock-control none -s 800 -c 420 --csv --log-file gpurun_out/launches_${MATH}.csv \
     python bench.py --math $MATH --steps 3 --warmup 3 --no-cpu > gpurun_out/ncu_bench_${MATH}.log 2>&1
