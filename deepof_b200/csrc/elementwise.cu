@@ -154,6 +154,9 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float *__restric
 // block = 256 threads = (256/QW) pixel rows x QW channel quads (QW = power of two <= 32 chosen from the channel count, so narrow
 // layers still use every lane); a block owns a quad stripe and a pixel range, so the column sums of the result (BiasAddGrad)
 // reduce in registers -> shared -> one atomicAdd per channel per block.
+// WB = false: the fp32 gradient is NOT written back (bf16 math: the only readers of the finished gradient are tensor-core kernels that
+// take the bf16 shadow), which cuts the traffic of this HBM-bound pass from 14 to 10 bytes per element.
+template <bool WB>
 __global__ void __launch_bounds__(256) elu_bwd_kernel(float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c4, int qw,
                                                       long long pix_per_block, float *db, __nv_bfloat16 *g16) {
     const int ql = threadIdx.x & (qw - 1);
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(256) elu_bwd_kernel(float *g, int g_ld, const 
             const float4 yv = __ldg(reinterpret_cast<const float4 *>(y + p * y_ld + q * 4));
             gv.x *= elu_grad_from_out(yv.x); gv.y *= elu_grad_from_out(yv.y);
             gv.z *= elu_grad_from_out(yv.z); gv.w *= elu_grad_from_out(yv.w);
-            *reinterpret_cast<float4 *>(g + p * g_ld + q * 4) = gv;
+            if (WB) *reinterpret_cast<float4 *>(g + p * g_ld + q * 4) = gv;
             if (g16 != nullptr) {               // bf16 shadow of the finished gradient for the tensor-core consumers
                 __nv_bfloat162 lo = __floats2bfloat162_rn(gv.x, gv.y), hi = __floats2bfloat162_rn(gv.z, gv.w);
                 uint2 pk;
@@ -343,7 +346,7 @@ extern "C" int dofb_cast_bf16(const float *src, int src_ld, void *dst_bf16, int 
     return 0;
 }
 
-extern "C" int dofb_elu_bwd(float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c, float *db, void *g_bf16, void *stream) {
+static int elu_bwd_launch(float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c, float *db, void *g_bf16, bool write_back, void *stream) {
     DOFB_CHECK_ARG(g && y && n_pix > 0 && c > 0, "dofb_elu_bwd: bad argument");
     DOFB_CHECK_ARG(c % 4 == 0 && g_ld % 4 == 0 && y_ld % 4 == 0 && aligned16(g) && aligned16(y),
                    "dofb_elu_bwd: channels/pitches must be multiples of 4 and pointers 16-byte aligned (c=%d)", c);
@@ -357,10 +360,24 @@ extern "C" int dofb_elu_bwd(float *g, int g_ld, const float *y, int y_ld, long l
     if (ppb < 4 * rows) ppb = 4 * rows;
     ppb = (ppb + rows - 1) / rows * rows;
     blocks = (n_pix + ppb - 1) / ppb;
-    elu_bwd_kernel<<<dim3((unsigned)blocks, stripes), 256, 0, as_stream(stream)>>>(g, g_ld, y, y_ld, n_pix, c4, qw, ppb, db,
-                                                                                   reinterpret_cast<__nv_bfloat16 *>(g_bf16));
+    if (write_back)
+        elu_bwd_kernel<true><<<dim3((unsigned)blocks, stripes), 256, 0, as_stream(stream)>>>(g, g_ld, y, y_ld, n_pix, c4, qw, ppb, db,
+                                                                                             reinterpret_cast<__nv_bfloat16 *>(g_bf16));
+    else
+        elu_bwd_kernel<false><<<dim3((unsigned)blocks, stripes), 256, 0, as_stream(stream)>>>(g, g_ld, y, y_ld, n_pix, c4, qw, ppb, db,
+                                                                                              reinterpret_cast<__nv_bfloat16 *>(g_bf16));
     DOFB_LAUNCH_OK();
     return 0;
+}
+
+extern "C" int dofb_elu_bwd(float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c, float *db, void *g_bf16, void *stream) {
+    return elu_bwd_launch(g, g_ld, y, y_ld, n_pix, c, db, g_bf16, true, stream);
+}
+
+extern "C" int dofb_elu_bwd_shadow(const float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c, float *db, void *g_bf16,
+                                   void *stream) {
+    DOFB_CHECK_ARG(g_bf16 != nullptr, "dofb_elu_bwd_shadow: needs the bf16 output");
+    return elu_bwd_launch(const_cast<float *>(g), g_ld, y, y_ld, n_pix, c, db, g_bf16, false, stream);
 }
 
 extern "C" int dofb_adam(float *theta, const float *g, float *m, float *v, long long n, float lr_t, float beta1, float beta2,

@@ -183,8 +183,11 @@ class FlowNetS:
     N_SCALES = 6
     REFINE_SPEC = REFINE
 
+    TC_HEAD_MAX_PIX = 32 * 24 * 32          # heads with at most this many output pixels go through the tensor-core GEMM
+
     def _alloc(self):
         B, H, W, dev = self.B, self.H, self.W, self.device
+        self._head_geom = {}
         z = lambda h, w, c, b=B: torch.zeros(b, h, w, c, dtype=torch.float32, device=dev)  # noqa: E731
         self._z = z
         # first-layer input: dense for the SIMT path; zero-bordered (2 rows/cols before, 4/6 after) for the tcgen05 first-layer
@@ -290,6 +293,20 @@ class FlowNetS:
                                     up_y=S(a[tgt], skipc, upc), up_dy=S(d[tgt], skipc, upc),
                                     pr_y=S(a[tgt], skipc + upc, 2), pr_dy=S(d[tgt], skipc + upc, 2)))
 
+    def _head_fwd(self, s, x):
+        """pr_s = 3x3 conv to 2 channels.  Coarse scales (small maps, 386..1026 input channels) are GEMM-shaped with a long K and too few
+        pixels to fill the GPU with the streaming SIMT kernel, so in the tensor-core math modes they run through the gather-GEMM
+        (N padded to 32); the fine scales are bandwidth-bound and stay on the strip kernel."""
+        P = self.params
+        h, w = self.hw[s]
+        if self.math != MATH_FP32 and self.B * h * w <= self.TC_HEAD_MAX_PIX:
+            g = self._head_geom.get(s)
+            if g is None:
+                g = self._head_geom[s] = conv_geom(self.B, h, w, x.c, 2, 3, 1)
+            self._k(f"head_fwd:pr{s}", ops.conv_fwd, g, x, P[f"pr{s}/weights"], P[f"pr{s}/biases"], full(self.pr[s]), ACT_NONE, self.math)
+        else:
+            self._k(f"head_fwd:pr{s}", ops.head_fwd, x, P[f"pr{s}/weights"], P[f"pr{s}/biases"], self.pr[s])
+
     # ------------------------------------------------------------------ forward
     def _preprocess(self, source, target):
         self._k("preprocess", ops.preprocess, source, target, self.mean, self.x6, [self.pyr_src[s] for s in range(1, self.N_SCALES + 1)],
@@ -322,7 +339,8 @@ class FlowNetS:
         P, G, mth, mthw = self.params, self.grads, self.math, self.math_wgrad
         if L["op"] == "conv":
             w, dw, db = P[L["wname"] + "/weights"], G[L["wname"] + "/weights"], G[L["wname"] + "/biases"]
-            self._k("elu_bwd:" + L["name"], ops.elu_bwd, L["dy"], L["y"], db)                      # + bias gradient
+            # + bias gradient; bf16 math: only the bf16 shadow of the finished gradient is read again (by this layer's wgrad / dgrad)
+            self._k("elu_bwd:" + L["name"], ops.elu_bwd, L["dy"], L["y"], db, mth == MATH_BF16 and mthw == MATH_BF16)
             if L["xpad"] is not None:
                 self._k("conv_wgrad:" + L["name"], ops.conv1_wgrad, L["g"], L["xpad"], self.x6_origin, L["dy"], dw, None,
                         self._sh.get(id(L["xpad"])) if mthw == MATH_BF16 else None)
@@ -349,13 +367,13 @@ class FlowNetS:
         for R in self.refine:
             s = R["s"]
             x, _ = self.feat[s]
-            self._k(f"head_fwd:pr{s}", ops.head_fwd, x, P[f"pr{s}/weights"], P[f"pr{s}/biases"], self.pr[s])
+            self._head_fwd(s, x)
             self._k("deconv_fwd:" + R["up"], ops.conv_dgrad, R["g"], x, P[R["up"] + "/weights"], P[R["up"] + "/biases"],
                     R["up_y"], ACT_ELU, False, mth)
             self._k("uppr_fwd:" + R["uppr"], ops.uppr_fwd, self.pr[s], P[R["uppr"] + "/weights"], P[R["uppr"] + "/biases"], R["pr_y"])
             if mth == MATH_BF16:
                 self._k("cast:" + R["uppr"], ops.cast_bf16, R["pr_y"])
-        self._k("head_fwd:pr1", ops.head_fwd, self.feat[1][0], P["pr1/weights"], P["pr1/biases"], self.pr[1])
+        self._head_fwd(1, self.feat[1][0])
         lw = [float(v) for v in loss_weight]
         self.loss_weight = lw
         hp = self.hyper
@@ -408,7 +426,8 @@ class FlowNetS:
             self._k("uppr_bwd:" + R["uppr"], ops.uppr_bwd, self.pr[s], R["pr_dy"], P[R["uppr"] + "/weights"], self.dpr[s],
                     G[R["uppr"] + "/weights"], G[R["uppr"] + "/biases"])
             # upconv (ELU): gradient through the activation, then weight / bias / input gradients
-            self._k("elu_bwd:" + R["up"], ops.elu_bwd, R["up_dy"], R["up_y"], G[R["up"] + "/biases"])      # + bias gradient
+            self._k("elu_bwd:" + R["up"], ops.elu_bwd, R["up_dy"], R["up_y"], G[R["up"] + "/biases"],           # + bias gradient
+                    mth == MATH_BF16 and mthw == MATH_BF16)
             self._k("deconv_wgrad:" + R["up"], ops.conv_wgrad, R["g"], R["up_dy"], x, G[R["up"] + "/weights"], None, mthw)
             self._k("deconv_dgrad:" + R["up"], ops.conv_fwd, R["g"], R["up_dy"], P[R["up"] + "/weights"], None, dx, ACT_NONE,
                     mth)                                                   # first writer of d feat_s

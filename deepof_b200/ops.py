@@ -194,10 +194,15 @@ def conv_wgrad(g: ConvGeom, x: Slab, dy: Slab, dw, db, math=MATH_FP32, bias_on_l
     check(fn(C.byref(g), x.ptr, x.ld, dy.ptr, dy.ld, dw.data_ptr(), db.data_ptr() if db is not None else None, math, _stream()))
 
 
-def elu_bwd(g: Slab, y: Slab, db=None):
-    """g *= elu'(y); with db, also db += column sums of the result (the layer's bias gradient) in the same pass."""
+def elu_bwd(g: Slab, y: Slab, db=None, shadow_only=False):
+    """g *= elu'(y); with db, also db += column sums of the result (the layer's bias gradient) in the same pass.
+    shadow_only: write the result to the bf16 shadow of g only (g itself untouched) -- see dofb_elu_bwd_shadow."""
     assert g.c == y.c and g.n_pix == y.n_pix
-    check(_lib.load().dofb_elu_bwd(g.ptr, g.ld, y.ptr, y.ld, g.n_pix, g.c, db.data_ptr() if db is not None else None, g.ptr16, _stream()))
+    dbp = db.data_ptr() if db is not None else None
+    if shadow_only:
+        check(_lib.load().dofb_elu_bwd_shadow(g.ptr, g.ld, y.ptr, y.ld, g.n_pix, g.c, dbp, _need16(g, "elu_bwd"), _stream()))
+        return
+    check(_lib.load().dofb_elu_bwd(g.ptr, g.ld, y.ptr, y.ld, g.n_pix, g.c, dbp, g.ptr16, _stream()))
 
 
 def cast_bf16(s: Slab):

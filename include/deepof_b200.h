@@ -163,6 +163,9 @@ int dofb_cast_bf16(const float *src, int src_ld, void *dst_bf16, int dst_ld, lon
  * result (the BiasAddGrad of the layer) in the same pass. */
 int dofb_elu_bwd(float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c, float *db, void *g_bf16 /* optional shadow */,
                  void *stream);
+/* Same, but the result goes ONLY to the bf16 shadow (g itself is left untouched): for bf16 math, where the finished gradient of a conv
+ * output is read by tensor-core kernels alone. */
+int dofb_elu_bwd_shadow(const float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c, float *db, void *g_bf16, void *stream);
 
 /* ---- thin heads (N = 2: bandwidth-bound, not tensor-core shapes) ---------- */
 /* pr_s = conv3x3(feat -> 2) linear, flyingChairsWrapFlow.py:58,69,80,91,102,113 */

@@ -1,0 +1,61 @@
+"""Turn the files scripts/profile_gpu.sh leaves in gpurun_out/ into the tables of profiles/rNN_ncu_summary.md (run in the dev container).
+
+    python scripts/summarize_profiles.py bf16 > /tmp/tables.md
+"""
+import collections
+import csv
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+OUT = ROOT / "gpurun_out"
+math = sys.argv[1] if len(sys.argv) > 1 else "bf16"
+
+COLS = ["Kernel Name", "launch__grid_size", "launch__registers_per_thread", "gpu__time_duration.sum", "dram__bytes_read.sum",
+        "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "l1tex__m_xbar2l1tex_read_bytes.sum",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active"]
+
+
+def launch_table():
+    path = OUT / f"launches_{math}.csv"
+    rows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))]
+    hdr = rows[0]
+    ik, iv, iu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    agg = collections.OrderedDict()
+    for r in rows[1:]:
+        name = re.sub(r"\(.*", "", r[ik]).replace("void ", "").replace("dofb::", "")
+        v = float(r[iv].replace(",", ""))
+        v = v / 1000.0 if r[iu] in ("ns", "nsecond") else v
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(a[1] for a in agg.values())
+    print(f"| kernel | launches | total µs | share |\n|---|---:|---:|---:|")
+    for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"| `{k[:80]}` | {a[0]} | {a[1]:.1f} | {100 * a[1] / tot:.1f}% |")
+    tc = sum(a[1] for k, a in agg.items() if k.startswith("tc_"))
+    print(f"\ntcgen05 kernels (`tc_*`): {100 * tc / tot:.1f}% of the device time of this capture; total {tot / 1000:.2f} ms over {sum(a[0] for a in agg.values())} launches.\n")
+
+
+def rep_table(rep):
+    txt = subprocess.run(["ncu", "-i", str(OUT / rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(txt.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = [hdr.index(c) for c in COLS if c in hdr]
+    print("| " + " | ".join(hdr[i].replace("__", "\\_\\_") for i in idx) + " |\n|" + "---|" * len(idx))
+    print("| " + " | ".join(units[i] for i in idx) + " |")
+    for r in rows[2:]:
+        print("| " + " | ".join(re.sub(r"\(.*", "", r[i]).replace("void ", "")[:60] if i == idx[0] else r[i] for i in idx) + " |")
+    print()
+
+
+print(f"## Launch list (`ncu --metrics gpu__time_duration.sum`; full CSV: launches_{math}.csv)\n")
+launch_table()
+for rep, title in (("prof_tc_gemm.ncu-rep", "tcgen05 gather-GEMM (conv fwd / dgrad / transposed conv)"), ("prof_tc_wgrad.ncu-rep", "tcgen05 weight gradient"),
+                   ("prof_hbm.ncu-rep", "streaming kernels (flow heads, warp+loss, Adam)")):
+    if (OUT / rep).exists():
+        print(f"## {title}, `ncu --set full`  (`gpurun_out/{rep}`)\n")
+        rep_table(rep)

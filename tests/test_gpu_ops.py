@@ -342,6 +342,17 @@ def test_elu_bwd():
     ops.elu_bwd(ops.Slab(gb, 16, 32), ops.Slab(yb, 8, 32), db)
     assert rel(gb[..., 16:48], xr.grad) < 1e-6
     assert rel(db - 0.5, xr.grad.sum(dim=(0, 1, 2))) < 1e-5          # fused BiasAddGrad
+    # shadow-only form (bf16 math): g itself stays untouched, the bf16 shadow receives the rounded result, db as before
+    gb2 = torch.zeros(2, 5, 6, 64, device="cuda")
+    gb2[..., 16:48] = gr.cuda()
+    keep = gb2.clone()
+    g16 = torch.zeros(gb2.shape, dtype=torch.bfloat16, device="cuda")
+    db2 = torch.zeros(32, device="cuda")
+    ops.elu_bwd(ops.Slab(gb2, 16, 32, g16), ops.Slab(yb, 8, 32), db2, shadow_only=True)
+    assert torch.equal(gb2, keep)
+    assert torch.equal(g16[..., 16:48], gb[..., 16:48].to(torch.bfloat16))
+    assert float(g16[..., :16].abs().max()) == 0.0 and float(g16[..., 48:].abs().max()) == 0.0
+    assert rel(db2, xr.grad.sum(dim=(0, 1, 2))) < 1e-5
 
 
 def test_adam_matches_tf_form():

@@ -246,6 +246,24 @@ def test_bf16_conv1_fwd_and_wgrad_match_simt(B, H, W, ci):
     assert rel(dw1, dw0) < BF_TOL
 
 
+@pytest.mark.parametrize("B,h,w,c,ld", [(4, 6, 8, 1024, 1024), (2, 12, 16, 1026, 1088), (3, 24, 32, 770, 832)])
+def test_head_fwd_through_the_gather_gemm(B, h, w, c, ld):
+    """Coarse-scale flow heads (3x3 conv to 2 channels, output pitch 2) through the tensor-core gather-GEMM vs the SIMT head kernel."""
+    from deepof_b200 import ops
+    g = torch.Generator().manual_seed(B + h + c)
+    x = _buf(B, h, w, ld, c, g)
+    wt = (torch.randn(3, 3, c, 2, generator=g) / math.sqrt(9 * c)).cuda()
+    b = (torch.randn(2, generator=g) * 0.1).cuda()
+    pr0 = torch.zeros(B, h, w, 2, device="cuda")
+    ops.head_fwd(ops.Slab(x, 0, c), wt, b, pr0)
+    geom = ops.conv_geom(B, h, w, c, 2, 3, 1)
+    for mth, tol in ((ops.MATH_TF32, TOL), (ops.MATH_BF16, BF_TOL)):
+        pr1 = torch.full_like(pr0, 7.0)
+        ops.conv_fwd(geom, ops.Slab(x, 0, c, _shadow(x)), wt, b, ops.full(pr1), ops.ACT_NONE, mth)
+        torch.cuda.synchronize()
+        assert rel(pr1, pr0) < tol, mth
+
+
 def test_conv_fwd_accumulate_flag():
     """ACT_ACCUMULATE: y += conv(x) + bias in all three math modes (used where a transposed conv's input gradient lands second)."""
     from deepof_b200 import ops
