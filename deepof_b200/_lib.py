@@ -65,6 +65,7 @@ SIGNATURES = {
     "dofb_elu_bwd_shadow": (_I, [_P, _I, _P, _I, _LL, _I, _P, _P, _P]),
     "dofb_invalidate_weight_cache": (None, []),
     "dofb_enable_weight_cache": (None, [_I]),
+    "dofb_enable_cta_pairs": (None, [_I]),
     "dofb_head_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "dofb_head_dgrad": (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _P]),
     "dofb_head_wgrad": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P]),

@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include <unordered_map>
 #include <mutex>
 #include <vector>
@@ -70,6 +71,82 @@ __device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *map, u
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
+// ---- thread-block clusters / CTA pairs (cta_group::2) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(const void *p, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    // (default .release.cta semantics as in CUTLASS' ClusterBarrier::arrive: a cluster-scope release would first drain every global
+    // store this thread has in flight -- measured: ~1000 cycles per arrive, which throttled the whole pipeline)
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads issued by either CTA of a pair; the bytes are accounted on the mbarrier at `bar_cluster_addr` (the leader's)
+__device__ __forceinline__ void tma2_load_2d(void *dst, const CUtensorMap *map, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(void *dst, const CUtensorMap *map, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_5d(void *dst, const CUtensorMap *map, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3,
+                                             int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// M = 256 across the CTA pair (each CTA: its own 128 rows of A and HALF of the N rows of B; D rows 0-127 land in the leader's TMEM,
+// rows 128-255 in the peer's); issued by ONE thread of the leader CTA
+template <bool BF>
+__device__ __forceinline__ void umma2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if (BF)
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+            "}" ::"r"(d_tmem),
+            "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+            "}" ::"r"(d_tmem),
+            "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+}
+// arrives on the mbarrier at this shared-memory offset in BOTH CTAs of the pair when the leader's MMAs so far have completed
+__device__ __forceinline__ void umma2_commit_both(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -224,13 +301,26 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // BF = false: fp32 activations/weights fed as TF32 (32 channels per 128-byte K block, UMMA_K = 8);
 // BF = true : bf16 shadows of the activations + bf16 packed weights (64 channels per K block, UMMA_K = 16): same bytes per stage,
 //             twice the MMA rate and twice the K per byte fetched from L2.  Accumulation and the epilogue stay fp32.
-template <int BN, int STAGES, bool BF>
+// CG2 = true (BN = 256): CTA PAIRS (cluster of 2, tcgen05 cta_group::2).  The pair computes a 256-row x 256-column tile: each CTA gathers
+// the A rows of its own 128-pixel M tile and only HALF of the weight tile (128 of the 256 B rows); the leader's MMA thread issues
+// M = 256 instructions that read B from both CTAs' shared memory and write rows 0-127 to its own TMEM, rows 128-255 to the peer's.
+// Per 128x256x64 k-block a CTA then pulls 16 + 16 KB instead of 16 + 32 KB through the L2->SM path, which is the chip-wide limit
+// (~6300 B/cycle) the wide layers sit on.  Barriers: `full` lives in the leader (its own expect_tx for both CTAs' bytes + one remote
+// arrive of the peer's producer); `empty` / `acc_full` are signalled in both CTAs by a multicast tcgen05.commit; `acc_empty` of the
+// leader collects the 8 + 8 epilogue warps of both CTAs.
+template <int BN, int STAGES, bool BF, bool CG2 = false>
 __global__ void __launch_bounds__(TCG_THREADS, 1)
 tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ TcParams P) {
     constexpr int KELEMS = BF ? 64 : 32;             // channels per K block (128 bytes)
-    constexpr int B_BYTES = BN * TC_BK * 4;
-    constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+    static_assert(!CG2 || BN == 256, "CTA pairs are used for the 256-column tiles only");
+    constexpr int BROWS = CG2 ? BN / 2 : BN;          // B rows staged by this CTA
+    constexpr int B_BYTES = BROWS * TC_BK * 4;
+    // k-blocks per pipeline stage: the narrow tiles (BN <= 64) retire a k-block in 64-128 MMA cycles, faster than one producer thread and
+    // one barrier round trip can follow, so they move two k-blocks per stage (half the barrier traffic, four TMA boxes issued by four lanes)
+    constexpr int KPS = (BN <= 64 && !CG2) ? 2 : 1;
+    constexpr int SUB_BYTES = TC_A_BYTES + B_BYTES;
+    constexpr int STAGE_BYTES = KPS * SUB_BYTES;
     constexpr int ACC_COLS = BN < 32 ? 32 : BN;
     constexpr int TMEM_COLS = 2 * ACC_COLS;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -244,68 +334,110 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kiters = P.ntaps * P.ncb;
-    const int m_tiles = P.m_tiles, total_tiles = P.m_tiles * P.n_tiles;
+    const int siters = (kiters + KPS - 1) / KPS;         // pipeline-stage iterations per tile
+    // work units: tiles (single CTA) or PAIRS of M tiles (CTA pairs; an odd last pair has a phantom second tile: TMA zero-fills it,
+    // the epilogue finds no valid row)
+    const uint32_t rank = CG2 ? cluster_ctarank() : 0u;
+    const int m_units = CG2 ? (P.m_tiles + 1) / 2 : P.m_tiles;
+    const int total_tiles = m_units * P.n_tiles;
+    const int unit0 = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, unit_step = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], TCG_EPI_WARPS); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], CG2 ? 2 : 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], CG2 ? 2 * TCG_EPI_WARPS : TCG_EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == TCG_EPI_WARPS && lane == 0) { prefetch_tmap(&map_a); prefetch_tmap(&map_b); }
-    if (warp == TCG_EPI_WARPS + 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == TCG_EPI_WARPS + 1) {
+        if (CG2) tmem_alloc2(tmem_slot, TMEM_COLS);      // (the same warp of both CTAs)
+        else tmem_alloc(tmem_slot, TMEM_COLS);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (CG2) cluster_sync_all();                        // barrier inits + TMEM allocation visible in both CTAs
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == TCG_EPI_WARPS) {
-        // ===== TMA producer =====
+        // ===== TMA producer (one thread: UTMALDG takes uniform operands, so spreading the boxes over lanes only adds a divergence waterfall) =====
         if (lane == 0) {
-            int it = 0;                                   // running k-iteration count across tiles
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int mt = t % m_tiles, nt = t / m_tiles;
+            int it = 0;                                   // running stage-iteration count across tiles
+            for (int t = unit0; t < total_tiles; t += unit_step) {
+                const int mt = (t % m_units) * (CG2 ? 2 : 1) + (int)rank, nt = t / m_units;
                 const int tx = mt % P.tiles_x, ty = (mt / P.tiles_x) % P.tiles_y, tn = mt / (P.tiles_x * P.tiles_y);
-                const int ix0 = tx * P.TW, iy0 = ty * P.TH, in0 = tn * P.TN, n0 = nt * BN;
-                for (int k = 0; k < kiters; ++k, ++it) {
+                const int ix0 = tx * P.TW, iy0 = ty * P.TH, in0 = tn * P.TN, n0 = nt * BN + (int)rank * BROWS;
+                int tp = 0, cb = 0;                       // (tap, channel block) of the next k-block
+                for (int si = 0; si < siters; ++si, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
+                    const int nk = kiters - si * KPS < KPS ? kiters - si * KPS : KPS;      // k-blocks in this stage
                     mbar_wait(&empty_bar[s], ph ^ 1);
-                    const int tp = k / P.ncb, cb = k - tp * P.ncb;
-                    const TapInfo ti = P.taps[tp];
-                    uint8_t *sa = smem + s * STAGE_BYTES;
-                    uint8_t *sb = sa + TC_A_BYTES;
-                    mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-                    if (P.parity)
-                        tma_load_5d(sa, &map_a, &full_bar[s], ti.px * P.a_ld + P.a_coff + cb * KELEMS, ix0 + ti.ox, ti.py, iy0 + ti.oy, in0);
-                    else
-                        tma_load_4d(sa, &map_a, &full_bar[s], P.a_coff + cb * KELEMS, ix0 + ti.ox, iy0 + ti.oy, in0);
-                    tma_load_2d(sb, &map_b, &full_bar[s], ti.wk + cb * KELEMS, n0);
+                    uint32_t lbar = 0;
+                    if (CG2) {
+                        lbar = map_to_cta(&full_bar[s], 0);                          // the leader's barrier counts both CTAs' bytes
+                        if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+                        else mbar_arrive_cluster(lbar);
+                    } else {
+                        mbar_expect_tx(&full_bar[s], nk * SUB_BYTES);
+                    }
+#pragma unroll
+                    for (int j = 0; j < KPS; ++j) {
+                        if (j < nk) {
+                            const TapInfo ti = P.taps[tp];
+                            uint8_t *sa = smem + s * STAGE_BYTES + j * SUB_BYTES;
+                            if (CG2) {
+                                if (P.parity)
+                                    tma2_load_5d(sa, &map_a, lbar, ti.px * P.a_ld + P.a_coff + cb * KELEMS, ix0 + ti.ox, ti.py, iy0 + ti.oy, in0);
+                                else
+                                    tma2_load_4d(sa, &map_a, lbar, P.a_coff + cb * KELEMS, ix0 + ti.ox, iy0 + ti.oy, in0);
+                                tma2_load_2d(sa + TC_A_BYTES, &map_b, lbar, ti.wk + cb * KELEMS, n0);
+                            } else {
+                                if (P.parity)
+                                    tma_load_5d(sa, &map_a, &full_bar[s], ti.px * P.a_ld + P.a_coff + cb * KELEMS, ix0 + ti.ox, ti.py, iy0 + ti.oy, in0);
+                                else
+                                    tma_load_4d(sa, &map_a, &full_bar[s], P.a_coff + cb * KELEMS, ix0 + ti.ox, iy0 + ti.oy, in0);
+                                tma_load_2d(sa + TC_A_BYTES, &map_b, &full_bar[s], ti.wk + cb * KELEMS, n0);
+                            }
+                            if (++cb == P.ncb) { cb = 0; ++tp; }
+                        }
+                    }
                 }
             }
         }
     } else if (warp == TCG_EPI_WARPS + 1) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = BF ? make_idesc_bf16(TC_BM, BN) : make_idesc_tf32(TC_BM, BN);
+        // ===== MMA issuer (one thread; CTA pairs: of the leader CTA only) =====
+        if (lane == 0 && rank == 0) {
+            constexpr int UM = CG2 ? 2 * TC_BM : TC_BM;
+            constexpr uint32_t idesc = BF ? make_idesc_bf16(UM, BN) : make_idesc_tf32(UM, BN);
             int it = 0, lt = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
+            for (int t = unit0; t < total_tiles; t += unit_step, ++lt) {
                 const int acc = lt & 1;
-                mbar_wait(&acc_empty[acc], ((lt >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+                mbar_wait(&acc_empty[acc], ((lt >> 1) & 1) ^ 1);      // epilogue(s) have drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
-                for (int k = 0; k < kiters; ++k, ++it) {
+                for (int si = 0; si < siters; ++si, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
+                    const int nk = kiters - si * KPS < KPS ? kiters - si * KPS : KPS;
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
-                    const uint64_t da = make_desc_k128(sa), db = make_desc_k128(sa + TC_A_BYTES);
 #pragma unroll
-                    for (int kk = 0; kk < TC_BK / 8; ++kk)  // UMMA_K = 8 (tf32) / 16 (bf16) = 32 bytes: advance inside the 128 B swizzle row
-                        umma<BF>(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (k | kk) != 0);
-                    umma_commit(&empty_bar[s]);             // frees the smem slot when these MMAs retire
+                    for (int j = 0; j < KPS; ++j) {
+                        if (j < nk) {
+                            const uint32_t sa = smem_u32(smem + s * STAGE_BYTES + j * SUB_BYTES);
+                            const uint64_t da = make_desc_k128(sa), db = make_desc_k128(sa + TC_A_BYTES);
+#pragma unroll
+                            for (int kk = 0; kk < TC_BK / 8; ++kk) {  // UMMA_K = 8 (tf32) / 16 (bf16) = 32 bytes: advance inside the 128 B swizzle row
+                                if (CG2) umma2<BF>(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (si | j | kk) != 0);
+                                else umma<BF>(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (si | j | kk) != 0);
+                            }
+                        }
+                    }
+                    if (CG2) umma2_commit_both(&empty_bar[s]);  // frees the smem slot (of both CTAs) when these MMAs retire
+                    else umma_commit(&empty_bar[s]);
                 }
-                umma_commit(&acc_full[acc]);                // accumulator complete
+                if (CG2) umma2_commit_both(&acc_full[acc]);     // accumulator complete (both halves)
+                else umma_commit(&acc_full[acc]);
             }
         }
     } else {
@@ -324,8 +456,8 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const bool out_al = ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0) && (P.out_ld % 4 == 0);
         const bool elu = P.act == DOFB_ACT_ELU, has16 = P.out16 != nullptr, accum = P.accumulate != 0;
         int lt = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
-            const int mt = t % m_tiles, nt = t / m_tiles;
+        for (int t = unit0; t < total_tiles; t += unit_step, ++lt) {
+            const int mt = (t % m_units) * (CG2 ? 2 : 1) + (int)rank, nt = t / m_units;
             const int tx = mt % P.tiles_x, ty = (mt / P.tiles_x) % P.tiles_y, tn = mt / (P.tiles_x * P.tiles_y);
             const int ix = tx * P.TW + r % P.TW, iy = ty * P.TH + (r / P.TW) % P.TH, nn = tn * P.TN + r / (P.TW * P.TH);
             const int n0 = nt * BN;
@@ -440,14 +572,19 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[acc]);    // this warp's share of the accumulator is free again
+            if (lane == 0) {                                // this warp's share of the accumulator is free again
+                if (CG2) mbar_arrive_cluster(map_to_cta(&acc_empty[acc], 0));   // (the leader's barrier collects both CTAs)
+                else mbar_arrive(&acc_empty[acc]);
+            }
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG2) cluster_sync_all();                        // the peer may still be reading / being written through the pair's TMEM + smem
+    else __syncthreads();
     if (warp == TCG_EPI_WARPS + 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        if (CG2) tmem_dealloc2(tmem_base, TMEM_COLS);
+        else tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -544,6 +681,8 @@ static std::unordered_map<PackKey, PackEntry, PackKeyHash> g_pack;
 static std::mutex g_pack_mu;
 static unsigned long long g_weight_epoch = 1;      // bumped by dofb_invalidate_weight_cache() (the optimiser step)
 static bool g_cache_enabled = false;               // off: every call re-packs (always correct); on: caller promises to invalidate
+static bool g_cta_pairs = false;                   // cta_group::2 tiles for the 256-column layers (dofb_enable_cta_pairs)
+void enable_cta_pairs(int on) { g_cta_pairs = on != 0; }
 
 void invalidate_weight_cache() {
     std::lock_guard<std::mutex> lk(g_pack_mu);
@@ -586,20 +725,47 @@ static void choose_tile(int cnt_y, int cnt_x, int &TW, int &TH, int &TN) {
     TN = TC_BM / (TW * TH);
 }
 
-template <int BN, int STAGES, bool BF = false>
+template <int BN, int STAGES, bool BF = false, bool CG2 = false>
 static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &Pin, int tiles, int n_tiles, cudaStream_t st) {
-    constexpr int smem = STAGES * (TC_A_BYTES + BN * TC_BK * 4) + TCG_STG_BYTES + 1024 + 256;
+    constexpr int KPS = (BN <= 64 && !CG2) ? 2 : 1;
+    constexpr int smem = STAGES * KPS * (TC_A_BYTES + (CG2 ? BN / 2 : BN) * TC_BK * 4) + TCG_STG_BYTES + 1024 + 256;
     static_assert(smem <= 227 * 1024, "shared-memory budget");
     static bool configured = false;
     if (!configured) {
-        DOFB_CUDA_OK(cudaFuncSetAttribute(tc_gather_gemm_kernel<BN, STAGES, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        DOFB_CUDA_OK(cudaFuncSetAttribute(tc_gather_gemm_kernel<BN, STAGES, BF, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
     TcParams P = Pin;
     P.m_tiles = tiles; P.n_tiles = n_tiles;
+    if (CG2) {
+        // CTA pairs: one cluster of 2 per pair of M tiles, persistent over at most #SMs / 2 clusters
+        const long long units = (long long)((tiles + 1) / 2) * n_tiles;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(num_sms() / 2 * 2, 1, 1);
+        cfg.blockDim = dim3(TCG_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        // a pair needs both SMs of one TPC; parts with single-SM TPCs co-schedule fewer than #SMs / 2 clusters, and a persistent grid
+        // larger than what is co-resident would run in two waves
+        static int max_clusters = 0;
+        if (max_clusters == 0) {
+            DOFB_CUDA_OK(cudaOccupancyMaxActiveClusters(&max_clusters, tc_gather_gemm_kernel<BN, STAGES, BF, CG2>, &cfg));
+            if (max_clusters < 1) max_clusters = 1;
+            if (getenv("DOFB_VERBOSE")) fprintf(stderr, "deepof_b200: %d co-resident CTA pairs on %d SMs\n", max_clusters, num_sms());
+        }
+        const int clusters = (int)(units < max_clusters ? units : max_clusters);
+        cfg.gridDim = dim3(2 * clusters, 1, 1);
+        DOFB_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_gather_gemm_kernel<BN, STAGES, BF, CG2>, ma, mb, P));
+        count_launch();
+        return 0;
+    }
     const long long total = (long long)tiles * n_tiles;
     const int grid = (int)(total < num_sms() ? total : num_sms());
-    tc_gather_gemm_kernel<BN, STAGES, BF><<<grid, TCG_THREADS, smem, st>>>(ma, mb, P);
+    tc_gather_gemm_kernel<BN, STAGES, BF, CG2><<<grid, TCG_THREADS, smem, st>>>(ma, mb, P);
     DOFB_LAUNCH_OK();
     return 0;
 }
@@ -677,26 +843,32 @@ static int run_gather(const GatherSpec &G, const TcParams &Pin, cudaStream_t st)
     }
     int bn = n_rows > 128 ? 256 : (n_rows > 64 ? 128 : (n_rows > 32 ? 64 : 32));
     while (bn > 64 && (long long)tiles * ((n_rows + bn - 1) / bn) < num_sms()) bn >>= 1;   // small maps: more, narrower tiles
+    // 256-column tiles with enough M tiles to fill the GPU with pairs: CTA pairs (each CTA stages half of the weight tile)
+    const bool pairs = g_cta_pairs && bn == 256 && (long long)((tiles + 1) / 2) * ((n_rows + 255) / 256) >= num_sms() / 2;
     {
         const uint64_t dims[2] = {(uint64_t)taps_all * cpad, (uint64_t)n_rows};
         const uint64_t str[1] = {(uint64_t)taps_all * cpad * esz};
-        const uint32_t box[2] = {(uint32_t)kel, (uint32_t)bn};
+        const uint32_t box[2] = {(uint32_t)kel, (uint32_t)(pairs ? bn / 2 : bn)};
         if (make_map(&mb, wp, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, dt)) return 1;
     }
     const int n_tiles = (n_rows + bn - 1) / bn;
+    if (pairs) {
+        if (bf) return launch_tc<256, 6, true, true>(ma, mb, P, tiles, n_tiles, st);
+        return launch_tc<256, 6, false, true>(ma, mb, P, tiles, n_tiles, st);
+    }
     if (bf) {
         switch (bn) {
             case 256: return launch_tc<256, 4, true>(ma, mb, P, tiles, n_tiles, st);
             case 128: return launch_tc<128, 6, true>(ma, mb, P, tiles, n_tiles, st);
-            case 64: return launch_tc<64, 8, true>(ma, mb, P, tiles, n_tiles, st);
-            default: return launch_tc<32, 8, true>(ma, mb, P, tiles, n_tiles, st);
+            case 64: return launch_tc<64, 4, true>(ma, mb, P, tiles, n_tiles, st);
+            default: return launch_tc<32, 5, true>(ma, mb, P, tiles, n_tiles, st);
         }
     }
     switch (bn) {
         case 256: return launch_tc<256, 4>(ma, mb, P, tiles, n_tiles, st);
         case 128: return launch_tc<128, 6>(ma, mb, P, tiles, n_tiles, st);
-        case 64: return launch_tc<64, 8>(ma, mb, P, tiles, n_tiles, st);
-        default: return launch_tc<32, 8>(ma, mb, P, tiles, n_tiles, st);
+        case 64: return launch_tc<64, 4>(ma, mb, P, tiles, n_tiles, st);
+        default: return launch_tc<32, 5>(ma, mb, P, tiles, n_tiles, st);
     }
 }
 
@@ -1174,15 +1346,15 @@ int tc_conv1_fwd(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, in
         switch (bn) {
             case 256: return launch_tc<256, 4, true>(ma, mb, P, tiles, n_tiles, st);
             case 128: return launch_tc<128, 6, true>(ma, mb, P, tiles, n_tiles, st);
-            case 64: return launch_tc<64, 8, true>(ma, mb, P, tiles, n_tiles, st);
-            default: return launch_tc<32, 8, true>(ma, mb, P, tiles, n_tiles, st);
+            case 64: return launch_tc<64, 4, true>(ma, mb, P, tiles, n_tiles, st);
+            default: return launch_tc<32, 5, true>(ma, mb, P, tiles, n_tiles, st);
         }
     }
     switch (bn) {
         case 256: return launch_tc<256, 4>(ma, mb, P, tiles, n_tiles, st);
         case 128: return launch_tc<128, 6>(ma, mb, P, tiles, n_tiles, st);
-        case 64: return launch_tc<64, 8>(ma, mb, P, tiles, n_tiles, st);
-        default: return launch_tc<32, 8>(ma, mb, P, tiles, n_tiles, st);
+        case 64: return launch_tc<64, 4>(ma, mb, P, tiles, n_tiles, st);
+        default: return launch_tc<32, 5>(ma, mb, P, tiles, n_tiles, st);
     }
 }
 

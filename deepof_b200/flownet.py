@@ -18,6 +18,7 @@ Memory plan (NHWC fp32, sized for 180 GB HBM3e; B=32 @384x512 needs ~3 GB):
 from __future__ import annotations
 
 import math
+import os
 from collections import OrderedDict
 
 import torch
@@ -138,6 +139,7 @@ class FlowNetS:
         self._plan()
         self.warp_loss = ops.WarpLoss(self.device)
         ops._lib.load().dofb_enable_weight_cache(1)     # this engine invalidates after every parameter change
+        ops._lib.load().dofb_enable_cta_pairs(0 if os.environ.get("DOFB_CTA_PAIRS", "1") == "0" else 1)   # cta_group::2 tiles for the wide layers
         self.profile = None            # list of (tag, start_event, end_event) when per-launch timing is on
         if seed is not None:
             self.init_params(seed)

@@ -140,7 +140,9 @@ void dofb_invalidate_weight_cache(void);
 /* Off by default (every call re-packs its weights: always correct).  A caller that enables the cache promises to call
  * dofb_invalidate_weight_cache() after changing weight values; the training engine does (once per Adam step). */
 void dofb_enable_weight_cache(int on);
-
+/* Tensor-core tiles of 256 columns as CTA pairs (thread-block clusters of 2, tcgen05 cta_group::2: each CTA stages half of the weight tile).
+ * Process-wide switch; results are identical up to fp32 summation order (same per-tile K order: bit-identical in practice). */
+void dofb_enable_cta_pairs(int on);
 /* ---- BF16 tensor-core math (tcgen05 kind::f16, bf16 operands, fp32 accumulate + fp32 epilogue) ----
  * Activations keep their fp32 NHWC buffers; every producer additionally writes a bf16 "shadow" with the same pitch in elements
  * (a multiple of 64), and the tensor-core consumers read the shadows: half the bytes per K element and twice the MMA rate of the
