@@ -1014,14 +1014,19 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) {
 
 // BF = false: fp32 operands as TF32 (32-channel x 32-pixel regions, 32-byte-atom swizzle); BF = true: bf16 shadows (64-channel x
 // 64-pixel regions, plain 128-byte swizzle, UMMA_K = 16).  Same bytes per stage, twice the pixels (K) per stage.
-template <int BN, int STAGES, bool BF>
+// CG2 = true: CTA pairs along the work-item axis (cluster 2x1x1 with the items on grid x, cta_group::2, M = 256): the two CTAs hold DIFFERENT A tiles (two taps /
+// channel blocks / packed tap groups of the same column block) and each stages only HALF of the shared dy tile -- the operand that is
+// otherwise re-fetched from L2 by every tap.  Same barrier protocol as the gather-GEMM pairs.
+template <int BN, int STAGES, bool BF, bool CG2 = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy,
                 const __grid_constant__ WgParams P) {
     constexpr int CH = BF ? 64 : 32;                    // channels per region (128 bytes)
     constexpr int REGION = (BF ? 64 : 32) * 128;        // bytes: pixels per stage x 128
     constexpr int A_REGS = TC_BM / CH, B_REGS = BN / CH;
-    constexpr int A_BYTES = A_REGS * REGION, B_BYTES = B_REGS * REGION;
+    constexpr int B_OWN = CG2 ? B_REGS / 2 : B_REGS;    // dy regions staged by this CTA
+    static_assert(!CG2 || (B_REGS >= 2 && B_REGS % 2 == 0), "CTA pairs need at least two column regions");
+    constexpr int A_BYTES = A_REGS * REGION, B_BYTES = B_OWN * REGION;
     constexpr int KADV = BF ? 128 : 64;                 // descriptor units (16 B) per MMA along K: 16 or 8 pixel rows of 128 B
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
@@ -1033,23 +1038,34 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_bar + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int item = blockIdx.y;
-    const int nblk = item % P.n_nblk, mblk = (item / P.n_nblk) % P.n_mblk, tapi = item / (P.n_nblk * P.n_mblk);
+    // single CTA: column block fastest.  Pairs: the (tap, row block) index fastest, so that the two CTAs of a cluster (consecutive
+    // blockIdx.x) share the column block; an odd count leaves a phantom partner that repeats the last A tile and writes nothing.
+    const uint32_t rank = CG2 ? cluster_ctarank() : 0u;
+    const int item = CG2 ? blockIdx.x : blockIdx.y, split = CG2 ? blockIdx.y : blockIdx.x;   // (a CTA pair must be consecutive in x)
+    const int n_am = P.ntaps * P.n_mblk, n_am2 = (n_am + 1) & ~1;
+    const int am_raw = CG2 ? item % n_am2 : item / P.n_nblk;
+    const bool phantom = am_raw >= n_am;
+    const int am = phantom ? n_am - 1 : am_raw;
+    const int nblk = CG2 ? item / n_am2 : item % P.n_nblk, mblk = am % P.n_mblk, tapi = am / P.n_mblk;
     const int m0 = mblk * TC_BM, n0 = nblk * BN;
-    const int t_begin = blockIdx.x * P.tiles_per_split;
+    const int t_begin = split * P.tiles_per_split;
     const int t_end = min(P.tiles_total, t_begin + P.tiles_per_split);
     const int kiters = t_end - t_begin;
     if (kiters <= 0) return;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], CG2 ? 2 : 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(accum_bar, 1);
         fence_barrier_init();
     }
     if (warp == 4 && lane == 0) { prefetch_tmap(&map_x); prefetch_tmap(&map_dy); }
-    if (warp == 5) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp == 5) {
+        if (CG2) tmem_alloc2(tmem_slot, TMEM_COLS);
+        else tmem_alloc(tmem_slot, TMEM_COLS);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (CG2) cluster_sync_all();
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const TapInfo ti = P.taps[tapi];
@@ -1057,16 +1073,24 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
     if (warp == 4) {
         // ===== TMA producer: lane 0 owns the barrier hand-shake, lanes 0..(4+BN/32) issue one 4 KB box each =====
         // channel origin of the X / DY operand and how many 32-channel blocks each needs
-        const int x_c0 = P.swap ? n0 : m0, dy_c0 = P.swap ? m0 : n0;
-        const int x_blocks = P.swap ? B_REGS : A_REGS, dy_blocks = P.swap ? A_REGS : B_REGS;
+        const int x_c0 = P.swap ? n0 : m0, dy_c0 = (P.swap ? m0 : n0) + (CG2 ? (int)rank * (BN / 2) : 0);
+        const int x_blocks = P.swap ? B_REGS : A_REGS, dy_blocks = P.swap ? A_REGS : B_OWN;      // (pairs are never used in swap mode)
         for (int it = 0; it < kiters; ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1;
+            uint32_t lbar = 0;
             if (lane == 0) {
                 mbar_wait(&empty_bar[s], ph ^ 1);
-                mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                if (CG2) {
+                    lbar = map_to_cta(&full_bar[s], 0);                  // the leader's barrier counts both CTAs' bytes
+                    if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+                    else mbar_arrive_cluster(lbar);
+                } else {
+                    mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                }
             }
             __syncwarp();
+            if (CG2) lbar = __shfl_sync(0xffffffffu, lbar, 0);
             const int tile = t_begin + it;
             const int tx = tile % P.tiles_x, ty = (tile / P.tiles_x) % P.tiles_y, tn = tile / (P.tiles_x * P.tiles_y);
             const int ix0 = tx * P.TW, iy0 = ty * P.TH, in0 = tn * P.TN;
@@ -1080,7 +1104,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                     // bf16: region j = filter row 2*tapi + j, all 64 elements of the chunk
                     const int kh = min(2 * tapi + (BF ? j : (j >> 1)), P.c1_kh - 1);   // (an odd kh count re-loads the last row; masked later)
                     const TapInfo tr = P.taps[kh];
-                    tma_load_5d(sx + j * REGION, &map_x, &full_bar[s], BF ? 0 : (j & 1) * 32, ix0, tr.py, iy0 + tr.oy, in0);
+                    if (CG2) tma2_load_5d(sx + j * REGION, &map_x, lbar, BF ? 0 : (j & 1) * 32, ix0, tr.py, iy0 + tr.oy, in0);
+                    else tma_load_5d(sx + j * REGION, &map_x, &full_bar[s], BF ? 0 : (j & 1) * 32, ix0, tr.py, iy0 + tr.oy, in0);
                 } else {
                     TapInfo tr = ti;
                     int c0 = x_c0 + j * CH;
@@ -1089,20 +1114,25 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                         tr = P.taps[min(tapi * P.pack_g + j / per, P.ntaps_real - 1)];
                         c0 = (j % per) * CH;
                     }
-                    if (P.parity)
-                        tma_load_5d(sx + j * REGION, &map_x, &full_bar[s], tr.px * P.x_ld + c0, ix0 + tr.ox, tr.py, iy0 + tr.oy, in0);
-                    else
-                        tma_load_4d(sx + j * REGION, &map_x, &full_bar[s], c0, ix0 + tr.ox, iy0 + tr.oy, in0);
+                    if (CG2) {
+                        if (P.parity) tma2_load_5d(sx + j * REGION, &map_x, lbar, tr.px * P.x_ld + c0, ix0 + tr.ox, tr.py, iy0 + tr.oy, in0);
+                        else tma2_load_4d(sx + j * REGION, &map_x, lbar, c0, ix0 + tr.ox, iy0 + tr.oy, in0);
+                    } else {
+                        if (P.parity) tma_load_5d(sx + j * REGION, &map_x, &full_bar[s], tr.px * P.x_ld + c0, ix0 + tr.ox, tr.py, iy0 + tr.oy, in0);
+                        else tma_load_4d(sx + j * REGION, &map_x, &full_bar[s], c0, ix0 + tr.ox, iy0 + tr.oy, in0);
+                    }
                 }
             } else if (lane < x_blocks + dy_blocks) {
                 const int j = lane - x_blocks;
-                tma_load_4d(sd + j * REGION, &map_dy, &full_bar[s], dy_c0 + j * CH, ix0, iy0, in0);
+                if (CG2) tma2_load_4d(sd + j * REGION, &map_dy, lbar, dy_c0 + j * CH, ix0, iy0, in0);
+                else tma_load_4d(sd + j * REGION, &map_dy, &full_bar[s], dy_c0 + j * CH, ix0, iy0, in0);
             }
             __syncwarp();
         }
     } else if (warp == 5) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = (BF ? make_idesc_bf16(TC_BM, BN) : make_idesc_tf32(TC_BM, BN)) | (1u << 15) | (1u << 16);   // A, B MN-major
+        if (lane == 0 && rank == 0) {
+            constexpr int UM = CG2 ? 2 * TC_BM : TC_BM;
+            constexpr uint32_t idesc = (BF ? make_idesc_bf16(UM, BN) : make_idesc_tf32(UM, BN)) | (1u << 15) | (1u << 16);   // A, B MN-major
             for (int it = 0; it < kiters; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
@@ -1111,11 +1141,15 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
                 const uint64_t da = make_desc_mn<BF>(sa, REGION), db = make_desc_mn<BF>(sa + A_BYTES, REGION);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)             // 8 (tf32) / 16 (bf16) pixels per MMA
-                    umma<BF>(tmem_base, da + (uint64_t)(k * KADV), db + (uint64_t)(k * KADV), idesc, (it | k) != 0);
-                umma_commit(&empty_bar[s]);
+                for (int k = 0; k < 4; ++k) {           // 8 (tf32) / 16 (bf16) pixels per MMA
+                    if (CG2) umma2<BF>(tmem_base, da + (uint64_t)(k * KADV), db + (uint64_t)(k * KADV), idesc, (it | k) != 0);
+                    else umma<BF>(tmem_base, da + (uint64_t)(k * KADV), db + (uint64_t)(k * KADV), idesc, (it | k) != 0);
+                }
+                if (CG2) umma2_commit_both(&empty_bar[s]);
+                else umma_commit(&empty_bar[s]);
             }
-            umma_commit(accum_bar);
+            if (CG2) umma2_commit_both(accum_bar);
+            else umma_commit(accum_bar);
         }
     } else {
         const int r = warp * 32 + lane;
@@ -1127,6 +1161,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         for (int j = 0; j < BN / 32; ++j) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * 32), v);
+            if (phantom) continue;
             if (P.conv1) {
                 const int kh = 2 * tapi + (r >> 6), kw = (r & 63) >> 3, ci = r & 7;
                 if (kh >= P.c1_kh || kw >= P.c1_kw || ci >= P.CI) continue;
@@ -1156,22 +1191,41 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
         }
         tc_fence_before();
     }
-    __syncthreads();
+    if (CG2) cluster_sync_all();
+    else __syncthreads();
     if (warp == 5) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        if (CG2) tmem_dealloc2(tmem_base, TMEM_COLS);
+        else tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
-template <int BN, int STAGES, bool BF = false>
+template <int BN, int STAGES, bool BF = false, bool CG2 = false>
 static int launch_wg(const CUtensorMap &mx, const CUtensorMap &md, const WgParams &P, int splits, int items, cudaStream_t st) {
-    constexpr int smem = STAGES * (4 + BN / 32) * WG_REGION + 1024 + 256;      // identical for both operand types
+    constexpr int smem = STAGES * (TC_BM + (CG2 ? BN / 2 : BN)) * 128 + 1024 + 256;      // (A + B rows) x 128 bytes per stage, both operand types
+    static_assert(smem <= 227 * 1024, "shared-memory budget");
     static bool configured = false;
     if (!configured) {
-        DOFB_CUDA_OK(cudaFuncSetAttribute(tc_wgrad_kernel<BN, STAGES, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        DOFB_CUDA_OK(cudaFuncSetAttribute(tc_wgrad_kernel<BN, STAGES, BF, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    tc_wgrad_kernel<BN, STAGES, BF><<<dim3(splits, items, 1), TC_THREADS, smem, st>>>(mx, md, P);
+    if (CG2) {
+        // `items` = (tap, row block) count rounded up to even, times the column blocks; clusters of 2 along x (cta_group::2 pairs must be)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(items, splits, 1);
+        cfg.blockDim = dim3(TC_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        if (getenv("DOFB_VERBOSE")) fprintf(stderr, "deepof_b200: wgrad pairs grid (%d, %d) smem %d\n", splits, items, smem);
+        DOFB_CUDA_OK(cudaLaunchKernelEx(&cfg, tc_wgrad_kernel<BN, STAGES, BF, CG2>, mx, md, P));
+        count_launch();
+        return 0;
+    }
+    tc_wgrad_kernel<BN, STAGES, BF, CG2><<<dim3(splits, items, 1), TC_THREADS, smem, st>>>(mx, md, P);
     DOFB_LAUNCH_OK();
     return 0;
 }
@@ -1227,7 +1281,9 @@ int tc_conv_wgrad(const dofb_conv_geom *g, const float *x, int x_ld, const float
     if (bf && bn < 64) bn = 64;
     P.n_mblk = (P.m_valid + TC_BM - 1) / TC_BM;
     P.n_nblk = (n_ch + bn - 1) / bn;
-    const int items = P.ntaps * P.n_mblk * P.n_nblk;
+    // CTA pairs (two A tiles share one dy tile, half of it staged per CTA): any non-swapped layer with >= 128 columns
+    const bool pairs = g_cta_pairs && !P.swap && bn >= 128 && P.ntaps * P.n_mblk >= 2;
+    const int items = pairs ? ((P.ntaps * P.n_mblk + 1) & ~1) * P.n_nblk : P.ntaps * P.n_mblk * P.n_nblk;
     long long splits = ((long long)num_sms() * 2 + items - 1) / items;
     if (splits < 1) splits = 1;
     if (splits > P.tiles_total) splits = P.tiles_total;
@@ -1255,6 +1311,12 @@ int tc_conv_wgrad(const dofb_conv_geom *g, const float *x, int x_ld, const float
         const uint64_t str[3] = {(uint64_t)dy_ld * esz, (uint64_t)g->ow * dy_ld * esz, (uint64_t)g->oh * g->ow * dy_ld * esz};
         const uint32_t box[4] = {(uint32_t)CH, (uint32_t)P.TW, (uint32_t)P.TH, (uint32_t)P.TN};
         if (make_map(&md, db, 4, dims, str, box, swz, dt)) return 1;
+    }
+    if (pairs) {
+        if (bf) return bn == 256 ? launch_wg<256, 6, true, true>(mx, md, P, (int)splits, items, st)
+                                 : launch_wg<128, 8, true, true>(mx, md, P, (int)splits, items, st);
+        return bn == 256 ? launch_wg<256, 6, false, true>(mx, md, P, (int)splits, items, st)
+                         : launch_wg<128, 8, false, true>(mx, md, P, (int)splits, items, st);
     }
     if (bf) {
         switch (bn) {
