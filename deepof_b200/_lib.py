@@ -69,7 +69,7 @@ SIGNATURES = {
     "dofb_head_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "dofb_head_dgrad": (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _P]),
     "dofb_head_wgrad": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P]),
-    "dofb_uppr_fwd": (_I, [_P, _I, _I, _I, _P, _P, _P, _I, _P]),
+    "dofb_uppr_fwd": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
     "dofb_uppr_bwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "dofb_adam": (_I, [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _P]),
     "dofb_epe_sum": (_I, [_P, _P, _LL, _P, _P]),

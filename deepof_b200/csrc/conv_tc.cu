@@ -289,8 +289,26 @@ struct TcParams {
     int ntaps;
     int parity;                  // 0: rank-4 unit-stride map, 1: rank-5 stride-2 map
     int act, accumulate;
+    // several output sub-grids ("phases" of a strided input gradient / transposed conv) in ONE launch: phase q owns the global M tiles
+    // [m_begin, m_begin + m_tiles) and the taps [tap0, tap0 + ntaps); nphase <= 1: the scalar fields above describe the only phase
+    int nphase;
+    struct Phase { int y0, x0, cnt_y, cnt_x, tiles_x, tiles_y, m_begin, tap0, ntaps; } ph[4];
     TapInfo taps[TC_MAX_TAPS];
 };
+
+struct TileView { int y0, x0, cnt_y, cnt_x, tiles_x, tiles_y, tap0, ntaps, mt; };
+__device__ __forceinline__ TileView tile_view(const TcParams &P, int mt) {
+    TileView v;
+    if (P.nphase <= 1) {
+        v.y0 = P.y0; v.x0 = P.x0; v.cnt_y = P.cnt_y; v.cnt_x = P.cnt_x; v.tiles_x = P.tiles_x; v.tiles_y = P.tiles_y; v.tap0 = 0; v.ntaps = P.ntaps; v.mt = mt;
+        return v;
+    }
+    int q = 0;
+    while (q + 1 < P.nphase && mt >= P.ph[q + 1].m_begin) ++q;
+    v.y0 = P.ph[q].y0; v.x0 = P.ph[q].x0; v.cnt_y = P.ph[q].cnt_y; v.cnt_x = P.ph[q].cnt_x; v.tiles_x = P.ph[q].tiles_x; v.tiles_y = P.ph[q].tiles_y;
+    v.tap0 = P.ph[q].tap0; v.ntaps = P.ph[q].ntaps; v.mt = mt - P.ph[q].m_begin;
+    return v;
+}
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -333,8 +351,6 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int kiters = P.ntaps * P.ncb;
-    const int siters = (kiters + KPS - 1) / KPS;         // pipeline-stage iterations per tile
     // work units: tiles (single CTA) or PAIRS of M tiles (CTA pairs; an odd last pair has a phantom second tile: TMA zero-fills it,
     // the epilogue finds no valid row)
     const uint32_t rank = CG2 ? cluster_ctarank() : 0u;
@@ -363,10 +379,13 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         if (lane == 0) {
             int it = 0;                                   // running stage-iteration count across tiles
             for (int t = unit0; t < total_tiles; t += unit_step) {
-                const int mt = (t % m_units) * (CG2 ? 2 : 1) + (int)rank, nt = t / m_units;
-                const int tx = mt % P.tiles_x, ty = (mt / P.tiles_x) % P.tiles_y, tn = mt / (P.tiles_x * P.tiles_y);
+                const int nt = t / m_units;
+                const TileView V = tile_view(P, (t % m_units) * (CG2 ? 2 : 1) + (int)rank);
+                const int mt = V.mt;
+                const int tx = mt % V.tiles_x, ty = (mt / V.tiles_x) % V.tiles_y, tn = mt / (V.tiles_x * V.tiles_y);
                 const int ix0 = tx * P.TW, iy0 = ty * P.TH, in0 = tn * P.TN, n0 = nt * BN + (int)rank * BROWS;
-                int tp = 0, cb = 0;                       // (tap, channel block) of the next k-block
+                const int kiters = V.ntaps * P.ncb, siters = (kiters + KPS - 1) / KPS;
+                int tp = V.tap0, cb = 0;                  // (tap, channel block) of the next k-block
                 for (int si = 0; si < siters; ++si, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
@@ -415,6 +434,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 mbar_wait(&acc_empty[acc], ((lt >> 1) & 1) ^ 1);      // epilogue(s) have drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
+                const int kiters = tile_view(P, (t % m_units) * (CG2 ? 2 : 1)).ntaps * P.ncb, siters = (kiters + KPS - 1) / KPS;
                 for (int si = 0; si < siters; ++si, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
@@ -457,13 +477,15 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const bool elu = P.act == DOFB_ACT_ELU, has16 = P.out16 != nullptr, accum = P.accumulate != 0;
         int lt = 0;
         for (int t = unit0; t < total_tiles; t += unit_step, ++lt) {
-            const int mt = (t % m_units) * (CG2 ? 2 : 1) + (int)rank, nt = t / m_units;
-            const int tx = mt % P.tiles_x, ty = (mt / P.tiles_x) % P.tiles_y, tn = mt / (P.tiles_x * P.tiles_y);
+            const int nt = t / m_units;
+            const TileView V = tile_view(P, (t % m_units) * (CG2 ? 2 : 1) + (int)rank);
+            const int mt = V.mt;
+            const int tx = mt % V.tiles_x, ty = (mt / V.tiles_x) % V.tiles_y, tn = mt / (V.tiles_x * V.tiles_y);
             const int ix = tx * P.TW + r % P.TW, iy = ty * P.TH + (r / P.TW) % P.TH, nn = tn * P.TN + r / (P.TW * P.TH);
             const int n0 = nt * BN;
-            const bool row_ok = ix < P.cnt_x && iy < P.cnt_y && nn < P.B;
+            const bool row_ok = ix < V.cnt_x && iy < V.cnt_y && nn < P.B;
             // element offset of this thread's output pixel (-1: no pixel); fetched by the storing lanes through shuffles
-            const long long my_off = row_ok ? (((long long)nn * P.rh + P.y0 + iy * P.rstep) * P.rw + P.x0 + ix * P.rstep) * P.out_ld : -1;
+            const long long my_off = row_ok ? (((long long)nn * P.rh + V.y0 + iy * P.rstep) * P.rw + V.x0 + ix * P.rstep) * P.out_ld : -1;
             const bool fast = __all_sync(0xffffffffu, row_ok) && out_al && n0 + BN <= P.n_valid;
             const int acc = lt & 1;
             // pixel offsets of the 4 rows this lane stores in every sub-chunk, and (accumulate) the old values of the first one,
@@ -814,17 +836,35 @@ static int run_gather(const GatherSpec &G, const TcParams &Pin, cudaStream_t st)
         }
         DOFB_LAUNCH_OK();
     }
-    for (int t = 0; t < P.ntaps; ++t) P.taps[t].wk *= cpad;     // caller stored the canonical tap index
+    const int taps_listed = P.nphase > 1 ? P.ph[P.nphase - 1].tap0 + P.ph[P.nphase - 1].ntaps : P.ntaps;
+    for (int t = 0; t < taps_listed; ++t) P.taps[t].wk *= cpad;     // caller stored the canonical tap index
     P.ncb = cpad / kel;
     P.a_coff = G.a_coff; P.a_ld = G.a_ld;
     P.out = G.out; P.out_ld = G.out_ld; P.out16 = G.accumulate ? nullptr : reinterpret_cast<__nv_bfloat16 *>(G.out16);
     P.bias = G.bias; P.n_valid = G.n_valid; P.rh = G.rh; P.rw = G.rw;
     P.act = G.act; P.accumulate = G.accumulate; P.B = G.B;
-    choose_tile(P.cnt_y, P.cnt_x, P.TW, P.TH, P.TN);
-    P.tiles_x = (P.cnt_x + P.TW - 1) / P.TW;
-    P.tiles_y = (P.cnt_y + P.TH - 1) / P.TH;
-    const int tiles_n = (G.B + P.TN - 1) / P.TN;
-    const int tiles = P.tiles_x * P.tiles_y * tiles_n;
+    int tiles;
+    if (P.nphase > 1) {
+        // one pixel-tile shape for all phases (their sub-grids differ by at most one row / column); the phase starts are kept even so that
+        // a CTA pair never straddles two phases (an odd phase ends in a phantom tile)
+        int my = 0, mx = 0;
+        for (int q = 0; q < P.nphase; ++q) { my = P.ph[q].cnt_y > my ? P.ph[q].cnt_y : my; mx = P.ph[q].cnt_x > mx ? P.ph[q].cnt_x : mx; }
+        choose_tile(my, mx, P.TW, P.TH, P.TN);
+        const int tiles_n = (G.B + P.TN - 1) / P.TN;
+        int begin = 0;
+        for (int q = 0; q < P.nphase; ++q) {
+            P.ph[q].tiles_x = (P.ph[q].cnt_x + P.TW - 1) / P.TW;
+            P.ph[q].tiles_y = (P.ph[q].cnt_y + P.TH - 1) / P.TH;
+            P.ph[q].m_begin = begin;
+            begin += (P.ph[q].tiles_x * P.ph[q].tiles_y * tiles_n + 1) & ~1;
+        }
+        tiles = begin;
+    } else {
+        choose_tile(P.cnt_y, P.cnt_x, P.TW, P.TH, P.TN);
+        P.tiles_x = (P.cnt_x + P.TW - 1) / P.TW;
+        P.tiles_y = (P.cnt_y + P.TH - 1) / P.TH;
+        tiles = P.tiles_x * P.tiles_y * ((G.B + P.TN - 1) / P.TN);
+    }
     // ---- tensor maps ----
     const CUtensorMapDataType dt = bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     CUtensorMap ma, mb;
@@ -918,30 +958,38 @@ int tc_conv_dgrad(const dofb_conv_geom *g, const float *dy, int dy_ld, const flo
     G.out = dx; G.out_ld = dx_ld; G.rh = g->ih; G.rw = g->iw; G.n_valid = g->ci; G.bias = bias; G.act = act; G.accumulate = accumulate;
     G.B = g->B;
     const int s = g->stride;
+    // all stride^2 phases (output sub-grids with their own sub-kernel taps) run in ONE persistent launch
+    TcParams P;
+    memset(&P, 0, sizeof(P));
+    P.rstep = s; P.parity = 0;
+    int nph = 0, nt = 0;
     for (int py = 0; py < s; ++py)
         for (int px = 0; px < s; ++px) {
-            TcParams P;
-            memset(&P, 0, sizeof(P));
-            P.rstep = s;
-            P.y0 = ((py - g->pad_t) % s + s) % s;
-            P.x0 = ((px - g->pad_l) % s + s) % s;
-            P.cnt_y = P.y0 < g->ih ? (g->ih - P.y0 + s - 1) / s : 0;
-            P.cnt_x = P.x0 < g->iw ? (g->iw - P.x0 + s - 1) / s : 0;
-            if (P.cnt_y == 0 || P.cnt_x == 0) continue;
-            P.parity = 0;
-            int nt = 0;
+            TcParams::Phase &H = P.ph[nph];
+            H.y0 = ((py - g->pad_t) % s + s) % s;
+            H.x0 = ((px - g->pad_l) % s + s) % s;
+            H.cnt_y = H.y0 < g->ih ? (g->ih - H.y0 + s - 1) / s : 0;
+            H.cnt_x = H.x0 < g->iw ? (g->iw - H.x0 + s - 1) / s : 0;
+            if (H.cnt_y == 0 || H.cnt_x == 0) continue;
+            H.tap0 = nt;
             for (int kh = py; kh < g->kh; kh += s)
                 for (int kw = px; kw < g->kw; kw += s) {
                     TapInfo &t = P.taps[nt++];
-                    t.oy = (short)((P.y0 + g->pad_t - kh) / s);   // exact: (y0 + pad_t - kh) is a multiple of s in this phase
-                    t.ox = (short)((P.x0 + g->pad_l - kw) / s);
+                    t.oy = (short)((H.y0 + g->pad_t - kh) / s);   // exact: (y0 + pad_t - kh) is a multiple of s in this phase
+                    t.ox = (short)((H.x0 + g->pad_l - kw) / s);
                     t.py = t.px = 0;
                     t.wk = kh * g->kw + kw;
                 }
-            P.ntaps = nt;
-            DOFB_CHECK_ARG(nt > 0, "dofb_conv_dgrad(tf32): phase without taps (kernel smaller than the stride)");
-            if (run_gather(G, P, st)) return 1;
+            H.ntaps = nt - H.tap0;
+            DOFB_CHECK_ARG(H.ntaps > 0, "dofb_conv_dgrad(tensor): phase without taps (kernel smaller than the stride)");
+            ++nph;
         }
+    if (nph == 0) return 0;
+    if (nph == 1) {     // (stride 1, or degenerate maps): plain single-phase description
+        P.y0 = P.ph[0].y0; P.x0 = P.ph[0].x0; P.cnt_y = P.ph[0].cnt_y; P.cnt_x = P.ph[0].cnt_x; P.ntaps = P.ph[0].ntaps;
+    }
+    P.nphase = nph;
+    if (run_gather(G, P, st)) return 1;
     return 0;
 }
 

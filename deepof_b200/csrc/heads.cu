@@ -4,6 +4,7 @@
 //   up_pr    = slim.conv2d_transpose(pr_s, 2, [4,4], stride=2, act=None)    :66,77,88,99,110
 // and their TF-autodiff gradients.  Weight layouts are TF's: pr [3,3,c,2]; up_pr [4,4,co=2,ci=2].
 #include "common.cuh"
+#include <cuda_bf16.h>
 
 namespace dofb {
 
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__(HW_WARPS * 32, 3) head_wgrad_kernel(const floa
 // ---- up_pr forward: y[b,Y,X,o] = bias[o] + sum_{kh,kw,i} pr[b,(Y+1-kh)/2,(X+1-kw)/2,i] * W[kh,kw,o,i] ----
 __global__ void __launch_bounds__(256) uppr_fwd_kernel(const float *__restrict__ pr, int B, int h, int w,
                                                        const float *__restrict__ Wt, const float *__restrict__ bias,
-                                                       float *__restrict__ Y, int y_ld) {
+                                                       float *__restrict__ Y, int y_ld, __nv_bfloat16 *__restrict__ Y16) {
     __shared__ float ws[64];
     if (threadIdx.x < 64) ws[threadIdx.x] = Wt[threadIdx.x];
     __syncthreads();
@@ -387,6 +388,7 @@ __global__ void __launch_bounds__(256) uppr_fwd_kernel(const float *__restrict__
             }
         }
         *reinterpret_cast<float2 *>(Y + p * y_ld) = make_float2(o0, o1);
+        if (Y16 != nullptr) *reinterpret_cast<__nv_bfloat162 *>(Y16 + p * y_ld) = __floats2bfloat162_rn(o0, o1);   // bf16 shadow of the concat slice
     }
 }
 
@@ -522,7 +524,7 @@ extern "C" int dofb_head_wgrad(const float *x, int x_ld, const float *dpr, int B
     return 0;
 }
 
-extern "C" int dofb_uppr_fwd(const float *pr, int B, int h, int w, const float *wt, const float *bias, float *y, int y_ld,
+extern "C" int dofb_uppr_fwd(const float *pr, int B, int h, int w, const float *wt, const float *bias, float *y, void *y_bf16, int y_ld,
                              void *stream) {
     DOFB_CHECK_ARG(pr && wt && bias && y && B > 0 && h > 0 && w > 0, "dofb_uppr_fwd: bad argument");
     DOFB_CHECK_ARG(y_ld % 2 == 0 && (reinterpret_cast<uintptr_t>(y) & 7u) == 0, "dofb_uppr_fwd: output slice must be 8-byte aligned with an even pitch");
@@ -530,7 +532,8 @@ extern "C" int dofb_uppr_fwd(const float *pr, int B, int h, int w, const float *
     long long blocks = (n + 255) / 256;
     const long long cap = (long long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
-    uppr_fwd_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(pr, B, h, w, wt, bias, y, y_ld);
+    DOFB_CHECK_ARG(y_bf16 == nullptr || (reinterpret_cast<uintptr_t>(y_bf16) & 3u) == 0, "dofb_uppr_fwd: bf16 shadow slice must be 4-byte aligned");
+    uppr_fwd_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(pr, B, h, w, wt, bias, y, y_ld, reinterpret_cast<__nv_bfloat16 *>(y_bf16));
     DOFB_LAUNCH_OK();
     return 0;
 }

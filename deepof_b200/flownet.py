@@ -373,8 +373,6 @@ class FlowNetS:
             self._k("deconv_fwd:" + R["up"], ops.conv_dgrad, R["g"], x, P[R["up"] + "/weights"], P[R["up"] + "/biases"],
                     R["up_y"], ACT_ELU, False, mth)
             self._k("uppr_fwd:" + R["uppr"], ops.uppr_fwd, self.pr[s], P[R["uppr"] + "/weights"], P[R["uppr"] + "/biases"], R["pr_y"])
-            if mth == MATH_BF16:
-                self._k("cast:" + R["uppr"], ops.cast_bf16, R["pr_y"])
         self._head_fwd(1, self.feat[1][0])
         lw = [float(v) for v in loss_weight]
         self.loss_weight = lw

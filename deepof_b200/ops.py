@@ -232,7 +232,7 @@ def head_wgrad(x: Slab, dpr, dw, db):
 def uppr_fwd(pr, w, b, y: Slab):
     B, h, wd, _ = pr.shape
     assert y.c == 2 and y.h == 2 * h and y.w == 2 * wd
-    check(_lib.load().dofb_uppr_fwd(pr.data_ptr(), B, h, wd, w.data_ptr(), b.data_ptr(), y.ptr, y.ld, _stream()))
+    check(_lib.load().dofb_uppr_fwd(pr.data_ptr(), B, h, wd, w.data_ptr(), b.data_ptr(), y.ptr, y.ptr16, y.ld, _stream()))   # (+ bf16 shadow)
 
 
 def uppr_bwd(pr, dy: Slab, w, dpr, dw, db):

@@ -179,7 +179,8 @@ int dofb_head_wgrad(const float *x, int x_ld, const float *dpr, int B, int h, in
                     float *dwt, float *dbias, void *stream);
 /* up_pr = conv2d_transpose 4x4/2 (2 -> 2) linear, :66,77,88,99,110.  wt [4,4,2,2] = [kh,kw,co,ci] */
 int dofb_uppr_fwd(const float *pr, int B, int h, int w, const float *wt, const float *bias,
-                  float *y /* [B,2h,2w,y_ld] slice */, int y_ld, void *stream);
+                  float *y /* [B,2h,2w,y_ld] slice */, void *y_bf16 /* optional bf16 shadow of the same slice, may be NULL */, int y_ld,
+                  void *stream);
 int dofb_uppr_bwd(const float *pr, const float *dy, int dy_ld, int B, int h, int w, const float *wt,
                   float *dpr /* += */, float *dwt /* += */, float *dbias /* += */, void *stream);
 
