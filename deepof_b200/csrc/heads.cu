@@ -14,6 +14,18 @@ constexpr int HD_PX = 8;   // pixels per warp strip in the forward head
 // emits FMUL+FFMA+FADD per pair of multiply-adds; explicit packed FMAs halve the FMA instruction count instead.
 __device__ __forceinline__ void fma2(float2 &acc, float a, float2 b) { acc = __ffma2_rn(make_float2(a, a), b, acc); }
 
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// 16-byte copy that writes zeros instead when `valid` is false (src-size 0: nothing is read)
+__device__ __forceinline__ void cp_async16_zfill(void *smem_dst, const void *gsrc, bool valid) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(valid ? 16 : 0)
+                 : "memory");
+}
+
 // Sum 16 per-lane values across the warp with 16 shuffles (instead of 16 x 5): every step halves the number of values a lane
 // keeps.  On return lane L holds the warp total of value index L >> 1 (lanes 2i and 2i+1 hold the same number).
 __device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
@@ -45,38 +57,52 @@ __device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
 // into three rotating accumulator rows (the output rows y-1, y, y+1 it touches), so the 3x vertical re-read of a gather
 // formulation -- which made this kernel L2-bandwidth bound -- disappears.  S = (row index within the strip) mod 3 is a
 // template parameter so that the accumulator rotation is pure register renaming.
+// The work items (input row, 128-channel pass) stream through a per-warp shared-memory ring of HF_NBUF slots filled with cp.async
+// two items ahead (10 pixels x 16 B per lane each; out-of-range pixels / rows / channels are zero-filled by the copy itself).
 // The [3,3,c,2] filter is staged once per block in shared memory (<= 74 KB for c = 1026).
+constexpr int HF_NBUF = 3;
+constexpr int HF_RING_F4 = HF_NBUF * (HD_PX + 2) * 32;       // float4 per warp
+
+__device__ __forceinline__ void head_fwd_issue(float4 *ring, int slot, const float *__restrict__ X, int x_ld, int h, int w, int c4, int b, int iy,
+                                               int q, int x0) {
+    const bool row_ok = iy >= 0 && iy < h && q < c4;
+    const int cy = iy < 0 ? 0 : (iy >= h ? h - 1 : iy), cq = q < c4 ? q : 0;
+    const float *rowp = X + ((long long)b * h + cy) * w * x_ld + cq * 4;
+    float4 *dst = ring + slot * (HD_PX + 2) * 32;
+#pragma unroll
+    for (int i = 0; i < HD_PX + 2; ++i) {
+        const int sx = x0 - 1 + i;
+        const int cx = sx < 0 ? 0 : (sx >= w ? w - 1 : sx);
+        cp_async16_zfill(dst + i * 32, rowp + (long long)cx * x_ld, row_ok && sx >= 0 && sx < w);
+    }
+    cp_async_commit();
+}
+
 template <int S>
-__device__ __forceinline__ void head_fwd_row(float2 (&acc)[3][HD_PX], const float *__restrict__ X, int x_ld, int h, int w, int c4,
-                                             const float *wsm, int b, int iy, int x0, bool k0, bool k1, bool k2, int lane) {
-    if (iy < 0 || iy >= h) return;
-    const float *rowp = X + ((long long)b * h + iy) * w * x_ld;
-    for (int q = lane; q < c4; q += 32) {
-        float4 xv[HD_PX + 2];
+__device__ __forceinline__ void head_fwd_item(float2 (&acc)[3][HD_PX], const float4 *ring, int slot, int c4, const float *wsm, int q, bool k0,
+                                              bool k1, bool k2) {
+    if (q >= c4) return;                                    // (this lane has no channels in this pass; its slot holds zeros anyway)
+    float4 xv[HD_PX + 2];
+    const float4 *src = ring + slot * (HD_PX + 2) * 32;
 #pragma unroll
-        for (int i = 0; i < HD_PX + 2; ++i) {
-            const int sx = x0 - 1 + i;
-            xv[i] = (sx >= 0 && sx < w) ? __ldg(reinterpret_cast<const float4 *>(rowp + (long long)sx * x_ld + q * 4))
-                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+    for (int i = 0; i < HD_PX + 2; ++i) xv[i] = src[i * 32];
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-            // input row iy feeds output row iy - kh + 1, which lives in accumulator slot (S + 1 - kh) mod 3
-            const bool on = kh == 0 ? k0 : (kh == 1 ? k1 : k2);
-            if (!on) continue;                              // (warp-uniform: that output row is outside the strip)
-            float2 (&a)[HD_PX] = acc[(S + 4 - kh) % 3];
+    for (int kh = 0; kh < 3; ++kh) {
+        // input row iy feeds output row iy - kh + 1, which lives in accumulator slot (S + 1 - kh) mod 3
+        const bool on = kh == 0 ? k0 : (kh == 1 ? k1 : k2);
+        if (!on) continue;                                  // (warp-uniform: that output row is outside the strip)
+        float2 (&a)[HD_PX] = acc[(S + 4 - kh) % 3];
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                const float4 *wp = reinterpret_cast<const float4 *>(wsm + ((kh * 3 + kw) * c4 + q) * 8);
-                const float4 wa = wp[0], wb = wp[1];       // (c0o0,c0o1,c1o0,c1o1) (c2o0,c2o1,c3o0,c3o1)
+        for (int kw = 0; kw < 3; ++kw) {
+            const float4 *wp = reinterpret_cast<const float4 *>(wsm + ((kh * 3 + kw) * c4 + q) * 8);
+            const float4 wa = wp[0], wb = wp[1];           // (c0o0,c0o1,c1o0,c1o1) (c2o0,c2o1,c3o0,c3o1)
 #pragma unroll
-                for (int p = 0; p < HD_PX; ++p) {
-                    const float4 xx = xv[p + kw];
-                    fma2(a[p], xx.x, make_float2(wa.x, wa.y));
-                    fma2(a[p], xx.y, make_float2(wa.z, wa.w));
-                    fma2(a[p], xx.z, make_float2(wb.x, wb.y));
-                    fma2(a[p], xx.w, make_float2(wb.z, wb.w));
-                }
+            for (int p = 0; p < HD_PX; ++p) {
+                const float4 xx = xv[p + kw];
+                fma2(a[p], xx.x, make_float2(wa.x, wa.y));
+                fma2(a[p], xx.y, make_float2(wa.z, wa.w));
+                fma2(a[p], xx.z, make_float2(wb.x, wb.y));
+                fma2(a[p], xx.w, make_float2(wb.z, wb.w));
             }
         }
     }
@@ -95,21 +121,23 @@ __device__ __forceinline__ void head_fwd_emit(float2 (&acc)[3][HD_PX], float *__
     if ((lane & 1) == 0 && x0 + (idx >> 1) < w) pr[(((long long)b * h + oy) * w + x0) * 2 + idx] = tot + __ldg(bias + (idx & 1));
 }
 
-__global__ void __launch_bounds__(128, 3) head_fwd_kernel(const float *__restrict__ X, int x_ld, int B, int h, int w, int c,
+__global__ void __launch_bounds__(128, 2) head_fwd_kernel(const float *__restrict__ X, int x_ld, int B, int h, int w, int c,
                                                           const float *__restrict__ Wt, const float *__restrict__ bias,
                                                           float *__restrict__ pr, int R, int strips_y, int strips_x) {
-    extern __shared__ __align__(16) float wsm[];           // [9][c4*4][2], zero padded beyond c
+    extern __shared__ __align__(16) float hf_smem[];       // [4 warps] ring | filter [9][c4*4][2] (zero padded beyond c)
     const int c4 = (c + 3) >> 2;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int warps_per_block = blockDim.x >> 5;
+    float4 *ring = reinterpret_cast<float4 *>(hf_smem) + wid * HF_RING_F4 + lane;
+    float *wsm = hf_smem + warps_per_block * HF_RING_F4 * 4;
     for (int i = threadIdx.x; i < 9 * c4 * 8; i += blockDim.x) {
         const int tap = i / (c4 * 8), r = i - tap * (c4 * 8);
         wsm[i] = (r >> 1) < c ? __ldg(Wt + (long long)tap * c * 2 + r) : 0.f;
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int warps_per_block = blockDim.x >> 5;
+    const int n_pass = (c4 + 31) / 32;
     const long long n_strips = (long long)B * strips_y * strips_x;
-    for (long long sid = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); sid < n_strips;
-         sid += (long long)gridDim.x * warps_per_block) {
+    for (long long sid = (long long)blockIdx.x * warps_per_block + wid; sid < n_strips; sid += (long long)gridDim.x * warps_per_block) {
         const int sx = (int)(sid % strips_x);
         const int sy = (int)((sid / strips_x) % strips_y);
         const int b = (int)(sid / ((long long)strips_x * strips_y));
@@ -121,12 +149,26 @@ __global__ void __launch_bounds__(128, 3) head_fwd_kernel(const float *__restric
 #pragma unroll
             for (int p = 0; p < HD_PX; ++p) acc[s][p] = make_float2(0.f, 0.f);
         const int nrows = y1 - y0 + 2;                      // input rows y0-1 .. y1
+        const int n_items = nrows * n_pass;                 // item i = (row i / n_pass, pass i % n_pass), slot i % HF_NBUF
+        // prologue: items 0 and 1 in flight
+#pragma unroll
+        for (int i = 0; i < HF_NBUF - 1; ++i) {
+            if (i < n_items) head_fwd_issue(ring, i % HF_NBUF, X, x_ld, h, w, c4, b, y0 - 1 + i / n_pass, (i % n_pass) * 32 + lane, x0);
+            else cp_async_commit();
+        }
+        int it = 0;
         for (int t = 0; t < nrows; t += 3) {
             // row t (S = 0), t + 1 (S = 1), t + 2 (S = 2); input row iy = y0 - 1 + t feeds outputs iy+1 (kh 0), iy (kh 1), iy-1 (kh 2)
 #define DOFB_HEAD_ROW(SS)                                                                                                   \
             if (t + SS < nrows) {                                                                                           \
                 const int iy = y0 - 1 + t + SS;                                                                             \
-                head_fwd_row<SS>(acc, X, x_ld, h, w, c4, wsm, b, iy, x0, iy + 1 < y1, iy >= y0 && iy < y1, iy - 1 >= y0, lane); \
+                for (int pass = 0; pass < n_pass; ++pass, ++it) {                                                           \
+                    cp_async_wait<HF_NBUF - 2>();           /* item `it` has landed (one younger group may be pending) */   \
+                    head_fwd_item<SS>(acc, ring, it % HF_NBUF, c4, wsm, pass * 32 + lane, iy + 1 < y1, iy >= y0 && iy < y1, iy - 1 >= y0); \
+                    const int nx = it + HF_NBUF - 1;        /* refill the slot consumed in the previous iteration */          \
+                    if (nx < n_items) head_fwd_issue(ring, nx % HF_NBUF, X, x_ld, h, w, c4, b, y0 - 1 + nx / n_pass, (nx % n_pass) * 32 + lane, x0); \
+                    else cp_async_commit();                                                                                 \
+                }                                                                                                           \
                 if (iy - 1 >= y0) head_fwd_emit<SS>(acc, pr, bias, h, w, b, iy - 1, x0, lane);                             \
             }
             DOFB_HEAD_ROW(0)
@@ -134,6 +176,7 @@ __global__ void __launch_bounds__(128, 3) head_fwd_kernel(const float *__restric
             DOFB_HEAD_ROW(2)
 #undef DOFB_HEAD_ROW
         }
+        cp_async_wait<0>();
     }
 }
 
@@ -164,12 +207,6 @@ struct DprSeg {
     }
 };
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
 constexpr int HW_WARPS = 4;                                 // warps per block of the streaming gradient kernels
 constexpr int HW_SMEM = HW_WARPS * 32 * 32 * 16;            // per-warp ring: 32 pixels x 32 lanes x 16 B -> 64 KB per block
 
@@ -178,7 +215,7 @@ constexpr int HW_SMEM = HW_WARPS * 32 * 32 * 16;            // per-warp ring: 32
 // ACC (read-modify-write): the old values stream through the same cp.async shared-memory ring as X in the weight-gradient kernel
 // below (a whole segment in flight per warp), because a register look-ahead of a few pixels leaves the kernel DRAM-latency bound.
 template <bool ACC>
-__global__ void __launch_bounds__(HW_WARPS * 32, 2) head_dgrad_kernel(const float *__restrict__ dpr, int B, int h, int w, int c,
+__global__ void __launch_bounds__(HW_WARPS * 32, 3) head_dgrad_kernel(const float *__restrict__ dpr, int B, int h, int w, int c,
                                                                      const float *__restrict__ Wt, float *__restrict__ dX, int dx_ld,
                                                                      long long n_seg, int segs_per_row) {
     extern __shared__ __align__(16) float4 xring_all[];     // [warp][pixel slot][lane] (ACC only)
@@ -225,31 +262,44 @@ __global__ void __launch_bounds__(HW_WARPS * 32, 2) head_dgrad_kernel(const floa
         sg.col(0, c0);
         sg.col(1, c1);
         float *dst = dX + (row * w + x0) * dx_ld + chl;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        // one pixel; j is a compile-time constant in the unrolled full-segment path below (window shift = register renaming)
+        auto pixel = [&](int j) {
             if (ACC && (j & 7) == 0) cp_async_wait<3>();    // (see head_wgrad_kernel for the group arithmetic)
-            if (j < len) {
-                sg.col(j + 2, c2);
-                // four independent packed chains: (channels 0,1 | 2,3) x (u | v component of dpr)
-                float2 a01 = make_float2(0.f, 0.f), a23 = a01, b01 = a01, b23 = a01;
-                if (ACC) { const float4 old = xr[j * 32]; a01 = make_float2(old.x, old.y); a23 = make_float2(old.z, old.w); }
+            sg.col(j + 2, c2);
+            // four independent packed chains: (channels 0,1 | 2,3) x (u | v component of dpr); FFMA2 takes the scalar multiplier directly
+            float2 a01 = make_float2(0.f, 0.f), a23 = a01, b01 = a01, b23 = a01;
+            if (ACC) { const float4 old = xr[j * 32]; a01 = make_float2(old.x, old.y); a23 = make_float2(old.z, old.w); }
 #pragma unroll
-                for (int kh = 0; kh < 3; ++kh)
+            for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-                    for (int kw = 0; kw < 3; ++kw) {
-                        // dpr seen through tap (kh,kw) of the TRANSPOSED stencil: (y - kh + 1, x - kw + 1)
-                        const float2 gg = kw == 0 ? c2[2 - kh] : (kw == 1 ? c1[2 - kh] : c0[2 - kh]);
-                        const int tap = kh * 3 + kw;
-                        fma2(a01, gg.x, wr[tap][0][0]); fma2(b01, gg.y, wr[tap][0][1]);
-                        fma2(a23, gg.x, wr[tap][1][0]); fma2(b23, gg.y, wr[tap][1][1]);
-                    }
-                if (active) *reinterpret_cast<float4 *>(dst + (long long)j * dx_ld) = make_float4(a01.x + b01.x, a01.y + b01.y, a23.x + b23.x, a23.y + b23.y);
+                for (int kw = 0; kw < 3; ++kw) {
+                    // dpr seen through tap (kh,kw) of the TRANSPOSED stencil: (y - kh + 1, x - kw + 1)
+                    const float2 gg = kw == 0 ? c2[2 - kh] : (kw == 1 ? c1[2 - kh] : c0[2 - kh]);
+                    const int tap = kh * 3 + kw;
+                    fma2(a01, gg.x, wr[tap][0][0]); fma2(b01, gg.y, wr[tap][0][1]);
+                    fma2(a23, gg.x, wr[tap][1][0]); fma2(b23, gg.y, wr[tap][1][1]);
+                }
+            if (active) *reinterpret_cast<float4 *>(dst + (long long)j * dx_ld) = make_float4(a01.x + b01.x, a01.y + b01.y, a23.x + b23.x, a23.y + b23.y);
 #pragma unroll
-                for (int r = 0; r < 3; ++r) { c0[r] = c1[r]; c1[r] = c2[r]; }
-            }
+            for (int r = 0; r < 3; ++r) { c0[r] = c1[r]; c1[r] = c2[r]; }
             if (ACC) {
                 if (j < len_n) cp_async16(xr + j * 32, on + (long long)j * dx_ld);
                 if ((j & 7) == 7) cp_async_commit();
+            }
+        };
+        if (len == 32) {        // the common case: straight-line code, no per-pixel branch (a branch per pixel pins the window to fixed
+                                // registers and costs ~20 MOVs per pixel)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) pixel(j);
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < len; ++j) pixel(j);
+            if (ACC) {          // keep the group count of a full segment (the waits count groups)
+#pragma unroll 1
+                for (int j = len; j < 32; ++j) {
+                    if (j < len_n) cp_async16(xr + j * 32, on + (long long)j * dx_ld);
+                    if ((j & 7) == 7) cp_async_commit();
+                }
             }
         }
     }
@@ -313,28 +363,37 @@ __global__ void __launch_bounds__(HW_WARPS * 32, 3) head_wgrad_kernel(const floa
         float2 c0[3], c1[3], c2[3];
         sg.col(0, c0);
         sg.col(1, c1);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        auto pixel = [&](int j) {
             // groups in flight behind the one holding pixel j: the rest of this segment + what was already requested of the next = 3
             if ((j & 7) == 0) cp_async_wait<3>();
-            if (j < len) {
-                const float4 xv = xr[j * 32];
-                sg.col(j + 2, c2);
+            const float4 xv = xr[j * 32];
+            sg.col(j + 2, c2);
 #pragma unroll
-                for (int kh = 0; kh < 3; ++kh)
+            for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-                    for (int kw = 0; kw < 3; ++kw) {
-                        const float2 gg = kw == 0 ? c2[2 - kh] : (kw == 1 ? c1[2 - kh] : c0[2 - kh]);
-                        const int tap = kh * 3 + kw;
-                        fma2(acc[tap][0], xv.x, gg); fma2(acc[tap][1], xv.y, gg);
-                        fma2(acc[tap][2], xv.z, gg); fma2(acc[tap][3], xv.w, gg);
-                    }
+                for (int kw = 0; kw < 3; ++kw) {
+                    const float2 gg = kw == 0 ? c2[2 - kh] : (kw == 1 ? c1[2 - kh] : c0[2 - kh]);
+                    const int tap = kh * 3 + kw;
+                    fma2(acc[tap][0], xv.x, gg); fma2(acc[tap][1], xv.y, gg);
+                    fma2(acc[tap][2], xv.z, gg); fma2(acc[tap][3], xv.w, gg);
+                }
 #pragma unroll
-                for (int r = 0; r < 3; ++r) { c0[r] = c1[r]; c1[r] = c2[r]; }
-            }
+            for (int r = 0; r < 3; ++r) { c0[r] = c1[r]; c1[r] = c2[r]; }
             // slot j is free (its value sits in registers and has been used): refill it with pixel j of the next segment
             if (j < len_n) cp_async16(xr + j * 32, xn + (long long)j * x_ld);
             if ((j & 7) == 7) cp_async_commit();
+        };
+        if (len == 32) {        // straight-line code for the common full segment (see head_dgrad_kernel)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) pixel(j);
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < len; ++j) pixel(j);
+#pragma unroll 1
+            for (int j = len; j < 32; ++j) {            // keep the group count of a full segment
+                if (j < len_n) cp_async16(xr + j * 32, xn + (long long)j * x_ld);
+                if ((j & 7) == 7) cp_async_commit();
+            }
         }
     }
     cp_async_wait<0>();
@@ -465,12 +524,12 @@ extern "C" int dofb_head_fwd(const float *x, int x_ld, int B, int h, int w, int 
     long long blocks = (strips + 3) / 4;
     const long long cap = (long long)num_sms() * 8;
     if (blocks > cap) blocks = cap;
-    const int smem = 9 * ((c + 3) / 4) * 8 * (int)sizeof(float);
+    const int smem = 4 * HF_RING_F4 * 16 + 9 * ((c + 3) / 4) * 8 * (int)sizeof(float);      // rings of the 4 warps + the filter
     DOFB_CHECK_ARG(smem <= 200 * 1024, "dofb_head_fwd: %d channels do not fit the shared-memory filter stage", c);
-    static int configured = 0;
-    if (smem > 48 * 1024 && configured < smem) {
+    static bool configured = false;
+    if (!configured) {
         DOFB_CUDA_OK(cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = 200 * 1024;
+        configured = true;
     }
     head_fwd_kernel<<<(unsigned)blocks, 128, smem, as_stream(stream)>>>(x, x_ld, B, h, w, c, wt, bias, pr, R, strips_y, strips_x);
     DOFB_LAUNCH_OK();
@@ -493,7 +552,7 @@ extern "C" int dofb_head_dgrad(const float *dpr, int B, int h, int w, int c, con
     DOFB_CHECK_ARG(dpr && wt && dx && B > 0 && h > 0 && w > 0 && c > 0, "dofb_head_dgrad: bad argument");
     DOFB_CHECK_ARG(dx_ld % 4 == 0 && aligned16(dx) && dx_ld >= ((c + 3) & ~3), "dofb_head_dgrad: dx pitch %d must be a multiple of 4 covering c=%d", dx_ld, c);
     dim3 grid; long long n_seg; int spr;
-    head_stream_grid(B, h, w, c, 8, grid, n_seg, spr);
+    head_stream_grid(B, h, w, c, 12, grid, n_seg, spr);
     if (accumulate) {
         static bool configured = false;
         if (!configured) {
