@@ -24,6 +24,10 @@ class ConvGeom(C.Structure):
                 ("kh", C.c_int), ("kw", C.c_int), ("stride", C.c_int), ("pad_t", C.c_int), ("pad_l", C.c_int)]
 
 
+class PackJob(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("taps", C.c_int), ("ci", C.c_int), ("co", C.c_int), ("contract_ci", C.c_int)]
+
+
 class LossScale(C.Structure):
     _fields_ = [("flow", C.c_void_p), ("src", C.c_void_p), ("tgt", C.c_void_p),
                 ("recon", C.c_void_p), ("dflow", C.c_void_p), ("loss4", C.c_void_p),
@@ -66,6 +70,7 @@ SIGNATURES = {
     "dofb_invalidate_weight_cache": (None, []),
     "dofb_enable_weight_cache": (None, [_I]),
     "dofb_enable_cta_pairs": (None, [_I]),
+    "dofb_pack_weights_batch": (_I, [_P, _I, _I, _P]),
     "dofb_head_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "dofb_head_dgrad": (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _P]),
     "dofb_head_wgrad": (_I, [_P, _I, _P, _I, _I, _I, _I, _P, _P, _P]),

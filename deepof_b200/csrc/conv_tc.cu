@@ -655,6 +655,50 @@ __global__ void __launch_bounds__(256) pack_weights_t_kernel(const float *__rest
     }
 }
 
+// Both orientations for MANY layers in one launch (the engine packs every layer once per optimiser step: ~80 tiny launches otherwise).
+// Block -> job by a scan of the job table; fwd-orientation jobs work in 32x32 transpose tiles, bwd-orientation jobs in 2048-element runs.
+struct PackJobDev { const float *w; void *wp; int taps, ci, co, cpad, contract_ci, blk0; };
+constexpr int PACK_BATCH_MAX = 48;
+struct PackBatch { int n; PackJobDev j[PACK_BATCH_MAX]; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) pack_batch_kernel(const __grid_constant__ PackBatch Bt) {
+    __shared__ float tile[32][33];
+    int q = 0;
+    while (q + 1 < Bt.n && (int)blockIdx.x >= Bt.j[q + 1].blk0) ++q;
+    const PackJobDev J = Bt.j[q];
+    const int local = blockIdx.x - J.blk0;
+    T *Wp = reinterpret_cast<T *>(J.wp);
+    if (J.contract_ci) {
+        const int tiles_n = (J.co + 31) / 32, tiles_c = J.cpad / 32;
+        const int n0 = (local % tiles_n) * 32, c0 = ((local / tiles_n) % tiles_c) * 32, t = local / (tiles_n * tiles_c);
+        const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;         // 32 x 8
+#pragma unroll
+        for (int r = ty; r < 32; r += 8) {
+            const int c = c0 + r, n = n0 + tx;
+            tile[r][tx] = (c < J.ci && n < J.co) ? __ldg(J.w + ((long long)t * J.ci + c) * J.co + n) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = ty; r < 32; r += 8) {
+            const int n = n0 + r, c = c0 + tx;
+            if (n < J.co && c < J.cpad) Wp[((long long)n * J.taps + t) * J.cpad + c] = cvt_out<T>(tile[tx][r]);
+        }
+    } else {
+        const long long total = (long long)J.ci * J.taps * J.cpad;
+        const long long i0 = (long long)local * 2048;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const long long i = i0 + u * 256 + threadIdx.x;
+            if (i >= total) break;
+            const int c = (int)(i % J.cpad);
+            const int t = (int)((i / J.cpad) % J.taps);
+            const int n = (int)(i / ((long long)J.cpad * J.taps));
+            Wp[i] = cvt_out<T>(c < J.co ? __ldg(J.w + ((long long)t * J.ci + n) * J.co + c) : 0.f);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side: tensor maps, caches, launch
 // ------------------------------------------------------------------------------------------------
@@ -732,6 +776,38 @@ static int get_pack_buffer(const void *w, int orient, size_t floats, float **out
     else g_pack[{w, orient}] = {p, floats, g_weight_epoch};
     *out = p;
     *fresh = false;
+    return 0;
+}
+
+// Pack a list of layers (see pack_batch_kernel); entries whose cached copy is current are skipped.  Exactly the buffers / layouts that
+// run_gather would create lazily, so the convolutions that follow find them fresh.
+int pack_weights_batch(const dofb_pack_job *jobs, int n_jobs, int bf16, cudaStream_t st) {
+    DOFB_CHECK_ARG(jobs != nullptr || n_jobs == 0, "dofb_pack_weights_batch: null job list");
+    const int kel = bf16 ? 64 : 32;
+    int k = 0;
+    while (k < n_jobs) {
+        PackBatch Bt;
+        Bt.n = 0;
+        int blocks = 0;
+        for (; k < n_jobs && Bt.n < PACK_BATCH_MAX; ++k) {
+            const dofb_pack_job &j = jobs[k];
+            DOFB_CHECK_ARG(j.w && j.taps > 0 && j.ci > 0 && j.co > 0, "dofb_pack_weights_batch: bad job %d", k);
+            const int kc = j.contract_ci ? j.ci : j.co, n_rows = j.contract_ci ? j.co : j.ci;
+            const int cpad = (kc + kel - 1) / kel * kel;
+            const size_t welems = (size_t)n_rows * j.taps * cpad;
+            float *wp = nullptr;
+            bool fresh = false;
+            if (get_pack_buffer(j.w, (j.contract_ci ? 1 : 0) + (bf16 ? 8 : 0), bf16 ? (welems + 1) / 2 : welems, &wp, &fresh)) return 1;
+            if (fresh) continue;
+            PackJobDev &d = Bt.j[Bt.n++];
+            d.w = j.w; d.wp = wp; d.taps = j.taps; d.ci = j.ci; d.co = j.co; d.cpad = cpad; d.contract_ci = j.contract_ci ? 1 : 0; d.blk0 = blocks;
+            blocks += j.contract_ci ? ((j.co + 31) / 32) * (cpad / 32) * j.taps : (int)((welems + 2047) / 2048);
+        }
+        if (Bt.n == 0) continue;
+        if (bf16) pack_batch_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(Bt);
+        else pack_batch_kernel<float><<<blocks, 256, 0, st>>>(Bt);
+        DOFB_LAUNCH_OK();
+    }
     return 0;
 }
 

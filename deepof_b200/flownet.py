@@ -295,6 +295,35 @@ class FlowNetS:
                                     up_y=S(a[tgt], skipc, upc), up_dy=S(d[tgt], skipc, upc),
                                     pr_y=S(a[tgt], skipc + upc, 2), pr_dy=S(d[tgt], skipc + upc, 2)))
 
+    def _pack_jobs(self):
+        """(weight, orientation) of every tensor-core gather-GEMM the step runs: conv fwd / transposed-conv dgrad read the contract-ci copy,
+        conv dgrad / transposed-conv fwd the contract-co copy; built once (the parameter views never move)."""
+        if getattr(self, "_jobs", None) is None:
+            P, seen, entries = self.params, set(), []
+
+            def add(w, contract_ci):
+                key = (w.data_ptr(), contract_ci)
+                if key not in seen:
+                    seen.add(key)
+                    entries.append((w, contract_ci))
+            for L in self.tower:
+                if L["op"] != "conv" or L["xpad"] is not None:
+                    continue
+                w = P[L["wname"] + "/weights"]
+                add(w, 1)
+                if L["dx"] is not None:
+                    add(w, 0)
+            for R in self.refine:
+                w = P[R["up"] + "/weights"]
+                add(w, 0)
+                add(w, 1)
+            for s in range(1, self.N_SCALES + 1):
+                h, wd = self.hw[s]
+                if self.B * h * wd <= self.TC_HEAD_MAX_PIX:
+                    add(P[f"pr{s}/weights"], 1)
+            self._jobs = ops.make_pack_jobs(entries)
+        return self._jobs
+
     def _head_fwd(self, s, x):
         """pr_s = 3x3 conv to 2 channels.  Coarse scales (small maps, 386..1026 input channels) are GEMM-shaped with a long K and too few
         pixels to fill the GPU with the streaming SIMT kernel, so in the tensor-core math modes they run through the gather-GEMM
@@ -364,6 +393,8 @@ class FlowNetS:
             raise ops.DeepOFError(f"expected [B={self.B},{self.H},{self.W},3] NHWC inputs, got {tuple(source.shape)} / {tuple(target.shape)}")
         P, mth = self.params, self.math
         self._preprocess(source, target)
+        if mth != MATH_FP32:        # every layer's tensor-core weight copies in one launch (no-op while they are current)
+            self._k("pack_weights", ops.pack_weights_batch, self._pack_jobs(), mth == MATH_BF16)
         for L in self.tower:
             self._fwd_layer(L)
         for R in self.refine:

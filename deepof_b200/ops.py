@@ -210,6 +210,21 @@ def cast_bf16(s: Slab):
     check(_lib.load().dofb_cast_bf16(s.ptr, s.ld, _need16(s, "cast_bf16"), s.ld, s.n_pix, s.c, _stream()))
 
 
+def make_pack_jobs(entries):
+    """entries: (weight tensor [kh,kw,ci,co], contract_ci) -> ctypes array for pack_weights_batch (build once, reuse every step)."""
+    arr = (_lib.PackJob * len(entries))()
+    for i, (w, contract_ci) in enumerate(entries):
+        _req(w, "w")
+        kh, kw, ci, co = w.shape
+        arr[i] = _lib.PackJob(w.data_ptr(), kh * kw, ci, co, int(contract_ci))
+    return arr
+
+
+def pack_weights_batch(jobs, bf16: bool):
+    """(Re)pack the tensor-core weight copies of many layers in one launch (see dofb_pack_weights_batch)."""
+    check(_lib.load().dofb_pack_weights_batch(C.cast(jobs, C.c_void_p), len(jobs), int(bf16), _stream()))
+
+
 def invalidate_weight_cache():
     _lib.load().dofb_invalidate_weight_cache()
 

@@ -140,6 +140,11 @@ void dofb_invalidate_weight_cache(void);
 /* Off by default (every call re-packs its weights: always correct).  A caller that enables the cache promises to call
  * dofb_invalidate_weight_cache() after changing weight values; the training engine does (once per Adam step). */
 void dofb_enable_weight_cache(int on);
+/* With the cache enabled: (re)pack the tensor-core operand copies of many layers in ONE launch (instead of lazily, one or two small
+ * launches per layer and step).  contract_ci = 1: the copy dofb_conv_fwd* reads; 0: the copy dofb_conv_dgrad* reads.  bf16 selects the
+ * bf16 (dofb_*_bf16) or fp32/TF32 copies.  Up-to-date copies are skipped. */
+typedef struct { const float *w; int taps, ci, co, contract_ci; } dofb_pack_job;
+int dofb_pack_weights_batch(const dofb_pack_job *jobs, int n_jobs, int bf16, void *stream);
 /* Tensor-core tiles of 256 columns as CTA pairs (thread-block clusters of 2, tcgen05 cta_group::2: each CTA stages half of the weight tile).
  * Process-wide switch; results are identical up to fp32 summation order (same per-tile K order: bit-identical in practice). */
 void dofb_enable_cta_pairs(int on);
