@@ -685,16 +685,28 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const __grid_constant__
             if (n < J.co && c < J.cpad) Wp[((long long)n * J.taps + t) * J.cpad + c] = cvt_out<T>(tile[tx][r]);
         }
     } else {
+        // straight padded copy, 4 consecutive K elements per thread (co and cpad are multiples of 4 for every layer that gets here
+        // through the vector path; others take the scalar tail)
         const long long total = (long long)J.ci * J.taps * J.cpad;
         const long long i0 = (long long)local * 2048;
+        const bool vec = (J.co & 3) == 0 && (reinterpret_cast<uintptr_t>(J.w) & 15) == 0;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const long long i = i0 + u * 256 + threadIdx.x;
+        for (int u = 0; u < 2; ++u) {
+            const long long i = i0 + (u * 256 + threadIdx.x) * 4;
             if (i >= total) break;
             const int c = (int)(i % J.cpad);
-            const int t = (int)((i / J.cpad) % J.taps);
-            const int n = (int)(i / ((long long)J.cpad * J.taps));
-            Wp[i] = cvt_out<T>(c < J.co ? __ldg(J.w + ((long long)t * J.ci + n) * J.co + c) : 0.f);
+            const long long row = i / J.cpad;                   // = n * taps + t
+            const int t = (int)(row % J.taps), n = (int)(row / J.taps);
+            const float *src = J.w + ((long long)t * J.ci + n) * J.co + c;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (vec && c + 3 < J.co) v = __ldg(reinterpret_cast<const float4 *>(src));
+            else {
+                if (c < J.co) v.x = __ldg(src);
+                if (c + 1 < J.co) v.y = __ldg(src + 1);
+                if (c + 2 < J.co) v.z = __ldg(src + 2);
+                if (c + 3 < J.co) v.w = __ldg(src + 3);
+            }
+            Wp[i] = cvt_out<T>(v.x); Wp[i + 1] = cvt_out<T>(v.y); Wp[i + 2] = cvt_out<T>(v.z); Wp[i + 3] = cvt_out<T>(v.w);
         }
     }
 }
