@@ -402,3 +402,103 @@ def test_tf32_engine_tracks_fp32_engine_and_oracle_epe():
     worst = max(rel(etf.grads[n], e32.grads[n]) for n in e32.grads)
     print(f"tf32 vs fp32 gradient: cosine={cos:.6f} worst per-tensor max-norm deviation={worst:.3e}")
     assert cos > 0.98
+
+# ---- CTA pairs (cta_group::2) vs single-CTA tiles: same K order per tile, so forward / input gradients must be bit-identical --------
+
+@pytest.fixture
+def cta_pairs():
+    from deepof_b200 import _lib
+    lib = _lib.load()
+    yield lib
+    lib.dofb_enable_cta_pairs(1)        # (the engine's default)
+
+
+PAIR_CASES = [(32, 48, 64, 256, 256, 3, 1), (31, 12, 16, 512, 512, 3, 1),      # odd tile count: phantom second tile
+              (32, 48, 64, 256, 512, 3, 2), (16, 24, 32, 512, 256, 4, 2), (32, 6, 8, 1024, 1024, 3, 1)]
+
+
+@pytest.mark.parametrize("case", PAIR_CASES)
+@pytest.mark.parametrize("mth", [1, 2])
+def test_cta_pairs_fwd_and_dgrad_bit_identical(case, mth, cta_pairs):
+    from deepof_b200 import ops
+    B, H, W, ci, co, k, s = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = _buf(B, H, W, (ci + 63) // 64 * 64, ci, g)
+    w = (torch.randn(k, k, ci, co, generator=g) / math.sqrt(k * k * ci)).cuda()
+    b = (torch.randn(co, generator=g) * 0.1).cuda()
+    geom = ops.conv_geom(B, H, W, ci, co, k, s)
+    yl = (co + 63) // 64 * 64
+    dy = _buf(B, geom.oh, geom.ow, yl, co, g)
+    ys, ds = [], []
+    for pairs in (0, 1):
+        cta_pairs.dofb_enable_cta_pairs(pairs)
+        y = torch.zeros(B, geom.oh, geom.ow, yl, device="cuda")
+        ops.conv_fwd(geom, ops.Slab(x, 0, ci, _shadow(x)), w, b, ops.Slab(y, 0, co), ops.ACT_ELU, mth)
+        d = torch.full((B, H, W, x.shape[3]), 0.5, device="cuda")
+        ops.conv_dgrad(geom, ops.Slab(dy, 0, co, _shadow(dy)), w, None, ops.Slab(d, 0, ci), ops.ACT_NONE, True, mth)   # (strided: all phases, one launch)
+        torch.cuda.synchronize()
+        ys.append(y); ds.append(d)
+    assert torch.equal(ys[0], ys[1])
+    assert torch.equal(ds[0], ds[1])
+    ref = torch.zeros_like(ys[0])
+    ops.conv_fwd(geom, ops.Slab(x, 0, ci), w, b, ops.Slab(ref, 0, co), ops.ACT_ELU, ops.MATH_FP32)
+    assert rel(ys[1], ref) < (BF_TOL if mth == 2 else TOL)
+
+
+@pytest.mark.parametrize("case", [(8, 48, 64, 256, 256, 3, 1), (8, 48, 64, 128, 256, 5, 2), (8, 96, 128, 64, 128, 5, 2), (8, 96, 128, 32, 194, 4, 2),
+                                  (8, 48, 64, 256, 130, 3, 1), (3, 6, 8, 1024, 1024, 3, 1)])
+@pytest.mark.parametrize("mth", [1, 2])
+def test_cta_pairs_wgrad_matches_single_cta(case, mth, cta_pairs):
+    """Weight gradient: pairs of A tiles sharing a dy tile (odd tap counts leave a phantom partner); fp32 atomics -> order-level differences."""
+    from deepof_b200 import ops
+    B, H, W, ci, co, k, s = case
+    g = torch.Generator().manual_seed(sum(case) + 7)
+    x = _buf(B, H, W, (ci + 63) // 64 * 64, ci, g)
+    geom = ops.conv_geom(B, H, W, ci, co, k, s)
+    dy = _buf(B, geom.oh, geom.ow, (co + 63) // 64 * 64, co, g)
+    outs = []
+    for pairs in (0, 1):
+        cta_pairs.dofb_enable_cta_pairs(pairs)
+        dw = torch.zeros(k, k, ci, co, device="cuda")
+        ops.conv_wgrad(geom, ops.Slab(x, 0, ci, _shadow(x)), ops.Slab(dy, 0, co, _shadow(dy)), dw, None, mth)
+        torch.cuda.synchronize()
+        outs.append(dw)
+    assert rel(outs[1], outs[0]) < 1e-5
+    ref = torch.zeros_like(outs[0])
+    ops.conv_wgrad(geom, ops.Slab(x, 0, ci), ops.Slab(dy, 0, co), ref, None, ops.MATH_FP32)
+    assert rel(outs[1], ref) < (BF_TOL if mth == 2 else TOL)
+
+
+def test_pack_weights_batch_matches_lazy_packing():
+    """dofb_pack_weights_batch fills the cache the convolutions read: results must equal the lazily packed path bit for bit."""
+    from deepof_b200 import ops, _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(11)
+    B, H, W = 2, 12, 16
+    specs = [(64, 128, 3, 1), (130, 96, 5, 2), (256, 256, 3, 1), (32, 194, 4, 2)]
+    ws = [(torch.randn(k, k, ci, co, generator=g) / math.sqrt(k * k * ci)).cuda() for ci, co, k, s in specs]
+    xs = [_buf(B, H, W, (ci + 63) // 64 * 64, ci, g) for ci, co, k, s in specs]
+
+    def run_all(mth):
+        outs = []
+        for (ci, co, k, s), w, x in zip(specs, ws, xs):
+            geom = ops.conv_geom(B, H, W, ci, co, k, s)
+            y = torch.zeros(B, geom.oh, geom.ow, (co + 63) // 64 * 64, device="cuda")
+            ops.conv_fwd(geom, ops.Slab(x, 0, ci, _shadow(x)), w, None, ops.Slab(y, 0, co), ops.ACT_NONE, mth)
+            d = torch.zeros_like(x)
+            ops.conv_dgrad(geom, ops.Slab(y, 0, co, _shadow(y)), w, None, ops.Slab(d, 0, ci), ops.ACT_NONE, False, mth)
+            outs += [y, d]
+        torch.cuda.synchronize()
+        return outs
+    for mth in (ops.MATH_TF32, ops.MATH_BF16):
+        lib.dofb_enable_weight_cache(0)
+        lazy = run_all(mth)
+        lib.dofb_enable_weight_cache(1)                 # (bumps the epoch: nothing is fresh)
+        jobs = ops.make_pack_jobs([(w, c) for w in ws for c in (1, 0)])
+        ops.pack_weights_batch(jobs, mth == ops.MATH_BF16)
+        before = lib.dofb_launch_count()
+        batched = run_all(mth)
+        assert lib.dofb_launch_count() - before == 2 * len(specs)          # no pack launches: one fwd + one (merged-phase) dgrad per layer
+        lib.dofb_enable_weight_cache(0)
+        for a, b_ in zip(lazy, batched):
+            assert torch.equal(a, b_)
