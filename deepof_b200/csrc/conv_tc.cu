@@ -248,6 +248,20 @@ __device__ __forceinline__ uint64_t make_desc_k128(uint32_t saddr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
+// Same layout read from a HALO tile: the 128 M rows are 16 groups of 8 consecutive 128-byte rows, one group per image row of a tile
+// 8 pixels wide inside a halo buffer 16 pixels wide (group stride 16 x 128 B = 2048 B), starting `row_off` rows into the buffer (the tap's
+// (dy, dx) shift).  Measured on B200: the 128-byte swizzle is applied on ABSOLUTE shared-memory address bits (exactly what TMA wrote), so a
+// start address that is only 128-byte aligned needs NO base-offset [49,52) -- setting it to (addr >> 7) & 7 breaks every dx != 0 tap.
+__device__ __forceinline__ uint64_t make_desc_k128_halo(uint32_t buf_addr, int row_off) {
+    const uint32_t saddr = buf_addr + (uint32_t)row_off * 128u;
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(2048 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 // instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b_format TF32 [7,10)/[10,13)=2,
 // a/b major K (bits 15/16 = 0), N>>3 at [17,23), M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
@@ -266,6 +280,7 @@ constexpr int TC_BM = 128, TC_BK = 32, TC_THREADS = 192, TC_MAX_TAPS = 49;
 // With 4 epilogue warps (one per scheduler, no latency hiding) every layer of the net was bound by the epilogue, not by the MMAs.
 constexpr int TCG_EPI_WARPS = 8, TCG_THREADS = (TCG_EPI_WARPS + 2) * 32, TCG_STG_BYTES = TCG_EPI_WARPS * 32 * 16 * 4;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
+constexpr int TC_HALO_ROWS = 18;                // halo box rows: 16 tile rows + a vertical tap span of up to 2
 
 struct TapInfo {
     short oy, ox;      // unit mode: source = (iy + oy, ix + ox); parity mode: quotient offsets (qy, qx)
@@ -292,21 +307,22 @@ struct TcParams {
     // several output sub-grids ("phases" of a strided input gradient / transposed conv) in ONE launch: phase q owns the global M tiles
     // [m_begin, m_begin + m_tiles) and the taps [tap0, tap0 + ntaps); nphase <= 1: the scalar fields above describe the only phase
     int nphase;
-    struct Phase { int y0, x0, cnt_y, cnt_x, tiles_x, tiles_y, m_begin, tap0, ntaps; } ph[4];
+    int oy_min, ox_min;          // halo mode: smallest tap offsets of the (only) phase = origin of the halo box relative to the tile
+    struct Phase { int y0, x0, cnt_y, cnt_x, tiles_x, tiles_y, m_begin, tap0, ntaps, oy_min, ox_min; } ph[4];
     TapInfo taps[TC_MAX_TAPS];
 };
 
-struct TileView { int y0, x0, cnt_y, cnt_x, tiles_x, tiles_y, tap0, ntaps, mt; };
+struct TileView { int y0, x0, cnt_y, cnt_x, tiles_x, tiles_y, tap0, ntaps, mt, oy_min, ox_min; };
 __device__ __forceinline__ TileView tile_view(const TcParams &P, int mt) {
     TileView v;
     if (P.nphase <= 1) {
-        v.y0 = P.y0; v.x0 = P.x0; v.cnt_y = P.cnt_y; v.cnt_x = P.cnt_x; v.tiles_x = P.tiles_x; v.tiles_y = P.tiles_y; v.tap0 = 0; v.ntaps = P.ntaps; v.mt = mt;
+        v.y0 = P.y0; v.x0 = P.x0; v.cnt_y = P.cnt_y; v.cnt_x = P.cnt_x; v.tiles_x = P.tiles_x; v.tiles_y = P.tiles_y; v.tap0 = 0; v.ntaps = P.ntaps; v.mt = mt; v.oy_min = P.oy_min; v.ox_min = P.ox_min;
         return v;
     }
     int q = 0;
     while (q + 1 < P.nphase && mt >= P.ph[q + 1].m_begin) ++q;
     v.y0 = P.ph[q].y0; v.x0 = P.ph[q].x0; v.cnt_y = P.ph[q].cnt_y; v.cnt_x = P.ph[q].cnt_x; v.tiles_x = P.ph[q].tiles_x; v.tiles_y = P.ph[q].tiles_y;
-    v.tap0 = P.ph[q].tap0; v.ntaps = P.ph[q].ntaps; v.mt = mt - P.ph[q].m_begin;
+    v.tap0 = P.ph[q].tap0; v.ntaps = P.ph[q].ntaps; v.mt = mt - P.ph[q].m_begin; v.oy_min = P.ph[q].oy_min; v.ox_min = P.ph[q].ox_min;
     return v;
 }
 
@@ -326,7 +342,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // (~6300 B/cycle) the wide layers sit on.  Barriers: `full` lives in the leader (its own expect_tx for both CTAs' bytes + one remote
 // arrive of the peer's producer); `empty` / `acc_full` are signalled in both CTAs by a multicast tcgen05.commit; `acc_empty` of the
 // leader collects the 8 + 8 epilogue warps of both CTAs.
-template <int BN, int STAGES, bool BF, bool CG2 = false>
+// HALO = true (unit-stride gathers on maps of at least 16 x 8 pixels, BN <= 128): the tile is 8 pixels wide and 16 rows tall, and per channel
+// block ONE TMA box of 18 rows x 16 columns lands in an A slot; every filter tap then reads its shifted 128 rows straight out of that halo
+// (descriptor start = tap offset in rows), so A crosses the L2->SM path once per channel block instead of once per tap.  The weights stream
+// through their own ring (STAGES slots of one k-block), K order = (channel block, tap).
+template <int BN, int STAGES, bool BF, bool CG2 = false, bool HALO = false>
 __global__ void __launch_bounds__(TCG_THREADS, 1)
 tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                       const __grid_constant__ TcParams P) {
@@ -336,19 +356,24 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     constexpr int B_BYTES = BROWS * TC_BK * 4;
     // k-blocks per pipeline stage: the narrow tiles (BN <= 64) retire a k-block in 64-128 MMA cycles, faster than one producer thread and
     // one barrier round trip can follow, so they move two k-blocks per stage (half the barrier traffic, four TMA boxes issued by four lanes)
-    constexpr int KPS = (BN <= 64 && !CG2) ? 2 : 1;
+    static_assert(!HALO || (!CG2 && BN <= 128), "halo tiles: single CTA, at most 128 columns");
+    constexpr int KPS = (BN <= 64 && !CG2 && !HALO) ? 2 : 1;
     constexpr int SUB_BYTES = TC_A_BYTES + B_BYTES;
     constexpr int STAGE_BYTES = KPS * SUB_BYTES;
+    constexpr int HA_SLOTS = 3, HA_BYTES = TC_HALO_ROWS * 16 * 128;       // halo slots: 18 rows x 16 pixels x 128 B = 36 KB
+    constexpr int RING_BYTES = HALO ? HA_SLOTS * HA_BYTES + STAGES * B_BYTES : STAGES * STAGE_BYTES;
     constexpr int ACC_COLS = BN < 32 ? 32 : BN;
     constexpr int TMEM_COLS = 2 * ACC_COLS;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float *stage_f = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);                 // [8 warps][32 rows][16 floats] epilogue transpose tiles
+    float *stage_f = reinterpret_cast<float *>(smem + RING_BYTES);                           // [8 warps][32 rows][16 floats] epilogue transpose tiles
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(stage_f + TCG_EPI_WARPS * 32 * 16);
     uint64_t *empty_bar = full_bar + STAGES;
     uint64_t *acc_full = empty_bar + STAGES;       // [2] MMA -> epilogue
     uint64_t *acc_empty = acc_full + 2;            // [2] epilogue -> MMA (4 warps arrive)
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    uint64_t *a_full = acc_empty + 2;              // [3] halo mode: A slots (full_bar / empty_bar then belong to the B ring)
+    uint64_t *a_empty = a_full + 3;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_empty + 3);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // work units: tiles (single CTA) or PAIRS of M tiles (CTA pairs; an odd last pair has a phantom second tile: TMA zero-fills it,
@@ -361,6 +386,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], CG2 ? 2 : 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], CG2 ? 2 * TCG_EPI_WARPS : TCG_EPI_WARPS); }
+        for (int a = 0; a < 3; ++a) { mbar_init(&a_full[a], 1); mbar_init(&a_empty[a], 1); }
         fence_barrier_init();
     }
     if (warp == TCG_EPI_WARPS && lane == 0) { prefetch_tmap(&map_a); prefetch_tmap(&map_b); }
@@ -377,13 +403,29 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     if (warp == TCG_EPI_WARPS) {
         // ===== TMA producer (one thread: UTMALDG takes uniform operands, so spreading the boxes over lanes only adds a divergence waterfall) =====
         if (lane == 0) {
-            int it = 0;                                   // running stage-iteration count across tiles
+            int it = 0, ita = 0;                          // running stage-iteration counts across tiles (halo mode: B ring / A ring)
             for (int t = unit0; t < total_tiles; t += unit_step) {
                 const int nt = t / m_units;
                 const TileView V = tile_view(P, (t % m_units) * (CG2 ? 2 : 1) + (int)rank);
                 const int mt = V.mt;
                 const int tx = mt % V.tiles_x, ty = (mt / V.tiles_x) % V.tiles_y, tn = mt / (V.tiles_x * V.tiles_y);
                 const int ix0 = tx * P.TW, iy0 = ty * P.TH, in0 = tn * P.TN, n0 = nt * BN + (int)rank * BROWS;
+                if (HALO) {
+                    // K order (channel block, tap): one halo box per channel block, one weight k-block per (channel block, tap)
+                    for (int cb = 0; cb < P.ncb; ++cb, ++ita) {
+                        const int sa_i = ita % HA_SLOTS;
+                        mbar_wait(&a_empty[sa_i], ((ita / HA_SLOTS) & 1) ^ 1);
+                        mbar_expect_tx(&a_full[sa_i], HA_BYTES);
+                        tma_load_4d(smem + sa_i * HA_BYTES, &map_a, &a_full[sa_i], P.a_coff + cb * KELEMS, ix0 + V.ox_min, iy0 + V.oy_min, in0);
+                        for (int tp = 0; tp < V.ntaps; ++tp, ++it) {
+                            const int s = it % STAGES;
+                            mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+                            mbar_expect_tx(&full_bar[s], B_BYTES);
+                            tma_load_2d(smem + HA_SLOTS * HA_BYTES + s * B_BYTES, &map_b, &full_bar[s], P.taps[V.tap0 + tp].wk + cb * KELEMS, n0);
+                        }
+                    }
+                    continue;
+                }
                 const int kiters = V.ntaps * P.ncb, siters = (kiters + KPS - 1) / KPS;
                 int tp = V.tap0, cb = 0;                  // (tap, channel block) of the next k-block
                 for (int si = 0; si < siters; ++si, ++it) {
@@ -428,12 +470,36 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         if (lane == 0 && rank == 0) {
             constexpr int UM = CG2 ? 2 * TC_BM : TC_BM;
             constexpr uint32_t idesc = BF ? make_idesc_bf16(UM, BN) : make_idesc_tf32(UM, BN);
-            int it = 0, lt = 0;
+            int it = 0, ita = 0, lt = 0;
             for (int t = unit0; t < total_tiles; t += unit_step, ++lt) {
                 const int acc = lt & 1;
                 mbar_wait(&acc_empty[acc], ((lt >> 1) & 1) ^ 1);      // epilogue(s) have drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
+                if (HALO) {
+                    const TileView V = tile_view(P, t % m_units);
+                    for (int cb = 0; cb < P.ncb; ++cb, ++ita) {
+                        const int sa_i = ita % HA_SLOTS;
+                        mbar_wait(&a_full[sa_i], (ita / HA_SLOTS) & 1);
+                        tc_fence_after();
+                        const uint32_t abuf = smem_u32(smem + sa_i * HA_BYTES);
+                        for (int tp = 0; tp < V.ntaps; ++tp, ++it) {
+                            const int s = it % STAGES;
+                            mbar_wait(&full_bar[s], (it / STAGES) & 1);
+                            tc_fence_after();
+                            const TapInfo ti = P.taps[V.tap0 + tp];
+                            const uint64_t da = make_desc_k128_halo(abuf, (ti.oy - V.oy_min) * 16 + (ti.ox - V.ox_min));
+                            const uint64_t db = make_desc_k128(smem_u32(smem + HA_SLOTS * HA_BYTES + s * B_BYTES));
+#pragma unroll
+                            for (int kk = 0; kk < TC_BK / 8; ++kk)
+                                umma<BF>(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (cb | tp | kk) != 0);
+                            umma_commit(&empty_bar[s]);     // weight slot free
+                        }
+                        umma_commit(&a_empty[sa_i]);        // halo slot free once every tap has read it
+                    }
+                    umma_commit(&acc_full[acc]);
+                    continue;
+                }
                 const int kiters = tile_view(P, (t % m_units) * (CG2 ? 2 : 1)).ntaps * P.ncb, siters = (kiters + KPS - 1) / KPS;
                 for (int si = 0; si < siters; ++si, ++it) {
                     const int s = it % STAGES;
@@ -759,6 +825,8 @@ static std::unordered_map<PackKey, PackEntry, PackKeyHash> g_pack;
 static std::mutex g_pack_mu;
 static unsigned long long g_weight_epoch = 1;      // bumped by dofb_invalidate_weight_cache() (the optimiser step)
 static bool g_cache_enabled = false;               // off: every call re-packs (always correct); on: caller promises to invalidate
+static bool g_halo = false;                        // halo-tile reuse of A across filter taps (dofb_enable_halo_tiles)
+void enable_halo(int on) { g_halo = on != 0; }
 static bool g_cta_pairs = false;                   // cta_group::2 tiles for the 256-column layers (dofb_enable_cta_pairs)
 void enable_cta_pairs(int on) { g_cta_pairs = on != 0; }
 
@@ -835,14 +903,15 @@ static void choose_tile(int cnt_y, int cnt_x, int &TW, int &TH, int &TN) {
     TN = TC_BM / (TW * TH);
 }
 
-template <int BN, int STAGES, bool BF = false, bool CG2 = false>
+template <int BN, int STAGES, bool BF = false, bool CG2 = false, bool HALO = false>
 static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &Pin, int tiles, int n_tiles, cudaStream_t st) {
-    constexpr int KPS = (BN <= 64 && !CG2) ? 2 : 1;
-    constexpr int smem = STAGES * KPS * (TC_A_BYTES + (CG2 ? BN / 2 : BN) * TC_BK * 4) + TCG_STG_BYTES + 1024 + 256;
+    constexpr int KPS = (BN <= 64 && !CG2 && !HALO) ? 2 : 1;
+    constexpr int smem = (HALO ? 3 * TC_HALO_ROWS * 16 * 128 + STAGES * BN * TC_BK * 4
+                               : STAGES * KPS * (TC_A_BYTES + (CG2 ? BN / 2 : BN) * TC_BK * 4)) + TCG_STG_BYTES + 1024 + 256;
     static_assert(smem <= 227 * 1024, "shared-memory budget");
     static bool configured = false;
     if (!configured) {
-        DOFB_CUDA_OK(cudaFuncSetAttribute(tc_gather_gemm_kernel<BN, STAGES, BF, CG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        DOFB_CUDA_OK(cudaFuncSetAttribute(tc_gather_gemm_kernel<BN, STAGES, BF, CG2, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
     TcParams P = Pin;
@@ -875,7 +944,7 @@ static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcParam
     }
     const long long total = (long long)tiles * n_tiles;
     const int grid = (int)(total < num_sms() ? total : num_sms());
-    tc_gather_gemm_kernel<BN, STAGES, BF, CG2><<<grid, TCG_THREADS, smem, st>>>(ma, mb, P);
+    tc_gather_gemm_kernel<BN, STAGES, BF, CG2, HALO><<<grid, TCG_THREADS, smem, st>>>(ma, mb, P);
     DOFB_LAUNCH_OK();
     return 0;
 }
@@ -931,8 +1000,41 @@ static int run_gather(const GatherSpec &G, const TcParams &Pin, cudaStream_t st)
     P.out = G.out; P.out_ld = G.out_ld; P.out16 = G.accumulate ? nullptr : reinterpret_cast<__nv_bfloat16 *>(G.out16);
     P.bias = G.bias; P.n_valid = G.n_valid; P.rh = G.rh; P.rw = G.rw;
     P.act = G.act; P.accumulate = G.accumulate; P.B = G.B;
+    // ---- halo tiles: unit-stride gather, every phase at least 16 x 8 pixels, tap offsets spanning <= 2 rows / 8 columns, >= 2 taps ----
+    const int n_rows_out = G.contract_ci ? G.w_co : G.w_ci;
+    bool halo = g_halo && !P.parity && n_rows_out <= 128;
+    {
+        const int nq = P.nphase > 1 ? P.nphase : 1;
+        for (int q = 0; q < nq && halo; ++q) {
+            const int t0 = P.nphase > 1 ? P.ph[q].tap0 : 0, tn = P.nphase > 1 ? P.ph[q].ntaps : P.ntaps;
+            const int cy = P.nphase > 1 ? P.ph[q].cnt_y : P.cnt_y, cx = P.nphase > 1 ? P.ph[q].cnt_x : P.cnt_x;
+            int oy0 = 1 << 20, oy1 = -(1 << 20), ox0 = 1 << 20, ox1 = -(1 << 20);
+            for (int t = t0; t < t0 + tn; ++t) {
+                oy0 = P.taps[t].oy < oy0 ? P.taps[t].oy : oy0; oy1 = P.taps[t].oy > oy1 ? P.taps[t].oy : oy1;
+                ox0 = P.taps[t].ox < ox0 ? P.taps[t].ox : ox0; ox1 = P.taps[t].ox > ox1 ? P.taps[t].ox : ox1;
+            }
+            if (tn < 2 || oy1 - oy0 > TC_HALO_ROWS - 16 || ox1 - ox0 > 8 || cy < 16 || cx < 8) halo = false;
+            if (P.nphase > 1) { P.ph[q].oy_min = oy0; P.ph[q].ox_min = ox0; } else { P.oy_min = oy0; P.ox_min = ox0; }
+        }
+    }
     int tiles;
-    if (P.nphase > 1) {
+    if (halo) {
+        P.TW = 8; P.TH = 16; P.TN = 1;
+        if (P.nphase > 1) {
+            int begin = 0;
+            for (int q = 0; q < P.nphase; ++q) {
+                P.ph[q].tiles_x = (P.ph[q].cnt_x + 7) / 8;
+                P.ph[q].tiles_y = (P.ph[q].cnt_y + 15) / 16;
+                P.ph[q].m_begin = begin;
+                begin += P.ph[q].tiles_x * P.ph[q].tiles_y * G.B;
+            }
+            tiles = begin;
+        } else {
+            P.tiles_x = (P.cnt_x + 7) / 8;
+            P.tiles_y = (P.cnt_y + 15) / 16;
+            tiles = P.tiles_x * P.tiles_y * G.B;
+        }
+    } else if (P.nphase > 1) {
         // one pixel-tile shape for all phases (their sub-grids differ by at most one row / column); the phase starts are kept even so that
         // a CTA pair never straddles two phases (an odd phase ends in a phantom tile)
         int my = 0, mx = 0;
@@ -959,7 +1061,7 @@ static int run_gather(const GatherSpec &G, const TcParams &Pin, cudaStream_t st)
     if (!P.parity) {
         const uint64_t dims[4] = {(uint64_t)cpad, (uint64_t)G.aw, (uint64_t)G.ah, (uint64_t)G.B};
         const uint64_t str[3] = {(uint64_t)G.a_ld * esz, (uint64_t)G.aw * G.a_ld * esz, (uint64_t)G.ah * G.aw * G.a_ld * esz};
-        const uint32_t box[4] = {(uint32_t)kel, (uint32_t)P.TW, (uint32_t)P.TH, (uint32_t)P.TN};
+        const uint32_t box[4] = {(uint32_t)kel, halo ? 16u : (uint32_t)P.TW, halo ? (uint32_t)TC_HALO_ROWS : (uint32_t)P.TH, (uint32_t)P.TN};
         if (make_map(&ma, abase, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, dt)) return 1;
     } else {
         DOFB_CHECK_ARG(G.ah % 2 == 0 && G.aw % 2 == 0, "tc conv: stride-2 gather needs even map sizes (%d x %d)", G.ah, G.aw);
@@ -983,6 +1085,20 @@ static int run_gather(const GatherSpec &G, const TcParams &Pin, cudaStream_t st)
     if (pairs) {
         if (bf) return launch_tc<256, 6, true, true>(ma, mb, P, tiles, n_tiles, st);
         return launch_tc<256, 6, false, true>(ma, mb, P, tiles, n_tiles, st);
+    }
+    if (halo) {     // (bn <= 128 here: n_rows <= 128)
+        if (bf) {
+            switch (bn) {
+                case 128: return launch_tc<128, 4, true, false, true>(ma, mb, P, tiles, n_tiles, st);
+                case 64: return launch_tc<64, 8, true, false, true>(ma, mb, P, tiles, n_tiles, st);
+                default: return launch_tc<32, 8, true, false, true>(ma, mb, P, tiles, n_tiles, st);
+            }
+        }
+        switch (bn) {
+            case 128: return launch_tc<128, 4, false, false, true>(ma, mb, P, tiles, n_tiles, st);
+            case 64: return launch_tc<64, 8, false, false, true>(ma, mb, P, tiles, n_tiles, st);
+            default: return launch_tc<32, 8, false, false, true>(ma, mb, P, tiles, n_tiles, st);
+        }
     }
     if (bf) {
         switch (bn) {

@@ -148,6 +148,9 @@ int dofb_pack_weights_batch(const dofb_pack_job *jobs, int n_jobs, int bf16, voi
 /* Tensor-core tiles of 256 columns as CTA pairs (thread-block clusters of 2, tcgen05 cta_group::2: each CTA stages half of the weight tile).
  * Process-wide switch; results are identical up to fp32 summation order (same per-tile K order: bit-identical in practice). */
 void dofb_enable_cta_pairs(int on);
+/* Unit-stride gathers on maps of at least 16 x 8 pixels (<= 128 output columns): stage ONE halo box of the input per tile and channel block
+ * and let every filter tap read its shifted rows out of it, instead of one TMA box per tap.  Process-wide switch. */
+void dofb_enable_halo_tiles(int on);
 /* ---- BF16 tensor-core math (tcgen05 kind::f16, bf16 operands, fp32 accumulate + fp32 epilogue) ----
  * Activations keep their fp32 NHWC buffers; every producer additionally writes a bf16 "shadow" with the same pitch in elements
  * (a multiple of 64), and the tensor-core consumers read the shadows: half the bytes per K element and twice the MMA rate of the

@@ -502,3 +502,36 @@ def test_pack_weights_batch_matches_lazy_packing():
         lib.dofb_enable_weight_cache(0)
         for a, b_ in zip(lazy, batched):
             assert torch.equal(a, b_)
+
+
+@pytest.mark.parametrize("which,case", [("fwd", (4, 48, 64, 64, 128, 3, 1)), ("fwd", (2, 32, 24, 128, 64, 3, 1)), ("dgrad", (4, 96, 128, 32, 194, 4, 2)),
+                                        ("dgrad", (2, 96, 128, 64, 128, 5, 2)), ("dgrad", (2, 34, 22, 128, 256, 3, 1))])
+@pytest.mark.parametrize("mth", [1, 2])
+def test_halo_tiles_match_per_tap_gather(which, case, mth):
+    """Opt-in halo path (one TMA box per tile and channel block, MMA descriptors offset by whole rows of the halo) vs the per-tap gather;
+    only the K order differs (channel block outer), so the results agree to fp32 summation order."""
+    from deepof_b200 import ops, _lib
+    lib = _lib.load()
+    B, H, W, ci, co, k, s = case
+    g = torch.Generator().manual_seed(sum(case) + 3)
+    w = (torch.randn(k, k, ci, co, generator=g) / math.sqrt(k * k * ci)).cuda()
+    geom = ops.conv_geom(B, H, W, ci, co, k, s)
+    xl, yl = (ci + 63) // 64 * 64, (co + 63) // 64 * 64
+    outs = []
+    try:
+        for halo in (0, 1):
+            lib.dofb_enable_halo_tiles(halo)
+            if which == "fwd":
+                x = _buf(B, H, W, xl, ci, torch.Generator().manual_seed(5))
+                y = torch.zeros(B, geom.oh, geom.ow, yl, device="cuda")
+                ops.conv_fwd(geom, ops.Slab(x, 0, ci, _shadow(x)), w, None, ops.Slab(y, 0, co), ops.ACT_ELU, mth)
+                outs.append(y)
+            else:
+                dy = _buf(B, geom.oh, geom.ow, yl, co, torch.Generator().manual_seed(6))
+                d = torch.zeros(B, H, W, xl, device="cuda")
+                ops.conv_dgrad(geom, ops.Slab(dy, 0, co, _shadow(dy)), w, None, ops.Slab(d, 0, ci), ops.ACT_NONE, False, mth)
+                outs.append(d)
+            torch.cuda.synchronize()
+    finally:
+        lib.dofb_enable_halo_tiles(0)
+    assert rel(outs[1], outs[0]) < 1e-5
