@@ -67,6 +67,7 @@ SIGNATURES = {
     "dofb_conv_wgrad_tbias": (_I, [_G, _P, _I, _P, _I, _P, _P, _I, _P]),
     "dofb_elu_bwd": (_I, [_P, _I, _P, _I, _LL, _I, _P, _P, _P]),
     "dofb_elu_bwd_shadow": (_I, [_P, _I, _P, _I, _LL, _I, _P, _P, _P]),
+    "dofb_elu_bwd_shadow16": (_I, [_P, _I, _P, _I, _LL, _I, _P, _P, _P]),
     "dofb_invalidate_weight_cache": (None, []),
     "dofb_enable_weight_cache": (None, [_I]),
     "dofb_enable_cta_pairs": (None, [_I]),

@@ -156,8 +156,10 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float *__restric
 // reduce in registers -> shared -> one atomicAdd per channel per block.
 // WB = false: the fp32 gradient is NOT written back (bf16 math: the only readers of the finished gradient are tensor-core kernels that
 // take the bf16 shadow), which cuts the traffic of this HBM-bound pass from 14 to 10 bytes per element.
-template <bool WB>
-__global__ void __launch_bounds__(256) elu_bwd_kernel(float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c4, int qw,
+// Y16 = true: the ELU output is read from its bf16 shadow (8 instead of 10 bytes per element; ELU' = y > 0 ? 1 : y + 1 then carries the
+// shadow's 2^-9 relative rounding of y, the same order as the bf16 rounding of the gradient itself).
+template <bool WB, bool Y16>
+__global__ void __launch_bounds__(256) elu_bwd_kernel(float *g, int g_ld, const void *y_any, int y_ld, long long n_pix, int c4, int qw,
                                                       long long pix_per_block, float *db, __nv_bfloat16 *g16) {
     const int ql = threadIdx.x & (qw - 1);
     const int q = blockIdx.y * qw + ql;
@@ -169,7 +171,15 @@ __global__ void __launch_bounds__(256) elu_bwd_kernel(float *g, int g_ld, const 
     if (q < c4) {
         for (long long p = p0 + prow; p < p1; p += rows) {
             float4 gv = *reinterpret_cast<float4 *>(g + p * g_ld + q * 4);
-            const float4 yv = __ldg(reinterpret_cast<const float4 *>(y + p * y_ld + q * 4));
+            float4 yv;
+            if (Y16) {
+                const uint2 pk = __ldg(reinterpret_cast<const uint2 *>(static_cast<const __nv_bfloat16 *>(y_any) + p * y_ld + q * 4));
+                const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&pk.x));
+                const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&pk.y));
+                yv = make_float4(lo.x, lo.y, hi.x, hi.y);
+            } else {
+                yv = __ldg(reinterpret_cast<const float4 *>(static_cast<const float *>(y_any) + p * y_ld + q * 4));
+            }
             gv.x *= elu_grad_from_out(yv.x); gv.y *= elu_grad_from_out(yv.y);
             gv.z *= elu_grad_from_out(yv.z); gv.w *= elu_grad_from_out(yv.w);
             if (WB) *reinterpret_cast<float4 *>(g + p * g_ld + q * 4) = gv;
@@ -346,9 +356,10 @@ extern "C" int dofb_cast_bf16(const float *src, int src_ld, void *dst_bf16, int 
     return 0;
 }
 
-static int elu_bwd_launch(float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c, float *db, void *g_bf16, bool write_back, void *stream) {
+static int elu_bwd_launch(float *g, int g_ld, const void *y, bool y16, int y_ld, long long n_pix, int c, float *db, void *g_bf16, bool write_back,
+                          void *stream) {
     DOFB_CHECK_ARG(g && y && n_pix > 0 && c > 0, "dofb_elu_bwd: bad argument");
-    DOFB_CHECK_ARG(c % 4 == 0 && g_ld % 4 == 0 && y_ld % 4 == 0 && aligned16(g) && aligned16(y),
+    DOFB_CHECK_ARG(c % 4 == 0 && g_ld % 4 == 0 && y_ld % 4 == 0 && aligned16(g) && (reinterpret_cast<uintptr_t>(y) & (y16 ? 7u : 15u)) == 0,
                    "dofb_elu_bwd: channels/pitches must be multiples of 4 and pointers 16-byte aligned (c=%d)", c);
     const int c4 = c / 4;
     int qw = 1;
@@ -360,24 +371,29 @@ static int elu_bwd_launch(float *g, int g_ld, const float *y, int y_ld, long lon
     if (ppb < 4 * rows) ppb = 4 * rows;
     ppb = (ppb + rows - 1) / rows * rows;
     blocks = (n_pix + ppb - 1) / ppb;
-    if (write_back)
-        elu_bwd_kernel<true><<<dim3((unsigned)blocks, stripes), 256, 0, as_stream(stream)>>>(g, g_ld, y, y_ld, n_pix, c4, qw, ppb, db,
-                                                                                             reinterpret_cast<__nv_bfloat16 *>(g_bf16));
-    else
-        elu_bwd_kernel<false><<<dim3((unsigned)blocks, stripes), 256, 0, as_stream(stream)>>>(g, g_ld, y, y_ld, n_pix, c4, qw, ppb, db,
-                                                                                              reinterpret_cast<__nv_bfloat16 *>(g_bf16));
+    const dim3 grid((unsigned)blocks, stripes);
+    __nv_bfloat16 *g16 = reinterpret_cast<__nv_bfloat16 *>(g_bf16);
+    if (write_back) elu_bwd_kernel<true, false><<<grid, 256, 0, as_stream(stream)>>>(g, g_ld, y, y_ld, n_pix, c4, qw, ppb, db, g16);
+    else if (y16) elu_bwd_kernel<false, true><<<grid, 256, 0, as_stream(stream)>>>(g, g_ld, y, y_ld, n_pix, c4, qw, ppb, db, g16);
+    else elu_bwd_kernel<false, false><<<grid, 256, 0, as_stream(stream)>>>(g, g_ld, y, y_ld, n_pix, c4, qw, ppb, db, g16);
     DOFB_LAUNCH_OK();
     return 0;
 }
 
 extern "C" int dofb_elu_bwd(float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c, float *db, void *g_bf16, void *stream) {
-    return elu_bwd_launch(g, g_ld, y, y_ld, n_pix, c, db, g_bf16, true, stream);
+    return elu_bwd_launch(g, g_ld, y, false, y_ld, n_pix, c, db, g_bf16, true, stream);
 }
 
 extern "C" int dofb_elu_bwd_shadow(const float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c, float *db, void *g_bf16,
                                    void *stream) {
     DOFB_CHECK_ARG(g_bf16 != nullptr, "dofb_elu_bwd_shadow: needs the bf16 output");
-    return elu_bwd_launch(const_cast<float *>(g), g_ld, y, y_ld, n_pix, c, db, g_bf16, false, stream);
+    return elu_bwd_launch(const_cast<float *>(g), g_ld, y, false, y_ld, n_pix, c, db, g_bf16, false, stream);
+}
+
+extern "C" int dofb_elu_bwd_shadow16(const float *g, int g_ld, const void *y_bf16, int y_ld, long long n_pix, int c, float *db, void *g_bf16,
+                                     void *stream) {
+    DOFB_CHECK_ARG(g_bf16 != nullptr && y_bf16 != nullptr, "dofb_elu_bwd_shadow16: needs the bf16 input and output");
+    return elu_bwd_launch(const_cast<float *>(g), g_ld, y_bf16, true, y_ld, n_pix, c, db, g_bf16, false, stream);
 }
 
 extern "C" int dofb_adam(float *theta, const float *g, float *m, float *v, long long n, float lr_t, float beta1, float beta2,

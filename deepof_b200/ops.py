@@ -6,6 +6,7 @@ Tensors are NHWC float32 CUDA tensors; ``Slab`` describes a channel slice of a p
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import torch
@@ -200,7 +201,10 @@ def elu_bwd(g: Slab, y: Slab, db=None, shadow_only=False):
     assert g.c == y.c and g.n_pix == y.n_pix
     dbp = db.data_ptr() if db is not None else None
     if shadow_only:
-        check(_lib.load().dofb_elu_bwd_shadow(g.ptr, g.ld, y.ptr, y.ld, g.n_pix, g.c, dbp, _need16(g, "elu_bwd"), _stream()))
+        if y.ptr16 is not None and os.environ.get("DOFB_ELU_Y32", "0") != "1":      # ELU output from its bf16 shadow: 8 B per element
+            check(_lib.load().dofb_elu_bwd_shadow16(g.ptr, g.ld, y.ptr16, y.ld, g.n_pix, g.c, dbp, _need16(g, "elu_bwd"), _stream()))
+        else:
+            check(_lib.load().dofb_elu_bwd_shadow(g.ptr, g.ld, y.ptr, y.ld, g.n_pix, g.c, dbp, _need16(g, "elu_bwd"), _stream()))
         return
     check(_lib.load().dofb_elu_bwd(g.ptr, g.ld, y.ptr, y.ld, g.n_pix, g.c, dbp, g.ptr16, _stream()))
 

@@ -176,6 +176,8 @@ int dofb_elu_bwd(float *g, int g_ld, const float *y, int y_ld, long long n_pix, 
 /* Same, but the result goes ONLY to the bf16 shadow (g itself is left untouched): for bf16 math, where the finished gradient of a conv
  * output is read by tensor-core kernels alone. */
 int dofb_elu_bwd_shadow(const float *g, int g_ld, const float *y, int y_ld, long long n_pix, int c, float *db, void *g_bf16, void *stream);
+/* Same, reading the ELU output from its bf16 shadow (the cheapest form: 8 bytes per element). */
+int dofb_elu_bwd_shadow16(const float *g, int g_ld, const void *y_bf16, int y_ld, long long n_pix, int c, float *db, void *g_bf16, void *stream);
 
 /* ---- thin heads (N = 2: bandwidth-bound, not tensor-core shapes) ---------- */
 /* pr_s = conv3x3(feat -> 2) linear, flyingChairsWrapFlow.py:58,69,80,91,102,113 */

@@ -353,6 +353,15 @@ def test_elu_bwd():
     assert torch.equal(g16[..., 16:48], gb[..., 16:48].to(torch.bfloat16))
     assert float(g16[..., :16].abs().max()) == 0.0 and float(g16[..., 48:].abs().max()) == 0.0
     assert rel(db2, xr.grad.sum(dim=(0, 1, 2))) < 1e-5
+    # ... and with the ELU output taken from ITS bf16 shadow: ELU' = y>0 ? 1 : y+1 evaluated on the rounded y
+    y16 = yb.to(torch.bfloat16)
+    g16b = torch.zeros(gb2.shape, dtype=torch.bfloat16, device="cuda")
+    db3 = torch.zeros(32, device="cuda")
+    ops.elu_bwd(ops.Slab(gb2, 16, 32, g16b), ops.Slab(yb, 8, 32, y16), db3, shadow_only=True)
+    yr = y16[..., 8:40].float()
+    want = gr.cuda() * torch.where(yr > 0, torch.ones_like(yr), yr + 1.0)
+    assert torch.equal(g16b[..., 16:48], want.to(torch.bfloat16))
+    assert rel(db3, want.sum(dim=(0, 1, 2))) < 1e-5
 
 
 def test_adam_matches_tf_form():
