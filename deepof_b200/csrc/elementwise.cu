@@ -34,6 +34,7 @@ int num_sms() {
 struct PreParams {
     const float *src, *tgt;
     float *x6, *x6b;
+    __nv_bfloat16 *x6_16, *x6b_16;   // bf16 form of the network input (pitch 8), written instead of x6 / x6b when set
     int x6_ld, x6_h, x6_w, x6_y0, x6_x0;
     int B, H, W;
     float mean[3];
@@ -64,7 +65,24 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
         }
         const long long xo = (((long long)b * P.x6_h + y + P.x6_y0) * P.x6_w + x + P.x6_x0) * P.x6_ld;
         float *o = P.x6 + xo;
-        if (P.x6 == nullptr) {
+        if (P.x6_16 != nullptr) {                   // bf16 network input, 8 channels = one 16-byte store per buffer
+            const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+            if (P.x6b_16 != nullptr) {
+                __nv_bfloat162 s0 = __floats2bfloat162_rn(a[0], a[1]), s1 = __floats2bfloat162_rn(a[2], 0.f);
+                __nv_bfloat162 t0 = __floats2bfloat162_rn(t[0], t[1]), t1 = __floats2bfloat162_rn(t[2], 0.f);
+                uint4 ps, pt;
+                ps.x = *reinterpret_cast<uint32_t *>(&s0); ps.y = *reinterpret_cast<uint32_t *>(&s1); ps.z = ps.w = *reinterpret_cast<const uint32_t *>(&z);
+                pt.x = *reinterpret_cast<uint32_t *>(&t0); pt.y = *reinterpret_cast<uint32_t *>(&t1); pt.z = pt.w = ps.z;
+                *reinterpret_cast<uint4 *>(P.x6_16 + xo) = ps;
+                *reinterpret_cast<uint4 *>(P.x6b_16 + xo) = pt;
+            } else {
+                __nv_bfloat162 v0 = __floats2bfloat162_rn(a[0], a[1]), v1 = __floats2bfloat162_rn(a[2], t[0]), v2 = __floats2bfloat162_rn(t[1], t[2]);
+                uint4 pk;
+                pk.x = *reinterpret_cast<uint32_t *>(&v0); pk.y = *reinterpret_cast<uint32_t *>(&v1); pk.z = *reinterpret_cast<uint32_t *>(&v2);
+                pk.w = *reinterpret_cast<const uint32_t *>(&z);
+                *reinterpret_cast<uint4 *>(P.x6_16 + xo) = pk;
+            }
+        } else if (P.x6 == nullptr) {
             // pyramid-only call (models whose network input and loss images differ: VGG16 photo/geo pairs)
         } else if (P.x6b != nullptr) {             // siamese: source and target in separate 3(+pad)-channel buffers
             float *ob = P.x6b + xo;
@@ -273,19 +291,39 @@ extern "C" const char *dofb_last_error(void) { return err_buf(); }
 extern "C" long long dofb_launch_count(void) { return g_launches.load(); }
 extern "C" void dofb_reset_launch_count(void) { g_launches.store(0); }
 
+static int preprocess_launch(const float *src, const float *tgt, const float mean_bgr[3], float divisor, int B, int H, int W, float *x6,
+                             float *x6b, void *x6_16, void *x6b_16, int x6_ld, int x6_h, int x6_w, int x6_y0, int x6_x0, int n_scales,
+                             float *const *pyr_src, float *const *pyr_tgt, void *stream);
+
 extern "C" int dofb_preprocess(const float *src, const float *tgt, const float mean_bgr[3], float divisor, int B, int H, int W, float *x6,
                                float *x6b, int x6_ld, int x6_h, int x6_w, int x6_y0, int x6_x0, int n_scales,
                                float *const *pyr_src, float *const *pyr_tgt, void *stream) {
-    DOFB_CHECK_ARG(src && tgt && mean_bgr && (x6 || n_scales > 0), "dofb_preprocess: null argument");
+    return preprocess_launch(src, tgt, mean_bgr, divisor, B, H, W, x6, x6b, nullptr, nullptr, x6_ld, x6_h, x6_w, x6_y0, x6_x0, n_scales, pyr_src,
+                             pyr_tgt, stream);
+}
+
+extern "C" int dofb_preprocess_bf16(const float *src, const float *tgt, const float mean_bgr[3], float divisor, int B, int H, int W,
+                                    void *x6_bf16, void *x6b_bf16, int x6_h, int x6_w, int x6_y0, int x6_x0, int n_scales,
+                                    float *const *pyr_src, float *const *pyr_tgt, void *stream) {
+    DOFB_CHECK_ARG(x6_bf16 && aligned16(x6_bf16) && (x6b_bf16 == nullptr || aligned16(x6b_bf16)), "dofb_preprocess_bf16: needs 16-byte aligned bf16 buffers (pitch 8)");
+    return preprocess_launch(src, tgt, mean_bgr, divisor, B, H, W, nullptr, nullptr, x6_bf16, x6b_bf16, 8, x6_h, x6_w, x6_y0, x6_x0, n_scales, pyr_src,
+                             pyr_tgt, stream);
+}
+
+static int preprocess_launch(const float *src, const float *tgt, const float mean_bgr[3], float divisor, int B, int H, int W, float *x6,
+                             float *x6b, void *x6_16, void *x6b_16, int x6_ld, int x6_h, int x6_w, int x6_y0, int x6_x0, int n_scales,
+                             float *const *pyr_src, float *const *pyr_tgt, void *stream) {
+    DOFB_CHECK_ARG(src && tgt && mean_bgr && (x6 || x6_16 || n_scales > 0), "dofb_preprocess: null argument");
     DOFB_CHECK_ARG(B > 0 && H > 0 && W > 0 && (x6 == nullptr || x6_ld >= 6) && divisor != 0.f, "dofb_preprocess: bad shape B=%d H=%d W=%d ld=%d", B, H, W, x6_ld);
     DOFB_CHECK_ARG(n_scales >= 0 && n_scales <= 8, "dofb_preprocess: n_scales=%d out of range", n_scales);
     DOFB_CHECK_ARG(n_scales == 0 || (H % (1 << n_scales) == 0 && W % (1 << n_scales) == 0),
                    "dofb_preprocess: H=%d W=%d must be multiples of 2^%d", H, W, n_scales);
     DOFB_CHECK_ARG(x6_ld != 8 || aligned16(x6), "dofb_preprocess: x6 must be 16-byte aligned");
-    DOFB_CHECK_ARG(x6 == nullptr || (x6_y0 >= 0 && x6_x0 >= 0 && x6_y0 + H <= x6_h && x6_x0 + W <= x6_w), "dofb_preprocess: the image does not fit the x6 buffer");
+    DOFB_CHECK_ARG((x6 == nullptr && x6_16 == nullptr) || (x6_y0 >= 0 && x6_x0 >= 0 && x6_y0 + H <= x6_h && x6_x0 + W <= x6_w), "dofb_preprocess: the image does not fit the x6 buffer");
     PreParams P;
     P.src = src; P.tgt = tgt; P.x6 = x6; P.x6_ld = x6_ld; P.B = B; P.H = H; P.W = W;
     P.x6_h = x6_h; P.x6_w = x6_w; P.x6_y0 = x6_y0; P.x6_x0 = x6_x0; P.x6b = x6b;
+    P.x6_16 = reinterpret_cast<__nv_bfloat16 *>(x6_16); P.x6b_16 = reinterpret_cast<__nv_bfloat16 *>(x6b_16);
     for (int c = 0; c < 3; ++c) P.mean[c] = mean_bgr[c];
     P.divisor = divisor;
     P.n_scales = n_scales;

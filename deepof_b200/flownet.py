@@ -342,12 +342,10 @@ class FlowNetS:
 
     # ------------------------------------------------------------------ forward
     def _preprocess(self, source, target):
+        bf = self.math == MATH_BF16 and self.x6.shape[3] == 8      # bf16 first-layer kernels: the network input is produced in bf16 only
         self._k("preprocess", ops.preprocess, source, target, self.mean, self.x6, [self.pyr_src[s] for s in range(1, self.N_SCALES + 1)],
-                [self.pyr_tgt[s] for s in range(1, self.N_SCALES + 1)], self.x6_origin, self.x6b)
-        if self.math == MATH_BF16:          # bf16 copies of the zero-bordered first-layer inputs
-            for t in (self.x6, self.x6b):
-                if t is not None:
-                    self._k("cast:x6", ops.cast_bf16_raw, t, self._sh[id(t)], t.shape[3])
+                [self.pyr_tgt[s] for s in range(1, self.N_SCALES + 1)], self.x6_origin, self.x6b, 255.0,
+                self._sh[id(self.x6)] if bf else None, self._sh[id(self.x6b)] if bf and self.x6b is not None else None)
 
     def _fwd_layer(self, L):
         P, mth = self.params, self.math

@@ -95,7 +95,7 @@ def conv_geom(B, ih, iw, ci, co, k, stride) -> ConvGeom:
     return ConvGeom(B, ih, iw, ci, oh, ow, co, k, k, stride, pt, pl)
 
 
-def preprocess(src, tgt, mean, x6, pyr_src, pyr_tgt, origin=(0, 0), x6b=None, divisor=255.0):
+def preprocess(src, tgt, mean, x6, pyr_src, pyr_tgt, origin=(0, 0), x6b=None, divisor=255.0, x6_16=None, x6b_16=None):
     """x6 may be larger than the image (zero border for dofb_conv1_*); ``origin`` = (row, col) of the image in it.
     With ``x6b`` (siamese models) the source goes to x6[..., 0:3] and the target to x6b[..., 0:3] instead of 6 stacked channels."""
     _req(src, "src"); _req(tgt, "tgt")
@@ -109,6 +109,12 @@ def preprocess(src, tgt, mean, x6, pyr_src, pyr_tgt, origin=(0, 0), x6b=None, di
     ps = (C.c_void_p * max(n, 1))(*[t.data_ptr() for t in pyr_src])
     pt = (C.c_void_p * max(n, 1))(*[t.data_ptr() for t in pyr_tgt])
     lib = _lib.load()
+    if x6_16 is not None:           # bf16 network input only (bf16 first-layer kernels): no fp32 x6 is written
+        assert x6_16.dtype == torch.bfloat16 and x6_16.shape[3] == 8 and x6_16.is_cuda and x6_16.is_contiguous()
+        check(lib.dofb_preprocess_bf16(src.data_ptr(), tgt.data_ptr(), m, float(divisor), B, H, W, x6_16.data_ptr(),
+                                       x6b_16.data_ptr() if x6b_16 is not None else None, x6_16.shape[1], x6_16.shape[2], origin[0], origin[1], n, ps, pt,
+                                       _stream()))
+        return
     xs = x6.shape if x6 is not None else (0, 0, 0, 0)
     check(lib.dofb_preprocess(src.data_ptr(), tgt.data_ptr(), m, float(divisor), B, H, W, x6.data_ptr() if x6 is not None else None,
                               x6b.data_ptr() if x6b is not None else None, xs[3], xs[1], xs[2], origin[0], origin[1], n, ps, pt, _stream()))

@@ -55,6 +55,11 @@ void dofb_reset_launch_count(void);
 int dofb_preprocess(const float *src, const float *tgt, const float mean_bgr[3], float divisor,
                     int B, int H, int W, float *x6, float *x6b, int x6_ld, int x6_h, int x6_w, int x6_y0, int x6_x0,
                     int n_scales, float *const *pyr_src, float *const *pyr_tgt, void *stream);
+/* Same, but the network input is written as bf16 (pitch 8: [src BGR, tgt BGR, 0, 0], or with x6b_bf16 the siamese pair [BGR,0..] / [BGR,0..])
+ * for the bf16 first-layer kernels; the fp32 form is not produced. */
+int dofb_preprocess_bf16(const float *src, const float *tgt, const float mean_bgr[3], float divisor, int B, int H, int W,
+                         void *x6_bf16, void *x6b_bf16 /* may be NULL */, int x6_h, int x6_w, int x6_y0, int x6_x0, int n_scales,
+                         float *const *pyr_src, float *const *pyr_tgt, void *stream);
 
 /* ---- warp + Charbonnier photometric + smoothness loss -------------------- */
 /* Replaces: flyingChairsWrapFlow.loss_interp (flyingChairsWrapFlow.py:752-876,

@@ -73,6 +73,16 @@ def test_preprocess_and_pyramid():
     ops.preprocess(src.cuda(), tgt.cuda(), fs.FLYINGCHAIRS_MEAN, xa, ps, pt, x6b=xt)
     assert torch.equal(xa[..., :3], x6[..., :3]) and torch.equal(xt[..., :3], x6[..., 3:6])
     assert float(xa[..., 3:].abs().max()) == 0.0 and float(xt[..., 3:].abs().max()) == 0.0
+    # bf16 network input (bf16 first-layer kernels): exactly the rounded fp32 values, zero border untouched, pyramids as before
+    xb16 = torch.zeros(B, H + 6, W + 8, 8, dtype=torch.bfloat16, device="cuda")
+    ps2 = [torch.zeros_like(t) for t in ps]
+    pt2 = [torch.zeros_like(t) for t in pt]
+    ops.preprocess(src.cuda(), tgt.cuda(), fs.FLYINGCHAIRS_MEAN, None, ps2, pt2, origin=(2, 2), x6_16=xb16)
+    assert torch.equal(xb16, xb.to(torch.bfloat16))
+    assert all(torch.equal(a, b) for a, b in zip(ps + pt, ps2 + pt2))
+    xa16, xt16 = torch.zeros_like(xb16), torch.zeros_like(xb16)
+    ops.preprocess(src.cuda(), tgt.cuda(), fs.FLYINGCHAIRS_MEAN, None, ps2, pt2, origin=(2, 2), x6_16=xa16, x6b_16=xt16)
+    assert torch.equal(xa16[:, 2:2 + H, 2:2 + W], xa.to(torch.bfloat16)) and torch.equal(xt16[:, 2:2 + H, 2:2 + W], xt.to(torch.bfloat16))
     xi, ni = fs.preprocess(src)
     xo, no = fs.preprocess(tgt)
     ref6 = torch.cat([xi, xo, torch.zeros(B, H, W, 2)], dim=3)
