@@ -156,6 +156,12 @@ def cpu_step_rate(sample_pairs: int, steps: int, warmup: int):
     import torch
     from oracle import flownet_s as ofs, adam as oadam
     from deepof_b200.synth import make_pairs
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would silently make this arm single-threaded)
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    torch.set_num_threads(max(1, avail))
     threads = torch.get_num_threads()
     src, tgt, _ = make_pairs(sample_pairs, H, W, seed=0)
     params = ofs.init_params(1)
