@@ -281,6 +281,7 @@ constexpr int TC_BM = 128, TC_BK = 32, TC_THREADS = 192, TC_MAX_TAPS = 49;
 constexpr int TCG_EPI_WARPS = 8, TCG_THREADS = (TCG_EPI_WARPS + 2) * 32, TCG_STG_BYTES = TCG_EPI_WARPS * 32 * 16 * 4;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 constexpr int TC_HALO_ROWS = 18;                // halo box rows: 16 tile rows + a vertical tap span of up to 2
+constexpr int TC_HALO_TAPS = 4;                 // taps per phase the halo path handles (weights of one channel block share the slot)
 
 struct TapInfo {
     short oy, ox;      // unit mode: source = (iy + oy, ix + ox); parity mode: quotient offsets (qy, qx)
@@ -344,8 +345,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 // leader collects the 8 + 8 epilogue warps of both CTAs.
 // HALO = true (unit-stride gathers on maps of at least 16 x 8 pixels, BN <= 128): the tile is 8 pixels wide and 16 rows tall, and per channel
 // block ONE TMA box of 18 rows x 16 columns lands in an A slot; every filter tap then reads its shifted 128 rows straight out of that halo
-// (descriptor start = tap offset in rows), so A crosses the L2->SM path once per channel block instead of once per tap.  The weights stream
-// through their own ring (STAGES slots of one k-block), K order = (channel block, tap).
+// (descriptor start = tap offset in rows), so A crosses the L2->SM path once per channel block instead of once per tap.  The weight k-blocks
+// of all (<= 4) taps of that channel block ride in the same slot behind the same barrier; K order = (channel block, tap); STAGES = slots.
 template <int BN, int STAGES, bool BF, bool CG2 = false, bool HALO = false>
 __global__ void __launch_bounds__(TCG_THREADS, 1)
 tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -360,8 +361,11 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     constexpr int KPS = (BN <= 64 && !CG2 && !HALO) ? 2 : 1;
     constexpr int SUB_BYTES = TC_A_BYTES + B_BYTES;
     constexpr int STAGE_BYTES = KPS * SUB_BYTES;
-    constexpr int HA_SLOTS = 3, HA_BYTES = TC_HALO_ROWS * 16 * 128;       // halo slots: 18 rows x 16 pixels x 128 B = 36 KB
-    constexpr int RING_BYTES = HALO ? HA_SLOTS * HA_BYTES + STAGES * B_BYTES : STAGES * STAGE_BYTES;
+    // halo mode: a slot = one halo box (18 rows x 16 pixels x 128 B = 36 KB) + the weight k-blocks of ALL (<= TC_HALO_TAPS) taps of the phase
+    // for that channel block, behind ONE barrier (per-tap weight stages left the single MMA-issue thread as the bottleneck)
+    constexpr int HA_BYTES = TC_HALO_ROWS * 16 * 128, HS_BYTES = HA_BYTES + TC_HALO_TAPS * B_BYTES;
+    constexpr int HA_SLOTS = HALO ? STAGES : 1;
+    constexpr int RING_BYTES = HALO ? HA_SLOTS * HS_BYTES : STAGES * STAGE_BYTES;
     constexpr int ACC_COLS = BN < 32 ? 32 : BN;
     constexpr int TMEM_COLS = 2 * ACC_COLS;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -411,18 +415,15 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 const int tx = mt % V.tiles_x, ty = (mt / V.tiles_x) % V.tiles_y, tn = mt / (V.tiles_x * V.tiles_y);
                 const int ix0 = tx * P.TW, iy0 = ty * P.TH, in0 = tn * P.TN, n0 = nt * BN + (int)rank * BROWS;
                 if (HALO) {
-                    // K order (channel block, tap): one halo box per channel block, one weight k-block per (channel block, tap)
+                    // K order (channel block, tap): per channel block one slot = the halo box + the weight k-blocks of every tap
                     for (int cb = 0; cb < P.ncb; ++cb, ++ita) {
                         const int sa_i = ita % HA_SLOTS;
+                        uint8_t *slot = smem + sa_i * HS_BYTES;
                         mbar_wait(&a_empty[sa_i], ((ita / HA_SLOTS) & 1) ^ 1);
-                        mbar_expect_tx(&a_full[sa_i], HA_BYTES);
-                        tma_load_4d(smem + sa_i * HA_BYTES, &map_a, &a_full[sa_i], P.a_coff + cb * KELEMS, ix0 + V.ox_min, iy0 + V.oy_min, in0);
-                        for (int tp = 0; tp < V.ntaps; ++tp, ++it) {
-                            const int s = it % STAGES;
-                            mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
-                            mbar_expect_tx(&full_bar[s], B_BYTES);
-                            tma_load_2d(smem + HA_SLOTS * HA_BYTES + s * B_BYTES, &map_b, &full_bar[s], P.taps[V.tap0 + tp].wk + cb * KELEMS, n0);
-                        }
+                        mbar_expect_tx(&a_full[sa_i], HA_BYTES + V.ntaps * B_BYTES);
+                        tma_load_4d(slot, &map_a, &a_full[sa_i], P.a_coff + cb * KELEMS, ix0 + V.ox_min, iy0 + V.oy_min, in0);
+                        for (int tp = 0; tp < V.ntaps; ++tp)
+                            tma_load_2d(slot + HA_BYTES + tp * B_BYTES, &map_b, &a_full[sa_i], P.taps[V.tap0 + tp].wk + cb * KELEMS, n0);
                     }
                     continue;
                 }
@@ -482,20 +483,16 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                         const int sa_i = ita % HA_SLOTS;
                         mbar_wait(&a_full[sa_i], (ita / HA_SLOTS) & 1);
                         tc_fence_after();
-                        const uint32_t abuf = smem_u32(smem + sa_i * HA_BYTES);
-                        for (int tp = 0; tp < V.ntaps; ++tp, ++it) {
-                            const int s = it % STAGES;
-                            mbar_wait(&full_bar[s], (it / STAGES) & 1);
-                            tc_fence_after();
+                        const uint32_t abuf = smem_u32(smem + sa_i * HS_BYTES);
+                        for (int tp = 0; tp < V.ntaps; ++tp) {
                             const TapInfo ti = P.taps[V.tap0 + tp];
                             const uint64_t da = make_desc_k128_halo(abuf, (ti.oy - V.oy_min) * 16 + (ti.ox - V.ox_min));
-                            const uint64_t db = make_desc_k128(smem_u32(smem + HA_SLOTS * HA_BYTES + s * B_BYTES));
+                            const uint64_t db = make_desc_k128(abuf + HA_BYTES + tp * B_BYTES);
 #pragma unroll
                             for (int kk = 0; kk < TC_BK / 8; ++kk)
                                 umma<BF>(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (cb | tp | kk) != 0);
-                            umma_commit(&empty_bar[s]);     // weight slot free
                         }
-                        umma_commit(&a_empty[sa_i]);        // halo slot free once every tap has read it
+                        umma_commit(&a_empty[sa_i]);        // slot free once every tap has been multiplied
                     }
                     umma_commit(&acc_full[acc]);
                     continue;
@@ -906,7 +903,8 @@ static void choose_tile(int cnt_y, int cnt_x, int &TW, int &TH, int &TN) {
 template <int BN, int STAGES, bool BF = false, bool CG2 = false, bool HALO = false>
 static int launch_tc(const CUtensorMap &ma, const CUtensorMap &mb, const TcParams &Pin, int tiles, int n_tiles, cudaStream_t st) {
     constexpr int KPS = (BN <= 64 && !CG2 && !HALO) ? 2 : 1;
-    constexpr int smem = (HALO ? 3 * TC_HALO_ROWS * 16 * 128 + STAGES * BN * TC_BK * 4
+    static_assert(!HALO || STAGES <= 3, "halo slots share the three a_full / a_empty barriers");
+    constexpr int smem = (HALO ? STAGES * (TC_HALO_ROWS * 16 * 128 + TC_HALO_TAPS * BN * TC_BK * 4)
                                : STAGES * KPS * (TC_A_BYTES + (CG2 ? BN / 2 : BN) * TC_BK * 4)) + TCG_STG_BYTES + 1024 + 256;
     static_assert(smem <= 227 * 1024, "shared-memory budget");
     static bool configured = false;
@@ -1000,7 +998,7 @@ static int run_gather(const GatherSpec &G, const TcParams &Pin, cudaStream_t st)
     P.out = G.out; P.out_ld = G.out_ld; P.out16 = G.accumulate ? nullptr : reinterpret_cast<__nv_bfloat16 *>(G.out16);
     P.bias = G.bias; P.n_valid = G.n_valid; P.rh = G.rh; P.rw = G.rw;
     P.act = G.act; P.accumulate = G.accumulate; P.B = G.B;
-    // ---- halo tiles: unit-stride gather, every phase at least 16 x 8 pixels, tap offsets spanning <= 2 rows / 8 columns, >= 2 taps ----
+    // ---- halo tiles: unit-stride gather, every phase at least 16 x 8 pixels, <= 4 taps per phase spanning <= 2 rows / 8 columns ----
     const int n_rows_out = G.contract_ci ? G.w_co : G.w_ci;
     bool halo = g_halo && !P.parity && n_rows_out <= 128;
     {
@@ -1013,7 +1011,8 @@ static int run_gather(const GatherSpec &G, const TcParams &Pin, cudaStream_t st)
                 oy0 = P.taps[t].oy < oy0 ? P.taps[t].oy : oy0; oy1 = P.taps[t].oy > oy1 ? P.taps[t].oy : oy1;
                 ox0 = P.taps[t].ox < ox0 ? P.taps[t].ox : ox0; ox1 = P.taps[t].ox > ox1 ? P.taps[t].ox : ox1;
             }
-            if (tn < 2 || oy1 - oy0 > TC_HALO_ROWS - 16 || ox1 - ox0 > 8 || cy < 16 || cx < 8) halo = false;
+            if (tn > TC_HALO_TAPS || oy1 - oy0 > TC_HALO_ROWS - 16 || ox1 - ox0 > 8 || cy < 16 || cx < 8) halo = false;
+            if (nq == 1 && tn < 2) halo = false;        // (a 1x1 convolution has nothing to share)
             if (P.nphase > 1) { P.ph[q].oy_min = oy0; P.ph[q].ox_min = ox0; } else { P.oy_min = oy0; P.ox_min = ox0; }
         }
     }
@@ -1089,15 +1088,15 @@ static int run_gather(const GatherSpec &G, const TcParams &Pin, cudaStream_t st)
     if (halo) {     // (bn <= 128 here: n_rows <= 128)
         if (bf) {
             switch (bn) {
-                case 128: return launch_tc<128, 4, true, false, true>(ma, mb, P, tiles, n_tiles, st);
-                case 64: return launch_tc<64, 8, true, false, true>(ma, mb, P, tiles, n_tiles, st);
-                default: return launch_tc<32, 8, true, false, true>(ma, mb, P, tiles, n_tiles, st);
+                case 128: return launch_tc<128, 2, true, false, true>(ma, mb, P, tiles, n_tiles, st);
+                case 64: return launch_tc<64, 3, true, false, true>(ma, mb, P, tiles, n_tiles, st);
+                default: return launch_tc<32, 3, true, false, true>(ma, mb, P, tiles, n_tiles, st);
             }
         }
         switch (bn) {
-            case 128: return launch_tc<128, 4, false, false, true>(ma, mb, P, tiles, n_tiles, st);
-            case 64: return launch_tc<64, 8, false, false, true>(ma, mb, P, tiles, n_tiles, st);
-            default: return launch_tc<32, 8, false, false, true>(ma, mb, P, tiles, n_tiles, st);
+            case 128: return launch_tc<128, 2, false, false, true>(ma, mb, P, tiles, n_tiles, st);
+            case 64: return launch_tc<64, 3, false, false, true>(ma, mb, P, tiles, n_tiles, st);
+            default: return launch_tc<32, 3, false, false, true>(ma, mb, P, tiles, n_tiles, st);
         }
     }
     if (bf) {

@@ -504,11 +504,13 @@ def test_pack_weights_batch_matches_lazy_packing():
             assert torch.equal(a, b_)
 
 
-@pytest.mark.parametrize("which,case", [("fwd", (4, 48, 64, 64, 128, 3, 1)), ("fwd", (2, 32, 24, 128, 64, 3, 1)), ("dgrad", (4, 96, 128, 32, 194, 4, 2)),
-                                        ("dgrad", (2, 96, 128, 64, 128, 5, 2)), ("dgrad", (2, 34, 22, 128, 256, 3, 1))])
+@pytest.mark.parametrize("which,case", [("dgrad", (4, 96, 128, 32, 194, 4, 2)), ("dgrad", (2, 64, 96, 64, 386, 4, 2)), ("dgrad", (2, 48, 64, 128, 130, 4, 2)),
+                                        ("dgrad", (2, 64, 48, 64, 128, 3, 2)), ("dgrad", (3, 34, 22, 96, 64, 2, 1)), ("fwd", (2, 40, 24, 64, 128, 2, 1)),
+                                        ("fwd", (4, 48, 64, 64, 128, 3, 1)), ("dgrad", (2, 96, 128, 64, 128, 5, 2))])   # (last two: > 4 taps, per-tap path)
 @pytest.mark.parametrize("mth", [1, 2])
 def test_halo_tiles_match_per_tap_gather(which, case, mth):
-    """Opt-in halo path (one TMA box per tile and channel block, MMA descriptors offset by whole rows of the halo) vs the per-tap gather;
+    """Opt-in halo path (one TMA box per tile and channel block, MMA descriptors offset by whole rows of the halo; phases of <= 4 taps:
+    the 4x4 / stride-2 transposed convs and 3x3 / stride-2 input gradients) vs the per-tap gather;
     only the K order differs (channel block outer), so the results agree to fp32 summation order."""
     from deepof_b200 import ops, _lib
     lib = _lib.load()
