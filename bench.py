@@ -148,6 +148,28 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU / reference arm
+def _host_cores() -> int:
+    """Physical cores in this process's affinity mask, capped by the cgroup v2 CPU quota (oversubscribing OpenMP threads is far slower)."""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        cpus = list(range(os.cpu_count() or 1))
+    groups = set()
+    for c in cpus:
+        try:
+            groups.add(open(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list").read().strip())
+        except OSError:
+            groups.add(str(c))
+    n = max(1, len(groups))
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return n
+
+
 def cpu_step_rate(sample_pairs: int, steps: int, warmup: int):
     """Times the oracle (reference-semantics CPU restatement, torch fp32) training step on the host cores.
 
@@ -156,12 +178,10 @@ def cpu_step_rate(sample_pairs: int, steps: int, warmup: int):
     import torch
     from oracle import flownet_s as ofs, adam as oadam
     from deepof_b200.synth import make_pairs
-    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would silently make this arm single-threaded)
-    try:
-        avail = len(os.sched_getaffinity(0))
-    except AttributeError:
-        avail = os.cpu_count() or 1
-    torch.set_num_threads(max(1, avail))
+    # torchrun exports OMP_NUM_THREADS=1, which would silently make this arm single-threaded: in that case (only) use the physical
+    # cores this process may run on, capped by the cgroup CPU quota; a plain `python bench.py` keeps torch's own default
+    if "OMP_NUM_THREADS" in os.environ:
+        torch.set_num_threads(_host_cores())
     threads = torch.get_num_threads()
     src, tgt, _ = make_pairs(sample_pairs, H, W, seed=0)
     params = ofs.init_params(1)
