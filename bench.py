@@ -178,10 +178,9 @@ def cpu_step_rate(sample_pairs: int, steps: int, warmup: int):
     import torch
     from oracle import flownet_s as ofs, adam as oadam
     from deepof_b200.synth import make_pairs
-    # torchrun exports OMP_NUM_THREADS=1, which would silently make this arm single-threaded: in that case (only) use the physical
-    # cores this process may run on, capped by the cgroup CPU quota; a plain `python bench.py` keeps torch's own default
-    if "OMP_NUM_THREADS" in os.environ:
-        torch.set_num_threads(_host_cores())
+    # the physical cores this process may run on, capped by the cgroup CPU quota: torchrun exports OMP_NUM_THREADS=1 (would make this arm
+    # single-threaded) and torch's own default ignores the quota (64 threads on a 16-CPU quota on the bench boxes)
+    torch.set_num_threads(_host_cores())
     threads = torch.get_num_threads()
     src, tgt, _ = make_pairs(sample_pairs, H, W, seed=0)
     params = ofs.init_params(1)
