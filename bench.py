@@ -334,6 +334,12 @@ def run_ours(args, rank, local_rank, world):
         gemm_ms = sum(classes[k]["ms"] for k in gemm)
         gemm_fl = sum(classes[k]["flops"] for k in gemm)
         gemm_n = sum(classes[k]["launches"] for k in gemm)
+        # DRAM bytes per launch of the tcgen05 family, from the committed ncu capture of the same workload (profiles/r01_tc_traffic.json:
+        # `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over the 44 tc_* launches of one step); only valid for that workload
+        tc_traffic = None
+        tr = ROOT / "profiles" / "r01_tc_traffic.json"
+        if tr.exists() and args.math == "bf16" and args.model == "flownets" and B == PER_GPU_BATCH:
+            tc_traffic = float(json.loads(tr.read_text())["dram_bytes_per_launch"])
         tf32 = args.math == "tf32"
         peak = peaks["bf16_sustained"] * (0.5 if tf32 else 1.0)        # bf16 math (and the fp32 SIMT path) are divided by the bf16 peak
         ach = gemm_fl / (gemm_ms * 1e-3) / 1e12
@@ -342,7 +348,8 @@ def run_ours(args, rank, local_rank, world):
                                                 "fp32": "SIMT fp32 FFMA (parity-grade path)"}[args.math],
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})" + (" x0.5 for tf32" if tf32 else ""),
-                "traffic": None, "share_of_step": gemm_ms / total_ms, "launches_per_step": gemm_n,
+                "traffic": tc_traffic, "traffic_source": "profiles/r01_tc_traffic.json (ncu dram bytes, average per tc_* launch)" if tc_traffic else None,
+                "share_of_step": gemm_ms / total_ms, "launches_per_step": gemm_n,
                 "avg_launch_ms": gemm_ms / max(gemm_n, 1)}
         breakdown = []
         for k, c in sorted(classes.items(), key=lambda kv: -kv[1]["ms"]):

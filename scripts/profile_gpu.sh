@@ -14,3 +14,7 @@ ncu --set full --clock-control none --import-source on -k regex:tc_wgrad -s 30 -
 ncu --set full --clock-control none --import-source on -k regex:"warp_loss|head_dgrad|head_wgrad|head_fwd|adam" -s 40 -c 6 -f -o gpurun_out/prof_hbm \
     python bench.py --math $MATH --steps 1 --warmup 3 --no-cpu > /dev/null 2>&1
 ls -la gpurun_out/*.ncu-rep gpurun_out/launches_${MATH}.csv
+# 3) DRAM traffic of every tcgen05 launch of one step (cheap metrics only) -> gpurun_out/tc_traffic_${MATH}.csv
+#    (scripts/summarize_profiles.py turns it into profiles/rNN_tc_traffic.json, which bench.py reports as roofline.traffic)
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:"tc_" -s 60 -c 44 --csv \
+    --log-file gpurun_out/tc_traffic_${MATH}.csv python scripts/prof_heads.py $MATH > /dev/null 2>&1
