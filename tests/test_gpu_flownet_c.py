@@ -81,3 +81,26 @@ def test_flownetc_train_steps_reduce_loss():
         eng.train_step(src.cuda(), tgt.cuda(), lr=1.6e-5)
     eng.forward(src.cuda(), tgt.cuda(), with_grad=False)
     assert eng.total_loss().item() < l0
+
+
+def test_flownetc_bf16_tracks_fp32(case):
+    """bf16 tensor-core mode (bf16 shadows, CTA pairs, merged stride phases, batched packs, bf16 siamese pre-processing) on FlowNetC."""
+    from deepof_b200.flownet import FlowNetC
+    B, H, W = 2, 192, 256
+    eb = FlowNetC(B, H, W, seed=None, math_mode="bf16", tc_wgrad=True)
+    eb.load_params(case["params"])
+    eb.forward(case["src"].cuda(), case["tgt"].cuda())
+    eb.backward()
+    e32 = case["eng"]
+    epe32 = metrics.flow_ee(metrics.eval_flow(e32.pr[1].cpu() * 10.0, H, W), case["gt"]).item()
+    epeb = metrics.flow_ee(metrics.eval_flow(eb.pr[1].cpu() * 10.0, H, W), case["gt"]).item()
+    print(f"FlowNetC bf16 vs fp32: EPE {epe32:.6f} / {epeb:.6f}")
+    assert abs(epeb - epe32) < 1e-3                                   # north_star tolerance
+    assert torch.allclose(eb.loss4, e32.loss4, rtol=2e-2, atol=1e-3)
+    assert torch.isfinite(eb.grad).all()
+    cos = torch.nn.functional.cosine_similarity(eb.grad.double(), e32.grad.double(), dim=0).item()
+    print("gradient cosine bf16 vs fp32:", cos)
+    assert cos > 0.8
+    for _ in range(2):
+        eb.train_step(case["src"].cuda(), case["tgt"].cuda(), lr=1.6e-5)
+    assert torch.isfinite(eb.theta).all()
