@@ -1,4 +1,4 @@
-// tcgen05 (kind::tf32) implicit-GEMM convolution family for sm_100a (math = DOFB_MATH_TF32).
+// tcgen05 (kind::tf32 / kind::f16) implicit-GEMM convolution family for sm_100a (math = DOFB_MATH_TF32 and the *_bf16 entry points).
 //
 //   out[row][n] (+)= sum_{tap, c} A[gather(row, tap)][c] * W(tap, c, n)
 //
@@ -9,12 +9,14 @@
 //         is the TMA out-of-bounds zero fill (asymmetric pads are just a coordinate offset), so
 //         there is no im2col buffer and no padding kernel.  Stride-2 convs view the map as
 //         [N, H/2, 2, W/2, 2*C] (rank-5 map) so that the strided gather is again a dense box.
-// W     = weights re-packed per call to K-major [N][taps*Cpad] (zero padded), one TMA 2-D load.
-// acc   = fp32 in TMEM (BN columns); epilogue warps read it with tcgen05.ld, fuse bias + ELU
+// W     = weights re-packed to K-major [N][taps*Cpad] (zero padded; cached per optimiser step), one TMA 2-D load.
+// acc   = fp32 in TMEM (2 x BN columns); epilogue warps read it with tcgen05.ld, fuse bias + ELU
 //         (+ accumulate) and store NHWC with the caller's pitch (concat slices written in place).
 //
-// Warp roles (192 threads): warps 0-3 epilogue (TMEM lane quarter = warp id), warp 4 TMA producer,
-// warp 5 TMEM allocator + single-thread MMA issuer.  mbarrier ring of STAGES smem slots.
+// Gather-GEMM warp roles (320 threads): warps 0-7 epilogue (TMEM lane quarter = warp & 3), warp 8 TMA producer,
+// warp 9 TMEM allocator + single-thread MMA issuer; mbarrier ring of STAGES smem slots; CTA pairs (cta_group::2) for the
+// 256-column tiles; all stride phases of a transposed gather in one persistent launch; opt-in halo tiles.
+// Weight-gradient and correlation kernels (192 threads): warps 0-3 epilogue / operand generators, warp 4 producer, warp 5 MMA.
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -356,7 +358,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     constexpr int BROWS = CG2 ? BN / 2 : BN;          // B rows staged by this CTA
     constexpr int B_BYTES = BROWS * TC_BK * 4;
     // k-blocks per pipeline stage: the narrow tiles (BN <= 64) retire a k-block in 64-128 MMA cycles, faster than one producer thread and
-    // one barrier round trip can follow, so they move two k-blocks per stage (half the barrier traffic, four TMA boxes issued by four lanes)
+    // one barrier round trip can follow, so they move two k-blocks per stage (half the barrier traffic per k-block)
     static_assert(!HALO || (!CG2 && BN <= 128), "halo tiles: single CTA, at most 128 columns");
     constexpr int KPS = (BN <= 64 && !CG2 && !HALO) ? 2 : 1;
     constexpr int SUB_BYTES = TC_A_BYTES + B_BYTES;
@@ -374,7 +376,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(stage_f + TCG_EPI_WARPS * 32 * 16);
     uint64_t *empty_bar = full_bar + STAGES;
     uint64_t *acc_full = empty_bar + STAGES;       // [2] MMA -> epilogue
-    uint64_t *acc_empty = acc_full + 2;            // [2] epilogue -> MMA (4 warps arrive)
+    uint64_t *acc_empty = acc_full + 2;            // [2] epilogue -> MMA (the 8 epilogue warps arrive; 16 for a CTA pair)
     uint64_t *a_full = acc_empty + 2;              // [3] halo mode: A slots (full_bar / empty_bar then belong to the B ring)
     uint64_t *a_empty = a_full + 3;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_empty + 3);
