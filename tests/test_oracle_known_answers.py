@@ -227,3 +227,64 @@ def test_forward_structure_small():
     assert prev1.shape == (1, 96, 128, 3) and len(losses) == 6
     want = sum(w * l["total"] for w, l in zip(fs.LOSS_WEIGHTS, losses))
     assert abs(total.item() - want.item()) < 1e-5
+
+
+# ---- FlowNetC correlation (paper definition; the reference has no such layer) and VGG16 oracle pieces ----------------------------
+
+def test_correlation_known_answers():
+    """corr[b,y,x,(i,j)] = <f1[y,x], f2[y+dy_i, x+dx_j]> / C with zero outside: the centre channel of a map with itself is the mean square,
+    a shifted copy moves the peak to the matching displacement, channels pointing outside the map are exactly zero."""
+    from oracle import flownet_c as oc
+    g = torch.Generator().manual_seed(0)
+    B, h, w, c, md, s2 = 1, 9, 11, 8, 4, 2
+    D = 2 * (md // s2) + 1
+    f = torch.randn(B, h, w, c, generator=g)
+    out = oc.correlation(f, f, md, s2)
+    assert out.shape == (B, h, w, D * D)
+    centre = (D // 2) * D + D // 2
+    assert torch.allclose(out[..., centre], (f * f).mean(-1), atol=1e-6)
+    # f2 = f1 shifted by (dy, dx) = (+2, -2): the response at channel (dy=+2, dx=-2) equals the mean square wherever the shift stays inside
+    f2 = torch.zeros_like(f)
+    f2[:, 2:, :w - 2] = f[:, :h - 2, 2:]
+    out2 = oc.correlation(f, f2, md, s2)
+    ch = ((2 + md) // s2) * D + ((-2 + md) // s2)
+    assert torch.allclose(out2[:, :h - 2, 2:, ch], (f * f).mean(-1)[:, :h - 2, 2:], atol=1e-6)
+    # top-left pixel, displacement (-4, -4) looks outside the map -> exactly zero
+    assert float(out[0, 0, 0, 0].abs()) == 0.0
+    # linear in each argument
+    a = torch.randn(B, h, w, c, generator=g)
+    assert torch.allclose(oc.correlation(2.0 * f + a, f2, md, s2), 2.0 * out2 + oc.correlation(a, f2, md, s2), atol=1e-5)
+
+
+def test_flownetc_and_vgg16_oracle_structure():
+    from oracle import flownet_c as oc, vgg16 as ov
+    shapes = oc.param_shapes()
+    assert shapes["conv3_1/weights"] == (3, 3, 473, 256) and shapes["conv_redir/weights"] == (1, 1, 256, 32)      # 32 + 21*21 channels
+    assert "conv1/weights" in shapes and shapes["conv1/weights"] == (7, 7, 3, 64)                                # siamese: 3 input channels
+    vs = ov.param_shapes()
+    assert sum(1 for k in vs if k.startswith("conv") and k.endswith("weights")) == 13
+    x = torch.arange(2 * 4 * 6 * 1, dtype=torch.float32).reshape(2, 4, 6, 1)
+    y = ov.max_pool2(x)
+    assert y.shape == (2, 2, 3, 1) and torch.equal(y[0, :, :, 0], torch.tensor([[7., 9., 11.], [19., 21., 23.]]))
+
+
+def test_bench_host_cores_and_reference_contract(monkeypatch):
+    """bench.py's CPU arm: a sane thread count (physical cores within the affinity mask, cgroup quota cap) and the reference-arm JSON keys."""
+    import importlib
+    import json
+    import sys
+    sys.path.insert(0, str(__import__("pathlib").Path(__file__).resolve().parent.parent))
+    bench = importlib.import_module("bench")
+    n = bench._host_cores()
+    assert 1 <= n <= (len(__import__("os").sched_getaffinity(0)) if hasattr(__import__("os"), "sched_getaffinity") else 4096)
+    lines = []
+    monkeypatch.setattr("builtins.print", lambda *a, **k: lines.append(a[0]))
+    monkeypatch.setattr(bench, "cpu_step_rate", lambda sample, steps, warm: (dict(value=2.0, unit=bench.UNIT, cores=n, kind="port", sample="stub"), 1.0))
+    args = type("A", (), dict(steps=3, warmup=1, gpus=2))()
+    bench.run_reference(args, 1, 2)                 # other ranks: no work, no line
+    assert lines == []
+    bench.run_reference(args, 0, 2)
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == bench.UNIT and d["higher_is_better"] is True
+    assert d["e2e"] == {"value": 2.0, "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] == "port" and d["n_gpus"] == 2
