@@ -76,17 +76,24 @@ def layer_flops(B: int, model: str = "flownets"):
     return fl
 
 
-def layer_bytes(B: int, n_param_floats: int):
-    """Algorithmic HBM bytes for the bandwidth-bound launches."""
+def layer_bytes(B: int, n_param_floats: int, lean: bool = False):
+    """Algorithmic HBM bytes for the bandwidth-bound launches.  lean bf16 engine: the heads read the bf16 feature maps
+    (2 B per channel) and move the 20-float Z map / the 64-column bf16 D9 map once each way."""
     by = {}
     px = sum((H >> s) * (W >> s) for s in range(1, 7)) * B
     by["warp_loss"] = px * (44 + 8) - (px - B * (H >> 1) * (W >> 1)) * 12      # recon written for scale 1 only
     by["adam"] = n_param_floats * 28
     for s, c in {6: 1024, 5: 1026, 4: 770, 3: 386, 2: 194, 1: 98}.items():
         n = B * (H >> s) * (W >> s)
-        by[f"head_fwd:pr{s}"] = n * (c * 4 + 8)
-        by[f"head_dgrad:pr{s}"] = n * (c * 4 * (1 if s == 1 else 2) + 8)
-        by[f"head_wgrad:pr{s}"] = n * (c * 4 + 8)
+        if lean:
+            by[f"head_fwd:pr{s}"] = n * (c * 2 + 80)
+            by[f"head_tapsum:pr{s}"] = n * (80 + 8)
+            by[f"head_dpr9:pr{s}"] = n * (8 + 36)
+            by[f"head_wgrad:pr{s}"] = n * (c * 2 + 128)
+        else:
+            by[f"head_fwd:pr{s}"] = n * (c * 4 + 8)
+            by[f"head_dgrad:pr{s}"] = n * (c * 4 * (1 if s == 1 else 2) + 8)
+            by[f"head_wgrad:pr{s}"] = n * (c * 4 + 8)
     return by
 
 
@@ -319,7 +326,7 @@ def run_ours(args, rank, local_rank, world):
         eng.profile = None
         avg = {k: sum(v) / len(v) * (len(v) / psteps) for k, v in per.items()}     # ms per step per tag
         fl = layer_flops(B, args.model)
-        by = layer_bytes(B, eng.arena.n_true)
+        by = layer_bytes(B, eng.arena.n_true, getattr(eng, 'lean', False))
         peaks = load_peaks()
         classes = {}
         for tag, tms in avg.items():

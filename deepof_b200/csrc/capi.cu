@@ -77,13 +77,13 @@ extern "C" int dofb_conv1_fwd(const dofb_conv_geom *g, const float *x, int xp_h,
 // ---- BF16 tensor-core math: operands are bf16 shadows of the NHWC activations (same pitch in elements, multiple of 64) ----
 extern "C" int dofb_conv_fwd_bf16(const dofb_conv_geom *g, const void *x_bf16, int x_ld, const float *w, const float *bias, float *y,
                                   void *y_bf16, int y_ld, int act, void *stream) {
-    DOFB_CHECK_ARG(x_bf16 && w && y, "dofb_conv_fwd_bf16: null tensor");
+    DOFB_CHECK_ARG(x_bf16 && w && (y || y_bf16), "dofb_conv_fwd_bf16: null tensor");
     return tc_conv_fwd(g, nullptr, x_ld, w, bias, y, y_ld, act, as_stream(stream), x_bf16, y_bf16);
 }
 
 extern "C" int dofb_conv_dgrad_bf16(const dofb_conv_geom *g, const void *dy_bf16, int dy_ld, const float *w, const float *bias, float *dx,
                                     void *dx_bf16, int dx_ld, int act, int accumulate, void *stream) {
-    DOFB_CHECK_ARG(dy_bf16 && w && dx, "dofb_conv_dgrad_bf16: null tensor");
+    DOFB_CHECK_ARG(dy_bf16 && w && (dx || dx_bf16), "dofb_conv_dgrad_bf16: null tensor");
     return tc_conv_dgrad(g, nullptr, dy_ld, w, bias, dx, dx_ld, act, accumulate, as_stream(stream), dy_bf16, dx_bf16);
 }
 

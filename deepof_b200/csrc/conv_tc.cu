@@ -538,7 +538,10 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const int r = quad * 32 + lane;                     // row of the tile == TMEM lane
         float4 *stg = reinterpret_cast<float4 *>(stage_f) + warp * (32 * 4);
         const int q = lane & 3, rsub = lane >> 2;           // store phase: this lane's column quad and row within a group of 8
-        const bool out_al = ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0) && (P.out_ld % 4 == 0);
+        // (P.out == nullptr: bf16-only output -- the lean bf16 engine keeps no fp32 copy of activations only tensor-core kernels read)
+        const bool has32 = P.out != nullptr;
+        const bool out_al = ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0) && (P.out_ld % 4 == 0) &&
+                            ((reinterpret_cast<uintptr_t>(P.out16) & 7) == 0);
         const bool elu = P.act == DOFB_ACT_ELU, has16 = P.out16 != nullptr, accum = P.accumulate != 0;
         int lt = 0;
         for (int t = unit0; t < total_tiles; t += unit_step, ++lt) {
@@ -551,7 +554,10 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             const bool row_ok = ix < V.cnt_x && iy < V.cnt_y && nn < P.B;
             // element offset of this thread's output pixel (-1: no pixel); fetched by the storing lanes through shuffles
             const long long my_off = row_ok ? (((long long)nn * P.rh + V.y0 + iy * P.rstep) * P.rw + V.x0 + ix * P.rstep) * P.out_ld : -1;
-            const bool fast = __all_sync(0xffffffffu, row_ok) && out_al && n0 + BN <= P.n_valid;
+            // fast path: every row a real pixel and the valid columns a whole number of 4-column quads (a partial last column block only
+            // costs one predicate per store: the 20-column Z maps of the flow heads take this path)
+            const bool colfull = n0 + BN <= P.n_valid;
+            const bool fast = __all_sync(0xffffffffu, row_ok) && out_al && (colfull || (P.n_valid & 3) == 0);
             const int acc = lt & 1;
             // pixel offsets of the 4 rows this lane stores in every sub-chunk, and (accumulate) the old values of the first one,
             // requested BEFORE waiting for the accumulator so that their DRAM latency hides behind the MMAs still running
@@ -588,19 +594,21 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 __syncwarp();
                 const int col = cbase + q * 4;
                 if (fast) {
+                    const bool col_ok = colfull || col < P.n_valid;
                     float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (P.bias != nullptr) bv = __ldg(reinterpret_cast<const float4 *>(P.bias + col));
+                    if (P.bias != nullptr && col_ok) bv = __ldg(reinterpret_cast<const float4 *>(P.bias + col));
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int rr = i * 8 + rsub;
                         float4 o = stg[rr * 4 + (q ^ ((rr >> 1) & 3))];
+                        if (!col_ok) continue;
                         o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
                         if (elu) {                          // fast ELU: exp via MUFU (absolute error ~1e-7, irrelevant next to TF32/BF16 operands)
                             o.x = o.x > 0.f ? o.x : __expf(o.x) - 1.f; o.y = o.y > 0.f ? o.y : __expf(o.y) - 1.f;
                             o.z = o.z > 0.f ? o.z : __expf(o.z) - 1.f; o.w = o.w > 0.f ? o.w : __expf(o.w) - 1.f;
                         }
                         if (accum) { o.x += olds[i].x; o.y += olds[i].y; o.z += olds[i].z; o.w += olds[i].w; }
-                        *reinterpret_cast<float4 *>(P.out + offs[i] + col) = o;
+                        if (has32) *reinterpret_cast<float4 *>(P.out + offs[i] + col) = o;
                         if (has16) {                        // bf16 shadow for the next tensor-core consumer (same pitch, 8-byte store)
                             __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
                             uint2 pk;
@@ -633,7 +641,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                         float *dst = P.out + off + col;
                         if (vec) {
                             o.x += olds[i].x; o.y += olds[i].y; o.z += olds[i].z; o.w += olds[i].w;
-                            *reinterpret_cast<float4 *>(dst) = o;
+                            if (has32) *reinterpret_cast<float4 *>(dst) = o;
                             if (has16) {
                                 __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
                                 uint2 pk;
@@ -647,7 +655,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                             for (int e = 0; e < 4; ++e)
                                 if (col + e < P.n_valid) {
                                     const float val = accum ? dst[e] + ov[e] : ov[e];
-                                    dst[e] = val;
+                                    if (has32) dst[e] = val;
                                     if (has16) P.out16[off + col + e] = __float2bfloat16_rn(val);
                                 }
                         }
@@ -998,6 +1006,7 @@ static int run_gather(const GatherSpec &G, const TcParams &Pin, cudaStream_t st)
     P.ncb = cpad / kel;
     P.a_coff = G.a_coff; P.a_ld = G.a_ld;
     P.out = G.out; P.out_ld = G.out_ld; P.out16 = G.accumulate ? nullptr : reinterpret_cast<__nv_bfloat16 *>(G.out16);
+    DOFB_CHECK_ARG(G.out != nullptr || (G.out16 != nullptr && !G.accumulate), "tc conv: a bf16-only output needs the bf16 buffer and cannot accumulate");
     P.bias = G.bias; P.n_valid = G.n_valid; P.rh = G.rh; P.rw = G.rw;
     P.act = G.act; P.accumulate = G.accumulate; P.B = G.B;
     // ---- halo tiles: unit-stride gather, every phase at least 16 x 8 pixels, <= 4 taps per phase spanning <= 2 rows / 8 columns ----
@@ -1631,7 +1640,7 @@ static int conv1_prepare(const dofb_conv_geom *g, const void *x, bool bf, int xp
 int tc_conv1_fwd(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *w, const float *bias,
                  float *y, int y_ld, int act, cudaStream_t st, void *y16, const void *x16) {
     const bool bf = x16 != nullptr;                 // bf16 copy of the zero-bordered input -> kind::f16, one K block per filter row
-    DOFB_CHECK_ARG(g && (x || x16) && w && y, "dofb_conv1_fwd: null argument");
+    DOFB_CHECK_ARG(g && (x || x16) && w && (y || y16), "dofb_conv1_fwd: null argument");
     TcParams P;
     memset(&P, 0, sizeof(P));
     P.cnt_y = g->oh; P.cnt_x = g->ow; P.rstep = 1;

@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(256) uppr_fwd_kernel(const float *__restrict__
                 o1 += v.x * wk[2] + v.y * wk[3];
             }
         }
-        *reinterpret_cast<float2 *>(Y + p * y_ld) = make_float2(o0, o1);
+        if (Y != nullptr) *reinterpret_cast<float2 *>(Y + p * y_ld) = make_float2(o0, o1);
         if (Y16 != nullptr) *reinterpret_cast<__nv_bfloat162 *>(Y16 + p * y_ld) = __floats2bfloat162_rn(o0, o1);   // bf16 shadow of the concat slice
     }
 }
@@ -585,7 +585,7 @@ extern "C" int dofb_head_wgrad(const float *x, int x_ld, const float *dpr, int B
 
 extern "C" int dofb_uppr_fwd(const float *pr, int B, int h, int w, const float *wt, const float *bias, float *y, void *y_bf16, int y_ld,
                              void *stream) {
-    DOFB_CHECK_ARG(pr && wt && bias && y && B > 0 && h > 0 && w > 0, "dofb_uppr_fwd: bad argument");
+    DOFB_CHECK_ARG(pr && wt && bias && (y || y_bf16) && B > 0 && h > 0 && w > 0, "dofb_uppr_fwd: bad argument");
     DOFB_CHECK_ARG(y_ld % 2 == 0 && (reinterpret_cast<uintptr_t>(y) & 7u) == 0, "dofb_uppr_fwd: output slice must be 8-byte aligned with an even pitch");
     const long long n = (long long)B * 4 * h * w;
     long long blocks = (n + 255) / 256;

@@ -108,8 +108,22 @@ def bilinear_deconv(shape):
     return w.float()
 
 
+class Buf:
+    """One NHWC activation / gradient buffer: fp32 master (``t``, may be None in the lean bf16 engine) + bf16 shadow (``t16``, may be None)."""
+    __slots__ = ("t", "t16", "shape")
+
+    def __init__(self, shape, device, want32=True, want16=False):
+        self.shape = tuple(shape)
+        self.t = torch.zeros(shape, dtype=torch.float32, device=device) if want32 else None
+        self.t16 = torch.zeros(shape, dtype=torch.bfloat16, device=device) if want16 else None
+
+
 class FlowNetS:
-    """Static-shape FlowNetS engine.  ``math``: 'fp32' (SIMT FFMA, parity grade) or 'tf32' (tcgen05)."""
+    """Static-shape FlowNetS engine.  ``math``: 'fp32' (SIMT FFMA, parity grade), 'tf32' or 'bf16' (tcgen05).
+
+    bf16 math runs the LEAN schedule unless DOFB_LEAN=0: activations that only tensor-core kernels read are kept in bf16
+    alone, the flow heads run on the tensor pipe in tap-in-N form (csrc/heads_tc.cu) and the head input gradients are added on the fly
+    by the ELU' pass of each slab instead of being written to memory."""
 
     def __init__(self, batch: int, height: int = 384, width: int = 512, device="cuda", variant: str = "A",
                  math_mode: str = "fp32", mean=FLYINGCHAIRS_MEAN, hyper=None, seed: int | None = 1, tc_wgrad: bool = False):
@@ -129,8 +143,14 @@ class FlowNetS:
         self.hyper = dict(HYPER)
         if hyper:
             self.hyper.update(hyper)
+        self.lean = self.math == MATH_BF16 and self.ARCH in ("S", "C") and os.environ.get("DOFB_LEAN", "1") != "0"
         self.arena = ParamArena(self.param_shapes(), self.device)
-        self.theta, self.grad = self.arena.new(), self.arena.new()
+        self.theta = self.arena.new()
+        # gradient arena (+ in the lean engine a tail holding the [C,20] tap-in-N weight gradients of the flow heads, zeroed by the same memset)
+        head_c = [shape[2] for name, shape in self.arena.shapes.items() if name.startswith("pr") and name.endswith("weights")]
+        self._grad_store = torch.zeros(self.arena.numel + (sum(_round_up(c * 20, 64) for c in head_c) if self.lean else 0),
+                                       dtype=torch.float32, device=self.device)
+        self.grad = self._grad_store[:self.arena.numel]
         self.m, self.v = self.arena.new(), self.arena.new()
         self.params = self.arena.views(self.theta)
         self.grads = self.arena.views(self.grad)
@@ -206,15 +226,14 @@ class FlowNetS:
         shp = self._buffer_shapes()
         if self.math == MATH_BF16:      # bf16 K blocks are 64 channels: pitches become multiples of 64
             shp = {k: (h, w, _round_up(c, 64)) for k, (h, w, c) in shp.items()}
-        self.act = {k: z(*v) for k, v in shp.items()}
-        self.dact = {k: z(*v) for k, v in shp.items()}
-        # bf16 shadows (same shapes): written by the tensor-core epilogues / elu_bwd / cast, read by the tensor-core consumers
+        bf = self.math == MATH_BF16
+        # lean bf16 engine: only buffers some fp32 kernel still reads keep their fp32 master (FlowNetC: the correlation runs on fp32 maps)
+        keep32 = self.NEED32 if self.lean else set(shp)
+        self.act = {k: Buf((B,) + v, dev, want32=k in keep32, want16=bf) for k, v in shp.items()}
+        self.dact = {k: Buf((B,) + v, dev, want32=True, want16=bf) for k, v in shp.items()}
+        # bf16 copies of the first-layer inputs (VGG: read by the generic kernels; S/C: by the bf16 first-layer kernels)
         self._sh = {}
-        if self.math == MATH_BF16:
-            for dct in (self.act, self.dact):
-                for t in dct.values():
-                    self._sh[id(t)] = torch.zeros(t.shape, dtype=torch.bfloat16, device=dev)
-            # bf16 copies of the first-layer inputs (VGG: read by the generic kernels; S/C: by the bf16 first-layer kernels)
+        if bf:
             self._sh[id(self.x6)] = torch.zeros(self.x6.shape, dtype=torch.bfloat16, device=dev)
             if self.x6b is not None:
                 self._sh[id(self.x6b)] = torch.zeros(self.x6b.shape, dtype=torch.bfloat16, device=dev)
@@ -225,12 +244,29 @@ class FlowNetS:
         self.pyr_tgt = {s: z(*self.hw[s], 3) for s in range(1, self.N_SCALES + 1)}
         self.recon1 = z(*self.hw[1], 3)
         self.loss4 = torch.zeros(self.N_SCALES, 4, dtype=torch.float32, device=dev)
+        if self.lean:
+            # tap-in-N flow heads: Z maps share one flat buffer (forward is sequential), the bf16 im2col of dpr_s has one buffer per scale
+            # (its 64-column rows keep columns 18.. at zero), [C,20] weights / weight gradients per head
+            h1, w1 = self.hw[1]
+            self._z_flat = torch.zeros(B * h1 * w1 * 20, dtype=torch.float32, device=dev)
+            self.head_z = {s: self._z_flat[:B * hh * ww * 20].view(B, hh, ww, 20) for s, (hh, ww) in self.hw.items()}
+            self.head_d9 = {s: torch.zeros(B, hh, ww, 64, dtype=torch.bfloat16, device=dev) for s, (hh, ww) in self.hw.items()}
+            self.head_wz, self.head_dwz, off = {}, {}, self.arena.numel
+            for s in range(1, self.N_SCALES + 1):
+                c = self.arena.shapes[f"pr{s}/weights"][2]
+                self.head_wz[s] = torch.zeros(1, 1, c, 20, dtype=torch.float32, device=dev)
+                self.head_dwz[s] = self._grad_store[off:off + c * 20].view(1, 1, c, 20)
+                off += _round_up(c * 20, 64)
+
+    NEED32 = frozenset()            # activation buffers that keep an fp32 master in the lean engine
 
     def _S(self, t, c0, c):
+        if isinstance(t, Buf):
+            return Slab(t.t, c0, c, t.t16)
         return Slab(t, c0, c, self._sh.get(id(t)))
 
     def _F(self, t):
-        return Slab(t, 0, t.shape[3], self._sh.get(id(t)))
+        return self._S(t, 0, t.shape[3])
 
     def _buffer_shapes(self):
         H, W = self.H, self.W
@@ -293,9 +329,21 @@ class FlowNetS:
             g = conv_geom(B, 2 * hs, 2 * ws, upc, cfeat, 4, 2)     # the conv whose input-gradient is this deconv
             assert g.oh == hs and g.ow == ws and g.pad_t == 1
             tgt = cat[s - 1]
-            self.refine.append(dict(s=s, g=g, up=up, uppr=uppr,
+            self.refine.append(dict(s=s, g=g, up=up, uppr=uppr, skipc=skipc, upc=upc,
                                     up_y=S(a[tgt], skipc, upc), up_dy=S(d[tgt], skipc, upc),
                                     pr_y=S(a[tgt], skipc + upc, 2), pr_dy=S(d[tgt], skipc + upc, 2)))
+        if self.lean:
+            # which conv outputs are the skip part (channel 0..) of a flow head's input feat_s: their ELU' pass adds that head's input gradient
+            for L in self.tower:
+                if L["op"] != "conv":
+                    continue
+                for s, (fx, _fd) in self.feat.items():
+                    if fx.t16 is L["y"].t16 and L["y"].c0 == 0:
+                        L["head_s"] = s
+                # the head of scale 1 no longer writes d concat1 first: the conv reading concat1 becomes the first writer of its gradient
+                if L["dx"] is not None and L["dx"].t is self.dact["concat1"].t:
+                    L["acc"] = False
+            self._head_geom1 = {s: conv_geom(B, self.hw[s][0], self.hw[s][1], self.feat[s][0].c, 20, 1, 1) for s in self.feat}
 
     def _pack_jobs(self):
         """(weight, orientation) of every tensor-core gather-GEMM the step runs: conv fwd / transposed-conv dgrad read the contract-ci copy,
@@ -321,7 +369,9 @@ class FlowNetS:
                 add(w, 1)
             for s in range(1, self.N_SCALES + 1):
                 h, wd = self.hw[s]
-                if self.B * h * wd <= self.TC_HEAD_MAX_PIX:
+                if self.lean:
+                    add(self.head_wz[s], 1)             # tap-in-N form: a 1x1 convolution with the [1,1,C,20] weights
+                elif self.B * h * wd <= self.TC_HEAD_MAX_PIX:
                     add(P[f"pr{s}/weights"], 1)
             self._jobs = ops.make_pack_jobs(entries)
         return self._jobs
@@ -332,7 +382,11 @@ class FlowNetS:
         (N padded to 32); the fine scales are bandwidth-bound and stay on the strip kernel."""
         P = self.params
         h, w = self.hw[s]
-        if self.math != MATH_FP32 and self.B * h * w <= self.TC_HEAD_MAX_PIX:
+        if self.lean:       # tap-in-N: Z = x (1x1) Wz on the tensor pipe (x crosses the chip once), pr = bias + 9-tap sum over the 20-float map
+            z = self.head_z[s]
+            self._k(f"head_fwd:pr{s}", ops.conv_fwd, self._head_geom1[s], x, self.head_wz[s], None, full(z), ACT_NONE, MATH_BF16)
+            self._k(f"head_tapsum:pr{s}", ops.head_tapsum, z, P[f"pr{s}/biases"], self.pr[s])
+        elif self.math != MATH_FP32 and self.B * h * w <= self.TC_HEAD_MAX_PIX:
             g = self._head_geom.get(s)
             if g is None:
                 g = self._head_geom[s] = conv_geom(self.B, h, w, x.c, 2, 3, 1)
@@ -371,14 +425,19 @@ class FlowNetS:
         if L["op"] == "conv":
             w, dw, db = P[L["wname"] + "/weights"], G[L["wname"] + "/weights"], G[L["wname"] + "/biases"]
             # + bias gradient; bf16 math: only the bf16 shadow of the finished gradient is read again (by this layer's wgrad / dgrad)
-            self._k("elu_bwd:" + L["name"], ops.elu_bwd, L["dy"], L["y"], db, mth == MATH_BF16 and mthw == MATH_BF16)
+            if self.lean and "head_s" in L:     # ... and the input gradient of the flow head reading this slab is added on the fly
+                hs = L["head_s"]
+                self._k("elu_bwd:" + L["name"], ops.head_dgrad_elu, self.dpr[hs], P[f"pr{hs}/weights"], 0, L["dy"], L["y"], L["dy"], L["y"].c, db)
+            else:
+                self._k("elu_bwd:" + L["name"], ops.elu_bwd, L["dy"], L["y"], db, mth == MATH_BF16 and mthw == MATH_BF16)
             if L["xpad"] is not None:
                 self._k("conv_wgrad:" + L["name"], ops.conv1_wgrad, L["g"], L["xpad"], self.x6_origin, L["dy"], dw, None,
                         self._sh.get(id(L["xpad"])) if mthw == MATH_BF16 else None)
             else:
                 self._k("conv_wgrad:" + L["name"], ops.conv_wgrad, L["g"], L["x"], L["dy"], dw, None, mthw)
             if L["dx"] is not None:
-                self._k("conv_dgrad:" + L["name"], ops.conv_dgrad, L["g"], L["dy"], w, None, L["dx"], ACT_NONE, L["acc"], mth)
+                dx = Slab(L["dx"].t, L["dx"].c0, L["dx"].c) if self.lean else L["dx"]      # (lean: no bf16 shadow of an unfinished gradient)
+                self._k("conv_dgrad:" + L["name"], ops.conv_dgrad, L["g"], L["dy"], w, None, dx, ACT_NONE, L["acc"], mth)
         elif L["op"] == "pool":
             self._k("pool_bwd:" + L["name"], ops.maxpool2_bwd, L["x"], L["dy"], L["dx"])
         elif L["op"] == "corr":
@@ -393,6 +452,9 @@ class FlowNetS:
             raise ops.DeepOFError(f"expected [B={self.B},{self.H},{self.W},3] NHWC inputs, got {tuple(source.shape)} / {tuple(target.shape)}")
         P, mth = self.params, self.math
         self._preprocess(source, target)
+        if self.lean:
+            sc = range(1, self.N_SCALES + 1)
+            self._k("pack_weights", ops.head_wz_pack, [P[f"pr{s}/weights"] for s in sc], [self.head_wz[s] for s in sc])
         if mth != MATH_FP32:        # every layer's tensor-core weight copies in one launch (no-op while they are current)
             self._k("pack_weights", ops.pack_weights_batch, self._pack_jobs(), mth == MATH_BF16)
         for L in self.tower:
@@ -440,7 +502,50 @@ class FlowNetS:
         if reducer is not None:
             reducer.ready(min(self.arena.offsets[n + "/weights"] for n in names))
 
+    def _head_wgrad_tc(self, s):
+        """dW_pr_s on the tensor pipe: D9 = bf16 im2col of dpr_s (+ bias gradient), dWz = feat_s^T . D9 (1x1 weight-gradient GEMM, feat_s read
+        once), then re-laid out into the canonical [3,3,C,2] gradient."""
+        G = self.grads
+        x, _ = self.feat[s]
+        d9 = self.head_d9[s]
+        self._k(f"head_dpr9:pr{s}", ops.head_dpr9, self.dpr[s], d9, G[f"pr{s}/biases"])
+        self._k(f"head_wgrad:pr{s}", ops.conv_wgrad, self._head_geom1[s], x, Slab(None, 0, 20, d9), self.head_dwz[s], None, MATH_BF16)
+        self._k(f"head_unpack:pr{s}", ops.head_dwz_unpack, [G[f"pr{s}/weights"]], [self.head_dwz[s]])
+
+    def _backward_lean(self, reducer=None):
+        """Backward of the lean bf16 engine: same order as backward(), but no kernel writes a flow head's input gradient: the pass that
+        finishes each channel slab of feat_s (ELU' + bias gradient + bf16 shadow) adds it on the fly (dofb_head_dgrad_elu_bf16)."""
+        P, G, mth = self.params, self.grads, self.math
+        self._k("zero_grad", self._grad_store.zero_)
+        if reducer is not None:
+            reducer.begin()
+        self._head_wgrad_tc(1)
+        self._grad_ready(reducer, "pr1")
+        for R in reversed(self.refine):                      # s = 2,3,4,5,6
+            s, fs = R["s"], R["s"] - 1
+            x, dx = self.feat[s]
+            fy, fd = self.feat[fs]
+            skipc, upc = R["skipc"], R["upc"]
+            # gradient of [upconv | up_pr] outputs inside feat_{s-1}: (deconv_dgrad of the previous iteration, none at scale 1) + head pr_{s-1}
+            slab_d = fd.sub(skipc, upc + 2)
+            self._k("elu_bwd:" + R["up"], ops.head_dgrad_elu, self.dpr[fs], P[f"pr{fs}/weights"], skipc, None if fs == 1 else slab_d,
+                    fy.sub(skipc, upc + 2), slab_d, upc, G[R["up"] + "/biases"])
+            self._k("uppr_bwd:" + R["uppr"], ops.uppr_bwd, self.pr[s], R["pr_dy"], P[R["uppr"] + "/weights"], self.dpr[s],
+                    G[R["uppr"] + "/weights"], G[R["uppr"] + "/biases"])
+            self._k("deconv_wgrad:" + R["up"], ops.conv_wgrad, R["g"], R["up_dy"], x, G[R["up"] + "/weights"], None, mth)
+            self._k("deconv_dgrad:" + R["up"], ops.conv_fwd, R["g"], R["up_dy"], P[R["up"] + "/weights"], None, Slab(dx.t, dx.c0, dx.c),
+                    ACT_NONE, mth)                           # first (plain-store) writer of d feat_s
+            self._head_wgrad_tc(s)
+            self._grad_ready(reducer, f"pr{s}", R["up"], R["uppr"])
+        rev = list(reversed(self.tower))
+        for i, L in enumerate(rev):
+            self._bwd_layer(L)
+            if L["op"] == "conv" and all(M.get("wname") != L["wname"] for M in rev[i + 1:]):
+                self._grad_ready(reducer, L["wname"])
+
     def backward(self, reducer=None):
+        if self.lean:
+            return self._backward_lean(reducer)
         P, G, mth, mthw = self.params, self.grads, self.math, self.math_wgrad
         self._k("zero_grad", self.grad.zero_)
         if reducer is not None:
@@ -516,6 +621,7 @@ def param_shapes_c() -> "OrderedDict[str, tuple]":
 
 class FlowNetC(FlowNetS):
     ARCH = "C"
+    NEED32 = frozenset({"c3a", "c3b", "cat3"})      # the correlation band-GEMMs read / write fp32 maps (TF32)
 
     @staticmethod
     def param_shapes():

@@ -34,21 +34,33 @@ def _req(t: torch.Tensor, name: str) -> None:
 
 @dataclass
 class Slab:
-    """Channels [c0, c0+c) of a contiguous [B,H,W,ld] buffer (optionally with its bf16 shadow of the same shape)."""
-    t: torch.Tensor
+    """Channels [c0, c0+c) of a contiguous [B,H,W,ld] buffer (optionally with its bf16 shadow of the same shape).
+
+    ``t`` may be None for a bf16-only buffer (lean bf16 engine: activations that only tensor-core kernels read keep no fp32 copy);
+    ``ptr`` is then None and a kernel that needs the fp32 data fails loudly instead of reading zeros."""
+    t: torch.Tensor | None
     c0: int
     c: int
     t16: torch.Tensor | None = None
 
     def __post_init__(self):
-        _req(self.t, "Slab")
-        assert self.t.dim() == 4 and 0 <= self.c0 and self.c0 + self.c <= self.t.shape[3]
+        if self.t is not None:
+            _req(self.t, "Slab")
+        elif self.t16 is None:
+            raise DeepOFError("Slab: needs an fp32 buffer or a bf16 buffer")
+        ref = self._ref
+        assert ref.dim() == 4 and 0 <= self.c0 and self.c0 + self.c <= ref.shape[3]
         if self.t16 is not None:
-            assert self.t16.dtype == torch.bfloat16 and self.t16.shape == self.t.shape and self.t16.is_cuda and self.t16.is_contiguous()
+            assert self.t16.dtype == torch.bfloat16 and self.t16.is_cuda and self.t16.is_contiguous()
+            assert self.t is None or self.t16.shape == self.t.shape
 
     @property
-    def ptr(self) -> int:
-        return self.t.data_ptr() + 4 * self.c0
+    def _ref(self) -> torch.Tensor:
+        return self.t if self.t is not None else self.t16
+
+    @property
+    def ptr(self):
+        return None if self.t is None else self.t.data_ptr() + 4 * self.c0
 
     @property
     def ptr16(self):
@@ -56,26 +68,32 @@ class Slab:
 
     @property
     def ld(self) -> int:
-        return self.t.shape[3]
+        return self._ref.shape[3]
 
     @property
     def B(self):
-        return self.t.shape[0]
+        return self._ref.shape[0]
 
     @property
     def h(self):
-        return self.t.shape[1]
+        return self._ref.shape[1]
 
     @property
     def w(self):
-        return self.t.shape[2]
+        return self._ref.shape[2]
 
     @property
     def n_pix(self) -> int:
-        return self.t.shape[0] * self.t.shape[1] * self.t.shape[2]
+        r = self._ref
+        return r.shape[0] * r.shape[1] * r.shape[2]
 
     def dense(self) -> torch.Tensor:
-        return self.t[..., self.c0:self.c0 + self.c]
+        return self._ref[..., self.c0:self.c0 + self.c]
+
+    def sub(self, c0: int, c: int) -> "Slab":
+        """Channels [c0, c0+c) of this slab."""
+        assert 0 <= c0 and c0 + c <= self.c
+        return Slab(self.t, self.c0 + c0, c, self.t16)
 
 
 def full(t: torch.Tensor, c: int | None = None) -> Slab:
@@ -237,6 +255,59 @@ def pack_weights_batch(jobs, bf16: bool):
 
 def invalidate_weight_cache():
     _lib.load().dofb_invalidate_weight_cache()
+
+
+def _need32(s: Slab, who: str):
+    if s.ptr is None:
+        raise DeepOFError(f"{who}: this kernel reads/writes the fp32 buffer, but the slab is bf16-only")
+    return s.ptr
+
+
+def head_wz_pack(ws, wzs):
+    """wz[k] = [C,20] tap-in-N form of the head weights w[k] = [3,3,C,2] (dofb_head_wz_pack), all heads in one launch."""
+    n = len(ws)
+    a = (C.c_void_p * n)(*[t.data_ptr() for t in ws])
+    b = (C.c_void_p * n)(*[t.data_ptr() for t in wzs])
+    cs = (C.c_int * n)(*[int(t.shape[2]) for t in ws])
+    check(_lib.load().dofb_head_wz_pack(n, a, b, cs, _stream()))
+
+
+def head_dwz_unpack(dws, dwzs):
+    """dw[k][tap][c][n] += dwz[k][c][tap*2+n]."""
+    n = len(dws)
+    a = (C.c_void_p * n)(*[t.data_ptr() for t in dws])
+    b = (C.c_void_p * n)(*[t.data_ptr() for t in dwzs])
+    cs = (C.c_int * n)(*[int(t.shape[2]) for t in dws])
+    check(_lib.load().dofb_head_dwz_unpack(n, a, b, cs, _stream()))
+
+
+def head_tapsum(z, bias, pr):
+    _req(z, "z"); _req(pr, "pr")
+    B, h, w, ld = z.shape
+    check(_lib.load().dofb_head_tapsum(z.data_ptr(), ld, B, h, w, bias.data_ptr(), pr.data_ptr(), _stream()))
+
+
+def head_dpr9(dpr, d9, dbias=None):
+    _req(dpr, "dpr")
+    assert d9.dtype == torch.bfloat16 and d9.is_cuda and d9.is_contiguous() and tuple(d9.shape[:3]) == tuple(dpr.shape[:3])
+    B, h, w, _ = dpr.shape
+    check(_lib.load().dofb_head_dpr9(dpr.data_ptr(), B, h, w, d9.data_ptr(), d9.shape[3], dbias.data_ptr() if dbias is not None else None, _stream()))
+
+
+def head_dgrad_elu(dpr, w_head, c0: int, g: Slab | None, y: Slab, out: Slab, c_elu: int, db=None):
+    """Finish the gradient of the channel slab ``out`` (= channels [c0, c0+out.c) of the head's input feat_s): adds the head's input
+    gradient to ``g`` (or to zero), applies ELU' (from the bf16 ELU outputs ``y``) on the first c_elu channels -> bf16 shadow of ``out`` and
+    bias gradient ``db``; the remaining (linear) channels are written in fp32 to ``out`` (dofb_head_dgrad_elu_bf16)."""
+    _req(dpr, "dpr"); _req(w_head, "w_head")
+    B, h, w, _ = dpr.shape
+    c = out.c
+    assert (g is None or g.c == c) and y.c == c and out.n_pix == B * h * w
+    lin = c_elu < c
+    check(_lib.load().dofb_head_dgrad_elu_bf16(
+        dpr.data_ptr(), B, h, w, w_head.data_ptr(), int(w_head.shape[2]), int(c0), c, int(c_elu),
+        _need32(g, "head_dgrad_elu") if g is not None else None, g.ld if g is not None else 0,
+        _need16(y, "head_dgrad_elu") if c_elu else None, y.ld, _need16(out, "head_dgrad_elu") if c_elu else None, out.ld,
+        _need32(out, "head_dgrad_elu") if lin else None, out.ld, db.data_ptr() if db is not None else None, _stream()))
 
 
 def head_fwd(x: Slab, w, b, pr):

@@ -194,10 +194,30 @@ int dofb_head_wgrad(const float *x, int x_ld, const float *dpr, int B, int h, in
                     float *dwt, float *dbias, void *stream);
 /* up_pr = conv2d_transpose 4x4/2 (2 -> 2) linear, :66,77,88,99,110.  wt [4,4,2,2] = [kh,kw,co,ci] */
 int dofb_uppr_fwd(const float *pr, int B, int h, int w, const float *wt, const float *bias,
-                  float *y /* [B,2h,2w,y_ld] slice */, void *y_bf16 /* optional bf16 shadow of the same slice, may be NULL */, int y_ld,
+                  float *y /* [B,2h,2w,y_ld] slice; may be NULL when y_bf16 is given */, void *y_bf16 /* optional bf16 shadow of the same slice, may be NULL */, int y_ld,
                   void *stream);
 int dofb_uppr_bwd(const float *pr, const float *dy, int dy_ld, int B, int h, int w, const float *wt,
                   float *dpr /* += */, float *dwt /* += */, float *dbias /* += */, void *stream);
+
+/* ---- flow heads of the lean bf16 engine (tap-in-N form: see csrc/heads_tc.cu) --------------------------------------------
+ * pr_s = conv3x3(feat_s -> 2) (flyingChairsWrapFlow.py:58,69,80,91,102,113) without any fp32 copy of feat_s:
+ *   forward : wz = dofb_head_wz_pack(w)  ->  Z = dofb_conv_fwd_bf16(1x1, ci = C, co = 20, x = bf16 feat)  ->  pr = dofb_head_tapsum(Z)
+ *   wgrad   : D9 = dofb_head_dpr9(dpr)   ->  dWz = dofb_conv_wgrad_bf16(1x1, ci = C, co = 20, dy = D9)  ->  dofb_head_dwz_unpack
+ *   dgrad   : fused into the pass that finishes the gradient of each channel slab of feat_s (dofb_head_dgrad_elu_bf16). */
+/* wz[k][c*20 + tap*2 + n] = w[k][tap][c][n] (columns 18, 19 zero): the [1,1,C,20] weights of the 1x1 form; up to 8 heads per call */
+int dofb_head_wz_pack(int n_heads, const float *const *w /* [3,3,C,2] each */, float *const *wz /* [C,20] each */, const int *C, void *stream);
+/* dw[k][tap][c][n] += dwz[k][c*20 + tap*2 + n] */
+int dofb_head_dwz_unpack(int n_heads, float *const *dw, const float *const *dwz, const int *C, void *stream);
+/* pr[b,y,x,n] = bias[n] + sum_{kh,kw} Z[b, y+kh-1, x+kw-1, (kh*3+kw)*2 + n]  (zero outside the map) */
+int dofb_head_tapsum(const float *z, int z_ld, int B, int h, int w, const float *bias, float *pr /* [B,h,w,2] */, void *stream);
+/* D9[b,y,x,(kh*3+kw)*2 + n] = bf16(dpr[b, y-kh+1, x-kw+1, n]) (zero outside; only columns 0..17 are written); dbias[n] += sum dpr[...,n] */
+int dofb_head_dpr9(const float *dpr, int B, int h, int w, void *d9_bf16, int d9_ld, float *dbias /* may be NULL */, void *stream);
+/* One channel slab [c0, c0+c) of feat_s: v = (g ? g : 0) + head_input_gradient(dpr, w)[c0..];
+ *   channels [0, c_elu): out_bf16 = bf16(v * ELU'(y_bf16)), db[ch] += column sums (conv / transposed-conv outputs);
+ *   channels [c_elu, c): gout = v (fp32, linear: the 2-channel up_pr slice).  g / y / out / gout point at the slab start. */
+int dofb_head_dgrad_elu_bf16(const float *dpr, int B, int h, int w, const float *wt /* [3,3,c_total,2] */, int c_total, int c0, int c,
+                             int c_elu, const float *g /* may be NULL */, int g_ld, const void *y_bf16, int y_ld, void *out_bf16,
+                             int out_ld, float *gout, int gout_ld, float *db /* may be NULL */, void *stream);
 
 /* ---- optimiser ------------------------------------------------------------ */
 /* Replaces: tf.train.AdamOptimizer(lr).minimize (flyingChairsTrain.py:124), 52 ApplyAdam

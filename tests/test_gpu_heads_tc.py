@@ -1,0 +1,185 @@
+"""Flow heads of the lean bf16 engine (csrc/heads_tc.cu) against plain PyTorch fp32/fp64 references of the same ops.
+
+pr_s = slim.conv2d(feat_s, 2, [3,3], activation_fn=None) (flyingChairsWrapFlow.py:58,69,80,91,102,113) and its TF-autodiff gradients,
+computed in tap-in-N form on the tensor pipe.  Operands are rounded to bf16 exactly as the kernels see them, so the tolerances only
+cover fp32 summation order (1e-4 relative) -- except where a bf16 OUTPUT is compared (2^-8 relative)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _no_weight_cache():
+    from deepof_b200 import _lib
+    _lib.load().dofb_enable_weight_cache(0)
+    yield
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+CASES = [  # B, h, w, C, pitch
+    (2, 24, 32, 98, 128),       # pr1-like
+    (1, 12, 16, 194, 256),      # pr2-like
+    (2, 6, 8, 386, 448),
+    (1, 3, 4, 1026, 1088),      # pr5-like, ragged tiles
+    (3, 10, 14, 64, 64),
+]
+
+
+def _feat(B, h, w, C, ld, gen):
+    x = torch.zeros(B, h, w, ld)
+    x[..., :C] = _bf(torch.randn(B, h, w, C, generator=gen))
+    return x
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_head_forward_tap_in_n(case):
+    from deepof_b200 import ops
+    B, h, w, C, ld = case
+    gen = torch.Generator().manual_seed(sum(case))
+    x = _feat(B, h, w, C, ld, gen)
+    wt = _bf(torch.randn(3, 3, C, 2, generator=gen) / math.sqrt(9 * C))
+    bias = torch.randn(2, generator=gen) * 0.1
+    want = F.conv2d(x[..., :C].permute(0, 3, 1, 2).double(), wt.permute(3, 2, 0, 1).double(), bias.double(), padding=1).permute(0, 2, 3, 1)
+    x16 = x.to(torch.bfloat16).cuda()
+    wz = torch.zeros(1, 1, C, 20, device="cuda")
+    ops.head_wz_pack([wt.cuda()], [wz])
+    assert torch.equal(wz[0, 0, :, :18].cpu().view(C, 9, 2), wt.permute(2, 0, 1, 3).reshape(C, 9, 2))
+    assert float(wz[..., 18:].abs().max()) == 0.0
+    z = torch.full((B, h, w, 20), float("nan"), device="cuda")
+    ops.conv_fwd(ops.conv_geom(B, h, w, C, 20, 1, 1), ops.Slab(None, 0, C, x16), wz, None, ops.full(z), ops.ACT_NONE, ops.MATH_BF16)
+    pr = torch.zeros(B, h, w, 2, device="cuda")
+    ops.head_tapsum(z, bias.cuda(), pr)
+    torch.cuda.synchronize()
+    assert torch.isfinite(z).all()
+    assert rel(pr, want) < 1e-4
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_head_weight_gradient_tap_in_n(case):
+    from deepof_b200 import ops
+    B, h, w, C, ld = case
+    gen = torch.Generator().manual_seed(7 + sum(case))
+    x = _feat(B, h, w, C, ld, gen)
+    dpr = torch.randn(B, h, w, 2, generator=gen)
+    # dW[kh,kw,c,n] = sum_p x[p + off][c] * dpr[p][n]; the tensor-core operand of dpr is its bf16 rounding
+    xd = x[..., :C].permute(0, 3, 1, 2).double().requires_grad_(False)
+    wd = torch.zeros(2, C, 3, 3, dtype=torch.float64, requires_grad=True)
+    out = F.conv2d(xd, wd, None, padding=1)
+    out.backward(_bf(dpr).permute(0, 3, 1, 2).double())
+    want_dw = wd.grad.permute(2, 3, 1, 0)                      # [3,3,C,2]
+    want_db = dpr.double().sum(dim=(0, 1, 2))
+    d9 = torch.zeros(B, h, w, 64, dtype=torch.bfloat16, device="cuda")
+    db = torch.zeros(2, device="cuda")
+    ops.head_dpr9(dpr.cuda(), d9, db)
+    assert float(d9[..., 18:].float().abs().max()) == 0.0
+    dwz = torch.zeros(1, 1, C, 20, device="cuda")
+    ops.conv_wgrad(ops.conv_geom(B, h, w, C, 20, 1, 1), ops.Slab(None, 0, C, x.to(torch.bfloat16).cuda()), ops.Slab(None, 0, 20, d9), dwz,
+                   None, ops.MATH_BF16)
+    dw = torch.zeros(3, 3, C, 2, device="cuda")
+    ops.head_dwz_unpack([dw], [dwz])
+    torch.cuda.synchronize()
+    assert rel(dw, want_dw) < 1e-4
+    assert rel(db, want_db) < 1e-4
+    assert float(dwz[..., 18:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("case", [(2, 24, 32, 98, 128, 64, 34, 32, True), (2, 24, 32, 98, 128, 0, 64, 64, True),
+                                  (1, 12, 16, 194, 256, 128, 66, 64, False), (1, 6, 8, 1026, 1088, 0, 512, 512, True),
+                                  (2, 5, 37, 98, 128, 64, 34, 32, False)])
+def test_head_input_gradient_fused_with_elu(case):
+    """(g + dX_head)[slab] * ELU'(y) -> bf16, bias gradient = column sums, linear tail in fp32."""
+    from deepof_b200 import ops
+    B, h, w, C, ld, c0, c, c_elu, with_g = case
+    gen = torch.Generator().manual_seed(11 + sum(case[:8]))
+    wt = torch.randn(3, 3, C, 2, generator=gen) / math.sqrt(18)
+    dpr = torch.randn(B, h, w, 2, generator=gen)
+    g = torch.zeros(B, h, w, ld)
+    g[..., :C] = torch.randn(B, h, w, C, generator=gen)
+    y = torch.zeros(B, h, w, ld)
+    y[..., :C] = _bf(torch.randn(B, h, w, C, generator=gen).clamp(min=-0.95))
+    # reference: transposed 3x3 stencil = gradient of the forward conv
+    xd = torch.zeros(B, C, h, w, dtype=torch.float64, requires_grad=True)
+    F.conv2d(xd, wt.permute(3, 2, 0, 1).double(), None, padding=1).backward(dpr.permute(0, 3, 1, 2).double())
+    head = xd.grad.permute(0, 2, 3, 1)                          # [B,h,w,C]
+    v = head[..., c0:c0 + c] + (g[..., c0:c0 + c].double() if with_g else 0.0)
+    ys = y[..., c0:c0 + c_elu].double()
+    v_elu = v[..., :c_elu] * torch.where(ys > 0, torch.ones_like(ys), ys + 1.0)
+    gd = g.clone().cuda()
+    g16 = torch.zeros(B, h, w, ld, dtype=torch.bfloat16, device="cuda")
+    y16 = y.to(torch.bfloat16).cuda()
+    db = torch.zeros(max(c_elu, 1), device="cuda")
+    ops.head_dgrad_elu(dpr.cuda(), wt.cuda(), c0, ops.Slab(gd, c0, c) if with_g else None, ops.Slab(None, c0, c, y16),
+                       ops.Slab(gd, c0, c, g16), c_elu, db)
+    torch.cuda.synchronize()
+    got16 = g16[..., c0:c0 + c_elu].float()
+    assert rel(got16, v_elu) < 2 ** -7
+    assert rel(db[:c_elu], v_elu.sum(dim=(0, 1, 2))) < 2e-4
+    if c_elu < c:
+        assert rel(gd[..., c0 + c_elu:c0 + c], v[..., c_elu:]) < 1e-5
+    # nothing outside the slab is touched
+    untouched = torch.ones(ld, dtype=torch.bool)
+    untouched[c0 + c_elu:c0 + c] = False
+    assert torch.equal(gd.cpu()[..., untouched], g[..., untouched])
+    outside = torch.ones(ld, dtype=torch.bool)
+    outside[c0:c0 + c_elu] = False
+    assert float(g16[..., outside.cuda()].float().abs().max()) == 0.0
+
+
+def test_bf16_only_conv_output_matches_shadow():
+    """dofb_conv_fwd_bf16 with y = NULL writes only the bf16 buffer, bit-identical to the shadow of the fp32 + bf16 form."""
+    from deepof_b200 import ops
+    B, H, W, ci, co = 2, 12, 16, 128, 128
+    gen = torch.Generator().manual_seed(5)
+    x16 = torch.randn(B, H, W, ci, generator=gen).to(torch.bfloat16).cuda()
+    wt = (torch.randn(3, 3, ci, co, generator=gen) / math.sqrt(9 * ci)).cuda()
+    b = (torch.randn(co, generator=gen) * 0.1).cuda()
+    geom = ops.conv_geom(B, H, W, ci, co, 3, 1)
+    y = torch.zeros(B, H, W, co, device="cuda")
+    ya, yb = torch.zeros(B, H, W, co, dtype=torch.bfloat16, device="cuda"), torch.zeros(B, H, W, co, dtype=torch.bfloat16, device="cuda")
+    ops.conv_fwd(geom, ops.Slab(None, 0, ci, x16), wt, b, ops.Slab(y, 0, co, ya), ops.ACT_ELU, ops.MATH_BF16)
+    ops.conv_fwd(geom, ops.Slab(None, 0, ci, x16), wt, b, ops.Slab(None, 0, co, yb), ops.ACT_ELU, ops.MATH_BF16)
+    torch.cuda.synchronize()
+    assert torch.equal(ya, yb)
+    assert float(y.abs().max()) > 0
+
+
+@pytest.mark.parametrize("model", ["flownets", "flownetc"])
+def test_lean_engine_matches_classic_bf16_engine(model, monkeypatch):
+    """The lean schedule (bf16-only activations, tap-in-N heads, fused head input gradient) computes the same step as the classic bf16
+    schedule: losses, flows and every parameter gradient agree to bf16-rounding level."""
+    from deepof_b200.flownet import FlowNetS, FlowNetC
+    from deepof_b200.synth import make_pairs
+    cls = FlowNetS if model == "flownets" else FlowNetC
+    B, H, W = 2, 128, 192
+    src, tgt, _ = make_pairs(B, H, W, seed=21)
+    monkeypatch.setenv("DOFB_LEAN", "0")
+    e0 = cls(B, H, W, math_mode="bf16", seed=1, tc_wgrad=True)
+    monkeypatch.setenv("DOFB_LEAN", "1")
+    e1 = cls(B, H, W, math_mode="bf16", seed=1, tc_wgrad=True)
+    assert not e0.lean and e1.lean
+    for e in (e0, e1):
+        e.forward(src.cuda(), tgt.cuda(), with_grad=True)
+        e.backward()
+    torch.cuda.synchronize()
+    assert rel(e1.loss4, e0.loss4) < 2e-3
+    for s in range(1, 7):
+        assert float((e1.pr[s] - e0.pr[s]).abs().max()) < 2e-2 * max(1.0, float(e0.pr[s].abs().max()))
+    worst = {}
+    for name in e0.grads:
+        a, b = e1.grads[name].double().flatten(), e0.grads[name].double().flatten()
+        cos = float(torch.dot(a, b) / (a.norm() * b.norm() + 1e-30))
+        worst[name] = cos
+        assert cos > 0.98, (name, cos)
+        assert abs(float(a.norm() / (b.norm() + 1e-30)) - 1.0) < 0.1, name
