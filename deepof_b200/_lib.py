@@ -56,6 +56,7 @@ SIGNATURES = {
     "dofb_conv1_fwd": (_I, [_G, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P]),
     "dofb_conv_fwd_bf16": (_I, [_G, _P, _I, _P, _P, _P, _P, _I, _I, _P]),
     "dofb_conv_dgrad_bf16": (_I, [_G, _P, _I, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "dofb_conv_dgrad_gate_bf16": (_I, [_G, _P, _I, _P, _P, _P, _I, _I, _P, _I, _P, _P]),
     "dofb_conv_wgrad_bf16": (_I, [_G, _P, _I, _P, _I, _P, _P]),
     "dofb_cast_bf16": (_I, [_P, _I, _P, _I, _LL, _I, _P]),
     "dofb_conv1_wgrad": (_I, [_G, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P]),

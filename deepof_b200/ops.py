@@ -207,6 +207,16 @@ def conv_dgrad(g: ConvGeom, dy: Slab, w, bias, dx: Slab, act=ACT_NONE, accumulat
                               dx.ptr, dx.ld, act, int(accumulate), math, _stream()))
 
 
+def conv_dgrad_gate(g: ConvGeom, dy: Slab, w, dx: Slab, y: Slab, gate_cols: int, accumulate=False, db=None):
+    """Input gradient whose epilogue finishes the slab: bf16(dgrad (+ dx) * ELU'(y)) into dx's bf16 buffer for the first ``gate_cols``
+    channels (+ bias gradient ``db``), plain fp32 for the rest (dofb_conv_dgrad_gate_bf16)."""
+    _req(w, "w")
+    assert y.ld == dx.ld and y.c == dx.c and y.n_pix == dx.n_pix
+    check(_lib.load().dofb_conv_dgrad_gate_bf16(C.byref(g), _need16(dy, "conv_dgrad_gate"), dy.ld, w.data_ptr(), dx.ptr, _need16(dx, "conv_dgrad_gate"),
+                                                dx.ld, int(accumulate), _need16(y, "conv_dgrad_gate"), int(gate_cols),
+                                                db.data_ptr() if db is not None else None, _stream()))
+
+
 def conv_wgrad(g: ConvGeom, x: Slab, dy: Slab, dw, db, math=MATH_FP32, bias_on_large=False):
     _req(dw, "dw")
     lib = _lib.load()

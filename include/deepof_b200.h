@@ -165,6 +165,13 @@ int dofb_conv_fwd_bf16(const dofb_conv_geom *g, const void *x_bf16, int x_ld, co
 int dofb_conv_dgrad_bf16(const dofb_conv_geom *g, const void *dy_bf16, int dy_ld, const float *w, const float *bias, float *dx,
                          void *dx_bf16 /* written only when !accumulate; may be NULL */, int dx_ld, int act, int accumulate, void *stream);
 int dofb_conv_wgrad_bf16(const dofb_conv_geom *g, const void *x_bf16, int x_ld, const void *dy_bf16, int dy_ld, float *dw, void *stream);
+/* Input gradient whose epilogue FINISHES the gradient of the slab (Conv2DBackpropInput + AddN + EluGrad + BiasAddGrad of the layer
+ * that produced the slab, in one kernel):  v = conv_input_gradient(dy, w) (+ dx when accumulate);
+ *   channels [0, gate_cols): dx_bf16 = bf16(v * ELU'(y_bf16)) -- bf16 ONLY, the fp32 buffer is not written -- and db[ch] += column sums;
+ *   channels [gate_cols, ci): dx = v (fp32, linear).
+ * y_bf16 / dx / dx_bf16 share the geometry and pitch dx_ld; dx may be NULL when !accumulate and gate_cols == ci; db may be NULL. */
+int dofb_conv_dgrad_gate_bf16(const dofb_conv_geom *g, const void *dy_bf16, int dy_ld, const float *w, float *dx, void *dx_bf16, int dx_ld,
+                              int accumulate, const void *y_bf16, int gate_cols, float *db, void *stream);
 /* dst_bf16[p, 0..c) = bf16(src[p, 0..c)) for producers that have no fused shadow output (flow heads' up_pr, correlation, pooling) */
 /* First layer in bf16: x_bf16 = bf16 copy (dofb_cast_bf16, pitch 8) of the zero-bordered input of dofb_conv1_fwd; one 128-byte K block
  * per filter row (half the L2->shared traffic of the TF32 form).  Same geometry arguments and semantics as dofb_conv1_fwd / _wgrad. */

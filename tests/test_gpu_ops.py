@@ -137,6 +137,21 @@ def test_warp_loss_golden(golden_dir):
         assert rel(dflow, torch.from_numpy(z[f"dflow_{variant}"])) < 2e-5
 
 
+@pytest.mark.parametrize("name", ["s6_6x8", "s4_24x32", "s3_48x64"])
+def test_warp_matches_reference_check_loss_fixture(golden_dir, name):
+    """The CUDA warp against the fixture produced by the REFERENCE's own NumPy warp (/root/reference/check_loss.py:61-135, executed by
+    tests/golden/make_check_loss_golden.py): interior pixels, where its flat-index clamp equals the TF graph's per-axis clamp."""
+    z = np.load(golden_dir / "check_loss_warp.npz")
+    flow = torch.from_numpy(z[name + "_flow"]).float()[None]
+    tgt = torch.from_numpy(z[name + "_target"]).float()[None]
+    want = z[name + "_recon"].reshape(tgt.shape[1:])
+    for variant in ("A", "B"):
+        _, recon, _ = _run_warp_loss(flow, tgt.flip(2), tgt, 1.0, variant)
+        assert np.abs(recon[0].numpy().astype(np.float64) - want).max() < 2e-6
+        _, recon, _ = _run_warp_loss(flow / 2.5, tgt.flip(2), tgt, 2.5, variant)       # flow_scale multiplies first (:783)
+        assert np.abs(recon[0].numpy().astype(np.float64) - want).max() < 2e-5
+
+
 def test_warp_known_answers_on_device():
     B, h, w = 2, 6, 8
     g = torch.Generator().manual_seed(0)
