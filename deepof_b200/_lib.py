@@ -56,7 +56,6 @@ SIGNATURES = {
     "dofb_conv1_fwd": (_I, [_G, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P]),
     "dofb_conv_fwd_bf16": (_I, [_G, _P, _I, _P, _P, _P, _P, _I, _I, _P]),
     "dofb_conv_dgrad_bf16": (_I, [_G, _P, _I, _P, _P, _P, _P, _I, _I, _I, _P]),
-    "dofb_conv_dgrad_gate_bf16": (_I, [_G, _P, _I, _P, _P, _P, _I, _I, _P, _I, _P, _P]),
     "dofb_conv_wgrad_bf16": (_I, [_G, _P, _I, _P, _I, _P, _P]),
     "dofb_cast_bf16": (_I, [_P, _I, _P, _I, _LL, _I, _P]),
     "dofb_conv1_wgrad": (_I, [_G, _P, _I, _I, _I, _I, _P, _I, _P, _P, _P]),
@@ -85,7 +84,7 @@ SIGNATURES = {
     "dofb_head_dwz_unpack": (_I, [_I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int), _P]),
     "dofb_head_tapsum": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "dofb_head_dpr9": (_I, [_P, _I, _I, _I, _P, _I, _P, _P]),
-    "dofb_head_dgrad_elu_bf16": (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _I, _P, _P]),
+    "dofb_head_dgrad_elu_bf16": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _I, _P, _P]),
     "dofb_adam": (_I, [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _P]),
     "dofb_epe_sum": (_I, [_P, _P, _LL, _P, _P]),
     "dofb_corr_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P]),

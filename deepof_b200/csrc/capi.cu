@@ -14,8 +14,7 @@ int launch_colsum(const float *X, int ld, long long n_pix, int c, float *out, cu
 int tc_conv_fwd(const dofb_conv_geom *g, const float *x, int x_ld, const float *w, const float *bias, float *y, int y_ld,
                 int act, cudaStream_t st, const void *x16 = nullptr, void *y16 = nullptr);
 int tc_conv_dgrad(const dofb_conv_geom *g, const float *dy, int dy_ld, const float *w, const float *bias, float *dx, int dx_ld,
-                  int act, int accumulate, cudaStream_t st, const void *dy16 = nullptr, void *dx16 = nullptr,
-                  const void *gate16 = nullptr, int gate_cols = 0, float *db = nullptr);
+                  int act, int accumulate, cudaStream_t st, const void *dy16 = nullptr, void *dx16 = nullptr);
 int tc_conv_wgrad(const dofb_conv_geom *g, const float *x, int x_ld, const float *dy, int dy_ld, float *dw, cudaStream_t st,
                   const void *x16 = nullptr, const void *dy16 = nullptr);
 void invalidate_weight_cache();
@@ -86,13 +85,6 @@ extern "C" int dofb_conv_dgrad_bf16(const dofb_conv_geom *g, const void *dy_bf16
                                     void *dx_bf16, int dx_ld, int act, int accumulate, void *stream) {
     DOFB_CHECK_ARG(dy_bf16 && w && (dx || dx_bf16), "dofb_conv_dgrad_bf16: null tensor");
     return tc_conv_dgrad(g, nullptr, dy_ld, w, bias, dx, dx_ld, act, accumulate, as_stream(stream), dy_bf16, dx_bf16);
-}
-
-extern "C" int dofb_conv_dgrad_gate_bf16(const dofb_conv_geom *g, const void *dy_bf16, int dy_ld, const float *w, float *dx, void *dx_bf16,
-                                         int dx_ld, int accumulate, const void *y_bf16, int gate_cols, float *db, void *stream) {
-    DOFB_CHECK_ARG(dy_bf16 && w && dx_bf16 && y_bf16 && g, "dofb_conv_dgrad_gate_bf16: null tensor");
-    DOFB_CHECK_ARG(!accumulate || dx, "dofb_conv_dgrad_gate_bf16: accumulate needs the fp32 gradient buffer");
-    return tc_conv_dgrad(g, nullptr, dy_ld, w, nullptr, dx, dx_ld, DOFB_ACT_NONE, accumulate, as_stream(stream), dy_bf16, dx_bf16, y_bf16, gate_cols, db);
 }
 
 extern "C" int dofb_conv_wgrad_bf16(const dofb_conv_geom *g, const void *x_bf16, int x_ld, const void *dy_bf16, int dy_ld, float *dw,

@@ -280,8 +280,7 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
 constexpr int TC_BM = 128, TC_BK = 32, TC_THREADS = 192, TC_MAX_TAPS = 49;
 // gather-GEMM kernel: 8 epilogue warps (two per TMEM lane quadrant, alternating 16-column sub-chunks) + TMA producer + MMA issuer.
 // With 4 epilogue warps (one per scheduler, no latency hiding) every layer of the net was bound by the epilogue, not by the MMAs.
-constexpr int TCG_EPI_WARPS = 8, TCG_THREADS = (TCG_EPI_WARPS + 2) * 32;
-constexpr int TCG_STG_BYTES = TCG_EPI_WARPS * 32 * 16 * 4 + TCG_EPI_WARPS * 8 * 4 * 16;   // transpose tiles + bias-gradient partials
+constexpr int TCG_EPI_WARPS = 8, TCG_THREADS = (TCG_EPI_WARPS + 2) * 32, TCG_STG_BYTES = TCG_EPI_WARPS * 32 * 16 * 4;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;   // 16 KB
 constexpr int TC_HALO_ROWS = 18;                // halo box rows: 16 tile rows + a vertical tap span of up to 2
 constexpr int TC_HALO_TAPS = 4;                 // taps per phase the halo path handles (weights of one channel block share the slot)
@@ -308,10 +307,6 @@ struct TcParams {
     int ntaps;
     int parity;                  // 0: rank-4 unit-stride map, 1: rank-5 stride-2 map
     int act, accumulate;
-    // GATE epilogue (finishing a gradient slab in the producing GEMM): columns [0, gate_cols) become bf16(value * ELU'(gate16)) in out16
-    // ONLY (no fp32 store), their column sums go to db (BiasAddGrad); columns >= gate_cols stay linear fp32 stores into out.
-    // gate16 has the geometry and pitch of out / out16.
-    const __nv_bfloat16 *gate16; int gate_cols; float *db;
     // several output sub-grids ("phases" of a strided input gradient / transposed conv) in ONE launch: phase q owns the global M tiles
     // [m_begin, m_begin + m_tiles) and the taps [tap0, tap0 + ntaps); nphase <= 1: the scalar fields above describe the only phase
     int nphase;
@@ -378,8 +373,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     float *stage_f = reinterpret_cast<float *>(smem + RING_BYTES);                           // [8 warps][32 rows][16 floats] epilogue transpose tiles
-    float4 *db_sm = reinterpret_cast<float4 *>(stage_f + TCG_EPI_WARPS * 32 * 16);          // [8 warps][8 sub-chunk slots][4 column quads] bias-gradient partials
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(db_sm + TCG_EPI_WARPS * 8 * 4);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(stage_f + TCG_EPI_WARPS * 32 * 16);
     uint64_t *empty_bar = full_bar + STAGES;
     uint64_t *acc_full = empty_bar + STAGES;       // [2] MMA -> epilogue
     uint64_t *acc_empty = acc_full + 2;            // [2] epilogue -> MMA (the 8 epilogue warps arrive; 16 for a CTA pair)
@@ -547,36 +541,11 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         // (P.out == nullptr: bf16-only output -- the lean bf16 engine keeps no fp32 copy of activations only tensor-core kernels read)
         const bool has32 = P.out != nullptr;
         const bool out_al = ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0) && (P.out_ld % 4 == 0) &&
-                            ((reinterpret_cast<uintptr_t>(P.out16) & 7) == 0) && ((reinterpret_cast<uintptr_t>(P.gate16) & 7) == 0);
-        const bool elu = P.act == DOFB_ACT_ELU, accum = P.accumulate != 0;
-        const bool gate = P.gate16 != nullptr;
-        const bool has16 = P.out16 != nullptr && !gate;     // plain bf16 shadow (gate mode writes out16 itself, gated columns only)
-        const bool want_db = gate && P.db != nullptr;
-        float4 *dbw = db_sm + warp * 32;                    // [slot j >> 1][q]
-        if (want_db) dbw[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-        __syncwarp();
-        // bias-gradient partials are kept per warp in shared memory while the CTA stays on one column tile (tiles walk M fastest) and
-        // flushed with one vector atomic per column quad when the column tile changes / at the end
-        auto flush_db = [&](int nt_done) {
-            if (rsub == 0) {
-#pragma unroll 1
-                for (int sl = 0; sl < (NSUB + 1) / 2; ++sl) {
-                    const int col = nt_done * BN + (2 * sl + half) * 16 + q * 4;
-                    if (2 * sl + half < NSUB && col < P.gate_cols) {
-                        const float4 v = dbw[sl * 4 + q];
-                        if ((reinterpret_cast<uintptr_t>(P.db + col) & 15) == 0) atomicAdd(reinterpret_cast<float4 *>(P.db + col), v);
-                        else { atomicAdd(P.db + col, v.x); atomicAdd(P.db + col + 1, v.y); atomicAdd(P.db + col + 2, v.z); atomicAdd(P.db + col + 3, v.w); }
-                    }
-                    dbw[sl * 4 + q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-            __syncwarp();
-        };
-        int lt = 0, nt_prev = -1;
+                            ((reinterpret_cast<uintptr_t>(P.out16) & 7) == 0);
+        const bool elu = P.act == DOFB_ACT_ELU, has16 = P.out16 != nullptr, accum = P.accumulate != 0;
+        int lt = 0;
         for (int t = unit0; t < total_tiles; t += unit_step, ++lt) {
             const int nt = t / m_units;
-            if (want_db && nt != nt_prev && nt_prev >= 0) flush_db(nt_prev);
-            nt_prev = nt;
             const TileView V = tile_view(P, (t % m_units) * (CG2 ? 2 : 1) + (int)rank);
             const int mt = V.mt;
             const int tx = mt % V.tiles_x, ty = (mt / V.tiles_x) % V.tiles_y, tn = mt / (V.tiles_x * V.tiles_y);
@@ -586,26 +555,21 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             // element offset of this thread's output pixel (-1: no pixel); fetched by the storing lanes through shuffles
             const long long my_off = row_ok ? (((long long)nn * P.rh + V.y0 + iy * P.rstep) * P.rw + V.x0 + ix * P.rstep) * P.out_ld : -1;
             // fast path: every row a real pixel and the valid columns a whole number of 4-column quads (a partial last column block only
-            // costs one predicate per store: the 20-column Z maps of the flow heads take this path); in gate mode the quads of the gated
-            // columns are whole and the (<= 3 column) linear tail is handled by scalar code
+            // costs one predicate per store: the 20-column Z maps of the flow heads take this path)
             const bool colfull = n0 + BN <= P.n_valid;
-            const bool fast = __all_sync(0xffffffffu, row_ok) && out_al && (colfull || (P.n_valid & 3) == 0 || (gate && (P.gate_cols & 3) == 0));
+            const bool fast = __all_sync(0xffffffffu, row_ok) && out_al && (colfull || (P.n_valid & 3) == 0);
             const int acc = lt & 1;
             // pixel offsets of the 4 rows this lane stores in every sub-chunk, and (accumulate) the old values of the first one,
             // requested BEFORE waiting for the accumulator so that their DRAM latency hides behind the MMAs still running
             long long offs[4];
             float4 olds[4], nxt[4];
-            uint2 gys[4], gnx[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 offs[i] = __shfl_sync(0xffffffffu, my_off, i * 8 + rsub);
                 olds[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 nxt[i] = olds[i];
-                gys[i] = make_uint2(0u, 0u);
-                gnx[i] = gys[i];
                 const int col0 = n0 + half * 16 + q * 4;
                 if (accum && out_al && offs[i] >= 0 && col0 + 3 < P.n_valid) olds[i] = *reinterpret_cast<const float4 *>(P.out + offs[i] + col0);
-                if (gate && out_al && offs[i] >= 0 && col0 + 3 < P.gate_cols) gys[i] = __ldg(reinterpret_cast<const uint2 *>(P.gate16 + offs[i] + col0));
             }
             mbar_wait(&acc_full[acc], (lt >> 1) & 1);
             tc_fence_after();
@@ -615,14 +579,12 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * ACC_COLS + j * 16), v);
                 const int cbase = n0 + j * 16;
                 if (cbase >= P.n_valid) continue;           // (warp-uniform)
-                if ((accum || gate) && j + 2 < NSUB) {      // next sub-chunk's old values / gate values in flight while this one is processed
+                if (accum && j + 2 < NSUB) {                // next sub-chunk's old values in flight while this one is processed
                     const int coln = cbase + 32 + q * 4;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        gnx[i] = make_uint2(0u, 0u);
-                        if (accum && out_al && offs[i] >= 0 && coln + 3 < P.n_valid) nxt[i] = *reinterpret_cast<const float4 *>(P.out + offs[i] + coln);
-                        if (gate && out_al && offs[i] >= 0 && coln + 3 < P.gate_cols) gnx[i] = __ldg(reinterpret_cast<const uint2 *>(P.gate16 + offs[i] + coln));
+                        if (out_al && offs[i] >= 0 && coln + 3 < P.n_valid) nxt[i] = *reinterpret_cast<const float4 *>(P.out + offs[i] + coln);
                     }
                 }
                 // row `lane`, 16-byte slot c -> physical slot c ^ ((lane >> 1) & 3)
@@ -631,51 +593,10 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     stg[lane * 4 + (c ^ ((lane >> 1) & 3))] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
                 __syncwarp();
                 const int col = cbase + q * 4;
-                const bool gated = gate && col + 3 < P.gate_cols;       // this lane's whole quad is gated (gate_cols need not be a multiple of 4 here)
-                float4 dsum = make_float4(0.f, 0.f, 0.f, 0.f);
-                // value of one stored quad after bias / activation / accumulation; gated quads: * ELU'(y) -> bf16 only (+ bias-gradient partial)
-                auto finish_vec = [&](float4 o, int i, long long off) {
-                    if (gated) {
-                        const float2 ylo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&gys[i].x));
-                        const float2 yhi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&gys[i].y));
-                        o.x *= elu_grad_from_out(ylo.x); o.y *= elu_grad_from_out(ylo.y);
-                        o.z *= elu_grad_from_out(yhi.x); o.w *= elu_grad_from_out(yhi.y);
-                        dsum.x += o.x; dsum.y += o.y; dsum.z += o.z; dsum.w += o.w;
-                    } else if (has32) {
-                        *reinterpret_cast<float4 *>(P.out + off + col) = o;
-                    }
-                    if (gated || has16) {                   // bf16 output (shadow for the next tensor-core consumer, or the gated gradient itself)
-                        __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
-                        uint2 pk;
-                        pk.x = *reinterpret_cast<uint32_t *>(&lo);
-                        pk.y = *reinterpret_cast<uint32_t *>(&hi);
-                        *reinterpret_cast<uint2 *>(P.out16 + off + col) = pk;
-                    }
-                };
-                // scalar tail: partial quads, unaligned slabs, the linear columns behind the gated ones
-                auto finish_scalar = [&](const float4 &o4, long long off) {
-                    const float ov[4] = {o4.x, o4.y, o4.z, o4.w};
-                    float dv[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        if (col + e < P.n_valid) {
-                            float val = accum ? P.out[off + col + e] + ov[e] : ov[e];
-                            if (gate && col + e < P.gate_cols) {
-                                val *= elu_grad_from_out(__bfloat162float(P.gate16[off + col + e]));
-                                P.out16[off + col + e] = __float2bfloat16_rn(val);
-                                dv[e] = val;
-                            } else {
-                                if (has32) P.out[off + col + e] = val;
-                                if (has16) P.out16[off + col + e] = __float2bfloat16_rn(val);
-                            }
-                        }
-                    dsum.x += dv[0]; dsum.y += dv[1]; dsum.z += dv[2]; dsum.w += dv[3];
-                };
                 if (fast) {
                     const bool col_ok = colfull || col < P.n_valid;
-                    const bool vec = colfull || col + 3 < P.n_valid;
                     float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (P.bias != nullptr && vec) bv = __ldg(reinterpret_cast<const float4 *>(P.bias + col));
+                    if (P.bias != nullptr && col_ok) bv = __ldg(reinterpret_cast<const float4 *>(P.bias + col));
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int rr = i * 8 + rsub;
@@ -686,11 +607,14 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                             o.x = o.x > 0.f ? o.x : __expf(o.x) - 1.f; o.y = o.y > 0.f ? o.y : __expf(o.y) - 1.f;
                             o.z = o.z > 0.f ? o.z : __expf(o.z) - 1.f; o.w = o.w > 0.f ? o.w : __expf(o.w) - 1.f;
                         }
-                        if (vec && (!gate || gated || col >= P.gate_cols)) {
-                            if (accum) { o.x += olds[i].x; o.y += olds[i].y; o.z += olds[i].z; o.w += olds[i].w; }
-                            finish_vec(o, i, offs[i]);
-                        } else {
-                            finish_scalar(o, offs[i]);      // (only the <= 3-column linear tail of a gate launch gets here: no bias, no activation)
+                        if (accum) { o.x += olds[i].x; o.y += olds[i].y; o.z += olds[i].z; o.w += olds[i].w; }
+                        if (has32) *reinterpret_cast<float4 *>(P.out + offs[i] + col) = o;
+                        if (has16) {                        // bf16 shadow for the next tensor-core consumer (same pitch, 8-byte store)
+                            __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+                            uint2 pk;
+                            pk.x = *reinterpret_cast<uint32_t *>(&lo);
+                            pk.y = *reinterpret_cast<uint32_t *>(&hi);
+                            *reinterpret_cast<uint2 *>(P.out16 + offs[i] + col) = pk;
                         }
                     }
                 } else {
@@ -702,7 +626,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                         if (col + 2 < P.n_valid) bv.z = __ldg(P.bias + col + 2);
                         if (col + 3 < P.n_valid) bv.w = __ldg(P.bias + col + 3);
                     }
-                    const bool vec = out_al && col + 3 < P.n_valid && (!gate || gated || col >= P.gate_cols);
+                    const bool vec = out_al && col + 3 < P.n_valid;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const int rr = i * 8 + rsub;
@@ -714,28 +638,31 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                             o.x = o.x > 0.f ? o.x : __expf(o.x) - 1.f; o.y = o.y > 0.f ? o.y : __expf(o.y) - 1.f;
                             o.z = o.z > 0.f ? o.z : __expf(o.z) - 1.f; o.w = o.w > 0.f ? o.w : __expf(o.w) - 1.f;
                         }
+                        float *dst = P.out + off + col;
                         if (vec) {
                             o.x += olds[i].x; o.y += olds[i].y; o.z += olds[i].z; o.w += olds[i].w;
-                            finish_vec(o, i, off);
+                            if (has32) *reinterpret_cast<float4 *>(dst) = o;
+                            if (has16) {
+                                __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+                                uint2 pk;
+                                pk.x = *reinterpret_cast<uint32_t *>(&lo);
+                                pk.y = *reinterpret_cast<uint32_t *>(&hi);
+                                *reinterpret_cast<uint2 *>(P.out16 + off + col) = pk;
+                            }
                         } else {
-                            finish_scalar(o, off);
+                            const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (col + e < P.n_valid) {
+                                    const float val = accum ? dst[e] + ov[e] : ov[e];
+                                    if (has32) dst[e] = val;
+                                    if (has16) P.out16[off + col + e] = __float2bfloat16_rn(val);
+                                }
                         }
                     }
                 }
-                if (want_db) {                              // column sums of this sub-chunk: reduce over the 8 row lanes, park in shared memory
 #pragma unroll
-                    for (int m = 4; m < 32; m <<= 1) {
-                        dsum.x += __shfl_xor_sync(0xffffffffu, dsum.x, m); dsum.y += __shfl_xor_sync(0xffffffffu, dsum.y, m);
-                        dsum.z += __shfl_xor_sync(0xffffffffu, dsum.z, m); dsum.w += __shfl_xor_sync(0xffffffffu, dsum.w, m);
-                    }
-                    if (rsub == 0) {
-                        float4 a = dbw[(j >> 1) * 4 + q];
-                        a.x += dsum.x; a.y += dsum.y; a.z += dsum.z; a.w += dsum.w;
-                        dbw[(j >> 1) * 4 + q] = a;
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) { olds[i] = nxt[i]; gys[i] = gnx[i]; }
+                for (int i = 0; i < 4; ++i) olds[i] = nxt[i];
                 __syncwarp();
             }
             tc_fence_before();
@@ -745,7 +672,6 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 else mbar_arrive(&acc_empty[acc]);
             }
         }
-        if (want_db && nt_prev >= 0) flush_db(nt_prev);
     }
     tc_fence_before();
     if (CG2) cluster_sync_all();                        // the peer may still be reading / being written through the pair's TMEM + smem
@@ -1042,7 +968,6 @@ struct GatherSpec {
     void *out16;                                    // optional bf16 shadow of the output
     const float *bias; int act, accumulate;
     int B;
-    const void *gate16 = nullptr; int gate_cols = 0; float *db = nullptr;     // GATE epilogue (see TcParams)
 };
 
 static int run_gather(const GatherSpec &G, const TcParams &Pin, cudaStream_t st) {
@@ -1080,12 +1005,8 @@ static int run_gather(const GatherSpec &G, const TcParams &Pin, cudaStream_t st)
     for (int t = 0; t < taps_listed; ++t) P.taps[t].wk *= cpad;     // caller stored the canonical tap index
     P.ncb = cpad / kel;
     P.a_coff = G.a_coff; P.a_ld = G.a_ld;
-    P.out = G.out; P.out_ld = G.out_ld;
-    P.out16 = (G.accumulate && G.gate16 == nullptr) ? nullptr : reinterpret_cast<__nv_bfloat16 *>(G.out16);
-    P.gate16 = reinterpret_cast<const __nv_bfloat16 *>(G.gate16); P.gate_cols = G.gate16 ? G.gate_cols : 0; P.db = G.gate16 ? G.db : nullptr;
+    P.out = G.out; P.out_ld = G.out_ld; P.out16 = G.accumulate ? nullptr : reinterpret_cast<__nv_bfloat16 *>(G.out16);
     DOFB_CHECK_ARG(G.out != nullptr || (G.out16 != nullptr && !G.accumulate), "tc conv: a bf16-only output needs the bf16 buffer and cannot accumulate");
-    DOFB_CHECK_ARG(G.gate16 == nullptr || (G.out16 != nullptr && G.gate_cols > 0 && G.gate_cols <= G.n_valid && (G.gate_cols == G.n_valid || G.out != nullptr)),
-                   "tc conv (gate epilogue): needs the bf16 output, 0 < gate_cols <= channels, and the fp32 buffer for linear columns");
     P.bias = G.bias; P.n_valid = G.n_valid; P.rh = G.rh; P.rw = G.rw;
     P.act = G.act; P.accumulate = G.accumulate; P.B = G.B;
     // ---- halo tiles: unit-stride gather, every phase at least 16 x 8 pixels, <= 4 taps per phase spanning <= 2 rows / 8 columns ----
@@ -1240,7 +1161,7 @@ int tc_conv_fwd(const dofb_conv_geom *g, const float *x, int x_ld, const float *
 
 // ---- conv input gradient (and transposed-conv forward): bwd-type gather, one launch per stride phase ----
 int tc_conv_dgrad(const dofb_conv_geom *g, const float *dy, int dy_ld, const float *w, const float *bias, float *dx, int dx_ld, int act,
-                  int accumulate, cudaStream_t st, const void *dy16, void *dx16, const void *gate16, int gate_cols, float *db) {
+                  int accumulate, cudaStream_t st, const void *dy16, void *dx16) {
     DOFB_CHECK_ARG(g && g->kh * g->kw <= TC_MAX_TAPS, "dofb_conv_dgrad(tf32): at most %d taps", TC_MAX_TAPS);
     DOFB_CHECK_ARG(g->stride == 1 || g->stride == 2, "dofb_conv_dgrad(tf32): stride must be 1 or 2");
     DOFB_CHECK_ARG(dy_ld % (dy16 ? 64 : 32) == 0 && aligned16(dy), "dofb_conv_dgrad(tensor): pitch %d must be a multiple of %d and dy 16-byte aligned", dy_ld, dy16 ? 64 : 32);
@@ -1250,7 +1171,6 @@ int tc_conv_dgrad(const dofb_conv_geom *g, const float *dy, int dy_ld, const flo
     G.w = w; G.w_ci = g->ci; G.w_co = g->co; G.taps_h = g->kh; G.taps_w = g->kw; G.contract_ci = 0;
     G.out = dx; G.out_ld = dx_ld; G.rh = g->ih; G.rw = g->iw; G.n_valid = g->ci; G.bias = bias; G.act = act; G.accumulate = accumulate;
     G.B = g->B;
-    G.gate16 = gate16; G.gate_cols = gate_cols; G.db = db;
     const int s = g->stride;
     // all stride^2 phases (output sub-grids with their own sub-kernel taps) run in ONE persistent launch
     TcParams P;

@@ -10,7 +10,7 @@
 //     dWz[c, (tap, n)] = sum_q X[q, c] * D9[q, (tap, n)]       one 1x1 weight-gradient GEMM, X read ONCE
 // Both GEMMs run on the tcgen05 kernels of conv_tc.cu (dofb_conv_fwd_bf16 / dofb_conv_wgrad_bf16 with a 1x1 geometry); this file holds the
 // small re-layout kernels around them and the fused input-gradient kernel:
-//     g16[p, ch] = bf16( (g[p, ch] + sum_{tap,n} dpr[p - off(tap), n] * W[tap, c0 + ch, n]) * ELU'(y16[p, ch]) )   (+ bias gradient)
+//     g16[p, ch] = bf16( (g[p, ch] + sum_{j < 18} D9[p, j] * Wz[c0 + ch, j]) * ELU'(y16[p, ch]) )   (+ bias gradient)
 // i.e. the head's input gradient is never written to memory: it is added on the fly by the pass that finishes the gradient of the slab
 // (the ELU' / BiasAddGrad pass that had to stream the slab anyway).
 #include "common.cuh"
@@ -21,14 +21,6 @@ namespace dofb {
 constexpr int HZ_LD = 20;          // columns of Z / Wz / dWz: 9 taps x 2 outputs, padded to a multiple of 4
 
 __device__ __forceinline__ void fma2h(float2 &acc, float a, float2 b) { acc = __ffma2_rn(make_float2(a, a), b, acc); }
-__device__ __forceinline__ void cpa16(void *smem_dst, const void *gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cpa8(void *smem_dst, const void *gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---- W[3,3,C,2] <-> Wz[C,20] (the canonical [1,1,C,20] layout of a 1x1 convolution), several heads per launch ----
 constexpr int HZ_MAX_HEADS = 8;
@@ -114,176 +106,92 @@ __global__ void __launch_bounds__(256) head_dpr9_kernel(const float *__restrict_
 }
 
 // ---- fused: head input gradient + ELU' + bf16 shadow + bias gradient over one channel slab of feat_s ----
-// Same streaming structure as head_dgrad_kernel (heads.cu): a lane owns 4 channels (72 head weights in registers), a warp walks 32-pixel
-// row segments, the 3x3 window of dpr lives across the warp and moves by shuffles; the old gradient (fp32, 16 B per lane and pixel) and the
-// ELU outputs (bf16, 8 B) stream through per-warp cp.async rings one whole segment ahead.
+// The head's input gradient at pixel p, channel ch is an 18-term dot product of the pixel's D9 row (the bf16 im2col of dpr that the weight
+// gradient needs anyway) with row ch of Wz -- no neighbourhood access at all.  Thread layout of the plain ELU' pass (elementwise.cu): a
+// block = (256 / QW) pixel rows x QW channel quads; a thread keeps the 4 x 18 weights of its quad in registers and walks pixels, so the
+// kernel stays a streaming pass (8 B per element when an old gradient exists: fp32 g in, bf16 y in, bf16 out; 4 B without) with 36 packed
+// FMAs per quad on top.  The QW lanes of a pixel row read the same 36-byte D9 row (one L1 broadcast each).
 //   channels [0, c_elu)  : out16 = bf16((g + head) * ELU'(y16));  db[ch] += column sums          (conv / upconv outputs)
 //   channels [c_elu, c)  : gout  = g + head  (fp32, linear)                                         (the 2-channel up_pr slice)
-struct DprWin {
-    float2 prim[3], sec[3];
-    __device__ __forceinline__ void load(const float2 *img, int y, int x0, int h, int w, int lane) {
-        const int cx = x0 - 1 + lane, cx2 = x0 + 31 + lane;
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const int sy = y - 1 + r;
-            const bool okr = sy >= 0 && sy < h;
-            prim[r] = (okr && cx >= 0 && cx < w) ? __ldg(img + (long long)sy * w + cx) : make_float2(0.f, 0.f);
-            sec[r] = (lane < 2 && okr && cx2 < w) ? __ldg(img + (long long)sy * w + cx2) : make_float2(0.f, 0.f);
-        }
-    }
-    __device__ __forceinline__ void col(int j, float2 (&out)[3]) const {
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const float2 src = j < 32 ? prim[r] : sec[r];
-            out[r].x = __shfl_sync(0xffffffffu, src.x, j & 31);
-            out[r].y = __shfl_sync(0xffffffffu, src.y, j & 31);
-        }
-    }
-};
-
-constexpr int HF_WARPS = 4;
-constexpr int HF_SMEM_G = HF_WARPS * 32 * 32 * 16, HF_SMEM_Y = HF_WARPS * 32 * 32 * 8;
-
 struct HeadFusedParams {
-    const float *dpr; int B, h, w;
-    const float *Wt; int Ctot, c0;          // head weights [3,3,Ctot,2]; the slab starts at head channel c0
+    const __nv_bfloat16 *d9; int d9_ld;
+    const float *wz;                        // [c][20]: rows of the slab's channels
     int c, c_elu;
     const float *g; int g_ld;               // old gradient at the slab start (nullptr: none)
     const __nv_bfloat16 *y16; int y_ld;     // ELU outputs at the slab start
     __nv_bfloat16 *out16; int out16_ld;
     float *gout; int gout_ld;               // fp32 output of the linear channels (pointer at the slab start)
     float *db;
-    long long n_seg; int segs_per_row;
+    long long n_pix, pix_per_block;
+    int qw;
 };
 
+__device__ __forceinline__ float2 bf2_unpack(uint32_t u) { return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
+
 template <bool HASG>
-__global__ void __launch_bounds__(HF_WARPS * 32, 2) head_dgrad_elu_kernel(const __grid_constant__ HeadFusedParams P) {
-    extern __shared__ __align__(16) uint8_t hf_ring[];
-    float4 *gring = reinterpret_cast<float4 *>(hf_ring);
-    uint2 *yring = reinterpret_cast<uint2 *>(hf_ring + (HASG ? HF_SMEM_G : 0));
-    __shared__ float redb[128];
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int ch = (blockIdx.y * 32 + lane) * 4;
+__global__ void __launch_bounds__(256, 2) head_dgrad_elu_kernel(const __grid_constant__ HeadFusedParams P) {
+    const int qw = P.qw;
+    const int ql = threadIdx.x & (qw - 1);
+    const int ch = (blockIdx.y * qw + ql) * 4;
+    const int rows = 256 / qw;
+    const int prow = threadIdx.x / qw;
     const bool active = ch < P.c;
     const bool is_elu = ch < P.c_elu;                       // (c_elu is a multiple of 4: a quad never straddles the boundary)
-    const int chl = active ? ch : 0;
-    const int h = P.h, w = P.w;
-    redb[threadIdx.x] = 0.f;
-    float2 wr[9][2][2];
+    float2 w01[18], w23[18];                                // (W[j][ch], W[j][ch+1]), (W[j][ch+2], W[j][ch+3])
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap)
-#pragma unroll
-        for (int k = 0; k < 2; ++k)
-#pragma unroll
-            for (int o = 0; o < 2; ++o) {
-                wr[tap][k][o].x = (ch + 2 * k < P.c) ? __ldg(P.Wt + ((long long)tap * P.Ctot + P.c0 + ch + 2 * k) * 2 + o) : 0.f;
-                wr[tap][k][o].y = (ch + 2 * k + 1 < P.c) ? __ldg(P.Wt + ((long long)tap * P.Ctot + P.c0 + ch + 2 * k + 1) * 2 + o) : 0.f;
-            }
-    const long long n_warps = (long long)gridDim.x * HF_WARPS;
-    float4 *gr = gring + (wid * 32) * 32 + lane;
-    uint2 *yr = yring + (wid * 32) * 32 + lane;
-    const int ychl = is_elu ? chl : 0;                      // linear quads stream (and ignore) channel 0 of y
+    for (int j = 0; j < 18; ++j) {
+        w01[j] = make_float2(ch < P.c ? __ldg(P.wz + (long long)ch * HZ_LD + j) : 0.f, ch + 1 < P.c ? __ldg(P.wz + (long long)(ch + 1) * HZ_LD + j) : 0.f);
+        w23[j] = make_float2(ch + 2 < P.c ? __ldg(P.wz + (long long)(ch + 2) * HZ_LD + j) : 0.f, ch + 3 < P.c ? __ldg(P.wz + (long long)(ch + 3) * HZ_LD + j) : 0.f);
+    }
+    const long long p0 = (long long)blockIdx.x * P.pix_per_block;
+    const long long p1 = p0 + P.pix_per_block < P.n_pix ? p0 + P.pix_per_block : P.n_pix;
     float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
-    long long seg = (long long)blockIdx.x * HF_WARPS + wid;
-    if (seg < P.n_seg) {
-        const int x0 = (int)(seg % P.segs_per_row) * 32;
-        const int len = w - x0 < 32 ? w - x0 : 32;
-        const long long pix0 = (seg / P.segs_per_row) * w + x0;
+    if (active) {
+        for (long long p = p0 + prow; p < p1; p += rows) {
+            const uint4 *drow = reinterpret_cast<const uint4 *>(P.d9 + p * P.d9_ld);
+            const uint4 da = __ldg(drow), dbv = __ldg(drow + 1);
+            const uint32_t dc = __ldg(reinterpret_cast<const uint32_t *>(drow + 2));
+            float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (HASG) gv = __ldg(reinterpret_cast<const float4 *>(P.g + p * P.g_ld + ch));
+            uint2 ypk = make_uint2(0u, 0u);
+            if (is_elu) ypk = __ldg(reinterpret_cast<const uint2 *>(P.y16 + p * P.y_ld + ch));
+            const uint32_t dw[9] = {da.x, da.y, da.z, da.w, dbv.x, dbv.y, dbv.z, dbv.w, dc};
+            float2 a01 = make_float2(gv.x, gv.y), a23 = make_float2(gv.z, gv.w), b01 = make_float2(0.f, 0.f), b23 = b01;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            if (j < len) {
-                if (HASG) cpa16(gr + j * 32, P.g + (pix0 + j) * P.g_ld + chl);
-                cpa8(yr + j * 32, P.y16 + (pix0 + j) * P.y_ld + ychl);
+            for (int t = 0; t < 9; ++t) {                   // tap t: D9 columns (2t, 2t+1) = the two flow-gradient components
+                const float2 d = bf2_unpack(dw[t]);
+                fma2h(a01, d.x, w01[2 * t]); fma2h(b01, d.y, w01[2 * t + 1]);
+                fma2h(a23, d.x, w23[2 * t]); fma2h(b23, d.y, w23[2 * t + 1]);
             }
-            if ((j & 7) == 7) cpa_commit();
-        }
-    }
-    for (; seg < P.n_seg; seg += n_warps) {
-        const int xs = (int)(seg % P.segs_per_row);
-        const long long row = seg / P.segs_per_row;         // = b * h + y
-        const int y = (int)(row % h);
-        const int x0 = xs * 32;
-        const int len = w - x0 < 32 ? w - x0 : 32;
-        const long long nseg = seg + n_warps;
-        const int x0n = (int)(nseg % P.segs_per_row) * 32;
-        const int len_n = nseg < P.n_seg ? (w - x0n < 32 ? w - x0n : 32) : 0;
-        const long long pixn = (nseg / P.segs_per_row) * w + x0n;
-        const long long pix0 = row * w + x0;
-        DprWin sg;
-        sg.load(reinterpret_cast<const float2 *>(P.dpr) + (row - y) * w, y, x0, h, w, lane);
-        float2 c0[3], c1[3], c2[3];
-        sg.col(0, c0);
-        sg.col(1, c1);
-        auto pixel = [&](int j) {
-            if ((j & 7) == 0) cpa_wait<3>();
-            sg.col(j + 2, c2);
-            float2 a01 = make_float2(0.f, 0.f), a23 = a01, b01 = a01, b23 = a01;
-            if (HASG) { const float4 old = gr[j * 32]; a01 = make_float2(old.x, old.y); a23 = make_float2(old.z, old.w); }
-            const uint2 ypk = yr[j * 32];
-#pragma unroll
-            for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-                for (int kw = 0; kw < 3; ++kw) {
-                    const float2 gg = kw == 0 ? c2[2 - kh] : (kw == 1 ? c1[2 - kh] : c0[2 - kh]);
-                    const int tap = kh * 3 + kw;
-                    fma2h(a01, gg.x, wr[tap][0][0]); fma2h(b01, gg.y, wr[tap][0][1]);
-                    fma2h(a23, gg.x, wr[tap][1][0]); fma2h(b23, gg.y, wr[tap][1][1]);
-                }
             float4 v = make_float4(a01.x + b01.x, a01.y + b01.y, a23.x + b23.x, a23.y + b23.y);
-            if (active) {
-                if (is_elu) {
-                    const float2 ylo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&ypk.x));
-                    const float2 yhi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&ypk.y));
-                    v.x *= elu_grad_from_out(ylo.x); v.y *= elu_grad_from_out(ylo.y);
-                    v.z *= elu_grad_from_out(yhi.x); v.w *= elu_grad_from_out(yhi.y);
-                    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-                    uint2 pk;
-                    pk.x = *reinterpret_cast<const uint32_t *>(&lo);
-                    pk.y = *reinterpret_cast<const uint32_t *>(&hi);
-                    *reinterpret_cast<uint2 *>(P.out16 + (pix0 + j) * P.out16_ld + ch) = pk;
-                    bsum.x += v.x; bsum.y += v.y; bsum.z += v.z; bsum.w += v.w;
-                } else {
-                    float *dst = P.gout + (pix0 + j) * P.gout_ld + ch;
-                    dst[0] = v.x;
-                    if (ch + 1 < P.c) dst[1] = v.y;
-                    if (ch + 2 < P.c) dst[2] = v.z;
-                    if (ch + 3 < P.c) dst[3] = v.w;
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < 3; ++r) { c0[r] = c1[r]; c1[r] = c2[r]; }
-            if (j < len_n) {
-                if (HASG) cpa16(gr + j * 32, P.g + (pixn + j) * P.g_ld + chl);
-                cpa8(yr + j * 32, P.y16 + (pixn + j) * P.y_ld + ychl);
-            }
-            if ((j & 7) == 7) cpa_commit();
-        };
-        if (len == 32) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) pixel(j);
-        } else {
-#pragma unroll 1
-            for (int j = 0; j < len; ++j) pixel(j);
-#pragma unroll 1
-            for (int j = len; j < 32; ++j) {                // keep the group count of a full segment
-                if (j < len_n) {
-                    if (HASG) cpa16(gr + j * 32, P.g + (pixn + j) * P.g_ld + chl);
-                    cpa8(yr + j * 32, P.y16 + (pixn + j) * P.y_ld + ychl);
-                }
-                if ((j & 7) == 7) cpa_commit();
+            if (is_elu) {
+                const float2 ylo = bf2_unpack(ypk.x), yhi = bf2_unpack(ypk.y);
+                v.x *= elu_grad_from_out(ylo.x); v.y *= elu_grad_from_out(ylo.y);
+                v.z *= elu_grad_from_out(yhi.x); v.w *= elu_grad_from_out(yhi.y);
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<const uint32_t *>(&lo);
+                pk.y = *reinterpret_cast<const uint32_t *>(&hi);
+                *reinterpret_cast<uint2 *>(P.out16 + p * P.out16_ld + ch) = pk;
+                bsum.x += v.x; bsum.y += v.y; bsum.z += v.z; bsum.w += v.w;
+            } else {
+                float *dst = P.gout + p * P.gout_ld + ch;
+                dst[0] = v.x;
+                if (ch + 1 < P.c) dst[1] = v.y;
+                if (ch + 2 < P.c) dst[2] = v.z;
+                if (ch + 3 < P.c) dst[3] = v.w;
             }
         }
     }
-    cpa_wait<0>();
     if (P.db == nullptr) return;
+    __shared__ float4 red[256];
+    red[threadIdx.x] = bsum;
     __syncthreads();
-    if (active && is_elu) {
-        atomicAdd(&redb[lane * 4 + 0], bsum.x); atomicAdd(&redb[lane * 4 + 1], bsum.y);
-        atomicAdd(&redb[lane * 4 + 2], bsum.z); atomicAdd(&redb[lane * 4 + 3], bsum.w);
+    if (prow == 0 && active && is_elu) {
+        float4 sacc = red[ql];
+        for (int r = 1; r < rows; ++r) { const float4 t = red[r * qw + ql]; sacc.x += t.x; sacc.y += t.y; sacc.z += t.z; sacc.w += t.w; }
+        atomicAdd(P.db + ch, sacc.x); atomicAdd(P.db + ch + 1, sacc.y); atomicAdd(P.db + ch + 2, sacc.z); atomicAdd(P.db + ch + 3, sacc.w);
     }
-    __syncthreads();
-    const int cc = blockIdx.y * 128 + threadIdx.x;
-    if (cc < P.c_elu) atomicAdd(P.db + cc, redb[threadIdx.x]);
 }
 
 }  // namespace dofb
@@ -339,10 +247,11 @@ extern "C" int dofb_head_dpr9(const float *dpr, int B, int h, int w, void *d9_bf
     return 0;
 }
 
-extern "C" int dofb_head_dgrad_elu_bf16(const float *dpr, int B, int h, int w, const float *wt, int c_total, int c0, int c, int c_elu,
-                                        const float *g, int g_ld, const void *y_bf16, int y_ld, void *out_bf16, int out_ld,
+extern "C" int dofb_head_dgrad_elu_bf16(const void *d9_bf16, int d9_ld, int B, int h, int w, const float *wz, int c_total, int c0, int c,
+                                        int c_elu, const float *g, int g_ld, const void *y_bf16, int y_ld, void *out_bf16, int out_ld,
                                         float *gout, int gout_ld, float *db, void *stream) {
-    DOFB_CHECK_ARG(dpr && wt && B > 0 && h > 0 && w > 0 && c > 0 && c0 >= 0 && c0 + c <= c_total, "dofb_head_dgrad_elu_bf16: bad argument");
+    DOFB_CHECK_ARG(d9_bf16 && wz && B > 0 && h > 0 && w > 0 && c > 0 && c0 >= 0 && c0 + c <= c_total, "dofb_head_dgrad_elu_bf16: bad argument");
+    DOFB_CHECK_ARG(d9_ld >= 24 && d9_ld % 8 == 0 && aligned16(d9_bf16), "dofb_head_dgrad_elu_bf16: D9 needs a pitch that is a multiple of 8 and 16-byte alignment");
     DOFB_CHECK_ARG(c_elu >= 0 && c_elu <= c && c_elu % 4 == 0, "dofb_head_dgrad_elu_bf16: the ELU channel count %d must be a multiple of 4 within the slab", c_elu);
     DOFB_CHECK_ARG(c_elu == 0 || (y_bf16 && out_bf16 && y_ld % 4 == 0 && out_ld % 4 == 0 && (reinterpret_cast<uintptr_t>(y_bf16) & 7u) == 0 &&
                                   (reinterpret_cast<uintptr_t>(out_bf16) & 7u) == 0),
@@ -350,28 +259,27 @@ extern "C" int dofb_head_dgrad_elu_bf16(const float *dpr, int B, int h, int w, c
     DOFB_CHECK_ARG(c_elu == c || gout != nullptr, "dofb_head_dgrad_elu_bf16: linear channels need the fp32 output");
     DOFB_CHECK_ARG(g == nullptr || (aligned16(g) && g_ld % 4 == 0), "dofb_head_dgrad_elu_bf16: g must be 16-byte aligned with a pitch that is a multiple of 4");
     HeadFusedParams P;
-    P.dpr = dpr; P.B = B; P.h = h; P.w = w; P.Wt = wt; P.Ctot = c_total; P.c0 = c0; P.c = c; P.c_elu = c_elu;
+    P.d9 = reinterpret_cast<const __nv_bfloat16 *>(d9_bf16); P.d9_ld = d9_ld;
+    P.wz = wz + (long long)c0 * HZ_LD; P.c = c; P.c_elu = c_elu;
     P.g = g; P.g_ld = g_ld;
-    // a slab without ELU channels still needs a readable 8-byte stream for the (ignored) y ring: use dpr itself
-    P.y16 = c_elu > 0 ? reinterpret_cast<const __nv_bfloat16 *>(y_bf16) : reinterpret_cast<const __nv_bfloat16 *>(dpr);
-    P.y_ld = c_elu > 0 ? y_ld : 4;
+    P.y16 = reinterpret_cast<const __nv_bfloat16 *>(y_bf16); P.y_ld = y_ld;
     P.out16 = reinterpret_cast<__nv_bfloat16 *>(out_bf16); P.out16_ld = out_ld;
     P.gout = gout; P.gout_ld = gout_ld; P.db = db;
-    const int chunks = ((c + 3) / 4 + 31) / 32;
-    P.segs_per_row = (w + 31) / 32;
-    P.n_seg = (long long)B * h * P.segs_per_row;
-    long long warps = (long long)num_sms() * 8 * 2 / chunks;       // two waves of 8 resident warps per SM
-    if (warps < 4) warps = 4;
-    if (warps > P.n_seg) warps = P.n_seg;
-    const dim3 grid((unsigned)((warps + 3) / 4), chunks, 1);
-    static bool configured = false;
-    if (!configured) {
-        DOFB_CUDA_OK(cudaFuncSetAttribute(head_dgrad_elu_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, HF_SMEM_G + HF_SMEM_Y));
-        DOFB_CUDA_OK(cudaFuncSetAttribute(head_dgrad_elu_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, HF_SMEM_Y));
-        configured = true;
-    }
-    if (g != nullptr) head_dgrad_elu_kernel<true><<<grid, HF_WARPS * 32, HF_SMEM_G + HF_SMEM_Y, as_stream(stream)>>>(P);
-    else head_dgrad_elu_kernel<false><<<grid, HF_WARPS * 32, HF_SMEM_Y, as_stream(stream)>>>(P);
+    P.n_pix = (long long)B * h * w;
+    const int c4 = (c + 3) / 4;
+    int qw = 1;
+    while (qw < c4 && qw < 32) qw <<= 1;
+    const int stripes = (c4 + qw - 1) / qw, rows = 256 / qw;
+    long long blocks = (long long)num_sms() * 8 / stripes;
+    if (blocks < 1) blocks = 1;
+    long long ppb = (P.n_pix + blocks - 1) / blocks;
+    if (ppb < 4 * rows) ppb = 4 * rows;
+    ppb = (ppb + rows - 1) / rows * rows;
+    blocks = (P.n_pix + ppb - 1) / ppb;
+    P.pix_per_block = ppb; P.qw = qw;
+    const dim3 grid((unsigned)blocks, stripes);
+    if (g != nullptr) head_dgrad_elu_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(P);
+    else head_dgrad_elu_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(P);
     DOFB_LAUNCH_OK();
     return 0;
 }

@@ -38,6 +38,8 @@ class GradReducer:
 
     def broadcast_params(self, src: int = 0):
         dist.broadcast(self.engine.theta, src=src, group=self.group)
+        from . import ops
+        ops.invalidate_weight_cache()       # the tensor-core kernels keep packed copies of the weights: theta just changed under them
 
     def begin(self):
         self._next = len(self.bounds) - 1

@@ -344,38 +344,6 @@ class FlowNetS:
                 if L["dx"] is not None and L["dx"].t is self.dact["concat1"].t:
                     L["acc"] = False
             self._head_geom1 = {s: conv_geom(B, self.hw[s][0], self.hw[s][1], self.feat[s][0].c, 20, 1, 1) for s in self.feat}
-            # a conv output with ONE gradient contributor (the next conv's input gradient) is finished in that GEMM's epilogue
-            # (ELU', bias gradient, bf16 only): no fp32 gradient is written or re-read for it
-            convs = [L for L in self.tower if L["op"] == "conv"]
-            for L in convs:
-                if L["dx"] is None or L["acc"]:
-                    continue
-                prod = [Q for Q in convs if Q["dy"].t is L["dx"].t and Q["dy"].c0 == L["dx"].c0 and Q["dy"].c == L["dx"].c]
-                users = [Q for Q in self.tower if Q.get("dx") is not None and Q["dx"].t is L["dx"].t]
-                if len(prod) == 1 and len(users) == 1 and "head_s" not in prod[0] and os.environ.get("DOFB_GATE_DGRAD", "1") != "0":
-                    L["gate_dx"] = prod[0]
-                    prod[0]["finished_by_consumer"] = True
-            self._slab_geom = {}
-            for L in convs:
-                if "head_s" in L:
-                    self._slab(L["head_s"], 0, L["y"].c)
-            for R in self.refine:
-                self._slab(R["s"] - 1, R["skipc"], R["upc"] + 2)
-
-    def _slab(self, hs, c0, c):
-        """(1x1 geometry, [1,1,c,20] weight view) of the head-gradient GEMM for channels [c0, c0+c) of feat_hs."""
-        key = (hs, c0, c)
-        if key not in self._slab_geom:
-            h, w = self.hw[hs]
-            self._slab_geom[key] = (conv_geom(self.B, h, w, c, 20, 1, 1), self.head_wz[hs][:, :, c0:c0 + c, :])
-        return self._slab_geom[key]
-
-    def _head_slab_gate(self, tag, hs, c0, dx: Slab, y: Slab, gate_cols, accumulate, db):
-        """Finish the gradient of channels [c0, c0+dx.c) of feat_hs: the input gradient of the flow head pr_hs is a 1x1 GEMM
-        D9_hs . Wz^T (K = 18 of a 64-wide bf16 k-block) whose epilogue adds the gradient accumulated so far, applies ELU', writes the bf16
-        gradient and the bias gradient (dofb_conv_dgrad_gate_bf16)."""
-        g, wz = self._slab(hs, c0, dx.c)
-        self._k(tag, ops.conv_dgrad_gate, g, Slab(None, 0, 20, self.head_d9[hs]), wz, dx, y, gate_cols, accumulate, db)
 
     def _pack_jobs(self):
         """(weight, orientation) of every tensor-core gather-GEMM the step runs: conv fwd / transposed-conv dgrad read the contract-ci copy,
@@ -405,9 +373,6 @@ class FlowNetS:
                     add(self.head_wz[s], 1)             # tap-in-N form: a 1x1 convolution with the [1,1,C,20] weights
                 elif self.B * h * wd <= self.TC_HEAD_MAX_PIX:
                     add(P[f"pr{s}/weights"], 1)
-            if self.lean:
-                for _g, wz in self._slab_geom.values():
-                    add(wz, 0)                          # ... and its transposed use per gradient slab
             self._jobs = ops.make_pack_jobs(entries)
         return self._jobs
 
@@ -461,9 +426,8 @@ class FlowNetS:
             w, dw, db = P[L["wname"] + "/weights"], G[L["wname"] + "/weights"], G[L["wname"] + "/biases"]
             # + bias gradient; bf16 math: only the bf16 shadow of the finished gradient is read again (by this layer's wgrad / dgrad)
             if self.lean and "head_s" in L:     # ... and the input gradient of the flow head reading this slab is added on the fly
-                self._head_slab_gate("elu_bwd:" + L["name"], L["head_s"], 0, L["dy"], L["y"], L["y"].c, True, db)
-            elif L.get("finished_by_consumer"):
-                pass                            # the consumer's input-gradient GEMM already applied ELU' and summed the bias gradient
+                hs = L["head_s"]
+                self._k("elu_bwd:" + L["name"], ops.head_dgrad_elu, self.head_d9[hs], self.head_wz[hs], 0, L["dy"], L["y"], L["dy"], L["y"].c, db)
             else:
                 self._k("elu_bwd:" + L["name"], ops.elu_bwd, L["dy"], L["y"], db, mth == MATH_BF16 and mthw == MATH_BF16)
             if L["xpad"] is not None:
@@ -472,13 +436,8 @@ class FlowNetS:
             else:
                 self._k("conv_wgrad:" + L["name"], ops.conv_wgrad, L["g"], L["x"], L["dy"], dw, None, mthw)
             if L["dx"] is not None:
-                if L.get("gate_dx") is not None:
-                    Q = L["gate_dx"]
-                    self._k("conv_dgrad:" + L["name"], ops.conv_dgrad_gate, L["g"], L["dy"], w, Slab(None, L["dx"].c0, L["dx"].c, L["dx"].t16),
-                            Q["y"], Q["y"].c, False, G[Q["wname"] + "/biases"])
-                else:
-                    dx = Slab(L["dx"].t, L["dx"].c0, L["dx"].c) if self.lean else L["dx"]      # (lean: no bf16 shadow of an unfinished gradient)
-                    self._k("conv_dgrad:" + L["name"], ops.conv_dgrad, L["g"], L["dy"], w, None, dx, ACT_NONE, L["acc"], mth)
+                dx = Slab(L["dx"].t, L["dx"].c0, L["dx"].c) if self.lean else L["dx"]      # (lean: no bf16 shadow of an unfinished gradient)
+                self._k("conv_dgrad:" + L["name"], ops.conv_dgrad, L["g"], L["dy"], w, None, dx, ACT_NONE, L["acc"], mth)
         elif L["op"] == "pool":
             self._k("pool_bwd:" + L["name"], ops.maxpool2_bwd, L["x"], L["dy"], L["dx"])
         elif L["op"] == "corr":
@@ -568,8 +527,9 @@ class FlowNetS:
             fy, fd = self.feat[fs]
             skipc, upc = R["skipc"], R["upc"]
             # gradient of [upconv | up_pr] outputs inside feat_{s-1}: (deconv_dgrad of the previous iteration, none at scale 1) + head pr_{s-1}
-            self._head_slab_gate("elu_bwd:" + R["up"], fs, skipc, fd.sub(skipc, upc + 2), fy.sub(skipc, upc + 2), upc, fs != 1,
-                                 G[R["up"] + "/biases"])
+            slab_d = fd.sub(skipc, upc + 2)
+            self._k("elu_bwd:" + R["up"], ops.head_dgrad_elu, self.head_d9[fs], self.head_wz[fs], skipc, None if fs == 1 else slab_d,
+                    fy.sub(skipc, upc + 2), slab_d, upc, G[R["up"] + "/biases"])
             self._k("uppr_bwd:" + R["uppr"], ops.uppr_bwd, self.pr[s], R["pr_dy"], P[R["uppr"] + "/weights"], self.dpr[s],
                     G[R["uppr"] + "/weights"], G[R["uppr"] + "/biases"])
             self._k("deconv_wgrad:" + R["up"], ops.conv_wgrad, R["g"], R["up_dy"], x, G[R["up"] + "/weights"], None, mth)

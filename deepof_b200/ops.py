@@ -207,16 +207,6 @@ def conv_dgrad(g: ConvGeom, dy: Slab, w, bias, dx: Slab, act=ACT_NONE, accumulat
                               dx.ptr, dx.ld, act, int(accumulate), math, _stream()))
 
 
-def conv_dgrad_gate(g: ConvGeom, dy: Slab, w, dx: Slab, y: Slab, gate_cols: int, accumulate=False, db=None):
-    """Input gradient whose epilogue finishes the slab: bf16(dgrad (+ dx) * ELU'(y)) into dx's bf16 buffer for the first ``gate_cols``
-    channels (+ bias gradient ``db``), plain fp32 for the rest (dofb_conv_dgrad_gate_bf16)."""
-    _req(w, "w")
-    assert y.ld == dx.ld and y.c == dx.c and y.n_pix == dx.n_pix
-    check(_lib.load().dofb_conv_dgrad_gate_bf16(C.byref(g), _need16(dy, "conv_dgrad_gate"), dy.ld, w.data_ptr(), dx.ptr, _need16(dx, "conv_dgrad_gate"),
-                                                dx.ld, int(accumulate), _need16(y, "conv_dgrad_gate"), int(gate_cols),
-                                                db.data_ptr() if db is not None else None, _stream()))
-
-
 def conv_wgrad(g: ConvGeom, x: Slab, dy: Slab, dw, db, math=MATH_FP32, bias_on_large=False):
     _req(dw, "dw")
     lib = _lib.load()
@@ -304,17 +294,19 @@ def head_dpr9(dpr, d9, dbias=None):
     check(_lib.load().dofb_head_dpr9(dpr.data_ptr(), B, h, w, d9.data_ptr(), d9.shape[3], dbias.data_ptr() if dbias is not None else None, _stream()))
 
 
-def head_dgrad_elu(dpr, w_head, c0: int, g: Slab | None, y: Slab, out: Slab, c_elu: int, db=None):
+def head_dgrad_elu(d9, wz, c0: int, g: Slab | None, y: Slab, out: Slab, c_elu: int, db=None):
     """Finish the gradient of the channel slab ``out`` (= channels [c0, c0+out.c) of the head's input feat_s): adds the head's input
-    gradient to ``g`` (or to zero), applies ELU' (from the bf16 ELU outputs ``y``) on the first c_elu channels -> bf16 shadow of ``out`` and
-    bias gradient ``db``; the remaining (linear) channels are written in fp32 to ``out`` (dofb_head_dgrad_elu_bf16)."""
-    _req(dpr, "dpr"); _req(w_head, "w_head")
-    B, h, w, _ = dpr.shape
+    gradient (D9 row . Wz rows) to ``g`` (or to zero), applies ELU' (from the bf16 ELU outputs ``y``) on the first c_elu channels -> bf16
+    shadow of ``out`` and bias gradient ``db``; the remaining (linear) channels are written in fp32 to ``out`` (dofb_head_dgrad_elu_bf16)."""
+    _req(wz, "wz")
+    assert d9.dtype == torch.bfloat16 and d9.is_cuda and d9.is_contiguous() and d9.dim() == 4
+    B, h, w, d9_ld = d9.shape
     c = out.c
+    c_total = wz.numel() // 20
     assert (g is None or g.c == c) and y.c == c and out.n_pix == B * h * w
     lin = c_elu < c
     check(_lib.load().dofb_head_dgrad_elu_bf16(
-        dpr.data_ptr(), B, h, w, w_head.data_ptr(), int(w_head.shape[2]), int(c0), c, int(c_elu),
+        d9.data_ptr(), d9_ld, B, h, w, wz.data_ptr(), c_total, int(c0), c, int(c_elu),
         _need32(g, "head_dgrad_elu") if g is not None else None, g.ld if g is not None else 0,
         _need16(y, "head_dgrad_elu") if c_elu else None, y.ld, _need16(out, "head_dgrad_elu") if c_elu else None, out.ld,
         _need32(out, "head_dgrad_elu") if lin else None, out.ld, db.data_ptr() if db is not None else None, _stream()))

@@ -165,13 +165,6 @@ int dofb_conv_fwd_bf16(const dofb_conv_geom *g, const void *x_bf16, int x_ld, co
 int dofb_conv_dgrad_bf16(const dofb_conv_geom *g, const void *dy_bf16, int dy_ld, const float *w, const float *bias, float *dx,
                          void *dx_bf16 /* written only when !accumulate; may be NULL */, int dx_ld, int act, int accumulate, void *stream);
 int dofb_conv_wgrad_bf16(const dofb_conv_geom *g, const void *x_bf16, int x_ld, const void *dy_bf16, int dy_ld, float *dw, void *stream);
-/* Input gradient whose epilogue FINISHES the gradient of the slab (Conv2DBackpropInput + AddN + EluGrad + BiasAddGrad of the layer
- * that produced the slab, in one kernel):  v = conv_input_gradient(dy, w) (+ dx when accumulate);
- *   channels [0, gate_cols): dx_bf16 = bf16(v * ELU'(y_bf16)) -- bf16 ONLY, the fp32 buffer is not written -- and db[ch] += column sums;
- *   channels [gate_cols, ci): dx = v (fp32, linear).
- * y_bf16 / dx / dx_bf16 share the geometry and pitch dx_ld; dx may be NULL when !accumulate and gate_cols == ci; db may be NULL. */
-int dofb_conv_dgrad_gate_bf16(const dofb_conv_geom *g, const void *dy_bf16, int dy_ld, const float *w, float *dx, void *dx_bf16, int dx_ld,
-                              int accumulate, const void *y_bf16, int gate_cols, float *db, void *stream);
 /* dst_bf16[p, 0..c) = bf16(src[p, 0..c)) for producers that have no fused shadow output (flow heads' up_pr, correlation, pooling) */
 /* First layer in bf16: x_bf16 = bf16 copy (dofb_cast_bf16, pitch 8) of the zero-bordered input of dofb_conv1_fwd; one 128-byte K block
  * per filter row (half the L2->shared traffic of the TF32 form).  Same geometry arguments and semantics as dofb_conv1_fwd / _wgrad. */
@@ -219,11 +212,12 @@ int dofb_head_dwz_unpack(int n_heads, float *const *dw, const float *const *dwz,
 int dofb_head_tapsum(const float *z, int z_ld, int B, int h, int w, const float *bias, float *pr /* [B,h,w,2] */, void *stream);
 /* D9[b,y,x,(kh*3+kw)*2 + n] = bf16(dpr[b, y-kh+1, x-kw+1, n]) (zero outside; only columns 0..17 are written); dbias[n] += sum dpr[...,n] */
 int dofb_head_dpr9(const float *dpr, int B, int h, int w, void *d9_bf16, int d9_ld, float *dbias /* may be NULL */, void *stream);
-/* One channel slab [c0, c0+c) of feat_s: v = (g ? g : 0) + head_input_gradient(dpr, w)[c0..];
+/* One channel slab [c0, c0+c) of feat_s: v = (g ? g : 0) + sum_{j<18} D9[p, j] * wz[c0 + ch, j]  (the head's input gradient, from the same
+ * bf16 im2col D9 = dofb_head_dpr9(dpr) the weight gradient uses and the [C,20] weights of dofb_head_wz_pack);
  *   channels [0, c_elu): out_bf16 = bf16(v * ELU'(y_bf16)), db[ch] += column sums (conv / transposed-conv outputs);
  *   channels [c_elu, c): gout = v (fp32, linear: the 2-channel up_pr slice).  g / y / out / gout point at the slab start. */
-int dofb_head_dgrad_elu_bf16(const float *dpr, int B, int h, int w, const float *wt /* [3,3,c_total,2] */, int c_total, int c0, int c,
-                             int c_elu, const float *g /* may be NULL */, int g_ld, const void *y_bf16, int y_ld, void *out_bf16,
+int dofb_head_dgrad_elu_bf16(const void *d9_bf16, int d9_ld, int B, int h, int w, const float *wz /* [c_total,20] */, int c_total, int c0,
+                             int c, int c_elu, const float *g /* may be NULL */, int g_ld, const void *y_bf16, int y_ld, void *out_bf16,
                              int out_ld, float *gout, int gout_ld, float *db /* may be NULL */, void *stream);
 
 /* ---- optimiser ------------------------------------------------------------ */

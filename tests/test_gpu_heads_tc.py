@@ -99,7 +99,7 @@ def test_head_weight_gradient_tap_in_n(case):
                                   (1, 12, 16, 194, 256, 128, 66, 64, False), (1, 6, 8, 1026, 1088, 0, 512, 512, True),
                                   (2, 5, 37, 98, 128, 64, 34, 32, False)])
 def test_head_input_gradient_fused_with_elu(case):
-    """(g + dX_head)[slab] * ELU'(y) -> bf16, bias gradient = column sums, linear tail in fp32."""
+    """(g + dX_head)[slab] * ELU'(y) -> bf16, bias gradient = column sums, linear tail in fp32; dX_head from the bf16 im2col D9 of dpr."""
     from deepof_b200 import ops
     B, h, w, C, ld, c0, c, c_elu, with_g = case
     gen = torch.Generator().manual_seed(11 + sum(case[:8]))
@@ -109,9 +109,9 @@ def test_head_input_gradient_fused_with_elu(case):
     g[..., :C] = torch.randn(B, h, w, C, generator=gen)
     y = torch.zeros(B, h, w, ld)
     y[..., :C] = _bf(torch.randn(B, h, w, C, generator=gen).clamp(min=-0.95))
-    # reference: transposed 3x3 stencil = gradient of the forward conv
+    # reference: transposed 3x3 stencil = gradient of the forward conv, on the bf16 rounding of dpr (what D9 holds)
     xd = torch.zeros(B, C, h, w, dtype=torch.float64, requires_grad=True)
-    F.conv2d(xd, wt.permute(3, 2, 0, 1).double(), None, padding=1).backward(dpr.permute(0, 3, 1, 2).double())
+    F.conv2d(xd, wt.permute(3, 2, 0, 1).double(), None, padding=1).backward(_bf(dpr).permute(0, 3, 1, 2).double())
     head = xd.grad.permute(0, 2, 3, 1)                          # [B,h,w,C]
     v = head[..., c0:c0 + c] + (g[..., c0:c0 + c].double() if with_g else 0.0)
     ys = y[..., c0:c0 + c_elu].double()
@@ -120,8 +120,11 @@ def test_head_input_gradient_fused_with_elu(case):
     g16 = torch.zeros(B, h, w, ld, dtype=torch.bfloat16, device="cuda")
     y16 = y.to(torch.bfloat16).cuda()
     db = torch.zeros(max(c_elu, 1), device="cuda")
-    ops.head_dgrad_elu(dpr.cuda(), wt.cuda(), c0, ops.Slab(gd, c0, c) if with_g else None, ops.Slab(None, c0, c, y16),
-                       ops.Slab(gd, c0, c, g16), c_elu, db)
+    d9 = torch.zeros(B, h, w, 64, dtype=torch.bfloat16, device="cuda")
+    ops.head_dpr9(dpr.cuda(), d9, None)
+    wz = torch.zeros(1, 1, C, 20, device="cuda")
+    ops.head_wz_pack([wt.cuda()], [wz])
+    ops.head_dgrad_elu(d9, wz, c0, ops.Slab(gd, c0, c) if with_g else None, ops.Slab(None, c0, c, y16), ops.Slab(gd, c0, c, g16), c_elu, db)
     torch.cuda.synchronize()
     got16 = g16[..., c0:c0 + c_elu].float()
     assert rel(got16, v_elu) < 2 ** -7
@@ -135,54 +138,6 @@ def test_head_input_gradient_fused_with_elu(case):
     outside = torch.ones(ld, dtype=torch.bool)
     outside[c0:c0 + c_elu] = False
     assert float(g16[..., outside.cuda()].float().abs().max()) == 0.0
-
-
-GATE_CASES = [  # B, ih, iw, ci, co, k, stride, gate_cols, accumulate
-    (2, 12, 16, 128, 128, 3, 1, 128, False),
-    (2, 24, 32, 64, 128, 5, 2, 64, False),       # strided input gradient: 4 phases in one launch
-    (1, 10, 14, 34, 64, 1, 1, 32, True),         # 1x1, linear tail of 2 channels, accumulate (the flow-head slab form)
-    (2, 9, 21, 98, 64, 1, 1, 64, True),          # ragged map, gated 64 + linear 34
-    (1, 6, 8, 512, 256, 3, 1, 512, True),
-]
-
-
-@pytest.mark.parametrize("case", GATE_CASES)
-def test_conv_dgrad_with_gate_epilogue(case):
-    """dofb_conv_dgrad_gate_bf16: bf16((dgrad + old) * ELU'(y)) + bias gradient in the GEMM epilogue, linear tail in fp32."""
-    from deepof_b200 import ops
-    B, ih, iw, ci, co, k, stride, gate_cols, acc = case
-    gen = torch.Generator().manual_seed(3 + sum(case[:8]))
-    geom = ops.conv_geom(B, ih, iw, ci, co, k, stride)
-    ldx, ldy = (ci + 63) // 64 * 64, (co + 63) // 64 * 64
-    dy = torch.zeros(B, geom.oh, geom.ow, ldy)
-    dy[..., :co] = _bf(torch.randn(B, geom.oh, geom.ow, co, generator=gen))
-    wt = _bf(torch.randn(k, k, ci, co, generator=gen) / math.sqrt(k * k * co))
-    old = torch.zeros(B, ih, iw, ldx)
-    old[..., :ci] = torch.randn(B, ih, iw, ci, generator=gen)
-    y = torch.zeros(B, ih, iw, ldx)
-    y[..., :ci] = _bf(torch.randn(B, ih, iw, ci, generator=gen).clamp(min=-0.95))
-    # reference: the input gradient is autograd of the TF-SAME conv
-    xd = torch.zeros(B, ci, ih, iw, dtype=torch.float64, requires_grad=True)
-    pb, pa = geom.pad_t, max((geom.oh - 1) * stride + k - ih, 0) - geom.pad_t
-    pl, pr_ = geom.pad_l, max((geom.ow - 1) * stride + k - iw, 0) - geom.pad_l
-    out = F.conv2d(F.pad(xd, (pl, pr_, pb, pa)), wt.permute(3, 2, 0, 1).double(), None, stride=stride)
-    out.backward(dy[..., :co].permute(0, 3, 1, 2).double())
-    v = xd.grad.permute(0, 2, 3, 1) + (old[..., :ci].double() if acc else 0.0)
-    ys = y[..., :gate_cols].double()
-    want16 = v[..., :gate_cols] * torch.where(ys > 0, torch.ones_like(ys), ys + 1.0)
-    dx = old.clone().cuda()
-    dx16 = torch.zeros(B, ih, iw, ldx, dtype=torch.bfloat16, device="cuda")
-    db = torch.zeros(gate_cols, device="cuda")
-    need32 = acc or gate_cols < ci
-    ops.conv_dgrad_gate(geom, ops.Slab(None, 0, co, dy.to(torch.bfloat16).cuda()), wt.cuda(), ops.Slab(dx if need32 else None, 0, ci, dx16),
-                        ops.Slab(None, 0, ci, y.to(torch.bfloat16).cuda()), gate_cols, acc, db)
-    torch.cuda.synchronize()
-    assert rel(dx16[..., :gate_cols].float(), want16) < 2 ** -7
-    assert rel(db, want16.sum(dim=(0, 1, 2))) < 3e-4
-    assert float(dx16[..., gate_cols:].float().abs().max()) == 0.0
-    if gate_cols < ci:
-        assert rel(dx[..., gate_cols:ci], v[..., gate_cols:]) < 1e-5
-    assert torch.equal(dx.cpu()[..., :gate_cols], old[..., :gate_cols])             # the gated fp32 columns are not written
 
 
 def test_bf16_only_conv_output_matches_shadow():
