@@ -35,7 +35,15 @@ class LossScale(C.Structure):
                 ("flow_scale", C.c_float),
                 ("epsilon", C.c_float), ("alpha_c", C.c_float), ("alpha_s", C.c_float), ("lambda_smooth", C.c_float),
                 ("g_charb", C.c_float), ("g_u", C.c_float), ("g_v", C.c_float),
-                ("variant", C.c_int)]
+                ("variant", C.c_int), ("edge_w", C.c_void_p)]
+
+
+class _StencilEntry(C.Structure):
+    _fields_ = [("dy", C.c_int), ("dx", C.c_int), ("cin", C.c_int), ("cout", C.c_int), ("w", C.c_float)]
+
+
+class FlowStencil(C.Structure):
+    _fields_ = [("n", C.c_int), ("e", _StencilEntry * 64)]
 
 
 _P, _I, _F, _LL = C.c_void_p, C.c_int, C.c_float, C.c_longlong
@@ -63,6 +71,10 @@ SIGNATURES = {
     "dofb_conv1_wgrad_bf16": (_I, [_G, _P, _I, _I, _I, _I, _P, _I, _P, _P]),
     "dofb_warp_loss_workspace_bytes": (C.c_size_t, [_I, C.POINTER(LossScale)]),
     "dofb_warp_loss": (_I, [_I, C.POINTER(LossScale), _P, C.c_size_t, _P]),
+    "dofb_edge_weights_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
+    "dofb_edge_weights": (_I, [_P, _I, _I, _I, _P, _P, C.c_size_t, _P]),
+    "dofb_warp_loss_multi_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
+    "dofb_warp_loss_multi": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _F, _F, _F, _F, _F, C.POINTER(FlowStencil), _P, C.c_size_t, _P]),
     "dofb_conv_fwd": (_I, [_G, _P, _I, _P, _P, _P, _I, _I, _I, _P]),
     "dofb_conv_dgrad": (_I, [_G, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P]),
     "dofb_conv_wgrad": (_I, [_G, _P, _I, _P, _I, _P, _P, _I, _P]),

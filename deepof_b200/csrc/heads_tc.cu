@@ -107,10 +107,15 @@ __global__ void __launch_bounds__(256) head_dpr9_kernel(const float *__restrict_
 
 // ---- fused: head input gradient + ELU' + bf16 shadow + bias gradient over one channel slab of feat_s ----
 // The head's input gradient at pixel p, channel ch is an 18-term dot product of the pixel's D9 row (the bf16 im2col of dpr that the weight
-// gradient needs anyway) with row ch of Wz -- no neighbourhood access at all.  Thread layout of the plain ELU' pass (elementwise.cu): a
-// block = (256 / QW) pixel rows x QW channel quads; a thread keeps the 4 x 18 weights of its quad in registers and walks pixels, so the
-// kernel stays a streaming pass (8 B per element when an old gradient exists: fp32 g in, bf16 y in, bf16 out; 4 B without) with 36 packed
-// FMAs per quad on top.  The QW lanes of a pixel row read the same 36-byte D9 row (one L1 broadcast each).
+// gradient needs anyway) with row ch of Wz -- no neighbourhood access at all -- i.e. a [pixels x 32] . [32 x channels] GEMM fused into the
+// streaming pass that finishes the slab (8 B per element when an old gradient exists: fp32 g in, bf16 y in, bf16 out; 4 B without).
+// As 36 packed FMAs per channel quad the pass was FP32-issue bound (3x its HBM time); the products therefore run on warp-level tensor
+// core MMAs (mma.sync m16n8k16, bf16 x bf16 -> fp32: 16 MMAs per 16 pixels x 64 channels instead of 288 FMAs per thread).  This is a
+// bandwidth-bound element-wise pass, not a GEMM-bound kernel: warp-level MMAs keep the accumulators in the registers of the threads that
+// also hold the matching g / y / output elements (a tcgen05 tile would have to round-trip through TMEM and shared memory for nothing).
+// A warp owns 16 consecutive pixels x one 64-channel chunk per step.  The n index of the MMA is a PERMUTATION of the channels chosen so
+// that thread `tid` of a quad ends up with 16 CONTIGUOUS channels of its two pixel rows (n-tile t, column 2*tid+j <-> channel
+// 16*tid + 2*t + j): its g / y / output traffic is 16-byte vectors.
 //   channels [0, c_elu)  : out16 = bf16((g + head) * ELU'(y16));  db[ch] += column sums          (conv / upconv outputs)
 //   channels [c_elu, c)  : gout  = g + head  (fp32, linear)                                         (the 2-channel up_pr slice)
 struct HeadFusedParams {
@@ -122,76 +127,156 @@ struct HeadFusedParams {
     __nv_bfloat16 *out16; int out16_ld;
     float *gout; int gout_ld;               // fp32 output of the linear channels (pointer at the slab start)
     float *db;
-    long long n_pix, pix_per_block;
-    int qw;
+    long long n_pix;
 };
 
 __device__ __forceinline__ float2 bf2_unpack(uint32_t u) { return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u)); }
+__device__ __forceinline__ uint32_t bf2_pack(float lo, float hi) {
+    const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&v);
+}
+// D (fp32 16x8) += A (bf16 16x16, row-major) . B (bf16 16x8, column-major)
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int HF_THREADS = 256;
 
 template <bool HASG>
-__global__ void __launch_bounds__(256, 2) head_dgrad_elu_kernel(const __grid_constant__ HeadFusedParams P) {
-    const int qw = P.qw;
-    const int ql = threadIdx.x & (qw - 1);
-    const int ch = (blockIdx.y * qw + ql) * 4;
-    const int rows = 256 / qw;
-    const int prow = threadIdx.x / qw;
-    const bool active = ch < P.c;
-    const bool is_elu = ch < P.c_elu;                       // (c_elu is a multiple of 4: a quad never straddles the boundary)
-    float2 w01[18], w23[18];                                // (W[j][ch], W[j][ch+1]), (W[j][ch+2], W[j][ch+3])
+__global__ void __launch_bounds__(HF_THREADS, 2) head_dgrad_elu_kernel(const __grid_constant__ HeadFusedParams P) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int gid = lane >> 2, tid = lane & 3;              // MMA fragment coordinates: row group / thread in group
+    const int chunk0 = blockIdx.y * 64;                     // first slab channel of this block's 64-channel chunk
+    const int ch0 = chunk0 + tid * 16;                      // this thread's 16 contiguous channels
+    // B fragments (Wz^T, bf16): n-tile t, k-step s.  Column n = gid of tile t is channel chunk0 + 16*(gid>>1) + 2*t + (gid&1).
+    uint32_t bw[8][2][2];
 #pragma unroll
-    for (int j = 0; j < 18; ++j) {
-        w01[j] = make_float2(ch < P.c ? __ldg(P.wz + (long long)ch * HZ_LD + j) : 0.f, ch + 1 < P.c ? __ldg(P.wz + (long long)(ch + 1) * HZ_LD + j) : 0.f);
-        w23[j] = make_float2(ch + 2 < P.c ? __ldg(P.wz + (long long)(ch + 2) * HZ_LD + j) : 0.f, ch + 3 < P.c ? __ldg(P.wz + (long long)(ch + 3) * HZ_LD + j) : 0.f);
-    }
-    const long long p0 = (long long)blockIdx.x * P.pix_per_block;
-    const long long p1 = p0 + P.pix_per_block < P.n_pix ? p0 + P.pix_per_block : P.n_pix;
-    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (active) {
-        for (long long p = p0 + prow; p < p1; p += rows) {
-            const uint4 *drow = reinterpret_cast<const uint4 *>(P.d9 + p * P.d9_ld);
-            const uint4 da = __ldg(drow), dbv = __ldg(drow + 1);
-            const uint32_t dc = __ldg(reinterpret_cast<const uint32_t *>(drow + 2));
-            float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (HASG) gv = __ldg(reinterpret_cast<const float4 *>(P.g + p * P.g_ld + ch));
-            uint2 ypk = make_uint2(0u, 0u);
-            if (is_elu) ypk = __ldg(reinterpret_cast<const uint2 *>(P.y16 + p * P.y_ld + ch));
-            const uint32_t dw[9] = {da.x, da.y, da.z, da.w, dbv.x, dbv.y, dbv.z, dbv.w, dc};
-            float2 a01 = make_float2(gv.x, gv.y), a23 = make_float2(gv.z, gv.w), b01 = make_float2(0.f, 0.f), b23 = b01;
+    for (int t = 0; t < 8; ++t) {
+        const int chn = chunk0 + 16 * (gid >> 1) + 2 * t + (gid & 1);
+        const float *wrow = P.wz + (long long)chn * HZ_LD;
+        const bool ok = chn < P.c;
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {                   // tap t: D9 columns (2t, 2t+1) = the two flow-gradient components
-                const float2 d = bf2_unpack(dw[t]);
-                fma2h(a01, d.x, w01[2 * t]); fma2h(b01, d.y, w01[2 * t + 1]);
-                fma2h(a23, d.x, w23[2 * t]); fma2h(b23, d.y, w23[2 * t + 1]);
+        for (int s2 = 0; s2 < 2; ++s2)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int k = s2 * 16 + r * 8 + tid * 2;
+                const float w0 = (ok && k < 18) ? __ldg(wrow + k) : 0.f, w1 = (ok && k + 1 < 18) ? __ldg(wrow + k + 1) : 0.f;
+                bw[t][s2][r] = bf2_pack(w0, w1);
             }
-            float4 v = make_float4(a01.x + b01.x, a01.y + b01.y, a23.x + b23.x, a23.y + b23.y);
-            if (is_elu) {
-                const float2 ylo = bf2_unpack(ypk.x), yhi = bf2_unpack(ypk.y);
-                v.x *= elu_grad_from_out(ylo.x); v.y *= elu_grad_from_out(ylo.y);
-                v.z *= elu_grad_from_out(yhi.x); v.w *= elu_grad_from_out(yhi.y);
-                const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-                uint2 pk;
-                pk.x = *reinterpret_cast<const uint32_t *>(&lo);
-                pk.y = *reinterpret_cast<const uint32_t *>(&hi);
-                *reinterpret_cast<uint2 *>(P.out16 + p * P.out16_ld + ch) = pk;
-                bsum.x += v.x; bsum.y += v.y; bsum.z += v.z; bsum.w += v.w;
-            } else {
-                float *dst = P.gout + p * P.gout_ld + ch;
-                dst[0] = v.x;
-                if (ch + 1 < P.c) dst[1] = v.y;
-                if (ch + 2 < P.c) dst[2] = v.z;
-                if (ch + 3 < P.c) dst[3] = v.w;
+    }
+    float bsum[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) bsum[i] = 0.f;
+    const long long n_groups = (P.n_pix + 15) >> 4;
+    const long long warps_total = (long long)gridDim.x * (HF_THREADS / 32);
+    for (long long grp = (long long)blockIdx.x * (HF_THREADS / 32) + wid; grp < n_groups; grp += warps_total) {
+        const long long pr0 = grp * 16 + gid, pr1 = pr0 + 8;   // this thread's two pixel rows
+        const bool ok0 = pr0 < P.n_pix, ok1 = pr1 < P.n_pix;
+        // A fragments: D9 rows (columns 0..31; 18.. are zero in memory)
+        uint32_t a0[4], a1[4];
+        {
+            const uint32_t *d0 = reinterpret_cast<const uint32_t *>(P.d9 + pr0 * P.d9_ld), *d1 = reinterpret_cast<const uint32_t *>(P.d9 + pr1 * P.d9_ld);
+            a0[0] = ok0 ? __ldg(d0 + tid) : 0u;      a0[1] = ok1 ? __ldg(d1 + tid) : 0u;
+            a0[2] = ok0 ? __ldg(d0 + 4 + tid) : 0u;  a0[3] = ok1 ? __ldg(d1 + 4 + tid) : 0u;
+            a1[0] = ok0 ? __ldg(d0 + 8 + tid) : 0u;  a1[1] = ok1 ? __ldg(d1 + 8 + tid) : 0u;
+            a1[2] = 0u; a1[3] = 0u;                  // columns 24..31: always zero
+        }
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {                    // two halves of 8 channels (n-tiles 4*hf .. 4*hf+3) to bound the register footprint
+            const int cb = ch0 + 8 * hf;                    // 8 contiguous channels of this thread
+            const bool any = cb < P.c;
+            const bool vec_elu = cb + 8 <= P.c_elu;         // all 8 gated (the common case)
+            // ---- loads: old gradient (fp32) and ELU outputs (bf16) of the two rows ----
+            float gv[2][8];
+            uint4 yv[2];
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const long long prow = rr ? pr1 : pr0;
+                const bool okr = (rr ? ok1 : ok0) && any;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) gv[rr][e] = 0.f;
+                yv[rr] = make_uint4(0u, 0u, 0u, 0u);
+                if (okr) {
+                    if (HASG) {
+                        if (cb + 8 <= P.c) {
+                            const float4 lo = __ldg(reinterpret_cast<const float4 *>(P.g + prow * P.g_ld + cb));
+                            const float4 hi = __ldg(reinterpret_cast<const float4 *>(P.g + prow * P.g_ld + cb + 4));
+                            gv[rr][0] = lo.x; gv[rr][1] = lo.y; gv[rr][2] = lo.z; gv[rr][3] = lo.w;
+                            gv[rr][4] = hi.x; gv[rr][5] = hi.y; gv[rr][6] = hi.z; gv[rr][7] = hi.w;
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                if (cb + e < P.c) gv[rr][e] = __ldg(P.g + prow * P.g_ld + cb + e);
+                        }
+                    }
+                    if (vec_elu) yv[rr] = __ldg(reinterpret_cast<const uint4 *>(P.y16 + prow * P.y_ld + cb));
+                    else if (cb < P.c_elu) {                // partially gated octet (c_elu is a multiple of 4): first 4 channels
+                        const uint2 y2 = __ldg(reinterpret_cast<const uint2 *>(P.y16 + prow * P.y_ld + cb));
+                        yv[rr].x = y2.x; yv[rr].y = y2.y;
+                    }
+                }
+            }
+            // ---- head term on the tensor cores: 4 n-tiles x 2 k-steps ----
+            float acc[4][4];
+#pragma unroll
+            for (int tt = 0; tt < 4; ++tt) {
+                acc[tt][0] = acc[tt][1] = acc[tt][2] = acc[tt][3] = 0.f;
+                mma_bf16_16816(acc[tt], a0, bw[4 * hf + tt][0][0], bw[4 * hf + tt][0][1]);
+                mma_bf16_16816(acc[tt], a1, bw[4 * hf + tt][1][0], bw[4 * hf + tt][1][1]);
+            }
+            if (!any) continue;
+            // acc[tt][{0,1}] = row gid, channels cb + 2*tt + {0,1};  acc[tt][{2,3}] = row gid + 8, same channels
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                if (!(rr ? ok1 : ok0)) continue;
+                const long long prow = rr ? pr1 : pr0;
+                float v[8];
+#pragma unroll
+                for (int tt = 0; tt < 4; ++tt) { v[2 * tt] = acc[tt][2 * rr] + gv[rr][2 * tt]; v[2 * tt + 1] = acc[tt][2 * rr + 1] + gv[rr][2 * tt + 1]; }
+                const uint32_t yw[4] = {yv[rr].x, yv[rr].y, yv[rr].z, yv[rr].w};
+                if (vec_elu) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int tt = 0; tt < 4; ++tt) {
+                        const float2 yy = bf2_unpack(yw[tt]);
+                        v[2 * tt] *= elu_grad_from_out(yy.x); v[2 * tt + 1] *= elu_grad_from_out(yy.y);
+                        pk[tt] = bf2_pack(v[2 * tt], v[2 * tt + 1]);
+                        bsum[8 * hf + 2 * tt] += v[2 * tt]; bsum[8 * hf + 2 * tt + 1] += v[2 * tt + 1];
+                    }
+                    *reinterpret_cast<uint4 *>(P.out16 + prow * P.out16_ld + cb) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int chn = cb + e;
+                        if (chn >= P.c) break;
+                        if (chn < P.c_elu) {
+                            const float2 yy = bf2_unpack(yw[e >> 1]);
+                            const float val = v[e] * elu_grad_from_out((e & 1) ? yy.y : yy.x);
+                            P.out16[prow * P.out16_ld + chn] = __float2bfloat16_rn(val);
+                            bsum[8 * hf + e] += val;
+                        } else {
+                            P.gout[prow * P.gout_ld + chn] = v[e];
+                        }
+                    }
+                }
             }
         }
     }
     if (P.db == nullptr) return;
-    __shared__ float4 red[256];
-    red[threadIdx.x] = bsum;
+    // column sums: reduce over the 8 row groups of the warp (lanes with equal tid), then over the block's warps in shared memory
+    __shared__ float red[64];
+    if (threadIdx.x < 64) red[threadIdx.x] = 0.f;
     __syncthreads();
-    if (prow == 0 && active && is_elu) {
-        float4 sacc = red[ql];
-        for (int r = 1; r < rows; ++r) { const float4 t = red[r * qw + ql]; sacc.x += t.x; sacc.y += t.y; sacc.z += t.z; sacc.w += t.w; }
-        atomicAdd(P.db + ch, sacc.x); atomicAdd(P.db + ch + 1, sacc.y); atomicAdd(P.db + ch + 2, sacc.z); atomicAdd(P.db + ch + 3, sacc.w);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        float sacc = bsum[i];
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 4); sacc += __shfl_xor_sync(0xffffffffu, sacc, 8); sacc += __shfl_xor_sync(0xffffffffu, sacc, 16);
+        if (gid == 0) atomicAdd(&red[tid * 16 + i], sacc);
     }
+    __syncthreads();
+    if (threadIdx.x < 64 && chunk0 + threadIdx.x < P.c_elu) atomicAdd(P.db + chunk0 + threadIdx.x, red[threadIdx.x]);
 }
 
 }  // namespace dofb
@@ -266,20 +351,17 @@ extern "C" int dofb_head_dgrad_elu_bf16(const void *d9_bf16, int d9_ld, int B, i
     P.out16 = reinterpret_cast<__nv_bfloat16 *>(out_bf16); P.out16_ld = out_ld;
     P.gout = gout; P.gout_ld = gout_ld; P.db = db;
     P.n_pix = (long long)B * h * w;
-    const int c4 = (c + 3) / 4;
-    int qw = 1;
-    while (qw < c4 && qw < 32) qw <<= 1;
-    const int stripes = (c4 + qw - 1) / qw, rows = 256 / qw;
-    long long blocks = (long long)num_sms() * 8 / stripes;
+    DOFB_CHECK_ARG((reinterpret_cast<uintptr_t>(y_bf16) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out_bf16) & 15u) == 0 && y_ld % 8 == 0 && out_ld % 8 == 0,
+                   "dofb_head_dgrad_elu_bf16: bf16 slabs must be 16-byte aligned with pitches that are multiples of 8");
+    const int chunks = (c + 63) / 64;
+    const long long n_groups = (P.n_pix + 15) / 16;
+    long long blocks = (long long)num_sms() * 2 * 2 / chunks;       // two waves of two resident blocks per SM
     if (blocks < 1) blocks = 1;
-    long long ppb = (P.n_pix + blocks - 1) / blocks;
-    if (ppb < 4 * rows) ppb = 4 * rows;
-    ppb = (ppb + rows - 1) / rows * rows;
-    blocks = (P.n_pix + ppb - 1) / ppb;
-    P.pix_per_block = ppb; P.qw = qw;
-    const dim3 grid((unsigned)blocks, stripes);
-    if (g != nullptr) head_dgrad_elu_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(P);
-    else head_dgrad_elu_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(P);
+    const long long need = (n_groups + HF_THREADS / 32 - 1) / (HF_THREADS / 32);
+    if (blocks > need) blocks = need;
+    const dim3 grid((unsigned)blocks, chunks);
+    if (g != nullptr) head_dgrad_elu_kernel<true><<<grid, HF_THREADS, 0, as_stream(stream)>>>(P);
+    else head_dgrad_elu_kernel<false><<<grid, HF_THREADS, 0, as_stream(stream)>>>(P);
     DOFB_LAUNCH_OK();
     return 0;
 }

@@ -22,6 +22,7 @@ constexpr int WL_PIX_PER_BLOCK = WL_THREADS * WL_PPT;
 
 struct WLScale {
     const float *flow, *src, *tgt;
+    const float *edge_w;         // variant B: optional [B,h,w,2] weights of the (horizontal, vertical) smoothness terms
     float *recon, *dflow, *loss4;
     int B, h, w, bw;
     float s, eps2, ac, as, lambda;
@@ -135,30 +136,39 @@ __device__ __forceinline__ void do_pixel(const WLScale &S, long long pix, float 
                 return __ldg(reinterpret_cast<const float2 *>(fb + ((long long)yy * w + xx) * 2));
             return make_float2(0.f, 0.f);
         };
+        // optional edge weights (needImageGradients, warpflow.py:148-157): element losses of the (horizontal, vertical) differences
+        // at pixel q are multiplied by edge_w[q] = (ex, ey)
+        auto EW = [&](int yy, int xx) -> float2 {
+            if (S.edge_w == nullptr) return make_float2(1.f, 1.f);
+            return __ldg(reinterpret_cast<const float2 *>(S.edge_w) + (long long)b * hw + (long long)yy * w + xx);
+        };
         const float mh = (x < w - 1) ? 1.f : 0.f, mv = (y < h - 1) ? 1.f : 0.f;
         const float2 Fr = F2(y, x + 1), Fd = F2(y + 1, x);
         const float hU = mh * (fu_raw - Fr.x), hV = mh * (fv_raw - Fr.y);
         const float vU = mv * (fu_raw - Fd.x), vV = mv * (fv_raw - Fd.y);
+        const float2 e0 = EW(y, x);
         if (inside) {
-            acc.u += charb(hU, S.eps2, S.as) + charb(vU, S.eps2, S.as);
-            acc.v += charb(hV, S.eps2, S.as) + charb(vV, S.eps2, S.as);
+            acc.u += e0.x * charb(hU, S.eps2, S.as) + e0.y * charb(vU, S.eps2, S.as);
+            acc.v += e0.x * charb(hV, S.eps2, S.as) + e0.y * charb(vV, S.eps2, S.as);
         }
         if (want_grad) {
             float gU = 0.f, gV = 0.f;
             if (inside) {
-                gU += mh * charb_grad(hU, S.eps2, S.as) + mv * charb_grad(vU, S.eps2, S.as);
-                gV += mh * charb_grad(hV, S.eps2, S.as) + mv * charb_grad(vV, S.eps2, S.as);
+                gU += e0.x * mh * charb_grad(hU, S.eps2, S.as) + e0.y * mv * charb_grad(vU, S.eps2, S.as);
+                gV += e0.x * mh * charb_grad(hV, S.eps2, S.as) + e0.y * mv * charb_grad(vV, S.eps2, S.as);
             }
             const bool rows_in = (y >= S.bw) && (y < h - S.bw), cols_in = (x >= S.bw) && (x < w - S.bw);
             if (x >= 1 && rows_in && (x - 1 >= S.bw) && (x - 1 < w - S.bw)) {     // h[y,x-1] = F[y,x-1]-F[y,x]
                 const float2 Fl = F2(y, x - 1);
-                gU -= charb_grad(Fl.x - fu_raw, S.eps2, S.as);
-                gV -= charb_grad(Fl.y - fv_raw, S.eps2, S.as);
+                const float el = EW(y, x - 1).x;
+                gU -= el * charb_grad(Fl.x - fu_raw, S.eps2, S.as);
+                gV -= el * charb_grad(Fl.y - fv_raw, S.eps2, S.as);
             }
             if (y >= 1 && cols_in && (y - 1 >= S.bw) && (y - 1 < h - S.bw)) {     // v[y-1,x] = F[y-1,x]-F[y,x]
                 const float2 Ft = F2(y - 1, x);
-                gU -= charb_grad(Ft.x - fu_raw, S.eps2, S.as);
-                gV -= charb_grad(Ft.y - fv_raw, S.eps2, S.as);
+                const float et = EW(y - 1, x).y;
+                gU -= et * charb_grad(Ft.x - fu_raw, S.eps2, S.as);
+                gV -= et * charb_grad(Ft.y - fv_raw, S.eps2, S.as);
             }
             du += S.gu * gU * S.inv_nflow;
             dv += S.gv * gV * S.inv_nflow;
@@ -307,6 +317,9 @@ extern "C" int dofb_warp_loss(int n_scales, const dofb_loss_scale *scales, void 
         DOFB_CHECK_ARG(s.variant == 0 || s.variant == 1, "dofb_warp_loss: scale %d bad variant %d", i, s.variant);
         WLScale &d = P.sc[i];
         d.flow = s.flow; d.src = s.src; d.tgt = s.tgt; d.recon = s.recon; d.dflow = s.dflow; d.loss4 = s.loss4;
+        d.edge_w = s.variant == 1 ? s.edge_w : nullptr;
+        DOFB_CHECK_ARG(s.edge_w == nullptr || (s.variant == 1 && (reinterpret_cast<uintptr_t>(s.edge_w) & 7u) == 0),
+                       "dofb_warp_loss: scale %d: edge weights need variant B and 8-byte alignment", i);
         d.B = s.B; d.h = s.h; d.w = s.w;
         // border width: ceil(h * 0.1) evaluated like numpy does (double), flyingChairsWrapFlow.py:764-766
         d.bw = (int)ceil((double)s.h * 0.1);

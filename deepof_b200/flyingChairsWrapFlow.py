@@ -24,12 +24,12 @@ def _wl(device):
 
 class _LossInterpFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, flows, inputs, outputs, epsilon, alpha_c, alpha_s, lambda_smooth, flow_scale, variant):
+    def forward(ctx, flows, inputs, outputs, epsilon, alpha_c, alpha_s, lambda_smooth, flow_scale, variant, edge_w=None):
         flows, inputs, outputs = flows.contiguous(), inputs.contiguous(), outputs.contiguous()
         loss4 = torch.empty(4, dtype=torch.float32, device=flows.device)
         recon = torch.empty_like(inputs)
         cfg = dict(flow_scale=flow_scale, epsilon=epsilon, alpha_c=alpha_c, alpha_s=alpha_s, lambda_smooth=lambda_smooth,
-                   variant=variant)
+                   variant=variant, edge_w=edge_w)
         _wl(flows.device)([dict(flow=flows, src=inputs, tgt=outputs, recon=recon, dflow=None, loss4=loss4, **cfg)])
         ctx.save_for_backward(flows, inputs, outputs)
         ctx.cfg = cfg
@@ -46,12 +46,12 @@ class _LossInterpFn(torch.autograd.Function):
         scratch = torch.empty(4, dtype=torch.float32, device=flows.device)
         _wl(flows.device)([dict(flow=flows, src=inputs, tgt=outputs, recon=None, dflow=dflow, loss4=scratch,
                                 g_charb=g[0] + g[1], g_u=g[0] * lam + g[2], g_v=g[0] * lam + g[3], **cfg)])
-        return dflow, None, None, None, None, None, None, None, None
+        return dflow, None, None, None, None, None, None, None, None, None
 
 
-def _loss_interp(flows, inputs, outputs, epsilon, alpha_c, alpha_s, lambda_smooth, flow_scale, variant):
+def _loss_interp(flows, inputs, outputs, epsilon, alpha_c, alpha_s, lambda_smooth, flow_scale, variant, edge_w=None):
     t, c, u, v, recon = _LossInterpFn.apply(flows, inputs, outputs, float(epsilon), float(alpha_c), float(alpha_s),
-                                            float(lambda_smooth), float(flow_scale), variant)
+                                            float(lambda_smooth), float(flow_scale), variant, edge_w)
     return dict(zip(_KEYS, (t, c, u, v))), recon
 
 

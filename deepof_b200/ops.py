@@ -383,14 +383,19 @@ class WarpLoss:
             if tuple(src.shape) != (B, h, w, 3) or tuple(tgt.shape) != (B, h, w, 3):
                 raise DeepOFError(f"loss_interp: inputs/outputs must be [B,h,w,3] matching the flow {tuple(flow.shape)}")
             recon, dflow = s.get("recon"), s.get("dflow")
+            ew = s.get("edge_w")
+            if ew is not None:
+                _req(ew, "edge_w")
+                if tuple(ew.shape) != (B, h, w, 2) or int(s.get("variant", 0)) != 1:
+                    raise DeepOFError("loss_interp: edge weights must be [B,h,w,2] and need the variant-B loss")
             arr[i] = LossScale(flow.data_ptr(), src.data_ptr(), tgt.data_ptr(),
                                recon.data_ptr() if recon is not None else None,
                                dflow.data_ptr() if dflow is not None else None,
                                s["loss4"].data_ptr(), B, h, w, float(s["flow_scale"]),
                                float(s["epsilon"]), float(s["alpha_c"]), float(s["alpha_s"]), float(s["lambda_smooth"]),
                                float(s.get("g_charb", 1.0)), float(s.get("g_u", 1.0)), float(s.get("g_v", 1.0)),
-                               int(s.get("variant", 0)))
-            keep.append((flow, src, tgt, recon, dflow))
+                               int(s.get("variant", 0)), ew.data_ptr() if ew is not None else None)
+            keep.append((flow, src, tgt, recon, dflow, ew))
         lib = _lib.load()
         need = lib.dofb_warp_loss_workspace_bytes(n, arr)
         if self.ws is None or self.ws.numel() < need:
@@ -398,3 +403,68 @@ class WarpLoss:
         base = self.ws.data_ptr()
         off = (-base) % 256
         check(lib.dofb_warp_loss(n, arr, base + off, self.ws.numel() - off, _stream()))
+
+
+def _workspace(cache: dict, key, nbytes: int, device) -> torch.Tensor:
+    ws = cache.get(key)
+    if ws is None or ws.numel() < nbytes + 256:
+        ws = cache[key] = torch.zeros(int(nbytes) + 256, dtype=torch.uint8, device=device)
+    return ws
+
+
+_ws_cache: dict = {}
+
+
+def edge_weights(img: torch.Tensor) -> torch.Tensor:
+    """[B,h,w,2] edge weights of the edge-aware smoothness (version1/model/warpflow.py:91-116) for ``img`` [B,h,w,3] (dofb_edge_weights)."""
+    _req(img, "img")
+    B, h, w, c = img.shape
+    if c != 3:
+        raise DeepOFError("edge_weights: expected [B,h,w,3]")
+    lib = _lib.load()
+    need = lib.dofb_edge_weights_workspace_bytes(B, h, w)
+    ws = _workspace(_ws_cache, ("edge", str(img.device)), need, img.device)
+    base = ws.data_ptr()
+    off = (-base) % 256
+    out = torch.empty(B, h, w, 2, dtype=torch.float32, device=img.device)
+    check(lib.dofb_edge_weights(img.data_ptr(), B, h, w, out.data_ptr(), base + off, ws.numel() - off, _stream()))
+    return out
+
+
+def flow_stencil(delta_weights) -> "_lib.FlowStencil":
+    """Non-zero entries of a dense [3,3,Cf,Cf] smoothness constant (deltaWeights["FlowDeltaWeights"], sintelWrapFlow.py:378) as the
+    sparse stencil dofb_warp_loss_multi takes: out[p, cout] += w * in[p + (kh-1, kw-1), cin]."""
+    dw = torch.as_tensor(delta_weights, dtype=torch.float32).cpu()
+    if dw.dim() != 4 or tuple(dw.shape[:2]) != (3, 3) or dw.shape[2] != dw.shape[3]:
+        raise DeepOFError(f"FlowDeltaWeights must be [3,3,Cf,Cf], got {tuple(dw.shape)}")
+    nz = dw.nonzero().tolist()
+    if len(nz) > 64:
+        raise DeepOFError(f"FlowDeltaWeights has {len(nz)} non-zero entries; the CUDA stencil holds at most 64")
+    st = _lib.FlowStencil()
+    st.n = len(nz)
+    for i, (kh, kw, cin, cout) in enumerate(nz):
+        st.e[i].dy, st.e[i].dx, st.e[i].cin, st.e[i].cout, st.e[i].w = kh - 1, kw - 1, cin, cout, float(dw[kh, kw, cin, cout])
+    return st
+
+
+def warp_loss_multi(flow, frames, stencil, flow_scale, epsilon, alpha_c, alpha_s, lambda_smooth, g=(1.0, 1.0, 1.0), want_recon=True,
+                    want_grad=True):
+    """sintelWrapFlow.loss_interp_multi forward + d/dflow (dofb_warp_loss_multi) -> (loss4 [4], recon or None, dflow or None)."""
+    _req(flow, "flow"); _req(frames, "frames")
+    B, h, w, cf = flow.shape
+    if frames.shape[:3] != flow.shape[:3] or frames.shape[3] % 3 or cf != 2 * (frames.shape[3] // 3 - 1) or cf < 2:
+        raise DeepOFError(f"loss_interp_multi: flows {tuple(flow.shape)} do not match inputs {tuple(frames.shape)} (3T image and 2(T-1) flow channels)")
+    P = cf // 2
+    lib = _lib.load()
+    need = lib.dofb_warp_loss_multi_workspace_bytes(B, h, w)
+    ws = _workspace(_ws_cache, ("multi", str(flow.device)), need, flow.device)
+    base = ws.data_ptr()
+    off = (-base) % 256
+    loss4 = torch.empty(4, dtype=torch.float32, device=flow.device)
+    recon = torch.empty(B, h, w, 3 * P, dtype=torch.float32, device=flow.device) if want_recon else None
+    dflow = torch.empty_like(flow) if want_grad else None
+    check(lib.dofb_warp_loss_multi(flow.data_ptr(), frames.data_ptr(), recon.data_ptr() if recon is not None else None,
+                                   dflow.data_ptr() if dflow is not None else None, loss4.data_ptr(), B, h, w, P, float(flow_scale),
+                                   float(epsilon), float(alpha_c), float(alpha_s), float(lambda_smooth), float(g[0]), float(g[1]), float(g[2]),
+                                   C.byref(stencil), base + off, ws.numel() - off, _stream()))
+    return loss4, recon, dflow

@@ -3,14 +3,17 @@ from __future__ import annotations
 
 from .flyingChairsWrapFlow import _loss_interp
 from ._lib import DeepOFError
+from . import ops
 
 
 def loss_interp(flows, inputs, outputs, epsilon, alpha_c, alpha_s, lambda_smooth, flow_scale, deltaWeights=None):
-    """version1/model/warpflow.loss_interp (warpflow.py:4-173) with needMask=True and
-    needImageGradients=False, the values version1/model/Flownet.py:71-84 passes."""
+    """version1/model/warpflow.loss_interp (warpflow.py:4-173) with needMask=True (the value version1/model/Flownet.py:71-73 passes).
+
+    ``deltaWeights["needImageGradients"]`` (default False, Flownet.py:84) switches the edge-aware smoothness on (:91-116,148-157): the
+    element-wise smoothness losses are weighted by 1 - |Sobel(gray(inputs))| / max; the Sobel filters themselves are fixed constants
+    of the reference (Flownet.py:87-92) and are baked into the kernel."""
     dw = deltaWeights or {}
     if not dw.get("needMask", True):
         raise DeepOFError("loss_interp: needMask=False is not implemented on the CUDA path")
-    if dw.get("needImageGradients", False):
-        raise DeepOFError("loss_interp: needImageGradients=True (edge-aware smoothness) is not implemented yet (SURVEY.md 8f.4)")
-    return _loss_interp(flows, inputs, outputs, epsilon, alpha_c, alpha_s, lambda_smooth, flow_scale, 1)
+    edge_w = ops.edge_weights(inputs.contiguous()) if dw.get("needImageGradients", False) else None
+    return _loss_interp(flows, inputs, outputs, epsilon, alpha_c, alpha_s, lambda_smooth, flow_scale, 1, edge_w=edge_w)

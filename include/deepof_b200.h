@@ -80,6 +80,9 @@ typedef struct dofb_loss_scale {
      * For objective = weight * total they are {weight, weight*lambda, weight*lambda}. */
     float g_charb, g_u, g_v;
     int variant;         /* 0 = A (legacy), 1 = B (clean) */
+    /* variant B only, may be NULL: [B,h,w,2] edge weights (dofb_edge_weights) multiplying the element-wise smoothness losses of the
+     * horizontal / vertical flow differences -- needImageGradients = True of version1/model/warpflow.py:148-157 */
+    const float *edge_w;
 } dofb_loss_scale;
 
 /* bytes of scratch needed by dofb_warp_loss for these scales */
@@ -87,6 +90,30 @@ size_t dofb_warp_loss_workspace_bytes(int n_scales, const dofb_loss_scale *scale
 /* All scales in ONE launch (plus one tiny finalisation handled in-kernel by the
  * last block); deterministic fixed-order reduction. */
 int dofb_warp_loss(int n_scales, const dofb_loss_scale *scales, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Edge weights of the edge-aware smoothness (version1/model/warpflow.py:91-116): every image of the batch is stretched to 0..255 with
+ * its own min/max, truncated, converted to grayscale (0.2989, 0.5870, 0.1140 on channels 0,1,2), filtered with the 3x3 Sobel pair
+ * (SAME zero padding); edge_w[b,y,x,{0,1}] = 1 - |g_{x,y}| / max over the batch of |g_{x,y}|.   img: [B,h,w,3]. */
+size_t dofb_edge_weights_workspace_bytes(int B, int h, int w);
+int dofb_edge_weights(const float *img, int B, int h, int w, float *edge_w /* [B,h,w,2] */, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Multi-frame warp + loss: sintelWrapFlow.loss_interp_multi (sintelWrapFlow.py:492-630), forward and d/dflow in one pass.
+ *   frames [B,h,w,3(P+1)]: P+1 frames stacked on the channel axis; flow [B,h,w,2P]: one (U,V) pair per consecutive frame pair;
+ *   reconstruction channel c < 3P = frame c/3 + 1 warped by flow pair c/3, compared with channel c of `frames` (:544-581);
+ *   smoothness = 3x3 SAME conv of the SCALED flows with the constant deltaWeights["FlowDeltaWeights"] [3,3,2P,2P], given here as its
+ *   non-zero entries (out[p, cout] += w * in[p + (dy,dx), cin]); smoothness mask (even channels: last column, odd: last row) and border mask
+ *   before the pow; even channels -> U_loss, odd -> V_loss; all three terms divided by N = B * 3P * (h-2bw)(w-2bw).
+ *   g_* as in dofb_loss_scale.  recon [B,h,w,3P] and dflow [B,h,w,2P] may be NULL. */
+#define DOFB_STENCIL_MAX 64
+typedef struct dofb_flow_stencil {
+    int n;
+    struct { int dy, dx, cin, cout; float w; } e[DOFB_STENCIL_MAX];
+} dofb_flow_stencil;
+size_t dofb_warp_loss_multi_workspace_bytes(int B, int h, int w);
+int dofb_warp_loss_multi(const float *flow, const float *frames, float *recon, float *dflow, float *loss4 /* [4] */, int B, int h, int w,
+                         int n_pairs, float flow_scale, float epsilon, float alpha_c, float alpha_s, float lambda_smooth, float g_charb,
+                         float g_u, float g_v, const dofb_flow_stencil *stencil, void *workspace /* 256-byte aligned */,
+                         size_t workspace_bytes, void *stream);
 
 /* ---- convolution family (implicit GEMM) ---------------------------------- */
 /* Replaces: slim.conv2d / slim.conv2d_transpose (+BiasAdd +Elu) and their TF

@@ -149,3 +149,94 @@ def loss_interp_B(flows, inputs, outputs, epsilon, alpha_c, alpha_s, lambda_smoo
 def loss_interp(flows, inputs, outputs, epsilon, alpha_c, alpha_s, lambda_smooth, flow_scale, deltaWeights=None, variant="A"):
     fn = loss_interp_A if variant == "A" else loss_interp_B
     return fn(flows, inputs, outputs, epsilon, alpha_c, alpha_s, lambda_smooth, flow_scale, deltaWeights)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Edge-aware smoothness: version1/model/warpflow.py:91-116,148-157 (needImageGradients=True)
+# ---------------------------------------------------------------------------------------------------------------------
+SOBEL_X = [[-1.0, 0.0, 1.0], [-2.0, 0.0, 2.0], [-1.0, 0.0, 1.0]]       # version1/model/Flownet.py:87-90 (sobel_y = its transpose)
+GRAY_WEIGHTS = (0.2989, 0.5870, 0.1140)                                 # tf.image.rgb_to_grayscale, applied to channels 0,1,2 as stored
+
+
+def edge_weights(inputs: torch.Tensor) -> torch.Tensor:
+    """gradientsMaskFlow [B,h,w,2] = (1 - |sobel_x|/max|sobel_x|, 1 - |sobel_y|/max|sobel_y|) of the re-quantised grayscale image.
+
+    warpflow.py:92-116: every image of the batch is stretched to 0..255 with its OWN min/max over all pixels and channels (:95-99),
+    truncated to int32 and clipped (:100), converted to grayscale (:105; TF converts int32 images through float and truncates back),
+    filtered with the 3x3 Sobel pair (depthwise, SAME zero padding, :107-108) and each response is divided by its maximum magnitude
+    over the WHOLE batch (:109-110); eta = 1 (:113).  No gradient flows into the images (placeholders)."""
+    B, h, w, C = inputs.shape
+    x = inputs.detach().double()
+    mn = x.amin(dim=(1, 2, 3), keepdim=True)
+    mx = x.amax(dim=(1, 2, 3), keepdim=True)
+    q = torch.clamp(torch.trunc(255.0 * (x - mn) / (mx - mn)), 0, 255)
+    gray = torch.trunc(q[..., 0] * GRAY_WEIGHTS[0] + q[..., 1] * GRAY_WEIGHTS[1] + q[..., 2] * GRAY_WEIGHTS[2])      # [B,h,w]
+    kx = torch.tensor(SOBEL_X, dtype=torch.float64).view(1, 1, 3, 3)
+    gx = F.conv2d(gray.unsqueeze(1), kx, padding=1)[:, 0]
+    gy = F.conv2d(gray.unsqueeze(1), kx.transpose(2, 3), padding=1)[:, 0]
+    gx = gx / gx.abs().max()
+    gy = gy / gy.abs().max()
+    return torch.stack([1.0 - gx.abs(), 1.0 - gy.abs()], dim=3).to(inputs.dtype)
+
+
+def loss_interp_B_edge(flows, inputs, outputs, epsilon, alpha_c, alpha_s, lambda_smooth, flow_scale, deltaWeights=None):
+    """warpflow.loss_interp with needMask=True and needImageGradients=True (:148-157): the element-wise smoothness losses of U and V
+    ([h-delta, v-delta] channels) are multiplied by gradientsMaskFlow before the border mask."""
+    B, h, w, C = inputs.shape
+    scaled = flows * flow_scale
+    recon = warp(scaled, outputs)
+    charb, n_valid = photometric(recon, inputs, epsilon, alpha_c)
+    fpad = F.pad(flows, (0, 0, 0, 1, 0, 1))
+    hgrad = flows - fpad[:, :h, 1:w + 1, :]
+    vgrad = flows - fpad[:, 1:h + 1, :w, :]
+    sm = smoothness_mask(h, w, flows.dtype).unsqueeze(0)
+    bm = border_mask(h, w, flows.dtype).view(1, h, w, 1)
+    ew = edge_weights(inputs)
+    n_flow = n_valid / 3 * 2
+    e2 = epsilon * epsilon
+    u_delta = torch.stack([hgrad[..., 0], vgrad[..., 0]], dim=3) * sm
+    v_delta = torch.stack([hgrad[..., 1], vgrad[..., 1]], dim=3) * sm
+    u_loss = (torch.pow(u_delta ** 2 + e2, alpha_s) * ew * bm).sum() / n_flow
+    v_loss = (torch.pow(v_delta ** 2 + e2, alpha_s) * ew * bm).sum() / n_flow
+    total = charb + lambda_smooth * (u_loss + v_loss)
+    return {"total": total, "Charbonnier_reconstruct": charb, "U_loss": u_loss, "V_loss": v_loss}, recon
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Multi-frame warp / loss (SURVEY.md 8f.3): sintelWrapFlow.loss_interp_multi (sintelWrapFlow.py:492-630)
+# ---------------------------------------------------------------------------------------------------------------------
+def flow_delta_weights_multi(flow_channels: int, dtype=torch.float32) -> torch.Tensor:
+    """sintelWrapFlow.py:378: the same 18-value list poured into a [3,3,Cf,Cf] constant (row-major, remainder = last value 0)."""
+    return tf_constant_fill([float(v) for v in FLOW_DELTA_VALUES], (3, 3, flow_channels, flow_channels), dtype)
+
+
+def loss_interp_multi(flows, inputs, epsilon, alpha_c, alpha_s, lambda_smooth, flow_scale, deltaWeights=None):
+    """sintelWrapFlow.loss_interp_multi (:492-630), literal.
+
+    inputs [B,h,w,3T] (T frames stacked on channels), flows [B,h,w,2(T-1)].  Channel c < 3(T-1) of the reconstruction is channel c+3
+    (the NEXT frame) warped by flow pair 2*(c//3), 2*(c//3)+1 (:544-571) and is compared with channel c (:581).  Smoothness: dense 3x3
+    conv of the scaled flows with deltaWeights["FlowDeltaWeights"] (:606), smoothness mask then border mask BEFORE the pow (:612-613),
+    even channels -> U_loss, odd -> V_loss, both divided by the image N (:614-617).
+    Returns (lossDict, reconstructs [B,h,w,3(T-1)])."""
+    B, h, w, C = inputs.shape
+    P = C // 3 - 1
+    assert flows.shape[3] == 2 * P
+    scaled = flows * flow_scale                                       # :526
+    recs = []
+    for k in range(P):
+        recs.append(warp(scaled[..., 2 * k:2 * k + 2], inputs[..., 3 * (k + 1):3 * (k + 2)]))
+    recon = torch.cat(recs, dim=3)
+    diff = 255.0 * (recon - inputs[..., :C - 3])
+    ele = torch.pow(diff * diff + epsilon * epsilon, alpha_c)
+    bmask = border_mask(h, w, inputs.dtype).view(1, h, w, 1)
+    n_valid = float(B * (C - 3)) * float(bmask.sum().item())
+    charb = (ele * bmask).sum() / n_valid
+    wdelta = flow_delta_weights_multi(2 * P, flows.dtype) if deltaWeights is None else deltaWeights
+    fd = F.conv2d(scaled.permute(0, 3, 1, 2), wdelta.permute(3, 2, 0, 1), padding=1).permute(0, 2, 3, 1)
+    sm = smoothness_mask(h, w, flows.dtype).unsqueeze(0).repeat(1, 1, 1, P)      # [.., (masky, maskx) * P]  (:517-518)
+    clean = fd * sm * bmask
+    e2 = epsilon * epsilon
+    u_loss = torch.pow(clean[..., 0::2] ** 2 + e2, alpha_s).sum() / n_valid
+    v_loss = torch.pow(clean[..., 1::2] ** 2 + e2, alpha_s).sum() / n_valid
+    total = charb + lambda_smooth * (u_loss + v_loss)
+    return {"total": total, "Charbonnier_reconstruct": charb, "U_loss": u_loss, "V_loss": v_loss}, recon

@@ -103,7 +103,7 @@ def test_head_input_gradient_fused_with_elu(case):
     from deepof_b200 import ops
     B, h, w, C, ld, c0, c, c_elu, with_g = case
     gen = torch.Generator().manual_seed(11 + sum(case[:8]))
-    wt = torch.randn(3, 3, C, 2, generator=gen) / math.sqrt(18)
+    wt = _bf(torch.randn(3, 3, C, 2, generator=gen) / math.sqrt(18))      # (the kernel multiplies bf16 operands on the tensor cores)
     dpr = torch.randn(B, h, w, 2, generator=gen)
     g = torch.zeros(B, h, w, ld)
     g[..., :C] = torch.randn(B, h, w, C, generator=gen)
