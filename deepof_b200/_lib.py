@@ -75,6 +75,9 @@ SIGNATURES = {
     "dofb_edge_weights": (_I, [_P, _I, _I, _I, _P, _P, C.c_size_t, _P]),
     "dofb_warp_loss_multi_workspace_bytes": (C.c_size_t, [_I, _I, _I]),
     "dofb_warp_loss_multi": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _F, _F, _F, _F, _F, C.POINTER(FlowStencil), _P, C.c_size_t, _P]),
+    "dofb_decode_ppm": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _P]),
+    "dofb_decode_flo": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    "dofb_eval_flow_aee_sum": (_I, [_P, _I, _I, _I, _P, _I, _I, _F, _F, _F, _P, _P]),
     "dofb_conv_fwd": (_I, [_G, _P, _I, _P, _P, _P, _I, _I, _I, _P]),
     "dofb_conv_dgrad": (_I, [_G, _P, _I, _P, _P, _P, _I, _I, _I, _I, _P]),
     "dofb_conv_wgrad": (_I, [_G, _P, _I, _P, _I, _P, _P, _I, _P]),

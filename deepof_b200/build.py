@@ -11,7 +11,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libdeepof_b200.so"
-SOURCES = ["elementwise.cu", "warp_loss.cu", "warp_loss_ext.cu", "igemm_simt.cu", "heads.cu", "heads_tc.cu", "conv_tc.cu", "corr.cu", "capi.cu"]
+SOURCES = ["elementwise.cu", "warp_loss.cu", "warp_loss_ext.cu", "igemm_simt.cu", "heads.cu", "heads_tc.cu", "conv_tc.cu", "corr.cu", "data_path.cu", "capi.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

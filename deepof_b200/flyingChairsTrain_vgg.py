@@ -8,6 +8,7 @@ flyingChairsTrain_vgg.py:95-112,181-188), ``flyingChairsWrapFlow_vgg.VGG16(...)`
 from __future__ import annotations
 
 import numpy as np
+import torch
 
 from .flownet import VGG16Flow, VGG_LOSS_WEIGHTS, FLYINGCHAIRS_MEAN
 from .flyingChairsTrain import _StepBase, train as _train_base, LEARNING_RATE, learning_rate_at, load_deconv_weights  # noqa: F401
@@ -45,8 +46,12 @@ class train(_train_base):
         super().__init__(sample_fn, image_size=image_size, batch_size=batch_size, **kw)
 
     def _feed(self, batch, lr=None):
-        source = (np.asarray(batch[0], dtype=np.float32) - self.mean) / 255.0        # :182-183
-        target = (np.asarray(batch[1], dtype=np.float32) - self.mean) / 255.0
+        if isinstance(batch[0], torch.Tensor):               # device-decoded batches (flyingChairsLoader): pre-scale where the data is
+            mean = torch.as_tensor(self.mean, device=batch[0].device)
+            source, target = (batch[0].float() - mean) / 255.0, (batch[1].float() - mean) / 255.0
+        else:
+            source = (np.asarray(batch[0], dtype=np.float32) - self.mean) / 255.0        # :182-183
+            target = (np.asarray(batch[1], dtype=np.float32) - self.mean) / 255.0
         if self.augment_fn is not None:
             ps, pt, gs, gt = self.augment_fn(source, target)
         else:

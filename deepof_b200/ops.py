@@ -468,3 +468,36 @@ def warp_loss_multi(flow, frames, stencil, flow_scale, epsilon, alpha_c, alpha_s
                                    float(epsilon), float(alpha_c), float(alpha_s), float(lambda_smooth), float(g[0]), float(g[1]), float(g[2]),
                                    C.byref(stencil), base + off, ws.numel() - off, _stream()))
     return loss4, recon, dflow
+
+
+def decode_ppm(raw: torch.Tensor, data_off: torch.Tensor, src_hw, out_hw) -> torch.Tensor:
+    """raw: uint8 CUDA tensor with the file bytes; data_off: int64 CUDA tensor [B] (first pixel byte of each image) -> [B,oh,ow,3] BGR float."""
+    assert raw.dtype == torch.uint8 and raw.is_cuda and data_off.dtype == torch.int64 and data_off.is_cuda
+    B = data_off.numel()
+    out = torch.empty(B, out_hw[0], out_hw[1], 3, dtype=torch.float32, device=raw.device)
+    check(_lib.load().dofb_decode_ppm(raw.data_ptr(), data_off.data_ptr(), B, int(src_hw[0]), int(src_hw[1]), out.data_ptr(), int(out_hw[0]),
+                                      int(out_hw[1]), _stream()))
+    return out
+
+
+def decode_flo(raw: torch.Tensor, file_off: torch.Tensor, hw):
+    """-> ([B,h,w,2] float flow, status int tensor: non-zero = a header was not a .flo of that size)."""
+    assert raw.dtype == torch.uint8 and raw.is_cuda and file_off.dtype == torch.int64 and file_off.is_cuda
+    B = file_off.numel()
+    out = torch.empty(B, hw[0], hw[1], 2, dtype=torch.float32, device=raw.device)
+    status = torch.zeros(1, dtype=torch.int32, device=raw.device)
+    check(_lib.load().dofb_decode_flo(raw.data_ptr(), file_off.data_ptr(), B, int(hw[0]), int(hw[1]), out.data_ptr(), status.data_ptr(), _stream()))
+    return out, status
+
+
+def eval_flow_aee(flow1: torch.Tensor, gt: torch.Tensor, mult=2.0, clip=(-300.0, 250.0)) -> torch.Tensor:
+    """Average end-point error of the reference's evaluation recipe (flyingChairsTrain.py:264-266,294-296): a float64 device scalar."""
+    _req(flow1, "flow"); _req(gt, "gt")
+    B, h, w, _ = flow1.shape
+    Bg, H, W, _ = gt.shape
+    if Bg != B:
+        raise DeepOFError("eval_flow_aee: batch mismatch")
+    out = torch.zeros(1, dtype=torch.float64, device=flow1.device)
+    check(_lib.load().dofb_eval_flow_aee_sum(flow1.data_ptr(), B, h, w, gt.data_ptr(), H, W, float(mult), float(clip[0]), float(clip[1]),
+                                             out.data_ptr(), _stream()))
+    return out / float(B * H * W)

@@ -254,6 +254,21 @@ int dofb_head_dgrad_elu_bf16(const void *d9_bf16, int d9_ld, int B, int h, int w
 int dofb_adam(float *theta, const float *g, float *m, float *v, long long n,
               float lr_t, float beta1, float beta2, float epsilon, float grad_scale, void *stream);
 
+/* ---- data path either side of the step (FlyingChairs files decoded on the device, evaluation recipe) ------------------------------- */
+/* Binary P6 .ppm pixels (8-bit RGB; what cv2.imread(..., IMREAD_COLOR) reads at flyingChairsLoader.py:70-71,94-95) -> float BGR 0..255,
+ * resized like cv2.resize(img, (out_w, out_h)) (INTER_LINEAR on 8-bit data: OpenCV's 11-bit fixed-point bilinear; :76-78).
+ *   raw      : device buffer holding the file bytes of all images; data_off[b] (device) = byte offset of image b's first pixel
+ *   out      : [B,out_h,out_w,3] */
+int dofb_decode_ppm(const void *raw, const long long *data_off, int B, int src_h, int src_w, float *out, int out_h, int out_w, void *stream);
+/* Middlebury .flo (utils.readFlow, utils.py:4-21): float32 magic 202021.25, int32 w, int32 h, float32 [h][w][2]; file_off[b] (device) =
+ * byte offset of file b inside raw.  status[0] (device int) becomes non-zero when a header does not match (magic / w / h). */
+int dofb_decode_flo(const void *raw, const long long *file_off, int B, int h, int w, float *out /* [B,h,w,2] */, int *status, void *stream);
+/* Evaluation recipe of flyingChairsTrain.py:264-266,294-296 + utils.flow_ee (utils.py:64-68) in one pass:
+ * out[0] = sum over the B*H*W ground-truth pixels of | cv2.resize(clip(mult * flow, clip_lo, clip_hi), (W, H)) - gt |_2
+ * (mult = 2, clip = [-300, 250] in the reference); the caller divides by B*H*W. */
+int dofb_eval_flow_aee_sum(const float *flow /* [B,h,w,2] */, int B, int h, int w, const float *gt /* [B,H,W,2] */, int H, int W, float mult,
+                           float clip_lo, float clip_hi, double *out, void *stream);
+
 /* ---- metric ---------------------------------------------------------------- */
 /* utils.flow_ee (utils.py:64-68): out[0] = sum sqrt(du^2+dv^2), caller divides by n_pix. */
 int dofb_epe_sum(const float *flow, const float *gt, long long n_pix, double *out, void *stream);

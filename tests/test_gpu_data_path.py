@@ -1,0 +1,98 @@
+"""Device-side FlyingChairs data path: .ppm / .flo decode and the evaluation recipe against the reference's own
+host tools -- cv2.imread / cv2.resize (flyingChairsLoader.py:70-78) and utils.readFlow / utils.flow_ee (utils.py:4-21,64-68)."""
+import os
+
+import cv2
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _write_dataset(root, n, hw=(48, 64), comment=False):
+    from deepof_b200 import utils
+    data = os.path.join(root, "data")
+    os.makedirs(data, exist_ok=True)
+    rng = np.random.RandomState(5)
+    H, W = hw
+    with open(os.path.join(root, "FlyingChairs_train_val.txt"), "w") as f:
+        for i in range(n):
+            f.write("2\n" if i % 4 == 3 else "1\n")
+    flows = []
+    for i in range(n):
+        fid = "%05d" % (i + 1)
+        for k in (1, 2):
+            img = rng.randint(0, 256, (H, W, 3)).astype(np.uint8)       # RGB as stored in a P6 file
+            with open(os.path.join(data, f"{fid}_img{k}.ppm"), "wb") as f:
+                f.write(b"P6\n" + (b"# made by a test\n" if comment else b"") + b"%d %d\n255\n" % (W, H) + img.tobytes())
+        fl = (rng.randn(H, W, 2) * 5).astype(np.float32)
+        utils.writeFlow(os.path.join(data, fid + "_flow.flo"), fl)
+        flows.append(fl)
+    return data, flows
+
+
+@pytest.mark.parametrize("image_size,comment", [((48, 64), False), ((40, 56), True), ((24, 32), False)])
+def test_loader_decodes_like_cv2(tmp_path, image_size, comment):
+    from deepof_b200.flyingChairsLoader import flyingChairsLoader
+    from deepof_b200 import utils
+    data, flows = _write_dataset(str(tmp_path), 8, comment=comment)
+    ld = flyingChairsLoader(str(tmp_path), image_size, split_file=os.path.join(str(tmp_path), "FlyingChairs_train_val.txt"))
+    assert len(ld.trainList) == 6 and len(ld.valList) == 2 and ld.trainList[0] == "00001" and ld.valList[0] == "00004"
+    src, tgt, flow = ld.sampleTrain(3, 2)                                 # samples 3..5 of the train list
+    assert src.is_cuda and tuple(src.shape) == (3, image_size[0], image_size[1], 3) and tuple(flow.shape) == (3, 48, 64, 2)
+    for j, fid in enumerate(ld.trainList[3:6]):
+        for k, got in ((1, src), (2, tgt)):
+            ref = cv2.imread(os.path.join(data, f"{fid}_img{k}.ppm"), cv2.IMREAD_COLOR)
+            ref = cv2.resize(ref, (image_size[1], image_size[0]))
+            assert np.array_equal(got[j].cpu().numpy(), ref.astype(np.float32)), (fid, k)      # bit exact (8-bit fixed-point bilinear)
+        assert np.array_equal(flow[j].cpu().numpy(), utils.readFlow(os.path.join(data, fid + "_flow.flo")))
+    (vs, vt, vf), idxs = ld.sampleVal(2, 1)
+    assert list(idxs) == [0, 1] and tuple(vs.shape) == (2, image_size[0], image_size[1], 3)
+
+
+def test_bad_files_are_loud(tmp_path):
+    from deepof_b200.flyingChairsLoader import flyingChairsLoader
+    from deepof_b200 import DeepOFError
+    data, _ = _write_dataset(str(tmp_path), 4)
+    ld = flyingChairsLoader(str(tmp_path), (48, 64), split_file=os.path.join(str(tmp_path), "FlyingChairs_train_val.txt"))
+    with open(os.path.join(data, "00001_flow.flo"), "r+b") as f:
+        f.write(b"XXXX")
+    with pytest.raises(DeepOFError, match="Magic number"):
+        ld.sampleTrain(2, 1)
+    with open(os.path.join(data, "00002_img1.ppm"), "r+b") as f:
+        f.write(b"P5")
+    with pytest.raises(DeepOFError, match="P6"):
+        ld.hookTrainData([1])
+
+
+@pytest.mark.parametrize("hw,HW", [((24, 32), (48, 64)), ((20, 28), (48, 64)), ((192, 256), (384, 512))])
+def test_eval_recipe_matches_numpy_cv2(hw, HW):
+    """flows_all[0] * 2 -> clip -> cv2.resize -> utils.flow_ee (flyingChairsTrain.py:264-266,294-296)."""
+    from deepof_b200.flyingChairsLoader import evaluate_aee
+    from deepof_b200 import utils
+    g = torch.Generator().manual_seed(hw[0])
+    B = 3
+    flow1 = torch.randn(B, hw[0], hw[1], 2, generator=g) * 80.0          # some values beyond the clip range
+    gt = torch.randn(B, HW[0], HW[1], 2, generator=g) * 20.0
+    ups = []
+    for b in range(B):
+        fi = np.clip(flow1[b].numpy() * 2, -300.0, 250.0)
+        ups.append(cv2.resize(fi, (HW[1], HW[0]))[None])
+    want = utils.flow_ee(np.concatenate(ups, axis=0), gt.numpy())
+    got = evaluate_aee(flow1.cuda(), gt.cuda())
+    assert abs(got - want) < 1e-5 * max(1.0, want)
+    assert abs(utils.flow_ee(torch.from_numpy(np.concatenate(ups, axis=0)).cuda(), gt.cuda()) - want) < 1e-5 * max(1.0, want)
+
+
+def test_train_class_runs_from_a_dataset_directory(tmp_path):
+    """deepOF_fc.deepOF(data_path) end to end on a miniature data set: loader -> pre-scaling -> 4-feed VGG16 step (deepOF_fc.py:5-7)."""
+    from deepof_b200 import deepOF_fc
+    _write_dataset(str(tmp_path), 8, hw=(64, 96))
+    os.chdir(str(tmp_path))                               # the reference looks the split file up in the working directory
+    deepOF_fc.IMAGE_SIZE[:] = [64, 96]
+    try:
+        t = deepOF_fc.deepOF(str(tmp_path), batch_size=2, max_iters=2, math_mode="fp32", display=1)
+    finally:
+        deepOF_fc.IMAGE_SIZE[:] = [320, 448]
+    assert t.step.engine.t == 2 and np.isfinite(t.step.last_loss())
