@@ -27,11 +27,30 @@ METRIC = "FlyingChairs 384x512 training-step pairs/sec"
 UNIT = "pairs/s"
 H, W = 384, 512
 PER_GPU_BATCH = 32          # BASELINE.json configs[1]: FlowNetS training, batch=32, 1xB200
-TRAIN_GFLOP_PER_PAIR = None  # computed from the layer list below
+
+# BASELINE.json configs[1..4].  "weak": fixed per-GPU batch; "strong": fixed GLOBAL batch split over the ranks.
+CONFIGS = {
+    "flownets32": dict(baseline_config=1, model="flownets", hw=(384, 512), batch=32, scaling="weak", variant="A",
+                       what="FlowNetS training (fwd+bwd+Adam), synthetic FlyingChairs 384x512"),
+    "flownetc32": dict(baseline_config=2, model="flownetc", hw=(384, 512), batch=32, scaling="weak", variant="A",
+                       what="FlowNetC (correlation cost-volume) training, synthetic FlyingChairs 384x512"),
+    "guided64x8": dict(baseline_config=3, model="flownetc", hw=(384, 512), batch=64, scaling="strong", variant="B",
+                       what="FlowNetC guided: warp + photometric loss variant B (flyingChairsWrapFlow_vgg / version1 warpflow), global batch 64"),
+    "sintel16x8": dict(baseline_config=4, model="flownets", hw=(448, 1024), batch=16, scaling="strong", variant="A", sintel=True,
+                       what="Sintel fine-tune shape 448x1024 (436 padded), sintelTrain.py hyper-parameters, global batch 16"),
+}
+
+
+def config_kwargs(cfg):
+    """Engine keyword arguments of a config (reference constants: sintelWrapFlow.py:773, sintelTrain.py:50-53,180)."""
+    if cfg.get("sintel"):
+        from deepof_b200.flownet import SINTEL_MEAN
+        return dict(mean=SINTEL_MEAN, hyper=dict(epsilon=1e-4, alpha_c=0.3, alpha_s=0.3, lambda_smooth=0.0)), [16, 8, 4, 4, 2, 1]
+    return {}, [16, 8, 4, 2, 1, 1]
 
 
 # ----------------------------------------------------------------------------- workload arithmetic
-def layer_flops(B: int, model: str = "flownets"):
+def layer_flops(B: int, model: str = "flownets", H: int = H, W: int = W):
     """Algorithmic FLOPs per launch tag (2*M*N*K of the implicit GEMM), DESIGN.md 'kernels'."""
     from deepof_b200.flownet import TOWER, REFINE
     fl = {}
@@ -76,7 +95,7 @@ def layer_flops(B: int, model: str = "flownets"):
     return fl
 
 
-def layer_bytes(B: int, n_param_floats: int, lean: bool = False):
+def layer_bytes(B: int, n_param_floats: int, lean: bool = False, H: int = H, W: int = W):
     """Algorithmic HBM bytes for the bandwidth-bound launches.  lean bf16 engine: the heads read the bf16 feature maps
     (2 B per channel) and move the 20-float Z map / the 64-column bf16 D9 map once each way."""
     by = {}
@@ -211,7 +230,7 @@ def run_reference(args, rank, world):
         return
     sample = 2
     steps = max(1, min(args.steps, 20))
-    warm = max(1, min(args.warmup, 2))
+    warm = max(1, min(args.warmup, 3))
     cb, mean = cpu_step_rate(sample, steps, warm)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -227,225 +246,299 @@ def run_reference(args, rank, world):
 
 
 # ----------------------------------------------------------------------------- GPU arm
-def run_ours(args, rank, local_rank, world):
+def _barrier(world):
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def measure(cfg_name, math_mode, per_gpu_batch, steps, warmup, rank, local_rank, world, want_clocks=False, want_profile=False):
+    """One training configuration: W warm-up + K timed device-resident steps (`value`), then the same through TrainStep.run with pinned-host
+    inputs (`e2e`); times are CUDA events, max over ranks.  Returns a dict (rank 0: incl. the per-launch roofline breakdown)."""
     import torch
     import torch.distributed as dist
     from deepof_b200 import _lib
-    from deepof_b200.flyingChairsTrain import TrainStep, WEIGHT_L
+    from deepof_b200.flyingChairsTrain import TrainStep
     from deepof_b200.synth import make_pairs
-
-    torch.cuda.set_device(local_rank)
+    cfg = CONFIGS[cfg_name]
+    Hc, Wc = cfg["hw"]
+    kw, weights = config_kwargs(cfg)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    B = args.batch
     lib = _lib.load()
-    step = TrainStep(B, (H, W), device=dev, math_mode=args.math, distributed=world > 1, tc_wgrad=(args.math != "fp32"),
-                     model=args.model, variant=args.variant)
+    B = per_gpu_batch
+    step = TrainStep(B, (Hc, Wc), device=dev, math_mode=math_mode, distributed=world > 1, tc_wgrad=(math_mode != "fp32"),
+                     model=cfg["model"], variant=cfg["variant"], **kw)
     eng = step.engine
-    # two different synthetic batches per rank, alternated (working set per step ~3 GB >> 126 MB L2)
+    # two different synthetic batches per rank, alternated (working set per step >> 126 MB L2)
     batches = []
     for j in range(2):
-        s, t, _ = make_pairs(B, H, W, seed=1000 * rank + j)
-        batches.append((s.pin_memory(), t.pin_memory(), s.to(dev), t.to(dev)))
+        s_, t_, _ = make_pairs(B, Hc, Wc, seed=1000 * rank + j)
+        batches.append((s_.pin_memory(), t_.pin_memory(), s_.to(dev), t_.to(dev)))
     lr = 1.6e-5
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     def device_step(i):
-        _, _, s, t = batches[i % 2]
-        eng.train_step(s, t, WEIGHT_L, lr, allreduce=step.reducer)
+        _, _, s_, t_ = batches[i % 2]
+        eng.train_step(s_, t_, weights, lr, allreduce=step.reducer)
 
     def e2e_step(i):
-        s, t, _, _ = batches[i % 2]
-        step.run({"source_img": s, "target_img": t, "loss_weight": WEIGHT_L, "learning_rate": lr})
+        s_, t_, _, _ = batches[i % 2]
+        step.run({"source_img": s_, "target_img": t_, "loss_weight": weights, "learning_rate": lr})
         return step.last_loss(lag=1)       # D2H read of a step's loss every step (the previous step's: no device stall)
 
-    # ---- device-resident timing ("value") ----
-    for i in range(args.warmup):
+    for i in range(warmup):
         device_step(i)
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    _barrier(world)
+    sampler = ClockSampler(local_rank) if (rank == 0 and want_clocks) else None
     if sampler:
         sampler.start()
     lib.dofb_reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    _barrier(world)
     e0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         device_step(i)
     e1.record()
-    barrier()
+    _barrier(world)
     launches = int(lib.dofb_launch_count())
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler else None
     loss_dev = float(eng.total_loss().item())
-
-    # ---- end-to-end timing through the reference-facing API ("e2e") ----
-    for i in range(min(args.warmup, 3)):
+    # ---- end-to-end through the reference-facing API ----
+    for i in range(min(warmup, 3)):
         e2e_step(i)
-    barrier()
+    _barrier(world)
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    last = 0.0
-    for i in range(args.steps):
-        last = e2e_step(i)
+    for i in range(steps):
+        e2e_step(i)
     last = step.last_loss(lag=0)           # drain: the final step's loss is read inside the timed region as well
     f1.record()
-    barrier()
+    _barrier(world)
     ms_e2e = f0.elapsed_time(f1)
-
-    # ---- max over ranks ----
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     ddp_sync = None
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        # replicas must hold bit-identical parameters after every step (same broadcast start, same reduced gradients)
-        chk = eng.theta.double().sum().reshape(1)
+        # replicas must hold bit-identical parameters after every step: compare a position-weighted checksum AND the extremes
+        th = eng.theta.double()
+        idx = torch.arange(th.numel(), device=dev, dtype=torch.float64)
+        chk = torch.stack([th.sum(), (th * (1.0 + idx / th.numel())).sum(), th.abs().max()])
         lo, hi = chk.clone(), chk.clone()
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-        ddp_sync = bool((lo == hi).item())
+        ddp_sync = bool((lo == hi).all().item())
     ms, ms_e2e = float(t[0]), float(t[1])
-
-    # ---- per-launch timing for the roofline (rank 0, a few instrumented steps, CUDA events per launch) ----
-    roof, breakdown = None, None
-    if rank == 0:
+    gb = B * world
+    out = {"config": cfg_name, "math": math_mode, "per_gpu_batch": B, "global_batch": gb, "hw": [Hc, Wc],
+           "value": gb * steps / (ms * 1e-3), "ms_per_step": ms / steps, "e2e_value": gb * steps / (ms_e2e * 1e-3),
+           "e2e_ms_per_step": ms_e2e / steps, "gpu_launches": launches, "ddp_replicas_in_sync": ddp_sync, "clocks": clocks,
+           "loss_after": loss_dev, "loss_after_e2e": last, "h2d_bytes_per_step": 2 * B * Hc * Wc * 3 * 4, "lean": bool(getattr(eng, "lean", False)),
+           "n_params": eng.arena.n_true}
+    # ---- per-launch timing for the roofline (rank 0, a few instrumented LOCAL steps, CUDA events per launch) ----
+    if rank == 0 and want_profile:
         eng.profile = []
-        psteps = min(args.steps, 3)
+        psteps = min(steps, 3)
         for i in range(psteps):
-            # local steps only (no collective: the other ranks are already done)
-            eng.train_step(batches[i % 2][2], batches[i % 2][3], WEIGHT_L, lr, allreduce=None)
+            eng.train_step(batches[i % 2][2], batches[i % 2][3], weights, lr, allreduce=None)
         torch.cuda.synchronize()
         per = {}
-        for tag, a, b in eng.profile:
-            per.setdefault(tag, []).append(a.elapsed_time(b))
+        for tag, a_, b_ in eng.profile:
+            per.setdefault(tag, []).append(a_.elapsed_time(b_))
         eng.profile = None
-        avg = {k: sum(v) / len(v) * (len(v) / psteps) for k, v in per.items()}     # ms per step per tag
-        fl = layer_flops(B, args.model)
-        by = layer_bytes(B, eng.arena.n_true, getattr(eng, 'lean', False))
-        peaks = load_peaks()
-        classes = {}
-        for tag, tms in avg.items():
-            cls = tag.split(":")[0]
-            c = classes.setdefault(cls, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
-            c["ms"] += tms
-            c["flops"] += fl.get(tag, 0.0)
-            c["bytes"] += by.get(tag, 0.0)
-            c["launches"] += len(per[tag]) // psteps
-        total_ms = sum(c["ms"] for c in classes.values())
-        gemm = [k for k in classes if k.startswith("conv_") or k.startswith("deconv_")]   # (corr_* reported separately)
-        gemm_ms = sum(classes[k]["ms"] for k in gemm)
-        gemm_fl = sum(classes[k]["flops"] for k in gemm)
-        gemm_n = sum(classes[k]["launches"] for k in gemm)
-        # DRAM bytes per launch of the tcgen05 family, from the committed ncu capture of the same workload (profiles/r01_tc_traffic.json:
-        # `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over the 44 tc_* launches of one step); only valid for that workload
-        tc_traffic = None
-        tr = ROOT / "profiles" / "r01_tc_traffic.json"
-        if tr.exists() and args.math == "bf16" and args.model == "flownets" and B == PER_GPU_BATCH:
-            tc_traffic = float(json.loads(tr.read_text())["dram_bytes_per_launch"])
-        tf32 = args.math == "tf32"
-        peak = peaks["bf16_sustained"] * (0.5 if tf32 else 1.0)        # bf16 math (and the fp32 SIMT path) are divided by the bf16 peak
-        ach = gemm_fl / (gemm_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "implicit-GEMM conv family (fwd/dgrad/wgrad, conv + transposed conv), "
-                                             + {"tf32": "tcgen05 kind::tf32", "bf16": "tcgen05 kind::f16 (bf16 operands, fp32 accumulate)",
-                                                "fp32": "SIMT fp32 FFMA (parity-grade path)"}[args.math],
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})" + (" x0.5 for tf32" if tf32 else ""),
-                "traffic": tc_traffic, "traffic_source": "profiles/r01_tc_traffic.json (ncu dram bytes, average per tc_* launch)" if tc_traffic else None,
-                "share_of_step": gemm_ms / total_ms, "launches_per_step": gemm_n,
-                "avg_launch_ms": gemm_ms / max(gemm_n, 1)}
-        breakdown = []
-        for k, c in sorted(classes.items(), key=lambda kv: -kv[1]["ms"]):
-            e = {"class": k, "ms_per_step": round(c["ms"], 4), "share": round(c["ms"] / total_ms, 4), "launches": c["launches"]}
-            if c["flops"]:
-                e["tflops"] = round(c["flops"] / (c["ms"] * 1e-3) / 1e12, 3)
-            if c["bytes"]:
-                e["gbs"] = round(c["bytes"] / (c["ms"] * 1e-3) / 1e9, 1)
-                e["hbm_frac"] = round(e["gbs"] / peaks["hbm"], 4)
-            breakdown.append(e)
-        out_dir = ROOT / "gpurun_out"
-        out_dir.mkdir(exist_ok=True)
-        (out_dir / f"bench_layers_{args.model}_{args.math}_n{world}.json").write_text(json.dumps(
-            {"per_tag_ms": {k: round(v, 5) for k, v in sorted(avg.items(), key=lambda kv: -kv[1])}, "classes": breakdown}, indent=1))
+        out["per_tag_ms"] = {k: sum(v) / len(v) * (len(v) / psteps) for k, v in per.items()}
+        out["per_tag_launches"] = {k: len(v) // psteps for k, v in per.items()}
+    del step, eng, batches
+    torch.cuda.empty_cache()
+    return out
 
+
+def roofline_from(m, B):
+    """Conv-family roofline + per-class breakdown from the per-launch timings of measure(..., want_profile=True)."""
+    cfg = CONFIGS[m["config"]]
+    Hc, Wc = cfg["hw"]
+    avg = m["per_tag_ms"]
+    fl = layer_flops(B, cfg["model"], Hc, Wc)
+    by = layer_bytes(B, m["n_params"], m["lean"], Hc, Wc)
+    peaks = load_peaks()
+    classes = {}
+    for tag, tms in avg.items():
+        cls = tag.split(":")[0]
+        c = classes.setdefault(cls, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
+        c["ms"] += tms
+        c["flops"] += fl.get(tag, 0.0)
+        c["bytes"] += by.get(tag, 0.0)
+        c["launches"] += m["per_tag_launches"][tag]
+    total_ms = sum(c["ms"] for c in classes.values())
+    gemm = [k for k in classes if k.startswith("conv_") or k.startswith("deconv_")]   # (corr_* reported separately)
+    gemm_ms = sum(classes[k]["ms"] for k in gemm)
+    gemm_fl = sum(classes[k]["flops"] for k in gemm)
+    gemm_n = sum(classes[k]["launches"] for k in gemm)
+    math_mode = m["math"]
+    tf32 = math_mode == "tf32"
+    peak = peaks["bf16_sustained"] * (0.5 if tf32 else 1.0)        # bf16 math (and the fp32 SIMT path) are divided by the bf16 peak
+    ach = gemm_fl / (gemm_ms * 1e-3) / 1e12
+    # DRAM bytes per launch of the tcgen05 family from the committed ncu capture of THIS build and workload, if there is one
+    tc_traffic, tsrc = None, None
+    tr = ROOT / "profiles" / f"r02_tc_traffic_{math_mode}.json"
+    if tr.exists() and m["config"] == "flownets32" and B == PER_GPU_BATCH:
+        d = json.loads(tr.read_text())
+        tc_traffic, tsrc = float(d["dram_bytes_per_launch"]), f"profiles/{tr.name} (ncu dram__bytes_read+write, average per tc_* launch, build {d.get('build', '?')})"
+    roof = {"bound": "tensor", "kernel": "implicit-GEMM conv family (fwd/dgrad/wgrad, conv + transposed conv), "
+                                         + {"tf32": "tcgen05 kind::tf32", "bf16": "tcgen05 kind::f16 (bf16 operands, fp32 accumulate)",
+                                            "fp32": "SIMT fp32 FFMA (parity-grade path)"}[math_mode],
+            "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+            "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})" + (" x0.5 for tf32" if tf32 else ""),
+            "traffic": tc_traffic, "traffic_source": tsrc,
+            "share_of_step": gemm_ms / total_ms, "launches_per_step": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
+            "whole_step_frac": sum(fl.values()) / (m["ms_per_step"] * 1e-3) / 1e12 / peak}
+    breakdown = []
+    for k, c in sorted(classes.items(), key=lambda kv: -kv[1]["ms"]):
+        e = {"class": k, "ms_per_step": round(c["ms"], 4), "share": round(c["ms"] / total_ms, 4), "launches": c["launches"]}
+        if c["flops"]:
+            e["tflops"] = round(c["flops"] / (c["ms"] * 1e-3) / 1e12, 3)
+        if c["bytes"]:
+            e["gbs"] = round(c["bytes"] / (c["ms"] * 1e-3) / 1e9, 1)
+            e["hbm_frac"] = round(e["gbs"] / peaks["hbm"], 4)
+        breakdown.append(e)
+    return roof, breakdown
+
+
+def accuracy_block(dev, modes, train_steps=200):
+    """Oracle-anchored precision evidence (north_star: per-pixel flow error and multi-scale EPE against the reference-semantics fp32 CPU
+    forward): 8 held-out synthetic pairs (seed 1234), all six scales, on the initial weights AND on weights after `train_steps`
+    optimiser steps (non-trivial flows).  The CPU oracle runs ONLY here as the checker."""
+    import torch
+    from oracle import flownet_s as ofs
+    from deepof_b200.flownet import FlowNetS, FLOW_SCALES
+    from deepof_b200 import precision
+    from deepof_b200.flyingChairsLoader import evaluate_aee
+    from deepof_b200.synth import make_pairs
+    hb = 8
+    torch.set_num_threads(_host_cores())
+    hs, ht, hgt = make_pairs(hb, H, W, seed=1234)
+    # trained weights: the bf16 engine, 200 steps on 4 alternating synthetic batches at 10x the reference's learning rate
+    teng = FlowNetS(hb, H, W, device=dev, math_mode="bf16", seed=1, tc_wgrad=True)
+    tb = [tuple(x.to(dev) for x in make_pairs(hb, H, W, seed=500 + j)[:2]) for j in range(4)]
+    for i in range(train_steps):
+        teng.train_step(*tb[i % 4], lr=1.6e-4)
+    trained = teng.export_params()
+    del teng, tb
+    torch.cuda.empty_cache()
+    out = {"held_out_pairs": hb, "seed": 1234, "scales": 6, "trained_steps": train_steps, "tolerance": precision.TOLERANCE,
+           "reference": "fp32 CPU oracle forward (oracle/flownet_s.py, reference-semantics restatement) on the same weights and inputs"}
+    for which, params in (("init", ofs.init_params(1)), ("trained", trained)):
+        with torch.no_grad():
+            _l, flows_ref, _p, _t = ofs.forward(params, hs, ht)
+        epe_ref = evaluate_aee(flows_ref[0].to(dev), hgt.to(dev))
+        blk = {"oracle_flow_magnitude_px": [round(v, 5) for v in precision.flow_magnitude(flows_ref)], "epe_oracle": epe_ref, "modes": {}}
+        for mode in modes:
+            e = FlowNetS(hb, H, W, device=dev, math_mode=mode, seed=None, tc_wgrad=(mode != "fp32"))
+            e.load_params(params)
+            e.forward(hs.to(dev), ht.to(dev), with_grad=False)
+            flows = [e.pr[s] * FLOW_SCALES[s] for s in range(1, 7)]
+            st = precision.end_point_distance(flows, flows_ref)
+            epe = evaluate_aee(flows[0].contiguous(), hgt.to(dev))
+            blk["modes"][mode] = {"epd_mean_px": [round(m_, 7) for m_, _x in st], "epd_max_px": [round(x_, 6) for _m, x_ in st],
+                                  "epe": epe, "abs_epe_delta": abs(epe - epe_ref),
+                                  "within_tolerance": bool(precision.within(st, mode) and abs(epe - epe_ref) <= precision.TOLERANCE[mode]["epe_abs"])}
+            del e
+            torch.cuda.empty_cache()
+        out[which] = blk
+    return out
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = CONFIGS[args.config]
+    B = args.batch if args.batch else (cfg["batch"] if cfg["scaling"] == "weak" else max(1, cfg["batch"] // world))
+    main_m = measure(args.config, args.math, B, args.steps, args.warmup, rank, local_rank, world, want_clocks=True, want_profile=True)
+    # ---- the other tensor-core math mode on the same workload (the line carries both; `value` is args.math) ----
+    modes = {}
+    other_math = [] if args.no_extras else [m for m in ("tf32",) if m != args.math]
+    for mm in other_math:
+        r = measure(args.config, mm, B, max(3, min(args.steps, 5)), 3, rank, local_rank, world, want_profile=True)
+        modes[mm] = r
+    # ---- BASELINE configs[2..4] on this many GPUs (strong-scaling configs split their global batch over the ranks) ----
+    others = {}
+    if not args.no_extras:
+        for name, c in CONFIGS.items():
+            if name == args.config:
+                continue
+            if c["scaling"] == "strong" and c["batch"] % world:
+                continue
+            bo = c["batch"] if c["scaling"] == "weak" else c["batch"] // world
+            try:
+                others[name] = measure(name, args.math, bo, max(3, min(args.steps, 5)), 3, rank, local_rank, world)
+            except Exception as ex:      # a secondary configuration must not take the headline down with it
+                others[name] = {"config": name, "error": f"{type(ex).__name__}: {ex}"[:300]}
+                torch.cuda.empty_cache()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    # ---- accuracy of the benched math mode on a held-out synthetic batch (north_star: EPE within 1e-3 of the fp32 forward) ----
+    roof, breakdown = roofline_from(main_m, B)
+    out_dir = ROOT / "gpurun_out"
+    out_dir.mkdir(exist_ok=True)
+    (out_dir / f"bench_layers_{cfg['model']}_{args.math}_n{world}.json").write_text(json.dumps(
+        {"per_tag_ms": {k: round(v, 5) for k, v in sorted(main_m["per_tag_ms"].items(), key=lambda kv: -kv[1])}, "classes": breakdown}, indent=1))
+
+    def mode_entry(m):
+        e = {"value": m["value"], "ms_per_step": m["ms_per_step"], "e2e": m["e2e_value"], "unit": UNIT, "gpu_launches": m["gpu_launches"]}
+        if "per_tag_ms" in m:
+            r, _ = roofline_from(m, m["per_gpu_batch"])
+            e["roofline"] = {k: r[k] for k in ("achieved", "peak", "frac", "unit", "share_of_step", "whole_step_frac")}
+        return e
+    modes_out = {args.math: mode_entry(main_m)}
+    for mm, r in modes.items():
+        modes_out[mm] = mode_entry(r)
+    others_out = {}
+    for name, r in others.items():
+        if "error" in r:
+            others_out[name] = r
+            continue
+        c = CONFIGS[name]
+        others_out[name] = {"baseline_config": c["baseline_config"], "workload": c["what"], "scaling": c["scaling"], "hw": r["hw"],
+                            "per_gpu_batch": r["per_gpu_batch"], "global_batch": r["global_batch"], "value": r["value"], "unit": UNIT,
+                            "ms_per_step": r["ms_per_step"], "e2e": r["e2e_value"], "gpu_launches": r["gpu_launches"],
+                            "ddp_replicas_in_sync": r["ddp_replicas_in_sync"], "math": r["math"]}
+    # ---- accuracy of the math modes against the CPU oracle (rank 0, N=1 runs only: it needs the host cores) ----
     accuracy = None
-    if not args.no_accuracy:
-        from deepof_b200.flownet import FlowNetS, FlowNetC
-        from deepof_b200 import ops as _ops
-        cls = FlowNetS if args.model == "flownets" else FlowNetC
-        hb = 4
-        hs, ht, hgt = make_pairs(hb, H, W, seed=1234)
-        hs, ht, hgt = hs.to(dev), ht.to(dev), hgt.to(dev)
-        flows = {}
-        for mode in ("fp32", args.math):
-            if mode in flows:
-                continue
-            e = cls(hb, H, W, device=dev, math_mode=mode, seed=1, variant=args.variant, tc_wgrad=(mode != "fp32"))
-            e.forward(hs, ht, with_grad=False)
-            flows[mode] = (e.pr[1] * 10.0).clone()
-            del e
-        def epe(flow_s1):      # evaluation recipe of flyingChairsTrain.py:264-266,294-296: x2, clip, bilinear resize to HxW, AEE
-            f = torch.clamp(flow_s1 * 2.0, -300.0, 250.0).permute(0, 3, 1, 2)
-            f = torch.nn.functional.interpolate(f, size=(H, W), mode="bilinear", align_corners=False).permute(0, 2, 3, 1).contiguous()
-            out = torch.zeros(1, dtype=torch.float64, device=dev)
-            _ops.epe_sum(f, hgt.contiguous(), out)
-            return out.item() / (hb * H * W)
-        e32, em = epe(flows["fp32"]), epe(flows[args.math])
-        accuracy = {"held_out_pairs": hb, "epe_fp32_path": e32, "epe_benched_path": em, "abs_epe_delta": abs(em - e32),
-                    "flow_l1_mean_px": float((flows[args.math] - flows["fp32"]).abs().mean()),
-                    "flow_l1_max_px": float((flows[args.math] - flows["fp32"]).abs().max()), "tolerance": 1e-3,
-                    "note": "fp32 path == CPU oracle to 5e-7 px (tests/test_gpu_flownet.py)"}
-        torch.cuda.empty_cache()
+    if world == 1 and not args.no_accuracy and args.config == "flownets32":
+        accuracy = accuracy_block(dev, ["fp32", "tf32", "bf16"])
     # ---- the same step on the fp32 SIMT kernels (bit-auditable path), a few steps, for the record ----
     fp32_ref = None
-    if world == 1 and args.math != "fp32" and not args.no_accuracy:
-        del step, eng
-        torch.cuda.empty_cache()
-        s32 = TrainStep(B, (H, W), device=dev, math_mode="fp32", model=args.model, variant=args.variant)
-        for i in range(2):
-            s32.engine.train_step(batches[i % 2][2], batches[i % 2][3], WEIGHT_L, lr)
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        g0.record()
-        for i in range(3):
-            s32.engine.train_step(batches[i % 2][2], batches[i % 2][3], WEIGHT_L, lr)
-        g1.record()
-        torch.cuda.synchronize()
-        fp32_ref = {"math": "fp32 (SIMT FFMA kernels)", "ms_per_step": g0.elapsed_time(g1) / 3, "value": B * 3 / (g0.elapsed_time(g1) * 1e-3), "unit": UNIT}
-        del s32
-        torch.cuda.empty_cache()
+    if world == 1 and args.math != "fp32" and not args.no_accuracy and not args.no_extras:
+        r = measure(args.config, "fp32", B, 3, 2, rank, local_rank, world)
+        fp32_ref = {"math": "fp32 (SIMT FFMA kernels)", "ms_per_step": r["ms_per_step"], "value": r["value"], "unit": UNIT}
     # ---- CPU baseline on the host cores (N=1 only, bounded sample) ----
     cpu = None
     if world == 1 and not args.no_cpu:
         cpu, _ = cpu_step_rate(2, 5, 1)
-    gb = B * world
-    value = gb * args.steps / (ms * 1e-3)
-    e2e = gb * args.steps / (ms_e2e * 1e-3)
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    Hc, Wc = cfg["hw"]
+    line = {"metric": METRIC, "value": main_m["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": main_m["ms_per_step"], "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
             "dtype": {"tf32": "tf32", "bf16": "bf16", "fp32": "f32"}[args.math], "data": "synthetic",
-            "config": {"workload": f"{'FlowNetS' if args.model == 'flownets' else 'FlowNetC (correlation cost-volume)'} training "
-                                   f"(fwd+bwd+Adam), synthetic FlyingChairs {H}x{W}, batch={B} per GPU",
-                       "global_batch": gb, "parallelism": f"dp{world}",
-                       "loss_variant": "A (flyingChairsWrapFlow.loss_interp)" if args.variant == "A" else "B (flyingChairsWrapFlow_vgg / version1 warpflow)",
-                       "math": args.math, "l2": "inputs+activations per step (~3 GB) exceed the 126 MB L2; two alternating batches"},
-            "clocks": clocks,
-            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": 2 * B * H * W * 3 * 4, "d2h_bytes_per_step": 4,
+            "config": {"workload": f"{cfg['what']}, batch={B} per GPU (BASELINE.json configs[{cfg['baseline_config']}])",
+                       "name": args.config, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "loss_variant": "A (flyingChairsWrapFlow.loss_interp)" if cfg["variant"] == "A" else "B (flyingChairsWrapFlow_vgg / version1 warpflow)",
+                       "math": args.math, "schedule": "lean bf16 (bf16-only activations, tap-in-N flow heads)" if main_m["lean"] else "classic",
+                       "l2": "inputs+activations per step (~2 GB) exceed the 126 MB L2; two alternating batches"},
+            "clocks": main_m["clocks"],
+            "e2e": {"value": main_m["e2e_value"], "unit": UNIT, "ms_per_step": main_m["e2e_ms_per_step"],
+                    "h2d_bytes_per_step": main_m["h2d_bytes_per_step"], "d2h_bytes_per_step": 4,
                     "api": "deepof_b200.flyingChairsTrain.TrainStep.run(feed_dict) + last_loss(lag=1): pinned-host inputs, "
                            "H2D on a copy stream double-buffered against the previous step, loss D2H read one step late"},
-            "gpu_launches": launches, "ddp_replicas_in_sync": ddp_sync,
-            "roofline": roof, "cpu_baseline": cpu, "accuracy": accuracy, "fp32_math_path": fp32_ref, "kernel_classes": breakdown,
-            "loss_after": loss_dev, "loss_after_e2e": last}
+            "gpu_launches": main_m["gpu_launches"], "ddp_replicas_in_sync": main_m["ddp_replicas_in_sync"],
+            "roofline": roof, "cpu_baseline": cpu, "modes": modes_out, "other_configs": others_out, "accuracy": accuracy,
+            "fp32_math_path": fp32_ref, "kernel_classes": breakdown,
+            "loss_after": main_m["loss_after"], "loss_after_e2e": main_m["loss_after_e2e"]}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -458,13 +551,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--math", default=os.environ.get("DEEPOF_MATH", "bf16"), choices=["fp32", "tf32", "bf16"],
-                    help="bf16: tcgen05 kind::f16 on bf16 activation shadows + bf16 packed weights, fp32 accumulate/epilogue/master weights; tf32: tcgen05 tensor-core convolutions (TF32 operands, fp32 accumulate; EPE within 1e-3 of the fp32 path, "
-                         "checked in this run); fp32: SIMT FFMA parity path")
-    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="per-GPU batch (BASELINE config: 32)")
-    ap.add_argument("--model", default="flownets", choices=["flownets", "flownetc"], help="flownets = BASELINE configs[1]; flownetc = configs[2]")
-    ap.add_argument("--variant", default="A", choices=["A", "B"], help="loss_interp variant (A: flyingChairsWrapFlow, B: _vgg/version1)")
+                    help="bf16: tcgen05 kind::f16 on bf16 activations + bf16 packed weights, fp32 accumulate / master weights / loss / Adam "
+                         "(lean schedule); tf32: tcgen05 kind::tf32 on the fp32 buffers; fp32: SIMT FFMA parity path.  The line always carries "
+                         "the tf32 numbers as well (modes) and the oracle-anchored accuracy of all three")
+    ap.add_argument("--config", default="flownets32", choices=sorted(CONFIGS), help="BASELINE.json configuration (default: configs[1], the one the metric is quoted on)")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (default: the configuration's)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-accuracy", action="store_true", help="skip the held-out EPE check")
+    ap.add_argument("--no-accuracy", action="store_true", help="skip the oracle-anchored accuracy block")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary math mode and BASELINE configs[2..4]")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

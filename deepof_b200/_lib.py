@@ -96,7 +96,7 @@ SIGNATURES = {
     "dofb_uppr_fwd": (_I, [_P, _I, _I, _I, _P, _P, _P, _P, _I, _P]),
     "dofb_uppr_bwd": (_I, [_P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "dofb_head_wz_pack": (_I, [_I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int), _P]),
-    "dofb_head_dwz_unpack": (_I, [_I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int), _P]),
+    "dofb_head_wgrad_bf16": (_I, [_P, _I, _P, _I, _I, _I, _I, _I, _P, _P]),
     "dofb_head_tapsum": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "dofb_head_dpr9": (_I, [_P, _I, _I, _I, _P, _I, _P, _P]),
     "dofb_head_dgrad_elu_bf16": (_I, [_P, _I, _I, _I, _I, _P, _I, _I, _I, _I, _P, _I, _P, _I, _P, _I, _P, _I, _P, _P]),

@@ -16,7 +16,7 @@ int tc_conv_fwd(const dofb_conv_geom *g, const float *x, int x_ld, const float *
 int tc_conv_dgrad(const dofb_conv_geom *g, const float *dy, int dy_ld, const float *w, const float *bias, float *dx, int dx_ld,
                   int act, int accumulate, cudaStream_t st, const void *dy16 = nullptr, void *dx16 = nullptr);
 int tc_conv_wgrad(const dofb_conv_geom *g, const float *x, int x_ld, const float *dy, int dy_ld, float *dw, cudaStream_t st,
-                  const void *x16 = nullptr, const void *dy16 = nullptr);
+                  const void *x16 = nullptr, const void *dy16 = nullptr, int head_mode = 0);
 void invalidate_weight_cache();
 void enable_weight_cache(int on);
 void enable_cta_pairs(int on);
@@ -91,6 +91,14 @@ extern "C" int dofb_conv_wgrad_bf16(const dofb_conv_geom *g, const void *x_bf16,
                                     void *stream) {
     DOFB_CHECK_ARG(x_bf16 && dy_bf16 && dw && g, "dofb_conv_wgrad_bf16: null argument");
     return tc_conv_wgrad(g, nullptr, x_ld, nullptr, dy_ld, dw, as_stream(stream), x_bf16, dy_bf16);
+}
+
+// weight gradient of a flow head in tap-in-N form: dW[tap][c][n] += sum_q x[q][c] * D9[q][tap*2+n] (one pass over x on the tensor pipe)
+extern "C" int dofb_head_wgrad_bf16(const void *x_bf16, int x_ld, const void *d9_bf16, int d9_ld, int B, int h, int w, int c, float *dw,
+                                    void *stream) {
+    DOFB_CHECK_ARG(x_bf16 && d9_bf16 && dw && B > 0 && h > 0 && w > 0 && c > 0, "dofb_head_wgrad_bf16: bad argument");
+    dofb_conv_geom g = {B, h, w, c, h, w, 20, 1, 1, 1, 0, 0};
+    return tc_conv_wgrad(&g, nullptr, x_ld, nullptr, d9_ld, dw, as_stream(stream), x_bf16, d9_bf16, 1);
 }
 
 extern "C" int dofb_conv1_fwd_bf16(const dofb_conv_geom *g, const void *x_bf16, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *w,

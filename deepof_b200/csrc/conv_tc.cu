@@ -1230,6 +1230,7 @@ struct WgParams {
     int ntaps;
     int conv1, c1_kh, c1_kw;                 // first-layer mode: M = 2 filter rows x (8 pixels x 8 channels)
     int pack_g, pack_cb, ntaps_real;         // packed-M mode (ci = 32/64): M = pack_g taps x pack_cb channels
+    int head;                                // flow-head mode: 1x1 problem whose column j = tap*2 + n scatters to dW[tap][ci][n] ([3,3,CI,2])
     TapInfo taps[TC_MAX_TAPS];               // wk = canonical tap index (kh*KW + kw); conv1 mode: one entry per filter row
 };
 
@@ -1439,6 +1440,13 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 continue;
             }
             if (mrow >= P.m_valid) continue;
+            if (P.head) {                   // tap-in-N weight gradient of a flow head: straight into the canonical [3,3,CI,2] layout
+                if (j == 0) {
+#pragma unroll
+                    for (int q = 0; q < 18; ++q) atomicAdd(P.dW + ((long long)(q >> 1) * P.CI + mrow) * 2 + (q & 1), v[q]);
+                }
+                continue;
+            }
             if (!P.swap) {
                 if (n0 + j * 32 < P.n_valid)
                     atomic_add_row32(P.dW + ((long long)tap * P.CI + mrow) * P.CO + n0 + j * 32, v, min(32, P.n_valid - (n0 + j * 32)));
@@ -1493,7 +1501,7 @@ static int launch_wg(const CUtensorMap &mx, const CUtensorMap &md, const WgParam
 }
 
 int tc_conv_wgrad(const dofb_conv_geom *g, const float *x, int x_ld, const float *dy, int dy_ld, float *dw, cudaStream_t st,
-                  const void *x16, const void *dy16) {
+                  const void *x16, const void *dy16, int head_mode) {
     DOFB_CHECK_ARG(g && g->kh * g->kw <= TC_MAX_TAPS, "dofb_conv_wgrad(tensor): at most %d taps", TC_MAX_TAPS);
     DOFB_CHECK_ARG(g->stride == 1 || g->stride == 2, "dofb_conv_wgrad(tensor): stride must be 1 or 2");
     const bool bf = x16 != nullptr && dy16 != nullptr;
@@ -1505,6 +1513,9 @@ int tc_conv_wgrad(const dofb_conv_geom *g, const float *x, int x_ld, const float
     WgParams P;
     memset(&P, 0, sizeof(P));
     P.dW = dw; P.CI = g->ci; P.CO = g->co;
+    P.head = head_mode;
+    DOFB_CHECK_ARG(!head_mode || (g->kh == 1 && g->kw == 1 && g->co >= 18 && g->co <= 32 && g->ci > 64),
+                   "dofb_head_wgrad_bf16: needs a 1x1 geometry with 18..32 columns and more than 64 channels");
     // ci <= 64: several taps share one 128-row M tile (no wasted MMA rows); otherwise ci < 128 <= co swaps the operands
     P.pack_cb = (!bf && g->ci <= 32) ? 32 : 64;
     P.pack_g = g->ci <= 64 ? TC_BM / P.pack_cb : 1;

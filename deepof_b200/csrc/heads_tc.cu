@@ -7,7 +7,7 @@
 //     pr[p, n]       = bias[n] + sum_tap Z[p + off(tap), (tap, n)]        9-tap sum over a 20-float map
 // and for the weight gradient
 //     D9[q, (tap, n)] = dpr[q - off(tap), n]                   (im2col of the 2-channel flow gradient, bf16)
-//     dWz[c, (tap, n)] = sum_q X[q, c] * D9[q, (tap, n)]       one 1x1 weight-gradient GEMM, X read ONCE
+//     dW[tap, c, n]   = sum_q X[q, c] * D9[q, (tap, n)]        one 1x1 weight-gradient GEMM, X read ONCE (dofb_head_wgrad_bf16)
 // Both GEMMs run on the tcgen05 kernels of conv_tc.cu (dofb_conv_fwd_bf16 / dofb_conv_wgrad_bf16 with a 1x1 geometry); this file holds the
 // small re-layout kernels around them and the fused input-gradient kernel:
 //     g16[p, ch] = bf16( (g[p, ch] + sum_{j < 18} D9[p, j] * Wz[c0 + ch, j]) * ELU'(y16[p, ch]) )   (+ bias gradient)
@@ -22,12 +22,11 @@ constexpr int HZ_LD = 20;          // columns of Z / Wz / dWz: 9 taps x 2 output
 
 __device__ __forceinline__ void fma2h(float2 &acc, float a, float2 b) { acc = __ffma2_rn(make_float2(a, a), b, acc); }
 
-// ---- W[3,3,C,2] <-> Wz[C,20] (the canonical [1,1,C,20] layout of a 1x1 convolution), several heads per launch ----
+// ---- W[3,3,C,2] -> Wz[C,20] (the canonical [1,1,C,20] layout of a 1x1 convolution), several heads per launch ----
 constexpr int HZ_MAX_HEADS = 8;
 struct HeadZBatch { int n; const float *w[HZ_MAX_HEADS]; float *wz[HZ_MAX_HEADS]; int C[HZ_MAX_HEADS]; };
 
-// UNPACK = false: wz[c][j] = W[j>>1][c][j&1] (j < 18), 0 otherwise;   UNPACK = true: W[tap][c][n] += wz[c][tap*2+n]
-template <bool UNPACK>
+// wz[c][j] = W[j>>1][c][j&1] (j < 18), 0 otherwise
 __global__ void __launch_bounds__(256) head_wz_kernel(const __grid_constant__ HeadZBatch Bt) {
     const int k = blockIdx.y;
     const int C = Bt.C[k];
@@ -35,11 +34,7 @@ __global__ void __launch_bounds__(256) head_wz_kernel(const __grid_constant__ He
     float *__restrict__ wz = Bt.wz[k];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C * HZ_LD; i += gridDim.x * blockDim.x) {
         const int c = i / HZ_LD, j = i - c * HZ_LD;
-        if (UNPACK) {
-            if (j < 18) const_cast<float *>(w)[((long long)(j >> 1) * C + c) * 2 + (j & 1)] += wz[i];
-        } else {
-            wz[i] = j < 18 ? __ldg(w + ((long long)(j >> 1) * C + c) * 2 + (j & 1)) : 0.f;
-        }
+        wz[i] = j < 18 ? __ldg(w + ((long long)(j >> 1) * C + c) * 2 + (j & 1)) : 0.f;
     }
 }
 
@@ -67,7 +62,7 @@ __global__ void __launch_bounds__(256) head_tapsum_kernel(const float *__restric
     }
 }
 
-// ---- D9[q, tap*2 + n] = bf16(dpr[q - off(tap), n]) (columns 18.. of the 64-column rows stay zero) ; dbias[n] += sum_q dpr[q, n] ----
+// ---- D9[q, tap*2 + n] = bf16(dpr[q - off(tap), n]) (columns 18..31 are written as zeros, 32.. of the 64-column rows stay zero) ; dbias[n] += sum_q dpr[q, n] ----
 __global__ void __launch_bounds__(256) head_dpr9_kernel(const float *__restrict__ dpr, int B, int h, int w, __nv_bfloat16 *__restrict__ D9,
                                                         int d9_ld, float *__restrict__ dbias) {
     const long long n = (long long)B * h * w;
@@ -91,7 +86,8 @@ __global__ void __launch_bounds__(256) head_dpr9_kernel(const float *__restrict_
         uint4 *dst = reinterpret_cast<uint4 *>(D9 + p * d9_ld);
         dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        reinterpret_cast<uint32_t *>(dst + 2)[0] = pk[8];
+        dst[2] = make_uint4(pk[8], 0u, 0u, 0u);             // whole 32-byte sectors only (a 4-byte store would be a read-modify-write in DRAM)
+        dst[3] = make_uint4(0u, 0u, 0u, 0u);
     }
     if (dbias == nullptr) return;
     s0 = warp_sum(s0); s1 = warp_sum(s1);
@@ -283,7 +279,7 @@ __global__ void __launch_bounds__(HF_THREADS, 2) head_dgrad_elu_kernel(const __g
 
 using namespace dofb;
 
-static int head_z_launch(bool unpack, int n, const float *const *w, float *const *wz, const int *C, void *stream) {
+static int head_z_launch(int n, const float *const *w, float *const *wz, const int *C, void *stream) {
     DOFB_CHECK_ARG(n >= 0 && n <= HZ_MAX_HEADS && (n == 0 || (w && wz && C)), "dofb_head_wz: bad argument (at most %d heads per call)", HZ_MAX_HEADS);
     if (n == 0) return 0;
     HeadZBatch Bt;
@@ -295,19 +291,14 @@ static int head_z_launch(bool unpack, int n, const float *const *w, float *const
         cmax = C[i] > cmax ? C[i] : cmax;
     }
     const dim3 grid((cmax * HZ_LD + 255) / 256, n);
-    if (unpack) head_wz_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(Bt);
-    else head_wz_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(Bt);
+    head_wz_kernel<<<grid, 256, 0, as_stream(stream)>>>(Bt);
     DOFB_LAUNCH_OK();
     return 0;
 }
 
 extern "C" int dofb_head_wz_pack(int n, const float *const *w, float *const *wz, const int *C, void *stream) {
-    return head_z_launch(false, n, w, wz, C, stream);
+    return head_z_launch(n, w, wz, C, stream);
 }
-extern "C" int dofb_head_dwz_unpack(int n, float *const *dw, const float *const *dwz, const int *C, void *stream) {
-    return head_z_launch(true, n, const_cast<const float *const *>(dw), const_cast<float *const *>(dwz), C, stream);
-}
-
 extern "C" int dofb_head_tapsum(const float *z, int z_ld, int B, int h, int w, const float *bias, float *pr, void *stream) {
     DOFB_CHECK_ARG(z && bias && pr && B > 0 && h > 0 && w > 0 && z_ld >= 18 && z_ld % 2 == 0 && (reinterpret_cast<uintptr_t>(z) & 7u) == 0,
                    "dofb_head_tapsum: bad argument (Z needs >= 18 columns, an even pitch and 8-byte alignment)");

@@ -146,11 +146,7 @@ class FlowNetS:
         self.lean = self.math == MATH_BF16 and self.ARCH in ("S", "C") and os.environ.get("DOFB_LEAN", "1") != "0"
         self.arena = ParamArena(self.param_shapes(), self.device)
         self.theta = self.arena.new()
-        # gradient arena (+ in the lean engine a tail holding the [C,20] tap-in-N weight gradients of the flow heads, zeroed by the same memset)
-        head_c = [shape[2] for name, shape in self.arena.shapes.items() if name.startswith("pr") and name.endswith("weights")]
-        self._grad_store = torch.zeros(self.arena.numel + (sum(_round_up(c * 20, 64) for c in head_c) if self.lean else 0),
-                                       dtype=torch.float32, device=self.device)
-        self.grad = self._grad_store[:self.arena.numel]
+        self.grad = self.arena.new()
         self.m, self.v = self.arena.new(), self.arena.new()
         self.params = self.arena.views(self.theta)
         self.grads = self.arena.views(self.grad)
@@ -246,17 +242,13 @@ class FlowNetS:
         self.loss4 = torch.zeros(self.N_SCALES, 4, dtype=torch.float32, device=dev)
         if self.lean:
             # tap-in-N flow heads: Z maps share one flat buffer (forward is sequential), the bf16 im2col of dpr_s has one buffer per scale
-            # (its 64-column rows keep columns 18.. at zero), [C,20] weights / weight gradients per head
+            # (its 64-column rows keep columns 18.. at zero), [C,20] weights per head
             h1, w1 = self.hw[1]
             self._z_flat = torch.zeros(B * h1 * w1 * 20, dtype=torch.float32, device=dev)
             self.head_z = {s: self._z_flat[:B * hh * ww * 20].view(B, hh, ww, 20) for s, (hh, ww) in self.hw.items()}
             self.head_d9 = {s: torch.zeros(B, hh, ww, 64, dtype=torch.bfloat16, device=dev) for s, (hh, ww) in self.hw.items()}
-            self.head_wz, self.head_dwz, off = {}, {}, self.arena.numel
-            for s in range(1, self.N_SCALES + 1):
-                c = self.arena.shapes[f"pr{s}/weights"][2]
-                self.head_wz[s] = torch.zeros(1, 1, c, 20, dtype=torch.float32, device=dev)
-                self.head_dwz[s] = self._grad_store[off:off + c * 20].view(1, 1, c, 20)
-                off += _round_up(c * 20, 64)
+            self.head_wz = {s: torch.zeros(1, 1, self.arena.shapes[f"pr{s}/weights"][2], 20, dtype=torch.float32, device=dev)
+                            for s in range(1, self.N_SCALES + 1)}
 
     NEED32 = frozenset()            # activation buffers that keep an fp32 master in the lean engine
 
@@ -503,20 +495,19 @@ class FlowNetS:
             reducer.ready(min(self.arena.offsets[n + "/weights"] for n in names))
 
     def _head_wgrad_tc(self, s):
-        """dW_pr_s on the tensor pipe: D9 = bf16 im2col of dpr_s (+ bias gradient), dWz = feat_s^T . D9 (1x1 weight-gradient GEMM, feat_s read
-        once), then re-laid out into the canonical [3,3,C,2] gradient."""
+        """dW_pr_s on the tensor pipe: D9 = bf16 im2col of dpr_s (+ bias gradient), dW = feat_s^T . D9 (1x1 weight-gradient GEMM, feat_s read
+        once) accumulated straight into the canonical [3,3,C,2] gradient."""
         G = self.grads
         x, _ = self.feat[s]
         d9 = self.head_d9[s]
         self._k(f"head_dpr9:pr{s}", ops.head_dpr9, self.dpr[s], d9, G[f"pr{s}/biases"])
-        self._k(f"head_wgrad:pr{s}", ops.conv_wgrad, self._head_geom1[s], x, Slab(None, 0, 20, d9), self.head_dwz[s], None, MATH_BF16)
-        self._k(f"head_unpack:pr{s}", ops.head_dwz_unpack, [G[f"pr{s}/weights"]], [self.head_dwz[s]])
+        self._k(f"head_wgrad:pr{s}", ops.head_wgrad_tc, x, d9, G[f"pr{s}/weights"])
 
     def _backward_lean(self, reducer=None):
         """Backward of the lean bf16 engine: same order as backward(), but no kernel writes a flow head's input gradient: the pass that
         finishes each channel slab of feat_s (ELU' + bias gradient + bf16 shadow) adds it on the fly (dofb_head_dgrad_elu_bf16)."""
         P, G, mth = self.params, self.grads, self.math
-        self._k("zero_grad", self._grad_store.zero_)
+        self._k("zero_grad", self.grad.zero_)
         if reducer is not None:
             reducer.begin()
         self._head_wgrad_tc(1)

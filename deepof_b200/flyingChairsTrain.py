@@ -172,6 +172,10 @@ class train:
         self.iters_per_epoch = iters_per_epoch or max_iters
         self.max_epochs = max_epochs
 
+    def load_deconv_weights(self, var, sess=None):
+        """train.load_deconv_weights(var, sess) (flyingChairsTrain.py:78-92)."""
+        load_deconv_weights(var, sess)
+
     def _feed(self, batch, lr=None):
         d = {"source_img": batch[0], "target_img": batch[1], "loss_weight": self.WEIGHTS}
         if lr is not None:

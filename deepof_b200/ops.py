@@ -272,13 +272,11 @@ def head_wz_pack(ws, wzs):
     check(_lib.load().dofb_head_wz_pack(n, a, b, cs, _stream()))
 
 
-def head_dwz_unpack(dws, dwzs):
-    """dw[k][tap][c][n] += dwz[k][c][tap*2+n]."""
-    n = len(dws)
-    a = (C.c_void_p * n)(*[t.data_ptr() for t in dws])
-    b = (C.c_void_p * n)(*[t.data_ptr() for t in dwzs])
-    cs = (C.c_int * n)(*[int(t.shape[2]) for t in dws])
-    check(_lib.load().dofb_head_dwz_unpack(n, a, b, cs, _stream()))
+def head_wgrad_tc(x: Slab, d9, dw):
+    """dw[3,3,C,2] += weight gradient of the flow head from the bf16 feature map ``x`` and the bf16 im2col ``d9`` of dpr (dofb_head_wgrad_bf16)."""
+    _req(dw, "dw")
+    assert d9.dtype == torch.bfloat16 and d9.is_cuda and d9.is_contiguous() and tuple(d9.shape[:3]) == (x.B, x.h, x.w)
+    check(_lib.load().dofb_head_wgrad_bf16(_need16(x, "head_wgrad_tc"), x.ld, d9.data_ptr(), d9.shape[3], x.B, x.h, x.w, x.c, dw.data_ptr(), _stream()))
 
 
 def head_tapsum(z, bias, pr):

@@ -229,12 +229,13 @@ int dofb_uppr_bwd(const float *pr, const float *dy, int dy_ld, int B, int h, int
 /* ---- flow heads of the lean bf16 engine (tap-in-N form: see csrc/heads_tc.cu) --------------------------------------------
  * pr_s = conv3x3(feat_s -> 2) (flyingChairsWrapFlow.py:58,69,80,91,102,113) without any fp32 copy of feat_s:
  *   forward : wz = dofb_head_wz_pack(w)  ->  Z = dofb_conv_fwd_bf16(1x1, ci = C, co = 20, x = bf16 feat)  ->  pr = dofb_head_tapsum(Z)
- *   wgrad   : D9 = dofb_head_dpr9(dpr)   ->  dWz = dofb_conv_wgrad_bf16(1x1, ci = C, co = 20, dy = D9)  ->  dofb_head_dwz_unpack
+ *   wgrad   : D9 = dofb_head_dpr9(dpr)   ->  dofb_head_wgrad_bf16(x = bf16 feat, D9): a 1x1 weight-gradient GEMM writing the [3,3,C,2] layout
  *   dgrad   : fused into the pass that finishes the gradient of each channel slab of feat_s (dofb_head_dgrad_elu_bf16). */
 /* wz[k][c*20 + tap*2 + n] = w[k][tap][c][n] (columns 18, 19 zero): the [1,1,C,20] weights of the 1x1 form; up to 8 heads per call */
 int dofb_head_wz_pack(int n_heads, const float *const *w /* [3,3,C,2] each */, float *const *wz /* [C,20] each */, const int *C, void *stream);
-/* dw[k][tap][c][n] += dwz[k][c*20 + tap*2 + n] */
-int dofb_head_dwz_unpack(int n_heads, float *const *dw, const float *const *dwz, const int *C, void *stream);
+/* dw[tap][ch][n] += sum_q x[q][ch] * D9[q][tap*2 + n]  (x: bf16 [B,h,w,x_ld] slab of c > 64 channels; D9: dofb_head_dpr9, pitch 64) */
+int dofb_head_wgrad_bf16(const void *x_bf16, int x_ld, const void *d9_bf16, int d9_ld, int B, int h, int w, int c, float *dw /* [3,3,c,2] */,
+                         void *stream);
 /* pr[b,y,x,n] = bias[n] + sum_{kh,kw} Z[b, y+kh-1, x+kw-1, (kh*3+kw)*2 + n]  (zero outside the map) */
 int dofb_head_tapsum(const float *z, int z_ld, int B, int h, int w, const float *bias, float *pr /* [B,h,w,2] */, void *stream);
 /* D9[b,y,x,(kh*3+kw)*2 + n] = bf16(dpr[b, y-kh+1, x-kw+1, n]) (zero outside; only columns 0..17 are written); dbias[n] += sum dpr[...,n] */
