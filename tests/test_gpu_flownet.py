@@ -65,6 +65,9 @@ def test_all_52_gradients(small_case):
 
 
 def test_two_adam_steps_track_the_oracle(small_case):
+    """Two whole optimiser steps on the device against the CPU oracle + TF-form Adam (oracle/adam.py).  Adam's first steps move a weight
+    by ~lr * g / |g|: where the gradient is well conditioned (|g| above 1 % of the tensor's largest) the update must agree to a small
+    fraction of lr; entries whose gradient is rounding noise can take either sign and are only bounded."""
     from deepof_b200.flownet import FlowNetS
     c = small_case
     B, H, W = 2, 192, 256
@@ -77,15 +80,23 @@ def test_two_adam_steps_track_the_oracle(small_case):
         _t, grads, *_ = fs.loss_and_grads(params, c["src"], c["tgt"])
         opt.step(grads, lr)
         eng.train_step(c["src"].cuda(), c["tgt"].cuda(), fs.LOSS_WEIGHTS, lr)
+        n_sig = 0
         for name in params:
-            # Adam's first steps move every weight by ~lr whatever the gradient's size, so a weight whose gradient is ~0
-            # takes the sign of rounding noise.  Step 1 must agree except for such sign flips; after step 2 the ill-conditioned
-            # loss (see test_all_52_gradients) lets trajectories drift, bounded by 2*lr per step.  The optimiser kernel itself
-            # is checked exactly in test_gpu_ops.test_adam_matches_tf_form.
             d = (eng.params[name].cpu() - params[name]).abs()
-            assert d.max().item() <= 2 * lr * (it + 1) + 1e-7, (name, it, d.max().item())
+            g = grads[name].abs()
+            sig = g > 1e-2 * g.max()
+            n_sig += int(sig.sum())
+            # well-conditioned entries: same update to 2 % (step 1) / 10 % (step 2: second-moment history differs slightly) of lr
+            assert float(d[sig].max()) <= (0.02 if it == 0 else 0.10) * lr, (name, it, float(d[sig].max()) / lr)
+            assert float(d.max()) <= 2 * lr * (it + 1) + 1e-7                  # nothing moves further than Adam can move it
             if it == 0:
                 assert d.mean().item() < 0.05 * lr, (name, d.mean().item())
+        assert n_sig > 100_000                                                 # the strict bound covers a real share of the weights
+    # and the two trajectories still describe the same function: the losses after two steps agree
+    with torch.no_grad():
+        _l, _f, _p, total = fs.forward(params, c["src"], c["tgt"])
+    eng.forward(c["src"].cuda(), c["tgt"].cuda(), fs.LOSS_WEIGHTS, with_grad=False)
+    assert abs(float(eng.total_loss()) - float(total)) <= 1e-4 * abs(float(total))
 
 
 def test_golden_fixture(golden_dir):

@@ -31,6 +31,13 @@ def _buf(B, h, w, ld, c, gen):
     return t
 
 
+def _oracle_conv(x, w, b, stride, ci, co, elu=True):
+    """CPU oracle (oracle/tf_ops.py, float64) of slim.conv2d on the dense channels of a pitched buffer."""
+    from oracle import tf_ops
+    y = tf_ops.conv2d_same(x.cpu()[..., :ci].double(), w.cpu().double(), b.cpu().double() if b is not None else None, stride)
+    return tf_ops.elu(y) if elu else y
+
+
 FWD_CASES = [
     # B, H, W, ci, x_ld, co, k, s
     (2, 24, 32, 64, 128, 128, 5, 2),      # conv2-like, parity gather, asymmetric pad (1,2)
@@ -61,6 +68,10 @@ def test_tc_conv_fwd_and_dgrad_match_simt(case):
     torch.cuda.synchronize()
     assert rel(y1, y0) < TOL
     assert float(y1[..., :32].abs().max()) == 0.0
+    # ... and against the CPU oracle (not only against our own SIMT kernel)
+    want = _oracle_conv(x, w, b, s, ci, co)
+    assert rel(y1[..., 32:32 + co], want) < TOL
+    assert rel(y0[..., 32:32 + co], want) < 2e-5
     # input gradient
     dy = _buf(B, geom.oh, geom.ow, (co + 31) // 32 * 32, co, g)
     d0 = torch.full((B, H, W, x_ld), 0.25, device="cuda")
@@ -70,6 +81,10 @@ def test_tc_conv_fwd_and_dgrad_match_simt(case):
         ops.conv_dgrad(geom, ops.Slab(dy, 0, co), w, None, ops.Slab(d1, 0, ci), ops.ACT_NONE, acc, ops.MATH_TF32)
         torch.cuda.synchronize()
         assert rel(d1[..., :ci], d0[..., :ci]) < TOL, acc
+    # oracle: autograd of the TF-SAME conv (the last call above wrote the plain, non-accumulated gradient)
+    xd = torch.zeros(B, H, W, ci, dtype=torch.float64, requires_grad=True)
+    _oracle_conv(xd, w, None, s, ci, co, elu=False).backward(dy.cpu()[..., :co].double())
+    assert rel(d1[..., :ci], xd.grad) < TOL
 
 
 DECONV_CASES = [
@@ -97,6 +112,9 @@ def test_tc_deconv_fwd_and_dgrad_match_simt(case):
     ops.conv_dgrad(geom, ops.Slab(x, 0, cfeat), wt, b, ops.Slab(y1, 32, upc), ops.ACT_ELU, False, ops.MATH_TF32)
     torch.cuda.synchronize()
     assert rel(y1, y0) < TOL
+    from oracle import tf_ops
+    want = tf_ops.elu(tf_ops.conv2d_transpose_same(x.cpu()[..., :cfeat].double(), wt.cpu().double(), b.cpu().double(), 2))
+    assert rel(y1[..., 32:32 + upc], want) < TOL          # slim.conv2d_transpose restated by the CPU oracle
     dy = _buf(B, 2 * h, 2 * w, (upc + 31) // 32 * 32, upc, g)
     d0 = torch.zeros(B, h, w, fld, device="cuda")
     d1 = torch.zeros(B, h, w, fld, device="cuda")
@@ -135,6 +153,10 @@ def test_tc_wgrad_matches_simt(case):
     torch.cuda.synchronize()
     assert rel(dw1, dw0) < TOL
     assert rel(db1, db0) < 1e-4
+    # oracle: autograd of the TF-SAME conv with respect to the weights
+    wd = torch.zeros(k, k, ci, co, dtype=torch.float64, requires_grad=True)
+    _oracle_conv(x, wd, None, s, ci, co, elu=False).backward(dy.cpu()[..., :co].double())
+    assert rel(dw1, wd.grad) < TOL
 
 
 @pytest.mark.parametrize("B,H,W", [(2, 64, 128), (1, 384, 512), (3, 48, 80)])
@@ -182,6 +204,9 @@ def test_tc_correlation_matches_simt(B, h, w, md, s2):
     torch.cuda.synchronize()
     assert rel(o1[..., :D * D], o0[..., :D * D]) < TOL
     assert float((o1[..., D * D:] - 5.0).abs().max()) == 0.0          # nothing written past the D*D channels
+    from oracle import flownet_c, tf_ops
+    want = tf_ops.elu(flownet_c.correlation(f1.cpu().double(), f2.cpu().double(), md, s2))
+    assert rel(o1[..., :D * D], want) < TOL                            # the (paper-derived) CPU restatement of the cost volume
 
 
 @pytest.mark.parametrize("B,h,w,md,s2", [(2, 12, 64, 20, 2), (1, 7, 40, 20, 2), (2, 6, 128, 20, 2), (1, 5, 64, 16, 4), (1, 48, 64, 20, 2)])
