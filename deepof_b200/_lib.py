@@ -89,6 +89,7 @@ SIGNATURES = {
     "dofb_enable_weight_cache": (None, [_I]),
     "dofb_enable_cta_pairs": (None, [_I]),
     "dofb_enable_halo_tiles": (None, [_I]),
+    "dofb_enable_multiphase_halo": (None, [_I]),
     "dofb_pack_weights_batch": (_I, [_P, _I, _I, _P]),
     "dofb_head_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "dofb_head_dgrad": (_I, [_P, _I, _I, _I, _I, _P, _P, _I, _I, _P]),
@@ -104,6 +105,7 @@ SIGNATURES = {
     "dofb_epe_sum": (_I, [_P, _P, _LL, _P, _P]),
     "dofb_corr_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P]),
     "dofb_corr_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _I, _I, _P]),
+    "dofb_corr_bwd_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P]),
 }
 
 _lib = None

@@ -684,6 +684,222 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------
+// Multi-phase halo gather-GEMM: stride-2 transposed gathers with narrow N (transposed-conv forwards 4x4/2 to 32 / 64 channels, input
+// gradients of 5x5/2 and 3x3/2 convs to <= 128 channels).
+//
+// All stride^2 = 4 output phases of a transposed gather read the SAME 3 x 3 neighbourhood of the (small) source map -- every tap offset is
+// in {-1, 0, +1} -- yet the per-tap kernel above fetches a 16 KB A box per (phase, tap, channel block): 16 (4x4) or 25 (5x5) boxes per
+// channel block and 128 source pixels, which pins these layers to the chip-wide L2->SM limit at 15-35 % of the tensor peak.
+// Here a work unit is one SOURCE tile (8 x 16 pixels): per channel block ONE halo box (18 rows x 16 columns, 36 KB) lands in shared memory
+// and serves every tap of every phase (the MMA descriptor starts (oy+1)*16 + (ox+1) rows into the box, group stride 2048 B); the four
+// phases accumulate in four TMEM accumulators of BN columns (x 2: the epilogue of unit i overlaps the MMAs of unit i+1).  Weight k-blocks
+// stream through their own ring in chunks of <= 4 taps.  A crosses the L2->SM path once per channel block instead of 16-25 times.
+// Roles as above: warps 0-7 epilogue, warp 8 TMA producer, warp 9 TMEM allocator + MMA issuer.
+// ------------------------------------------------------------------------------------------------
+constexpr int MPH_A_SLOTS = 2, MPH_B_SLOTS = 4, MPH_MAX_CHUNKS = 16;
+struct MphParams {
+    float *out; __nv_bfloat16 *out16; int out_ld;
+    const float *bias;
+    int n_valid, rh, rw, B;
+    int tiles_x, tiles_y, m_tiles, n_tiles;
+    int a_coff, ncb, act, accumulate;
+    int nphase, nchunks;
+    struct Ph { int y0, x0, cnt_y, cnt_x; } ph[4];
+    struct Ck { short phase, tap0, ntaps, first; } ck[MPH_MAX_CHUNKS];
+    TapInfo taps[TC_MAX_TAPS];
+};
+
+template <int BN, bool BF>
+__global__ void __launch_bounds__(TCG_THREADS, 1)
+tc_mph_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ MphParams P) {
+    constexpr int KELEMS = BF ? 64 : 32;
+    constexpr int B_BYTES = BN * 128;                       // one tap's weight k-block
+    constexpr int HA_BYTES = TC_HALO_ROWS * 16 * 128;       // 36 KB halo box
+    constexpr int BS_BYTES = 4 * B_BYTES;                   // B slot: up to 4 taps
+    constexpr int ACC_COLS = 4 * BN, TMEM_COLS = 2 * ACC_COLS;
+    static_assert(TMEM_COLS <= 512 && BN >= 32, "four phase accumulators, double buffered");
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *smem_b = smem + MPH_A_SLOTS * HA_BYTES;
+    float *stage_f = reinterpret_cast<float *>(smem_b + MPH_B_SLOTS * BS_BYTES);
+    uint64_t *a_full = reinterpret_cast<uint64_t *>(stage_f + TCG_EPI_WARPS * 32 * 16);
+    uint64_t *a_empty = a_full + MPH_A_SLOTS;
+    uint64_t *b_full = a_empty + MPH_A_SLOTS;
+    uint64_t *b_empty = b_full + MPH_B_SLOTS;
+    uint64_t *acc_full = b_empty + MPH_B_SLOTS;
+    uint64_t *acc_empty = acc_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total = P.m_tiles * P.n_tiles;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < MPH_A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < MPH_B_SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], TCG_EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == TCG_EPI_WARPS && lane == 0) { prefetch_tmap(&map_a); prefetch_tmap(&map_b); }
+    if (warp == TCG_EPI_WARPS + 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == TCG_EPI_WARPS) {
+        if (lane == 0) {
+            int ita = 0, itb = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const int nt = t / P.m_tiles, mt = t % P.m_tiles;
+                const int tx = mt % P.tiles_x, ty = (mt / P.tiles_x) % P.tiles_y, tn = mt / (P.tiles_x * P.tiles_y);
+                const int ix0 = tx * 8, iy0 = ty * 16, n0 = nt * BN;
+                for (int cb = 0; cb < P.ncb; ++cb, ++ita) {
+                    const int sa = ita % MPH_A_SLOTS;
+                    mbar_wait(&a_empty[sa], ((ita / MPH_A_SLOTS) & 1) ^ 1);
+                    mbar_expect_tx(&a_full[sa], HA_BYTES);
+                    tma_load_4d(smem + sa * HA_BYTES, &map_a, &a_full[sa], P.a_coff + cb * KELEMS, ix0 - 1, iy0 - 1, tn);
+                    for (int c = 0; c < P.nchunks; ++c, ++itb) {
+                        const int sb = itb % MPH_B_SLOTS;
+                        const int ntp = P.ck[c].ntaps;
+                        mbar_wait(&b_empty[sb], ((itb / MPH_B_SLOTS) & 1) ^ 1);
+                        mbar_expect_tx(&b_full[sb], ntp * B_BYTES);
+                        for (int tp = 0; tp < ntp; ++tp)
+                            tma_load_2d(smem_b + sb * BS_BYTES + tp * B_BYTES, &map_b, &b_full[sb], P.taps[P.ck[c].tap0 + tp].wk + cb * KELEMS, n0);
+                    }
+                }
+            }
+        }
+    } else if (warp == TCG_EPI_WARPS + 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = BF ? make_idesc_bf16(TC_BM, BN) : make_idesc_tf32(TC_BM, BN);
+            int ita = 0, itb = 0, lt = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+                const int acc = lt & 1;
+                mbar_wait(&acc_empty[acc], ((lt >> 1) & 1) ^ 1);
+                tc_fence_after();
+                for (int cb = 0; cb < P.ncb; ++cb, ++ita) {
+                    const int sa = ita % MPH_A_SLOTS;
+                    mbar_wait(&a_full[sa], (ita / MPH_A_SLOTS) & 1);
+                    tc_fence_after();
+                    const uint32_t abuf = smem_u32(smem + sa * HA_BYTES);
+                    for (int c = 0; c < P.nchunks; ++c, ++itb) {
+                        const int sb = itb % MPH_B_SLOTS;
+                        mbar_wait(&b_full[sb], (itb / MPH_B_SLOTS) & 1);
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS + P.ck[c].phase * BN);
+                        const uint32_t bbuf = smem_u32(smem_b + sb * BS_BYTES);
+                        for (int tp = 0; tp < P.ck[c].ntaps; ++tp) {
+                            const TapInfo ti = P.taps[P.ck[c].tap0 + tp];
+                            const uint64_t da = make_desc_k128_halo(abuf, (ti.oy + 1) * 16 + (ti.ox + 1));
+                            const uint64_t db = make_desc_k128(bbuf + tp * B_BYTES);
+                            const bool first = cb == 0 && P.ck[c].first && tp == 0;
+#pragma unroll
+                            for (int kk = 0; kk < TC_BK / 8; ++kk) umma<BF>(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, !(first && kk == 0));
+                        }
+                        umma_commit(&b_empty[sb]);
+                    }
+                    umma_commit(&a_empty[sa]);
+                }
+                umma_commit(&acc_full[acc]);
+            }
+        }
+    } else {
+        // ===== epilogue: per phase the same TMEM -> shared-memory transpose -> bias / ELU / accumulate -> NHWC stores as the kernel above =====
+        constexpr int NSUB = BN / 16;
+        const int quad = warp & 3, half = warp >> 2;
+        const int r = quad * 32 + lane;
+        float4 *stg = reinterpret_cast<float4 *>(stage_f) + warp * (32 * 4);
+        const int q = lane & 3, rsub = lane >> 2;
+        const bool has32 = P.out != nullptr, has16 = P.out16 != nullptr, accum = P.accumulate != 0, elu = P.act == DOFB_ACT_ELU;
+        const bool out_al = ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0) && (P.out_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.out16) & 7) == 0);
+        int lt = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+            const int nt = t / P.m_tiles, mt = t % P.m_tiles;
+            const int tx = mt % P.tiles_x, ty = (mt / P.tiles_x) % P.tiles_y, tn = mt / (P.tiles_x * P.tiles_y);
+            const int ix = tx * 8 + (r & 7), iy = ty * 16 + (r >> 3);
+            const int n0 = nt * BN;
+            const int acc = lt & 1;
+            mbar_wait(&acc_full[acc], (lt >> 1) & 1);
+            tc_fence_after();
+            const bool colfull = n0 + BN <= P.n_valid;
+#pragma unroll 1
+            for (int ph = 0; ph < P.nphase; ++ph) {
+                const bool row_ok = ix < P.ph[ph].cnt_x && iy < P.ph[ph].cnt_y;
+                const long long my_off = row_ok ? (((long long)tn * P.rh + P.ph[ph].y0 + iy * 2) * P.rw + P.ph[ph].x0 + ix * 2) * P.out_ld : -1;
+                const bool fast = __all_sync(0xffffffffu, row_ok) && out_al && (colfull || (P.n_valid & 3) == 0);
+                long long offs[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) offs[i] = __shfl_sync(0xffffffffu, my_off, i * 8 + rsub);
+#pragma unroll 1
+                for (int j = half; j < NSUB; j += 2) {
+                    float v[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * ACC_COLS + ph * BN + j * 16), v);
+                    const int cbase = n0 + j * 16;
+                    if (cbase >= P.n_valid) continue;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        stg[lane * 4 + (c ^ ((lane >> 1) & 3))] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                    __syncwarp();
+                    const int col = cbase + q * 4;
+                    const bool vec = out_al && (colfull || col + 3 < P.n_valid);
+                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (P.bias != nullptr && col < P.n_valid) {
+                        bv.x = __ldg(P.bias + col);
+                        if (col + 1 < P.n_valid) bv.y = __ldg(P.bias + col + 1);
+                        if (col + 2 < P.n_valid) bv.z = __ldg(P.bias + col + 2);
+                        if (col + 3 < P.n_valid) bv.w = __ldg(P.bias + col + 3);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int rr = i * 8 + rsub;
+                        const long long off = offs[i];
+                        float4 o = stg[rr * 4 + (q ^ ((rr >> 1) & 3))];
+                        if ((!fast && off < 0) || col >= P.n_valid) continue;
+                        o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+                        if (elu) {
+                            o.x = o.x > 0.f ? o.x : __expf(o.x) - 1.f; o.y = o.y > 0.f ? o.y : __expf(o.y) - 1.f;
+                            o.z = o.z > 0.f ? o.z : __expf(o.z) - 1.f; o.w = o.w > 0.f ? o.w : __expf(o.w) - 1.f;
+                        }
+                        if (vec) {
+                            if (accum) {
+                                const float4 old = *reinterpret_cast<const float4 *>(P.out + off + col);
+                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                            }
+                            if (has32) *reinterpret_cast<float4 *>(P.out + off + col) = o;
+                            if (has16) {
+                                __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+                                uint2 pk;
+                                pk.x = *reinterpret_cast<uint32_t *>(&lo);
+                                pk.y = *reinterpret_cast<uint32_t *>(&hi);
+                                *reinterpret_cast<uint2 *>(P.out16 + off + col) = pk;
+                            }
+                        } else {
+                            const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (col + e < P.n_valid) {
+                                    const float val = accum ? P.out[off + col + e] + ov[e] : ov[e];
+                                    if (has32) P.out[off + col + e] = val;
+                                    if (has16) P.out16[off + col + e] = __float2bfloat16_rn(val);
+                                }
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TCG_EPI_WARPS + 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // weight re-packing: canonical TF layout [tap][ci][co] -> K-major [N][taps*Cpad]
 //   fwd  (contract over ci): Wp[co][tap*Cpad + ci] = W[tap][ci][co]
 //   bwd  (contract over co): Wp[ci][tap*Cpad + co] = W[tap][ci][co]
@@ -834,6 +1050,8 @@ static unsigned long long g_weight_epoch = 1;      // bumped by dofb_invalidate_
 static bool g_cache_enabled = false;               // off: every call re-packs (always correct); on: caller promises to invalidate
 static bool g_halo = false;                        // halo-tile reuse of A across filter taps (dofb_enable_halo_tiles)
 void enable_halo(int on) { g_halo = on != 0; }
+static bool g_mph = true;                          // multi-phase halo kernel for narrow stride-2 transposed gathers (dofb_enable_multiphase_halo)
+void enable_mph(int on) { g_mph = on != 0; }
 static bool g_cta_pairs = false;                   // cta_group::2 tiles for the 256-column layers (dofb_enable_cta_pairs)
 void enable_cta_pairs(int on) { g_cta_pairs = on != 0; }
 
@@ -1009,6 +1227,66 @@ static int run_gather(const GatherSpec &G, const TcParams &Pin, cudaStream_t st)
     DOFB_CHECK_ARG(G.out != nullptr || (G.out16 != nullptr && !G.accumulate), "tc conv: a bf16-only output needs the bf16 buffer and cannot accumulate");
     P.bias = G.bias; P.n_valid = G.n_valid; P.rh = G.rh; P.rw = G.rw;
     P.act = G.act; P.accumulate = G.accumulate; P.B = G.B;
+    // ---- multi-phase halo kernel: 4 phases of a stride-2 transposed gather, every tap offset in {-1,0,1}, at most 128 output columns ----
+    if (g_mph && P.nphase == 4 && !P.parity && P.rstep == 2 && n_rows <= 128 && true) {
+        bool ok = true;
+        int mcy = 0, mcx = 0, ncy = 1 << 30, ncx = 1 << 30;
+        for (int q = 0; q < 4; ++q) {
+            mcy = P.ph[q].cnt_y > mcy ? P.ph[q].cnt_y : mcy; mcx = P.ph[q].cnt_x > mcx ? P.ph[q].cnt_x : mcx;
+            ncy = P.ph[q].cnt_y < ncy ? P.ph[q].cnt_y : ncy; ncx = P.ph[q].cnt_x < ncx ? P.ph[q].cnt_x : ncx;
+            for (int t = P.ph[q].tap0; t < P.ph[q].tap0 + P.ph[q].ntaps; ++t)
+                if (P.taps[t].oy < -1 || P.taps[t].oy > 1 || P.taps[t].ox < -1 || P.taps[t].ox > 1) ok = false;
+        }
+        if (ncy < 8 || ncx < 8) ok = false;                 // tiny maps: the generic path wastes less
+        MphParams M;
+        memset(&M, 0, sizeof(M));
+        int nck = 0;
+        for (int q = 0; q < 4 && ok; ++q)
+            for (int t0 = 0; t0 < P.ph[q].ntaps; t0 += 4) {
+                if (nck >= MPH_MAX_CHUNKS) { ok = false; break; }
+                M.ck[nck].phase = (short)q; M.ck[nck].tap0 = (short)(P.ph[q].tap0 + t0);
+                M.ck[nck].ntaps = (short)(P.ph[q].ntaps - t0 < 4 ? P.ph[q].ntaps - t0 : 4); M.ck[nck].first = (short)(t0 == 0);
+                ++nck;
+            }
+        if (ok) {
+            const int bn = n_rows <= 32 ? 32 : 64;
+            M.out = G.out; M.out16 = G.accumulate ? nullptr : reinterpret_cast<__nv_bfloat16 *>(G.out16); M.out_ld = G.out_ld; M.bias = G.bias;
+            M.n_valid = G.n_valid; M.rh = G.rh; M.rw = G.rw; M.B = G.B;
+            M.tiles_x = (mcx + 7) / 8; M.tiles_y = (mcy + 15) / 16; M.m_tiles = M.tiles_x * M.tiles_y * G.B; M.n_tiles = (n_rows + bn - 1) / bn;
+            M.a_coff = G.a_coff; M.ncb = cpad / kel; M.act = G.act; M.accumulate = G.accumulate; M.nphase = 4; M.nchunks = nck;
+            for (int q = 0; q < 4; ++q) { M.ph[q].y0 = P.ph[q].y0; M.ph[q].x0 = P.ph[q].x0; M.ph[q].cnt_y = P.ph[q].cnt_y; M.ph[q].cnt_x = P.ph[q].cnt_x; }
+            for (int t = 0; t < taps_listed; ++t) M.taps[t] = P.taps[t];
+            DOFB_CHECK_ARG(G.out != nullptr || (G.out16 != nullptr && !G.accumulate), "tc conv: a bf16-only output needs the bf16 buffer and cannot accumulate");
+            const CUtensorMapDataType dtm = bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+            CUtensorMap ma, mb;
+            const uint64_t dims[4] = {(uint64_t)cpad, (uint64_t)G.aw, (uint64_t)G.ah, (uint64_t)G.B};
+            const uint64_t str[3] = {(uint64_t)G.a_ld * esz, (uint64_t)G.aw * G.a_ld * esz, (uint64_t)G.ah * G.aw * G.a_ld * esz};
+            const uint32_t box[4] = {(uint32_t)kel, 16u, (uint32_t)TC_HALO_ROWS, 1u};
+            if (make_map(&ma, abase, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, dtm)) return 1;
+            const uint64_t bdims[2] = {(uint64_t)taps_all * cpad, (uint64_t)n_rows};
+            const uint64_t bstr[1] = {(uint64_t)taps_all * cpad * esz};
+            const uint32_t bbox[2] = {(uint32_t)kel, (uint32_t)bn};
+            if (make_map(&mb, wp, 2, bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_128B, dtm)) return 1;
+            const long long total = (long long)M.m_tiles * M.n_tiles;
+            const int grid = (int)(total < num_sms() ? total : num_sms());
+#define DOFB_MPH_LAUNCH(BNv, BFv)                                                                                                         \
+    {                                                                                                                                    \
+        constexpr int smem_mph = MPH_A_SLOTS * TC_HALO_ROWS * 16 * 128 + MPH_B_SLOTS * 4 * BNv * 128 + TCG_EPI_WARPS * 32 * 16 * 4 + 1024 + 256; \
+        static_assert(smem_mph <= 227 * 1024, "shared-memory budget");                                                                  \
+        static bool cfgd = false;                                                                                                        \
+        if (!cfgd) {                                                                                                                     \
+            DOFB_CUDA_OK(cudaFuncSetAttribute(tc_mph_kernel<BNv, BFv>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_mph));          \
+            cfgd = true;                                                                                                                 \
+        }                                                                                                                                \
+        tc_mph_kernel<BNv, BFv><<<grid, TCG_THREADS, smem_mph, st>>>(ma, mb, M);                                                        \
+    }
+            if (bf) { if (bn == 32) DOFB_MPH_LAUNCH(32, true) else DOFB_MPH_LAUNCH(64, true) }
+            else { if (bn == 32) DOFB_MPH_LAUNCH(32, false) else DOFB_MPH_LAUNCH(64, false) }
+#undef DOFB_MPH_LAUNCH
+            DOFB_LAUNCH_OK();
+            return 0;
+        }
+    }
     // ---- halo tiles: unit-stride gather, every phase at least 16 x 8 pixels, <= 4 taps per phase spanning <= 2 rows / 8 columns ----
     const int n_rows_out = G.contract_ci ? G.w_co : G.w_ci;
     bool halo = g_halo && !P.parity && n_rows_out <= 128;
@@ -2139,6 +2417,222 @@ int tc_corr_bwd(const float *f1, const float *f2, int ld, int B, int h, int w, i
         if (make_map(&mf, F, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
         const int grid = P.units < num_sms() ? P.units : num_sms();
         tc_corr_bwd_kernel<<<grid, TC_THREADS, smem, st>>>(mf, P);
+        DOFB_LAUNCH_OK();
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Correlation backward, bf16 operands (kind::f16), eight generator warps.
+// Same band-GEMM as tc_corr_bwd_kernel, re-balanced around what limited it (the four warps that WRITE the band matrix):
+//   * bf16: a 128-byte swizzle row holds 64 K columns (pixels) instead of 32 -> 4 K-blocks per vertical displacement instead of 8, and the
+//     F pixels come from the bf16 shadows of conv3a / conv3b (MN-major, 4 TMA boxes of 8 KB per K-block);
+//   * the K-blocks per displacement (4) equal the pipeline depth, so stage s ALWAYS holds K-block s: the 64 tile rows whose image row
+//     does not match K-block s are all-zero in stage s for the whole kernel -- zeroed once, never written again;
+//   * each of the four stages has its own pair of generator warps (64 threads = the 64 active rows), so four K-blocks are generated
+//     concurrently and a thread touches only its own row of its own stage;
+//   * two TMEM accumulators (2 x 256 columns): the epilogue of unit i (all eight warps: lane quadrant = warp & 3, column half = warp >> 2)
+//     overlaps the MMAs of unit i + 1.
+// ------------------------------------------------------------------------------------------------
+struct CorrBwd16Params {
+    const float *g; int g_ld;         // dout [B,h,w,g_ld] fp32, D*D channels used
+    float *out; int out_ld;           // df1 or df2 [B,h,w,out_ld] fp32
+    int B, h, w, md, s2, D, transpose;
+    int ypairs, xtiles, units;
+    float inv_c;
+};
+constexpr int CB16_STAGE = TC_A_BYTES + 4 * 8192;      // 16 KB generated A + 32 KB TMA B (4 channel regions x 64 pixels x 128 B)
+constexpr int CB16_GP = 33;                            // pitch of a thread's private g row (floats): D <= 33
+
+__global__ void __launch_bounds__(TCG_THREADS, 1)
+tc_corr_bwd16_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_constant__ CorrBwd16Params P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float *g_stage = reinterpret_cast<float *>(smem + 4 * CB16_STAGE);                     // [8 warps][32 lanes][33]
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(g_stage + 8 * 32 * CB16_GP);
+    full_bar = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(full_bar) + 7) & ~uintptr_t(7));
+    uint64_t *empty_bar = full_bar + 4;
+    uint64_t *acc_full = empty_bar + 4;
+    uint64_t *acc_empty = acc_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 4; ++s) { mbar_init(&full_bar[s], 3); mbar_init(&empty_bar[s], 1); }    // TMA thread + the stage's 2 generator warps
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], TCG_EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == TCG_EPI_WARPS && lane == 0) prefetch_tmap(&map_f);
+    if (warp == TCG_EPI_WARPS + 1) tmem_alloc(tmem_slot, 512);
+    if (warp < TCG_EPI_WARPS) {
+        // the rows of stage s that belong to the OTHER image row stay zero for the whole kernel: 64 rows x 128 B per stage
+        for (int i = threadIdx.x; i < 4 * 64 * 8; i += TCG_EPI_WARPS * 32) {
+            const int s = i / 512, rr = (i / 8) % 64, ch = i % 8;
+            const int row = (1 - (s >> 1)) * 64 + rr;
+            *reinterpret_cast<uint4 *>(smem + s * CB16_STAGE + row * 128 + ch * 16) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        fence_proxy_async();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == TCG_EPI_WARPS) {
+        // ===== TMA producer: the 64 F pixels of K-block kb, one 8 KB box per 64-channel region (lanes 0..3) =====
+        long long n = 0;                                   // fills of every stage so far (all four stages advance together)
+        for (int u = blockIdx.x; u < P.units; u += gridDim.x) {
+            const int xt = u % P.xtiles, yp = (u / P.xtiles) % P.ypairs, b = u / (P.xtiles * P.ypairs);
+            const int x0 = xt * 64, y0 = yp * 2;
+            for (int dyi = 0; dyi < P.D; ++dyi, ++n) {
+                const int dy = -P.md + dyi * P.s2;
+                for (int kb = 0; kb < 4; ++kb) {
+                    if (lane == 0) {
+                        mbar_wait(&empty_bar[kb], (uint32_t)((n & 1) ^ 1));
+                        mbar_expect_tx(&full_bar[kb], 4 * 8192);
+                    }
+                    __syncwarp();
+                    if (lane < 4)
+                        tma_load_4d(smem + kb * CB16_STAGE + TC_A_BYTES + lane * 8192, &map_f, &full_bar[kb], lane * 64, x0 - 32 + (kb & 1) * 64,
+                                    y0 + (kb >> 1) + (P.transpose ? -dy : dy), b);
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == TCG_EPI_WARPS + 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(TC_BM, 256) | (1u << 16);      // A K-major, B MN-major
+            long long n = 0;
+            int lu = 0;
+            for (int u = blockIdx.x; u < P.units; u += gridDim.x, ++lu) {
+                const int acc = lu & 1;
+                mbar_wait(&acc_empty[acc], (uint32_t)(((lu >> 1) & 1) ^ 1));
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+                for (int dyi = 0; dyi < P.D; ++dyi, ++n) {
+                    for (int kb = 0; kb < 4; ++kb) {
+                        mbar_wait(&full_bar[kb], (uint32_t)(n & 1));
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + kb * CB16_STAGE);
+                        const uint64_t da = make_desc_k128(sa), db = make_desc_mn<true>(sa + TC_A_BYTES, 8192);
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)          // K = 16 pixels per MMA: A +32 B inside the swizzle row, B +16 pixel rows (2 KB)
+                            umma_bf16(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 128), idesc, (dyi | kb | kk) != 0);
+                        umma_commit(&empty_bar[kb]);
+                    }
+                }
+                umma_commit(&acc_full[acc]);
+            }
+        }
+    } else {
+        // ===== generators: warp pair p = warp >> 1 owns stage / K-block p; its 64 threads are the 64 tile rows of image row p >> 1 =====
+        const int kb = warp >> 1, ry = kb >> 1, xl = (warp & 1) * 32 + lane;
+        const int r = ry * 64 + xl;                                  // tile row this thread writes
+        float *my_g = g_stage + (warp * 32 + lane) * CB16_GP;
+        uint8_t *arow = smem + kb * CB16_STAGE + r * 128;
+        const int s2_mask = P.s2 - 1, s2_shift = P.s2 == 1 ? 0 : (P.s2 == 2 ? 1 : 2);
+        const int xk0 = (kb & 1) * 64;
+        const int t0 = P.transpose ? (xl + 32 - xk0 + P.md) : (xk0 - xl - 32 + P.md);
+        const int tstep = P.transpose ? -1 : 1;
+        // epilogue coordinates (TMEM lane = tile row; a different row than the one this thread generates)
+        const int er = (warp & 3) * 32 + lane, ery = er >> 6, exl = er & 63, ecol0 = (warp >> 2) * 128;
+        long long n = 0;
+        int lu = 0;
+        for (int u = blockIdx.x; u < P.units; u += gridDim.x, ++lu) {
+            const int xt = u % P.xtiles, yp = (u / P.xtiles) % P.ypairs, b = u / (P.xtiles * P.ypairs);
+            const int x0 = xt * 64, y0 = yp * 2;
+            const int py = y0 + ry, px = x0 + xl;
+            const bool pix_ok = py < P.h && px < P.w;
+            for (int dyi = 0; dyi < P.D; ++dyi, ++n) {
+                const int dy = -P.md + dyi * P.s2;
+                const int gy = P.transpose ? py - dy : py;
+                const bool grow_ok = pix_ok && gy >= 0 && gy < P.h;
+                const float *grow = P.g + ((long long)b * P.h + (grow_ok ? gy : 0)) * P.w * P.g_ld + dyi * P.D;
+                for (int j = 0; j < P.D; ++j) {
+                    float v = 0.f;
+                    if (grow_ok) {
+                        const int gx = P.transpose ? px - (-P.md + j * P.s2) : px;
+                        if (gx >= 0 && gx < P.w) v = __ldg(grow + (long long)gx * P.g_ld + j);
+                    }
+                    my_g[j] = v;
+                }
+                mbar_wait(&empty_bar[kb], (uint32_t)((n & 1) ^ 1));
+#pragma unroll
+                for (int cidx = 0; cidx < 8; ++cidx) {
+                    float v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const int t = t0 + tstep * (cidx * 8 + e);
+                        v[e] = (grow_ok && t >= 0 && t <= 2 * P.md && (t & s2_mask) == 0) ? my_g[t >> s2_shift] : 0.f;
+                    }
+                    uint4 pk;
+                    __nv_bfloat162 q0 = __floats2bfloat162_rn(v[0], v[1]), q1 = __floats2bfloat162_rn(v[2], v[3]);
+                    __nv_bfloat162 q2 = __floats2bfloat162_rn(v[4], v[5]), q3 = __floats2bfloat162_rn(v[6], v[7]);
+                    pk.x = *reinterpret_cast<uint32_t *>(&q0); pk.y = *reinterpret_cast<uint32_t *>(&q1);
+                    pk.z = *reinterpret_cast<uint32_t *>(&q2); pk.w = *reinterpret_cast<uint32_t *>(&q3);
+                    *reinterpret_cast<uint4 *>(arow + ((cidx ^ (r & 7)) << 4)) = pk;
+                }
+                fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_bar[kb]);
+            }
+            // ---- epilogue of this unit: 128 rows x 256 channels fp32 ----
+            const int acc = lu & 1;
+            mbar_wait(&acc_full[acc], (uint32_t)((lu >> 1) & 1));
+            tc_fence_after();
+            const int epy = y0 + ery, epx = x0 + exl;
+            const bool e_ok = epy < P.h && epx < P.w;
+            float *orow = P.out + (((long long)b * P.h + (e_ok ? epy : 0)) * P.w + (e_ok ? epx : 0)) * P.out_ld + ecol0;
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(acc * 256 + ecol0 + j * 32), v);
+                if (e_ok) {
+#pragma unroll
+                    for (int qd = 0; qd < 8; ++qd)
+                        *reinterpret_cast<float4 *>(orow + j * 32 + qd * 4) =
+                            make_float4(v[4 * qd] * P.inv_c, v[4 * qd + 1] * P.inv_c, v[4 * qd + 2] * P.inv_c, v[4 * qd + 3] * P.inv_c);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TCG_EPI_WARPS + 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+int tc_corr_bwd16(const void *f1_16, const void *f2_16, int ld, int B, int h, int w, int c, int md, int s2, const float *dout, int dout_ld,
+                  float *df1, float *df2, int dld, cudaStream_t st) {
+    DOFB_CHECK_ARG(c == 256 && ld % 64 == 0 && dld % 4 == 0 && aligned16(f1_16) && aligned16(f2_16) && aligned16(df1) && aligned16(df2),
+                   "dofb_corr_bwd_bf16: needs c = 256 channels, bf16 pitches multiples of 64, 16-byte aligned pointers");
+    DOFB_CHECK_ARG(md >= 0 && md <= 32 && (s2 == 1 || s2 == 2 || s2 == 4) && md % s2 == 0 && 2 * (md / s2) + 1 <= CB16_GP,
+                   "dofb_corr_bwd_bf16: max displacement <= 32, stride2 in {1,2,4} dividing it, at most %d displacements per axis", CB16_GP);
+    constexpr int smem = 4 * CB16_STAGE + 8 * 32 * CB16_GP * 4 + 1024 + 256;
+    static_assert(smem <= 227 * 1024, "shared-memory budget");
+    static bool configured = false;
+    if (!configured) {
+        DOFB_CUDA_OK(cudaFuncSetAttribute(tc_corr_bwd16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+        CorrBwd16Params P;
+        P.g = dout; P.g_ld = dout_ld; P.out = pass == 0 ? df1 : df2; P.out_ld = dld;
+        P.B = B; P.h = h; P.w = w; P.md = md; P.s2 = s2; P.D = 2 * (md / s2) + 1; P.transpose = pass;
+        P.ypairs = (h + 1) / 2; P.xtiles = (w + 63) / 64; P.units = B * P.ypairs * P.xtiles; P.inv_c = 1.0f / (float)c;
+        const void *F = pass == 0 ? f2_16 : f1_16;
+        CUtensorMap mf;
+        const uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)B};
+        const uint64_t str[3] = {(uint64_t)ld * 2, (uint64_t)w * ld * 2, (uint64_t)h * w * ld * 2};
+        const uint32_t box[4] = {64, 64, 1, 1};
+        if (make_map(&mf, F, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)) return 1;
+        const int grid = P.units < num_sms() ? P.units : num_sms();
+        tc_corr_bwd16_kernel<<<grid, TCG_THREADS, smem, st>>>(mf, P);
         DOFB_LAUNCH_OK();
     }
     return 0;

@@ -90,8 +90,17 @@ int tc_corr_fwd(const float *f1, const float *f2, int ld, int B, int h, int w, i
                 cudaStream_t st);
 int tc_corr_bwd(const float *f1, const float *f2, int ld, int B, int h, int w, int c, int md, int s2, const float *dout, int dout_ld,
                 float *df1, float *df2, int dld, cudaStream_t st);
+int tc_corr_bwd16(const void *f1_16, const void *f2_16, int ld, int B, int h, int w, int c, int md, int s2, const float *dout, int dout_ld,
+                  float *df1, float *df2, int dld, cudaStream_t st);
 }
 using namespace dofb;
+
+extern "C" int dofb_corr_bwd_bf16(const void *f1_bf16, const void *f2_bf16, int ld, int B, int h, int w, int c, int max_disp, int stride2,
+                                  const float *dout, int dout_ld, float *df1, float *df2, int dld, void *stream) {
+    DOFB_CHECK_ARG(f1_bf16 && f2_bf16 && dout && df1 && df2 && B > 0 && h > 0 && w > 0, "dofb_corr_bwd_bf16: bad argument");
+    DOFB_CHECK_ARG(dout_ld >= (2 * (max_disp / stride2) + 1) * (2 * (max_disp / stride2) + 1), "dofb_corr_bwd_bf16: dout pitch too small");
+    return tc_corr_bwd16(f1_bf16, f2_bf16, ld, B, h, w, c, max_disp, stride2, dout, dout_ld, df1, df2, dld, as_stream(stream));
+}
 
 extern "C" int dofb_corr_fwd(const float *f1, const float *f2, int ld, int B, int h, int w, int c, int max_disp, int stride2,
                              float *out, int out_ld, int act, int math, void *stream) {

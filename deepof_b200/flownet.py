@@ -158,6 +158,7 @@ class FlowNetS:
         ops._lib.load().dofb_enable_cta_pairs(0 if os.environ.get("DOFB_CTA_PAIRS", "1") == "0" else 1)   # cta_group::2 tiles for the wide layers
         # halo-tile reuse of A across taps: correct (tests) but slower than the per-tap gather in its first form -> opt-in
         ops._lib.load().dofb_enable_halo_tiles(1 if os.environ.get("DOFB_HALO", "0") == "1" else 0)
+        ops._lib.load().dofb_enable_multiphase_halo(0 if os.environ.get("DOFB_MPH", "1") == "0" else 1)
         self.profile = None            # list of (tag, start_event, end_event) when per-launch timing is on
         if seed is not None:
             self.init_params(seed)
@@ -247,6 +248,9 @@ class FlowNetS:
             self._z_flat = torch.zeros(B * h1 * w1 * 20, dtype=torch.float32, device=dev)
             self.head_z = {s: self._z_flat[:B * hh * ww * 20].view(B, hh, ww, 20) for s, (hh, ww) in self.hw.items()}
             self.head_d9 = {s: torch.zeros(B, hh, ww, 64, dtype=torch.bfloat16, device=dev) for s, (hh, ww) in self.hw.items()}
+            # gradient of the 2-channel up_pr outputs: compact [B,h,w,2] maps (inside the pitched concat gradient every pixel of them is its own
+            # 32-byte sector for the 4x4 gather of uppr_bwd)
+            self.dpr_up = {s: torch.zeros(B, hh, ww, 2, dtype=torch.float32, device=dev) for s, (hh, ww) in self.hw.items() if s < self.N_SCALES}
             self.head_wz = {s: torch.zeros(1, 1, self.arena.shapes[f"pr{s}/weights"][2], 20, dtype=torch.float32, device=dev)
                             for s in range(1, self.N_SCALES + 1)}
 
@@ -435,7 +439,7 @@ class FlowNetS:
         elif L["op"] == "corr":
             self._k("elu_bwd:corr", ops.elu_bwd, L["dy4"], L["y4"], None)
             self._k("corr_bwd", ops.corr_bwd, L["f1"], L["f2"], L["dy"], L["df1"], L["df2"], L["max_disp"], L["stride2"],
-                    MATH_TF32 if mth == MATH_BF16 else mth)
+                    mth if (mth != MATH_BF16 or os.environ.get("DOFB_CORR_BWD16", "1") != "0") else MATH_TF32)   # bf16: band-GEMMs on the bf16 shadows
 
     def forward(self, source: torch.Tensor, target: torch.Tensor, loss_weight=LOSS_WEIGHTS, with_grad: bool = True):
         """flowNet(inputs, outputs, loss_weight): runs the whole forward; when ``with_grad`` the fused
@@ -520,8 +524,8 @@ class FlowNetS:
             # gradient of [upconv | up_pr] outputs inside feat_{s-1}: (deconv_dgrad of the previous iteration, none at scale 1) + head pr_{s-1}
             slab_d = fd.sub(skipc, upc + 2)
             self._k("elu_bwd:" + R["up"], ops.head_dgrad_elu, self.head_d9[fs], self.head_wz[fs], skipc, None if fs == 1 else slab_d,
-                    fy.sub(skipc, upc + 2), slab_d, upc, G[R["up"] + "/biases"])
-            self._k("uppr_bwd:" + R["uppr"], ops.uppr_bwd, self.pr[s], R["pr_dy"], P[R["uppr"] + "/weights"], self.dpr[s],
+                    fy.sub(skipc, upc + 2), slab_d, upc, G[R["up"] + "/biases"], self.dpr_up[fs])
+            self._k("uppr_bwd:" + R["uppr"], ops.uppr_bwd, self.pr[s], full(self.dpr_up[fs]), P[R["uppr"] + "/weights"], self.dpr[s],
                     G[R["uppr"] + "/weights"], G[R["uppr"] + "/biases"])
             self._k("deconv_wgrad:" + R["up"], ops.conv_wgrad, R["g"], R["up_dy"], x, G[R["up"] + "/weights"], None, mth)
             self._k("deconv_dgrad:" + R["up"], ops.conv_fwd, R["g"], R["up_dy"], P[R["up"] + "/weights"], None, Slab(dx.t, dx.c0, dx.c),

@@ -292,10 +292,11 @@ def head_dpr9(dpr, d9, dbias=None):
     check(_lib.load().dofb_head_dpr9(dpr.data_ptr(), B, h, w, d9.data_ptr(), d9.shape[3], dbias.data_ptr() if dbias is not None else None, _stream()))
 
 
-def head_dgrad_elu(d9, wz, c0: int, g: Slab | None, y: Slab, out: Slab, c_elu: int, db=None):
+def head_dgrad_elu(d9, wz, c0: int, g: Slab | None, y: Slab, out: Slab, c_elu: int, db=None, lin_out: torch.Tensor | None = None):
     """Finish the gradient of the channel slab ``out`` (= channels [c0, c0+out.c) of the head's input feat_s): adds the head's input
     gradient (D9 row . Wz rows) to ``g`` (or to zero), applies ELU' (from the bf16 ELU outputs ``y``) on the first c_elu channels -> bf16
-    shadow of ``out`` and bias gradient ``db``; the remaining (linear) channels are written in fp32 to ``out`` (dofb_head_dgrad_elu_bf16)."""
+    shadow of ``out`` and bias gradient ``db``; the remaining (linear) channels are written in fp32 to ``out`` -- or to the compact tensor
+    ``lin_out`` -- (dofb_head_dgrad_elu_bf16)."""
     _req(wz, "wz")
     assert d9.dtype == torch.bfloat16 and d9.is_cuda and d9.is_contiguous() and d9.dim() == 4
     B, h, w, d9_ld = d9.shape
@@ -303,11 +304,18 @@ def head_dgrad_elu(d9, wz, c0: int, g: Slab | None, y: Slab, out: Slab, c_elu: i
     c_total = wz.numel() // 20
     assert (g is None or g.c == c) and y.c == c and out.n_pix == B * h * w
     lin = c_elu < c
+    gout, gout_ld = None, out.ld
+    if lin and lin_out is not None:         # compact [B,h,w,c-c_elu] destination of the linear channels (slab channel ch lands at ch - c_elu)
+        _req(lin_out, "lin_out")
+        assert tuple(lin_out.shape) == (B, h, w, c - c_elu)
+        gout, gout_ld = lin_out.data_ptr() - 4 * int(c_elu), c - c_elu
+    elif lin:
+        gout = _need32(out, "head_dgrad_elu")
     check(_lib.load().dofb_head_dgrad_elu_bf16(
         d9.data_ptr(), d9_ld, B, h, w, wz.data_ptr(), c_total, int(c0), c, int(c_elu),
         _need32(g, "head_dgrad_elu") if g is not None else None, g.ld if g is not None else 0,
         _need16(y, "head_dgrad_elu") if c_elu else None, y.ld, _need16(out, "head_dgrad_elu") if c_elu else None, out.ld,
-        _need32(out, "head_dgrad_elu") if lin else None, out.ld, db.data_ptr() if db is not None else None, _stream()))
+        gout, gout_ld, db.data_ptr() if db is not None else None, _stream()))
 
 
 def head_fwd(x: Slab, w, b, pr):
@@ -358,6 +366,10 @@ def corr_fwd(f1: Slab, f2: Slab, out: Slab, max_disp=20, stride2=2, act=ACT_NONE
 
 def corr_bwd(f1: Slab, f2: Slab, dout: Slab, df1: Slab, df2: Slab, max_disp=20, stride2=2, math=MATH_FP32):
     assert df1.ld == df2.ld
+    if math == MATH_BF16:
+        check(_lib.load().dofb_corr_bwd_bf16(_need16(f1, "corr_bwd"), _need16(f2, "corr_bwd"), f1.ld, f1.B, f1.h, f1.w, f1.c, max_disp, stride2,
+                                             dout.ptr, dout.ld, df1.ptr, df2.ptr, df1.ld, _stream()))
+        return
     check(_lib.load().dofb_corr_bwd(f1.ptr, f2.ptr, f1.ld, f1.B, f1.h, f1.w, f1.c, max_disp, stride2, dout.ptr, dout.ld,
                                     df1.ptr, df2.ptr, df1.ld, math, _stream()))
 

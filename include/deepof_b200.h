@@ -183,6 +183,9 @@ void dofb_enable_cta_pairs(int on);
 /* Unit-stride gathers on maps of at least 16 x 8 pixels (<= 128 output columns): stage ONE halo box of the input per tile and channel block
  * and let every filter tap read its shifted rows out of it, instead of one TMA box per tap.  Process-wide switch. */
 void dofb_enable_halo_tiles(int on);
+/* Stride-2 transposed gathers (conv2d_transpose forwards, input gradients of stride-2 convs) with at most 128 output channels: one halo box of
+ * the source map per channel block serves every tap of all four output phases (tc_mph_kernel).  On by default; process-wide switch. */
+void dofb_enable_multiphase_halo(int on);
 /* ---- BF16 tensor-core math (tcgen05 kind::f16, bf16 operands, fp32 accumulate + fp32 epilogue) ----
  * Activations keep their fp32 NHWC buffers; every producer additionally writes a bf16 "shadow" with the same pitch in elements
  * (a multiple of 64), and the tensor-core consumers read the shadows: half the bytes per K element and twice the MMA rate of the
@@ -282,6 +285,11 @@ int dofb_corr_fwd(const float *f1, const float *f2, int ld, int B, int h, int w,
                   float *out, int out_ld, int act, int math, void *stream);
 int dofb_corr_bwd(const float *f1, const float *f2, int ld, int B, int h, int w, int c, int max_disp, int stride2,
                   const float *dout, int dout_ld, float *df1, float *df2, int dld, int math, void *stream);
+
+/* Same gradients from the bf16 shadows of f1 / f2 (pitch ld in elements, a multiple of 64) on tcgen05 kind::f16 band-GEMMs; dout and the
+ * gradients stay fp32.  c = 256. */
+int dofb_corr_bwd_bf16(const void *f1_bf16, const void *f2_bf16, int ld, int B, int h, int w, int c, int max_disp, int stride2,
+                       const float *dout, int dout_ld, float *df1, float *df2, int dld, void *stream);
 
 #ifdef __cplusplus
 }

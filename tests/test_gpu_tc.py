@@ -562,3 +562,86 @@ def test_halo_tiles_match_per_tap_gather(which, case, mth):
     finally:
         lib.dofb_enable_halo_tiles(0)
     assert rel(outs[1], outs[0]) < 1e-5
+
+
+MPH_CASES = [
+    # which, B, ih, iw, ci, co, k   (geometry of the stride-2 conv whose input gradient / transpose this is)
+    ("deconv", 2, 48, 64, 32, 194, 4),        # upconv1-like: transposed conv 194 -> 32
+    ("deconv", 1, 48, 64, 64, 386, 4),        # upconv2-like
+    ("deconv", 1, 44, 56, 128, 130, 4),       # two 64-column tiles, ragged source map 22 x 28
+    ("dgrad", 2, 48, 64, 64, 128, 5),         # conv2-like input gradient (phases of 9/6/6/4 taps)
+    ("dgrad", 1, 40, 48, 128, 256, 5),        # conv3_1-like
+    ("dgrad", 2, 34, 46, 96, 160, 3),         # 3x3/2, odd map
+]
+
+
+@pytest.mark.parametrize("case", MPH_CASES)
+@pytest.mark.parametrize("mth", [1, 2])
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_multiphase_halo_kernel_matches_per_tap_gather(case, mth, accumulate):
+    """tc_mph_kernel (one halo box of the source map serves all taps of all four stride phases) against the per-tap gather kernel and the
+    CPU oracle: transposed-conv forward with bias + ELU, and accumulating / overwriting input gradients."""
+    from deepof_b200 import ops, _lib
+    from oracle import tf_ops
+    which, B, ih, iw, ci, co, k = case
+    if which == "deconv" and accumulate:
+        pytest.skip("a transposed-conv forward never accumulates")
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(len(which) + sum(case[1:]))
+    geom = ops.conv_geom(B, ih, iw, ci, co, k, 2)
+    P = 64 if mth == 2 else 32
+    ld_s, ld_l = (co + P - 1) // P * P, (ci + P - 1) // P * P
+    small = _buf(B, geom.oh, geom.ow, ld_s, co, g)                     # the gathered (source) map
+    if mth == 2:
+        small = small.to(torch.bfloat16).float()
+    wt = (torch.randn(k, k, ci, co, generator=g) / math.sqrt(k * k * co)).cuda()
+    bias = (torch.randn(ci, generator=g) * 0.1).cuda() if which == "deconv" else None
+    act = ops.ACT_ELU if which == "deconv" else ops.ACT_NONE
+    base = torch.randn(B, ih, iw, ld_l, generator=g).cuda()
+    outs = []
+    for on in (0, 1):
+        lib.dofb_enable_multiphase_halo(on)
+        y = base.clone()
+        y16 = torch.zeros(B, ih, iw, ld_l, dtype=torch.bfloat16, device="cuda") if mth == 2 else None
+        ops.conv_dgrad(geom, ops.Slab(small, 0, co, small.to(torch.bfloat16) if mth == 2 else None), wt, bias, ops.Slab(y, 0, ci, y16), act, accumulate, mth)
+        torch.cuda.synchronize()
+        outs.append((y, y16))
+    lib.dofb_enable_multiphase_halo(1)
+    assert rel(outs[1][0][..., :ci], outs[0][0][..., :ci]) < 2e-5
+    assert torch.equal(outs[1][0][..., ci:], base[..., ci:])           # pad channels untouched
+    if mth == 2 and not accumulate:
+        assert rel(outs[1][1][..., :ci].float(), outs[0][1][..., :ci].float()) < 2 ** -7
+    # oracle: the input gradient of the TF-SAME stride-2 conv (== conv2d_transpose for the 4x4 case)
+    xd = torch.zeros(B, ih, iw, ci, dtype=torch.float64, requires_grad=True)
+    wq = wt.cpu().to(torch.bfloat16).double() if mth == 2 else wt.cpu().double()
+    tf_ops.conv2d_same(xd, wq, None, 2).backward(small.cpu()[..., :co].double())
+    want = xd.grad
+    if which == "deconv":
+        want = tf_ops.elu(want + bias.cpu().double())
+    if accumulate:
+        want = want + base.cpu()[..., :ci].double()
+    assert rel(outs[1][0][..., :ci], want) < (2e-5 if mth == 2 else TOL)
+
+
+@pytest.mark.parametrize("B,h,w,md,s2", [(2, 12, 64, 20, 2), (1, 7, 40, 20, 2), (2, 6, 128, 20, 2), (1, 5, 64, 16, 4), (1, 48, 64, 20, 2), (3, 9, 70, 8, 1)])
+def test_bf16_correlation_backward_matches_oracle(B, h, w, md, s2):
+    """tc_corr_bwd16_kernel (bf16 band-GEMMs, eight generator warps) against autograd of the CPU restatement of the cost volume."""
+    from deepof_b200 import ops
+    from oracle import flownet_c
+    g = torch.Generator().manual_seed(B * h + w + 5)
+    c = 256
+    f1 = _buf(B, h, w, c, c, g).to(torch.bfloat16)
+    f2 = _buf(B, h, w, c, c, g).to(torch.bfloat16)
+    D = 2 * (md // s2) + 1
+    dout = _buf(B, h, w, D * D + 7, D * D, g)
+    d1 = torch.full((B, h, w, c), 3.0, device="cuda")
+    d2 = torch.full((B, h, w, c), 3.0, device="cuda")
+    dummy = torch.zeros(B, h, w, c, device="cuda")
+    ops.corr_bwd(ops.Slab(dummy, 0, c, f1), ops.Slab(dummy, 0, c, f2), ops.Slab(dout, 0, D * D), ops.Slab(d1, 0, c), ops.Slab(d2, 0, c), md, s2, ops.MATH_BF16)
+    torch.cuda.synchronize()
+    a = f1.float().cpu().double().requires_grad_(True)
+    b = f2.float().cpu().double().requires_grad_(True)
+    # the kernel multiplies the bf16 rounding of dout (the band matrix is generated in bf16)
+    flownet_c.correlation(a, b, md, s2).backward(dout.cpu()[..., :D * D].to(torch.bfloat16).double())
+    assert rel(d1, a.grad) < 2e-5
+    assert rel(d2, b.grad) < 2e-5
