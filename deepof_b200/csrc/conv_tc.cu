@@ -709,32 +709,37 @@ struct MphParams {
     TapInfo taps[TC_MAX_TAPS];
 };
 
-template <int BN, bool BF>
+// C1 = true: the FIRST-LAYER form (conv1 7x7/2 on the zero-bordered 8-channel input, bf16): one "phase", taps = filter rows whose K chunk
+// is 8 pixels x 8 channels; the halo box is {64 elements, 8 ox, 2 row parities, 19 row pairs} of the rank-5 overlapping-row map (38 KB
+// instead of 7 x 16 KB per tile), tap kh starts ((oy_k - oy_min) * 2 + parity_k) * 8 rows into it (same 2048-byte group stride), and
+// the 7 weight k-blocks (56 KB) are loaded ONCE per CTA and stay in shared memory.
+template <int BN, bool BF, bool C1 = false>
 __global__ void __launch_bounds__(TCG_THREADS, 1)
 tc_mph_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ MphParams P) {
     constexpr int KELEMS = BF ? 64 : 32;
     constexpr int B_BYTES = BN * 128;                       // one tap's weight k-block
-    constexpr int HA_BYTES = TC_HALO_ROWS * 16 * 128;       // 36 KB halo box
-    constexpr int BS_BYTES = 4 * B_BYTES;                   // B slot: up to 4 taps
-    constexpr int ACC_COLS = 4 * BN, TMEM_COLS = 2 * ACC_COLS;
-    static_assert(TMEM_COLS <= 512 && BN >= 32, "four phase accumulators, double buffered");
+    constexpr int HA_BYTES = C1 ? 19 * 2 * 8 * 128 : TC_HALO_ROWS * 16 * 128;       // 38 KB / 36 KB halo box
+    constexpr int BS_BYTES = C1 ? 8 * B_BYTES : 4 * B_BYTES;                       // B slot: up to 4 taps (C1: all <= 8 filter rows, resident)
+    constexpr int A_SLOTS = C1 ? 3 : MPH_A_SLOTS, B_SLOTS = C1 ? 1 : MPH_B_SLOTS;
+    constexpr int ACC_COLS = (C1 ? 1 : 4) * BN, TMEM_COLS = 2 * ACC_COLS;
+    static_assert(TMEM_COLS <= 512 && TMEM_COLS >= 32 && BN >= 32, "phase accumulators, double buffered");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t *smem_b = smem + MPH_A_SLOTS * HA_BYTES;
-    float *stage_f = reinterpret_cast<float *>(smem_b + MPH_B_SLOTS * BS_BYTES);
+    uint8_t *smem_b = smem + A_SLOTS * HA_BYTES;
+    float *stage_f = reinterpret_cast<float *>(smem_b + B_SLOTS * BS_BYTES);
     uint64_t *a_full = reinterpret_cast<uint64_t *>(stage_f + TCG_EPI_WARPS * 32 * 16);
-    uint64_t *a_empty = a_full + MPH_A_SLOTS;
-    uint64_t *b_full = a_empty + MPH_A_SLOTS;
-    uint64_t *b_empty = b_full + MPH_B_SLOTS;
-    uint64_t *acc_full = b_empty + MPH_B_SLOTS;
+    uint64_t *a_empty = a_full + A_SLOTS;
+    uint64_t *b_full = a_empty + A_SLOTS;
+    uint64_t *b_empty = b_full + B_SLOTS;
+    uint64_t *acc_full = b_empty + B_SLOTS;
     uint64_t *acc_empty = acc_full + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total = P.m_tiles * P.n_tiles;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < MPH_A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < MPH_B_SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < B_SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], TCG_EPI_WARPS); }
         fence_barrier_init();
     }
@@ -748,19 +753,28 @@ tc_mph_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     if (warp == TCG_EPI_WARPS) {
         if (lane == 0) {
             int ita = 0, itb = 0;
+            if (C1) {                                      // the whole filter: once per CTA (n_tiles == 1)
+                const int ntp = P.ck[0].ntaps;
+                mbar_expect_tx(&b_full[0], ntp * B_BYTES);
+                for (int tp = 0; tp < ntp; ++tp) tma_load_2d(smem_b + tp * B_BYTES, &map_b, &b_full[0], P.taps[tp].wk, 0);
+            }
             for (int t = blockIdx.x; t < total; t += gridDim.x) {
                 const int nt = t / P.m_tiles, mt = t % P.m_tiles;
                 const int tx = mt % P.tiles_x, ty = (mt / P.tiles_x) % P.tiles_y, tn = mt / (P.tiles_x * P.tiles_y);
                 const int ix0 = tx * 8, iy0 = ty * 16, n0 = nt * BN;
                 for (int cb = 0; cb < P.ncb; ++cb, ++ita) {
-                    const int sa = ita % MPH_A_SLOTS;
-                    mbar_wait(&a_empty[sa], ((ita / MPH_A_SLOTS) & 1) ^ 1);
+                    const int sa = ita % A_SLOTS;
+                    mbar_wait(&a_empty[sa], ((ita / A_SLOTS) & 1) ^ 1);
                     mbar_expect_tx(&a_full[sa], HA_BYTES);
+                    if (C1) {
+                        tma_load_5d(smem + sa * HA_BYTES, &map_a, &a_full[sa], 0, ix0, 0, iy0 + P.a_coff, tn);    // (a_coff = smallest row-pair offset)
+                        continue;
+                    }
                     tma_load_4d(smem + sa * HA_BYTES, &map_a, &a_full[sa], P.a_coff + cb * KELEMS, ix0 - 1, iy0 - 1, tn);
                     for (int c = 0; c < P.nchunks; ++c, ++itb) {
-                        const int sb = itb % MPH_B_SLOTS;
+                        const int sb = itb % B_SLOTS;
                         const int ntp = P.ck[c].ntaps;
-                        mbar_wait(&b_empty[sb], ((itb / MPH_B_SLOTS) & 1) ^ 1);
+                        mbar_wait(&b_empty[sb], ((itb / B_SLOTS) & 1) ^ 1);
                         mbar_expect_tx(&b_full[sb], ntp * B_BYTES);
                         for (int tp = 0; tp < ntp; ++tp)
                             tma_load_2d(smem_b + sb * BS_BYTES + tp * B_BYTES, &map_b, &b_full[sb], P.taps[P.ck[c].tap0 + tp].wk + cb * KELEMS, n0);
@@ -772,18 +786,31 @@ tc_mph_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         if (lane == 0) {
             constexpr uint32_t idesc = BF ? make_idesc_bf16(TC_BM, BN) : make_idesc_tf32(TC_BM, BN);
             int ita = 0, itb = 0, lt = 0;
+            if (C1) { mbar_wait(&b_full[0], 0); tc_fence_after(); }
             for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
                 const int acc = lt & 1;
                 mbar_wait(&acc_empty[acc], ((lt >> 1) & 1) ^ 1);
                 tc_fence_after();
                 for (int cb = 0; cb < P.ncb; ++cb, ++ita) {
-                    const int sa = ita % MPH_A_SLOTS;
-                    mbar_wait(&a_full[sa], (ita / MPH_A_SLOTS) & 1);
+                    const int sa = ita % A_SLOTS;
+                    mbar_wait(&a_full[sa], (ita / A_SLOTS) & 1);
                     tc_fence_after();
                     const uint32_t abuf = smem_u32(smem + sa * HA_BYTES);
+                    if (C1) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
+                        for (int tp = 0; tp < P.ck[0].ntaps; ++tp) {
+                            const TapInfo ti = P.taps[tp];
+                            const uint64_t da = make_desc_k128_halo(abuf, ((ti.oy - P.a_coff) * 2 + ti.py) * 8);
+                            const uint64_t db = make_desc_k128(smem_u32(smem_b + tp * B_BYTES));
+#pragma unroll
+                            for (int kk = 0; kk < TC_BK / 8; ++kk) umma<BF>(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (tp | kk) != 0);
+                        }
+                        umma_commit(&a_empty[sa]);
+                        continue;
+                    }
                     for (int c = 0; c < P.nchunks; ++c, ++itb) {
-                        const int sb = itb % MPH_B_SLOTS;
-                        mbar_wait(&b_full[sb], (itb / MPH_B_SLOTS) & 1);
+                        const int sb = itb % B_SLOTS;
+                        mbar_wait(&b_full[sb], (itb / B_SLOTS) & 1);
                         tc_fence_after();
                         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS + P.ck[c].phase * BN);
                         const uint32_t bbuf = smem_u32(smem_b + sb * BS_BYTES);
@@ -824,7 +851,8 @@ tc_mph_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 #pragma unroll 1
             for (int ph = 0; ph < P.nphase; ++ph) {
                 const bool row_ok = ix < P.ph[ph].cnt_x && iy < P.ph[ph].cnt_y;
-                const long long my_off = row_ok ? (((long long)tn * P.rh + P.ph[ph].y0 + iy * 2) * P.rw + P.ph[ph].x0 + ix * 2) * P.out_ld : -1;
+                const int rs = C1 ? 1 : 2;
+                const long long my_off = row_ok ? (((long long)tn * P.rh + P.ph[ph].y0 + iy * rs) * P.rw + P.ph[ph].x0 + ix * rs) * P.out_ld : -1;
                 const bool fast = __all_sync(0xffffffffu, row_ok) && out_al && (colfull || (P.n_valid & 3) == 0);
                 long long offs[4];
 #pragma unroll
@@ -1956,6 +1984,41 @@ int tc_conv1_fwd(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, in
     const uint64_t str[1] = {(uint64_t)g->kh * 64 * (bf ? 2 : 4)};
     const uint32_t box[2] = {bf ? 64u : 32u, (uint32_t)bn};
     if (make_map(&mb, wp, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32)) return 1;
+    // ---- bf16, 64 output channels, maps of at least 16 x 8: row-halo tiles with the whole filter resident in shared memory (tc_mph_kernel<.., C1>) ----
+    if (g_mph && bf && g->co > 32 && g->co <= 64 && g->oh >= 16 && g->ow >= 8 && g->kh <= 8) {
+        int omin = 1 << 20, omax = -(1 << 20);
+        for (int kh = 0; kh < g->kh; ++kh) { omin = P.taps[kh].oy < omin ? P.taps[kh].oy : omin; omax = P.taps[kh].oy > omax ? P.taps[kh].oy : omax; }
+        if (omax - omin <= 3) {
+            MphParams M;
+            memset(&M, 0, sizeof(M));
+            M.out = y; M.out16 = reinterpret_cast<__nv_bfloat16 *>(y16); M.out_ld = y_ld; M.bias = bias;
+            M.n_valid = g->co; M.rh = g->oh; M.rw = g->ow; M.B = g->B;
+            M.tiles_x = (g->ow + 7) / 8; M.tiles_y = (g->oh + 15) / 16; M.m_tiles = M.tiles_x * M.tiles_y * g->B; M.n_tiles = 1;
+            M.a_coff = omin; M.ncb = 1; M.act = act; M.accumulate = 0; M.nphase = 1; M.nchunks = 1;
+            M.ph[0].y0 = 0; M.ph[0].x0 = 0; M.ph[0].cnt_y = g->oh; M.ph[0].cnt_x = g->ow;
+            M.ck[0].phase = 0; M.ck[0].tap0 = 0; M.ck[0].ntaps = (short)g->kh; M.ck[0].first = 1;
+            for (int kh = 0; kh < g->kh; ++kh) M.taps[kh] = P.taps[kh];
+            const int rowoff_c = xp_x0 - g->pad_l;
+            const uint64_t rowb = (uint64_t)xp_w * 8 * 2;
+            const uint64_t adims[5] = {64, (uint64_t)g->ow, 2, (uint64_t)xp_h / 2, (uint64_t)g->B};
+            const uint64_t astr[4] = {16 * 2, rowb, 2 * rowb, (uint64_t)xp_h * rowb};
+            const uint32_t abox[5] = {64u, 8u, 2u, 19u, 1u};
+            CUtensorMap mah;
+            if (make_map(&mah, static_cast<const uint8_t *>(x16) + (size_t)rowoff_c * 8 * 2, 5, adims, astr, abox, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)) return 1;
+            constexpr int smem_c1 = 3 * 19 * 2 * 8 * 128 + 8 * 64 * 128 + TCG_EPI_WARPS * 32 * 16 * 4 + 1024 + 256;
+            static_assert(smem_c1 <= 227 * 1024, "shared-memory budget");
+            static bool cfgd = false;
+            if (!cfgd) {
+                DOFB_CUDA_OK(cudaFuncSetAttribute(tc_mph_kernel<64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_c1));
+                cfgd = true;
+            }
+            const int grid = M.m_tiles < num_sms() ? M.m_tiles : num_sms();
+            tc_mph_kernel<64, true, true><<<grid, TCG_THREADS, smem_c1, st>>>(mah, mb, M);
+            DOFB_LAUNCH_OK();
+            return 0;
+        }
+    }
     const int n_tiles = (g->co + bn - 1) / bn;
     if (bf) {
         switch (bn) {

@@ -5,10 +5,11 @@
 // and version1/model/warpflow.loss_interp (warpflow.py:4-173, variant B): B*3*4 tf.gather
 // nodes + ~40 element-wise/reduce nodes per scale, plus their TF-autodiff gradients.
 //
-// HBM-bound: algorithmic traffic is 44 B/pixel forward (flow 8 + src 12 + tgt 12 + recon 12)
-// + 8 B/pixel for dflow.  Layout NHWC fp32; each thread owns 4 consecutive pixels so that
-// flow / src / recon / dflow move as float4; the 4-corner gather of the target goes through
-// the read-only path (neighbouring pixels share 128 B lines, so it is L1/L2 resident).
+// Algorithmic traffic is 44 B/pixel forward (flow 8 + src 12 + tgt 12 + recon 12) + 8 B/pixel for dflow.  Layout NHWC fp32; a block
+// owns 1024 consecutive pixels: its flow and source streams are staged into shared memory by two TMA bulk copies (cp.async.bulk +
+// mbarrier), each thread owns 4 consecutive pixels (float4 traffic for flow / src / recon / dflow); the 4-corner gather of the target
+// is data dependent and goes through the read-only path (neighbouring pixels share 128 B lines: L1/L2 resident).
+// At these sizes the kernel is bound by the ~10 powf per pixel of the Charbonnier terms (kept exact for parity), not by HBM.
 // Reduction: warp shuffle -> block -> per-block partial in a workspace; the LAST block to
 // finish (atomic ticket) sums the partials in a fixed order, so the loss is bit-stable.
 #include "common.cuh"
@@ -178,23 +179,51 @@ __device__ __forceinline__ void do_pixel(const WLScale &S, long long pix, float 
     dV = dv;
 }
 
+// ---- TMA (bulk async copy) staging of a block's contiguous operand streams ----
+// A block owns 1024 consecutive pixels of one scale: their flow (8 KB) and source (12 KB) values are two contiguous byte ranges, fetched
+// by ONE thread with two cp.async.bulk copies that complete on an mbarrier; the 256 threads then read their float4s from shared memory.
+// (The target image is gathered at data-dependent positions and stays on the read-only L1/L2 path.)
+__device__ __forceinline__ uint32_t wl_smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void wl_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(wl_smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(wl_smem_u32(bar))
+                 : "memory");
+}
+
 template <int VARIANT>
-__device__ __forceinline__ void run_scale(const WLScale &S, int local_block, Acc3 &acc) {
+__device__ __forceinline__ void run_scale(const WLScale &S, int local_block, Acc3 &acc, float *stage, uint64_t *bar) {
     const long long npix = (long long)S.B * S.h * S.w;
-    const long long p0 = ((long long)local_block * WL_THREADS + threadIdx.x) * WL_PPT;
+    const long long pb = (long long)local_block * WL_PIX_PER_BLOCK;
+    const long long p0 = pb + (long long)threadIdx.x * WL_PPT;
+    const bool staged = S.vec_ok && pb + WL_PIX_PER_BLOCK <= npix;      // (block-uniform) full block, 16-byte aligned streams
+    if (staged) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(wl_smem_u32(bar)));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(wl_smem_u32(bar)), "r"(WL_PIX_PER_BLOCK * 20) : "memory");
+            wl_bulk_g2s(stage, S.flow + pb * 2, WL_PIX_PER_BLOCK * 8, bar);
+            wl_bulk_g2s(stage + WL_PIX_PER_BLOCK * 2, S.src + pb * 3, WL_PIX_PER_BLOCK * 12, bar);
+        }
+        __syncthreads();                                                // barrier initialised before anyone polls it
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tWL_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra WL_DONE;\n\tbra WL_WAIT;\n\tWL_DONE:\n\t}" ::"r"(
+                wl_smem_u32(bar))
+            : "memory");
+    }
     if (p0 >= npix) return;
     const bool want_grad = S.dflow != nullptr;
     if (S.vec_ok && p0 + WL_PPT <= npix) {
         // float4 path: 4 pixels = 2 float4 of flow, 3 float4 of src / recon, 2 float4 of dflow
         float f[8], s3[12], rec[12], dfl[8];
-        const float4 *fp = reinterpret_cast<const float4 *>(S.flow + p0 * 2);
-        const float4 *sp = reinterpret_cast<const float4 *>(S.src + p0 * 3);
+        const float4 *fp = staged ? reinterpret_cast<const float4 *>(stage + threadIdx.x * 8) : reinterpret_cast<const float4 *>(S.flow + p0 * 2);
+        const float4 *sp = staged ? reinterpret_cast<const float4 *>(stage + WL_PIX_PER_BLOCK * 2 + threadIdx.x * 12)
+                                  : reinterpret_cast<const float4 *>(S.src + p0 * 3);
         float4 t;
-        t = __ldg(fp);     f[0] = t.x; f[1] = t.y; f[2] = t.z; f[3] = t.w;
-        t = __ldg(fp + 1); f[4] = t.x; f[5] = t.y; f[6] = t.z; f[7] = t.w;
+        t = fp[0]; f[0] = t.x; f[1] = t.y; f[2] = t.z; f[3] = t.w;
+        t = fp[1]; f[4] = t.x; f[5] = t.y; f[6] = t.z; f[7] = t.w;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            t = __ldg(sp + i);
+            t = sp[i];
             s3[4 * i] = t.x; s3[4 * i + 1] = t.y; s3[4 * i + 2] = t.z; s3[4 * i + 3] = t.w;
         }
 #pragma unroll
@@ -234,8 +263,10 @@ __global__ void __launch_bounds__(WL_THREADS) warp_loss_kernel(const __grid_cons
         if ((int)blockIdx.x >= P.sc[i].block_begin) si = i;
     const WLScale &S = P.sc[si];
     Acc3 acc = {0.f, 0.f, 0.f};
-    if (S.variant == 0) run_scale<0>(S, blockIdx.x - S.block_begin, acc);
-    else run_scale<1>(S, blockIdx.x - S.block_begin, acc);
+    __shared__ __align__(128) float stage[WL_PIX_PER_BLOCK * 5];      // flow (2 floats / pixel) | source (3 floats / pixel) of this block
+    __shared__ __align__(8) uint64_t stage_bar;
+    if (S.variant == 0) run_scale<0>(S, blockIdx.x - S.block_begin, acc, stage, &stage_bar);
+    else run_scale<1>(S, blockIdx.x - S.block_begin, acc, stage, &stage_bar);
 
     // ---- block reduction ----
     __shared__ float red[3][WL_THREADS / 32];

@@ -24,17 +24,45 @@ class GradReducer:
     makes that stream wait for the gradients already enqueued, and the remaining backward kernels overlap the transfer over
     NVLink 5 / NVSwitch.  ``finish()`` joins before Adam and returns the 1/world scale the optimiser folds in."""
 
-    def __init__(self, engine, bucket_mb: float = 32.0, group=None):
+    def __init__(self, engine, bucket_mb: float = 32.0, tail_mb: float = 4.0, group=None):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed must be initialised before building a GradReducer")
         self.engine = engine
         self.group = group
         self.world = dist.get_world_size(group)
-        n = engine.grad.numel()
-        per = max(int(bucket_mb * (1 << 20) // 4), 1)
-        self.bounds = [(i, min(i + per, n)) for i in range(0, n, per)]      # ascending; consumed from the end
+        self.bounds = self.plan_buckets(list(engine.arena.offsets.values()), engine.grad.numel(), bucket_mb, tail_mb)
         self._next = len(self.bounds) - 1
         self._works = []
+
+    @staticmethod
+    def plan_buckets(tensor_offsets, numel: int, bucket_mb: float = 32.0, tail_mb: float = 4.0):
+        """Ascending (start, end) element ranges, cut at TENSOR boundaries so that a bucket can be issued the moment the layer that completes
+        it has run.  The backward finishes the arena back to front, so the LAST bucket to become ready is the one at offset 0 (conv1 ...):
+        nothing can overlap its all-reduce, hence it is kept small (<= tail_mb); the others are >= bucket_mb so that NVLink sees few, large
+        messages."""
+        starts = sorted(set(int(o) for o in tensor_offsets))
+        assert starts and starts[0] == 0
+        per, tail = max(int(bucket_mb * (1 << 20) // 4), 1), max(int(tail_mb * (1 << 20) // 4), 1)
+        # first bucket (offset 0): as many leading tensors as fit into tail_mb (at least one)
+        cuts = [0]
+        first_end = numel
+        for o in starts[1:]:
+            if o > tail:
+                break
+            first_end = o
+        if first_end >= numel:
+            return [(0, numel)]
+        cuts.append(first_end)
+        # the rest, walking forward: close a bucket at the first tensor boundary past bucket_mb
+        for o in starts:
+            if o > cuts[-1] and o - cuts[-1] >= per:
+                cuts.append(o)
+        if cuts[-1] != numel:
+            if numel - cuts[-1] < per // 4 and len(cuts) > 2:      # a small remainder joins its neighbour
+                cuts[-1] = numel
+            else:
+                cuts.append(numel)
+        return [(a, b) for a, b in zip(cuts[:-1], cuts[1:])]
 
     def broadcast_params(self, src: int = 0):
         dist.broadcast(self.engine.theta, src=src, group=self.group)

@@ -50,3 +50,24 @@ def flow_ee(f1, f2, mask=None):
     f1, f2 = np.asarray(f1), np.asarray(f2)
     ee_tot = np.sqrt((f1[:, :, :, 0] - f2[:, :, :, 0]) ** 2 + (f1[:, :, :, 1] - f2[:, :, :, 1]) ** 2)
     return np.mean(ee_tot, axis=None)
+
+
+def pad_to_multiple(images, mult: int = 64, mode: str = "replicate"):
+    """[B,H,W,C] -> [B,ceil(H/mult)*mult,ceil(W/mult)*mult,C] by padding the bottom / right edge (Sintel's 436 x 1024 -> 448 x 1024: the
+    engines need H and W to be multiples of 64).  Returns (padded, (H, W)) so that outputs can be cropped back with ``crop_to``."""
+    import torch
+    import torch.nn.functional as F
+    t = torch.as_tensor(images)
+    B, H, W, C = t.shape
+    ph, pw = (-H) % mult, (-W) % mult
+    if ph == 0 and pw == 0:
+        return t, (H, W)
+    x = t.permute(0, 3, 1, 2).float()
+    x = F.pad(x, (0, pw, 0, ph), mode=mode if mode != "zeros" else "constant")
+    return x.permute(0, 2, 3, 1).contiguous(), (H, W)
+
+
+def crop_to(t, hw, scale: int = 1):
+    """Crop a [B,h,w,C] map produced at 1/scale resolution of a padded input back to the un-padded size hw."""
+    h, w = -(-hw[0] // scale), -(-hw[1] // scale)
+    return t[:, :h, :w, :]

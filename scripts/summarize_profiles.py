@@ -59,3 +59,34 @@ for rep, title in (("prof_tc_gemm.ncu-rep", "tcgen05 gather-GEMM (conv fwd / dgr
     if (OUT / rep).exists():
         print(f"## {title}, `ncu --set full`  (`gpurun_out/{rep}`)\n")
         rep_table(rep)
+
+
+def traffic_json():
+    """gpurun_out/tc_traffic_<math>.csv (ncu dram bytes per tc_* launch of one step) -> profiles/r02_tc_traffic_<math>.json (bench.py: roofline.traffic)."""
+    import json
+    path = OUT / f"tc_traffic_{math}.csv"
+    if not path.exists():
+        return
+    rows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))]
+    hdr = rows[0]
+    ik, im, iv, iu, iid = hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit"), hdr.index("ID")
+    per = collections.OrderedDict()
+    for r in rows[1:]:
+        d = per.setdefault(r[iid], {"kernel": re.sub(r"\(.*", "", r[ik]).replace("void ", "").replace("dofb::", ""), "bytes": 0.0, "us": 0.0})
+        v = float(r[iv].replace(",", ""))
+        if r[im].startswith("dram__bytes"):
+            d["bytes"] += v * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[iu], 1.0)
+        elif r[im].startswith("gpu__time"):
+            d["us"] = v / 1000.0 if r[iu] in ("ns", "nsecond") else v
+    launches = list(per.values())
+    build = subprocess.run(["git", "log", "--format=%h", "-1"], capture_output=True, text=True, cwd=ROOT).stdout.strip()
+    out = {"source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:tc_ python scripts/prof_heads.py {math} "
+                     "(one training step, B=32, 384x512)", "build": build, "launches": len(launches),
+           "dram_bytes_total": sum(d["bytes"] for d in launches), "dram_bytes_per_launch": sum(d["bytes"] for d in launches) / max(len(launches), 1),
+           "time_us_total": sum(d["us"] for d in launches),
+           "per_launch": [{"kernel": d["kernel"], "us": round(d["us"], 1), "dram_MB": round(d["bytes"] / 1e6, 1)} for d in sorted(launches, key=lambda d: -d["us"])]}
+    (ROOT / "profiles" / f"r02_tc_traffic_{math}.json").write_text(json.dumps(out, indent=1))
+    print(f"tc_* DRAM traffic: {out['dram_bytes_total'] / 1e9:.2f} GB over {len(launches)} launches -> profiles/r02_tc_traffic_{math}.json\n")
+
+
+traffic_json()

@@ -88,25 +88,29 @@ sys.path.insert(0, {root!r})
 from deepof_b200.ddp import GradReducer
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", rank=rank, world_size=world)
+class Arena:
+    # 10 "tensors" of 100000 floats (+3 at the end): bucket cuts fall on tensor boundaries
+    offsets = {{f"t{{i}}": i * 100000 for i in range(10)}}
 class Eng:
-    pass
+    arena = Arena()
 e = Eng()
 n = 1000003
 e.grad = torch.full((n,), float(rank + 1))
 e.theta = torch.full((n,), float(rank))
-r = GradReducer(e, bucket_mb=1.0)
+r = GradReducer(e, bucket_mb=1.0, tail_mb=0.5)
 r.broadcast_params()
 assert float(e.theta.abs().max()) == 0.0          # rank 0's parameters everywhere
 scale = r(e.grad)
 assert abs(scale - 1.0 / world) < 1e-12
 want = sum(range(1, world + 1))
 assert torch.all(e.grad == want), (rank, e.grad[:3])
-assert len(r.bounds) == 4 and r.bounds[-1][1] == n
+# tail bucket: the leading tensors that fit 0.5 MB (131072 floats -> one tensor); then >= 1 MB (262144 floats -> 3 tensors) each
+assert r.bounds == [(0, 100000), (100000, 400000), (400000, 700000), (700000, n)], r.bounds
 # overlapped form: the backward reports falling arena offsets; every bucket is reduced exactly once, top bucket first
 e.grad.fill_(float(rank + 1))
 r.begin()
-r.ready(900000); assert len(r._works) == 0          # the last bucket starts at 786432: not yet entirely final
-r.ready(786432); assert len(r._works) == 1
+r.ready(900000); assert len(r._works) == 0          # the last bucket starts at 700000: not yet entirely final
+r.ready(700000); assert len(r._works) == 1
 r.ready(300000); assert len(r._works) == 2
 r.ready(300000); assert len(r._works) == 2          # idempotent
 assert abs(r.finish() - 1.0 / world) < 1e-12
