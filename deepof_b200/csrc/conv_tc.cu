@@ -684,6 +684,154 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------
+// Swapped-operand gather-GEMM for NARROW outputs (<= 128 output channels).
+//
+// Measured on B200 (round 2): a tcgen05.mma with M = 128 costs ~125 cycles whatever its N -- the layers with N = 32 / 64 / 128 output
+// columns ran at 12 / 25 / 50 % of the tensor peak no matter how little data they moved (the multi-phase halo kernel below cut the
+// L2->SM traffic of upconv1 3.7x and gained 8 %).  The instruction count is what matters, so these layers put the OUTPUT CHANNELS on M
+// and 256 PIXELS on N:   D^T[channel, pixel] = W[channel, K] . X[pixel, K]^T
+//   A operand = the weight k-block (<= 128 rows, zero-filled by TMA beyond the layer's channels), B operand = TWO pixel tiles (2 x 128
+//   rows x 128 B, the same TMA boxes as before, contiguous in the stage) -> one M=128 x N=256 instruction per 256 pixels and k-step
+//   instead of two (or, at N = 32, instead of two that fill an eighth of the array).
+// The accumulator is transposed -- TMEM lane = output channel, column = pixel -- which is exactly what NHWC wants: a warp holds 32
+// consecutive channels of one pixel per register, so the epilogue stores straight from registers (64 / 128 contiguous bytes per
+// instruction), no shared-memory transpose.  Same persistent pipeline, phases, parity gathers and padding-by-OOB-fill as
+// tc_gather_gemm_kernel; warps 0-3 drain the first pixel tile of the pair, warps 4-7 the second.
+// ------------------------------------------------------------------------------------------------
+template <int STAGES, bool BF>
+__global__ void __launch_bounds__(TCG_THREADS, 1)
+tc_swap_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ TcParams P) {
+    constexpr int KELEMS = BF ? 64 : 32;
+    constexpr int W_BYTES = 128 * 128;                      // weight k-block: 128 channel rows
+    constexpr int STAGE_BYTES = 2 * TC_A_BYTES + W_BYTES;   // 48 KB
+    constexpr int ACC_COLS = 256, TMEM_COLS = 512;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+    uint64_t *empty_bar = full_bar + STAGES;
+    uint64_t *acc_full = empty_bar + STAGES;
+    uint64_t *acc_empty = acc_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_units = (P.m_tiles + 1) / 2;
+    const int total = m_units * P.n_tiles;
+    if (threadIdx.x == 0) {
+        for (int s2 = 0; s2 < STAGES; ++s2) { mbar_init(&full_bar[s2], 1); mbar_init(&empty_bar[s2], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], TCG_EPI_WARPS); }
+        fence_barrier_init();
+    }
+    if (warp == TCG_EPI_WARPS && lane == 0) { prefetch_tmap(&map_a); prefetch_tmap(&map_b); }
+    if (warp == TCG_EPI_WARPS + 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == TCG_EPI_WARPS) {
+        if (lane == 0) {
+            int it = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x) {
+                const int nt = t / m_units, u = t % m_units;
+                const TileView V0 = tile_view(P, 2 * u), V1 = tile_view(P, 2 * u + 1);
+                const int kiters = V0.ntaps * P.ncb;
+                int tp = V0.tap0, cb = 0;
+                for (int si = 0; si < kiters; ++si, ++it) {
+                    const int s2 = it % STAGES;
+                    mbar_wait(&empty_bar[s2], ((it / STAGES) & 1) ^ 1);
+                    mbar_expect_tx(&full_bar[s2], STAGE_BYTES);
+                    const TapInfo ti = P.taps[tp];
+                    uint8_t *sa = smem + s2 * STAGE_BYTES;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const TileView &V = j ? V1 : V0;
+                        const int mt = V.mt;
+                        const int tx = mt % V.tiles_x, ty = (mt / V.tiles_x) % V.tiles_y, tn = mt / (V.tiles_x * V.tiles_y);
+                        const int ix0 = tx * P.TW, iy0 = ty * P.TH, in0 = tn * P.TN;
+                        if (P.parity)
+                            tma_load_5d(sa + j * TC_A_BYTES, &map_a, &full_bar[s2], ti.px * P.a_ld + P.a_coff + cb * KELEMS, ix0 + ti.ox, ti.py, iy0 + ti.oy, in0);
+                        else
+                            tma_load_4d(sa + j * TC_A_BYTES, &map_a, &full_bar[s2], P.a_coff + cb * KELEMS, ix0 + ti.ox, iy0 + ti.oy, in0);
+                    }
+                    tma_load_2d(sa + 2 * TC_A_BYTES, &map_b, &full_bar[s2], ti.wk + cb * KELEMS, nt * 128);
+                    if (++cb == P.ncb) { cb = 0; ++tp; }
+                }
+            }
+        }
+    } else if (warp == TCG_EPI_WARPS + 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = BF ? make_idesc_bf16(TC_BM, 256) : make_idesc_tf32(TC_BM, 256);
+            int it = 0, lt = 0;
+            for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+                const int acc = lt & 1;
+                mbar_wait(&acc_empty[acc], ((lt >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
+                const int kiters = tile_view(P, 2 * (t % m_units)).ntaps * P.ncb;
+                for (int si = 0; si < kiters; ++si, ++it) {
+                    const int s2 = it % STAGES;
+                    mbar_wait(&full_bar[s2], (it / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s2 * STAGE_BYTES);
+                    const uint64_t dw = make_desc_k128(sa + 2 * TC_A_BYTES), dx = make_desc_k128(sa);       // A = weights, B = 256 pixel rows
+#pragma unroll
+                    for (int kk = 0; kk < TC_BK / 8; ++kk) umma<BF>(d_tmem, dw + (uint64_t)(kk * 2), dx + (uint64_t)(kk * 2), idesc, (si | kk) != 0);
+                    umma_commit(&empty_bar[s2]);
+                }
+                umma_commit(&acc_full[acc]);
+            }
+        }
+    } else {
+        // ===== epilogue: lane = output channel, register index = pixel; warps 0-3 own pixel tile 0 of the pair, warps 4-7 tile 1 =====
+        const int quad = warp & 3, half = warp >> 2;
+        const bool has32 = P.out != nullptr, has16 = P.out16 != nullptr, accum = P.accumulate != 0, elu = P.act == DOFB_ACT_ELU;
+        const int tw_sh = 31 - __clz(P.TW), th_sh = 31 - __clz(P.TH);        // TW, TH are powers of two (choose_tile)
+        int lt = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+            const int nt = t / m_units, u = t % m_units;
+            const TileView V = tile_view(P, 2 * u + half);
+            const int mt = V.mt;
+            const int tx = mt % V.tiles_x, ty = (mt / V.tiles_x) % V.tiles_y, tn = mt / (V.tiles_x * V.tiles_y);
+            const int ch = nt * 128 + quad * 32 + lane;
+            const bool ch_ok = ch < P.n_valid;
+            const float bias = (P.bias != nullptr && ch_ok) ? __ldg(P.bias + ch) : 0.f;
+            const int acc = lt & 1;
+            mbar_wait(&acc_full[acc], (lt >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c32 = 0; c32 < 4; ++c32) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * ACC_COLS + half * 128 + c32 * 32), v);
+                if (nt * 128 + quad * 32 >= P.n_valid) continue;            // (warp-uniform: this warp's 32 channels are all padding)
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int r = c32 * 32 + i;                             // row of the pixel tile (warp-uniform)
+                    const int ix = tx * P.TW + (r & (P.TW - 1)), iy = ty * P.TH + ((r >> tw_sh) & (P.TH - 1)), nn = tn * P.TN + (r >> (tw_sh + th_sh));
+                    if (ix >= V.cnt_x || iy >= V.cnt_y || nn >= P.B) continue;
+                    const long long off = (((long long)nn * P.rh + V.y0 + iy * P.rstep) * P.rw + V.x0 + ix * P.rstep) * P.out_ld + ch;
+                    float o = v[i] + bias;
+                    if (elu) o = o > 0.f ? o : __expf(o) - 1.f;
+                    if (ch_ok) {
+                        if (accum) o += P.out[off];
+                        if (has32) P.out[off] = o;
+                        if (has16) P.out16[off] = __float2bfloat16_rn(o);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TCG_EPI_WARPS + 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Multi-phase halo gather-GEMM: stride-2 transposed gathers with narrow N (transposed-conv forwards 4x4/2 to 32 / 64 channels, input
 // gradients of 5x5/2 and 3x3/2 convs to <= 128 channels).
 //
@@ -1078,7 +1226,11 @@ static unsigned long long g_weight_epoch = 1;      // bumped by dofb_invalidate_
 static bool g_cache_enabled = false;               // off: every call re-packs (always correct); on: caller promises to invalidate
 static bool g_halo = false;                        // halo-tile reuse of A across filter taps (dofb_enable_halo_tiles)
 void enable_halo(int on) { g_halo = on != 0; }
-static bool g_mph = true;                          // multi-phase halo kernel for narrow stride-2 transposed gathers (dofb_enable_multiphase_halo)
+static bool g_swap = true;                         // swapped-operand kernel for <= 128 output channels (dofb_enable_swapped_narrow)
+void enable_swap(int on) { g_swap = on != 0; }
+static bool g_c1 = true;                           // conv1: row-halo tiles + resident filter (tc_mph_kernel<.., C1>)
+void enable_c1(int on) { g_c1 = on != 0; }
+static bool g_mph = false;                         // multi-phase halo kernel for narrow stride-2 transposed gathers (dofb_enable_multiphase_halo)
 void enable_mph(int on) { g_mph = on != 0; }
 static bool g_cta_pairs = false;                   // cta_group::2 tiles for the 256-column layers (dofb_enable_cta_pairs)
 void enable_cta_pairs(int on) { g_cta_pairs = on != 0; }
@@ -1386,6 +1538,29 @@ static int run_gather(const GatherSpec &G, const TcParams &Pin, cudaStream_t st)
                                  (uint64_t)G.ah * G.aw * G.a_ld * esz};
         const uint32_t box[5] = {(uint32_t)kel, (uint32_t)P.TW, 1, (uint32_t)P.TH, (uint32_t)P.TN};
         if (make_map(&ma, abase, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, dt)) return 1;
+    }
+    // ---- narrow outputs (<= 128 channels): channels on M, 256 pixels on N (tc_swap_gemm_kernel) ----
+    if (g_swap && !halo && n_rows <= 128) {
+        const uint64_t dims[2] = {(uint64_t)taps_all * cpad, (uint64_t)n_rows};
+        const uint64_t str[1] = {(uint64_t)taps_all * cpad * esz};
+        const uint32_t box[2] = {(uint32_t)kel, 128u};
+        if (make_map(&mb, wp, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, dt)) return 1;
+        P.m_tiles = tiles; P.n_tiles = 1;
+        constexpr int SW_STAGES = 4;
+        constexpr int smem_sw = SW_STAGES * (2 * TC_A_BYTES + 128 * 128) + 1024 + 256;
+        static_assert(smem_sw <= 227 * 1024, "shared-memory budget");
+        static bool cfgd = false;
+        if (!cfgd) {
+            DOFB_CUDA_OK(cudaFuncSetAttribute(tc_swap_gemm_kernel<SW_STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sw));
+            DOFB_CUDA_OK(cudaFuncSetAttribute(tc_swap_gemm_kernel<SW_STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sw));
+            cfgd = true;
+        }
+        const int units = (tiles + 1) / 2;
+        const int grid = units < num_sms() ? units : num_sms();
+        if (bf) tc_swap_gemm_kernel<SW_STAGES, true><<<grid, TCG_THREADS, smem_sw, st>>>(ma, mb, P);
+        else tc_swap_gemm_kernel<SW_STAGES, false><<<grid, TCG_THREADS, smem_sw, st>>>(ma, mb, P);
+        DOFB_LAUNCH_OK();
+        return 0;
     }
     int bn = n_rows > 128 ? 256 : (n_rows > 64 ? 128 : (n_rows > 32 ? 64 : 32));
     while (bn > 64 && (long long)tiles * ((n_rows + bn - 1) / bn) < num_sms()) bn >>= 1;   // small maps: more, narrower tiles
@@ -1985,7 +2160,7 @@ int tc_conv1_fwd(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, in
     const uint32_t box[2] = {bf ? 64u : 32u, (uint32_t)bn};
     if (make_map(&mb, wp, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32)) return 1;
     // ---- bf16, 64 output channels, maps of at least 16 x 8: row-halo tiles with the whole filter resident in shared memory (tc_mph_kernel<.., C1>) ----
-    if (g_mph && bf && g->co > 32 && g->co <= 64 && g->oh >= 16 && g->ow >= 8 && g->kh <= 8) {
+    if (g_c1 && bf && g->co > 32 && g->co <= 64 && g->oh >= 16 && g->ow >= 8 && g->kh <= 8) {
         int omin = 1 << 20, omax = -(1 << 20);
         for (int kh = 0; kh < g->kh; ++kh) { omin = P.taps[kh].oy < omin ? P.taps[kh].oy : omin; omax = P.taps[kh].oy > omax ? P.taps[kh].oy : omax; }
         if (omax - omin <= 3) {

@@ -9,8 +9,11 @@ import torch
 # and the north_star bound on the evaluation-recipe EPE
 TOLERANCE = {
     "fp32": {"epd_mean_px": 2e-5, "epd_max_px": 5e-4, "epe_abs": 1e-3},
-    "tf32": {"epd_mean_px": 1e-3, "epd_max_px": 2e-2, "epe_abs": 1e-3},
-    "bf16": {"epd_mean_px": 5e-3, "epd_max_px": 8e-2, "epe_abs": 1e-3},
+    # measured (scripts/precision_report.py, 192x256; bench.py re-measures at 384x512): tf32 mean 1.2e-3..3.3e-3 / max 4e-3..1.7e-2 px,
+    # bf16 mean 2.6e-3..4.1e-3 / max 1.2e-2..1.4e-2 px at scale 1 (init .. trained weights); kind::tf32 TRUNCATES its operands to 10
+    # mantissa bits while the bf16 operands are rounded to nearest, which is why bf16 is no worse than tf32 here
+    "tf32": {"epd_mean_px": 8e-3, "epd_max_px": 5e-2, "epe_abs": 1e-3},
+    "bf16": {"epd_mean_px": 8e-3, "epd_max_px": 5e-2, "epe_abs": 1e-3},
 }
 
 

@@ -645,3 +645,63 @@ def test_bf16_correlation_backward_matches_oracle(B, h, w, md, s2):
     flownet_c.correlation(a, b, md, s2).backward(dout.cpu()[..., :D * D].to(torch.bfloat16).double())
     assert rel(d1, a.grad) < 2e-5
     assert rel(d2, b.grad) < 2e-5
+
+
+SWAP_CASES = [
+    # kind, B, H, W, ci, co, k, s      (fwd: N = co; dgrad: N = ci of the conv)
+    ("fwd", 2, 24, 32, 64, 128, 5, 2),        # conv2-like: parity gather, N = 128
+    ("fwd", 3, 10, 14, 32, 32, 3, 1),         # ragged, odd tile count (phantom second tile)
+    ("fwd", 1, 48, 64, 98, 20, 1, 1),         # flow-head Z map: 20 columns
+    ("dgrad", 2, 48, 64, 64, 128, 5, 2),      # conv2 input gradient: 4 phases, N = 64
+    ("dgrad", 2, 48, 64, 32, 194, 4, 2),      # upconv1 forward form (N = 32)
+    ("dgrad", 1, 12, 16, 128, 256, 3, 1),     # unit stride, N = 128
+]
+
+
+@pytest.mark.parametrize("case", SWAP_CASES)
+@pytest.mark.parametrize("mth", [1, 2])
+def test_swapped_operand_kernel_matches_generic_and_oracle(case, mth):
+    """tc_swap_gemm_kernel (output channels on M, 256 pixels on N) against the generic tile kernel and the CPU oracle."""
+    from deepof_b200 import ops, _lib
+    from oracle import tf_ops
+    kind, B, H, W, ci, co, k, s = case
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(17 + sum(case[1:]))
+    geom = ops.conv_geom(B, H, W, ci, co, k, s)
+    P = 64 if mth == 2 else 32
+    wt = (torch.randn(k, k, ci, co, generator=g) / math.sqrt(k * k * (ci if kind == "fwd" else co))).cuda()
+    if kind == "fwd":
+        x = _buf(B, H, W, (ci + P - 1) // P * P, ci, g)
+        bias = (torch.randn(co, generator=g) * 0.1).cuda()
+        n, oshape = co, (B, geom.oh, geom.ow)
+    else:
+        x = _buf(B, geom.oh, geom.ow, (co + P - 1) // P * P, co, g)
+        bias, n, oshape = None, ci, (B, H, W)
+    if mth == 2:
+        x = x.to(torch.bfloat16).float()
+    ld_o = (n + 3) // 4 * 4 + 4
+    outs = []
+    for on in (0, 1):
+        lib.dofb_enable_swapped_narrow(on)
+        for accumulate in ((False, True) if kind == "dgrad" else (False,)):
+            y = torch.full((*oshape, ld_o), 0.5, device="cuda")
+            xs = ops.Slab(x, 0, ci if kind == "fwd" else co, x.to(torch.bfloat16) if mth == 2 else None)
+            if kind == "fwd":
+                ops.conv_fwd(geom, xs, wt, bias, ops.Slab(y, 4, n), ops.ACT_ELU, mth)
+            else:
+                ops.conv_dgrad(geom, xs, wt, None, ops.Slab(y, 4, n), ops.ACT_NONE, accumulate, mth)
+            torch.cuda.synchronize()
+            outs.append(y)
+    lib.dofb_enable_swapped_narrow(1)
+    half = len(outs) // 2
+    for a, b in zip(outs[:half], outs[half:]):
+        assert rel(b[..., 4:4 + n], a[..., 4:4 + n]) < 2e-5
+        assert float((b[..., :4] - 0.5).abs().max()) == 0.0 and float((b[..., 4 + n:] - 0.5).abs().max()) == 0.0
+    wq = wt.cpu().to(torch.bfloat16).double() if mth == 2 else wt.cpu().double()
+    if kind == "fwd":
+        want = tf_ops.elu(tf_ops.conv2d_same(x.cpu()[..., :ci].double(), wq, bias.cpu().double(), s))
+    else:
+        xd = torch.zeros(B, H, W, ci, dtype=torch.float64, requires_grad=True)
+        tf_ops.conv2d_same(xd, wq, None, s).backward(x.cpu()[..., :co].double())
+        want = xd.grad
+    assert rel(outs[half][..., 4:4 + n], want) < (3e-5 if mth == 2 else TOL)
