@@ -1913,6 +1913,16 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 atomic_add_row32(dst, v, min(32, P.n_valid - (n0 + j * 32)));
                 continue;
             }
+            if (P.pack_g > 1 && P.swap) {      // dy on M (row = co), packed taps on N: column = (tap of the group, ci)
+                if (mrow >= P.m_valid) continue;
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const int col = j * 32 + q;
+                    const int tsel = tapi * P.pack_g + col / P.pack_cb, ci = col % P.pack_cb;
+                    if (tsel < P.ntaps_real && ci < P.CI) atomicAdd(P.dW + ((long long)P.taps[tsel].wk * P.CI + ci) * P.CO + mrow, v[q]);
+                }
+                continue;
+            }
             if (P.pack_g > 1) {
                 const int tsel = tapi * P.pack_g + r / P.pack_cb, ci = r % P.pack_cb;
                 if (tsel >= P.ntaps_real || ci >= P.CI) continue;
@@ -2003,6 +2013,10 @@ int tc_conv_wgrad(const dofb_conv_geom *g, const float *x, int x_ld, const float
     P.swap = (P.pack_g == 1 && g->ci < 128 && g->co >= 128) ? 1 : 0;
     P.m_valid = P.pack_g > 1 ? TC_BM : (P.swap ? g->co : g->ci);
     P.n_valid = P.swap ? g->ci : g->co;
+    // bf16, 33..64 input and 65..128 output channels (conv2): dy on the M side (co rows) and FOUR taps of x on the N side (4 x 64 columns):
+    // an M=128 tcgen05.mma costs the same at N = 256 as at N = 128, so this form needs half the MMA instructions of "2 taps on M, co on N"
+    const bool npack = bf && g_swap && !head_mode && g->ci > 32 && g->ci <= 64 && g->co > 64 && g->co <= 128 && g->kh * g->kw >= 4;
+    if (npack) { P.pack_cb = 64; P.pack_g = 4; P.swap = 1; P.m_valid = g->co; P.n_valid = 256; }
     P.parity = g->stride == 2; P.x_ld = x_ld;
     P.ntaps_real = g->kh * g->kw;
     P.ntaps = (P.ntaps_real + P.pack_g - 1) / P.pack_g;
