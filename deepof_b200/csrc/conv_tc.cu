@@ -1846,7 +1846,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
                 if (P.conv1) {
                     // tf32: region j = filter row 2*tapi + (j>>1), floats [(j&1)*32, +32) of its 8-pixel chunk;
                     // bf16: region j = filter row 2*tapi + j, all 64 elements of the chunk
-                    const int kh = min(2 * tapi + (BF ? j : (j >> 1)), P.c1_kh - 1);   // (an odd kh count re-loads the last row; masked later)
+                    // (swap form, bf16: FOUR filter rows on the N side -> region j = filter row 4*tapi + j)
+                    const int kh = min((P.swap ? 4 : 2) * tapi + (BF ? j : (j >> 1)), P.c1_kh - 1);   // (rows past the filter re-load the last one; masked later)
                     const TapInfo tr = P.taps[kh];
                     if (CG2) tma2_load_5d(sx + j * REGION, &map_x, lbar, BF ? 0 : (j & 1) * 32, ix0, tr.py, iy0 + tr.oy, in0);
                     else tma_load_5d(sx + j * REGION, &map_x, &full_bar[s], BF ? 0 : (j & 1) * 32, ix0, tr.py, iy0 + tr.oy, in0);
@@ -1906,6 +1907,16 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(j * 32), v);
             if (phantom) continue;
+            if (P.conv1 && P.swap) {           // dy on M (row = co), four filter rows on N: column = (row of the group, kw, ci)
+                if (mrow >= P.m_valid) continue;
+#pragma unroll
+                for (int q = 0; q < 32; ++q) {
+                    const int col = j * 32 + q;
+                    const int kh = 4 * tapi + (col >> 6), kw = (col & 63) >> 3, ci = col & 7;
+                    if (kh < P.c1_kh && kw < P.c1_kw && ci < P.CI) atomicAdd(P.dW + (((long long)kh * P.c1_kw + kw) * P.CI + ci) * P.CO + mrow, v[q]);
+                }
+                continue;
+            }
             if (P.conv1) {
                 const int kh = 2 * tapi + (r >> 6), kw = (r & 63) >> 3, ci = r & 7;
                 if (kh >= P.c1_kh || kw >= P.c1_kw || ci >= P.CI) continue;
@@ -2252,10 +2263,14 @@ int tc_conv1_wgrad(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, 
     P.tiles_x = (g->ow + P.TW - 1) / P.TW;
     P.tiles_y = (g->oh + P.TH - 1) / P.TH;
     P.tiles_total = P.tiles_x * P.tiles_y * ((g->B + P.TN - 1) / P.TN);
-    const int bn = g->co > 128 ? 256 : (g->co > 64 ? 128 : (g->co > 32 ? 64 : 32));
+    int bn = g->co > 128 ? 256 : (g->co > 64 ? 128 : (g->co > 32 ? 64 : 32));
     P.ntaps = (g->kh + 1) / 2;                 // work items along the filter rows: pairs of rows
     P.n_mblk = 1;
     P.n_nblk = (g->co + bn - 1) / bn;
+    if (bf && g_swap && g->co <= 128) {        // dy on M (co rows), four filter rows on N (4 x 64 columns): half the MMA instructions
+        P.swap = 1; P.m_valid = g->co; P.n_valid = 256; bn = 256;
+        P.ntaps = (g->kh + 3) / 4; P.n_nblk = 1;
+    }
     const int items = P.ntaps * P.n_nblk;
     // split-K so that items x splits fills (but never exceeds) ONE wave of one CTA per SM: rounding up to "two waves" used to leave a
     // third, nearly empty wave behind two full ones (measured: 1 wave 1.29 ms, 2 waves 1.33 ms, the old rounding 1.63 ms for the conv class)
