@@ -1563,7 +1563,8 @@ static int run_gather(const GatherSpec &G, const TcParams &Pin, cudaStream_t st)
         return 0;
     }
     int bn = n_rows > 128 ? 256 : (n_rows > 64 ? 128 : (n_rows > 32 ? 64 : 32));
-    while (bn > 64 && (long long)tiles * ((n_rows + bn - 1) / bn) < num_sms()) bn >>= 1;   // small maps: more, narrower tiles
+    // (No narrowing of the tiles on small maps: an M=128 tcgen05.mma costs the same ~128 cycles at N = 64 as at N = 256, so "more, narrower
+    // tiles" only multiplied the instruction count -- conv6_2 ran 576 MMAs per tile in two waves of 64-column tiles, exactly its measured 74 us.)
     // 256-column tiles with enough M tiles to fill the GPU with pairs: CTA pairs (each CTA stages half of the weight tile)
     const bool pairs = g_cta_pairs && bn == 256 && (long long)((tiles + 1) / 2) * ((n_rows + 255) / 256) >= num_sms() / 2;
     {
