@@ -21,7 +21,7 @@ TOL = 3e-3
 
 
 def rel(a, b):
-    a, b = a.detach().double(), b.detach().double()
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
 
 
