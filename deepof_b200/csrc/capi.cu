@@ -21,9 +21,7 @@ void invalidate_weight_cache();
 void enable_weight_cache(int on);
 void enable_cta_pairs(int on);
 void enable_halo(int on);
-void enable_mph(int on);
-void enable_swap(int on);
-void enable_c1(int on);
+void enable_npack(int on);
 int pack_weights_batch(const dofb_pack_job *jobs, int n_jobs, int bf16, cudaStream_t st);
 int tc_conv1_fwd(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *w, const float *bias,
                  float *y, int y_ld, int act, cudaStream_t st, void *y16 = nullptr, const void *x16 = nullptr);
@@ -128,9 +126,7 @@ extern "C" void dofb_invalidate_weight_cache(void) { invalidate_weight_cache(); 
 extern "C" void dofb_enable_weight_cache(int on) { enable_weight_cache(on); }
 extern "C" void dofb_enable_cta_pairs(int on) { enable_cta_pairs(on); }
 extern "C" void dofb_enable_halo_tiles(int on) { enable_halo(on); }
-extern "C" void dofb_enable_multiphase_halo(int on) { enable_mph(on); }
-extern "C" void dofb_enable_swapped_narrow(int on) { enable_swap(on); }
-extern "C" void dofb_enable_conv1_halo(int on) { enable_c1(on); }
+extern "C" void dofb_enable_wgrad_npack(int on) { enable_npack(on); }
 extern "C" int dofb_pack_weights_batch(const dofb_pack_job *jobs, int n_jobs, int bf16, void *stream) {
     return pack_weights_batch(jobs, n_jobs, bf16, as_stream(stream));
 }

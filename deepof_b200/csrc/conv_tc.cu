@@ -684,398 +684,6 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------------
-// Swapped-operand gather-GEMM for NARROW outputs (<= 128 output channels).
-//
-// Measured on B200 (round 2): a tcgen05.mma with M = 128 costs ~125 cycles whatever its N -- the layers with N = 32 / 64 / 128 output
-// columns ran at 12 / 25 / 50 % of the tensor peak no matter how little data they moved (the multi-phase halo kernel below cut the
-// L2->SM traffic of upconv1 3.7x and gained 8 %).  The instruction count is what matters, so these layers put the OUTPUT CHANNELS on M
-// and 256 PIXELS on N:   D^T[channel, pixel] = W[channel, K] . X[pixel, K]^T
-//   A operand = the weight k-block (<= 128 rows, zero-filled by TMA beyond the layer's channels), B operand = TWO pixel tiles (2 x 128
-//   rows x 128 B, the same TMA boxes as before, contiguous in the stage) -> one M=128 x N=256 instruction per 256 pixels and k-step
-//   instead of two (or, at N = 32, instead of two that fill an eighth of the array).
-// The accumulator is transposed -- TMEM lane = output channel, column = pixel -- which is exactly what NHWC wants: a warp holds 32
-// consecutive channels of one pixel per register, so the epilogue stores straight from registers (64 / 128 contiguous bytes per
-// instruction), no shared-memory transpose.  Same persistent pipeline, phases, parity gathers and padding-by-OOB-fill as
-// tc_gather_gemm_kernel; warps 0-3 drain the first pixel tile of the pair, warps 4-7 the second.
-// ------------------------------------------------------------------------------------------------
-template <int STAGES, bool BF>
-__global__ void __launch_bounds__(TCG_THREADS, 1)
-tc_swap_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ TcParams P) {
-    constexpr int KELEMS = BF ? 64 : 32;
-    constexpr int W_BYTES = 128 * 128;                      // weight k-block: 128 channel rows
-    constexpr int STAGE_BYTES = 2 * TC_A_BYTES + W_BYTES;   // 48 KB
-    constexpr int ACC_COLS = 256, TMEM_COLS = 512;
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
-    uint64_t *empty_bar = full_bar + STAGES;
-    uint64_t *acc_full = empty_bar + STAGES;
-    uint64_t *acc_empty = acc_full + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_units = (P.m_tiles + 1) / 2;
-    const int total = m_units * P.n_tiles;
-    if (threadIdx.x == 0) {
-        for (int s2 = 0; s2 < STAGES; ++s2) { mbar_init(&full_bar[s2], 1); mbar_init(&empty_bar[s2], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], TCG_EPI_WARPS); }
-        fence_barrier_init();
-    }
-    if (warp == TCG_EPI_WARPS && lane == 0) { prefetch_tmap(&map_a); prefetch_tmap(&map_b); }
-    if (warp == TCG_EPI_WARPS + 1) tmem_alloc(tmem_slot, TMEM_COLS);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == TCG_EPI_WARPS) {
-        if (lane == 0) {
-            int it = 0;
-            for (int t = blockIdx.x; t < total; t += gridDim.x) {
-                const int nt = t / m_units, u = t % m_units;
-                const TileView V0 = tile_view(P, 2 * u), V1 = tile_view(P, 2 * u + 1);
-                const int kiters = V0.ntaps * P.ncb;
-                int tp = V0.tap0, cb = 0;
-                for (int si = 0; si < kiters; ++si, ++it) {
-                    const int s2 = it % STAGES;
-                    mbar_wait(&empty_bar[s2], ((it / STAGES) & 1) ^ 1);
-                    mbar_expect_tx(&full_bar[s2], STAGE_BYTES);
-                    const TapInfo ti = P.taps[tp];
-                    uint8_t *sa = smem + s2 * STAGE_BYTES;
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const TileView &V = j ? V1 : V0;
-                        const int mt = V.mt;
-                        const int tx = mt % V.tiles_x, ty = (mt / V.tiles_x) % V.tiles_y, tn = mt / (V.tiles_x * V.tiles_y);
-                        const int ix0 = tx * P.TW, iy0 = ty * P.TH, in0 = tn * P.TN;
-                        if (P.parity)
-                            tma_load_5d(sa + j * TC_A_BYTES, &map_a, &full_bar[s2], ti.px * P.a_ld + P.a_coff + cb * KELEMS, ix0 + ti.ox, ti.py, iy0 + ti.oy, in0);
-                        else
-                            tma_load_4d(sa + j * TC_A_BYTES, &map_a, &full_bar[s2], P.a_coff + cb * KELEMS, ix0 + ti.ox, iy0 + ti.oy, in0);
-                    }
-                    tma_load_2d(sa + 2 * TC_A_BYTES, &map_b, &full_bar[s2], ti.wk + cb * KELEMS, nt * 128);
-                    if (++cb == P.ncb) { cb = 0; ++tp; }
-                }
-            }
-        }
-    } else if (warp == TCG_EPI_WARPS + 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = BF ? make_idesc_bf16(TC_BM, 256) : make_idesc_tf32(TC_BM, 256);
-            int it = 0, lt = 0;
-            for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
-                const int acc = lt & 1;
-                mbar_wait(&acc_empty[acc], ((lt >> 1) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
-                const int kiters = tile_view(P, 2 * (t % m_units)).ntaps * P.ncb;
-                for (int si = 0; si < kiters; ++si, ++it) {
-                    const int s2 = it % STAGES;
-                    mbar_wait(&full_bar[s2], (it / STAGES) & 1);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + s2 * STAGE_BYTES);
-                    const uint64_t dw = make_desc_k128(sa + 2 * TC_A_BYTES), dx = make_desc_k128(sa);       // A = weights, B = 256 pixel rows
-#pragma unroll
-                    for (int kk = 0; kk < TC_BK / 8; ++kk) umma<BF>(d_tmem, dw + (uint64_t)(kk * 2), dx + (uint64_t)(kk * 2), idesc, (si | kk) != 0);
-                    umma_commit(&empty_bar[s2]);
-                }
-                umma_commit(&acc_full[acc]);
-            }
-        }
-    } else {
-        // ===== epilogue: lane = output channel, register index = pixel; warps 0-3 own pixel tile 0 of the pair, warps 4-7 tile 1 =====
-        const int quad = warp & 3, half = warp >> 2;
-        const bool has32 = P.out != nullptr, has16 = P.out16 != nullptr, accum = P.accumulate != 0, elu = P.act == DOFB_ACT_ELU;
-        const int tw_sh = 31 - __clz(P.TW), th_sh = 31 - __clz(P.TH);        // TW, TH are powers of two (choose_tile)
-        int lt = 0;
-        for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
-            const int nt = t / m_units, u = t % m_units;
-            const TileView V = tile_view(P, 2 * u + half);
-            const int mt = V.mt;
-            const int tx = mt % V.tiles_x, ty = (mt / V.tiles_x) % V.tiles_y, tn = mt / (V.tiles_x * V.tiles_y);
-            const int ch = nt * 128 + quad * 32 + lane;
-            const bool ch_ok = ch < P.n_valid;
-            const float bias = (P.bias != nullptr && ch_ok) ? __ldg(P.bias + ch) : 0.f;
-            const int acc = lt & 1;
-            mbar_wait(&acc_full[acc], (lt >> 1) & 1);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c32 = 0; c32 < 4; ++c32) {
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * ACC_COLS + half * 128 + c32 * 32), v);
-                if (nt * 128 + quad * 32 >= P.n_valid) continue;            // (warp-uniform: this warp's 32 channels are all padding)
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int r = c32 * 32 + i;                             // row of the pixel tile (warp-uniform)
-                    const int ix = tx * P.TW + (r & (P.TW - 1)), iy = ty * P.TH + ((r >> tw_sh) & (P.TH - 1)), nn = tn * P.TN + (r >> (tw_sh + th_sh));
-                    if (ix >= V.cnt_x || iy >= V.cnt_y || nn >= P.B) continue;
-                    const long long off = (((long long)nn * P.rh + V.y0 + iy * P.rstep) * P.rw + V.x0 + ix * P.rstep) * P.out_ld + ch;
-                    float o = v[i] + bias;
-                    if (elu) o = o > 0.f ? o : __expf(o) - 1.f;
-                    if (ch_ok) {
-                        if (accum) o += P.out[off];
-                        if (has32) P.out[off] = o;
-                        if (has16) P.out16[off] = __float2bfloat16_rn(o);
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[acc]);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == TCG_EPI_WARPS + 1) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Multi-phase halo gather-GEMM: stride-2 transposed gathers with narrow N (transposed-conv forwards 4x4/2 to 32 / 64 channels, input
-// gradients of 5x5/2 and 3x3/2 convs to <= 128 channels).
-//
-// All stride^2 = 4 output phases of a transposed gather read the SAME 3 x 3 neighbourhood of the (small) source map -- every tap offset is
-// in {-1, 0, +1} -- yet the per-tap kernel above fetches a 16 KB A box per (phase, tap, channel block): 16 (4x4) or 25 (5x5) boxes per
-// channel block and 128 source pixels, which pins these layers to the chip-wide L2->SM limit at 15-35 % of the tensor peak.
-// Here a work unit is one SOURCE tile (8 x 16 pixels): per channel block ONE halo box (18 rows x 16 columns, 36 KB) lands in shared memory
-// and serves every tap of every phase (the MMA descriptor starts (oy+1)*16 + (ox+1) rows into the box, group stride 2048 B); the four
-// phases accumulate in four TMEM accumulators of BN columns (x 2: the epilogue of unit i overlaps the MMAs of unit i+1).  Weight k-blocks
-// stream through their own ring in chunks of <= 4 taps.  A crosses the L2->SM path once per channel block instead of 16-25 times.
-// Roles as above: warps 0-7 epilogue, warp 8 TMA producer, warp 9 TMEM allocator + MMA issuer.
-// ------------------------------------------------------------------------------------------------
-constexpr int MPH_A_SLOTS = 2, MPH_B_SLOTS = 4, MPH_MAX_CHUNKS = 16;
-struct MphParams {
-    float *out; __nv_bfloat16 *out16; int out_ld;
-    const float *bias;
-    int n_valid, rh, rw, B;
-    int tiles_x, tiles_y, m_tiles, n_tiles;
-    int a_coff, ncb, act, accumulate;
-    int nphase, nchunks;
-    struct Ph { int y0, x0, cnt_y, cnt_x; } ph[4];
-    struct Ck { short phase, tap0, ntaps, first; } ck[MPH_MAX_CHUNKS];
-    TapInfo taps[TC_MAX_TAPS];
-};
-
-// C1 = true: the FIRST-LAYER form (conv1 7x7/2 on the zero-bordered 8-channel input, bf16): one "phase", taps = filter rows whose K chunk
-// is 8 pixels x 8 channels; the halo box is {64 elements, 8 ox, 2 row parities, 19 row pairs} of the rank-5 overlapping-row map (38 KB
-// instead of 7 x 16 KB per tile), tap kh starts ((oy_k - oy_min) * 2 + parity_k) * 8 rows into it (same 2048-byte group stride), and
-// the 7 weight k-blocks (56 KB) are loaded ONCE per CTA and stay in shared memory.
-template <int BN, bool BF, bool C1 = false>
-__global__ void __launch_bounds__(TCG_THREADS, 1)
-tc_mph_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ MphParams P) {
-    constexpr int KELEMS = BF ? 64 : 32;
-    constexpr int B_BYTES = BN * 128;                       // one tap's weight k-block
-    constexpr int HA_BYTES = C1 ? 19 * 2 * 8 * 128 : TC_HALO_ROWS * 16 * 128;       // 38 KB / 36 KB halo box
-    constexpr int BS_BYTES = C1 ? 8 * B_BYTES : 4 * B_BYTES;                       // B slot: up to 4 taps (C1: all <= 8 filter rows, resident)
-    constexpr int A_SLOTS = C1 ? 3 : MPH_A_SLOTS, B_SLOTS = C1 ? 1 : MPH_B_SLOTS;
-    constexpr int ACC_COLS = (C1 ? 1 : 4) * BN, TMEM_COLS = 2 * ACC_COLS;
-    static_assert(TMEM_COLS <= 512 && TMEM_COLS >= 32 && BN >= 32, "phase accumulators, double buffered");
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t *smem_b = smem + A_SLOTS * HA_BYTES;
-    float *stage_f = reinterpret_cast<float *>(smem_b + B_SLOTS * BS_BYTES);
-    uint64_t *a_full = reinterpret_cast<uint64_t *>(stage_f + TCG_EPI_WARPS * 32 * 16);
-    uint64_t *a_empty = a_full + A_SLOTS;
-    uint64_t *b_full = a_empty + A_SLOTS;
-    uint64_t *b_empty = b_full + B_SLOTS;
-    uint64_t *acc_full = b_empty + B_SLOTS;
-    uint64_t *acc_empty = acc_full + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int total = P.m_tiles * P.n_tiles;
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < A_SLOTS; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < B_SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], TCG_EPI_WARPS); }
-        fence_barrier_init();
-    }
-    if (warp == TCG_EPI_WARPS && lane == 0) { prefetch_tmap(&map_a); prefetch_tmap(&map_b); }
-    if (warp == TCG_EPI_WARPS + 1) tmem_alloc(tmem_slot, TMEM_COLS);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == TCG_EPI_WARPS) {
-        if (lane == 0) {
-            int ita = 0, itb = 0;
-            if (C1) {                                      // the whole filter: once per CTA (n_tiles == 1)
-                const int ntp = P.ck[0].ntaps;
-                mbar_expect_tx(&b_full[0], ntp * B_BYTES);
-                for (int tp = 0; tp < ntp; ++tp) tma_load_2d(smem_b + tp * B_BYTES, &map_b, &b_full[0], P.taps[tp].wk, 0);
-            }
-            for (int t = blockIdx.x; t < total; t += gridDim.x) {
-                const int nt = t / P.m_tiles, mt = t % P.m_tiles;
-                const int tx = mt % P.tiles_x, ty = (mt / P.tiles_x) % P.tiles_y, tn = mt / (P.tiles_x * P.tiles_y);
-                const int ix0 = tx * 8, iy0 = ty * 16, n0 = nt * BN;
-                for (int cb = 0; cb < P.ncb; ++cb, ++ita) {
-                    const int sa = ita % A_SLOTS;
-                    mbar_wait(&a_empty[sa], ((ita / A_SLOTS) & 1) ^ 1);
-                    mbar_expect_tx(&a_full[sa], HA_BYTES);
-                    if (C1) {
-                        tma_load_5d(smem + sa * HA_BYTES, &map_a, &a_full[sa], 0, ix0, 0, iy0 + P.a_coff, tn);    // (a_coff = smallest row-pair offset)
-                        continue;
-                    }
-                    tma_load_4d(smem + sa * HA_BYTES, &map_a, &a_full[sa], P.a_coff + cb * KELEMS, ix0 - 1, iy0 - 1, tn);
-                    for (int c = 0; c < P.nchunks; ++c, ++itb) {
-                        const int sb = itb % B_SLOTS;
-                        const int ntp = P.ck[c].ntaps;
-                        mbar_wait(&b_empty[sb], ((itb / B_SLOTS) & 1) ^ 1);
-                        mbar_expect_tx(&b_full[sb], ntp * B_BYTES);
-                        for (int tp = 0; tp < ntp; ++tp)
-                            tma_load_2d(smem_b + sb * BS_BYTES + tp * B_BYTES, &map_b, &b_full[sb], P.taps[P.ck[c].tap0 + tp].wk + cb * KELEMS, n0);
-                    }
-                }
-            }
-        }
-    } else if (warp == TCG_EPI_WARPS + 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = BF ? make_idesc_bf16(TC_BM, BN) : make_idesc_tf32(TC_BM, BN);
-            int ita = 0, itb = 0, lt = 0;
-            if (C1) { mbar_wait(&b_full[0], 0); tc_fence_after(); }
-            for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
-                const int acc = lt & 1;
-                mbar_wait(&acc_empty[acc], ((lt >> 1) & 1) ^ 1);
-                tc_fence_after();
-                for (int cb = 0; cb < P.ncb; ++cb, ++ita) {
-                    const int sa = ita % A_SLOTS;
-                    mbar_wait(&a_full[sa], (ita / A_SLOTS) & 1);
-                    tc_fence_after();
-                    const uint32_t abuf = smem_u32(smem + sa * HA_BYTES);
-                    if (C1) {
-                        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
-                        for (int tp = 0; tp < P.ck[0].ntaps; ++tp) {
-                            const TapInfo ti = P.taps[tp];
-                            const uint64_t da = make_desc_k128_halo(abuf, ((ti.oy - P.a_coff) * 2 + ti.py) * 8);
-                            const uint64_t db = make_desc_k128(smem_u32(smem_b + tp * B_BYTES));
-#pragma unroll
-                            for (int kk = 0; kk < TC_BK / 8; ++kk) umma<BF>(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (tp | kk) != 0);
-                        }
-                        umma_commit(&a_empty[sa]);
-                        continue;
-                    }
-                    for (int c = 0; c < P.nchunks; ++c, ++itb) {
-                        const int sb = itb % B_SLOTS;
-                        mbar_wait(&b_full[sb], (itb / B_SLOTS) & 1);
-                        tc_fence_after();
-                        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS + P.ck[c].phase * BN);
-                        const uint32_t bbuf = smem_u32(smem_b + sb * BS_BYTES);
-                        for (int tp = 0; tp < P.ck[c].ntaps; ++tp) {
-                            const TapInfo ti = P.taps[P.ck[c].tap0 + tp];
-                            const uint64_t da = make_desc_k128_halo(abuf, (ti.oy + 1) * 16 + (ti.ox + 1));
-                            const uint64_t db = make_desc_k128(bbuf + tp * B_BYTES);
-                            const bool first = cb == 0 && P.ck[c].first && tp == 0;
-#pragma unroll
-                            for (int kk = 0; kk < TC_BK / 8; ++kk) umma<BF>(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, !(first && kk == 0));
-                        }
-                        umma_commit(&b_empty[sb]);
-                    }
-                    umma_commit(&a_empty[sa]);
-                }
-                umma_commit(&acc_full[acc]);
-            }
-        }
-    } else {
-        // ===== epilogue: per phase the same TMEM -> shared-memory transpose -> bias / ELU / accumulate -> NHWC stores as the kernel above =====
-        constexpr int NSUB = BN / 16;
-        const int quad = warp & 3, half = warp >> 2;
-        const int r = quad * 32 + lane;
-        float4 *stg = reinterpret_cast<float4 *>(stage_f) + warp * (32 * 4);
-        const int q = lane & 3, rsub = lane >> 2;
-        const bool has32 = P.out != nullptr, has16 = P.out16 != nullptr, accum = P.accumulate != 0, elu = P.act == DOFB_ACT_ELU;
-        const bool out_al = ((reinterpret_cast<uintptr_t>(P.out) & 15) == 0) && (P.out_ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.out16) & 7) == 0);
-        int lt = 0;
-        for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
-            const int nt = t / P.m_tiles, mt = t % P.m_tiles;
-            const int tx = mt % P.tiles_x, ty = (mt / P.tiles_x) % P.tiles_y, tn = mt / (P.tiles_x * P.tiles_y);
-            const int ix = tx * 8 + (r & 7), iy = ty * 16 + (r >> 3);
-            const int n0 = nt * BN;
-            const int acc = lt & 1;
-            mbar_wait(&acc_full[acc], (lt >> 1) & 1);
-            tc_fence_after();
-            const bool colfull = n0 + BN <= P.n_valid;
-#pragma unroll 1
-            for (int ph = 0; ph < P.nphase; ++ph) {
-                const bool row_ok = ix < P.ph[ph].cnt_x && iy < P.ph[ph].cnt_y;
-                const int rs = C1 ? 1 : 2;
-                const long long my_off = row_ok ? (((long long)tn * P.rh + P.ph[ph].y0 + iy * rs) * P.rw + P.ph[ph].x0 + ix * rs) * P.out_ld : -1;
-                const bool fast = __all_sync(0xffffffffu, row_ok) && out_al && (colfull || (P.n_valid & 3) == 0);
-                long long offs[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) offs[i] = __shfl_sync(0xffffffffu, my_off, i * 8 + rsub);
-#pragma unroll 1
-                for (int j = half; j < NSUB; j += 2) {
-                    float v[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * ACC_COLS + ph * BN + j * 16), v);
-                    const int cbase = n0 + j * 16;
-                    if (cbase >= P.n_valid) continue;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c)
-                        stg[lane * 4 + (c ^ ((lane >> 1) & 3))] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-                    __syncwarp();
-                    const int col = cbase + q * 4;
-                    const bool vec = out_al && (colfull || col + 3 < P.n_valid);
-                    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (P.bias != nullptr && col < P.n_valid) {
-                        bv.x = __ldg(P.bias + col);
-                        if (col + 1 < P.n_valid) bv.y = __ldg(P.bias + col + 1);
-                        if (col + 2 < P.n_valid) bv.z = __ldg(P.bias + col + 2);
-                        if (col + 3 < P.n_valid) bv.w = __ldg(P.bias + col + 3);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int rr = i * 8 + rsub;
-                        const long long off = offs[i];
-                        float4 o = stg[rr * 4 + (q ^ ((rr >> 1) & 3))];
-                        if ((!fast && off < 0) || col >= P.n_valid) continue;
-                        o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-                        if (elu) {
-                            o.x = o.x > 0.f ? o.x : __expf(o.x) - 1.f; o.y = o.y > 0.f ? o.y : __expf(o.y) - 1.f;
-                            o.z = o.z > 0.f ? o.z : __expf(o.z) - 1.f; o.w = o.w > 0.f ? o.w : __expf(o.w) - 1.f;
-                        }
-                        if (vec) {
-                            if (accum) {
-                                const float4 old = *reinterpret_cast<const float4 *>(P.out + off + col);
-                                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                            }
-                            if (has32) *reinterpret_cast<float4 *>(P.out + off + col) = o;
-                            if (has16) {
-                                __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
-                                uint2 pk;
-                                pk.x = *reinterpret_cast<uint32_t *>(&lo);
-                                pk.y = *reinterpret_cast<uint32_t *>(&hi);
-                                *reinterpret_cast<uint2 *>(P.out16 + off + col) = pk;
-                            }
-                        } else {
-                            const float ov[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                if (col + e < P.n_valid) {
-                                    const float val = accum ? P.out[off + col + e] + ov[e] : ov[e];
-                                    if (has32) P.out[off + col + e] = val;
-                                    if (has16) P.out16[off + col + e] = __float2bfloat16_rn(val);
-                                }
-                        }
-                    }
-                    __syncwarp();
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[acc]);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == TCG_EPI_WARPS + 1) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // weight re-packing: canonical TF layout [tap][ci][co] -> K-major [N][taps*Cpad]
 //   fwd  (contract over ci): Wp[co][tap*Cpad + ci] = W[tap][ci][co]
 //   bwd  (contract over co): Wp[ci][tap*Cpad + co] = W[tap][ci][co]
@@ -1226,12 +834,8 @@ static unsigned long long g_weight_epoch = 1;      // bumped by dofb_invalidate_
 static bool g_cache_enabled = false;               // off: every call re-packs (always correct); on: caller promises to invalidate
 static bool g_halo = false;                        // halo-tile reuse of A across filter taps (dofb_enable_halo_tiles)
 void enable_halo(int on) { g_halo = on != 0; }
-static bool g_swap = true;                         // swapped-operand kernel for <= 128 output channels (dofb_enable_swapped_narrow)
-void enable_swap(int on) { g_swap = on != 0; }
-static bool g_c1 = true;                           // conv1: row-halo tiles + resident filter (tc_mph_kernel<.., C1>)
-void enable_c1(int on) { g_c1 = on != 0; }
-static bool g_mph = false;                         // multi-phase halo kernel for narrow stride-2 transposed gathers (dofb_enable_multiphase_halo)
-void enable_mph(int on) { g_mph = on != 0; }
+static bool g_npack = true;                        // wgrad: dy on M and four taps / filter rows on N for the narrow first layers (dofb_enable_wgrad_npack)
+void enable_npack(int on) { g_npack = on != 0; }
 static bool g_cta_pairs = false;                   // cta_group::2 tiles for the 256-column layers (dofb_enable_cta_pairs)
 void enable_cta_pairs(int on) { g_cta_pairs = on != 0; }
 
@@ -1407,66 +1011,6 @@ static int run_gather(const GatherSpec &G, const TcParams &Pin, cudaStream_t st)
     DOFB_CHECK_ARG(G.out != nullptr || (G.out16 != nullptr && !G.accumulate), "tc conv: a bf16-only output needs the bf16 buffer and cannot accumulate");
     P.bias = G.bias; P.n_valid = G.n_valid; P.rh = G.rh; P.rw = G.rw;
     P.act = G.act; P.accumulate = G.accumulate; P.B = G.B;
-    // ---- multi-phase halo kernel: 4 phases of a stride-2 transposed gather, every tap offset in {-1,0,1}, at most 128 output columns ----
-    if (g_mph && P.nphase == 4 && !P.parity && P.rstep == 2 && n_rows <= 128 && true) {
-        bool ok = true;
-        int mcy = 0, mcx = 0, ncy = 1 << 30, ncx = 1 << 30;
-        for (int q = 0; q < 4; ++q) {
-            mcy = P.ph[q].cnt_y > mcy ? P.ph[q].cnt_y : mcy; mcx = P.ph[q].cnt_x > mcx ? P.ph[q].cnt_x : mcx;
-            ncy = P.ph[q].cnt_y < ncy ? P.ph[q].cnt_y : ncy; ncx = P.ph[q].cnt_x < ncx ? P.ph[q].cnt_x : ncx;
-            for (int t = P.ph[q].tap0; t < P.ph[q].tap0 + P.ph[q].ntaps; ++t)
-                if (P.taps[t].oy < -1 || P.taps[t].oy > 1 || P.taps[t].ox < -1 || P.taps[t].ox > 1) ok = false;
-        }
-        if (ncy < 8 || ncx < 8) ok = false;                 // tiny maps: the generic path wastes less
-        MphParams M;
-        memset(&M, 0, sizeof(M));
-        int nck = 0;
-        for (int q = 0; q < 4 && ok; ++q)
-            for (int t0 = 0; t0 < P.ph[q].ntaps; t0 += 4) {
-                if (nck >= MPH_MAX_CHUNKS) { ok = false; break; }
-                M.ck[nck].phase = (short)q; M.ck[nck].tap0 = (short)(P.ph[q].tap0 + t0);
-                M.ck[nck].ntaps = (short)(P.ph[q].ntaps - t0 < 4 ? P.ph[q].ntaps - t0 : 4); M.ck[nck].first = (short)(t0 == 0);
-                ++nck;
-            }
-        if (ok) {
-            const int bn = n_rows <= 32 ? 32 : 64;
-            M.out = G.out; M.out16 = G.accumulate ? nullptr : reinterpret_cast<__nv_bfloat16 *>(G.out16); M.out_ld = G.out_ld; M.bias = G.bias;
-            M.n_valid = G.n_valid; M.rh = G.rh; M.rw = G.rw; M.B = G.B;
-            M.tiles_x = (mcx + 7) / 8; M.tiles_y = (mcy + 15) / 16; M.m_tiles = M.tiles_x * M.tiles_y * G.B; M.n_tiles = (n_rows + bn - 1) / bn;
-            M.a_coff = G.a_coff; M.ncb = cpad / kel; M.act = G.act; M.accumulate = G.accumulate; M.nphase = 4; M.nchunks = nck;
-            for (int q = 0; q < 4; ++q) { M.ph[q].y0 = P.ph[q].y0; M.ph[q].x0 = P.ph[q].x0; M.ph[q].cnt_y = P.ph[q].cnt_y; M.ph[q].cnt_x = P.ph[q].cnt_x; }
-            for (int t = 0; t < taps_listed; ++t) M.taps[t] = P.taps[t];
-            DOFB_CHECK_ARG(G.out != nullptr || (G.out16 != nullptr && !G.accumulate), "tc conv: a bf16-only output needs the bf16 buffer and cannot accumulate");
-            const CUtensorMapDataType dtm = bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-            CUtensorMap ma, mb;
-            const uint64_t dims[4] = {(uint64_t)cpad, (uint64_t)G.aw, (uint64_t)G.ah, (uint64_t)G.B};
-            const uint64_t str[3] = {(uint64_t)G.a_ld * esz, (uint64_t)G.aw * G.a_ld * esz, (uint64_t)G.ah * G.aw * G.a_ld * esz};
-            const uint32_t box[4] = {(uint32_t)kel, 16u, (uint32_t)TC_HALO_ROWS, 1u};
-            if (make_map(&ma, abase, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, dtm)) return 1;
-            const uint64_t bdims[2] = {(uint64_t)taps_all * cpad, (uint64_t)n_rows};
-            const uint64_t bstr[1] = {(uint64_t)taps_all * cpad * esz};
-            const uint32_t bbox[2] = {(uint32_t)kel, (uint32_t)bn};
-            if (make_map(&mb, wp, 2, bdims, bstr, bbox, CU_TENSOR_MAP_SWIZZLE_128B, dtm)) return 1;
-            const long long total = (long long)M.m_tiles * M.n_tiles;
-            const int grid = (int)(total < num_sms() ? total : num_sms());
-#define DOFB_MPH_LAUNCH(BNv, BFv)                                                                                                         \
-    {                                                                                                                                    \
-        constexpr int smem_mph = MPH_A_SLOTS * TC_HALO_ROWS * 16 * 128 + MPH_B_SLOTS * 4 * BNv * 128 + TCG_EPI_WARPS * 32 * 16 * 4 + 1024 + 256; \
-        static_assert(smem_mph <= 227 * 1024, "shared-memory budget");                                                                  \
-        static bool cfgd = false;                                                                                                        \
-        if (!cfgd) {                                                                                                                     \
-            DOFB_CUDA_OK(cudaFuncSetAttribute(tc_mph_kernel<BNv, BFv>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_mph));          \
-            cfgd = true;                                                                                                                 \
-        }                                                                                                                                \
-        tc_mph_kernel<BNv, BFv><<<grid, TCG_THREADS, smem_mph, st>>>(ma, mb, M);                                                        \
-    }
-            if (bf) { if (bn == 32) DOFB_MPH_LAUNCH(32, true) else DOFB_MPH_LAUNCH(64, true) }
-            else { if (bn == 32) DOFB_MPH_LAUNCH(32, false) else DOFB_MPH_LAUNCH(64, false) }
-#undef DOFB_MPH_LAUNCH
-            DOFB_LAUNCH_OK();
-            return 0;
-        }
-    }
     // ---- halo tiles: unit-stride gather, every phase at least 16 x 8 pixels, <= 4 taps per phase spanning <= 2 rows / 8 columns ----
     const int n_rows_out = G.contract_ci ? G.w_co : G.w_ci;
     bool halo = g_halo && !P.parity && n_rows_out <= 128;
@@ -1539,32 +1083,9 @@ static int run_gather(const GatherSpec &G, const TcParams &Pin, cudaStream_t st)
         const uint32_t box[5] = {(uint32_t)kel, (uint32_t)P.TW, 1, (uint32_t)P.TH, (uint32_t)P.TN};
         if (make_map(&ma, abase, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, dt)) return 1;
     }
-    // ---- narrow outputs (<= 128 channels): channels on M, 256 pixels on N (tc_swap_gemm_kernel) ----
-    if (g_swap && !halo && n_rows <= 128) {
-        const uint64_t dims[2] = {(uint64_t)taps_all * cpad, (uint64_t)n_rows};
-        const uint64_t str[1] = {(uint64_t)taps_all * cpad * esz};
-        const uint32_t box[2] = {(uint32_t)kel, 128u};
-        if (make_map(&mb, wp, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, dt)) return 1;
-        P.m_tiles = tiles; P.n_tiles = 1;
-        constexpr int SW_STAGES = 4;
-        constexpr int smem_sw = SW_STAGES * (2 * TC_A_BYTES + 128 * 128) + 1024 + 256;
-        static_assert(smem_sw <= 227 * 1024, "shared-memory budget");
-        static bool cfgd = false;
-        if (!cfgd) {
-            DOFB_CUDA_OK(cudaFuncSetAttribute(tc_swap_gemm_kernel<SW_STAGES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sw));
-            DOFB_CUDA_OK(cudaFuncSetAttribute(tc_swap_gemm_kernel<SW_STAGES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sw));
-            cfgd = true;
-        }
-        const int units = (tiles + 1) / 2;
-        const int grid = units < num_sms() ? units : num_sms();
-        if (bf) tc_swap_gemm_kernel<SW_STAGES, true><<<grid, TCG_THREADS, smem_sw, st>>>(ma, mb, P);
-        else tc_swap_gemm_kernel<SW_STAGES, false><<<grid, TCG_THREADS, smem_sw, st>>>(ma, mb, P);
-        DOFB_LAUNCH_OK();
-        return 0;
-    }
     int bn = n_rows > 128 ? 256 : (n_rows > 64 ? 128 : (n_rows > 32 ? 64 : 32));
-    // (No narrowing of the tiles on small maps: an M=128 tcgen05.mma costs the same ~128 cycles at N = 64 as at N = 256, so "more, narrower
-    // tiles" only multiplied the instruction count -- conv6_2 ran 576 MMAs per tile in two waves of 64-column tiles, exactly its measured 74 us.)
+    // (No narrowing of the tiles on small maps: measured, an M=128 tcgen05.mma costs ~125 cycles at N = 32 .. 64 and 128 at N = 256, so "more,
+    // narrower tiles" only multiplied the instruction count -- conv6_2 ran 576 MMAs per tile in two waves of 64-column tiles = its measured 74 us.)
     // 256-column tiles with enough M tiles to fill the GPU with pairs: CTA pairs (each CTA stages half of the weight tile)
     const bool pairs = g_cta_pairs && bn == 256 && (long long)((tiles + 1) / 2) * ((n_rows + 255) / 256) >= num_sms() / 2;
     {
@@ -2027,7 +1548,7 @@ int tc_conv_wgrad(const dofb_conv_geom *g, const float *x, int x_ld, const float
     P.n_valid = P.swap ? g->ci : g->co;
     // bf16, 33..64 input and 65..128 output channels (conv2): dy on the M side (co rows) and FOUR taps of x on the N side (4 x 64 columns):
     // an M=128 tcgen05.mma costs the same at N = 256 as at N = 128, so this form needs half the MMA instructions of "2 taps on M, co on N"
-    const bool npack = bf && g_swap && !head_mode && g->ci > 32 && g->ci <= 64 && g->co > 64 && g->co <= 128 && g->kh * g->kw >= 4;
+    const bool npack = bf && g_npack && !head_mode && g->ci > 32 && g->ci <= 64 && g->co > 64 && g->co <= 128 && g->kh * g->kw >= 4;
     if (npack) { P.pack_cb = 64; P.pack_g = 4; P.swap = 1; P.m_valid = g->co; P.n_valid = 256; }
     P.parity = g->stride == 2; P.x_ld = x_ld;
     P.ntaps_real = g->kh * g->kw;
@@ -2185,41 +1706,6 @@ int tc_conv1_fwd(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, in
     const uint64_t str[1] = {(uint64_t)g->kh * 64 * (bf ? 2 : 4)};
     const uint32_t box[2] = {bf ? 64u : 32u, (uint32_t)bn};
     if (make_map(&mb, wp, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32)) return 1;
-    // ---- bf16, 64 output channels, maps of at least 16 x 8: row-halo tiles with the whole filter resident in shared memory (tc_mph_kernel<.., C1>) ----
-    if (g_c1 && bf && g->co > 32 && g->co <= 64 && g->oh >= 16 && g->ow >= 8 && g->kh <= 8) {
-        int omin = 1 << 20, omax = -(1 << 20);
-        for (int kh = 0; kh < g->kh; ++kh) { omin = P.taps[kh].oy < omin ? P.taps[kh].oy : omin; omax = P.taps[kh].oy > omax ? P.taps[kh].oy : omax; }
-        if (omax - omin <= 3) {
-            MphParams M;
-            memset(&M, 0, sizeof(M));
-            M.out = y; M.out16 = reinterpret_cast<__nv_bfloat16 *>(y16); M.out_ld = y_ld; M.bias = bias;
-            M.n_valid = g->co; M.rh = g->oh; M.rw = g->ow; M.B = g->B;
-            M.tiles_x = (g->ow + 7) / 8; M.tiles_y = (g->oh + 15) / 16; M.m_tiles = M.tiles_x * M.tiles_y * g->B; M.n_tiles = 1;
-            M.a_coff = omin; M.ncb = 1; M.act = act; M.accumulate = 0; M.nphase = 1; M.nchunks = 1;
-            M.ph[0].y0 = 0; M.ph[0].x0 = 0; M.ph[0].cnt_y = g->oh; M.ph[0].cnt_x = g->ow;
-            M.ck[0].phase = 0; M.ck[0].tap0 = 0; M.ck[0].ntaps = (short)g->kh; M.ck[0].first = 1;
-            for (int kh = 0; kh < g->kh; ++kh) M.taps[kh] = P.taps[kh];
-            const int rowoff_c = xp_x0 - g->pad_l;
-            const uint64_t rowb = (uint64_t)xp_w * 8 * 2;
-            const uint64_t adims[5] = {64, (uint64_t)g->ow, 2, (uint64_t)xp_h / 2, (uint64_t)g->B};
-            const uint64_t astr[4] = {16 * 2, rowb, 2 * rowb, (uint64_t)xp_h * rowb};
-            const uint32_t abox[5] = {64u, 8u, 2u, 19u, 1u};
-            CUtensorMap mah;
-            if (make_map(&mah, static_cast<const uint8_t *>(x16) + (size_t)rowoff_c * 8 * 2, 5, adims, astr, abox, CU_TENSOR_MAP_SWIZZLE_128B,
-                         CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)) return 1;
-            constexpr int smem_c1 = 3 * 19 * 2 * 8 * 128 + 8 * 64 * 128 + TCG_EPI_WARPS * 32 * 16 * 4 + 1024 + 256;
-            static_assert(smem_c1 <= 227 * 1024, "shared-memory budget");
-            static bool cfgd = false;
-            if (!cfgd) {
-                DOFB_CUDA_OK(cudaFuncSetAttribute(tc_mph_kernel<64, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_c1));
-                cfgd = true;
-            }
-            const int grid = M.m_tiles < num_sms() ? M.m_tiles : num_sms();
-            tc_mph_kernel<64, true, true><<<grid, TCG_THREADS, smem_c1, st>>>(mah, mb, M);
-            DOFB_LAUNCH_OK();
-            return 0;
-        }
-    }
     const int n_tiles = (g->co + bn - 1) / bn;
     if (bf) {
         switch (bn) {
@@ -2268,7 +1754,7 @@ int tc_conv1_wgrad(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, 
     P.ntaps = (g->kh + 1) / 2;                 // work items along the filter rows: pairs of rows
     P.n_mblk = 1;
     P.n_nblk = (g->co + bn - 1) / bn;
-    if (bf && g_swap && g->co <= 128) {        // dy on M (co rows), four filter rows on N (4 x 64 columns): half the MMA instructions
+    if (bf && g_npack && g->co <= 128) {       // dy on M (co rows), four filter rows on N (4 x 64 columns): half the MMA instructions
         P.swap = 1; P.m_valid = g->co; P.n_valid = 256; bn = 256;
         P.ntaps = (g->kh + 3) / 4; P.n_nblk = 1;
     }

@@ -158,9 +158,7 @@ class FlowNetS:
         ops._lib.load().dofb_enable_cta_pairs(0 if os.environ.get("DOFB_CTA_PAIRS", "1") == "0" else 1)   # cta_group::2 tiles for the wide layers
         # halo-tile reuse of A across taps: correct (tests) but slower than the per-tap gather in its first form -> opt-in
         ops._lib.load().dofb_enable_halo_tiles(1 if os.environ.get("DOFB_HALO", "0") == "1" else 0)
-        ops._lib.load().dofb_enable_multiphase_halo(1 if os.environ.get("DOFB_MPH", "0") == "1" else 0)
-        ops._lib.load().dofb_enable_swapped_narrow(0 if os.environ.get("DOFB_SWAP", "1") == "0" else 1)
-        ops._lib.load().dofb_enable_conv1_halo(0 if os.environ.get("DOFB_C1", "1") == "0" else 1)
+        ops._lib.load().dofb_enable_wgrad_npack(0 if os.environ.get("DOFB_NPACK", "1") == "0" else 1)
         self.profile = None            # list of (tag, start_event, end_event) when per-launch timing is on
         if seed is not None:
             self.init_params(seed)

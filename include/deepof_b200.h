@@ -183,16 +183,10 @@ void dofb_enable_cta_pairs(int on);
 /* Unit-stride gathers on maps of at least 16 x 8 pixels (<= 128 output columns): stage ONE halo box of the input per tile and channel block
  * and let every filter tap read its shifted rows out of it, instead of one TMA box per tap.  Process-wide switch. */
 void dofb_enable_halo_tiles(int on);
-/* Stride-2 transposed gathers (conv2d_transpose forwards, input gradients of stride-2 convs) with at most 128 output channels: one halo box of
- * the source map per channel block serves every tap of all four output phases (tc_mph_kernel).  Off by default (measured: these layers are
- * bound by the MMA instruction count, not by operand traffic -- see dofb_enable_swapped_narrow); process-wide switch. */
-void dofb_enable_multiphase_halo(int on);
-/* Gathers with at most 128 output channels: output channels on the MMA's M side, 256 pixels on N (one tcgen05.mma per 256 pixels and k-step:
- * tc_swap_gemm_kernel).  On by default; process-wide switch; identical results up to fp32 summation order. */
-void dofb_enable_swapped_narrow(int on);
-/* dofb_conv1_fwd_bf16 with 33..64 output channels: row-halo tiles (one 38 KB box instead of 7 x 16 KB per tile) and the whole filter resident
- * in shared memory.  On by default; process-wide switch. */
-void dofb_enable_conv1_halo(int on);
+/* Weight gradients of the narrow first layers in bf16 (conv1: 7x7x6->64; conv2-shaped: 33..64 -> 65..128 channels): dy on the MMA's M side and
+ * FOUR filter rows / taps of x on the N side (256 columns), so that every tcgen05.mma is a full 128 x 256 instruction (measured: an M=128 MMA
+ * costs the same at N = 64 as at N = 256).  On by default; process-wide switch; same result up to fp32 summation order. */
+void dofb_enable_wgrad_npack(int on);
 /* ---- BF16 tensor-core math (tcgen05 kind::f16, bf16 operands, fp32 accumulate + fp32 epilogue) ----
  * Activations keep their fp32 NHWC buffers; every producer additionally writes a bf16 "shadow" with the same pitch in elements
  * (a multiple of 64), and the tensor-core consumers read the shadows: half the bytes per K element and twice the MMA rate of the

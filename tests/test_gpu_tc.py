@@ -564,65 +564,6 @@ def test_halo_tiles_match_per_tap_gather(which, case, mth):
     assert rel(outs[1], outs[0]) < 1e-5
 
 
-MPH_CASES = [
-    # which, B, ih, iw, ci, co, k   (geometry of the stride-2 conv whose input gradient / transpose this is)
-    ("deconv", 2, 48, 64, 32, 194, 4),        # upconv1-like: transposed conv 194 -> 32
-    ("deconv", 1, 48, 64, 64, 386, 4),        # upconv2-like
-    ("deconv", 1, 44, 56, 128, 130, 4),       # two 64-column tiles, ragged source map 22 x 28
-    ("dgrad", 2, 48, 64, 64, 128, 5),         # conv2-like input gradient (phases of 9/6/6/4 taps)
-    ("dgrad", 1, 40, 48, 128, 256, 5),        # conv3_1-like
-    ("dgrad", 2, 34, 46, 96, 160, 3),         # 3x3/2, odd map
-]
-
-
-@pytest.mark.parametrize("case", MPH_CASES)
-@pytest.mark.parametrize("mth", [1, 2])
-@pytest.mark.parametrize("accumulate", [False, True])
-def test_multiphase_halo_kernel_matches_per_tap_gather(case, mth, accumulate):
-    """tc_mph_kernel (one halo box of the source map serves all taps of all four stride phases) against the per-tap gather kernel and the
-    CPU oracle: transposed-conv forward with bias + ELU, and accumulating / overwriting input gradients."""
-    from deepof_b200 import ops, _lib
-    from oracle import tf_ops
-    which, B, ih, iw, ci, co, k = case
-    if which == "deconv" and accumulate:
-        pytest.skip("a transposed-conv forward never accumulates")
-    lib = _lib.load()
-    g = torch.Generator().manual_seed(len(which) + sum(case[1:]))
-    geom = ops.conv_geom(B, ih, iw, ci, co, k, 2)
-    P = 64 if mth == 2 else 32
-    ld_s, ld_l = (co + P - 1) // P * P, (ci + P - 1) // P * P
-    small = _buf(B, geom.oh, geom.ow, ld_s, co, g)                     # the gathered (source) map
-    if mth == 2:
-        small = small.to(torch.bfloat16).float()
-    wt = (torch.randn(k, k, ci, co, generator=g) / math.sqrt(k * k * co)).cuda()
-    bias = (torch.randn(ci, generator=g) * 0.1).cuda() if which == "deconv" else None
-    act = ops.ACT_ELU if which == "deconv" else ops.ACT_NONE
-    base = torch.randn(B, ih, iw, ld_l, generator=g).cuda()
-    outs = []
-    for on in (0, 1):
-        lib.dofb_enable_multiphase_halo(on)
-        y = base.clone()
-        y16 = torch.zeros(B, ih, iw, ld_l, dtype=torch.bfloat16, device="cuda") if mth == 2 else None
-        ops.conv_dgrad(geom, ops.Slab(small, 0, co, small.to(torch.bfloat16) if mth == 2 else None), wt, bias, ops.Slab(y, 0, ci, y16), act, accumulate, mth)
-        torch.cuda.synchronize()
-        outs.append((y, y16))
-    lib.dofb_enable_multiphase_halo(1)
-    assert rel(outs[1][0][..., :ci], outs[0][0][..., :ci]) < 2e-5
-    assert torch.equal(outs[1][0][..., ci:], base[..., ci:])           # pad channels untouched
-    if mth == 2 and not accumulate:
-        assert rel(outs[1][1][..., :ci].float(), outs[0][1][..., :ci].float()) < 2 ** -7
-    # oracle: the input gradient of the TF-SAME stride-2 conv (== conv2d_transpose for the 4x4 case)
-    xd = torch.zeros(B, ih, iw, ci, dtype=torch.float64, requires_grad=True)
-    wq = wt.cpu().to(torch.bfloat16).double() if mth == 2 else wt.cpu().double()
-    tf_ops.conv2d_same(xd, wq, None, 2).backward(small.cpu()[..., :co].double())
-    want = xd.grad
-    if which == "deconv":
-        want = tf_ops.elu(want + bias.cpu().double())
-    if accumulate:
-        want = want + base.cpu()[..., :ci].double()
-    assert rel(outs[1][0][..., :ci], want) < (2e-5 if mth == 2 else TOL)
-
-
 @pytest.mark.parametrize("B,h,w,md,s2", [(2, 12, 64, 20, 2), (1, 7, 40, 20, 2), (2, 6, 128, 20, 2), (1, 5, 64, 16, 4), (1, 48, 64, 20, 2), (3, 9, 70, 8, 1)])
 def test_bf16_correlation_backward_matches_oracle(B, h, w, md, s2):
     """tc_corr_bwd16_kernel (bf16 band-GEMMs, eight generator warps) against autograd of the CPU restatement of the cost volume."""
@@ -647,61 +588,28 @@ def test_bf16_correlation_backward_matches_oracle(B, h, w, md, s2):
     assert rel(d2, b.grad) < 2e-5
 
 
-SWAP_CASES = [
-    # kind, B, H, W, ci, co, k, s      (fwd: N = co; dgrad: N = ci of the conv)
-    ("fwd", 2, 24, 32, 64, 128, 5, 2),        # conv2-like: parity gather, N = 128
-    ("fwd", 3, 10, 14, 32, 32, 3, 1),         # ragged, odd tile count (phantom second tile)
-    ("fwd", 1, 48, 64, 98, 20, 1, 1),         # flow-head Z map: 20 columns
-    ("dgrad", 2, 48, 64, 64, 128, 5, 2),      # conv2 input gradient: 4 phases, N = 64
-    ("dgrad", 2, 48, 64, 32, 194, 4, 2),      # upconv1 forward form (N = 32)
-    ("dgrad", 1, 12, 16, 128, 256, 3, 1),     # unit stride, N = 128
-]
-
-
-@pytest.mark.parametrize("case", SWAP_CASES)
-@pytest.mark.parametrize("mth", [1, 2])
-def test_swapped_operand_kernel_matches_generic_and_oracle(case, mth):
-    """tc_swap_gemm_kernel (output channels on M, 256 pixels on N) against the generic tile kernel and the CPU oracle."""
+@pytest.mark.parametrize("case", [(2, 24, 32, 64, 128, 128, 5, 2), (1, 48, 64, 64, 64, 128, 3, 1), (2, 40, 56, 48, 64, 96, 5, 2)])
+def test_wgrad_tap_packing_on_n_matches_m_side_packing(case):
+    """conv2-shaped bf16 weight gradients: 'dy on M, four taps of x on N' (full 128 x 256 MMAs) against the default 'two taps on M' form
+    and the CPU oracle."""
     from deepof_b200 import ops, _lib
     from oracle import tf_ops
-    kind, B, H, W, ci, co, k, s = case
+    B, H, W, ci, x_ld, co, k, s = case
     lib = _lib.load()
-    g = torch.Generator().manual_seed(17 + sum(case[1:]))
+    g = torch.Generator().manual_seed(sum(case))
     geom = ops.conv_geom(B, H, W, ci, co, k, s)
-    P = 64 if mth == 2 else 32
-    wt = (torch.randn(k, k, ci, co, generator=g) / math.sqrt(k * k * (ci if kind == "fwd" else co))).cuda()
-    if kind == "fwd":
-        x = _buf(B, H, W, (ci + P - 1) // P * P, ci, g)
-        bias = (torch.randn(co, generator=g) * 0.1).cuda()
-        n, oshape = co, (B, geom.oh, geom.ow)
-    else:
-        x = _buf(B, geom.oh, geom.ow, (co + P - 1) // P * P, co, g)
-        bias, n, oshape = None, ci, (B, H, W)
-    if mth == 2:
-        x = x.to(torch.bfloat16).float()
-    ld_o = (n + 3) // 4 * 4 + 4
+    x = _buf(B, H, W, x_ld, ci, g).to(torch.bfloat16)
+    dy = _buf(B, geom.oh, geom.ow, (co + 63) // 64 * 64, co, g).to(torch.bfloat16)
+    dummy_x, dummy_dy = torch.zeros(x.shape, device="cuda"), torch.zeros(dy.shape, device="cuda")
     outs = []
     for on in (0, 1):
-        lib.dofb_enable_swapped_narrow(on)
-        for accumulate in ((False, True) if kind == "dgrad" else (False,)):
-            y = torch.full((*oshape, ld_o), 0.5, device="cuda")
-            xs = ops.Slab(x, 0, ci if kind == "fwd" else co, x.to(torch.bfloat16) if mth == 2 else None)
-            if kind == "fwd":
-                ops.conv_fwd(geom, xs, wt, bias, ops.Slab(y, 4, n), ops.ACT_ELU, mth)
-            else:
-                ops.conv_dgrad(geom, xs, wt, None, ops.Slab(y, 4, n), ops.ACT_NONE, accumulate, mth)
-            torch.cuda.synchronize()
-            outs.append(y)
-    lib.dofb_enable_swapped_narrow(1)
-    half = len(outs) // 2
-    for a, b in zip(outs[:half], outs[half:]):
-        assert rel(b[..., 4:4 + n], a[..., 4:4 + n]) < 2e-5
-        assert float((b[..., :4] - 0.5).abs().max()) == 0.0 and float((b[..., 4 + n:] - 0.5).abs().max()) == 0.0
-    wq = wt.cpu().to(torch.bfloat16).double() if mth == 2 else wt.cpu().double()
-    if kind == "fwd":
-        want = tf_ops.elu(tf_ops.conv2d_same(x.cpu()[..., :ci].double(), wq, bias.cpu().double(), s))
-    else:
-        xd = torch.zeros(B, H, W, ci, dtype=torch.float64, requires_grad=True)
-        tf_ops.conv2d_same(xd, wq, None, s).backward(x.cpu()[..., :co].double())
-        want = xd.grad
-    assert rel(outs[half][..., 4:4 + n], want) < (3e-5 if mth == 2 else TOL)
+        lib.dofb_enable_wgrad_npack(on)
+        dw = torch.zeros(k, k, ci, co, device="cuda")
+        ops.conv_wgrad(geom, ops.Slab(dummy_x, 0, ci, x), ops.Slab(dummy_dy, 0, co, dy), dw, None, ops.MATH_BF16)
+        torch.cuda.synchronize()
+        outs.append(dw)
+    lib.dofb_enable_wgrad_npack(1)
+    assert rel(outs[1], outs[0]) < 2e-5
+    wd = torch.zeros(k, k, ci, co, dtype=torch.float64, requires_grad=True)
+    tf_ops.conv2d_same(x.float().cpu()[..., :ci].double(), wd, None, s).backward(dy.float().cpu()[..., :co].double())
+    assert rel(outs[1], wd.grad) < 2e-5
