@@ -730,7 +730,8 @@ __global__ void __launch_bounds__(256) pack_weights_t_kernel(const float *__rest
 
 // Both orientations for MANY layers in one launch (the engine packs every layer once per optimiser step: ~80 tiny launches otherwise).
 // Block -> job by a scan of the job table; fwd-orientation jobs work in 32x32 transpose tiles, bwd-orientation jobs in 2048-element runs.
-struct PackJobDev { const float *w; void *wp; int taps, ci, co, cpad, contract_ci, blk0; };
+// wp2 != nullptr: the job ALSO writes the other (contract-co) orientation from the same tile, so the canonical weights are read once.
+struct PackJobDev { const float *w; void *wp; void *wp2; int taps, ci, co, cpad, cpad2, contract_ci, blk0; };
 constexpr int PACK_BATCH_MAX = 48;
 struct PackBatch { int n; PackJobDev j[PACK_BATCH_MAX]; };
 
@@ -743,7 +744,7 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const __grid_constant__
     const int local = blockIdx.x - J.blk0;
     T *Wp = reinterpret_cast<T *>(J.wp);
     if (J.contract_ci) {
-        const int tiles_n = (J.co + 31) / 32, tiles_c = J.cpad / 32;
+        const int tiles_n = J.wp2 ? J.cpad2 / 32 : (J.co + 31) / 32, tiles_c = J.cpad / 32;
         const int n0 = (local % tiles_n) * 32, c0 = ((local / tiles_n) % tiles_c) * 32, t = local / (tiles_n * tiles_c);
         const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;         // 32 x 8
 #pragma unroll
@@ -756,6 +757,14 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const __grid_constant__
         for (int r = ty; r < 32; r += 8) {
             const int n = n0 + r, c = c0 + tx;
             if (n < J.co && c < J.cpad) Wp[((long long)n * J.taps + t) * J.cpad + c] = cvt_out<T>(tile[tx][r]);
+        }
+        if (J.wp2 != nullptr) {             // contract-co orientation: the same tile, not transposed (rows = ci, K = co padded to cpad2)
+            T *Wq = reinterpret_cast<T *>(J.wp2);
+#pragma unroll
+            for (int r = ty; r < 32; r += 8) {
+                const int c = c0 + r, n = n0 + tx;
+                if (c < J.ci && n < J.cpad2) Wq[((long long)c * J.taps + t) * J.cpad2 + n] = cvt_out<T>(tile[r][tx]);
+            }
         }
     } else {
         // straight padded copy, 4 consecutive K elements per thread (co and cpad are multiples of 4 for every layer that gets here
@@ -779,7 +788,15 @@ __global__ void __launch_bounds__(256) pack_batch_kernel(const __grid_constant__
                 if (c + 2 < J.co) v.z = __ldg(src + 2);
                 if (c + 3 < J.co) v.w = __ldg(src + 3);
             }
-            Wp[i] = cvt_out<T>(v.x); Wp[i + 1] = cvt_out<T>(v.y); Wp[i + 2] = cvt_out<T>(v.z); Wp[i + 3] = cvt_out<T>(v.w);
+            if (sizeof(T) == 2) {           // (cpad and i are multiples of 4: one 8-byte store)
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<const uint32_t *>(&lo);
+                pk.y = *reinterpret_cast<const uint32_t *>(&hi);
+                *reinterpret_cast<uint2 *>(Wp + i) = pk;
+            } else {
+                *reinterpret_cast<float4 *>(Wp + i) = v;
+            }
         }
     }
 }
@@ -889,8 +906,20 @@ int pack_weights_batch(const dofb_pack_job *jobs, int n_jobs, int bf16, cudaStre
             if (get_pack_buffer(j.w, (j.contract_ci ? 1 : 0) + (bf16 ? 8 : 0), bf16 ? (welems + 1) / 2 : welems, &wp, &fresh)) return 1;
             if (fresh) continue;
             PackJobDev &d = Bt.j[Bt.n++];
-            d.w = j.w; d.wp = wp; d.taps = j.taps; d.ci = j.ci; d.co = j.co; d.cpad = cpad; d.contract_ci = j.contract_ci ? 1 : 0; d.blk0 = blocks;
-            blocks += j.contract_ci ? ((j.co + 31) / 32) * (cpad / 32) * j.taps : (int)((welems + 2047) / 2048);
+            d.w = j.w; d.wp = wp; d.wp2 = nullptr; d.cpad2 = 0;
+            d.taps = j.taps; d.ci = j.ci; d.co = j.co; d.cpad = cpad; d.contract_ci = j.contract_ci ? 1 : 0; d.blk0 = blocks;
+            // the other orientation of the same weights right behind it: one pass over the canonical tensor writes both copies
+            if (j.contract_ci && k + 1 < n_jobs && jobs[k + 1].w == j.w && !jobs[k + 1].contract_ci && jobs[k + 1].taps == j.taps &&
+                jobs[k + 1].ci == j.ci && jobs[k + 1].co == j.co) {
+                const int cpad2 = (j.co + kel - 1) / kel * kel;
+                const size_t w2 = (size_t)j.ci * j.taps * cpad2;
+                float *wq = nullptr;
+                bool fresh2 = false;
+                if (get_pack_buffer(j.w, (bf16 ? 8 : 0), bf16 ? (w2 + 1) / 2 : w2, &wq, &fresh2)) return 1;
+                d.wp2 = wq; d.cpad2 = cpad2;
+                ++k;
+            }
+            blocks += j.contract_ci ? (d.wp2 ? d.cpad2 / 32 : (j.co + 31) / 32) * (cpad / 32) * j.taps : (int)((welems + 2047) / 2048);
         }
         if (Bt.n == 0) continue;
         if (bf16) pack_batch_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(Bt);

@@ -361,8 +361,8 @@ class FlowNetS:
                     add(w, 0)
             for R in self.refine:
                 w = P[R["up"] + "/weights"]
+                add(w, 1)               # (contract-ci first: the batch kernel writes an adjacent (1, 0) pair in one pass over the weights)
                 add(w, 0)
-                add(w, 1)
             for s in range(1, self.N_SCALES + 1):
                 h, wd = self.hw[s]
                 if self.lean:
