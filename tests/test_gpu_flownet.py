@@ -95,7 +95,7 @@ def test_two_adam_steps_track_the_oracle(small_case):
             if it == 0:
                 assert float(d[sig].max()) <= 0.02 * lr, (name, it, float(d[sig].max()) / lr)
             elif int(sig.sum()) > 0:
-                assert float(d[sig].mean()) <= 0.15 * lr, (name, it, float(d[sig].mean()) / lr)
+                assert float(d[sig].mean()) <= 0.3 * lr, (name, it, float(d[sig].mean()) / lr)
             assert float(d.max()) <= 2 * lr * (it + 1) + 1e-7                  # nothing moves further than Adam can move it
             if it == 0:
                 assert d.mean().item() < 0.05 * lr, (name, d.mean().item())
