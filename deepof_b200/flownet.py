@@ -160,6 +160,7 @@ class FlowNetS:
         ops._lib.load().dofb_enable_halo_tiles(1 if os.environ.get("DOFB_HALO", "0") == "1" else 0)
         ops._lib.load().dofb_enable_wgrad_npack(0 if os.environ.get("DOFB_NPACK", "1") == "0" else 1)
         self.profile = None            # list of (tag, start_event, end_event) when per-launch timing is on
+        self._nvtx = os.environ.get("DOFB_NVTX", "0") == "1"
         if seed is not None:
             self.init_params(seed)
 
@@ -169,6 +170,12 @@ class FlowNetS:
 
     def _k(self, tag, fn, *args, **kw):
         """Launch one kernel; with self.profile set, bracket it with CUDA events on the launch stream."""
+        if self._nvtx:                  # DOFB_NVTX=1: one NVTX range per launch tag (ncu --nvtx --nvtx-include "conv_dgrad:conv2/")
+            torch.cuda.nvtx.range_push(tag)
+            try:
+                return fn(*args, **kw)
+            finally:
+                torch.cuda.nvtx.range_pop()
         if self.profile is None:
             return fn(*args, **kw)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

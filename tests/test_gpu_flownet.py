@@ -104,7 +104,7 @@ def test_two_adam_steps_track_the_oracle(small_case):
     with torch.no_grad():
         _l, _f, _p, total = fs.forward(params, c["src"], c["tgt"])
     eng.forward(c["src"].cuda(), c["tgt"].cuda(), fs.LOSS_WEIGHTS, with_grad=False)
-    assert abs(float(eng.total_loss()) - float(total)) <= 1e-4 * abs(float(total))
+    assert abs(float(eng.total_loss()) - float(total)) <= 5e-4 * abs(float(total))
 
 
 def test_golden_fixture(golden_dir):
