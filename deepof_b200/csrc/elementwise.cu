@@ -51,63 +51,90 @@ __device__ __forceinline__ void lrn3(const float x[3], float o[3]) {
     o[0] = x[0] / den; o[1] = x[1] / den; o[2] = x[2] / den;
 }
 
+// one pixel: inputs a (source), t (target) already scaled; writes the network input and the pyramid levels whose grid contains (x, y)
+__device__ __forceinline__ void preprocess_pixel(const PreParams &P, int b, int y, int x, const float a[3], const float t[3]) {
+    const long long xo = (((long long)b * P.x6_h + y + P.x6_y0) * P.x6_w + x + P.x6_x0) * P.x6_ld;
+    float *o = P.x6 + xo;
+    if (P.x6_16 != nullptr) {                   // bf16 network input, 8 channels = one 16-byte store per buffer
+        const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+        if (P.x6b_16 != nullptr) {
+            __nv_bfloat162 s0 = __floats2bfloat162_rn(a[0], a[1]), s1 = __floats2bfloat162_rn(a[2], 0.f);
+            __nv_bfloat162 t0 = __floats2bfloat162_rn(t[0], t[1]), t1 = __floats2bfloat162_rn(t[2], 0.f);
+            uint4 ps, pt;
+            ps.x = *reinterpret_cast<uint32_t *>(&s0); ps.y = *reinterpret_cast<uint32_t *>(&s1); ps.z = ps.w = *reinterpret_cast<const uint32_t *>(&z);
+            pt.x = *reinterpret_cast<uint32_t *>(&t0); pt.y = *reinterpret_cast<uint32_t *>(&t1); pt.z = pt.w = ps.z;
+            *reinterpret_cast<uint4 *>(P.x6_16 + xo) = ps;
+            *reinterpret_cast<uint4 *>(P.x6b_16 + xo) = pt;
+        } else {
+            __nv_bfloat162 v0 = __floats2bfloat162_rn(a[0], a[1]), v1 = __floats2bfloat162_rn(a[2], t[0]), v2 = __floats2bfloat162_rn(t[1], t[2]);
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t *>(&v0); pk.y = *reinterpret_cast<uint32_t *>(&v1); pk.z = *reinterpret_cast<uint32_t *>(&v2);
+            pk.w = *reinterpret_cast<const uint32_t *>(&z);
+            *reinterpret_cast<uint4 *>(P.x6_16 + xo) = pk;
+        }
+    } else if (P.x6 == nullptr) {
+        // pyramid-only call (models whose network input and loss images differ: VGG16 photo/geo pairs)
+    } else if (P.x6b != nullptr) {             // siamese: source and target in separate 3(+pad)-channel buffers
+        float *ob = P.x6b + xo;
+        o[0] = a[0]; o[1] = a[1]; o[2] = a[2];
+        ob[0] = t[0]; ob[1] = t[1]; ob[2] = t[2];
+        for (int c = 3; c < P.x6_ld; ++c) { o[c] = 0.f; ob[c] = 0.f; }
+    } else if (P.x6_ld == 8) {
+        reinterpret_cast<float4 *>(o)[0] = make_float4(a[0], a[1], a[2], t[0]);
+        reinterpret_cast<float4 *>(o)[1] = make_float4(t[1], t[2], 0.f, 0.f);
+    } else {
+        o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; o[3] = t[0]; o[4] = t[1]; o[5] = t[2];
+        for (int c = 6; c < P.x6_ld; ++c) o[c] = 0.f;
+    }
+    if (P.n_scales > 0 && ((x | y) & 1) == 0) {
+        float an[3], tn[3];
+        lrn3(a, an);
+        lrn3(t, tn);
+        for (int s = 0; s < P.n_scales; ++s) {
+            const int r = 2 << s;
+            if ((x & (r - 1)) | (y & (r - 1))) break;
+            const int hs = P.H >> (s + 1), ws = P.W >> (s + 1);
+            const long long q = (((long long)b * hs + (y >> (s + 1))) * ws + (x >> (s + 1))) * 3;
+            P.pyr_src[s][q] = an[0]; P.pyr_src[s][q + 1] = an[1]; P.pyr_src[s][q + 2] = an[2];
+            P.pyr_tgt[s][q] = tn[0]; P.pyr_tgt[s][q + 1] = tn[1]; P.pyr_tgt[s][q + 2] = tn[2];
+        }
+    }
+}
+
+// VEC4: a thread owns 4 consecutive pixels of a row (W % 4 == 0, 16-byte aligned images): 3 + 3 float4 loads instead of 24 scalar ones
+template <bool VEC4>
 __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__ PreParams P) {
     const long long npix = (long long)P.B * P.H * P.W;
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
+    const long long nitems = VEC4 ? npix / 4 : npix;
+    for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < nitems; it += (long long)gridDim.x * blockDim.x) {
+        const long long p = VEC4 ? it * 4 : it;
         const int x = (int)(p % P.W);
         const int y = (int)((p / P.W) % P.H);
         const int b = (int)(p / ((long long)P.W * P.H));
-        float a[3], t[3];
+        if (VEC4) {
+            float sv[12], tv[12];
+            const float4 *sp = reinterpret_cast<const float4 *>(P.src + p * 3), *tp = reinterpret_cast<const float4 *>(P.tgt + p * 3);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            a[c] = (__ldg(P.src + p * 3 + c) - P.mean[c]) / P.divisor;
-            t[c] = (__ldg(P.tgt + p * 3 + c) - P.mean[c]) / P.divisor;
-        }
-        const long long xo = (((long long)b * P.x6_h + y + P.x6_y0) * P.x6_w + x + P.x6_x0) * P.x6_ld;
-        float *o = P.x6 + xo;
-        if (P.x6_16 != nullptr) {                   // bf16 network input, 8 channels = one 16-byte store per buffer
-            const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
-            if (P.x6b_16 != nullptr) {
-                __nv_bfloat162 s0 = __floats2bfloat162_rn(a[0], a[1]), s1 = __floats2bfloat162_rn(a[2], 0.f);
-                __nv_bfloat162 t0 = __floats2bfloat162_rn(t[0], t[1]), t1 = __floats2bfloat162_rn(t[2], 0.f);
-                uint4 ps, pt;
-                ps.x = *reinterpret_cast<uint32_t *>(&s0); ps.y = *reinterpret_cast<uint32_t *>(&s1); ps.z = ps.w = *reinterpret_cast<const uint32_t *>(&z);
-                pt.x = *reinterpret_cast<uint32_t *>(&t0); pt.y = *reinterpret_cast<uint32_t *>(&t1); pt.z = pt.w = ps.z;
-                *reinterpret_cast<uint4 *>(P.x6_16 + xo) = ps;
-                *reinterpret_cast<uint4 *>(P.x6b_16 + xo) = pt;
-            } else {
-                __nv_bfloat162 v0 = __floats2bfloat162_rn(a[0], a[1]), v1 = __floats2bfloat162_rn(a[2], t[0]), v2 = __floats2bfloat162_rn(t[1], t[2]);
-                uint4 pk;
-                pk.x = *reinterpret_cast<uint32_t *>(&v0); pk.y = *reinterpret_cast<uint32_t *>(&v1); pk.z = *reinterpret_cast<uint32_t *>(&v2);
-                pk.w = *reinterpret_cast<const uint32_t *>(&z);
-                *reinterpret_cast<uint4 *>(P.x6_16 + xo) = pk;
+            for (int i = 0; i < 3; ++i) {
+                const float4 u = __ldg(sp + i), v = __ldg(tp + i);
+                sv[4 * i] = u.x; sv[4 * i + 1] = u.y; sv[4 * i + 2] = u.z; sv[4 * i + 3] = u.w;
+                tv[4 * i] = v.x; tv[4 * i + 1] = v.y; tv[4 * i + 2] = v.z; tv[4 * i + 3] = v.w;
             }
-        } else if (P.x6 == nullptr) {
-            // pyramid-only call (models whose network input and loss images differ: VGG16 photo/geo pairs)
-        } else if (P.x6b != nullptr) {             // siamese: source and target in separate 3(+pad)-channel buffers
-            float *ob = P.x6b + xo;
-            o[0] = a[0]; o[1] = a[1]; o[2] = a[2];
-            ob[0] = t[0]; ob[1] = t[1]; ob[2] = t[2];
-            for (int c = 3; c < P.x6_ld; ++c) { o[c] = 0.f; ob[c] = 0.f; }
-        } else if (P.x6_ld == 8) {
-            reinterpret_cast<float4 *>(o)[0] = make_float4(a[0], a[1], a[2], t[0]);
-            reinterpret_cast<float4 *>(o)[1] = make_float4(t[1], t[2], 0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float a[3], t[3];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { a[c] = (sv[3 * k + c] - P.mean[c]) / P.divisor; t[c] = (tv[3 * k + c] - P.mean[c]) / P.divisor; }
+                preprocess_pixel(P, b, y, x + k, a, t);
+            }
         } else {
-            o[0] = a[0]; o[1] = a[1]; o[2] = a[2]; o[3] = t[0]; o[4] = t[1]; o[5] = t[2];
-            for (int c = 6; c < P.x6_ld; ++c) o[c] = 0.f;
-        }
-        if (P.n_scales > 0 && ((x | y) & 1) == 0) {
-            float an[3], tn[3];
-            lrn3(a, an);
-            lrn3(t, tn);
-            for (int s = 0; s < P.n_scales; ++s) {
-                const int r = 2 << s;
-                if ((x & (r - 1)) | (y & (r - 1))) break;
-                const int hs = P.H >> (s + 1), ws = P.W >> (s + 1);
-                const long long q = (((long long)b * hs + (y >> (s + 1))) * ws + (x >> (s + 1))) * 3;
-                P.pyr_src[s][q] = an[0]; P.pyr_src[s][q + 1] = an[1]; P.pyr_src[s][q + 2] = an[2];
-                P.pyr_tgt[s][q] = tn[0]; P.pyr_tgt[s][q + 1] = tn[1]; P.pyr_tgt[s][q + 2] = tn[2];
+            float a[3], t[3];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                a[c] = (__ldg(P.src + p * 3 + c) - P.mean[c]) / P.divisor;
+                t[c] = (__ldg(P.tgt + p * 3 + c) - P.mean[c]) / P.divisor;
             }
+            preprocess_pixel(P, b, y, x, a, t);
         }
     }
 }
@@ -332,7 +359,10 @@ static int preprocess_launch(const float *src, const float *tgt, const float mea
         P.pyr_tgt[s] = s < n_scales ? pyr_tgt[s] : nullptr;
         DOFB_CHECK_ARG(s >= n_scales || (P.pyr_src[s] && P.pyr_tgt[s]), "dofb_preprocess: null pyramid level %d", s);
     }
-    preprocess_kernel<<<grid_for((long long)B * H * W, 256), 256, 0, as_stream(stream)>>>(P);
+    if (W % 4 == 0 && aligned16(src) && aligned16(tgt))
+        preprocess_kernel<true><<<grid_for((long long)B * H * W / 4, 256), 256, 0, as_stream(stream)>>>(P);
+    else
+        preprocess_kernel<false><<<grid_for((long long)B * H * W, 256), 256, 0, as_stream(stream)>>>(P);
     DOFB_LAUNCH_OK();
     return 0;
 }
