@@ -89,6 +89,8 @@ SIGNATURES = {
     "dofb_enable_weight_cache": (None, [_I]),
     "dofb_enable_cta_pairs": (None, [_I]),
     "dofb_enable_halo_tiles": (None, [_I]),
+    "dofb_enable_phase_in_n": (None, [_I]),
+    "dofb_enable_split_k": (None, [_I]),
     "dofb_enable_wgrad_npack": (None, [_I]),
     "dofb_pack_weights_batch": (_I, [_P, _I, _I, _P]),
     "dofb_head_fwd": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P, _P]),

@@ -21,6 +21,8 @@ void invalidate_weight_cache();
 void enable_weight_cache(int on);
 void enable_cta_pairs(int on);
 void enable_halo(int on);
+void enable_pin(int on);
+void enable_splitk(int on);
 void enable_npack(int on);
 int pack_weights_batch(const dofb_pack_job *jobs, int n_jobs, int bf16, cudaStream_t st);
 int tc_conv1_fwd(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, int xp_y0, int xp_x0, const float *w, const float *bias,
@@ -126,6 +128,8 @@ extern "C" void dofb_invalidate_weight_cache(void) { invalidate_weight_cache(); 
 extern "C" void dofb_enable_weight_cache(int on) { enable_weight_cache(on); }
 extern "C" void dofb_enable_cta_pairs(int on) { enable_cta_pairs(on); }
 extern "C" void dofb_enable_halo_tiles(int on) { enable_halo(on); }
+extern "C" void dofb_enable_phase_in_n(int on) { enable_pin(on); }
+extern "C" void dofb_enable_split_k(int on) { enable_splitk(on); }
 extern "C" void dofb_enable_wgrad_npack(int on) { enable_npack(on); }
 extern "C" int dofb_pack_weights_batch(const dofb_pack_job *jobs, int n_jobs, int bf16, void *stream) {
     return pack_weights_batch(jobs, n_jobs, bf16, as_stream(stream));

@@ -158,6 +158,8 @@ class FlowNetS:
         ops._lib.load().dofb_enable_cta_pairs(0 if os.environ.get("DOFB_CTA_PAIRS", "1") == "0" else 1)   # cta_group::2 tiles for the wide layers
         # halo-tile reuse of A across taps: correct (tests) but slower than the per-tap gather in its first form -> opt-in
         ops._lib.load().dofb_enable_halo_tiles(1 if os.environ.get("DOFB_HALO", "0") == "1" else 0)
+        ops._lib.load().dofb_enable_phase_in_n(0 if os.environ.get("DOFB_PIN", "1") == "0" else 1)      # phase-in-N stride-2 transposed gathers
+        ops._lib.load().dofb_enable_split_k(int(os.environ.get("DOFB_SPLITK", "1")))                    # split-K of the coarse layers
         ops._lib.load().dofb_enable_wgrad_npack(0 if os.environ.get("DOFB_NPACK", "1") == "0" else 1)
         self.profile = None            # list of (tag, start_event, end_event) when per-launch timing is on
         self._nvtx = os.environ.get("DOFB_NVTX", "0") == "1"

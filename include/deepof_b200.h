@@ -183,6 +183,16 @@ void dofb_enable_cta_pairs(int on);
 /* Unit-stride gathers on maps of at least 16 x 8 pixels (<= 128 output columns): stage ONE halo box of the input per tile and channel block
  * and let every filter tap read its shifted rows out of it, instead of one TMA box per tap.  Process-wide switch. */
 void dofb_enable_halo_tiles(int on);
+/* Stride-2 transposed gathers with 32 / 64 / 128 output channels (transposed-conv forward, strided-conv input gradient): put the four output
+ * phases side by side on the MMA's N dimension and walk the <= 9 distinct source offsets instead of the 16 / 25 filter taps (a phase without
+ * a tap at an offset multiplies zero weights).  on = 1 (default): maps large enough to fill the GPU; 2: always (tests); 0: never.  Process-wide
+ * switch; same result up to fp32 summation order. */
+void dofb_enable_phase_in_n(int on);
+/* Coarse maps (conv6_x, upconv5: fewer 128 x 256 tiles than SMs, K loops of 70-150 blocks): cut every tile's K loop into `ks` ranges, one
+ * work unit each; partial sums meet in the fp32 output (or an fp32 scratch map for a bf16-only output) through vector atomics and a finish
+ * pass applies bias / ELU / the bf16 rounding.  on = 1 (default): a cost model picks ks per layer; >= 2: that factor wherever legal (tests);
+ * 0: never.  Process-wide switch; same result up to fp32 summation order. */
+void dofb_enable_split_k(int on);
 /* Weight gradients of the narrow first layers in bf16 (conv1: 7x7x6->64; conv2-shaped: 33..64 -> 65..128 channels): dy on the MMA's M side and
  * FOUR filter rows / taps of x on the N side (256 columns), so that every tcgen05.mma is a full 128 x 256 instruction (measured: an M=128 MMA
  * costs the same at N = 64 as at N = 256).  On by default; process-wide switch; same result up to fp32 summation order. */

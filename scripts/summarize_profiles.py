@@ -90,3 +90,34 @@ def traffic_json():
 
 
 traffic_json()
+
+
+def layers_table(path=OUT / "prof_layers_raw.csv"):
+    """Per-layer table from the NVTX-filtered capture of scripts/profile_layers.sh (raw page exported on the GPU box)."""
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    ix = {h: i for i, h in enumerate(hdr)}
+    cols = [("gpu__time_duration.sum", "µs"), ("dram__bytes_read.sum", "DRAM rd MB"), ("dram__bytes_write.sum", "DRAM wr MB"),
+            ("l1tex__m_xbar2l1tex_read_bytes.sum", "L2→SM GB"), ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM %"),
+            ("launch__registers_per_thread", "regs"), ("launch__grid_size", "grid")]
+    cols = [(c, t) for c, t in cols if c in ix]
+    print("| NVTX range / kernel | " + " | ".join(t for _, t in cols) + " | DRAM TB/s | L2→SM TB/s |\n|---|" + "---:|" * (len(cols) + 2))
+    seen = set()
+    for r in rows[2:]:
+        name = re.sub(r"\(.*", "", r[ix["Kernel Name"]]).replace("void ", "").replace("dofb::", "")
+        name = re.sub(r"<.*", "", name)
+        if name in seen or "vectorized_elementwise" in name:
+            continue
+        seen.add(name)
+        us = float(r[ix["gpu__time_duration.sum"]])
+        rd, wr = float(r[ix["dram__bytes_read.sum"]]), float(r[ix["dram__bytes_write.sum"]])
+        xb = float(r[ix["l1tex__m_xbar2l1tex_read_bytes.sum"]])
+        vals = [r[ix[c]] for c, _ in cols]
+        vals = [f"{float(v):.1f}" if re.fullmatch(r"[0-9.]+", v) and "." in v else v for v in vals]
+        print(f"| `{name[:70]}` | " + " | ".join(vals) + f" | {(rd + wr) / us:.2f} | {xb * 1e3 / us:.2f} |")
+    print()
+
+
+if (OUT / "prof_layers_raw.csv").exists():
+    print("## Named layers of one bf16 step (B = 32, 384x512), `ncu --set full --nvtx-include <tag>/` (scripts/profile_layers.sh)\n")
+    layers_table()

@@ -163,6 +163,9 @@ def test_lean_engine_matches_classic_bf16_engine(model, monkeypatch):
     cls = FlowNetS if model == "flownets" else FlowNetC
     B, H, W = 2, 192, 256
     src, tgt, _ = make_pairs(B, H, W, seed=21)
+    # (split-K sums the coarse layers' K ranges through atomics in a run-dependent order; the Charbonnier gradient amplifies that fp32 noise
+    # -- bf16 vs fp32 gradients of this batch have cosines down to 0.6 -- so the schedule comparison runs both engines without it)
+    monkeypatch.setenv("DOFB_SPLITK", "0")
     monkeypatch.setenv("DOFB_LEAN", "0")
     e0 = cls(B, H, W, math_mode="bf16", seed=1, tc_wgrad=True)
     monkeypatch.setenv("DOFB_LEAN", "1")

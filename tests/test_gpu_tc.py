@@ -426,7 +426,10 @@ def test_tf32_engine_tracks_fp32_engine_and_oracle_epe():
     cos = torch.nn.functional.cosine_similarity(etf.grad.double(), e32.grad.double(), dim=0).item()
     worst = max(rel(etf.grads[n], e32.grads[n]) for n in e32.grads)
     print(f"tf32 vs fp32 gradient: cosine={cos:.6f} worst per-tensor max-norm deviation={worst:.3e}")
-    assert cos > 0.98
+    # (0.9866 with every K loop in one piece; at this tiny batch every layer is "coarse" and runs split-K, whose partial sums meet in a
+    # run-dependent order: measured 0.973 .. 0.982 -- scripts/splitk_check.py shows the forward flows moving by 2e-5 .. 1e-3 relative, the
+    # same order as TF32's own truncation, and the Charbonnier gradient amplifying it)
+    assert cos > 0.95
 
 # ---- CTA pairs (cta_group::2) vs single-CTA tiles: same K order per tile, so forward / input gradients must be bit-identical --------
 
@@ -455,14 +458,18 @@ def test_cta_pairs_fwd_and_dgrad_bit_identical(case, mth, cta_pairs):
     yl = (co + 63) // 64 * 64
     dy = _buf(B, geom.oh, geom.ow, yl, co, g)
     ys, ds = [], []
-    for pairs in (0, 1):
-        cta_pairs.dofb_enable_cta_pairs(pairs)
-        y = torch.zeros(B, geom.oh, geom.ow, yl, device="cuda")
-        ops.conv_fwd(geom, ops.Slab(x, 0, ci, _shadow(x)), w, b, ops.Slab(y, 0, co), ops.ACT_ELU, mth)
-        d = torch.full((B, H, W, x.shape[3]), 0.5, device="cuda")
-        ops.conv_dgrad(geom, ops.Slab(dy, 0, co, _shadow(dy)), w, None, ops.Slab(d, 0, ci), ops.ACT_NONE, True, mth)   # (strided: all phases, one launch)
-        torch.cuda.synchronize()
-        ys.append(y); ds.append(d)
+    cta_pairs.dofb_enable_split_k(0)          # (split-K partial sums meet through atomics in a run-dependent order: not bit-stable)
+    try:
+        for pairs in (0, 1):
+            cta_pairs.dofb_enable_cta_pairs(pairs)
+            y = torch.zeros(B, geom.oh, geom.ow, yl, device="cuda")
+            ops.conv_fwd(geom, ops.Slab(x, 0, ci, _shadow(x)), w, b, ops.Slab(y, 0, co), ops.ACT_ELU, mth)
+            d = torch.full((B, H, W, x.shape[3]), 0.5, device="cuda")
+            ops.conv_dgrad(geom, ops.Slab(dy, 0, co, _shadow(dy)), w, None, ops.Slab(d, 0, ci), ops.ACT_NONE, True, mth)   # (strided: all phases, one launch)
+            torch.cuda.synchronize()
+            ys.append(y); ds.append(d)
+    finally:
+        cta_pairs.dofb_enable_split_k(1)
     assert torch.equal(ys[0], ys[1])
     assert torch.equal(ds[0], ds[1])
     ref = torch.zeros_like(ys[0])
@@ -515,6 +522,7 @@ def test_pack_weights_batch_matches_lazy_packing():
             outs += [y, d]
         torch.cuda.synchronize()
         return outs
+    lib.dofb_enable_split_k(0)                # bit-for-bit comparison: no atomically summed K ranges
     for mth in (ops.MATH_TF32, ops.MATH_BF16):
         lib.dofb_enable_weight_cache(0)
         lazy = run_all(mth)
@@ -527,6 +535,7 @@ def test_pack_weights_batch_matches_lazy_packing():
         lib.dofb_enable_weight_cache(0)
         for a, b_ in zip(lazy, batched):
             assert torch.equal(a, b_)
+    lib.dofb_enable_split_k(1)
 
 
 @pytest.mark.parametrize("which,case", [("dgrad", (4, 96, 128, 32, 194, 4, 2)), ("dgrad", (2, 64, 96, 64, 386, 4, 2)), ("dgrad", (2, 48, 64, 128, 130, 4, 2)),
@@ -613,3 +622,109 @@ def test_wgrad_tap_packing_on_n_matches_m_side_packing(case):
     wd = torch.zeros(k, k, ci, co, dtype=torch.float64, requires_grad=True)
     tf_ops.conv2d_same(x.float().cpu()[..., :ci].double(), wd, None, s).backward(dy.float().cpu()[..., :co].double())
     assert rel(outs[1], wd.grad) < 2e-5
+
+
+@pytest.mark.parametrize("mth", ["tf32", "bf16"])
+@pytest.mark.parametrize("case", [
+    # (kind, B, h, w, c_contract, ld, c_out, k): deconv = 4x4/2 conv2d_transpose forward on an h x w map; dgrad = k x k / 2 conv input gradient
+    ("deconv", 2, 24, 32, 194, 256, 32, 4), ("deconv", 1, 48, 64, 386, 448, 64, 4), ("deconv", 2, 12, 16, 770, 832, 128, 4), ("deconv", 1, 9, 11, 100, 128, 64, 4),
+    ("dgrad", 2, 24, 32, 128, 128, 64, 5), ("dgrad", 1, 24, 32, 256, 256, 128, 5), ("dgrad", 2, 10, 12, 96, 128, 32, 3), ("dgrad", 1, 13, 9, 64, 64, 64, 7)])
+def test_phase_in_n_matches_per_phase_gather(case, mth):
+    """Stride-2 transposed gathers with 32 / 64 / 128 output channels: the four output phases side by side on N over the distinct source offsets
+    (dofb_enable_phase_in_n) against the per-phase / per-tap form -- same products, so equal up to fp32 summation order -- for
+    overwrite + bias + ELU + bf16 shadow (deconv forward) and for accumulation into an existing gradient (conv dgrad)."""
+    from deepof_b200 import ops, _lib
+    kind, B, h, w, cc, ld, cout, k = case
+    lib = _lib.load()
+    m = ops.MATH_BF16 if mth == "bf16" else ops.MATH_TF32
+    g = torch.Generator().manual_seed(sum(case[1:]) + 9)
+    x = _buf(B, h, w, ld, cc, g)
+    xs = _shadow(x) if mth == "bf16" else None
+    wt = (torch.randn(k, k, cout, cc, generator=g) / math.sqrt(k * k * cc / 4)).cuda()
+    b = (torch.randn(cout, generator=g) * 0.1).cuda()
+    geom = ops.conv_geom(B, 2 * h, 2 * w, cout, cc, k, 2)
+    assert (geom.oh, geom.ow) == (h, w)
+    ld_out = 128 + (cout + 63) // 64 * 64         # the slab sits between 64 foreign channels on either side
+    outs = []
+    try:
+        for on in (0, 2):
+            lib.dofb_enable_phase_in_n(on)
+            if kind == "deconv":
+                y = torch.zeros(B, 2 * h, 2 * w, ld_out, device="cuda")
+                ys = torch.zeros(y.shape, dtype=torch.bfloat16, device="cuda") if mth == "bf16" else None
+                ops.conv_dgrad(geom, ops.Slab(x, 0, cc, xs), wt, b, ops.Slab(y, 64, cout, ys), ops.ACT_ELU, False, m)
+                torch.cuda.synchronize()
+                if ys is not None:
+                    assert torch.equal(ys[..., 64:64 + cout], y[..., 64:64 + cout].to(torch.bfloat16))
+                    assert float(ys[..., :64].abs().max()) == 0.0 and float(ys[..., 64 + cout:].abs().max()) == 0.0
+                assert float(y[..., :64].abs().max()) == 0.0 and float(y[..., 64 + cout:].abs().max()) == 0.0
+            else:
+                y = torch.full((B, 2 * h, 2 * w, ld_out), 0.25, device="cuda")
+                ops.conv_dgrad(geom, ops.Slab(x, 0, cc, xs), wt, None, ops.Slab(y, 64, cout), ops.ACT_NONE, True, m)
+                torch.cuda.synchronize()
+                assert float((y[..., :64] - 0.25).abs().max()) == 0.0 and float((y[..., 64 + cout:] - 0.25).abs().max()) == 0.0
+                y = y - 0.25
+            outs.append(y[..., 64:64 + cout].clone())
+    finally:
+        lib.dofb_enable_phase_in_n(1)
+    assert rel(outs[1], outs[0]) < 1e-5
+    # and against the fp32 SIMT path (itself checked against the oracle elsewhere)
+    r = torch.zeros(B, 2 * h, 2 * w, ld_out, device="cuda")
+    ops.conv_dgrad(geom, ops.Slab(x, 0, cc), wt, b if kind == "deconv" else None, ops.Slab(r, 64, cout), ops.ACT_ELU if kind == "deconv" else ops.ACT_NONE, False, ops.MATH_FP32)
+    torch.cuda.synchronize()
+    assert rel(outs[1], r[..., 64:64 + cout]) < (BF_TOL if mth == "bf16" else TOL)
+
+
+@pytest.mark.parametrize("mth", ["tf32", "bf16"])
+@pytest.mark.parametrize("pairs", [0, 1])
+@pytest.mark.parametrize("case", [(4, 6, 8, 512, 512, 1024, 3, 2), (8, 3, 4, 1024, 1024, 1024, 3, 1), (2, 12, 16, 256, 320, 512, 3, 1), (3, 6, 8, 300, 320, 260, 3, 1)])
+@pytest.mark.parametrize("ks", [2, 3, 5])
+def test_split_k_matches_unsplit(case, ks, pairs, mth):
+    """Coarse 256-column layers: K loop cut into ks ranges with atomic partial sums + finish pass (dofb_enable_split_k) against the unsplit
+    launch, for forward (bias + ELU, fp32 and bf16-only outputs), input gradient overwriting and accumulating (all stride phases)."""
+    from deepof_b200 import ops, _lib
+    B, H, W, ci, x_ld, co, k, s = case
+    lib = _lib.load()
+    m = ops.MATH_BF16 if mth == "bf16" else ops.MATH_TF32
+    bf = mth == "bf16"
+    g = torch.Generator().manual_seed(sum(case) + 17)
+    x = _buf(B, H, W, x_ld, ci, g)
+    w = (torch.randn(k, k, ci, co, generator=g) / math.sqrt(k * k * ci)).cuda()
+    b = (torch.randn(co, generator=g) * 0.1).cuda()
+    geom = ops.conv_geom(B, H, W, ci, co, k, s)
+    y_ld = (co + 63) // 64 * 64 + 128
+    dy = _buf(B, geom.oh, geom.ow, (co + 63) // 64 * 64, co, g)
+    res = []
+    lib.dofb_enable_cta_pairs(pairs)
+    try:
+        for on in (0, ks):
+            lib.dofb_enable_split_k(on)
+            y = torch.zeros(B, geom.oh, geom.ow, y_ld, device="cuda")
+            ys = torch.zeros(y.shape, dtype=torch.bfloat16, device="cuda") if bf else None
+            ops.conv_fwd(geom, ops.Slab(x, 0, ci, _shadow(x) if bf else None), w, b, ops.Slab(y, 64, co, ys), ops.ACT_ELU, m)
+            out = [y[..., 64:64 + co].clone()]
+            torch.cuda.synchronize()
+            assert float(y[..., :64].abs().max()) == 0.0 and float(y[..., 64 + co:].abs().max()) == 0.0
+            if bf:
+                assert torch.equal(ys[..., 64:64 + co], y[..., 64:64 + co].to(torch.bfloat16))
+                y2s = torch.zeros(y.shape, dtype=torch.bfloat16, device="cuda")       # bf16-only output (lean schedule)
+                ops.conv_fwd(geom, ops.Slab(x, 0, ci, _shadow(x)), w, b, ops.Slab(None, 64, co, y2s), ops.ACT_ELU, m)
+                torch.cuda.synchronize()
+                if on == 0:
+                    assert torch.equal(y2s[..., 64:64 + co], ys[..., 64:64 + co])
+                else:           # atomically summed: the fp32 sums differ in the last bits, the bf16 roundings by at most one ulp
+                    assert rel(y2s[..., 64:64 + co].float(), ys[..., 64:64 + co].float()) < 8e-3
+                assert float(y2s[..., :64].abs().max()) == 0.0
+            for acc in (False, True):
+                d = torch.full((B, H, W, x_ld), 0.25, device="cuda")
+                ops.conv_dgrad(geom, ops.Slab(dy, 0, co, _shadow(dy) if bf else None), w, None, ops.Slab(d, 0, ci), ops.ACT_NONE, acc, m)
+                torch.cuda.synchronize()
+                if ci < x_ld:
+                    assert float((d[..., ci:] - 0.25).abs().max()) == 0.0
+                out.append(d[..., :ci] - (0.25 if acc else 0.0))
+            res.append(out)
+    finally:
+        lib.dofb_enable_split_k(1)
+        lib.dofb_enable_cta_pairs(1)
+    for a, r in zip(res[1], res[0]):
+        assert rel(a, r) < 5e-5           # same products, different fp32 summation order (K ranges meet through atomics)
