@@ -226,6 +226,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// ELU through one MUFU: ex2.approx.ftz (x * log2 e) - 1 (absolute error ~1e-7, irrelevant next to TF32 / BF16 operands).  __expf() compiles to the
+// non-ftz ex2 with a denormal-range fix-up (FSETP + two predicated FMULs per element): the epilogue of the K-poor layers is issue-bound
+// (ncu: conv1 forward, 28 instructions per output element), so those three instructions per element are worth removing.
+__device__ __forceinline__ float elu_fast(float x) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 1.4426950408889634f));
+    return x > 0.f ? x : e - 1.f;
+}
+
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
     uint32_t r[8];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -298,6 +307,7 @@ struct TcParams {
     int n_valid;                 // output channels
     int rh, rw;                  // output map
     int y0, x0, rstep;           // output pixel = (y0 + rstep*iy, x0 + rstep*ix)
+    int rstep_x;                 // != 0: column step differs from the row step (conv1 with four output pixels per row: x0 + 4*ix, y0 + iy)
     int B, cnt_y, cnt_x;         // row sub-grid
     int TW, TH, TN, tiles_x, tiles_y;
     int m_tiles, n_tiles;        // tiles along pixels / output channels (persistent scheduler)
@@ -572,6 +582,8 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         constexpr int NSUB = BN / 16;
         const int quad = warp & 3, half = warp >> 2;
         const int r = quad * 32 + lane;                     // row of the tile == TMEM lane
+        // (plain generic accesses: explicit st.shared / ld.shared asm here measured 0.5 % SLOWER per step -- the volatile asm pins the order of
+        // the accumulate path's global prefetches)
         float4 *stg = reinterpret_cast<float4 *>(stage_f) + warp * (32 * 4);
         const int q = lane & 3, rsub = lane >> 2;           // store phase: this lane's column quad and row within a group of 8
         // (P.out == nullptr: bf16-only output -- the lean bf16 engine keeps no fp32 copy of activations only tensor-core kernels read)
@@ -590,7 +602,7 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             const int n0 = nt * BN;
             const bool row_ok = ix < V.cnt_x && iy < V.cnt_y && nn < P.B;
             // element offset of this thread's output pixel (-1: no pixel); fetched by the storing lanes through shuffles
-            const long long my_off = row_ok ? (((long long)nn * P.rh + V.y0 + iy * P.rstep) * P.rw + V.x0 + ix * P.rstep) * P.out_ld : -1;
+            const long long my_off = row_ok ? (((long long)nn * P.rh + V.y0 + iy * P.rstep) * P.rw + V.x0 + ix * (PIN && P.rstep_x ? P.rstep_x : P.rstep)) * P.out_ld : -1;
             // fast path: every row a real pixel and the valid columns a whole number of 4-column quads (a partial last column block only
             // costs one predicate per store: the 20-column Z maps of the flow heads take this path)
             const bool colfull = PIN ? P.pin == P.n_valid : n0 + BN <= P.n_valid;
@@ -615,6 +627,8 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 #pragma unroll 1
             for (int j = half; j < NSUB; j += 2) {
                 float v[16];
+                // (measured: keeping the next sub-chunk's tcgen05.ld in flight while this one is processed is SLOWER -- 6.22 -> 6.34 ms per
+                // step, +20 registers -- the eight epilogue warps already overlap each other's TMEM latency)
                 tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * ACC_COLS + j * 16), v);
                 int cbase = n0 + j * 16;                    // first output channel of this sub-chunk
                 long long poff = 0;                         // (PIN) pixel offset of the phase this sub-chunk belongs to
@@ -648,8 +662,8 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                         if (!col_ok) continue;
                         o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
                         if (elu) {                          // fast ELU: exp via MUFU (absolute error ~1e-7, irrelevant next to TF32/BF16 operands)
-                            o.x = o.x > 0.f ? o.x : __expf(o.x) - 1.f; o.y = o.y > 0.f ? o.y : __expf(o.y) - 1.f;
-                            o.z = o.z > 0.f ? o.z : __expf(o.z) - 1.f; o.w = o.w > 0.f ? o.w : __expf(o.w) - 1.f;
+                            o.x = elu_fast(o.x); o.y = elu_fast(o.y);
+                            o.z = elu_fast(o.z); o.w = elu_fast(o.w);
                         }
                         if (SPLITK) { atomicAdd(reinterpret_cast<float4 *>(P.out + offs[i] + poff + col), o); continue; }
                         if (accum) { o.x += olds[i].x; o.y += olds[i].y; o.z += olds[i].z; o.w += olds[i].w; }
@@ -680,8 +694,8 @@ tc_gather_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                         float4 o = stg[rr * 4 + (q ^ ((rr >> 1) & 3))];
                         o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
                         if (elu) {
-                            o.x = o.x > 0.f ? o.x : __expf(o.x) - 1.f; o.y = o.y > 0.f ? o.y : __expf(o.y) - 1.f;
-                            o.z = o.z > 0.f ? o.z : __expf(o.z) - 1.f; o.w = o.w > 0.f ? o.w : __expf(o.w) - 1.f;
+                            o.x = elu_fast(o.x); o.y = elu_fast(o.y);
+                            o.z = elu_fast(o.z); o.w = elu_fast(o.w);
                         }
                         float *dst = P.out + off + col;
                         if (SPLITK) {
@@ -923,8 +937,8 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(float *__restrict__ 
             v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
         }
         if (act == DOFB_ACT_ELU) {
-            v.x = v.x > 0.f ? v.x : __expf(v.x) - 1.f; v.y = v.y > 0.f ? v.y : __expf(v.y) - 1.f;
-            v.z = v.z > 0.f ? v.z : __expf(v.z) - 1.f; v.w = v.w > 0.f ? v.w : __expf(v.w) - 1.f;
+            v.x = elu_fast(v.x); v.y = elu_fast(v.y);
+            v.z = elu_fast(v.z); v.w = elu_fast(v.w);
         }
         if (write32) *reinterpret_cast<float4 *>(acc + p * ld + c) = v;
         if (out16 != nullptr) {
@@ -2015,6 +2029,19 @@ __global__ void __launch_bounds__(256) pack_conv1_kernel(const float *__restrict
     }
 }
 
+// conv1, four output pixels per GEMM row (tc_conv1_fwd, bf16): per filter row r a [4 x co_pad] x [128] block,
+//   Wp[(p, n)][r * 128 + ipx * 8 + c] = W[r][ipx - 2p][c][n]   (0 <= ipx - 2p < kw, c < ci; zero elsewhere)
+// -- output pixel p of the group reads input pixels 2p .. 2p + kw - 1 of the group's 16-pixel window
+__global__ void __launch_bounds__(256) pack_conv1x4_kernel(const float *__restrict__ W, __nv_bfloat16 *__restrict__ Wp, int kh, int kw, int ci, int co,
+                                                           int co_pad) {
+    const int total = 4 * co_pad * kh * 128;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int c = i & 7, ipx = (i >> 3) & 15, r = (i >> 7) % kh, row = i / (128 * kh);
+        const int p = row / co_pad, n = row - p * co_pad, x = ipx - 2 * p;
+        Wp[i] = __float2bfloat16_rn((c < ci && x >= 0 && x < kw && n < co) ? __ldg(W + (((long long)r * kw + x) * ci + c) * co + n) : 0.f);
+    }
+}
+
 struct Conv1Map {
     const float *base; int ok;
     TapInfo rows[8];
@@ -2047,6 +2074,62 @@ int tc_conv1_fwd(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, in
     DOFB_CHECK_ARG(g && (x || x16) && w && (y || y16), "dofb_conv1_fwd: null argument");
     TcParams P;
     memset(&P, 0, sizeof(P));
+    // ---- bf16, <= 64 output channels: FOUR output pixels per GEMM row (phase-in-N with "phase" = pixel of the group) ----
+    // The N = 64 form issues 28 M=128 instructions per 128 pixels and is bound by them (an instruction costs the same at N = 64 and at 256).
+    // A group of four x-adjacent output pixels reads a 13-pixel window of every filter row = K 104 -> 128 (two K blocks of the 16-pixel
+    // window, which is simply the next group's first block), against [4 x 64] x 128 weights holding the filter row at the four pixel shifts:
+    // 14 instructions per 128 pixels.  Groups are 8 input pixels = 128 bytes apart, so a tile row of groups is contiguous memory.
+    if (bf && g_pin && g->stride == 2 && g->ci <= 8 && g->co <= 64 && g->co % 16 == 0 && g->ow % 4 == 0 && g->kw <= 7 && g->kh <= 8 &&
+        (g_pin == 2 || (long long)g->oh * g->ow * g->B >= 512ll * num_sms() / 2)) {
+        const int rowoff = xp_y0 - g->pad_t, coloff = xp_x0 - g->pad_l, groups = g->ow / 4, npad = g->co;
+        DOFB_CHECK_ARG(xp_h % 2 == 0 && xp_w % 2 == 0 && aligned16(x16), "dofb_conv1: buffer sizes must be even and the buffer 16-byte aligned");
+        DOFB_CHECK_ARG(rowoff >= 0 && coloff >= 0, "dofb_conv1: the zero border must cover the SAME padding (%d,%d)", g->pad_t, g->pad_l);
+        if (8 * (groups - 1) + 16 + coloff <= xp_w && 2 * (g->oh - 1) + rowoff + g->kh <= xp_h) {
+            for (int kh = 0; kh < g->kh; ++kh) {
+                P.taps[kh].oy = (short)((kh + rowoff) >> 1); P.taps[kh].py = (short)((kh + rowoff) & 1);
+                P.taps[kh].ox = 0; P.taps[kh].px = 0; P.taps[kh].wk = kh * 128;
+            }
+            P.cnt_y = g->oh; P.cnt_x = groups; P.rstep = 1; P.rstep_x = 4;
+            choose_tile(P.cnt_y, P.cnt_x, P.TW, P.TH, P.TN);
+            const uint64_t rowb = (uint64_t)xp_w * 8 * 2;
+            CUtensorMap ma, mb;
+            {   // d0: the 16-pixel window (two K blocks), d1: group (8 pixels on), d2: row parity, d3: row pair, d4: image
+                const uint64_t dims[5] = {128, (uint64_t)groups, 2, (uint64_t)xp_h / 2, (uint64_t)g->B};
+                const uint64_t str[4] = {128, rowb, 2 * rowb, (uint64_t)xp_h * rowb};
+                const uint32_t box[5] = {64u, (uint32_t)P.TW, 1, (uint32_t)P.TH, (uint32_t)P.TN};
+                if (make_map(&ma, static_cast<const uint8_t *>(x16) + (size_t)coloff * 16, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)) return 1;
+            }
+            P.parity = 1; P.ntaps = g->kh; P.ncb = 2; P.a_coff = 0; P.a_ld = 0;
+            P.pin = npad; P.pin_tap0[0] = 0; P.pin_ntaps[0] = g->kh;
+            for (int q = 0; q < 4; ++q) P.pin_off[q] = (long long)q * y_ld;
+            P.out = y; P.out_ld = y_ld; P.out16 = reinterpret_cast<__nv_bfloat16 *>(y16);
+            P.bias = bias; P.n_valid = g->co; P.rh = g->oh; P.rw = g->ow; P.act = act; P.accumulate = 0; P.B = g->B;
+            P.tiles_x = (P.cnt_x + P.TW - 1) / P.TW;
+            P.tiles_y = (P.cnt_y + P.TH - 1) / P.TH;
+            const int tiles = P.tiles_x * P.tiles_y * ((g->B + P.TN - 1) / P.TN);
+            float *wp = nullptr;
+            const size_t welems = (size_t)4 * npad * g->kh * 128;
+            bool fresh = false;
+            if (get_pack_buffer(w, 26, (welems + 1) / 2, &wp, &fresh)) return 1;
+            if (!fresh) {
+                pack_conv1x4_kernel<<<(unsigned)((welems + 255) / 256), 256, 0, st>>>(w, reinterpret_cast<__nv_bfloat16 *>(wp), g->kh, g->kw, g->ci, g->co, npad);
+                DOFB_LAUNCH_OK();
+            }
+            const int bn = 4 * npad;             // 64 .. 256 columns
+            const bool pairs = g_cta_pairs && bn >= 128 && (tiles + 1) / 2 >= num_sms() / 2;
+            const uint64_t dims[2] = {(uint64_t)g->kh * 128, (uint64_t)bn};
+            const uint64_t str[1] = {(uint64_t)g->kh * 128 * 2};
+            const uint32_t box[2] = {64u, (uint32_t)(pairs ? bn / 2 : bn)};
+            if (make_map(&mb, wp, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)) return 1;
+            if (bn == 256) return pairs ? launch_tc<256, 6, true, true, false, true>(ma, mb, P, tiles, 1, st)
+                                        : launch_tc<256, 4, true, false, false, true>(ma, mb, P, tiles, 1, st);
+            if (bn == 128) return pairs ? launch_tc<128, 8, true, true, false, true>(ma, mb, P, tiles, 1, st)
+                                        : launch_tc<128, 6, true, false, false, true>(ma, mb, P, tiles, 1, st);
+            // (narrower: fall through to the one-pixel-per-row form)
+            memset(&P, 0, sizeof(P));
+        }
+    }
     P.cnt_y = g->oh; P.cnt_x = g->ow; P.rstep = 1;
     choose_tile(P.cnt_y, P.cnt_x, P.TW, P.TH, P.TN);
     CUtensorMap ma, mb;

@@ -728,3 +728,41 @@ def test_split_k_matches_unsplit(case, ks, pairs, mth):
         lib.dofb_enable_cta_pairs(1)
     for a, r in zip(res[1], res[0]):
         assert rel(a, r) < 5e-5           # same products, different fp32 summation order (K ranges meet through atomics)
+
+
+@pytest.mark.parametrize("B,H,W,ci,co", [(2, 64, 128, 6, 64), (1, 384, 512, 6, 64), (3, 48, 80, 3, 64), (2, 40, 72, 6, 32), (5, 16, 24, 6, 64)])
+def test_conv1_four_pixels_per_row_matches_one_pixel_form(B, H, W, ci, co):
+    """conv1 forward (bf16) with four x-adjacent output pixels per GEMM row (N = 4 x co, K = the 16-pixel window of a filter row) against
+    the one-pixel-per-row form: same products -> equal up to fp32 summation order; bias + ELU + bf16 shadow, pad channels untouched."""
+    from deepof_b200 import ops, _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(B * H + W + ci + co)
+    k = 7
+    img = torch.randn(B, H, W, ci, generator=g).cuda()
+    padded = torch.zeros(B, H + 6, W + 8, 8, device="cuda")
+    padded[:, 2:2 + H, 2:2 + W, :ci] = img
+    padded16 = padded.to(torch.bfloat16)
+    w = (torch.randn(k, k, ci, co, generator=g) / math.sqrt(k * k * ci)).cuda()
+    b = (torch.randn(co, generator=g) * 0.1).cuda()
+    geom = ops.conv_geom(B, H, W, ci, co, k, 2)
+    outs = []
+    try:
+        for on in (0, 2):
+            lib.dofb_enable_phase_in_n(on)
+            y = torch.zeros(B, geom.oh, geom.ow, 128, device="cuda")
+            ys = torch.zeros(y.shape, dtype=torch.bfloat16, device="cuda")
+            ops.conv1_fwd(geom, padded, (2, 2), w, b, ops.Slab(y, 32, co, ys), ops.ACT_ELU, padded16)
+            torch.cuda.synchronize()
+            assert torch.equal(ys[..., 32:32 + co], y[..., 32:32 + co].to(torch.bfloat16))
+            assert float(y[..., :32].abs().max()) == 0.0 and float(y[..., 32 + co:].abs().max()) == 0.0
+            assert float(ys[..., :32].abs().max()) == 0.0 and float(ys[..., 32 + co:].abs().max()) == 0.0
+            outs.append(y[..., 32:32 + co].clone())
+            if on == 2:                          # bf16-only output (lean schedule)
+                y2 = torch.zeros(y.shape, dtype=torch.bfloat16, device="cuda")
+                ops.conv1_fwd(geom, padded, (2, 2), w, b, ops.Slab(None, 32, co, y2), ops.ACT_ELU, padded16)
+                torch.cuda.synchronize()
+                assert torch.equal(y2, ys)
+    finally:
+        lib.dofb_enable_phase_in_n(1)
+    assert rel(outs[1], outs[0]) < 1e-5
+    assert float(outs[0].abs().max()) > 0.1
