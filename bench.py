@@ -455,6 +455,8 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's debug stream (the "NCCL version ..." banner it prints at the VERSION / WARN levels) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     cfg = CONFIGS[args.config]
     B = args.batch if args.batch else (cfg["batch"] if cfg["scaling"] == "weak" else max(1, cfg["batch"] // world))

@@ -8,7 +8,7 @@ B="python bench.py --math $MATH --no-cpu --no-accuracy --no-extras"
 ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 420 --csv --log-file gpurun_out/launches_${MATH}.csv \
     $B --steps 3 --warmup 3 > gpurun_out/ncu_bench_${MATH}.log 2>&1
 # 2) full-set captures of the dominant kernels (a few launches each, after the warm-up)
-ncu --set full --clock-control none --import-source on -k regex:"tc_gather_gemm|tc_mph" -s 60 -c 6 -f -o gpurun_out/prof_tc_gemm \
+ncu --set full --clock-control none --import-source on -k regex:"tc_gather_gemm" -s 60 -c 6 -f -o gpurun_out/prof_tc_gemm \
     $B --steps 1 --warmup 3 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:tc_wgrad -s 30 -c 3 -f -o gpurun_out/prof_tc_wgrad \
     $B --steps 1 --warmup 3 > /dev/null 2>&1
