@@ -275,7 +275,10 @@ def measure(cfg_name, math_mode, per_gpu_batch, steps, warmup, rank, local_rank,
     batches = []
     for j in range(2):
         s_, t_, _ = make_pairs(B, Hc, Wc, seed=1000 * rank + j)
-        batches.append((s_.pin_memory(), t_.pin_memory(), s_.to(dev), t_.to(dev)))
+        # 8-bit images, as the reference's loader hands them to feed_dict (cv2.imread / cv2.resize arrays, flyingChairsLoader.py:64-80): the
+        # end-to-end arm feeds the pinned uint8 arrays, the device-resident arm their float32 casts -- the same numbers
+        s8, t8 = s_.round().clamp_(0, 255).to(torch.uint8), t_.round().clamp_(0, 255).to(torch.uint8)
+        batches.append((s8.pin_memory(), t8.pin_memory(), s8.float().to(dev), t8.float().to(dev)))
     lr = 1.6e-5
 
     def device_step(i):
@@ -334,7 +337,7 @@ def measure(cfg_name, math_mode, per_gpu_batch, steps, warmup, rank, local_rank,
     out = {"config": cfg_name, "math": math_mode, "per_gpu_batch": B, "global_batch": gb, "hw": [Hc, Wc],
            "value": gb * steps / (ms * 1e-3), "ms_per_step": ms / steps, "e2e_value": gb * steps / (ms_e2e * 1e-3),
            "e2e_ms_per_step": ms_e2e / steps, "gpu_launches": launches, "ddp_replicas_in_sync": ddp_sync, "clocks": clocks,
-           "loss_after": loss_dev, "loss_after_e2e": last, "h2d_bytes_per_step": 2 * B * Hc * Wc * 3 * 4, "lean": bool(getattr(eng, "lean", False)),
+           "loss_after": loss_dev, "loss_after_e2e": last, "h2d_bytes_per_step": batches[0][0].numel() * batches[0][0].element_size() * 2, "lean": bool(getattr(eng, "lean", False)),
            "n_params": eng.arena.n_true}
     # ---- per-launch timing for the roofline (rank 0, a few instrumented LOCAL steps, CUDA events per launch) ----
     if rank == 0 and want_profile:
@@ -535,7 +538,8 @@ def run_ours(args, rank, local_rank, world):
             "clocks": main_m["clocks"],
             "e2e": {"value": main_m["e2e_value"], "unit": UNIT, "ms_per_step": main_m["e2e_ms_per_step"],
                     "h2d_bytes_per_step": main_m["h2d_bytes_per_step"], "d2h_bytes_per_step": 4,
-                    "api": "deepof_b200.flyingChairsTrain.TrainStep.run(feed_dict) + last_loss(lag=1): pinned-host inputs, "
+                    "api": "deepof_b200.flyingChairsTrain.TrainStep.run(feed_dict) + last_loss(lag=1): pinned-host uint8 BGR images (the dtype "
+                           "flyingChairsLoader.py:64-80 returns and flyingChairsTrain.py:178 feeds; cast on the device by the pre-processing kernel), "
                            "H2D on a copy stream double-buffered against the previous step, loss D2H read one step late"},
             "gpu_launches": main_m["gpu_launches"], "ddp_replicas_in_sync": main_m["ddp_replicas_in_sync"],
             "roofline": roof, "cpu_baseline": cpu, "modes": modes_out, "other_configs": others_out, "accuracy": accuracy,

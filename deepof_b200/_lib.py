@@ -61,6 +61,8 @@ SIGNATURES = {
                              C.POINTER(C.c_void_p), _P]),
     "dofb_preprocess_bf16": (_I, [_P, _P, C.POINTER(C.c_float), _F, _I, _I, _I, _P, _P, _I, _I, _I, _I, _I, C.POINTER(C.c_void_p),
                                   C.POINTER(C.c_void_p), _P]),
+    "dofb_preprocess_u8": (_I, [_P, _P, C.POINTER(C.c_float), _F, _I, _I, _I, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, C.POINTER(C.c_void_p),
+                                C.POINTER(C.c_void_p), _P]),
     "dofb_conv1_fwd": (_I, [_G, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _I, _P]),
     "dofb_conv_fwd_bf16": (_I, [_G, _P, _I, _P, _P, _P, _P, _I, _I, _P]),
     "dofb_conv_dgrad_bf16": (_I, [_G, _P, _I, _P, _P, _P, _P, _I, _I, _I, _P]),

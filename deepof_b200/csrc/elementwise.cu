@@ -33,6 +33,7 @@ int num_sms() {
 // resize_bilinear at an integer ratio is exact decimation, so no interpolation is needed).
 struct PreParams {
     const float *src, *tgt;
+    const uint8_t *src8, *tgt8;      // U8 kernels: 8-bit BGR images as cv2.imread / cv2.resize return them (flyingChairsLoader.py:70-78)
     float *x6, *x6b;
     __nv_bfloat16 *x6_16, *x6b_16;   // bf16 form of the network input (pitch 8), written instead of x6 / x6b when set
     int x6_ld, x6_h, x6_w, x6_y0, x6_x0;
@@ -102,7 +103,9 @@ __device__ __forceinline__ void preprocess_pixel(const PreParams &P, int b, int 
 }
 
 // VEC4: a thread owns 4 consecutive pixels of a row (W % 4 == 0, 16-byte aligned images): 3 + 3 float4 loads instead of 24 scalar ones
-template <bool VEC4>
+// U8: the images are uint8 (what the reference's loader feeds; TF casts them to the float32 placeholders on the host) -- the cast happens
+//     here, (float)u8 is exact, so the result is bit-identical to feeding the float32 copy
+template <bool VEC4, bool U8 = false>
 __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__ PreParams P) {
     const long long npix = (long long)P.B * P.H * P.W;
     const long long nitems = VEC4 ? npix / 4 : npix;
@@ -113,12 +116,22 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
         const int b = (int)(p / ((long long)P.W * P.H));
         if (VEC4) {
             float sv[12], tv[12];
-            const float4 *sp = reinterpret_cast<const float4 *>(P.src + p * 3), *tp = reinterpret_cast<const float4 *>(P.tgt + p * 3);
+            if (U8) {                               // 12 bytes per image: three 32-bit words
+                const uint32_t *sp = reinterpret_cast<const uint32_t *>(P.src8 + p * 3), *tp = reinterpret_cast<const uint32_t *>(P.tgt8 + p * 3);
 #pragma unroll
-            for (int i = 0; i < 3; ++i) {
-                const float4 u = __ldg(sp + i), v = __ldg(tp + i);
-                sv[4 * i] = u.x; sv[4 * i + 1] = u.y; sv[4 * i + 2] = u.z; sv[4 * i + 3] = u.w;
-                tv[4 * i] = v.x; tv[4 * i + 1] = v.y; tv[4 * i + 2] = v.z; tv[4 * i + 3] = v.w;
+                for (int i = 0; i < 3; ++i) {
+                    const uint32_t u = __ldg(sp + i), v = __ldg(tp + i);
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) { sv[4 * i + b] = (float)((u >> (8 * b)) & 0xffu); tv[4 * i + b] = (float)((v >> (8 * b)) & 0xffu); }
+                }
+            } else {
+                const float4 *sp = reinterpret_cast<const float4 *>(P.src + p * 3), *tp = reinterpret_cast<const float4 *>(P.tgt + p * 3);
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const float4 u = __ldg(sp + i), v = __ldg(tp + i);
+                    sv[4 * i] = u.x; sv[4 * i + 1] = u.y; sv[4 * i + 2] = u.z; sv[4 * i + 3] = u.w;
+                    tv[4 * i] = v.x; tv[4 * i + 1] = v.y; tv[4 * i + 2] = v.z; tv[4 * i + 3] = v.w;
+                }
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -131,8 +144,8 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const __grid_constant__
             float a[3], t[3];
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                a[c] = (__ldg(P.src + p * 3 + c) - P.mean[c]) / P.divisor;
-                t[c] = (__ldg(P.tgt + p * 3 + c) - P.mean[c]) / P.divisor;
+                a[c] = ((U8 ? (float)__ldg(P.src8 + p * 3 + c) : __ldg(P.src + p * 3 + c)) - P.mean[c]) / P.divisor;
+                t[c] = ((U8 ? (float)__ldg(P.tgt8 + p * 3 + c) : __ldg(P.tgt + p * 3 + c)) - P.mean[c]) / P.divisor;
             }
             preprocess_pixel(P, b, y, x, a, t);
         }
@@ -320,7 +333,7 @@ extern "C" void dofb_reset_launch_count(void) { g_launches.store(0); }
 
 static int preprocess_launch(const float *src, const float *tgt, const float mean_bgr[3], float divisor, int B, int H, int W, float *x6,
                              float *x6b, void *x6_16, void *x6b_16, int x6_ld, int x6_h, int x6_w, int x6_y0, int x6_x0, int n_scales,
-                             float *const *pyr_src, float *const *pyr_tgt, void *stream);
+                             float *const *pyr_src, float *const *pyr_tgt, void *stream, const uint8_t *src8 = nullptr, const uint8_t *tgt8 = nullptr);
 
 extern "C" int dofb_preprocess(const float *src, const float *tgt, const float mean_bgr[3], float divisor, int B, int H, int W, float *x6,
                                float *x6b, int x6_ld, int x6_h, int x6_w, int x6_y0, int x6_x0, int n_scales,
@@ -337,10 +350,21 @@ extern "C" int dofb_preprocess_bf16(const float *src, const float *tgt, const fl
                              pyr_tgt, stream);
 }
 
+// 8-bit images (the arrays flyingChairsLoader.hookTrainData returns, flyingChairsLoader.py:64-80): same outputs as dofb_preprocess /
+// dofb_preprocess_bf16 on their float32 casts, bit for bit.  x6 / x6b (fp32, pitch x6_ld) or x6_bf16 / x6b_bf16 (pitch 8); unused ones NULL.
+extern "C" int dofb_preprocess_u8(const unsigned char *src, const unsigned char *tgt, const float mean_bgr[3], float divisor, int B, int H, int W,
+                                  float *x6, float *x6b, int x6_ld, void *x6_bf16, void *x6b_bf16, int x6_h, int x6_w, int x6_y0, int x6_x0,
+                                  int n_scales, float *const *pyr_src, float *const *pyr_tgt, void *stream) {
+    DOFB_CHECK_ARG(src && tgt, "dofb_preprocess_u8: null images");
+    DOFB_CHECK_ARG(x6_bf16 == nullptr || (aligned16(x6_bf16) && (x6b_bf16 == nullptr || aligned16(x6b_bf16))), "dofb_preprocess_u8: bf16 buffers must be 16-byte aligned");
+    return preprocess_launch(nullptr, nullptr, mean_bgr, divisor, B, H, W, x6_bf16 ? nullptr : x6, x6_bf16 ? nullptr : x6b, x6_bf16, x6b_bf16,
+                             x6_bf16 ? 8 : x6_ld, x6_h, x6_w, x6_y0, x6_x0, n_scales, pyr_src, pyr_tgt, stream, src, tgt);
+}
+
 static int preprocess_launch(const float *src, const float *tgt, const float mean_bgr[3], float divisor, int B, int H, int W, float *x6,
                              float *x6b, void *x6_16, void *x6b_16, int x6_ld, int x6_h, int x6_w, int x6_y0, int x6_x0, int n_scales,
-                             float *const *pyr_src, float *const *pyr_tgt, void *stream) {
-    DOFB_CHECK_ARG(src && tgt && mean_bgr && (x6 || x6_16 || n_scales > 0), "dofb_preprocess: null argument");
+                             float *const *pyr_src, float *const *pyr_tgt, void *stream, const uint8_t *src8, const uint8_t *tgt8) {
+    DOFB_CHECK_ARG(((src && tgt) || (src8 && tgt8)) && mean_bgr && (x6 || x6_16 || n_scales > 0), "dofb_preprocess: null argument");
     DOFB_CHECK_ARG(B > 0 && H > 0 && W > 0 && (x6 == nullptr || x6_ld >= 6) && divisor != 0.f, "dofb_preprocess: bad shape B=%d H=%d W=%d ld=%d", B, H, W, x6_ld);
     DOFB_CHECK_ARG(n_scales >= 0 && n_scales <= 8, "dofb_preprocess: n_scales=%d out of range", n_scales);
     DOFB_CHECK_ARG(n_scales == 0 || (H % (1 << n_scales) == 0 && W % (1 << n_scales) == 0),
@@ -348,7 +372,7 @@ static int preprocess_launch(const float *src, const float *tgt, const float mea
     DOFB_CHECK_ARG(x6_ld != 8 || aligned16(x6), "dofb_preprocess: x6 must be 16-byte aligned");
     DOFB_CHECK_ARG((x6 == nullptr && x6_16 == nullptr) || (x6_y0 >= 0 && x6_x0 >= 0 && x6_y0 + H <= x6_h && x6_x0 + W <= x6_w), "dofb_preprocess: the image does not fit the x6 buffer");
     PreParams P;
-    P.src = src; P.tgt = tgt; P.x6 = x6; P.x6_ld = x6_ld; P.B = B; P.H = H; P.W = W;
+    P.src = src; P.tgt = tgt; P.src8 = src8; P.tgt8 = tgt8; P.x6 = x6; P.x6_ld = x6_ld; P.B = B; P.H = H; P.W = W;
     P.x6_h = x6_h; P.x6_w = x6_w; P.x6_y0 = x6_y0; P.x6_x0 = x6_x0; P.x6b = x6b;
     P.x6_16 = reinterpret_cast<__nv_bfloat16 *>(x6_16); P.x6b_16 = reinterpret_cast<__nv_bfloat16 *>(x6b_16);
     for (int c = 0; c < 3; ++c) P.mean[c] = mean_bgr[c];
@@ -359,7 +383,12 @@ static int preprocess_launch(const float *src, const float *tgt, const float mea
         P.pyr_tgt[s] = s < n_scales ? pyr_tgt[s] : nullptr;
         DOFB_CHECK_ARG(s >= n_scales || (P.pyr_src[s] && P.pyr_tgt[s]), "dofb_preprocess: null pyramid level %d", s);
     }
-    if (W % 4 == 0 && aligned16(src) && aligned16(tgt))
+    if (src8 != nullptr) {
+        if (W % 4 == 0 && (reinterpret_cast<uintptr_t>(src8) & 3) == 0 && (reinterpret_cast<uintptr_t>(tgt8) & 3) == 0)
+            preprocess_kernel<true, true><<<grid_for((long long)B * H * W / 4, 256), 256, 0, as_stream(stream)>>>(P);
+        else
+            preprocess_kernel<false, true><<<grid_for((long long)B * H * W, 256), 256, 0, as_stream(stream)>>>(P);
+    } else if (W % 4 == 0 && aligned16(src) && aligned16(tgt))
         preprocess_kernel<true><<<grid_for((long long)B * H * W / 4, 256), 256, 0, as_stream(stream)>>>(P);
     else
         preprocess_kernel<false><<<grid_for((long long)B * H * W, 256), 256, 0, as_stream(stream)>>>(P);

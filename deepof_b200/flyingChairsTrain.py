@@ -39,6 +39,7 @@ class _StepBase:
     of step i.  Subclasses name the image feeds (``FEEDS``) and say how the engine consumes them."""
     FEEDS: tuple = ()
     DEFAULT_WEIGHTS: list = []
+    U8_FEEDS = True             # raw 0..255 images: uint8 feeds are shipped as bytes (the pre-scaled feeds of the VGG trainer are float)
 
     def _init_io(self, engine, distributed):
         self.engine = engine
@@ -48,6 +49,9 @@ class _StepBase:
         # pinned staging for pageable (numpy) feeds: the feed_dict H2D copy of flyingChairsTrain.py:178
         self._pin = [[torch.empty(shape, dtype=torch.float32).pin_memory() for _ in range(n)] for _ in range(2)]
         self._dev = [[torch.empty(shape, dtype=torch.float32, device=self.device) for _ in range(n)] for _ in range(2)]
+        # uint8 feeds (what the reference's loader returns: cv2.imread / cv2.resize arrays, flyingChairsLoader.py:64-80; TF casts them to the
+        # float32 placeholders on the host): shipped as bytes -- a quarter of the H2D traffic -- and cast by the pre-processing kernel
+        self._pin8 = self._dev8 = None
         self._copy_stream = torch.cuda.Stream(device=self.device)
         self._copied = [torch.cuda.Event() for _ in range(2)]       # H2D of slot i finished
         self._consumed = [torch.cuda.Event() for _ in range(2)]     # the step reading slot i has consumed its inputs
@@ -66,25 +70,31 @@ class _StepBase:
         self._n_feed += 1
         if all(isinstance(a, torch.Tensor) and a.is_cuda for a in arrays):
             return None, arrays
+        as_u8 = self.U8_FEEDS and all((isinstance(a, np.ndarray) and a.dtype == np.uint8) or (isinstance(a, torch.Tensor) and a.dtype == torch.uint8) for a in arrays)
+        if as_u8 and self._pin8 is None:
+            shape = tuple(self._pin[0][0].shape)
+            self._pin8 = [[torch.empty(shape, dtype=torch.uint8).pin_memory() for _ in arrays] for _ in range(2)]
+            self._dev8 = [[torch.empty(shape, dtype=torch.uint8, device=self.device) for _ in arrays] for _ in range(2)]
+        pin, devb = (self._pin8, self._dev8) if as_u8 else (self._pin, self._dev)
         host = []
         for j, arr in enumerate(arrays):
-            t = torch.as_tensor(arr, dtype=torch.float32)
+            t = torch.as_tensor(arr) if as_u8 else torch.as_tensor(arr, dtype=torch.float32)
             if tuple(t.shape) != tuple(self._pin[slot][j].shape):
                 raise ValueError(f"feed '{self.FEEDS[j]}': expected shape {tuple(self._pin[slot][j].shape)}, got {tuple(t.shape)} "
                                  "(static shapes, like the reference's placeholders)")
             if not t.is_pinned():                     # pageable feed (numpy): one host memcpy into pinned staging
                 self._copied[slot].synchronize()      # the previous H2D out of this staging buffer is done
-                self._pin[slot][j].copy_(t)
-                t = self._pin[slot][j]
+                pin[slot][j].copy_(t)
+                t = pin[slot][j]
             host.append(t)
         cur = torch.cuda.current_stream(self.device)
         with torch.cuda.stream(self._copy_stream):
             self._copy_stream.wait_event(self._consumed[slot])      # the step that last read this device buffer is past its inputs
             for j, t in enumerate(host):
-                self._dev[slot][j].copy_(t, non_blocking=True)
+                devb[slot][j].copy_(t, non_blocking=True)
             self._copied[slot].record(self._copy_stream)
         cur.wait_event(self._copied[slot])
-        return slot, self._dev[slot]
+        return slot, devb[slot]
 
     # ---- engine adapters (overridden for the 4-feed guided model) ----
     def _forward(self, dev, lw, with_grad):

@@ -22,6 +22,7 @@ class TrainStep(_StepBase):
     ``loss_weight`` [5]; ``learning_rate``."""
     FEEDS = ("photo_source", "photo_target", "geo_source", "geo_target")
     DEFAULT_WEIGHTS = WEIGHT_L
+    U8_FEEDS = False            # the trainer pre-scales its feeds on the host (flyingChairsTrain_vgg.py:181-188): float arrays
 
     def __init__(self, batch_size: int = BATCH_SIZE, image_size=(320, 448), device="cuda", math_mode="fp32", seed: int | None = 1,
                  distributed: bool = False, **kw):

@@ -116,7 +116,12 @@ def conv_geom(B, ih, iw, ci, co, k, stride) -> ConvGeom:
 def preprocess(src, tgt, mean, x6, pyr_src, pyr_tgt, origin=(0, 0), x6b=None, divisor=255.0, x6_16=None, x6b_16=None):
     """x6 may be larger than the image (zero border for dofb_conv1_*); ``origin`` = (row, col) of the image in it.
     With ``x6b`` (siamese models) the source goes to x6[..., 0:3] and the target to x6b[..., 0:3] instead of 6 stacked channels."""
-    _req(src, "src"); _req(tgt, "tgt")
+    u8 = isinstance(src, torch.Tensor) and src.dtype == torch.uint8
+    if u8:          # 8-bit images as the reference's loader returns them (flyingChairsLoader.py:64-80): cast on the device, bit-identical
+        if not (isinstance(tgt, torch.Tensor) and tgt.dtype == torch.uint8 and src.is_cuda and tgt.is_cuda and src.is_contiguous() and tgt.is_contiguous()):
+            raise DeepOFError("preprocess: uint8 source needs a contiguous uint8 CUDA target as well")
+    else:
+        _req(src, "src"); _req(tgt, "tgt")
     if x6 is not None:
         _req(x6, "x6")
     B, H, W, _ = src.shape
@@ -127,6 +132,17 @@ def preprocess(src, tgt, mean, x6, pyr_src, pyr_tgt, origin=(0, 0), x6b=None, di
     ps = (C.c_void_p * max(n, 1))(*[t.data_ptr() for t in pyr_src])
     pt = (C.c_void_p * max(n, 1))(*[t.data_ptr() for t in pyr_tgt])
     lib = _lib.load()
+    if u8:
+        if x6_16 is not None:
+            assert x6_16.dtype == torch.bfloat16 and x6_16.shape[3] == 8 and x6_16.is_cuda and x6_16.is_contiguous()
+        ref = x6_16 if x6_16 is not None else x6
+        xs = ref.shape if ref is not None else (0, 0, 0, 0)
+        check(lib.dofb_preprocess_u8(src.data_ptr(), tgt.data_ptr(), m, float(divisor), B, H, W,
+                                     x6.data_ptr() if (x6 is not None and x6_16 is None) else None,
+                                     x6b.data_ptr() if (x6b is not None and x6_16 is None) else None, xs[3],
+                                     x6_16.data_ptr() if x6_16 is not None else None, x6b_16.data_ptr() if x6b_16 is not None else None,
+                                     xs[1], xs[2], origin[0], origin[1], n, ps, pt, _stream()))
+        return
     if x6_16 is not None:           # bf16 network input only (bf16 first-layer kernels): no fp32 x6 is written
         assert x6_16.dtype == torch.bfloat16 and x6_16.shape[3] == 8 and x6_16.is_cuda and x6_16.is_contiguous()
         check(lib.dofb_preprocess_bf16(src.data_ptr(), tgt.data_ptr(), m, float(divisor), B, H, W, x6_16.data_ptr(),

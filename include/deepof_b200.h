@@ -60,6 +60,13 @@ int dofb_preprocess(const float *src, const float *tgt, const float mean_bgr[3],
 int dofb_preprocess_bf16(const float *src, const float *tgt, const float mean_bgr[3], float divisor, int B, int H, int W,
                          void *x6_bf16, void *x6b_bf16 /* may be NULL */, int x6_h, int x6_w, int x6_y0, int x6_x0, int n_scales,
                          float *const *pyr_src, float *const *pyr_tgt, void *stream);
+/* The same pre-processing from 8-bit BGR images -- the arrays the reference's loader returns (cv2.imread + cv2.resize, flyingChairsLoader.py:64-80)
+ * and its trainer feeds to the float32 placeholders (flyingChairsTrain.py:173-178; TF casts on the host).  (float)u8 is exact: outputs are
+ * bit-identical to dofb_preprocess / dofb_preprocess_bf16 on the float32 casts, with a quarter of the host-to-device bytes.  Give either the
+ * fp32 network input (x6 [, x6b], pitch x6_ld) or the bf16 one (x6_bf16 [, x6b_bf16], pitch 8); the others NULL. */
+int dofb_preprocess_u8(const unsigned char *src, const unsigned char *tgt, const float mean_bgr[3], float divisor, int B, int H, int W,
+                       float *x6, float *x6b, int x6_ld, void *x6_bf16, void *x6b_bf16, int x6_h, int x6_w, int x6_y0, int x6_x0,
+                       int n_scales, float *const *pyr_src, float *const *pyr_tgt, void *stream);
 
 /* ---- warp + Charbonnier photometric + smoothness loss -------------------- */
 /* Replaces: flyingChairsWrapFlow.loss_interp (flyingChairsWrapFlow.py:752-876,

@@ -96,3 +96,39 @@ def test_train_class_runs_from_a_dataset_directory(tmp_path):
     finally:
         deepOF_fc.IMAGE_SIZE[:] = [320, 448]
     assert t.step.engine.t == 2 and np.isfinite(t.step.last_loss())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("math_mode", ["fp32", "bf16"])
+def test_uint8_feeds_equal_their_float32_casts(math_mode, monkeypatch):
+    """TrainStep.run / fetch with uint8 images (what flyingChairsLoader.hookTrainData returns) == the same images fed as float32: the cast
+    happens in the pre-processing kernel and (float)u8 is exact -> identical network inputs, pyramids, losses and flows."""
+    import torch
+    from deepof_b200 import ops
+    from deepof_b200.flyingChairsTrain import TrainStep, WEIGHT_L
+    monkeypatch.setenv("DOFB_SPLITK", "0")        # bit-for-bit comparison of two engines: no atomically summed K ranges
+    B, H, W = 2, 192, 256                          # (smaller maps have an empty border mask at scale 6: NaN losses)
+    g = torch.Generator().manual_seed(3)
+    src8 = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8)
+    tgt8 = torch.randint(0, 256, (B, H, W, 3), generator=g, dtype=torch.uint8)
+    outs = []
+    for feed in ((src8.numpy(), tgt8.numpy()), (src8.float().numpy(), tgt8.float().numpy())):
+        step = TrainStep(B, (H, W), math_mode=math_mode, seed=1)
+        losses, flows, total = step.fetch({"source_img": feed[0], "target_img": feed[1], "loss_weight": WEIGHT_L})
+        step.run({"source_img": feed[0], "target_img": feed[1], "loss_weight": WEIGHT_L, "learning_rate": 1e-5})
+        outs.append((total, flows, step.last_loss(), step.engine.pyr_src[1].clone(), step.engine.pyr_tgt[2].clone()))
+    a, b = outs
+    assert np.isfinite(a[0]) and a[0] == b[0] and a[2] == b[2]
+    for fa, fb in zip(a[1], b[1]):
+        assert (fa == fb).all()
+    assert torch.equal(a[3], b[3]) and torch.equal(a[4], b[4])
+    # odd width: scalar path of the kernel
+    s8 = torch.randint(0, 256, (1, 8, 10, 3), generator=g, dtype=torch.uint8).cuda()
+    t8 = torch.randint(0, 256, (1, 8, 10, 3), generator=g, dtype=torch.uint8).cuda()
+    xa, xb = torch.zeros(1, 8, 10, 8, device="cuda"), torch.zeros(1, 8, 10, 8, device="cuda")
+    pa = [torch.zeros(1, 4, 5, 3, device="cuda") for _ in range(2)]
+    pb = [torch.zeros(1, 4, 5, 3, device="cuda") for _ in range(2)]
+    ops.preprocess(s8, t8, (100.0, 110.0, 120.0), xa, pa[:1], pa[1:])
+    ops.preprocess(s8.float(), t8.float(), (100.0, 110.0, 120.0), xb, pb[:1], pb[1:])
+    torch.cuda.synchronize()
+    assert torch.equal(xa, xb) and torch.equal(pa[0], pb[0]) and torch.equal(pa[1], pb[1])
