@@ -603,7 +603,9 @@ extern "C" int dofb_uppr_bwd(const float *pr, const float *dy, int dy_ld, int B,
     DOFB_CHECK_ARG(dy_ld % 2 == 0 && (reinterpret_cast<uintptr_t>(dy) & 7u) == 0, "dofb_uppr_bwd: dy slice must be 8-byte aligned with an even pitch");
     const long long n = (long long)B * h * w;
     long long blocks = (n + 255) / 256;
-    const long long cap = (long long)num_sms() * 8;
+    // every warp ends with 64 shuffle reductions of its weight-gradient accumulators (~1000 instructions): two blocks per SM amortise that
+    // over several pixels per thread (ncu: 22.6 M warp instructions for 393 k pixels with one pixel per thread)
+    const long long cap = (long long)num_sms() * 2;
     if (blocks > cap) blocks = cap;
     uppr_bwd_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(pr, dy, dy_ld, B, h, w, wt, dpr, dwt, dbias);
     DOFB_LAUNCH_OK();

@@ -7,6 +7,6 @@ for rep in 1 2; do for v in ${VARIANTS:-A B}; do
   python - <<PY
 import json
 d=json.load(open("gpurun_out/ab_$v$rep.json")); pt=json.load(open("gpurun_out/bench_layers_flownets_bf16_n1.json"))["per_tag_ms"]
-print("$v$rep", round(d["ms_per_step"],4), {k: round(pt[k],4) for k in ("conv_fwd:conv1","conv_dgrad:conv2","conv_dgrad:conv3_1","deconv_fwd:upconv1","deconv_dgrad:upconv1","conv_fwd:conv2")})
+print("$v$rep", round(d["ms_per_step"],4), {k: round(pt[k],4) for k in [k for k in pt if any(t in k for t in "${TAGS:-conv_fwd:conv1 conv_dgrad:conv2}".split())]})
 PY
 done; done
