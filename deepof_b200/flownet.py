@@ -160,6 +160,12 @@ class FlowNetS:
         ops._lib.load().dofb_enable_halo_tiles(1 if os.environ.get("DOFB_HALO", "0") == "1" else 0)
         ops._lib.load().dofb_enable_phase_in_n(0 if os.environ.get("DOFB_PIN", "1") == "0" else 1)      # phase-in-N stride-2 transposed gathers
         ops._lib.load().dofb_enable_split_k(int(os.environ.get("DOFB_SPLITK", "1")))                    # split-K of the coarse layers
+        # second stream for the flow-head / up_pr chains (small, latency-bound launches that only meet the big GEMMs at level boundaries)
+        self._side = None
+        if self.lean and os.environ.get("DOFB_SIDE_STREAM", "1") != "0":
+            with torch.cuda.device(self.device):
+                self._side = torch.cuda.Stream(device=self.device)
+        self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
         ops._lib.load().dofb_enable_wgrad_npack(0 if os.environ.get("DOFB_NPACK", "1") == "0" else 1)
         self.profile = None            # list of (tag, start_event, end_event) when per-launch timing is on
         self._nvtx = os.environ.get("DOFB_NVTX", "0") == "1"
@@ -169,6 +175,27 @@ class FlowNetS:
     @staticmethod
     def param_shapes():
         return param_shapes()
+
+    # ---- side stream: fork = the side stream waits for everything enqueued on the main stream so far; join = the reverse ----
+    def _side_on(self) -> bool:
+        return self._side is not None and self.profile is None and not self._nvtx
+
+    def _fork(self):
+        if self._side_on():
+            self._ev_fork.record()
+            self._side.wait_event(self._ev_fork)
+
+    def _join(self):
+        if self._side_on():
+            self._ev_join.record(self._side)
+            torch.cuda.current_stream(self.device).wait_event(self._ev_join)
+
+    def _ks(self, tag, fn, *args, **kw):
+        """_k on the side stream (between _fork() and _join()); serial when profiling."""
+        if not self._side_on():
+            return self._k(tag, fn, *args, **kw)
+        with torch.cuda.stream(self._side):
+            return fn(*args, **kw)
 
     def _k(self, tag, fn, *args, **kw):
         """Launch one kernel; with self.profile set, bracket it with CUDA events on the launch stream."""
@@ -381,7 +408,7 @@ class FlowNetS:
             self._jobs = ops.make_pack_jobs(entries)
         return self._jobs
 
-    def _head_fwd(self, s, x):
+    def _head_fwd(self, s, x, side=False):
         """pr_s = 3x3 conv to 2 channels.  Coarse scales (small maps, 386..1026 input channels) are GEMM-shaped with a long K and too few
         pixels to fill the GPU with the streaming SIMT kernel, so in the tensor-core math modes they run through the gather-GEMM
         (N padded to 32); the fine scales are bandwidth-bound and stay on the strip kernel."""
@@ -389,8 +416,9 @@ class FlowNetS:
         h, w = self.hw[s]
         if self.lean:       # tap-in-N: Z = x (1x1) Wz on the tensor pipe (x crosses the chip once), pr = bias + 9-tap sum over the 20-float map
             z = self.head_z[s]
-            self._k(f"head_fwd:pr{s}", ops.conv_fwd, self._head_geom1[s], x, self.head_wz[s], None, full(z), ACT_NONE, MATH_BF16)
-            self._k(f"head_tapsum:pr{s}", ops.head_tapsum, z, P[f"pr{s}/biases"], self.pr[s])
+            k = self._ks if side else self._k
+            k(f"head_fwd:pr{s}", ops.conv_fwd, self._head_geom1[s], x, self.head_wz[s], None, full(z), ACT_NONE, MATH_BF16)
+            k(f"head_tapsum:pr{s}", ops.head_tapsum, z, P[f"pr{s}/biases"], self.pr[s])
         elif self.math != MATH_FP32 and self.B * h * w <= self.TC_HEAD_MAX_PIX:
             g = self._head_geom.get(s)
             if g is None:
@@ -467,10 +495,14 @@ class FlowNetS:
         for R in self.refine:
             s = R["s"]
             x, _ = self.feat[s]
-            self._head_fwd(s, x)
+            # lean engine: the flow-head chain of the level (Z GEMM -> tap sum -> up_pr) runs on the side stream next to the transposed
+            # convolution; both read feat_s and write disjoint channel slices of feat_{s-1}
+            self._fork()
+            self._head_fwd(s, x, side=True)
+            self._ks("uppr_fwd:" + R["uppr"], ops.uppr_fwd, self.pr[s], P[R["uppr"] + "/weights"], P[R["uppr"] + "/biases"], R["pr_y"])
             self._k("deconv_fwd:" + R["up"], ops.conv_dgrad, R["g"], x, P[R["up"] + "/weights"], P[R["up"] + "/biases"],
                     R["up_y"], ACT_ELU, False, mth)
-            self._k("uppr_fwd:" + R["uppr"], ops.uppr_fwd, self.pr[s], P[R["uppr"] + "/weights"], P[R["uppr"] + "/biases"], R["pr_y"])
+            self._join()
         self._head_fwd(1, self.feat[1][0])
         lw = [float(v) for v in loss_weight]
         self.loss_weight = lw
@@ -507,14 +539,15 @@ class FlowNetS:
         if reducer is not None:
             reducer.ready(min(self.arena.offsets[n + "/weights"] for n in names))
 
-    def _head_wgrad_tc(self, s):
+    def _head_wgrad_tc(self, s, side=False):
         """dW_pr_s on the tensor pipe: D9 = bf16 im2col of dpr_s (+ bias gradient), dW = feat_s^T . D9 (1x1 weight-gradient GEMM, feat_s read
         once) accumulated straight into the canonical [3,3,C,2] gradient."""
         G = self.grads
         x, _ = self.feat[s]
         d9 = self.head_d9[s]
-        self._k(f"head_dpr9:pr{s}", ops.head_dpr9, self.dpr[s], d9, G[f"pr{s}/biases"])
-        self._k(f"head_wgrad:pr{s}", ops.head_wgrad_tc, x, d9, G[f"pr{s}/weights"])
+        k = self._ks if side else self._k
+        k(f"head_dpr9:pr{s}", ops.head_dpr9, self.dpr[s], d9, G[f"pr{s}/biases"])
+        k(f"head_wgrad:pr{s}", ops.head_wgrad_tc, x, d9, G[f"pr{s}/weights"])
 
     def _backward_lean(self, reducer=None):
         """Backward of the lean bf16 engine: same order as backward(), but no kernel writes a flow head's input gradient: the pass that
@@ -534,12 +567,16 @@ class FlowNetS:
             slab_d = fd.sub(skipc, upc + 2)
             self._k("elu_bwd:" + R["up"], ops.head_dgrad_elu, self.head_d9[fs], self.head_wz[fs], skipc, None if fs == 1 else slab_d,
                     fy.sub(skipc, upc + 2), slab_d, upc, G[R["up"] + "/biases"], self.dpr_up[fs])
-            self._k("uppr_bwd:" + R["uppr"], ops.uppr_bwd, self.pr[s], full(self.dpr_up[fs]), P[R["uppr"] + "/weights"], self.dpr[s],
-                    G[R["uppr"] + "/weights"], G[R["uppr"] + "/biases"])
+            # side stream: up_pr backward -> D9 of pr_s -> head weight gradient (reads feat_s, dpr; writes dpr_s, D9_s, their gradients);
+            # main stream: the transposed convolution's weight and input gradients (read the finished slab, write d feat_s)
+            self._fork()
+            self._ks("uppr_bwd:" + R["uppr"], ops.uppr_bwd, self.pr[s], full(self.dpr_up[fs]), P[R["uppr"] + "/weights"], self.dpr[s],
+                     G[R["uppr"] + "/weights"], G[R["uppr"] + "/biases"])
+            self._head_wgrad_tc(s, side=True)
             self._k("deconv_wgrad:" + R["up"], ops.conv_wgrad, R["g"], R["up_dy"], x, G[R["up"] + "/weights"], None, mth)
             self._k("deconv_dgrad:" + R["up"], ops.conv_fwd, R["g"], R["up_dy"], P[R["up"] + "/weights"], None, Slab(dx.t, dx.c0, dx.c),
                     ACT_NONE, mth)                           # first (plain-store) writer of d feat_s
-            self._head_wgrad_tc(s)
+            self._join()
             self._grad_ready(reducer, f"pr{s}", R["up"], R["uppr"])
         rev = list(reversed(self.tower))
         for i, L in enumerate(rev):
