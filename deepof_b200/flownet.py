@@ -166,6 +166,9 @@ class FlowNetS:
             with torch.cuda.device(self.device):
                 self._side = torch.cuda.Stream(device=self.device)
         self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
+        # ... and every weight gradient as well: the main stream keeps the critical chain (ELU' pass -> input gradient -> next ELU' pass), the
+        # weight-gradient GEMMs queue up behind it on the side stream and share the SMs with the bandwidth-bound ELU' passes
+        self._side_wgrad = self._side is not None and os.environ.get("DOFB_SIDE_WGRAD", "1") != "0"
         ops._lib.load().dofb_enable_wgrad_npack(0 if os.environ.get("DOFB_NPACK", "1") == "0" else 1)
         self.profile = None            # list of (tag, start_event, end_event) when per-launch timing is on
         self._nvtx = os.environ.get("DOFB_NVTX", "0") == "1"
@@ -189,6 +192,18 @@ class FlowNetS:
         if self._side_on():
             self._ev_join.record(self._side)
             torch.cuda.current_stream(self.device).wait_event(self._ev_join)
+
+    def _join_at(self, ev):
+        """The main stream waits for an event recorded on the side stream (finer than _join: later side work keeps running)."""
+        if self._side_on():
+            torch.cuda.current_stream(self.device).wait_event(ev)
+
+    def _side_event(self):
+        if not self._side_on():
+            return None
+        ev = torch.cuda.Event()
+        ev.record(self._side)
+        return ev
 
     def _ks(self, tag, fn, *args, **kw):
         """_k on the side stream (between _fork() and _join()); serial when profiling."""
@@ -463,11 +478,15 @@ class FlowNetS:
                 self._k("elu_bwd:" + L["name"], ops.head_dgrad_elu, self.head_d9[hs], self.head_wz[hs], 0, L["dy"], L["y"], L["dy"], L["y"].c, db)
             else:
                 self._k("elu_bwd:" + L["name"], ops.elu_bwd, L["dy"], L["y"], db, mth == MATH_BF16 and mthw == MATH_BF16)
+            wk = self._k
+            if self.lean and self._side_wgrad:      # weight gradient behind the side stream's queue; the input gradient below does not wait for it
+                self._fork()
+                wk = self._ks
             if L["xpad"] is not None:
-                self._k("conv_wgrad:" + L["name"], ops.conv1_wgrad, L["g"], L["xpad"], self.x6_origin, L["dy"], dw, None,
-                        self._sh.get(id(L["xpad"])) if mthw == MATH_BF16 else None)
+                wk("conv_wgrad:" + L["name"], ops.conv1_wgrad, L["g"], L["xpad"], self.x6_origin, L["dy"], dw, None,
+                   self._sh.get(id(L["xpad"])) if mthw == MATH_BF16 else None)
             else:
-                self._k("conv_wgrad:" + L["name"], ops.conv_wgrad, L["g"], L["x"], L["dy"], dw, None, mthw)
+                wk("conv_wgrad:" + L["name"], ops.conv_wgrad, L["g"], L["x"], L["dy"], dw, None, mthw)
             if L["dx"] is not None:
                 dx = Slab(L["dx"].t, L["dx"].c0, L["dx"].c) if self.lean else L["dx"]      # (lean: no bf16 shadow of an unfinished gradient)
                 self._k("conv_dgrad:" + L["name"], ops.conv_dgrad, L["g"], L["dy"], w, None, dx, ACT_NONE, L["acc"], mth)
@@ -534,10 +553,15 @@ class FlowNetS:
         return torch.dot(self.loss4[:, 0], self._lw_dev)
 
     # ------------------------------------------------------------------ backward
-    def _grad_ready(self, reducer, *names):
-        """Tell the gradient reducer that every parameter at or above the lowest offset of ``names`` has its final gradient."""
+    def _grad_ready(self, reducer, *names, side=False):
+        """Tell the gradient reducer that every parameter at or above the lowest offset of ``names`` has its final gradient
+        (``side``: the last writers were enqueued on the side stream -- the all-reduce must order itself behind that stream)."""
         if reducer is not None:
-            reducer.ready(min(self.arena.offsets[n + "/weights"] for n in names))
+            if side and self._side_on():
+                with torch.cuda.stream(self._side):
+                    reducer.ready(min(self.arena.offsets[n + "/weights"] for n in names))
+            else:
+                reducer.ready(min(self.arena.offsets[n + "/weights"] for n in names))
 
     def _head_wgrad_tc(self, s, side=False):
         """dW_pr_s on the tensor pipe: D9 = bf16 im2col of dpr_s (+ bias gradient), dW = feat_s^T . D9 (1x1 weight-gradient GEMM, feat_s read
@@ -547,7 +571,9 @@ class FlowNetS:
         d9 = self.head_d9[s]
         k = self._ks if side else self._k
         k(f"head_dpr9:pr{s}", ops.head_dpr9, self.dpr[s], d9, G[f"pr{s}/biases"])
+        ev = self._side_event() if side else None
         k(f"head_wgrad:pr{s}", ops.head_wgrad_tc, x, d9, G[f"pr{s}/weights"])
+        return ev
 
     def _backward_lean(self, reducer=None):
         """Backward of the lean bf16 engine: same order as backward(), but no kernel writes a flow head's input gradient: the pass that
@@ -572,17 +598,23 @@ class FlowNetS:
             self._fork()
             self._ks("uppr_bwd:" + R["uppr"], ops.uppr_bwd, self.pr[s], full(self.dpr_up[fs]), P[R["uppr"] + "/weights"], self.dpr[s],
                      G[R["uppr"] + "/weights"], G[R["uppr"] + "/biases"])
-            self._head_wgrad_tc(s, side=True)
-            self._k("deconv_wgrad:" + R["up"], ops.conv_wgrad, R["g"], R["up_dy"], x, G[R["up"] + "/weights"], None, mth)
+            ev_d9 = self._head_wgrad_tc(s, side=True)        # (event: D9_s written -- all the next ELU' pass needs from the side stream)
+            wk = self._ks if self._side_wgrad else self._k
+            wk("deconv_wgrad:" + R["up"], ops.conv_wgrad, R["g"], R["up_dy"], x, G[R["up"] + "/weights"], None, mth)
             self._k("deconv_dgrad:" + R["up"], ops.conv_fwd, R["g"], R["up_dy"], P[R["up"] + "/weights"], None, Slab(dx.t, dx.c0, dx.c),
                     ACT_NONE, mth)                           # first (plain-store) writer of d feat_s
-            self._join()
-            self._grad_ready(reducer, f"pr{s}", R["up"], R["uppr"])
+            if self._side_wgrad:
+                self._join_at(ev_d9)
+                self._grad_ready(reducer, f"pr{s}", R["up"], R["uppr"], side=True)
+            else:
+                self._join()
+                self._grad_ready(reducer, f"pr{s}", R["up"], R["uppr"])
         rev = list(reversed(self.tower))
         for i, L in enumerate(rev):
             self._bwd_layer(L)
             if L["op"] == "conv" and all(M.get("wname") != L["wname"] for M in rev[i + 1:]):
-                self._grad_ready(reducer, L["wname"])
+                self._grad_ready(reducer, L["wname"], side=self._side_wgrad)
+        self._join()                                          # every weight gradient is in before the all-reduce join / Adam
 
     def backward(self, reducer=None):
         if self.lean:
