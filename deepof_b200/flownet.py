@@ -504,6 +504,8 @@ class FlowNetS:
             raise ops.DeepOFError(f"expected [B={self.B},{self.H},{self.W},3] NHWC inputs, got {tuple(source.shape)} / {tuple(target.shape)}")
         P, mth = self.params, self.math
         self._preprocess(source, target)
+        # (the weight re-pack was tried on the side stream under the pre-processing kernel and conv1: no gain -- its 9.6 k small blocks fill
+        # the SMs' thread slots first and the persistent GEMM CTAs wait for them anyway)
         if self.lean:
             sc = range(1, self.N_SCALES + 1)
             self._k("pack_weights", ops.head_wz_pack, [P[f"pr{s}/weights"] for s in sc], [self.head_wz[s] for s in sc])
