@@ -126,51 +126,96 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / power / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML in a background thread (first
+    sample within a millisecond of start(); the timed region of K = 10 steps is only ~60 ms, shorter than nvidia-smi's start-up);
+    falls back to `nvidia-smi -lms` when the NVML binding is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    PERIOD_S = 0.004
 
     def __init__(self, gpu_index: int):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
         self.gpu = gpu_index
+        self.p = self.f = self.thread = None
+        self.rows = []          # (sm_mhz, max_mhz, power_w, reasons bitmask)
+        self._stop = False
+        self.source = None
+
+    def _nvml_loop(self, nv, h, mx):
+        while not self._stop:
+            try:
+                self.rows.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), mx, nv.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                                  int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))))
+            except Exception:
+                pass
+            time.sleep(self.PERIOD_S)
 
     def start(self):
         try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices: map the CUDA ordinal through CUDA_VISIBLE_DEVICES when it lists indices
+            idx = self.gpu
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                idx = int(vis.split(",")[self.gpu])
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self._nv = nv
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h, mx), daemon=True)
+            self.thread.start()
+            self.source = "nvml"
+            return
+        except Exception:
+            self.thread = None
+        try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                        "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+            self.source = "nvidia-smi"
         except Exception:
             self.p = None
 
     def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush()
-        rows = [r.split(",") for r in Path(self.f.name).read_text().strip().splitlines() if r.strip()]
         sm, mx, pw, reasons = [], [], [], set()
-        for r in rows:
-            try:
-                r = [c.strip() for c in r]
-                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
+        if self.thread is not None:
+            self._stop = True
+            self.thread.join(timeout=2)
+            nv = self._nv
+            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+            for s_, m_, p_, r_ in self.rows:
+                sm.append(s_); mx.append(m_); pw.append(p_)
+                for name, bit in bits.items():
+                    if r_ & bit:
                         reasons.add(name)
+        elif self.p is not None:
+            time.sleep(0.15)
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
             except Exception:
-                continue
-        os.unlink(self.f.name)
+                self.p.kill()
+            self.f.flush()
+            for r in [r.split(",") for r in Path(self.f.name).read_text().strip().splitlines() if r.strip()]:
+                try:
+                    r = [c.strip() for c in r]
+                    sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+                except Exception:
+                    continue
+            os.unlink(self.f.name)
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML binding and no nvidia-smi"]}
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         # "under load" = samples in the upper half of the power range seen
         thr = min(pw) + 0.5 * (max(pw) - min(pw))
         load = [s for s, p in zip(sm, pw) if p >= thr] or sm
         return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "reasons": sorted(reasons), "source": self.source}
 
 
 # ----------------------------------------------------------------------------- CPU / reference arm
