@@ -503,9 +503,20 @@ def run_ours(args, rank, local_rank, world):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's debug stream (the "NCCL version ..." banner it prints at the VERSION / WARN levels) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly one JSON line: whatever NCCL / the launcher print while the communicator comes up (the "NCCL version ..."
+        # banner) is sent to stderr by pointing file descriptor 1 at it for the duration of the initialisation
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            t0 = torch.zeros(1, device=dev)
+            dist.all_reduce(t0)                  # (communicator fully up before the descriptor is restored)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     cfg = CONFIGS[args.config]
     B = args.batch if args.batch else (cfg["batch"] if cfg["scaling"] == "weak" else max(1, cfg["batch"] // world))
     main_m = measure(args.config, args.math, B, args.steps, args.warmup, rank, local_rank, world, want_clocks=True, want_profile=True)

@@ -169,6 +169,8 @@ class FlowNetS:
         # ... and every weight gradient as well: the main stream keeps the critical chain (ELU' pass -> input gradient -> next ELU' pass), the
         # weight-gradient GEMMs queue up behind it on the side stream and share the SMs with the bandwidth-bound ELU' passes
         self._side_wgrad = self._side is not None and os.environ.get("DOFB_SIDE_WGRAD", "1") != "0"
+        self._zero_ev = None
+        self._side_extra = self._side_wgrad and os.environ.get("DOFB_SIDE_EXTRA", "1") != "0"   # gradient clear under the forward, pr1's weight gradient
         ops._lib.load().dofb_enable_wgrad_npack(0 if os.environ.get("DOFB_NPACK", "1") == "0" else 1)
         self.profile = None            # list of (tag, start_event, end_event) when per-launch timing is on
         self._nvtx = os.environ.get("DOFB_NVTX", "0") == "1"
@@ -503,6 +505,11 @@ class FlowNetS:
         if tuple(source.shape) != (self.B, self.H, self.W, 3) or tuple(target.shape) != (self.B, self.H, self.W, 3):
             raise ops.DeepOFError(f"expected [B={self.B},{self.H},{self.W},3] NHWC inputs, got {tuple(source.shape)} / {tuple(target.shape)}")
         P, mth = self.params, self.math
+        if with_grad and self.lean and self._side_extra and self._side_on():
+            # clear the gradient arena (weight gradients accumulate through atomics) on the side stream while the forward runs
+            self._fork()
+            self._ks("zero_grad", self.grad.zero_)
+            self._zero_ev = self._side_event()
         self._preprocess(source, target)
         # (the weight re-pack was tried on the side stream under the pre-processing kernel and conv1: no gain -- its 9.6 k small blocks fill
         # the SMs' thread slots first and the persistent GEMM CTAs wait for them anyway)
@@ -581,11 +588,21 @@ class FlowNetS:
         """Backward of the lean bf16 engine: same order as backward(), but no kernel writes a flow head's input gradient: the pass that
         finishes each channel slab of feat_s (ELU' + bias gradient + bf16 shadow) adds it on the fly (dofb_head_dgrad_elu_bf16)."""
         P, G, mth = self.params, self.grads, self.math
-        self._k("zero_grad", self.grad.zero_)
+        if self._zero_ev is not None:       # the gradient arena was cleared on the side stream under the forward pass
+            self._join_at(self._zero_ev)
+            self._zero_ev = None
+        else:
+            self._k("zero_grad", self.grad.zero_)
         if reducer is not None:
             reducer.begin()
-        self._head_wgrad_tc(1)
-        self._grad_ready(reducer, "pr1")
+        if self._side_extra:        # D9 of pr1 on the main stream (the first ELU' pass reads it), its weight-gradient GEMM behind it on the side stream
+            self._k("head_dpr9:pr1", ops.head_dpr9, self.dpr[1], self.head_d9[1], G["pr1/biases"])
+            self._fork()
+            self._ks("head_wgrad:pr1", ops.head_wgrad_tc, self.feat[1][0], self.head_d9[1], G["pr1/weights"])
+            self._grad_ready(reducer, "pr1", side=True)
+        else:
+            self._head_wgrad_tc(1)
+            self._grad_ready(reducer, "pr1")
         for R in reversed(self.refine):                      # s = 2,3,4,5,6
             s, fs = R["s"], R["s"] - 1
             x, dx = self.feat[s]
