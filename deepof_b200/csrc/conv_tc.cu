@@ -2633,6 +2633,9 @@ int tc_corr_bwd(const float *f1, const float *f2, int ld, int B, int h, int w, i
 //     does not match K-block s are all-zero in stage s for the whole kernel -- zeroed once, never written again;
 //   * each of the four stages has its own pair of generator warps (64 threads = the 64 active rows), so four K-blocks are generated
 //     concurrently and a thread touches only its own row of its own stage;
+//   * the band position of a (tile row, K-block) pair is the same for every unit and every dy, so the tiles are zeroed once and a generator
+//     thread only stores the <= D band entries of its row (two-byte stores at their swizzled column) per displacement -- the first form
+//     rebuilt all 64 columns with a compare / select / lookup each: 1750 instructions per row and displacement, 1.78 ms per step; now 0.95 ms;
 //   * two TMEM accumulators (2 x 256 columns): the epilogue of unit i (all eight warps: lane quadrant = warp & 3, column half = warp >> 2)
 //     overlaps the MMAs of unit i + 1.
 // ------------------------------------------------------------------------------------------------
@@ -2644,15 +2647,14 @@ struct CorrBwd16Params {
     float inv_c;
 };
 constexpr int CB16_STAGE = TC_A_BYTES + 4 * 8192;      // 16 KB generated A + 32 KB TMA B (4 channel regions x 64 pixels x 128 B)
-constexpr int CB16_GP = 33;                            // pitch of a thread's private g row (floats): D <= 33
+constexpr int CB16_GP = 33;                            // most displacements per axis (band entries a generator thread keeps in registers)
 
+template <int DMAX>                                    // compile-time bound of the displacements per axis (P.D <= DMAX)
 __global__ void __launch_bounds__(TCG_THREADS, 1)
 tc_corr_bwd16_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_constant__ CorrBwd16Params P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float *g_stage = reinterpret_cast<float *>(smem + 4 * CB16_STAGE);                     // [8 warps][32 lanes][33]
-    uint64_t *full_bar = reinterpret_cast<uint64_t *>(g_stage + 8 * 32 * CB16_GP);
-    full_bar = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(full_bar) + 7) & ~uintptr_t(7));
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + 4 * CB16_STAGE);
     uint64_t *empty_bar = full_bar + 4;
     uint64_t *acc_full = empty_bar + 4;
     uint64_t *acc_empty = acc_full + 2;
@@ -2667,10 +2669,11 @@ tc_corr_bwd16_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_con
     if (warp == TCG_EPI_WARPS && lane == 0) prefetch_tmap(&map_f);
     if (warp == TCG_EPI_WARPS + 1) tmem_alloc(tmem_slot, 512);
     if (warp < TCG_EPI_WARPS) {
-        // the rows of stage s that belong to the OTHER image row stay zero for the whole kernel: 64 rows x 128 B per stage
-        for (int i = threadIdx.x; i < 4 * 64 * 8; i += TCG_EPI_WARPS * 32) {
-            const int s = i / 512, rr = (i / 8) % 64, ch = i % 8;
-            const int row = (1 - (s >> 1)) * 64 + rr;
+        // every A tile starts all-zero.  The rows of stage s that belong to the OTHER image row stay zero for the whole kernel, and so does
+        // every column of an active row outside its band: the band position of (tile row, K-block) does not depend on the unit or on dy, so
+        // the generators only ever (re)write the <= D band entries of their row
+        for (int i = threadIdx.x; i < 4 * 128 * 8; i += TCG_EPI_WARPS * 32) {
+            const int s = i / 1024, row = (i / 8) % 128, ch = i % 8;
             *reinterpret_cast<uint4 *>(smem + s * CB16_STAGE + row * 128 + ch * 16) = make_uint4(0u, 0u, 0u, 0u);
         }
         fence_proxy_async();
@@ -2730,9 +2733,7 @@ tc_corr_bwd16_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_con
         // ===== generators: warp pair p = warp >> 1 owns stage / K-block p; its 64 threads are the 64 tile rows of image row p >> 1 =====
         const int kb = warp >> 1, ry = kb >> 1, xl = (warp & 1) * 32 + lane;
         const int r = ry * 64 + xl;                                  // tile row this thread writes
-        float *my_g = g_stage + (warp * 32 + lane) * CB16_GP;
         uint8_t *arow = smem + kb * CB16_STAGE + r * 128;
-        const int s2_mask = P.s2 - 1, s2_shift = P.s2 == 1 ? 0 : (P.s2 == 2 ? 1 : 2);
         const int xk0 = (kb & 1) * 64;
         const int t0 = P.transpose ? (xl + 32 - xk0 + P.md) : (xk0 - xl - 32 + P.md);
         const int tstep = P.transpose ? -1 : 1;
@@ -2750,29 +2751,25 @@ tc_corr_bwd16_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_con
                 const int gy = P.transpose ? py - dy : py;
                 const bool grow_ok = pix_ok && gy >= 0 && gy < P.h;
                 const float *grow = P.g + ((long long)b * P.h + (grow_ok ? gy : 0)) * P.w * P.g_ld + dyi * P.D;
-                for (int j = 0; j < P.D; ++j) {
+                // the D band values of this row: entry j sits at column c_j = (j * s2 - t0) * tstep of this K-block's 64 pixels.  Loads first
+                // (independent), then the slot, then <= D two-byte stores -- ncu showed the previous form (all 64 columns rebuilt with a
+                // compare / select / shared-memory lookup each) at 1750 instructions per (row, dy) and the kernel bound by them.
+                float gv[DMAX];
+#pragma unroll
+                for (int j = 0; j < DMAX; ++j) {
                     float v = 0.f;
-                    if (grow_ok) {
+                    if (j < P.D && grow_ok) {
                         const int gx = P.transpose ? px - (-P.md + j * P.s2) : px;
                         if (gx >= 0 && gx < P.w) v = __ldg(grow + (long long)gx * P.g_ld + j);
                     }
-                    my_g[j] = v;
+                    gv[j] = v;
                 }
                 mbar_wait(&empty_bar[kb], (uint32_t)((n & 1) ^ 1));
 #pragma unroll
-                for (int cidx = 0; cidx < 8; ++cidx) {
-                    float v[8];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const int t = t0 + tstep * (cidx * 8 + e);
-                        v[e] = (grow_ok && t >= 0 && t <= 2 * P.md && (t & s2_mask) == 0) ? my_g[t >> s2_shift] : 0.f;
-                    }
-                    uint4 pk;
-                    __nv_bfloat162 q0 = __floats2bfloat162_rn(v[0], v[1]), q1 = __floats2bfloat162_rn(v[2], v[3]);
-                    __nv_bfloat162 q2 = __floats2bfloat162_rn(v[4], v[5]), q3 = __floats2bfloat162_rn(v[6], v[7]);
-                    pk.x = *reinterpret_cast<uint32_t *>(&q0); pk.y = *reinterpret_cast<uint32_t *>(&q1);
-                    pk.z = *reinterpret_cast<uint32_t *>(&q2); pk.w = *reinterpret_cast<uint32_t *>(&q3);
-                    *reinterpret_cast<uint4 *>(arow + ((cidx ^ (r & 7)) << 4)) = pk;
+                for (int j = 0; j < DMAX; ++j) {
+                    const int c = (j * P.s2 - t0) * tstep;          // t = t0 + tstep * c = j * s2
+                    if (j < P.D && c >= 0 && c < 64)
+                        *reinterpret_cast<__nv_bfloat16 *>(arow + (((c >> 3) ^ (r & 7)) << 4) + ((c & 7) << 1)) = __float2bfloat16_rn(gv[j]);
                 }
                 fence_proxy_async();                    // generic-proxy writes -> visible to the tensor core (async proxy)
                 __syncwarp();
@@ -2815,11 +2812,12 @@ int tc_corr_bwd16(const void *f1_16, const void *f2_16, int ld, int B, int h, in
                    "dofb_corr_bwd_bf16: needs c = 256 channels, bf16 pitches multiples of 64, 16-byte aligned pointers");
     DOFB_CHECK_ARG(md >= 0 && md <= 32 && (s2 == 1 || s2 == 2 || s2 == 4) && md % s2 == 0 && 2 * (md / s2) + 1 <= CB16_GP,
                    "dofb_corr_bwd_bf16: max displacement <= 32, stride2 in {1,2,4} dividing it, at most %d displacements per axis", CB16_GP);
-    constexpr int smem = 4 * CB16_STAGE + 8 * 32 * CB16_GP * 4 + 1024 + 256;
+    constexpr int smem = 4 * CB16_STAGE + 1024 + 256;
     static_assert(smem <= 227 * 1024, "shared-memory budget");
     static bool configured = false;
     if (!configured) {
-        DOFB_CUDA_OK(cudaFuncSetAttribute(tc_corr_bwd16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        DOFB_CUDA_OK(cudaFuncSetAttribute(tc_corr_bwd16_kernel<21>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        DOFB_CUDA_OK(cudaFuncSetAttribute(tc_corr_bwd16_kernel<CB16_GP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
     for (int pass = 0; pass < 2; ++pass) {
@@ -2834,7 +2832,8 @@ int tc_corr_bwd16(const void *f1_16, const void *f2_16, int ld, int B, int h, in
         const uint32_t box[4] = {64, 64, 1, 1};
         if (make_map(&mf, F, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16)) return 1;
         const int grid = P.units < num_sms() ? P.units : num_sms();
-        tc_corr_bwd16_kernel<<<grid, TCG_THREADS, smem, st>>>(mf, P);
+        if (P.D <= 21) tc_corr_bwd16_kernel<21><<<grid, TCG_THREADS, smem, st>>>(mf, P);       // (FlowNetC: 21 displacements per axis)
+        else tc_corr_bwd16_kernel<CB16_GP><<<grid, TCG_THREADS, smem, st>>>(mf, P);
         DOFB_LAUNCH_OK();
     }
     return 0;
