@@ -109,6 +109,7 @@ SIGNATURES = {
     "dofb_epe_sum": (_I, [_P, _P, _LL, _P, _P]),
     "dofb_corr_fwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _P]),
     "dofb_corr_bwd": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _I, _I, _P]),
+    "dofb_corr_fwd_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P]),
     "dofb_corr_bwd_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _I, _P, _P, _I, _P]),
 }
 

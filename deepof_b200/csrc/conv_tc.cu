@@ -2250,6 +2250,7 @@ int tc_conv1_wgrad(const dofb_conv_geom *g, const float *x, int xp_h, int xp_w, 
 // ------------------------------------------------------------------------------------------------
 struct CorrParams {
     float *out; int out_ld;
+    __nv_bfloat16 *out16;    // optional bf16 shadow of the output (same pitch in elements)
     int B, h, w, c, md, s2, D;
     int ncb;                 // 32-channel blocks
     int ypairs, xtiles, units;
@@ -2262,6 +2263,7 @@ constexpr int CORR_BN = 256;
 constexpr int CORR_STAGE_BYTES = TC_A_BYTES + CORR_BN * TC_BK * 4;     // 48 KB
 constexpr int CORR_STG_LD = 97;                                         // staging row pitch (floats)
 
+template <bool BF>       // BF: bf16 maps (the shadows conv3 writes), 64 channels per 128-byte K block, kind::f16; else fp32 maps as TF32
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_corr_fwd_kernel(const __grid_constant__ CUtensorMap map_f1, const __grid_constant__ CUtensorMap map_f2,
                    const __grid_constant__ CorrParams P) {
@@ -2302,14 +2304,14 @@ tc_corr_fwd_kernel(const __grid_constant__ CUtensorMap map_f1, const __grid_cons
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t *sa = smem + s * CORR_STAGE_BYTES;
                     mbar_expect_tx(&full_bar[s], CORR_STAGE_BYTES);
-                    tma_load_4d(sa, &map_f1, &full_bar[s], k * TC_BK, x0, y0, b);
-                    tma_load_4d(sa + TC_A_BYTES, &map_f2, &full_bar[s], k * TC_BK, x0 - 32, y0 + dy, b);
+                    tma_load_4d(sa, &map_f1, &full_bar[s], k * (BF ? 64 : TC_BK), x0, y0, b);
+                    tma_load_4d(sa + TC_A_BYTES, &map_f2, &full_bar[s], k * (BF ? 64 : TC_BK), x0 - 32, y0 + dy, b);
                 }
             }
         }
     } else if (warp == 5) {
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_tf32(TC_BM, CORR_BN);
+            constexpr uint32_t idesc = BF ? make_idesc_bf16(TC_BM, CORR_BN) : make_idesc_tf32(TC_BM, CORR_BN);
             int it = 0, lt = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++lt) {
                 const int acc = lt & 1;
@@ -2325,7 +2327,7 @@ tc_corr_fwd_kernel(const __grid_constant__ CUtensorMap map_f1, const __grid_cons
                     const uint64_t da = make_desc_k128(sa), db = make_desc_k128(sa + TC_A_BYTES);
 #pragma unroll
                     for (int kk = 0; kk < TC_BK / 8; ++kk)
-                        umma_tf32(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (k | kk) != 0);
+                        umma<BF>(d_tmem, da + (uint64_t)(kk * 2), db + (uint64_t)(kk * 2), idesc, (k | kk) != 0);
                     umma_commit(&empty_bar[s]);
                 }
                 umma_commit(&acc_full[acc]);
@@ -2368,11 +2370,13 @@ tc_corr_fwd_kernel(const __grid_constant__ CUtensorMap map_f1, const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[acc]);     // accumulator drained into shared memory: MMA may overwrite it
             if (x < P.w && y < P.h) {
-                float *dst = P.out + (((long long)b * P.h + y) * P.w + x) * P.out_ld + dyi * P.D;
+                const long long off = (((long long)b * P.h + y) * P.w + x) * P.out_ld + dyi * P.D;
+                float *dst = P.out + off;
                 for (int jj = 0; jj < P.D; ++jj) {
                     float val = my_stage[lane + jj * P.s2] * P.inv_c;       // column (xl + 32 + dx) - (xw0 + 32 - md) = lane + jj*s2
                     if (P.act == DOFB_ACT_ELU) val = elu_f(val);
                     dst[jj] = val;
+                    if (P.out16 != nullptr) P.out16[off + jj] = __float2bfloat16_rn(val);      // bf16 shadow for the tensor-core consumer (same pitch)
                 }
             }
             __syncwarp();
@@ -2387,29 +2391,36 @@ tc_corr_fwd_kernel(const __grid_constant__ CUtensorMap map_f1, const __grid_cons
 }
 
 int tc_corr_fwd(const float *f1, const float *f2, int ld, int B, int h, int w, int c, int md, int s2, float *out, int out_ld, int act,
-                cudaStream_t st) {
-    DOFB_CHECK_ARG(c % 32 == 0 && ld % 32 == 0 && aligned16(f1) && aligned16(f2), "dofb_corr_fwd(tf32): c and pitch must be multiples of 32");
+                cudaStream_t st, const void *f1_16, const void *f2_16, void *out16) {
+    const bool bf = f1_16 != nullptr && f2_16 != nullptr;
+    const int kel = bf ? 64 : 32, esz = bf ? 2 : 4;
+    const void *a1 = bf ? f1_16 : (const void *)f1, *a2 = bf ? f2_16 : (const void *)f2;
+    DOFB_CHECK_ARG(c % kel == 0 && ld % kel == 0 && aligned16(a1) && aligned16(a2), "dofb_corr_fwd(tensor): c and pitch must be multiples of %d", kel);
     DOFB_CHECK_ARG(md >= 0 && md <= 32 && s2 >= 1 && md % s2 == 0 && md % 4 == 0,
-                   "dofb_corr_fwd(tf32): max displacement must be <= 32, a multiple of 4 and of stride2");
+                   "dofb_corr_fwd(tensor): max displacement must be <= 32, a multiple of 4 and of stride2");
     CorrParams P;
-    P.out = out; P.out_ld = out_ld; P.B = B; P.h = h; P.w = w; P.c = c; P.md = md; P.s2 = s2; P.D = 2 * (md / s2) + 1;
-    P.ncb = c / 32; P.ypairs = (h + 1) / 2; P.xtiles = (w + 63) / 64; P.units = B * P.ypairs * P.xtiles;
+    P.out = out; P.out_ld = out_ld; P.out16 = reinterpret_cast<__nv_bfloat16 *>(out16);
+    P.B = B; P.h = h; P.w = w; P.c = c; P.md = md; P.s2 = s2; P.D = 2 * (md / s2) + 1;
+    P.ncb = c / kel; P.ypairs = (h + 1) / 2; P.xtiles = (w + 63) / 64; P.units = B * P.ypairs * P.xtiles;
     P.act = act; P.inv_c = 1.0f / (float)c;
     CUtensorMap m1, m2;
     const uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)B};
-    const uint64_t str[3] = {(uint64_t)ld * 4, (uint64_t)w * ld * 4, (uint64_t)h * w * ld * 4};
-    const uint32_t box1[4] = {32, 64, 2, 1}, box2[4] = {32, 128, 2, 1};
-    if (make_map(&m1, f1, 4, dims, str, box1)) return 1;
-    if (make_map(&m2, f2, 4, dims, str, box2)) return 1;
+    const uint64_t str[3] = {(uint64_t)ld * esz, (uint64_t)w * ld * esz, (uint64_t)h * w * ld * esz};
+    const uint32_t box1[4] = {(uint32_t)kel, 64, 2, 1}, box2[4] = {(uint32_t)kel, 128, 2, 1};
+    const CUtensorMapDataType dt = bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    if (make_map(&m1, a1, 4, dims, str, box1, CU_TENSOR_MAP_SWIZZLE_128B, dt)) return 1;
+    if (make_map(&m2, a2, 4, dims, str, box2, CU_TENSOR_MAP_SWIZZLE_128B, dt)) return 1;
     constexpr int smem = CORR_STAGES * CORR_STAGE_BYTES + 4 * 32 * CORR_STG_LD * 4 + 1024 + 256;
     static bool configured = false;
     if (!configured) {
-        DOFB_CUDA_OK(cudaFuncSetAttribute(tc_corr_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        DOFB_CUDA_OK(cudaFuncSetAttribute(tc_corr_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        DOFB_CUDA_OK(cudaFuncSetAttribute(tc_corr_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
     const long long total = (long long)P.units * P.D;
     const int grid = (int)(total < num_sms() ? total : num_sms());
-    tc_corr_fwd_kernel<<<grid, TC_THREADS, smem, st>>>(m1, m2, P);
+    if (bf) tc_corr_fwd_kernel<true><<<grid, TC_THREADS, smem, st>>>(m1, m2, P);
+    else tc_corr_fwd_kernel<false><<<grid, TC_THREADS, smem, st>>>(m1, m2, P);
     DOFB_LAUNCH_OK();
     return 0;
 }

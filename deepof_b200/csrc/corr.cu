@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) corr_bwd_kernel(const float *__restrict__
 
 namespace dofb {
 int tc_corr_fwd(const float *f1, const float *f2, int ld, int B, int h, int w, int c, int md, int s2, float *out, int out_ld, int act,
-                cudaStream_t st);
+                cudaStream_t st, const void *f1_16 = nullptr, const void *f2_16 = nullptr, void *out16 = nullptr);
 int tc_corr_bwd(const float *f1, const float *f2, int ld, int B, int h, int w, int c, int md, int s2, const float *dout, int dout_ld,
                 float *df1, float *df2, int dld, cudaStream_t st);
 int tc_corr_bwd16(const void *f1_16, const void *f2_16, int ld, int B, int h, int w, int c, int md, int s2, const float *dout, int dout_ld,
@@ -100,6 +100,15 @@ extern "C" int dofb_corr_bwd_bf16(const void *f1_bf16, const void *f2_bf16, int 
     DOFB_CHECK_ARG(f1_bf16 && f2_bf16 && dout && df1 && df2 && B > 0 && h > 0 && w > 0, "dofb_corr_bwd_bf16: bad argument");
     DOFB_CHECK_ARG(dout_ld >= (2 * (max_disp / stride2) + 1) * (2 * (max_disp / stride2) + 1), "dofb_corr_bwd_bf16: dout pitch too small");
     return tc_corr_bwd16(f1_bf16, f2_bf16, ld, B, h, w, c, max_disp, stride2, dout, dout_ld, df1, df2, dld, as_stream(stream));
+}
+
+// bf16 maps (the shadows the conv3 epilogues write) on the tensor pipe (kind::f16, fp32 accumulate): half the L2->SM operand traffic of the
+// TF32 form; out (fp32, needed by the ELU' of the backward) and, optionally, its bf16 shadow out16 (same pitch) for the next convolution
+extern "C" int dofb_corr_fwd_bf16(const void *f1_bf16, const void *f2_bf16, int ld, int B, int h, int w, int c, int max_disp, int stride2,
+                                  float *out, void *out_bf16, int out_ld, int act, void *stream) {
+    DOFB_CHECK_ARG(f1_bf16 && f2_bf16 && out && B > 0 && h > 0 && w > 0 && c > 0 && stride2 > 0 && max_disp >= 0, "dofb_corr_fwd_bf16: bad argument");
+    DOFB_CHECK_ARG(out_ld >= (2 * (max_disp / stride2) + 1) * (2 * (max_disp / stride2) + 1), "dofb_corr_fwd_bf16: out pitch too small");
+    return tc_corr_fwd(nullptr, nullptr, ld, B, h, w, c, max_disp, stride2, out, out_ld, act, as_stream(stream), f1_bf16, f2_bf16, out_bf16);
 }
 
 extern "C" int dofb_corr_fwd(const float *f1, const float *f2, int ld, int B, int h, int w, int c, int max_disp, int stride2,

@@ -465,10 +465,16 @@ class FlowNetS:
             if mth == MATH_BF16:
                 self._k("cast:" + L["name"], ops.cast_bf16, L["y"])
         elif L["op"] == "corr":
-            self._k("corr_fwd", ops.corr_fwd, L["f1"], L["f2"], L["y"], L["max_disp"], L["stride2"], ACT_ELU,
-                    MATH_TF32 if mth == MATH_BF16 else mth)          # the correlation band-GEMMs read the fp32 maps (TF32)
-            if mth == MATH_BF16:
-                self._k("cast:corr", ops.cast_bf16, L["y"])
+            if mth == MATH_BF16 and L["f1"].t16 is not None and L["y"].t16 is not None and os.environ.get("DOFB_CORR_FWD16", "0") == "1":
+                # opt-in: bf16 shadows of conv3a / conv3b on the tensor pipe with the bf16 shadow of the volume written by the same epilogue.
+                # Measured SLOWER than TF32 maps + cast pass (0.69 vs 0.41 + 0.11 ms at B = 32): the kernel is bound by its band-extraction
+                # epilogue (21 scattered stores per pixel and displacement row), which the extra two-byte stores make worse
+                self._k("corr_fwd", ops.corr_fwd, L["f1"], L["f2"], L["y"], L["max_disp"], L["stride2"], ACT_ELU, MATH_BF16)
+            else:
+                self._k("corr_fwd", ops.corr_fwd, L["f1"], L["f2"], L["y"], L["max_disp"], L["stride2"], ACT_ELU,
+                        MATH_TF32 if mth == MATH_BF16 else mth)          # the correlation band-GEMMs read the fp32 maps (TF32)
+                if mth == MATH_BF16:
+                    self._k("cast:corr", ops.cast_bf16, L["y"])
 
     def _bwd_layer(self, L):
         P, G, mth, mthw = self.params, self.grads, self.math, self.math_wgrad

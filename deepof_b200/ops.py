@@ -376,6 +376,10 @@ def epe_sum(flow, gt, out):
 
 def corr_fwd(f1: Slab, f2: Slab, out: Slab, max_disp=20, stride2=2, act=ACT_NONE, math=MATH_FP32):
     assert f1.ld == f2.ld and f1.c == f2.c
+    if math == MATH_BF16:       # bf16 shadows of the maps; fp32 output + (when the slab has one) its bf16 shadow in the same pass
+        check(_lib.load().dofb_corr_fwd_bf16(_need16(f1, "corr_fwd"), _need16(f2, "corr_fwd"), f1.ld, f1.B, f1.h, f1.w, f1.c, max_disp, stride2,
+                                             out.ptr, out.ptr16, out.ld, act, _stream()))
+        return
     check(_lib.load().dofb_corr_fwd(f1.ptr, f2.ptr, f1.ld, f1.B, f1.h, f1.w, f1.c, max_disp, stride2, out.ptr, out.ld, act, math,
                                     _stream()))
 

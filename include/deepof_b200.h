@@ -301,6 +301,10 @@ int dofb_epe_sum(const float *flow, const float *gt, long long n_pix, double *ou
  * math = DOFB_MATH_TF32: the per-displacement channel dot products run as tcgen05 band-GEMMs (c, pitch % 32 == 0, max_disp <= 32). */
 int dofb_corr_fwd(const float *f1, const float *f2, int ld, int B, int h, int w, int c, int max_disp, int stride2,
                   float *out, int out_ld, int act, int math, void *stream);
+/* The same cost volume from the bf16 shadows of the two feature maps (tcgen05 kind::f16, fp32 accumulate): half the operand traffic of the
+ * TF32 form.  Writes `out` (fp32) and, when out_bf16 is not NULL, its bf16 shadow at the same pitch (no separate cast pass). */
+int dofb_corr_fwd_bf16(const void *f1_bf16, const void *f2_bf16, int ld, int B, int h, int w, int c, int max_disp, int stride2,
+                       float *out, void *out_bf16, int out_ld, int act, void *stream);
 int dofb_corr_bwd(const float *f1, const float *f2, int ld, int B, int h, int w, int c, int max_disp, int stride2,
                   const float *dout, int dout_ld, float *df1, float *df2, int dld, int math, void *stream);
 

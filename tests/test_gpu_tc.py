@@ -766,3 +766,25 @@ def test_conv1_four_pixels_per_row_matches_one_pixel_form(B, H, W, ci, co):
         lib.dofb_enable_phase_in_n(1)
     assert rel(outs[1], outs[0]) < 1e-5
     assert float(outs[0].abs().max()) > 0.1
+
+
+@pytest.mark.parametrize("B,h,w,md,s2", [(2, 12, 64, 20, 2), (1, 7, 40, 20, 2), (2, 6, 128, 20, 2), (1, 5, 64, 16, 4), (1, 48, 64, 20, 2)])
+def test_bf16_correlation_forward_matches_oracle(B, h, w, md, s2):
+    """tc_corr_fwd_kernel<true> (bf16 maps, kind::f16) against the CPU restatement of the cost volume evaluated on the same bf16-rounded
+    maps (fp32 accumulation of exact bf16 products -> tight bound), with the fused bf16 shadow of the output."""
+    from deepof_b200 import ops
+    from oracle import flownet_c, tf_ops
+    g = torch.Generator().manual_seed(B * h + w + 11)
+    c = 256
+    f1 = _buf(B, h, w, c, c, g).to(torch.bfloat16)
+    f2 = _buf(B, h, w, c, c, g).to(torch.bfloat16)
+    D = 2 * (md // s2) + 1
+    ld = D * D + 7
+    o = torch.full((B, h, w, ld), 5.0, device="cuda")
+    o16 = torch.full((B, h, w, ld), 5.0, device="cuda").to(torch.bfloat16)
+    ops.corr_fwd(ops.Slab(None, 0, c, f1), ops.Slab(None, 0, c, f2), ops.Slab(o, 0, D * D, o16), md, s2, ops.ACT_ELU, ops.MATH_BF16)
+    torch.cuda.synchronize()
+    want = tf_ops.elu(flownet_c.correlation(f1.float().cpu().double(), f2.float().cpu().double(), md, s2))
+    assert rel(o[..., :D * D], want) < 2e-5
+    assert float((o[..., D * D:] - 5.0).abs().max()) == 0.0 and float((o16[..., D * D:].float() - 5.0).abs().max()) == 0.0
+    assert torch.equal(o16[..., :D * D], o[..., :D * D].to(torch.bfloat16))
