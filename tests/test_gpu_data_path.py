@@ -132,3 +132,41 @@ def test_uint8_feeds_equal_their_float32_casts(math_mode, monkeypatch):
     ops.preprocess(s8.float(), t8.float(), (100.0, 110.0, 120.0), xb, pb[:1], pb[1:])
     torch.cuda.synchronize()
     assert torch.equal(xa, xb) and torch.equal(pa[0], pb[0]) and torch.equal(pa[1], pb[1])
+
+
+def _ref_host():
+    from pathlib import Path
+    return np.load(Path(__file__).resolve().parent / "golden" / "reference_host.npz")
+
+
+def test_device_loader_equals_reference_hook_train_data(tmp_path):
+    """flyingChairsLoader on the device (file bytes -> dofb_decode_ppm incl. the cv2.resize restatement, dofb_decode_flo) against what the
+    REFERENCE's hookTrainData (flyingChairsLoader.py:64-82, executed by tests/golden/make_reference_host_golden.py) returned for the same files."""
+    from deepof_b200.flyingChairsLoader import flyingChairsLoader
+    z = _ref_host()
+    ids = [str(i) for i in z["ids"]]
+    data = tmp_path / "data"
+    data.mkdir()
+    for fid in ids:
+        for k in (1, 2):
+            (data / f"{fid}_img{k}.ppm").write_bytes(z[f"ppm_{fid}_{k}"].tobytes())
+        (data / f"{fid}_flow.flo").write_bytes(z[f"flo_{fid}"].tobytes())
+    (tmp_path / "FlyingChairs_train_val.txt").write_text("1\n" * len(ids))
+    ld = flyingChairsLoader(str(tmp_path), [32, 48], split_file=str(tmp_path / "FlyingChairs_train_val.txt"))
+    src, tgt, flow = ld.sampleTrain(len(ids), 1)
+    torch.cuda.synchronize()
+    assert torch.equal(src.cpu(), torch.from_numpy(z["loader_source"].astype(np.float32)))      # bit-exact cv2.resize (shrinking), BGR order
+    assert torch.equal(tgt.cpu(), torch.from_numpy(z["loader_target"].astype(np.float32)))
+    assert torch.equal(flow.cpu(), torch.from_numpy(z["loader_flow"]))
+
+
+def test_device_eval_recipe_and_epe_equal_reference_lines():
+    """dofb_eval_flow_aee_sum (x2, clip, cv2.resize, AEE in one pass) and dofb_epe_sum against the numbers the reference's own lines
+    (flyingChairsTrain.py:263-267,294-296; utils.py:64-68) produced."""
+    from deepof_b200.flyingChairsLoader import evaluate_aee
+    from deepof_b200 import utils as U
+    z = _ref_host()
+    got = evaluate_aee(torch.from_numpy(z["eval_pr1"]).cuda(), torch.from_numpy(z["eval_gt"]).cuda())
+    assert abs(got - float(z["eval_aee"])) < 2e-5 * max(1.0, float(z["eval_aee"]))
+    ee = U.flow_ee(torch.from_numpy(z["ee_f1"]).cuda(), torch.from_numpy(z["ee_f2"]).cuda())
+    assert abs(ee - float(z["ee_aee"])) < 1e-5 * float(z["ee_aee"])
